@@ -1,0 +1,211 @@
+/*
+ * sindyn.h -- C ABI of libsindyn_cuda: B200 (sm_100a) kernels for SInDSLAM's per-frame
+ * dynamic-region detection path (DynaDetect + masked ORBextractor).
+ *
+ * Boundary rules: extern "C", plain pointers and sizes, int return codes (0 = SINDYN_OK), no
+ * exceptions, no OpenCV / torch types.  The caller owns all HOST memory; the library owns all
+ * DEVICE memory.  One handle = one sequence = one CUDA device + stream; handles are independent
+ * (multi-sequence / multi-GPU = several handles, no collectives).
+ *
+ * Every entry point cites the reference interface (file:line under qimao7213/SInDSLAM) it
+ * replaces.  Image arguments are row-major with an explicit row step in BYTES (cv::Mat::step).
+ */
+#ifndef SINDYN_H
+#define SINDYN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sindyn_ctx *sindyn_handle;
+
+enum sindyn_status {
+    SINDYN_OK = 0,
+    SINDYN_ERR_INVALID = 1,   /* bad argument / size mismatch */
+    SINDYN_ERR_CUDA = 2,      /* CUDA runtime error (see sindyn_last_error) */
+    SINDYN_ERR_NO_DEVICE = 3, /* no CUDA device: there is NO CPU fallback */
+    SINDYN_ERR_STATE = 4,     /* call order violated (e.g. detect before set_prev_frames) */
+    SINDYN_ERR_CAPACITY = 5   /* fixed-capacity device list overflowed */
+};
+
+/* Constructor arguments of ORB_SLAM2::DynaDetect (include/DynaDetect.h:98-105) plus the
+ * constants hard-coded in src/DynaDetect.cc:43-59,1029,1033 made run-time parameters.
+ * sindyn_default_config fills the reference's values. */
+typedef struct sindyn_config {
+    int width, height;            /* DynaDetect.cc:43-44 (640x480 hard-coded there) */
+    float fx, fy, cx, cy;         /* DynaDetect.h:100-103 */
+    float depth_scale;            /* DynaDetect.h:104 (DepthMapFactor, raw units per metre) */
+    float flow_scale;             /* DynaDetect.cc:1033  scale_element = 0.6 */
+    float brox_alpha, brox_gamma, brox_pyr_scale;             /* DynaDetect.cc:1029 */
+    int brox_inner, brox_outer, brox_solver;                  /* DynaDetect.cc:1029 */
+    float brox_omega;             /* SOR relaxation (internal to the un-vendored NCV solver) */
+    int refine;                   /* 1 = run the VariationalRefinement-equivalent pass (DynaDetect.cc:1133-1143) */
+    int n_row_cluster, n_col_cluster; /* DynaDetect.cc:46  (3 x 4 = 12 clusters) */
+    float depth_weight;           /* DynaDetect.cc:48 */
+    int device;                   /* CUDA device ordinal */
+    int use_graphs;               /* 1 = replay captured CUDA graphs for the launch-bound stages */
+    int plane_edges;              /* 1 = run the PEAC plane-edge stage (DynaDetect.cc:592-593) */
+} sindyn_config;
+
+void sindyn_default_config(sindyn_config *cfg, int width, int height);
+
+/* ------------------------------------------------------------------ life cycle */
+/* Replaces: DynaDetect::DynaDetect(imgLast, imgLastLast, fx, fy, cx, cy, depthScale)
+ * (include/DynaDetect.h:98-126) -- construction + intrinsics. */
+int sindyn_create(const sindyn_config *cfg, sindyn_handle *out);
+int sindyn_destroy(sindyn_handle h);
+const char *sindyn_last_error(sindyn_handle h);
+/* Use an external CUDA stream (cudaStream_t) for all work of this handle, e.g. torch's current
+ * stream so that torch.cuda.Event timing brackets the kernels.  NULL restores the own stream. */
+int sindyn_set_stream(sindyn_handle h, void *cuda_stream);
+int sindyn_synchronize(sindyn_handle h);
+/* number of kernel launches issued by this handle since creation (graph nodes count individually) */
+unsigned long long sindyn_launch_count(sindyn_handle h);
+
+/* The two BGR frames the constructor receives (DynaDetect.h:98-105; driver: rgbd_tum_noros.cc:103-107).
+ * Also zeroes the inter-frame state (imgDynaLast, imgMaskHighErrorLast, imgLabelLast; DynaDetect.h:109-112). */
+int sindyn_set_prev_frames(sindyn_handle h, const uint8_t *bgr_last, size_t step_last,
+                           const uint8_t *bgr_lastlast, size_t step_lastlast);
+
+/* Replaces: DynaDetect::DetectDynaArea(img, imgDepth, imgDyna, imgLabel, nImg)
+ * (include/DynaDetect.h:127-131, src/DynaDetect.cc:1377-1666).
+ * bgr: 8UC3, depth: 16UC1 raw; mask_out: 8UC1 {0,125,255}; label_out: 8UC1 merged cluster ids.
+ * Host pointers; H2D/D2H copies and the final synchronize happen inside. */
+int sindyn_detect(sindyn_handle h, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step,
+                  uint8_t *mask_out, size_t mask_step, uint8_t *label_out, size_t label_step, int frame_idx);
+
+/* Device-resident variant used for kernel-only timing: frames are staged once into `slot`
+ * (0 <= slot < SINDYN_MAX_SLOTS) and detect runs without host traffic; results stay on the
+ * device until sindyn_get_buffer. */
+#define SINDYN_MAX_SLOTS 8
+int sindyn_upload_frame(sindyn_handle h, int slot, const uint8_t *bgr, size_t bgr_step,
+                        const uint16_t *depth, size_t depth_step);
+int sindyn_detect_resident(sindyn_handle h, int slot, int frame_idx);
+
+/* Driver post-step: 15x15 ellipse dilation of the mask (rgbd_tum_noros.cc:108,136-139), and the
+ * generic getStructuringElement(MORPH_ELLIPSE,k x k) morphology used throughout DynaDetect.cc:51-59.
+ * op: 0 = dilate, 1 = erode, 2 = open, 3 = close. k in {1..15}. */
+int sindyn_morph_ellipse(sindyn_handle h, const uint8_t *src, size_t src_step, uint8_t *dst, size_t dst_step,
+                         int width, int height, int k, int op);
+
+/* ------------------------------------------------------------------ stage-level entry points
+ * (the seams of SURVEY.md section 4: identical inputs can be injected at every stage boundary,
+ * like the authors' own .flo injection hook, DynaDetect.cc:1149-1158). */
+
+/* cv::cuda::BroxOpticalFlow::calc(I0 = current, I1 = older, flow) (DynaDetect.cc:1029,1072,1124).
+ * I0/I1: w x h float in [0,1], densely packed; flow_uv: w x h x 2 float (CV_32FC2 layout), the RAW
+ * solver sign (I0(x) ~ I1(x + w)). */
+int sindyn_flow_brox(sindyn_handle h, const float *I0, const float *I1, int w, int hgt, float *flow_uv);
+
+/* Flow-branch prologue (DynaDetect.cc:1390-1392,1033-1048): BGR->gray, resize to
+ * (int)(flow_scale*W) x (int)(flow_scale*H) INTER_LINEAR, u8 out (and /255 float inside). */
+int sindyn_gray_resize(sindyn_handle h, const uint8_t *bgr, size_t bgr_step, uint8_t *gray_full, uint8_t *gray_small);
+
+/* Full flow branch up to the up-sampled flow (DynaDetect.cc:1033-1147): gray/resize of the three
+ * frames, Brox(cur, lastlast), large-motion test, optional Brox(cur, last), negate, refinement,
+ * resize to W x H, scale by 1/flow_scale.  flow_out: W x H x 2 float. large_motion_out may be NULL. */
+int sindyn_flow_branch(sindyn_handle h, const uint8_t *bgr_cur, size_t step_cur, float *flow_out, int *large_motion_out);
+
+/* cv::VariationalRefinement::create()->calc(I0, I1, flow) with default parameters
+ * (DynaDetect.cc:1133-1143): I0/I1 u8 w x h, flow in/out w x h x 2 float. */
+int sindyn_flow_refine(sindyn_handle h, const uint8_t *I0, const uint8_t *I1, int w, int hgt, float *flow_uv);
+
+/* Sample weighting + sort + in-border filter (DynaDetect.cc:1163-1231) followed by the robust
+ * homography that replaces cv::findHomography(pts, ptsLast, noArray(), RHO) (DynaDetect.cc:1235).
+ * flow: W x H x 2 float (already up-sampled).  H_out: 3x3 row-major double.  Uses the handle's
+ * state images (imgDynaLast / imgLabelLast).  n_pairs_out may be NULL. */
+int sindyn_estimate_homography(sindyn_handle h, const float *flow, double *H_out, int *n_pairs_out);
+/* Only the sample list (for parity of DynaDetect.cc:1163-1231): pts / pts_last are n x 2 float. */
+int sindyn_sample_pairs(sindyn_handle h, const float *flow, float *pts, float *pts_last, int capacity, int *n_out);
+
+/* Residual against the homography flow + thresholds -> two masks
+ * (DynaDetect.cc:1236-1367): residual_mag_out (W x H float, may be NULL), mask_low (0/128),
+ * mask_high (0/255); thresholds_out[4] = {otsu, triangle, t_low, t_high} (may be NULL). */
+int sindyn_residual_homography(sindyn_handle h, const float *flow, const double *Hm, float *residual_mag_out,
+                               uint8_t *mask_low, uint8_t *mask_high, float *thresholds_out);
+/* north_star variant: depth back-projection with the SE(3) pose T_old_cur (3x4 row-major, maps
+ * current-camera points into the older camera), reprojection to predicted flow, residual against
+ * the measured flow; same thresholding.  Needs an interface extension upstream (pose in). */
+int sindyn_residual_pose(sindyn_handle h, const float *flow, const uint16_t *depth, size_t depth_step,
+                         const double *T_old_cur, float *residual_mag_out, uint8_t *mask_low, uint8_t *mask_high,
+                         float *thresholds_out);
+
+/* DynaDetect::SegByKmeans (DynaDetect.cc:315-420): 4-level pyramid K-means on (X,Y,1.5 Z).
+ * labels_out: W x H u8; points_out: N x 3 float (may be NULL); centers_out: 12 x 3 float (may be NULL).
+ * Uses the handle's imgLabelLast for initialisation. */
+int sindyn_kmeans(sindyn_handle h, const uint16_t *depth, size_t depth_step, uint8_t *labels_out, float *points_out,
+                  float *centers_out);
+
+/* Cluster ordering (DynaDetect.cc:1425-1491): runs on the last sindyn_kmeans result.
+ * label_for_seg_edge_out: W x H u8 (0/255, dilated 7x7); order_out[12] = cluster ids kept, depth
+ * order, -1 padded; n_kept_out = allLabels.size(). */
+int sindyn_cluster_order(sindyn_handle h, uint8_t *label_for_seg_edge_out, int *order_out, int *n_kept_out);
+
+/* DynaDetect::CalOccluded gradient edges + end points (DynaDetect.cc:434-536).
+ * total_area_out (0/255), grad_edges_out (0/255, after OPEN 4x4); endpoints_out: n x 2 int (x,y)
+ * after NMS, raster order. */
+int sindyn_depth_edges(sindyn_handle h, const uint16_t *depth, size_t depth_step, uint8_t *total_area_out,
+                       uint8_t *grad_edges_out, int *endpoints_out, int capacity, int *n_endpoints_out);
+
+/* PEAC plane-contour edges (DynaDetect.cc:558-593; include/PEAC plane_fitter_pcl.hpp:275-317).
+ * plane_edges_out: W x H u8 (imgEdgeByPlane before filtering). */
+int sindyn_plane_edges(sindyn_handle h, const uint16_t *depth, size_t depth_step, uint8_t *plane_edges_out);
+
+/* Plane-edge filtering + imgOccluded1/2 (DynaDetect.cc:598-641). Inputs: plane edges (raw),
+ * gradient edges, end points. Outputs occluded1 (all edges, CLOSE 3x3) and occluded2 (plane edges kept). */
+int sindyn_filter_plane_edges(sindyn_handle h, const uint8_t *plane_edges, const uint8_t *grad_edges,
+                              const int *endpoints, int n_endpoints, uint8_t *occluded1_out, uint8_t *occluded2_out);
+
+/* DynaDetect::SegAndMergeV2 (DynaDetect.cc:653-1018) on the last k-means / cluster-order result.
+ * occluded1/2 and label_for_seg_edge are injected (host); label_out: W x H u8 merged labels
+ * (0 = invalid, 1..n). */
+int sindyn_recluster(sindyn_handle h, const uint8_t *occluded1, const uint8_t *occluded2, const uint16_t *depth,
+                     size_t depth_step, uint8_t *label_out, int *n_components_out);
+
+/* Mask fusion + per-cluster decision + final mask (DynaDetect.cc:1553-1636) and state roll
+ * (DynaDetect.cc:1660-1664).  Inputs injected: low (0/128), high (0/255), total_area, labels. */
+int sindyn_dynamic_decide(sindyn_handle h, const uint8_t *mask_low, const uint8_t *mask_high, const uint8_t *total_area,
+                          const uint8_t *labels, uint8_t *dyna_out);
+
+/* Inter-frame state (DynaDetect.h:164-178): which = 0 imgDynaLast, 1 imgMaskHighErrorLast,
+ * 2 imgLabelLast (u8 W x H); 3 imgRGBLast, 4 imgRGBLastLast (u8 W x H x 3). */
+int sindyn_get_state(sindyn_handle h, int which, uint8_t *out);
+int sindyn_set_state(sindyn_handle h, int which, const uint8_t *in);
+
+/* Per-stage device milliseconds of the last sindyn_detect (CUDA events):
+ * [0] upload+gray/resize [1] brox [2] large-motion+refine+upsample [3] homography [4] residual+masks
+ * [5] kmeans [6] depth edges [7] plane edges [8] recluster [9] decide+final [10] total.  n <= 16. */
+int sindyn_get_stage_ms(sindyn_handle h, float *ms, int n);
+
+/* ------------------------------------------------------------------ ORB extractor */
+typedef struct sindyn_orb *sindyn_orb_handle;
+typedef struct sindyn_keypoint { /* fields of cv::KeyPoint used by ORB-SLAM2 */
+    float x, y, size, angle, response;
+    int octave;
+} sindyn_keypoint;
+
+/* Replaces ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (include/ORBextractor.h:54-55, src/ORBextractor.cc:410-470). */
+int sindyn_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast,
+                      int width, int height, int device, sindyn_orb_handle *out);
+int sindyn_orb_destroy(sindyn_orb_handle h);
+/* Replaces ORBextractor::operator()(image, mask, keypoints, descriptors)
+ * (include/ORBextractor.h:62-64, src/ORBextractor.cc:1043-1164). mask may be NULL (== empty Mat).
+ * kps: capacity entries; desc: capacity x 32 bytes. *n_out = number of keypoints written. */
+int sindyn_orb_extract(sindyn_orb_handle h, const uint8_t *gray, size_t gray_step, const uint8_t *mask, size_t mask_step,
+                       sindyn_keypoint *kps, uint8_t *desc, int capacity, int *n_out);
+/* mvImagePyramid[level] (include/ORBextractor.h:88): copies level image (without the 19-px pad). */
+int sindyn_orb_get_pyramid_level(sindyn_orb_handle h, int level, uint8_t *out, int *w_out, int *h_out);
+int sindyn_orb_set_stream(sindyn_orb_handle h, void *cuda_stream);
+unsigned long long sindyn_orb_launch_count(sindyn_orb_handle h);
+const char *sindyn_orb_last_error(sindyn_orb_handle h);
+
+const char *sindyn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SINDYN_H */

@@ -1,0 +1,36 @@
+// brox.cuh -- coarse-to-fine Brox variational optical flow (replaces cv::cuda::BroxOpticalFlow,
+// ORB_SLAM2/src/DynaDetect.cc:1029,1072,1124).
+#pragma once
+#include "common.cuh"
+
+#define BROX_MAX_LEVELS 96
+
+struct BroxSolver {
+    int w = 0, h = 0, nl = 0;
+    int ws[BROX_MAX_LEVELS], hs[BROX_MAX_LEVELS];
+    size_t off[BROX_MAX_LEVELS];  // element offset of level k inside pyr0/pyr1 (level 0 is the caller's buffer)
+    float alpha, gamma, scale, omega;
+    int inner, outer, solver;
+    float *pyr0 = nullptr, *pyr1 = nullptr;
+    // per-level scratch, sized for level 0
+    float *A, *Iz, *Ix, *Iy, *Ixz, *Iyz, *Ixx, *Ixy, *Iyy;
+    float *u[2], *v[2], *du[3], *dv[3];
+    bool graph_ok = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    const float *g_I0 = nullptr, *g_I1 = nullptr;
+    float *g_out = nullptr;
+    float g_sign = 0.f;
+    unsigned long long graph_launches = 0;
+};
+
+int brox_num_levels_host(int w, int h, float scale, int outer, int *ws, int *hs);
+int brox_init(sindyn_base *ctx, BroxSolver *b, int w, int h, float alpha, float gamma, float scale, int inner, int outer,
+              int solver, float omega);
+// I0/I1: dense w x h float device images. flow_out: w x h x 2 interleaved, multiplied by `sign`
+// (the reference negates the solver output right away, DynaDetect.cc:1080).
+int brox_run(sindyn_base *ctx, BroxSolver *b, const float *I0, const float *I1, float *flow_out, float sign, bool use_graph);
+void brox_destroy(BroxSolver *b);
+
+// generic pixel-centre aligned bilinear resample of `planes` float planes (cv::resize INTER_LINEAR rule, float path)
+int launch_resample_f32(sindyn_base *ctx, const float *src, int sw, int sh, float *dst, int dw, int dh, float mul);

@@ -1,0 +1,42 @@
+// ctx.cuh -- the DynaDetect handle: configuration, device-resident frames and inter-frame state
+// (ORB_SLAM2/include/DynaDetect.h:164-188), and the per-stage solver objects.
+#pragma once
+#include "brox.cuh"
+#include "common.cuh"
+#include "preproc.cuh"
+#include "residual.cuh"
+
+struct sindyn_ctx : sindyn_base {
+    sindyn_config cfg;
+    int W = 0, H = 0, N = 0;
+    int fw = 0, fh = 0;  // flow grid: (int)(flow_scale*W) x (int)(flow_scale*H)  (DynaDetect.cc:1037)
+    bool have_prev = false;
+
+    // frames: BGR (W*H*3), gray full, gray small (u8 + float/255)
+    uint8_t *bgr[3] = {nullptr, nullptr, nullptr};  // ring: cur / last / lastlast by index rotation
+    uint8_t *gray[3] = {nullptr, nullptr, nullptr};
+    uint8_t *gsmall[3] = {nullptr, nullptr, nullptr};
+    float *gsmall_f[3] = {nullptr, nullptr, nullptr};
+    int i_cur = 0, i_last = 1, i_lastlast = 2;
+    uint16_t *depth = nullptr;
+    // device-resident staging slots for kernel-only timing
+    uint8_t *slot_bgr[SINDYN_MAX_SLOTS] = {};
+    uint16_t *slot_depth[SINDYN_MAX_SLOTS] = {};
+
+    // inter-frame state (DynaDetect.h:172-178)
+    uint8_t *dyna_last = nullptr, *high_last = nullptr, *label_last = nullptr;
+
+    // flow branch
+    ResizePlanU8 plan_flow;
+    BroxSolver brox;
+    float *flow_small = nullptr;  // fw x fh x 2
+    float *flow_full = nullptr;   // W x H x 2
+    // generic scratch for stage-level entry points
+    float *scratch_f0 = nullptr, *scratch_f1 = nullptr;  // N*2 floats each
+    uint8_t *scratch_u0 = nullptr, *scratch_u1 = nullptr, *scratch_u2 = nullptr, *scratch_u3 = nullptr;  // N*3 bytes each
+
+    ResidualStage resid;
+    uint8_t *mask_low = nullptr, *mask_high = nullptr;
+
+    float stage_ms[16] = {};
+};
