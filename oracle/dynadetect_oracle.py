@@ -202,3 +202,219 @@ def threshold_masks(mag):
     low = np.where(m8 > tl, 128, 0).astype(np.uint8)     # imgThhd * 0.5 -> 127.5 -> 128
     high = np.where(m8 > th, 255, 0).astype(np.uint8)
     return low, high, np.array([otsu, tri, tl, th], np.float32), m8
+
+
+# ----------------------------------------------------------------------------- SegByKmeans
+KM_FIX = 36  # fixed-point fraction bits of the order-independent centre accumulation ("oracle-fx")
+
+
+def depth_pyramid(depth, levels=4):
+    """DynaDetect.cc:324-337: successive cv::resize (default INTER_LINEAR) of the u16 image by 0.5."""
+    pyr = [depth]
+    for _ in range(1, levels):
+        p = pyr[-1]
+        pyr.append(cv2.resize(p, (int(p.shape[1] * np.float32(0.5)), int(p.shape[0] * np.float32(0.5)))))
+    return pyr
+
+
+def backproject_level(depth_lvl, s, fx, fy, cx, cy, depth_scale):
+    """DynaDetect.cc:347-369 (float32 arithmetic, ushort truncation of depth*scale)."""
+    f = np.float32
+    s = f(s)
+    h, w = depth_lvl.shape
+    d = (depth_lvl.astype(np.float32) * s).astype(np.uint16)              # ushort depth = pyr * scales[level]
+    df = d.astype(np.float32)
+    invalid = ((df / f(depth_scale)) >= f(6.0)) | (d == 0)
+    depth2 = df * (f(1.0) / f(depth_scale))
+    col, row = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    X = ((col - f(cx) * s) * depth2) * (f(1.0) / (f(fx) * s))
+    Y = ((row - f(cy) * s) * depth2) * (f(1.0) / (f(fy) * s))
+    Z = depth2 * f(DEPTH_WEIGHT)
+    pts = np.stack([X, Y, Z], -1).astype(np.float32)
+    pts[invalid] = 0
+    return pts.reshape(-1, 3)
+
+
+def kmeans_fx(points, K, labels, max_iter=4, eps=0.07):
+    """cv::kmeans(points, K, labels, (EPS+COUNT, 4, 0.07), 1, KMEANS_USE_INITIAL_LABELS, centers)
+    (DynaDetect.cc:397,408; semantics SURVEY Appendix C.1) with ONE documented deviation: the centre sums are
+    accumulated in 2^-36 fixed point (order independent) instead of OpenCV's sequential float32 sum, which no
+    parallel reduction can reproduce.  Returns (labels, centers, counts)."""
+    f = np.float32
+    labels = labels.astype(np.int32).copy()
+    N = points.shape[0]
+    fixed = np.rint(points.astype(np.float64) * float(1 << KM_FIX)).astype(np.int64)
+    centers = np.zeros((K, 3), np.float32)
+    old = np.zeros((K, 3), np.float32)
+    eps2 = eps * eps
+    it = 0
+    counts = None
+    while True:
+        centers, old = old, centers
+        sums = np.zeros((K, 3), np.int64)
+        for j in range(3):
+            sums[:, j] = np.bincount(labels, weights=None, minlength=K) * 0  # placeholder shape
+        counts = np.bincount(labels, minlength=K).astype(np.int64)
+        for j in range(3):
+            # exact int64 sums per label
+            order = np.argsort(labels, kind="stable")
+            cs = np.concatenate([[0], np.cumsum(fixed[order, j])])
+            ends = np.cumsum(counts)
+            starts = ends - counts
+            sums[:, j] = cs[ends] - cs[starts]
+        for k in range(K):
+            if counts[k] != 0:
+                continue
+            max_k = int(np.argmax(counts))  # first maximum, like the reference loop
+            scale = f(1.0) / f(counts[max_k])
+            base = (sums[max_k].astype(np.float64) * 2.0 ** -KM_FIX).astype(np.float32) * scale
+            old[max_k] = base  # the reference overwrites old_centers[max_k] with the normalised centre
+            idx = np.nonzero(labels == max_k)[0]
+            d = points[idx] - base
+            dist = np.zeros(len(idx), np.float32)
+            for j in range(3):
+                dist = (dist + d[:, j] * d[:, j]).astype(np.float32)
+            far = idx[len(idx) - 1 - int(np.argmax(dist[::-1]))]  # max_dist <= dist: the last maximum wins
+            counts[max_k] -= 1
+            counts[k] += 1
+            labels[far] = k
+            sums[max_k] -= fixed[far]
+            sums[k] += fixed[far]
+        shift = 0.0
+        for k in range(K):
+            c = (sums[k].astype(np.float64) * 2.0 ** -KM_FIX).astype(np.float32) * (f(1.0) / f(counts[k]))
+            centers[k] = c
+            if it > 0:
+                t = centers[k].astype(np.float64) - old[k].astype(np.float64)
+                shift = max(shift, float((t * t).sum()))
+        if it == 0:
+            shift = np.inf
+        it += 1
+        if it == max(max_iter, 2) or shift <= eps2:
+            break
+        # assign: argmin_k sum_d (x_d - c_kd)^2 in float32, first minimum wins
+        best = np.full(N, np.inf, np.float32)
+        lab = np.zeros(N, np.int32)
+        for k in range(K):
+            d = points - centers[k]
+            dist = np.zeros(N, np.float32)
+            for j in range(3):
+                dist = (dist + d[:, j] * d[:, j]).astype(np.float32)
+            m = dist < best
+            best[m] = dist[m]
+            lab[m] = k
+        labels = lab
+    return labels, centers.copy(), counts
+
+
+def seg_by_kmeans(depth, label_last, fx, fy, cx, cy, depth_scale, kmeans_impl="fx"):
+    """DynaDetect::SegByKmeans (DynaDetect.cc:315-420). kmeans_impl: 'fx' (order-independent sums, what the
+    CUDA kernel is bit-exact against) or 'cv2' (cv2.kmeans itself, sequential float32 sums)."""
+    H, W = depth.shape
+    scales = [1.0, 0.5, 0.25, 0.125]
+    pyr = depth_pyramid(depth, 4)
+    lab_lvl = [None] * 4
+    points = centers = None
+    for level in (3, 2, 1, 0):
+        s = np.float32(scales[level])
+        hp, wp = int(np.float32(H) * s), int(np.float32(W) * s)
+        pts = backproject_level(pyr[level], scales[level], fx, fy, cx, cy, depth_scale)
+        if level == 3:
+            if np.count_nonzero(label_last) == 0:
+                br, bc = np.float32(hp) / np.float32(3), np.float32(wp) / np.float32(4)
+                ii, jj = np.meshgrid(np.arange(hp, dtype=np.float32), np.arange(wp, dtype=np.float32), indexing="ij")
+                lab = (np.floor(ii / br) * 4 + np.floor(jj / bc)).astype(np.int32)
+            else:
+                lab = np.rint(cv2.resize(label_last.astype(np.float32), (wp, hp))).astype(np.int32)
+        else:
+            lab = np.rint(cv2.resize(lab_lvl[level + 1].astype(np.float32), (wp, hp))).astype(np.int32)
+        lab = lab.reshape(-1)
+        if kmeans_impl == "cv2":
+            crit = (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_COUNT, 4, 0.07)
+            _, l2, c2 = cv2.kmeans(pts, NUM_CLUSTER, lab.reshape(-1, 1).copy(), crit, 1, cv2.KMEANS_USE_INITIAL_LABELS)
+            lab, ctr = l2.reshape(-1), c2
+        else:
+            lab, ctr, _ = kmeans_fx(pts, NUM_CLUSTER, lab)
+        lab_lvl[level] = lab.reshape(hp, wp)
+        if level == 0:
+            points, centers = pts, ctr
+    return lab_lvl[0].astype(np.uint8), points, centers
+
+
+def cluster_order(labels, centers):
+    """DynaDetect.cc:1425-1491. Returns (order of kept cluster ids = allLabels, imgLabelForSegEdge dilated 7x7, count0)."""
+    H, W = labels.shape
+    z = centers[:, 2].astype(np.float32).copy()
+    z[z < 0.2] += np.float32(20.0)
+    sort_idx = np.argsort(z, kind="stable")
+    seg = np.zeros((H, W), np.uint8)
+    kept = []
+    ratio_area = np.float32(0)
+    total = np.float32(H * W)
+    count0 = 0
+    for i in range(NUM_CLUSTER):
+        idx = int(sort_idx[i])
+        each = labels == idx
+        cnt = int(np.count_nonzero(each))
+        if cnt < 60:
+            continue
+        kept.append(idx)
+        ratio = np.float32(cnt) * (np.float32(1.0) / total)
+        ratio_area = np.float32(ratio_area + ratio)
+        if count0 <= 5 and ratio_area < np.float32(0.6):
+            seg[each] = 255
+            count0 += 1
+    seg = cv2.morphologyEx(seg, cv2.MORPH_DILATE, ellipse(7))
+    return kept, seg, count0
+
+
+# ----------------------------------------------------------------------------- CalOccluded (gradient part)
+AROUND = [(0, -2), (1, -2), (2, -1), (2, 0), (2, 1), (1, 2), (0, 2), (-1, 2), (-2, 1), (-2, 0), (-2, -1), (-1, -2)]  # DynaDetect.h:113-125
+
+
+def depth_edges(depth, depth_scale):
+    """DynaDetect.cc:434-536. Returns (imgTotalArea, imgOccluded after OPEN4 (= imgOccludedForPlane), endpoints (x,y) after NMS)."""
+    f = np.float32
+    H, W = depth.shape
+    d1 = depth.astype(np.float32)
+    filt = cv2.medianBlur(d1, 5)
+    depth_max = f(filt.max())
+    total = np.zeros((H, W), np.uint8)
+    occl = np.zeros((H, W), np.uint8)
+    r = 3
+    c = filt[r:H - r, r:W - r]
+    total[r:H - r, r:W - r][(c > 0) & ((c / f(depth_scale)) < f(6.0))] = 255
+    val_max = np.zeros_like(c)
+    for i in range(5):
+        for j in range(5):
+            nb = filt[r + i - 2:H - r + i - 2, r + j - 2:W - r + j - 2]
+            diff = c - nb
+            skip = diff > depth_max * f(0.5)
+            val_max = np.where(skip, val_max, np.maximum(np.abs(val_max), np.abs(diff)))
+    occl[r:H - r, r:W - r][(val_max > c * f(0.03)) & (val_max > f(400.0))] = 255
+    occl = cv2.morphologyEx(occl, cv2.MORPH_OPEN, ellipse(4))
+    on = occl == 255
+    cnt = np.zeros((H, W), np.int32)
+    for dx, dy in AROUND:
+        sh = np.zeros((H, W), bool)
+        ys0, ys1 = max(0, -dy), min(H, H - dy)
+        xs0, xs1 = max(0, -dx), min(W, W - dx)
+        sh[ys0:ys1, xs0:xs1] = on[ys0 + dy:ys1 + dy, xs0 + dx:xs1 + dx]
+        cnt += sh
+    cand = on & (cnt <= 4)
+    cand[:3] = cand[-3:] = False
+    cand[:, :3] = cand[:, -3:] = False
+    ys, xs = np.nonzero(cand)  # raster order
+    kept = []
+    # applyNMS (DynaDetect.cc:110-143): sort by the never-assigned curvature (no-op), greedy 6-px suppression
+    for x, y in zip(xs.tolist(), ys.tolist()):
+        ok = True
+        for (qx, qy) in reversed(kept):
+            if qy < y - 6:
+                break
+            if (x - qx) * (x - qx) + (y - qy) * (y - qy) < 36:
+                ok = False
+                break
+        if ok:
+            kept.append((x, y))
+    return total, occl, np.array(kept, np.int32).reshape(-1, 2)

@@ -3,6 +3,9 @@
 #pragma once
 #include "brox.cuh"
 #include "common.cuh"
+#include "edges.cuh"
+#include "kmeans.cuh"
+#include "morph.cuh"
 #include "preproc.cuh"
 #include "residual.cuh"
 
@@ -37,6 +40,9 @@ struct sindyn_ctx : sindyn_base {
 
     ResidualStage resid;
     uint8_t *mask_low = nullptr, *mask_high = nullptr;
+
+    KmeansStage km;
+    EdgeStage edges;
 
     float stage_ms[16] = {};
 };
