@@ -418,3 +418,294 @@ def depth_edges(depth, depth_scale):
         if ok:
             kept.append((x, y))
     return total, occl, np.array(kept, np.int32).reshape(-1, 2)
+
+
+# ----------------------------------------------------------------------------- plane-edge filtering
+def filter_plane_edges(plane_edges, grad_edges, endpoints):
+    """DynaDetect.cc:598-641. plane_edges = imgEdgeByPlane from PEAC, grad_edges = imgOccludedForPlane.
+    Returns (imgOccluded1, imgOccluded2)."""
+    H, W = grad_edges.shape
+    e = cv2.subtract(plane_edges, grad_edges)
+    contours, _ = cv2.findContours(e, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+    out = np.zeros((H, W), np.uint8)
+    for i, c in enumerate(contours):
+        if len(c) < 25:
+            continue
+        one = np.zeros((H, W), np.uint8)
+        cv2.drawContours(one, contours, i, 255, 2)
+        one = cv2.morphologyEx(one, cv2.MORPH_DILATE, ellipse(10))
+        if any(one[y, x] == 255 for x, y in np.asarray(endpoints).reshape(-1, 2)):
+            one = cv2.morphologyEx(one, cv2.MORPH_ERODE, ellipse(7))
+            out = cv2.add(out, one)
+    occl2 = out.copy()
+    occl1 = cv2.morphologyEx(cv2.bitwise_or(grad_edges, out), cv2.MORPH_CLOSE, ellipse(3))
+    return occl1, occl2
+
+
+# ----------------------------------------------------------------------------- SegAndMergeV2
+def _hist_depth(depth_norm, mask):
+    """calcHist(&imgDepth, 1, 0, mask, hist, 1, {256}, {0,255}) (DynaDetect.cc:1691-1696): value 255 is dropped."""
+    return cv2.calcHist([depth_norm], [0], mask, [256], [0, 255])
+
+
+def cal_hist(img1, img2, depth_norm):
+    """DynaDetect.cc:1685-1739. Returns [CORREL, 1 - BHATTACHARYYA, INTERSECT]."""
+    h1 = _hist_depth(depth_norm, img1)
+    h2 = _hist_depth(depth_norm, img2)
+    m1, m2 = float(h1.max()), float(h2.max())
+    if m1 > m2:
+        h1 = cv2.normalize(h1, None, 0, 400, cv2.NORM_MINMAX, -1)
+        h2 = h2 * np.float32(1.0 / (m1 / 400))
+    else:
+        h2 = cv2.normalize(h2, None, 0, 400, cv2.NORM_MINMAX, -1)
+        h1 = h1 * np.float32(1.0 / (m2 / 400))
+    return [cv2.compareHist(h1, h2, cv2.HISTCMP_CORREL), 1 - cv2.compareHist(h1, h2, cv2.HISTCMP_BHATTACHARYYA),
+            cv2.compareHist(h1, h2, cv2.HISTCMP_INTERSECT)]
+
+
+def center_z_fx(points, mask):
+    """myCluster::calCenterPoint (DynaDetect.cc:256-293), z only (the only component consumed, :741).  The reference's
+    OpenMP float reduction is order dependent; restated with the same 2^-36 fixed-point sum as the k-means centres."""
+    idx = np.nonzero(mask.reshape(-1))[0]
+    s = int(np.rint(points[idx, 2].astype(np.float64) * float(1 << KM_FIX)).astype(np.int64).sum())
+    return np.float32(np.float32(s * 2.0 ** -KM_FIX) / np.float32(len(idx)))
+
+
+def seg_and_merge_v2(kept, labels_km, occluded1, occluded2, seg_edge, points, depth, debug=None):
+    """DynaDetect::SegAndMergeV2 (DynaDetect.cc:653-1018). kept = allLabels order (k-means ids by depth).
+    Returns imgLabelNew (u8; 0 = invalid, 1..n)."""
+    f = np.float32
+    H, W = labels_km.shape
+    clusters = []
+    occl_dil = cv2.morphologyEx(occluded1, cv2.MORPH_DILATE, ellipse(10))
+    for ki in kept[:-1]:                       # the last (farthest / invalid) cluster is not processed (:664)
+        orig = np.where(labels_km == ki, 255, 0).astype(np.uint8)
+        each = cv2.subtract(orig, occluded1)
+        each = cv2.morphologyEx(each, cv2.MORPH_OPEN, ellipse(4))
+        contours, _ = cv2.findContours(each, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+        for c, cnt in enumerate(contours):
+            if len(cnt) > 50 and cv2.contourArea(cnt) > 80:
+                temp = np.zeros((H, W), np.uint8)
+                cv2.drawContours(temp, contours, c, 255, cv2.FILLED)
+                temp = cv2.morphologyEx(temp, cv2.MORPH_DILATE, ellipse(9))
+                temp = cv2.bitwise_and(temp, orig)
+                cl = dict(img=temp, area=f(np.count_nonzero(temp)), lianjie=None, km=ki)
+                cl["dil"] = cv2.morphologyEx(temp, cv2.MORPH_DILATE, ellipse(7))
+                draw = np.zeros((H, W), np.uint8)
+                cv2.drawContours(draw, contours, c, 255, 2)
+                temp1 = cv2.subtract(draw, occl_dil)
+                temp1 = cv2.bitwise_and(temp1, seg_edge)
+                if np.count_nonzero(temp1) > 20:
+                    c2, _ = cv2.findContours(temp1, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+                    c2 = [q for q in c2 if len(q) >= 30]
+                    if len(c2) > 0:
+                        t = np.zeros((H, W), np.uint8)
+                        cv2.drawContours(t, c2, -1, 255, cv2.FILLED)
+                        cl["lianjie"] = t
+                cl["z"] = center_z_fx(points, temp)
+                clusters.append(cl)
+    for cl in clusters:
+        cl["score"] = f(cl["area"] * f(0.0003) - cl["z"])
+    clusters.sort(key=lambda c: -c["score"])    # std::sort descending (ties: unspecified in the reference)
+    n = len(clusters)
+    total_img = np.full((H, W), (n + 1) & 255, np.uint8)
+    for i, cl in enumerate(clusters):
+        total_img[cl["img"] > 0] = i
+    depth_max = float(depth.max())
+    depth_norm = cv2.convertScaleAbs(depth, alpha=(1.0 / depth_max) * 255.0) if depth_max > 0 else np.zeros((H, W), np.uint8)
+    M1 = np.zeros((n + 1, n + 1), np.float32)
+    M2 = np.zeros((n + 1, n + 1), np.float32)
+    M3 = np.zeros((n + 1, n + 1), np.float32)
+    Wt = np.ones((n + 1, n + 1), np.float32)
+    Rj = np.ones((n + 1, n + 1), np.float32)
+    small_label = int(min(f(0.7) * f(n), f(15.0)))
+    for i in range(n):
+        c1 = clusters[i]
+        for j in range(i + 1, n):
+            c2 = clusters[j]
+            v1 = v2 = v3 = f(0)
+            if c1["area"] < c2["area"]:
+                less_area, less_label = c1["area"], i
+            else:
+                less_area, less_label = c2["area"], j
+            if less_label < 10:
+                Wt[i, j] = Wt[j, i] = 0.7
+            elif less_label > small_label:
+                Wt[i, j] = Wt[j, i] = 2.0
+            overlap = cv2.bitwise_and(c1["dil"], c2["dil"])
+            is_must = False
+            if np.count_nonzero(overlap) > min(f(200.0), f(less_area * f(0.4))):
+                ov_edge = cv2.bitwise_and(overlap, occluded2)
+                v1 = f(1.0)
+                r = cal_hist(c1["img"], c2["img"], depth_norm)
+                v3 = f(r[0] + r[1] + r[2] * 0.0005)
+                if np.count_nonzero(ov_edge) > 100 and less_label < small_label:
+                    Rj[i, j] = Rj[j, i] = 0.0
+                    continue
+                elif v3 < f(0.19) and less_label < small_label and not is_must:
+                    Rj[i, j] = Rj[j, i] = 0.0
+                    continue
+                l1, l2 = c1["lianjie"], c2["lianjie"]
+                if l1 is not None and l2 is not None:
+                    ol = int(np.count_nonzero(cv2.bitwise_and(l1, l2)))
+                    if ol > 0:
+                        a1, a2 = int(np.count_nonzero(l1)), int(np.count_nonzero(l2))
+                        if ol > min(50, int(0.5 * min(a1, a2))):
+                            v2 = f(ol)
+                            if ol > 0.62 * a1 or ol > 0.62 * a2:
+                                v2 = f(max(250, ol))
+                                is_must = True
+                M1[i, j] = M1[j, i] = v1
+                M2[i, j] = M2[j, i] = v2
+                M3[i, j] = M3[j, i] = v3
+    T = ((M2 * f(0.01) + M3) * Rj * Wt).astype(np.float32)
+    if debug is not None:
+        debug.update(clusters=clusters, total_img=total_img.copy(), T=T.copy(), M2=M2, M3=M3, Rj=Rj, Wt=Wt)
+    labels = merge_and_relabel(T, total_img, n)
+    return labels
+
+
+def merge_and_relabel(T, total_img, n):
+    """Greedy merge + relabel (DynaDetect.cc:894-1016) on the RAG matrix T ((n+1) x (n+1) float32)."""
+    f = np.float32
+    T = T.copy()
+    H, W = total_img.shape
+    count_merged = 0
+    merge = [[] for _ in range(n + 1)]
+    merged = [0] * (n + 1)
+    i = 0
+    while i < min(NUM_CLUSTER - 1 + count_merged, n):
+        j = i + 1
+        while j < min(NUM_CLUSTER - 1 + count_merged, n):
+            score = T[j, i]
+            if score > f(0.9):
+                col = T[0:j, j].copy()
+                to_merge = i
+                val = T[j, i]
+                for k in range(j):
+                    if col[k] > val:
+                        to_merge = k
+                merged[j] = 1
+                merge[to_merge].append(j)
+                one_col = T[:, j].copy()
+                T[:, to_merge] += one_col
+                T[to_merge, :] += one_col
+                T[:, j] = 0
+                T[j, :] = 0
+                count_merged += 1
+            j += 1
+        i += 1
+    for i in range(min(NUM_CLUSTER - 1 + count_merged, n), n):
+        mc, best = n, f(0.2)
+        for j in range(i):
+            s = T[j, i]
+            if s > best:
+                best, mc = s, j
+        merged[i] = 1
+        merge[mc].append(i)
+        one_col = T[:, i].copy()
+        T[:, mc] += one_col
+        T[mc, :] += one_col
+        T[:, i] = 0
+        T[i, :] = 0
+    out = np.zeros((H, W), np.uint8)
+    idx = 1
+    for i in range(n):
+        if not merged[i]:
+            m = total_img == i
+            for a in merge[i]:
+                m |= total_img == a
+                for b in merge[a]:
+                    m |= total_img == b
+            out[m] = idx
+            idx += 1
+    return out
+
+
+# ----------------------------------------------------------------------------- decision + final mask
+def dynamic_decide(low_in, high, high_last, total_area, labels):
+    """DynaDetect.cc:1553-1636. low_in = imgMaskLowError (0/128), high (0/255). Returns imgDyna {0,125,255}."""
+    H, W = labels.shape
+    dyna = np.zeros((H, W), np.uint8)
+    low = cv2.bitwise_or(high_last, low_in)
+    low[low > 0] = 128
+    low = cv2.bitwise_and(low, total_area)
+    low = cv2.morphologyEx(low, cv2.MORPH_DILATE, ellipse(5))
+    nmax = int(labels.max())
+    for n in range(1, nmax + 1):
+        one = np.where(labels == n, 255, 0).astype(np.uint8)
+        border = cv2.copyMakeBorder(one, 1, 1, 1, 1, cv2.BORDER_CONSTANT, value=0)
+        border = cv2.bitwise_not(border)
+        with_high = cv2.bitwise_and(one, high)
+        if np.count_nonzero(with_high) > 100:
+            cs, _ = cv2.findContours(with_high, cv2.RETR_CCOMP, cv2.CHAIN_APPROX_NONE)
+            for c in cs:
+                area = cv2.contourArea(c)
+                ln = cv2.arcLength(c, True)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    roundness = np.float64(4 * np.pi * area) / np.float64(ln * ln)
+                seed = (0, 0)
+                for p in c[:, 0, :]:
+                    if low[p[1], p[0]] == 128:
+                        seed = (int(p[0]), int(p[1]))
+                        break
+                if (area > 100.0 and roundness > 0.2) or area > 2000.0:
+                    cv2.floodFill(low, border, seed, 50, 5, 5, 8 | cv2.FLOODFILL_MASK_ONLY | (50 << 8))
+        filled = np.where(border[1:-1, 1:-1] == 50, 255, 0).astype(np.uint8)
+        if np.count_nonzero(filled) > 0.5 * np.count_nonzero(one):
+            dyna = cv2.bitwise_or(dyna, one)
+        else:
+            dyna = cv2.bitwise_or(dyna, filled)
+    dyna = cv2.morphologyEx(dyna, cv2.MORPH_DILATE, ellipse(9))
+    static2 = (cv2.subtract(total_area, dyna).astype(np.float32) * np.float32(125.0 / 255.0))
+    static2 = np.rint(static2).astype(np.uint8)
+    return cv2.add(dyna, static2)
+
+
+# ----------------------------------------------------------------------------- sampling + homography
+def sample_pairs(flow, dyna_last, label_last):
+    """DynaDetect.cc:1163-1231: weighted 10-px grid samples, sorted by weight (descending), filtered by inBorder.
+    Returns (inputPoints, inputPointsLast) as float32 n x 2 (x, y)."""
+    f = np.float32
+    H, W = dyna_last.shape
+    cw = np.zeros(NUM_CLUSTER, np.float32)
+    dyn0 = dyna_last == 255
+    for i in range(1, NUM_CLUSTER):
+        one = label_last == i
+        cw[i] = f(np.count_nonzero(one & dyn0)) / (f(np.count_nonzero(one)) + f(1.0))
+    rows = list(range(10, H, 10))
+    cols = list(range(10, W, 10))
+    cv2.setRNGSeed(12345)                       # cv::RNG rng(12345) (DynaDetect.cc:1163)
+    g = np.zeros((len(rows) * len(cols), 1), np.float32)
+    cv2.randn(g, 0, 0.5)                        # rng.gaussian(0.5) per sample, raster order (:1187)
+    g = g.ravel()
+    items = []
+    k = 0
+    for r in rows:
+        for c in cols:
+            rd = g[k]
+            k += 1
+            dl = int(dyna_last[r, c])
+            if dl < 20:
+                w = f(rd + f(1.0))
+            elif 20 <= dl <= 230:
+                w = f(rd + f(1.2) * (f(1.0) - cw[int(label_last[r, c])]))
+            else:
+                w = f(rd + f(0.4))
+            items.append((c, r, w))
+    items.sort(key=lambda t: -t[2])              # std::sort descending (stable here; ties are measure-zero)
+    pts, last = [], []
+    for c, r, _ in items:
+        fx_, fy_ = flow[r, c]
+        lx, ly = f(f(c) - fx_), f(f(r) - fy_)
+        irow, icol = int(ly), int(lx)            # float -> int truncation toward zero at the inBorder call
+        if 0 <= irow <= H and 0 <= icol <= W:    # (uint)(v) <= dim : inclusive upper bound (DynaDetect.cc:103-106)
+            pts.append((f(c), f(r)))
+            last.append((lx, ly))
+    return np.array(pts, np.float32).reshape(-1, 2), np.array(last, np.float32).reshape(-1, 2)
+
+
+def estimate_homography(pts, pts_last):
+    """cv::findHomography(inputPoints, inputPointsLast, cv::noArray(), cv::RHO) (DynaDetect.cc:1235)."""
+    Hm, _ = cv2.findHomography(pts, pts_last, cv2.RHO)
+    return Hm

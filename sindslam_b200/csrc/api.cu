@@ -28,7 +28,6 @@ extern "C" void sindyn_default_config(sindyn_config *c, int width, int height)
     c->plane_edges = 1;
 }
 
-int sindyn_ctx_init_stages(sindyn_ctx *c);  // stages.cu
 
 extern "C" int sindyn_create(const sindyn_config *cfg, sindyn_handle *out)
 {
@@ -70,13 +69,15 @@ extern "C" int sindyn_create(const sindyn_config *cfg, sindyn_handle *out)
     SD_CHECK(resize_plan_init(c, &c->plan_flow, c->W, c->H, c->fw, c->fh));
     SD_CHECK(brox_init(c, &c->brox, c->fw, c->fh, cfg->brox_alpha, cfg->brox_gamma, cfg->brox_pyr_scale, cfg->brox_inner,
                        cfg->brox_outer, cfg->brox_solver, cfg->brox_omega));
+    SD_CHECK(brox_init(c, &c->brox_lm, c->fw, c->fh, cfg->brox_alpha, cfg->brox_gamma, cfg->brox_pyr_scale, cfg->brox_inner,
+                       cfg->brox_outer, cfg->brox_solver, cfg->brox_omega));
     SD_CHECK(residual_init(c, &c->resid, c->W, c->H));
+    SD_CHECK(flow_branch_init(c));
     SD_CHECK(sindyn_ctx_init_stages(c));
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     return SINDYN_OK;
 }
 
-void sindyn_ctx_destroy_stages(sindyn_ctx *c);  // stages.cu
 
 extern "C" int sindyn_destroy(sindyn_handle h)
 {
@@ -84,6 +85,7 @@ extern "C" int sindyn_destroy(sindyn_handle h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     brox_destroy(&h->brox);
+    brox_destroy(&h->brox_lm);
     sindyn_ctx_destroy_stages(h);
     h->free_all();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -100,7 +102,8 @@ extern "C" int sindyn_set_stream(sindyn_handle h, void *s)
     if (ns != h->stream) {
         CU_CHECK(h, cudaStreamSynchronize(h->stream));
         h->stream = ns;
-        h->brox.graph_ok = false;  // graphs are stream-agnostic, but re-capture keeps capture semantics simple
+        h->brox.graph_ok = false;
+        h->brox_lm.graph_ok = false;  // graphs are stream-agnostic, but re-capture keeps capture semantics simple
     }
     return SINDYN_OK;
 }

@@ -379,35 +379,44 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
     return SINDYN_OK;
 }
 
+static void brox_drop_graphs(BroxSolver *b)
+{
+    for (auto &g : b->slots) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+        g = BroxSolver::GraphSlot();
+    }
+    b->next_slot = 0;
+}
+
 int brox_run(sindyn_base *ctx, BroxSolver *b, const float *I0, const float *I1, float *flow_out, float sign, bool use_graph)
 {
     if (!use_graph) return brox_enqueue(ctx, b, I0, I1, flow_out, sign);
-    if (!(b->graph_ok && b->g_I0 == I0 && b->g_I1 == I1 && b->g_out == flow_out && b->g_sign == sign)) {
-        if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
-        if (b->graph) { cudaGraphDestroy(b->graph); b->graph = nullptr; }
-        b->graph_ok = false;
+    if (!b->graph_ok) { brox_drop_graphs(b); b->graph_ok = true; }
+    BroxSolver::GraphSlot *g = nullptr;
+    for (auto &s : b->slots)
+        if (s.ok && s.I0 == I0 && s.I1 == I1 && s.out == flow_out && s.sign == sign) g = &s;
+    if (!g) {
+        g = &b->slots[b->next_slot];
+        b->next_slot = (b->next_slot + 1) % 4;
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        if (g->graph) cudaGraphDestroy(g->graph);
+        *g = BroxSolver::GraphSlot();
         unsigned long long before = ctx->launches;
         CU_CHECK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         int st = brox_enqueue(ctx, b, I0, I1, flow_out, sign);
-        cudaError_t e = cudaStreamEndCapture(ctx->stream, &b->graph);
-        b->graph_launches = ctx->launches - before;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g->graph);
+        g->launches = ctx->launches - before;
         ctx->launches = before;
         if (st != SINDYN_OK) return st;
         CU_CHECK(ctx, e);
-        CU_CHECK(ctx, cudaGraphInstantiate(&b->graph_exec, b->graph, 0));
-        b->g_I0 = I0; b->g_I1 = I1; b->g_out = flow_out; b->g_sign = sign;
-        b->graph_ok = true;
+        CU_CHECK(ctx, cudaGraphInstantiate(&g->exec, g->graph, 0));
+        g->I0 = I0; g->I1 = I1; g->out = flow_out; g->sign = sign;
+        g->ok = true;
     }
-    CU_CHECK(ctx, cudaGraphLaunch(b->graph_exec, ctx->stream));
-    ctx->launches += b->graph_launches;
+    CU_CHECK(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += g->launches;
     return SINDYN_OK;
 }
 
-void brox_destroy(BroxSolver *b)
-{
-    if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
-    if (b->graph) cudaGraphDestroy(b->graph);
-    b->graph_exec = nullptr;
-    b->graph = nullptr;
-    b->graph_ok = false;
-}
+void brox_destroy(BroxSolver *b) { brox_drop_graphs(b); b->graph_ok = false; }

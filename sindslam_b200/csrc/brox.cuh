@@ -15,13 +15,19 @@ struct BroxSolver {
     // per-level scratch, sized for level 0
     float *A, *Iz, *Ix, *Iy, *Ixz, *Iyz, *Ixx, *Ixy, *Iyy;
     float *u[2], *v[2], *du[3], *dv[3];
-    bool graph_ok = false;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
-    const float *g_I0 = nullptr, *g_I1 = nullptr;
-    float *g_out = nullptr;
-    float g_sign = 0.f;
-    unsigned long long graph_launches = 0;
+    // captured CUDA graphs, keyed by the (I0, I1, out, sign) tuple: the frame ring of the handle rotates
+    // through three pointer combinations, each gets its own graph
+    struct GraphSlot {
+        bool ok = false;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const float *I0 = nullptr, *I1 = nullptr;
+        float *out = nullptr;
+        float sign = 0.f;
+        unsigned long long launches = 0;
+    } slots[4];
+    int next_slot = 0;
+    bool graph_ok = false;  // set to false to drop every cached graph (stream change)
 };
 
 int brox_num_levels_host(int w, int h, float scale, int outer, int *ws, int *hs);

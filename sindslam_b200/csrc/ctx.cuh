@@ -4,10 +4,12 @@
 #include "brox.cuh"
 #include "common.cuh"
 #include "edges.cuh"
+#include "homography.cuh"
 #include "kmeans.cuh"
 #include "morph.cuh"
 #include "preproc.cuh"
 #include "residual.cuh"
+#include "varref.cuh"
 
 struct sindyn_ctx : sindyn_base {
     sindyn_config cfg;
@@ -31,7 +33,12 @@ struct sindyn_ctx : sindyn_base {
 
     // flow branch
     ResizePlanU8 plan_flow;
-    BroxSolver brox;
+    BroxSolver brox, brox_lm;  // (cur, lastlast) and the large-motion (cur, last) solver
+    float *fb_mag = nullptr;
+    unsigned int *fb_hist = nullptr;
+    int *fb_flag = nullptr, *fb_flag_host = nullptr;
+    HomographyStage homog;
+    VarRefStage varref;
     float *flow_small = nullptr;  // fw x fh x 2
     float *flow_full = nullptr;   // W x H x 2
     // generic scratch for stage-level entry points
@@ -46,3 +53,10 @@ struct sindyn_ctx : sindyn_base {
 
     float stage_ms[16] = {};
 };
+
+// internal cross-module helpers (C++ linkage)
+int sindyn_prep_frame(sindyn_ctx *c, int idx);          // api.cu: BGR -> gray -> 0.6x gray (u8 + float)
+int flow_branch_init(sindyn_ctx *c);                    // flow.cu
+int flow_branch_run(sindyn_ctx *c, int *large_motion);  // flow.cu
+int sindyn_ctx_init_stages(sindyn_ctx *c);              // stages.cu
+void sindyn_ctx_destroy_stages(sindyn_ctx *c);          // stages.cu

@@ -1,0 +1,331 @@
+// homography.cu -- weighted grid sampling of the dense flow and robust homography estimation.
+//
+// Replaces ORB_SLAM2/src/DynaDetect.cc:1163-1235:
+//   clusterWeight (:1169-1177), the 10-px sample grid with weight = RNG(12345).gaussian(0.5) + class term
+//   (:1182-1204), std::sort by weight descending (:1217-1219), the inBorder filter with its int truncation and
+//   inclusive upper bound (:1221-1231, inBorder :103-106), and cv::findHomography(pts, ptsLast, noArray(), RHO)
+//   (:1235).
+// The sample list is bit-exact against the oracle.  cv::findHomography(RHO) is OpenCV's PROSAC+SPRT estimator
+// (un-vendored; order sensitive); it is replaced by a deterministic PROSAC-style parallel
+// hypothesise-and-verify estimator: HG_M minimal 4-point hypotheses drawn progressively from the top of the
+// sorted list (one warp each: DLT in double + inlier count at the RHO default 3 px), best consensus, then
+// Gauss-Newton refinement of the reprojection error on the inliers.  Parity with RHO is a stated tolerance
+// on the induced flow (tests/test_homography_gpu.py).
+#include "homography.cuh"
+
+__device__ const float c_gauss[HG_GAUSS_N] = {
+#include "gauss_table.inc"
+};
+
+// counts[0][i] = |label_last == i|, counts[1][i] = |label_last == i && dyna_last == 255|
+__global__ void k_cluster_weight_counts(const uint8_t *__restrict__ label_last, const uint8_t *__restrict__ dyna_last, int n,
+                                        int *__restrict__ counts)
+{
+    __shared__ int sc[2 * 16];
+    if (threadIdx.x < 32) sc[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int l = label_last[i];
+        if (l >= 1 && l < 12) {
+            atomicAdd(&sc[l], 1);
+            if (dyna_last[i] == 255) atomicAdd(&sc[16 + l], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
+}
+
+__device__ __forceinline__ unsigned int f2ord_desc(float f)
+{
+    unsigned int u = __float_as_uint(f);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending order of f
+    return ~u;                                        // descending
+}
+
+// single CTA: weights, stable descending sort, inBorder filter, ordered compaction
+__global__ void __launch_bounds__(1024) k_sample_pairs(const float2 *__restrict__ flow, const uint8_t *__restrict__ label_last,
+                                                       const uint8_t *__restrict__ dyna_last, const int *__restrict__ counts, int W, int H,
+                                                       float2 *__restrict__ pts, float2 *__restrict__ pts_last, int *__restrict__ n_out)
+{
+    __shared__ unsigned long long keys[HG_MAX_SAMPLES];
+    __shared__ float cw[12];
+    __shared__ int s_scan[1024 / 32];
+    __shared__ int s_base;
+    const int ncol = (W - 1) / 10, nrow = (H - 1) / 10;  // rows 10,20,.. < H ; cols 10,20,.. < W
+    const int ns = ncol * nrow;
+    if (threadIdx.x < 12) {
+        int i = threadIdx.x;
+        cw[i] = i >= 1 ? (float)counts[16 + i] / ((float)counts[i] + 1.0f) : 0.0f;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < HG_MAX_SAMPLES; k += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (k < ns) {
+            int r = k / ncol, c = k - r * ncol;
+            int row = 10 + 10 * r, col = 10 + 10 * c;
+            float randomd = c_gauss[k];
+            uint8_t dl = dyna_last[row * W + col];
+            float w;
+            if (dl < 20) w = randomd + 1.0f;
+            else if ((unsigned)(dl - 20) <= 230u - 20u) w = randomd + 1.2f * (1.0f - cw[min((int)label_last[row * W + col], 11)]);
+            else w = randomd + 0.4f;
+            key = ((unsigned long long)f2ord_desc(w) << 32) | (unsigned)k;
+        }
+        keys[k] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= HG_MAX_SAMPLES; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < HG_MAX_SAMPLES; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], b = keys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int start = 0; start < ns; start += blockDim.x) {
+        int i = start + threadIdx.x;
+        bool keep = false;
+        float pc = 0.f, pr = 0.f, lx = 0.f, ly = 0.f;
+        if (i < ns) {
+            int k = (int)(keys[i] & 0xffffffffull);
+            int r = k / ncol, c = k - r * ncol;
+            int row = 10 + 10 * r, col = 10 + 10 * c;
+            float2 f = flow[row * W + col];
+            pc = (float)col; pr = (float)row;
+            lx = pc - f.x; ly = pr - f.y;
+            int irow = (int)ly, icol = (int)lx;  // float -> int truncation at the inBorder call (DynaDetect.cc:1226)
+            keep = ((unsigned)irow <= (unsigned)H) && ((unsigned)icol <= (unsigned)W);
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, keep);
+        int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) s_scan[wid] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w2 = 0; w2 < wid; ++w2) off += s_scan[w2];
+        off += __popc(bal & ((1u << lane) - 1u));
+        if (keep) { pts[off] = make_float2(pc, pr); pts_last[off] = make_float2(lx, ly); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += s_scan[w2];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = s_base;
+}
+
+// ---------------------------------------------------------------- minimal solver
+__device__ bool solve8(double A[8][9])
+{
+    for (int c = 0; c < 8; ++c) {
+        int piv = c;
+        double best = fabs(A[c][c]);
+        for (int r = c + 1; r < 8; ++r)
+            if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
+        if (!(best > 1e-12)) return false;
+        if (piv != c)
+            for (int k = c; k < 9; ++k) { double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+        double inv = 1.0 / A[c][c];
+        for (int r = c + 1; r < 8; ++r) {
+            double f = A[r][c] * inv;
+            if (f != 0.0)
+                for (int k = c; k < 9; ++k) A[r][k] -= f * A[c][k];
+        }
+    }
+    for (int r = 7; r >= 0; --r) {
+        double s = A[r][8];
+        for (int k = r + 1; k < 8; ++k) s -= A[r][k] * A[k][8];
+        A[r][8] = s / A[r][r];
+    }
+    return true;
+}
+
+__device__ __forceinline__ unsigned int hg_hash(unsigned int x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// one warp per hypothesis
+__global__ void __launch_bounds__(256) k_homog_hypotheses(const float2 *__restrict__ pts, const float2 *__restrict__ pts_last,
+                                                          const int *__restrict__ n_ptr, double *__restrict__ Hs, int *__restrict__ scores)
+{
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= HG_M) return;
+    const int n = *n_ptr;
+    double h[8];
+    bool ok = n >= 4;
+    if (ok) {
+        // PROSAC-style progressive sampling pool: the top T of the weight-sorted list
+        int T = max(8, (int)(((long long)n * (m + 1) + HG_M - 1) / HG_M));
+        T = min(T, n);
+        int idx[4];
+        unsigned int s = hg_hash(0x9e3779b9u * (unsigned)(m + 1));
+        for (int k = 0; k < 4; ++k) {
+            for (int tries = 0; tries < 16; ++tries) {
+                s = hg_hash(s + 0x632be5abu);
+                idx[k] = (int)(s % (unsigned)T);
+                bool dup = false;
+                for (int q = 0; q < k; ++q) dup |= idx[q] == idx[k];
+                if (!dup) break;
+            }
+        }
+        double A[8][9];
+        for (int k = 0; k < 4; ++k) {
+            double x = pts[idx[k]].x, y = pts[idx[k]].y, u = pts_last[idx[k]].x, v = pts_last[idx[k]].y;
+            double r0[9] = {x, y, 1, 0, 0, 0, -u * x, -u * y, u};
+            double r1[9] = {0, 0, 0, x, y, 1, -v * x, -v * y, v};
+            for (int c = 0; c < 9; ++c) { A[2 * k][c] = r0[c]; A[2 * k + 1][c] = r1[c]; }
+        }
+        ok = solve8(A);
+        for (int c = 0; c < 8; ++c) h[c] = A[c][8];
+        for (int c = 0; c < 8; ++c) ok = ok && isfinite(h[c]);
+    }
+    int cnt = 0;
+    if (ok) {
+        for (int i = lane; i < n; i += 32) {
+            double x = pts[i].x, y = pts[i].y;
+            double w = h[6] * x + h[7] * y + 1.0;
+            double ex = (h[0] * x + h[1] * y + h[2]) / w - pts_last[i].x;
+            double ey = (h[3] * x + h[4] * y + h[5]) / w - pts_last[i].y;
+            cnt += (w > 1e-9 && ex * ex + ey * ey <= HG_THR2) ? 1 : 0;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+        scores[m] = ok ? cnt : -1;
+        for (int c = 0; c < 8; ++c) Hs[m * 8 + c] = ok ? h[c] : 0.0;
+    }
+}
+
+// single CTA: best consensus, then Gauss-Newton on the inliers (re-selected every iteration)
+__global__ void __launch_bounds__(1024) k_homog_select_refine(const float2 *__restrict__ pts, const float2 *__restrict__ pts_last,
+                                                              const int *__restrict__ n_ptr, const double *__restrict__ Hs,
+                                                              const int *__restrict__ scores, double *__restrict__ H_out,
+                                                              int *__restrict__ info)
+{
+    __shared__ int s_best[32], s_bidx[32];
+    __shared__ double s_acc[32][45];
+    __shared__ double s_h[8];
+    __shared__ int s_nin;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = *n_ptr;
+    int best = -2, bidx = 0;
+    for (int m = tid; m < HG_M; m += blockDim.x)
+        if (scores[m] > best) { best = scores[m]; bidx = m; }
+    for (int o = 16; o > 0; o >>= 1) {
+        int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) { s_best[wid] = best; s_bidx[wid] = bidx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w2 = 1; w2 < 32; ++w2)
+            if (s_best[w2] > best || (s_best[w2] == best && s_bidx[w2] < bidx)) { best = s_best[w2]; bidx = s_bidx[w2]; }
+        if (best >= 4) for (int c = 0; c < 8; ++c) s_h[c] = Hs[bidx * 8 + c];
+        else { for (int c = 0; c < 8; ++c) s_h[c] = 0.0; s_h[0] = 1.0; s_h[4] = 1.0; }  // identity when no consensus
+        info[0] = best;
+        info[1] = bidx;
+        s_best[0] = best;
+    }
+    __syncthreads();
+    best = s_best[0];
+    for (int iter = 0; iter < HG_GN_ITERS && best >= 4; ++iter) {
+        double acc[45];
+        for (int k = 0; k < 45; ++k) acc[k] = 0.0;
+        int nin = 0;
+        double h[8];
+        for (int c = 0; c < 8; ++c) h[c] = s_h[c];
+        for (int i = tid; i < n; i += blockDim.x) {
+            double x = pts[i].x, y = pts[i].y;
+            double w = h[6] * x + h[7] * y + 1.0;
+            double iw = 1.0 / w;
+            double uh = (h[0] * x + h[1] * y + h[2]) * iw, vh = (h[3] * x + h[4] * y + h[5]) * iw;
+            double rx = pts_last[i].x - uh, ry = pts_last[i].y - vh;
+            if (!(w > 1e-9) || rx * rx + ry * ry > HG_THR2) continue;
+            ++nin;
+            double Ju[8] = {x * iw, y * iw, iw, 0, 0, 0, -uh * x * iw, -uh * y * iw};
+            double Jv[8] = {0, 0, 0, x * iw, y * iw, iw, -vh * x * iw, -vh * y * iw};
+            int k = 0;
+            for (int a = 0; a < 8; ++a)
+                for (int b = a; b < 8; ++b) acc[k++] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+            for (int a = 0; a < 8; ++a) acc[36 + a] += Ju[a] * rx + Jv[a] * ry;
+            acc[44] += rx * rx + ry * ry;
+        }
+        for (int k = 0; k < 45; ++k) {
+            double v = acc[k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_acc[wid][k] = v;
+        }
+        for (int o = 16; o > 0; o >>= 1) nin += __shfl_xor_sync(0xffffffffu, nin, o);
+        if (tid == 0) s_nin = 0;
+        __syncthreads();
+        if (lane == 0) atomicAdd(&s_nin, nin);
+        __syncthreads();
+        if (tid == 0) {
+            double tot[45];
+            for (int k = 0; k < 45; ++k) { double v = 0; for (int w2 = 0; w2 < 32; ++w2) v += s_acc[w2][k]; tot[k] = v; }
+            if (s_nin >= 8) {
+                double A[8][9];
+                int k = 0;
+                for (int a = 0; a < 8; ++a)
+                    for (int b = a; b < 8; ++b) { A[a][b] = tot[k]; A[b][a] = tot[k]; ++k; }
+                for (int a = 0; a < 8; ++a) { A[a][8] = tot[36 + a]; A[a][a] *= 1.0 + 1e-9; }
+                if (solve8(A)) {
+                    bool fin = true;
+                    for (int c = 0; c < 8; ++c) fin = fin && isfinite(A[c][8]);
+                    if (fin) for (int c = 0; c < 8; ++c) s_h[c] += A[c][8];
+                }
+            }
+            info[2] = s_nin;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        for (int c = 0; c < 8; ++c) H_out[c] = s_h[c];
+        H_out[8] = 1.0;
+    }
+}
+
+int homography_init(sindyn_base *ctx, HomographyStage *g, int W, int H)
+{
+    g->W = W; g->H = H;
+    int ns = ((W - 1) / 10) * ((H - 1) / 10);
+    if (ns > HG_MAX_SAMPLES || ns > HG_GAUSS_N) { ctx->err = "homography: sample grid exceeds HG_MAX_SAMPLES"; return SINDYN_ERR_CAPACITY; }
+    SD_CHECK(ctx->dalloc(&g->counts, 32));
+    SD_CHECK(ctx->dalloc(&g->pts, 2 * HG_MAX_SAMPLES));
+    SD_CHECK(ctx->dalloc(&g->pts_last, 2 * HG_MAX_SAMPLES));
+    SD_CHECK(ctx->dalloc(&g->n_pairs, 4));
+    SD_CHECK(ctx->dalloc(&g->Hs, 8 * HG_M));
+    SD_CHECK(ctx->dalloc(&g->scores, HG_M));
+    SD_CHECK(ctx->dalloc(&g->H_dev, 9));
+    return SINDYN_OK;
+}
+
+int homography_sample(sindyn_base *ctx, HomographyStage *g, const float *flow, const uint8_t *label_last, const uint8_t *dyna_last)
+{
+    CU_CHECK(ctx, cudaMemsetAsync(g->counts, 0, sizeof(int) * 32, ctx->stream));
+    LAUNCH(ctx, k_cluster_weight_counts, SINDYN_NUM_SMS_B200, 256, 0, label_last, dyna_last, g->W * g->H, g->counts);
+    LAUNCH(ctx, k_sample_pairs, 1, 1024, 0, (const float2 *)flow, label_last, dyna_last, g->counts, g->W, g->H, (float2 *)g->pts,
+           (float2 *)g->pts_last, g->n_pairs);
+    LAUNCH_CHECK(ctx);
+    return SINDYN_OK;
+}
+
+int homography_estimate(sindyn_base *ctx, HomographyStage *g)
+{
+    LAUNCH(ctx, k_homog_hypotheses, cdiv(HG_M * 32, 256), 256, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs,
+           g->scores);
+    LAUNCH(ctx, k_homog_select_refine, 1, 1024, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs, g->scores,
+           g->H_dev, g->n_pairs + 1);
+    LAUNCH_CHECK(ctx);
+    return SINDYN_OK;
+}

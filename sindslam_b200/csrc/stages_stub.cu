@@ -8,10 +8,6 @@
 extern "C" int sindyn_detect(sindyn_handle h, const uint8_t *, size_t, const uint16_t *, size_t, uint8_t *, size_t, uint8_t *, size_t, int) { NOT_YET(h, "sindyn_detect"); }
 extern "C" int sindyn_upload_frame(sindyn_handle h, int, const uint8_t *, size_t, const uint16_t *, size_t) { NOT_YET(h, "sindyn_upload_frame"); }
 extern "C" int sindyn_detect_resident(sindyn_handle h, int, int) { NOT_YET(h, "sindyn_detect_resident"); }
-extern "C" int sindyn_flow_branch(sindyn_handle h, const uint8_t *, size_t, float *, int *) { NOT_YET(h, "sindyn_flow_branch"); }
-extern "C" int sindyn_flow_refine(sindyn_handle h, const uint8_t *, const uint8_t *, int, int, float *) { NOT_YET(h, "sindyn_flow_refine"); }
-extern "C" int sindyn_estimate_homography(sindyn_handle h, const float *, double *, int *) { NOT_YET(h, "sindyn_estimate_homography"); }
-extern "C" int sindyn_sample_pairs(sindyn_handle h, const float *, float *, float *, int, int *) { NOT_YET(h, "sindyn_sample_pairs"); }
 extern "C" int sindyn_plane_edges(sindyn_handle h, const uint16_t *, size_t, uint8_t *) { NOT_YET(h, "sindyn_plane_edges"); }
 extern "C" int sindyn_filter_plane_edges(sindyn_handle h, const uint8_t *, const uint8_t *, const int *, int, uint8_t *, uint8_t *) { NOT_YET(h, "sindyn_filter_plane_edges"); }
 extern "C" int sindyn_recluster(sindyn_handle h, const uint8_t *, const uint8_t *, const uint16_t *, size_t, uint8_t *, int *) { NOT_YET(h, "sindyn_recluster"); }
