@@ -48,6 +48,7 @@ typedef struct sindyn_config {
     int device;                   /* CUDA device ordinal */
     int use_graphs;               /* 1 = replay captured CUDA graphs for the launch-bound stages */
     int plane_edges;              /* 1 = run the PEAC plane-edge stage (DynaDetect.cc:592-593) */
+    int stage_timing;             /* 1 = bracket every stage with CUDA events (sindyn_get_stage_ms) */
 } sindyn_config;
 
 void sindyn_default_config(sindyn_config *cfg, int width, int height);
@@ -80,10 +81,32 @@ int sindyn_detect(sindyn_handle h, const uint8_t *bgr, size_t bgr_step, const ui
 /* Device-resident variant used for kernel-only timing: frames are staged once into `slot`
  * (0 <= slot < SINDYN_MAX_SLOTS) and detect runs without host traffic; results stay on the
  * device until sindyn_get_buffer. */
-#define SINDYN_MAX_SLOTS 8
+#define SINDYN_MAX_SLOTS 32
 int sindyn_upload_frame(sindyn_handle h, int slot, const uint8_t *bgr, size_t bgr_step,
                         const uint16_t *depth, size_t depth_step);
 int sindyn_detect_resident(sindyn_handle h, int slot, int frame_idx);
+
+/* Replaces: DynaDetect::DetectDynaByDenseOpticalFLow(std::promise<stImgMasks>&)
+ * (include/DynaDetect.h:147, src/DynaDetect.cc:1023-1374): the flow branch the reference runs in its
+ * own std::thread -- gray/resize, Brox, large-motion test, refinement, up-sampling, sample weighting,
+ * homography, residual, Otsu/Triangle thresholds.  Returns stImgMasks (DynaDetect.h:16-30):
+ * mask_low (0/128) and mask_high (0/255), W x H u8 host buffers (either may be NULL).
+ * roll != 0 additionally rolls imgRGBLastLast <- imgRGBLast <- cur (DynaDetect.cc:1661-1662) so that a
+ * sequence can be streamed through this entry point alone (BASELINE config "flow + residual"). */
+int sindyn_flow_residual(sindyn_handle h, const uint8_t *bgr, size_t bgr_step, uint8_t *mask_low, uint8_t *mask_high, int roll);
+/* Same on a frame staged with sindyn_upload_frame: no host traffic, no synchronize except the
+ * large-motion decision (which the reference also takes on the host, DynaDetect.cc:1073-1114). */
+int sindyn_flow_residual_resident(sindyn_handle h, int slot, int roll);
+/* Copy out the device-resident results of the last flow_residual call (any pointer may be NULL):
+ * flow W x H x 2 float, H 3x3 double, thresholds[4], masks. */
+int sindyn_get_flow_results(sindyn_handle h, float *flow, double *H_out, float *thresholds, uint8_t *mask_low, uint8_t *mask_high,
+                            int *large_motion);
+
+/* Measurement hook (no reference equivalent): runs one Brox solve on the handle's resident frames
+ * WITHOUT the CUDA graph, bracketing every launch of the SOR kernel with CUDA events on the handle's
+ * stream.  out[0] = summed SOR-kernel ms, out[1] = number of SOR launches, out[2] = whole-solve ms,
+ * out[3] = pixel-levels processed (sum over launches of w*h). */
+int sindyn_brox_profile(sindyn_handle h, double *out4);
 
 /* Driver post-step: 15x15 ellipse dilation of the mask (rgbd_tum_noros.cc:108,136-139), and the
  * generic getStructuringElement(MORPH_ELLIPSE,k x k) morphology used throughout DynaDetect.cc:51-59.

@@ -709,3 +709,77 @@ def estimate_homography(pts, pts_last):
     """cv::findHomography(inputPoints, inputPointsLast, cv::noArray(), cv::RHO) (DynaDetect.cc:1235)."""
     Hm, _ = cv2.findHomography(pts, pts_last, cv2.RHO)
     return Hm
+
+
+# ----------------------------------------------------------------------------- CPU flow engines of the reference
+def variational_refine(I0_u8, I1_u8, flow):
+    """cv::VariationalRefinement::create()->calc(I0, I1, flow) with default parameters, in place on a copy
+    (DynaDetect.cc:1133-1143).  Executed by the real OpenCV (cv2.VariationalRefinement)."""
+    f = np.ascontiguousarray(flow, np.float32).copy()
+    cv2.VariationalRefinement_create().calc(I0_u8, I1_u8, f)
+    return f
+
+
+def deepflow_restated(I0_u8, I1_u8):
+    """cv::optflow::createOptFlow_DeepFlow()->calc(I0, I1, flow) (DynaDetect.cc:1031,1075) -- the reference's default
+    CPU flow.  opencv_contrib's optflow module is NOT in cv2-headless, so this restates its published structure
+    (optflow/src/deepflow.cpp, 4.x: sigma 0.6 pre-blur, pyramid factor 0.95 down to >= 25 px, per level
+    VariationalRefinement(alpha=4*1.0, delta=0.5/3, gamma=5.0/3, fixedPoint=5, sor=25, omega=1.6), bilinear
+    up-sampling / 0.95) around the real cv2.VariationalRefinement solver.  Used only as the timed CPU baseline
+    ("DeepFlow-restated") -- PARITY UNPINNED, never a parity oracle."""
+    sigma, min_size, factor = 0.6, 25, 0.95
+    a = cv2.GaussianBlur(I0_u8.astype(np.float32), (5, 5), sigma)
+    b = cv2.GaussianBlur(I1_u8.astype(np.float32), (5, 5), sigma)
+    pyr = [(a, b)]
+    while True:
+        h, w = pyr[-1][0].shape
+        nw, nh = int(w * factor), int(h * factor)
+        if min(nw, nh) < min_size:
+            break
+        pyr.append((cv2.resize(pyr[-1][0], (nw, nh), interpolation=cv2.INTER_LINEAR),
+                    cv2.resize(pyr[-1][1], (nw, nh), interpolation=cv2.INTER_LINEAR)))
+    vr = cv2.VariationalRefinement_create()
+    vr.setAlpha(4 * 1.0)
+    vr.setDelta(0.5 / 3)
+    vr.setGamma(5.0 / 3)
+    vr.setFixedPointIterations(5)
+    vr.setSorIterations(25)
+    vr.setOmega(1.6)
+    h, w = pyr[-1][0].shape
+    flow = np.zeros((h, w, 2), np.float32)
+    for lvl in range(len(pyr) - 1, -1, -1):
+        A, B = pyr[lvl]
+        h, w = A.shape
+        if flow.shape[:2] != (h, w):
+            flow = cv2.resize(flow, (w, h), interpolation=cv2.INTER_LINEAR) * np.float32(1.0 / factor)
+        flow = np.ascontiguousarray(flow)
+        vr.calc(A, B, flow)
+    return flow, len(pyr)
+
+
+def flow_residual_cpu(bgr_cur, bgr_last, bgr_lastlast, dyna_last, label_last, engine="brox", refine=True):
+    """DynaDetect::DetectDynaByDenseOpticalFLow (DynaDetect.cc:1023-1374) end to end on the CPU.
+    engine: 'brox' (USECUDA build's solver, oracle/brox_cpu.c) or 'deepflow' (default CPU build, restated).
+    Returns dict(low, high, thr, flow, H, large_motion)."""
+    H, W = bgr_cur.shape[:2]
+    g = [gray_small(bgr2gray(x)) for x in (bgr_cur, bgr_last, bgr_lastlast)]
+
+    def calc(i_ref):
+        if engine == "brox":
+            return brox_flow(g[0].astype(np.float32) * np.float32(1 / 255.0), g[i_ref].astype(np.float32) * np.float32(1 / 255.0))
+        return deepflow_restated(g[0], g[i_ref])[0]
+
+    flow = -calc(2)
+    lm, _, _ = flow_magnitude_hist_large_motion(flow, W, H)
+    i_ref = 2
+    if lm:
+        flow = -calc(1)
+        i_ref = 1
+    if refine:
+        flow = variational_refine(g[0], g[i_ref], flow)
+    full = upsample_flow(flow, W, H)
+    p, q = sample_pairs(full, dyna_last, label_last)
+    Hm = estimate_homography(p, q)
+    mag = homography_residual(full, Hm)
+    low, high, thr, _ = threshold_masks(mag)
+    return dict(low=low, high=high, thr=thr, flow=full, H=Hm, large_motion=bool(lm))

@@ -30,6 +30,7 @@ class Config(C.Structure):
         ("brox_omega", C.c_float), ("refine", C.c_int),
         ("n_row_cluster", C.c_int), ("n_col_cluster", C.c_int), ("depth_weight", C.c_float),
         ("device", C.c_int), ("use_graphs", C.c_int), ("plane_edges", C.c_int),
+        ("stage_timing", C.c_int),
     ]
 
 
@@ -55,6 +56,10 @@ SIGNATURES = {
     "sindyn_detect": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i]),
     "sindyn_upload_frame": (_i, [_vp, _i, _vp, _sz, _vp, _sz]),
     "sindyn_detect_resident": (_i, [_vp, _i, _i]),
+    "sindyn_flow_residual": (_i, [_vp, _vp, _sz, _vp, _vp, _i]),
+    "sindyn_flow_residual_resident": (_i, [_vp, _i, _i]),
+    "sindyn_get_flow_results": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ip]),
+    "sindyn_brox_profile": (_i, [_vp, _vp]),
     "sindyn_morph_ellipse": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _i, _i]),
     "sindyn_flow_brox": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "sindyn_gray_resize": (_i, [_vp, _vp, _sz, _vp, _vp]),
@@ -185,6 +190,32 @@ class SinDyn:
 
     def detect_resident(self, slot, frame_idx):
         self._ck(self.lib.sindyn_detect_resident(self.h, slot, frame_idx), "detect_resident")
+
+    def flow_residual(self, bgr, roll=True, low=None, high=None):
+        """DetectDynaByDenseOpticalFLow (DynaDetect.cc:1023-1374) -> (mask_low, mask_high)."""
+        bgr = _u8(bgr)
+        low = np.empty((self.H, self.W), np.uint8) if low is None else low
+        high = np.empty((self.H, self.W), np.uint8) if high is None else high
+        self._ck(self.lib.sindyn_flow_residual(self.h, _p(bgr), bgr.strides[0], _p(low), _p(high), int(roll)), "flow_residual")
+        return low, high
+
+    def flow_residual_resident(self, slot, roll=True):
+        self._ck(self.lib.sindyn_flow_residual_resident(self.h, slot, int(roll)), "flow_residual_resident")
+
+    def flow_results(self):
+        flow = np.empty((self.H, self.W, 2), np.float32)
+        Hm = np.empty((3, 3), np.float64)
+        thr = np.empty(4, np.float32)
+        lo = np.empty((self.H, self.W), np.uint8)
+        hi = np.empty((self.H, self.W), np.uint8)
+        lm = C.c_int(0)
+        self._ck(self.lib.sindyn_get_flow_results(self.h, _p(flow), _p(Hm), _p(thr), _p(lo), _p(hi), C.byref(lm)), "get_flow_results")
+        return dict(flow=flow, H=Hm, thr=thr, low=lo, high=hi, large_motion=bool(lm.value))
+
+    def brox_profile(self):
+        out = np.zeros(4, np.float64)
+        self._ck(self.lib.sindyn_brox_profile(self.h, _p(out)), "brox_profile")
+        return dict(sor_ms=float(out[0]), sor_launches=int(out[1]), solve_ms=float(out[2]), pixel_levels=int(out[3]))
 
     def morph_ellipse(self, img, k, op):
         img = _u8(img)

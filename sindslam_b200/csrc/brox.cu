@@ -357,7 +357,10 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
                 p.dui = b->du[in]; p.dvi = b->dv[in];
                 p.duo = b->du[out]; p.dvo = b->dv[out];
                 p.w = w; p.h = h; p.alpha = b->alpha; p.gamma = b->gamma; p.omega = b->omega; p.nsweeps = ns;
+                const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
+                if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
                 LAUNCH(ctx, k_brox_inner, tgrd, BROX_NT, BROX_SMEM, p);
+                if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h; }
                 in = out;
                 remaining -= ns;
             }

@@ -52,11 +52,15 @@ struct sindyn_ctx : sindyn_base {
     EdgeStage edges;
 
     float stage_ms[16] = {};
+    cudaEvent_t ev[24] = {};
+    bool ev_ok = false;
+    int large_motion_last = 0;
 };
 
 // internal cross-module helpers (C++ linkage)
 int sindyn_prep_frame(sindyn_ctx *c, int idx);          // api.cu: BGR -> gray -> 0.6x gray (u8 + float)
 int flow_branch_init(sindyn_ctx *c);                    // flow.cu
 int flow_branch_run(sindyn_ctx *c, int *large_motion);  // flow.cu
+int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll);  // pipeline.cu
 int sindyn_ctx_init_stages(sindyn_ctx *c);              // stages.cu
 void sindyn_ctx_destroy_stages(sindyn_ctx *c);          // stages.cu

@@ -73,6 +73,7 @@ int flow_branch_run(sindyn_ctx *c, int *large_motion)
     const bool g = c->cfg.use_graphs != 0;
     const int nf = c->fw * c->fh;
     SD_CHECK(brox_run(c, &c->brox, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_lastlast], c->flow_small, -1.0f, g));
+    if (c->cfg.stage_timing && c->ev_ok) CU_CHECK(c, cudaEventRecord(c->ev[2], c->stream));
     CU_CHECK(c, cudaMemsetAsync(c->fb_hist, 0, sizeof(unsigned int) * 260, c->stream));
     unsigned int *gmax = c->fb_hist + 256;
     LAUNCH(c, k_flow_mag, cdiv(nf, 256), 256, 0, (const float2 *)c->flow_small, nf, c->fb_mag, gmax);

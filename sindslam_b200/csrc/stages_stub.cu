@@ -6,7 +6,6 @@
 
 
 extern "C" int sindyn_detect(sindyn_handle h, const uint8_t *, size_t, const uint16_t *, size_t, uint8_t *, size_t, uint8_t *, size_t, int) { NOT_YET(h, "sindyn_detect"); }
-extern "C" int sindyn_upload_frame(sindyn_handle h, int, const uint8_t *, size_t, const uint16_t *, size_t) { NOT_YET(h, "sindyn_upload_frame"); }
 extern "C" int sindyn_detect_resident(sindyn_handle h, int, int) { NOT_YET(h, "sindyn_detect_resident"); }
 extern "C" int sindyn_plane_edges(sindyn_handle h, const uint16_t *, size_t, uint8_t *) { NOT_YET(h, "sindyn_plane_edges"); }
 extern "C" int sindyn_filter_plane_edges(sindyn_handle h, const uint8_t *, const uint8_t *, const int *, int, uint8_t *, uint8_t *) { NOT_YET(h, "sindyn_filter_plane_edges"); }

@@ -1,0 +1,66 @@
+"""GPU parity of the fused flow + residual branch (sindyn_flow_residual = DetectDynaByDenseOpticalFLow,
+DynaDetect.cc:1023-1374) against the CPU oracle, streamed over a short synthetic sequence."""
+import numpy as np
+import pytest
+
+from oracle import dynadetect_oracle as orc
+from sindslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FLOW_EPE_TOL = 0.08     # px at 640x480 (= 0.05 px on the 384x288 grid / 0.6), mean EPE GPU branch vs CPU branch
+MASK_IOU_MIN = 0.97     # masks from independently solved flows (GPU Brox vs CPU Brox); bit-exactness is checked below with identical flow
+
+
+def _iou(a, b):
+    a, b = a > 0, b > 0
+    u = (a | b).sum()
+    return 1.0 if u == 0 else float((a & b).sum()) / float(u)
+
+
+@pytest.mark.parametrize("refine", [0, 1])
+def test_flow_residual_stream(seq_c1, refine):
+    from sindslam_b200.capi import SinDyn
+    scene, frames = seq_c1
+    cam = synth.TUM3
+    sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, refine=refine, stage_timing=1)
+    sd.set_prev_frames(frames[1].bgr, frames[0].bgr)
+    z = np.zeros((cam.height, cam.width), np.uint8)
+    for k in range(2, 5):
+        lo, hi = sd.flow_residual(frames[k].bgr, roll=True)
+        res = sd.flow_results()
+        assert np.array_equal(lo, res["low"]) and np.array_equal(hi, res["high"])
+        ref = orc.flow_residual_cpu(frames[k].bgr, frames[k - 1].bgr, frames[k - 2].bgr, z, z, "brox", refine=bool(refine))
+        assert res["large_motion"] == ref["large_motion"]
+        epe = float(np.sqrt(((res["flow"] - ref["flow"]) ** 2).sum(-1)).mean())
+        print("frame %d refine %d: flow EPE %.4f, IoU low %.4f high %.4f, thr gpu %s cpu %s, stage ms %s" % (
+            k, refine, epe, _iou(lo, ref["low"]), _iou(hi, ref["high"]), res["thr"], ref["thr"], np.round(sd.stage_ms()[:5], 3)))
+        assert epe <= FLOW_EPE_TOL
+        assert _iou(lo, ref["low"]) >= MASK_IOU_MIN and _iou(hi, ref["high"]) >= MASK_IOU_MIN
+        # identical flow + identical H -> residual / thresholds / masks bit-exact
+        mag = orc.homography_residual(res["flow"], res["H"])
+        olo, ohi, othr, _ = orc.threshold_masks(mag)
+        assert np.array_equal(othr, res["thr"])
+        assert np.array_equal(lo, olo) and np.array_equal(hi, ohi)
+    sd.close()
+
+
+def test_resident_equals_host_path(seq_c1):
+    from sindslam_b200.capi import SinDyn
+    _, frames = seq_c1
+    cam = synth.TUM3
+    a = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, refine=0)
+    b = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, refine=0)
+    for s in (a, b):
+        s.set_prev_frames(frames[1].bgr, frames[0].bgr)
+    for i, f in enumerate(frames):
+        b.upload_frame(i, f.bgr, f.depth)
+    for k in range(2, 5):
+        lo, hi = a.flow_residual(frames[k].bgr, roll=True)
+        b.flow_residual_resident(k, roll=True)
+        r = b.flow_results()
+        assert np.array_equal(lo, r["low"]) and np.array_equal(hi, r["high"])
+    p = b.brox_profile()
+    assert p["sor_launches"] == 150 and p["pixel_levels"] == 10 * 308090 and p["sor_ms"] > 0
+    a.close()
+    b.close()
