@@ -85,6 +85,9 @@ int sindyn_detect(sindyn_handle h, const uint8_t *bgr, size_t bgr_step, const ui
 int sindyn_upload_frame(sindyn_handle h, int slot, const uint8_t *bgr, size_t bgr_step,
                         const uint16_t *depth, size_t depth_step);
 int sindyn_detect_resident(sindyn_handle h, int slot, int frame_idx);
+/* Copy out the device-resident results of the last detect call (either pointer may be NULL): mask / labels W x H u8.
+ * Synchronizes, checks the fixed-capacity lists and collects the per-stage timings. */
+int sindyn_get_detect_results(sindyn_handle h, uint8_t *mask, uint8_t *labels);
 
 /* Replaces: DynaDetect::DetectDynaByDenseOpticalFLow(std::promise<stImgMasks>&)
  * (include/DynaDetect.h:147, src/DynaDetect.cc:1023-1374): the flow branch the reference runs in its
@@ -187,6 +190,11 @@ int sindyn_filter_plane_edges(sindyn_handle h, const uint8_t *plane_edges, const
  * (0 = invalid, 1..n). */
 int sindyn_recluster(sindyn_handle h, const uint8_t *occluded1, const uint8_t *occluded2, const uint16_t *depth,
                      size_t depth_step, uint8_t *label_out, int *n_components_out);
+
+/* Test hook (no reference equivalent): RAG matrix of the last sindyn_recluster / sindyn_detect call
+ * (correlationMatrixTotal, DynaDetect.cc:894; (n+1)^2 floats in sorted-rank space) and per-component area / score /
+ * sorted order.  Returns the number of components n (>= 0) or a negative... status is never negative: returns n. */
+int sindyn_get_recluster_debug(sindyn_handle h, float *T_out, int t_capacity, int *area_out, float *score_out, int *order_out);
 
 /* Mask fusion + per-cluster decision + final mask (DynaDetect.cc:1553-1636) and state roll
  * (DynaDetect.cc:1660-1664).  Inputs injected: low (0/128), high (0/255), total_area, labels. */

@@ -783,3 +783,48 @@ def flow_residual_cpu(bgr_cur, bgr_last, bgr_lastlast, dyna_last, label_last, en
     mag = homography_residual(full, Hm)
     low, high, thr, _ = threshold_masks(mag)
     return dict(low=low, high=high, thr=thr, flow=full, H=Hm, large_motion=bool(lm))
+
+
+# ----------------------------------------------------------------------------- DetectDynaArea end to end
+class DynaDetectOracle:
+    """ORB_SLAM2::DynaDetect (DynaDetect.h:95-189): constructor state + DetectDynaArea (DynaDetect.cc:1377-1666)."""
+
+    def __init__(self, bgr_last, bgr_lastlast, fx, fy, cx, cy, depth_scale, plane_edges=False, engine="brox", refine=True):
+        H, W = bgr_last.shape[:2]
+        self.W, self.H = W, H
+        self.fx, self.fy, self.cx, self.cy, self.depth_scale = fx, fy, cx, cy, depth_scale
+        self.plane_edges, self.engine, self.refine = plane_edges, engine, refine
+        self.rgb_last, self.rgb_lastlast = bgr_last.copy(), bgr_lastlast.copy()
+        z = np.zeros((H, W), np.uint8)
+        self.dyna_last, self.high_last, self.label_last = z.copy(), z.copy(), z.copy()
+
+    def detect(self, bgr, depth, inject_masks=None):
+        """Returns dict(mask, label, + every intermediate).  inject_masks = (low, high): skip the flow branch and use
+        these masks instead (the authors' own identical-flow hook, DynaDetect.cc:1149-1158)."""
+        out = {}
+        if inject_masks is None:
+            fr = flow_residual_cpu(bgr, self.rgb_last, self.rgb_lastlast, self.dyna_last, self.label_last, self.engine, self.refine)
+            low, high = fr["low"], fr["high"]
+            out["flow"] = fr
+        else:
+            low, high = inject_masks
+        labels_km, points, centers = seg_by_kmeans(depth, self.label_last, self.fx, self.fy, self.cx, self.cy, self.depth_scale, "fx")
+        kept, seg, _ = cluster_order(labels_km, centers)
+        total_area, grad, ep = depth_edges(depth, self.depth_scale)
+        if self.plane_edges:
+            from oracle import peac_oracle
+            plane = peac_oracle.plane_edges(depth, self.fx, self.fy, self.cx, self.cy, self.depth_scale)
+        else:
+            plane = np.zeros_like(grad)
+        occl1, occl2 = filter_plane_edges(plane, grad, ep)
+        dbg = {}
+        labels = seg_and_merge_v2(kept, labels_km, occl1, occl2, seg, points, depth, debug=dbg)
+        dyna = dynamic_decide(low, high, self.high_last, total_area, labels)
+        out.update(mask=dyna, label=labels, low=low, high=high, labels_km=labels_km, kept=kept, seg=seg, total_area=total_area,
+                   grad=grad, endpoints=ep, plane=plane, occl1=occl1, occl2=occl2, rag=dbg)
+        # state roll (DynaDetect.cc:1660-1664)
+        self.dyna_last = dyna.copy()
+        self.rgb_lastlast, self.rgb_last = self.rgb_last, bgr.copy()
+        self.high_last = high.copy()
+        self.label_last = labels.copy()
+        return out

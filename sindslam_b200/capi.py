@@ -56,6 +56,8 @@ SIGNATURES = {
     "sindyn_detect": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i]),
     "sindyn_upload_frame": (_i, [_vp, _i, _vp, _sz, _vp, _sz]),
     "sindyn_detect_resident": (_i, [_vp, _i, _i]),
+    "sindyn_get_detect_results": (_i, [_vp, _vp, _vp]),
+    "sindyn_get_recluster_debug": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "sindyn_flow_residual": (_i, [_vp, _vp, _sz, _vp, _vp, _i]),
     "sindyn_flow_residual_resident": (_i, [_vp, _i, _i]),
     "sindyn_get_flow_results": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ip]),
@@ -190,6 +192,21 @@ class SinDyn:
 
     def detect_resident(self, slot, frame_idx):
         self._ck(self.lib.sindyn_detect_resident(self.h, slot, frame_idx), "detect_resident")
+
+    def detect_results(self):
+        mask = np.empty((self.H, self.W), np.uint8)
+        label = np.empty((self.H, self.W), np.uint8)
+        self._ck(self.lib.sindyn_get_detect_results(self.h, _p(mask), _p(label)), "get_detect_results")
+        return mask, label
+
+    def recluster_debug(self):
+        cap = 129 * 129
+        T = np.zeros(cap, np.float32)
+        area = np.zeros(128, np.int32)
+        score = np.zeros(128, np.float32)
+        order = np.zeros(128, np.int32)
+        n = self.lib.sindyn_get_recluster_debug(self.h, _p(T), cap, _p(area), _p(score), _p(order))
+        return dict(n=n, T=T[:(n + 1) * (n + 1)].reshape(n + 1, n + 1).copy(), area=area[:n].copy(), score=score[:n].copy(), order=order[:n].copy())
 
     def flow_residual(self, bgr, roll=True, low=None, high=None):
         """DetectDynaByDenseOpticalFLow (DynaDetect.cc:1023-1374) -> (mask_low, mask_high)."""

@@ -95,20 +95,26 @@ int ccl_run(sindyn_base *ctx, const uint8_t *cls, int *labels, int W, int H, int
     return SINDYN_OK;
 }
 
-__global__ void k_ccl_top(const int *__restrict__ labels, int *__restrict__ top, int W, int H, const int *__restrict__ active)
+__global__ void k_ccl_top(const int *__restrict__ labels, int *__restrict__ top, int W, int H, const int *__restrict__ active,
+                          RegionStats *__restrict__ zero_stats)
 {
     const int plane = blockIdx.z;
     if (active && plane >= *active) return;
     const int N = W * H;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    top[(size_t)plane * N + i] = rc_top(labels + (size_t)plane * (N + 1), N, W, i);
+    const int *L = labels + (size_t)plane * (N + 1);
+    int t = rc_top(L, N, W, i);
+    top[(size_t)plane * N + i] = t;
+    // statistics are accumulated only at region roots: clear those entries here instead of a full memset
+    if (zero_stats && L[i] == i) { RegionStats z; z.steps = 0; z.area2 = 0; zero_stats[(size_t)plane * N + i] = z; }
 }
 
-int ccl_top_image(sindyn_base *ctx, const int *labels, int *top, int W, int H, int planes, const int *active_planes)
+int ccl_top_image(sindyn_base *ctx, const int *labels, int *top, int W, int H, int planes, const int *active_planes,
+                  RegionStats *zero_stats)
 {
     dim3 g(cdiv(W * H, 256), 1, planes);
-    LAUNCH(ctx, k_ccl_top, g, 256, 0, labels, top, W, H, active_planes);
+    LAUNCH(ctx, k_ccl_top, g, 256, 0, labels, top, W, H, active_planes, zero_stats);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }

@@ -53,8 +53,9 @@ __device__ __forceinline__ int rc_top(const int *L, int N, int W, int p)
     return r;
 }
 
-// top[plane][p] = rc_top
-int ccl_top_image(sindyn_base *ctx, const int *labels, int *top, int W, int H, int planes, const int *active_planes);
+// top[plane][p] = rc_top; zero_stats (may be null): clears stats[plane][root] of every region root (fg and bg)
+int ccl_top_image(sindyn_base *ctx, const int *labels, int *top, int W, int H, int planes, const int *active_planes,
+                  RegionStats *zero_stats);
 
 // Quad statistics.
 //  mode 0 (EXTERNAL): stats of top-level filled components, indexed by their root; `top` from ccl_top_image.

@@ -3,11 +3,14 @@
 #pragma once
 #include "brox.cuh"
 #include "common.cuh"
+#include "decide.cuh"
 #include "edges.cuh"
 #include "homography.cuh"
 #include "kmeans.cuh"
 #include "morph.cuh"
+#include "peac.cuh"
 #include "preproc.cuh"
+#include "recluster.cuh"
 #include "residual.cuh"
 #include "varref.cuh"
 
@@ -50,6 +53,12 @@ struct sindyn_ctx : sindyn_base {
 
     KmeansStage km;
     EdgeStage edges;
+    PeacStage peac;
+    ReclusterStage rc;
+    DecideStage dd;
+    uint8_t *plane_edges = nullptr;   // imgEdgeByPlane (zeros when cfg.plane_edges == 0)
+    cudaStream_t stream2 = nullptr;   // clustering branch (the reference runs the flow branch in its own std::thread)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     float stage_ms[16] = {};
     cudaEvent_t ev[24] = {};

@@ -92,3 +92,59 @@ int morph_run(sindyn_base *ctx, const uint8_t *src, uint8_t *dst, uint8_t *tmp, 
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }
+
+// ------------------------------------------------------------------ bitset morphology
+__device__ __forceinline__ uint16_t b_or(uint16_t a, uint16_t b) { return a | b; }
+__device__ __forceinline__ uint16_t b_and(uint16_t a, uint16_t b) { return a & b; }
+__device__ __forceinline__ ulonglong2 b_or(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x | b.x, a.y | b.y); }
+__device__ __forceinline__ ulonglong2 b_and(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x & b.x, a.y & b.y); }
+template <class T> __device__ __forceinline__ T b_fill(bool ones);
+template <> __device__ __forceinline__ uint16_t b_fill<uint16_t>(bool ones) { return ones ? 0xFFFFu : 0u; }
+template <> __device__ __forceinline__ ulonglong2 b_fill<ulonglong2>(bool ones)
+{
+    return ones ? make_ulonglong2(~0ull, ~0ull) : make_ulonglong2(0ull, 0ull);
+}
+
+#define BT_W 32
+#define BT_H 8
+template <class T, bool ERODE>
+__global__ void __launch_bounds__(BT_W *BT_H) k_morph_bits(const T *__restrict__ src, T *__restrict__ dst, int W, int H, int k)
+{
+    __shared__ T tile[BT_H + MORPH_MAX_K][BT_W + MORPH_MAX_K];
+    const int a = k / 2;
+    const int x0 = blockIdx.x * BT_W - a, y0 = blockIdx.y * BT_H - a;
+    const int tw = BT_W + k - 1, th = BT_H + k - 1;
+    const T fill = b_fill<T>(ERODE);
+    for (int i = threadIdx.y * BT_W + threadIdx.x; i < tw * th; i += BT_W * BT_H) {
+        int ty = i / tw, tx = i - ty * tw;
+        int gx = x0 + tx, gy = y0 + ty;
+        tile[ty][tx] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? src[(size_t)gy * W + gx] : fill;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * BT_W + threadIdx.x, y = blockIdx.y * BT_H + threadIdx.y;
+    if (x >= W || y >= H) return;
+    T v = fill;
+    for (int i = 0; i < k; ++i) {
+        const int j1 = c_j1[k][i], j2 = c_j2[k][i];
+        for (int j = j1; j < j2; ++j) {
+            T t = tile[threadIdx.y + i][threadIdx.x + j];
+            v = ERODE ? b_and(v, t) : b_or(v, t);
+        }
+    }
+    dst[(size_t)y * W + x] = v;
+}
+
+int morph_bits_run(sindyn_base *ctx, const void *src, void *dst, int W, int H, int k, bool erode, int elem_bytes)
+{
+    if (k < 1 || k > MORPH_MAX_K || (elem_bytes != 2 && elem_bytes != 16)) { ctx->err = "morph_bits: bad arguments"; return SINDYN_ERR_INVALID; }
+    dim3 blk(BT_W, BT_H), grd(cdiv(W, BT_W), cdiv(H, BT_H));
+    if (elem_bytes == 2) {
+        if (erode) LAUNCH(ctx, (k_morph_bits<uint16_t, true>), grd, blk, 0, (const uint16_t *)src, (uint16_t *)dst, W, H, k);
+        else LAUNCH(ctx, (k_morph_bits<uint16_t, false>), grd, blk, 0, (const uint16_t *)src, (uint16_t *)dst, W, H, k);
+    } else {
+        if (erode) LAUNCH(ctx, (k_morph_bits<ulonglong2, true>), grd, blk, 0, (const ulonglong2 *)src, (ulonglong2 *)dst, W, H, k);
+        else LAUNCH(ctx, (k_morph_bits<ulonglong2, false>), grd, blk, 0, (const ulonglong2 *)src, (ulonglong2 *)dst, W, H, k);
+    }
+    LAUNCH_CHECK(ctx);
+    return SINDYN_OK;
+}

@@ -13,3 +13,8 @@ int morph_init(sindyn_base *ctx);
 int morph_run(sindyn_base *ctx, const uint8_t *src, uint8_t *dst, uint8_t *tmp, int W, int H, int k, int op);
 // host helper: row spans [j1, j2) of the k x k ellipse (the formula of cv::getStructuringElement)
 void ellipse_spans(int k, int *j1, int *j2);
+
+// Morphology on per-pixel membership BITSETS (bit c = "pixel belongs to image c"): dilate = OR, erode = AND over
+// the same elliptic structuring element, out-of-image samples ignored -- i.e. up to 16 / 128 of the reference's
+// per-cluster morphologyEx calls (DynaDetect.cc:671,683,688) in one pass.  elem_bytes = 2 (uint16_t) or 16 (ulonglong2).
+int morph_bits_run(sindyn_base *ctx, const void *src, void *dst, int W, int H, int k, bool erode, int elem_bytes);

@@ -11,9 +11,21 @@ int sindyn_ctx_init_stages(sindyn_ctx *c)
     SD_CHECK(morph_init(c));
     SD_CHECK(kmeans_init(c, &c->km, c->W, c->H));
     SD_CHECK(edges_init(c, &c->edges, c->W, c->H));
+    SD_CHECK(peac_init(c, &c->peac, c->W, c->H));
+    SD_CHECK(recluster_init(c, &c->rc, c->W, c->H));
+    SD_CHECK(decide_init(c, &c->dd, c->W, c->H));
+    SD_CHECK(c->dalloc(&c->plane_edges, (size_t)c->N));
+    CU_CHECK(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     return SINDYN_OK;
 }
-void sindyn_ctx_destroy_stages(sindyn_ctx *) {}
+void sindyn_ctx_destroy_stages(sindyn_ctx *c)
+{
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+}
 
 extern "C" int sindyn_morph_ellipse(sindyn_handle h, const uint8_t *src, size_t src_step, uint8_t *dst, size_t dst_step, int width,
                                     int height, int k, int op)

@@ -5,12 +5,6 @@
 #define NOT_YET(h, name) do { if (!(h)) return SINDYN_ERR_INVALID; (h)->err = name ": stage not built yet"; return SINDYN_ERR_STATE; } while (0)
 
 
-extern "C" int sindyn_detect(sindyn_handle h, const uint8_t *, size_t, const uint16_t *, size_t, uint8_t *, size_t, uint8_t *, size_t, int) { NOT_YET(h, "sindyn_detect"); }
-extern "C" int sindyn_detect_resident(sindyn_handle h, int, int) { NOT_YET(h, "sindyn_detect_resident"); }
-extern "C" int sindyn_plane_edges(sindyn_handle h, const uint16_t *, size_t, uint8_t *) { NOT_YET(h, "sindyn_plane_edges"); }
-extern "C" int sindyn_filter_plane_edges(sindyn_handle h, const uint8_t *, const uint8_t *, const int *, int, uint8_t *, uint8_t *) { NOT_YET(h, "sindyn_filter_plane_edges"); }
-extern "C" int sindyn_recluster(sindyn_handle h, const uint8_t *, const uint8_t *, const uint16_t *, size_t, uint8_t *, int *) { NOT_YET(h, "sindyn_recluster"); }
-extern "C" int sindyn_dynamic_decide(sindyn_handle h, const uint8_t *, const uint8_t *, const uint8_t *, const uint8_t *, uint8_t *) { NOT_YET(h, "sindyn_dynamic_decide"); }
 
 struct sindyn_orb : sindyn_base {};
 extern "C" int sindyn_orb_create(int, float, int, int, int, int, int, int, sindyn_orb_handle *) { return SINDYN_ERR_STATE; }
