@@ -230,6 +230,9 @@ int sindyn_orb_extract(sindyn_orb_handle h, const uint8_t *gray, size_t gray_ste
                        sindyn_keypoint *kps, uint8_t *desc, int capacity, int *n_out);
 /* mvImagePyramid[level] (include/ORBextractor.h:88): copies level image (without the 19-px pad). */
 int sindyn_orb_get_pyramid_level(sindyn_orb_handle h, int level, uint8_t *out, int *w_out, int *h_out);
+/* Test hook: FAST candidates of one level after the last extract, in distribution order (vToDistributeKeys,
+ * ORBextractor.cc:820-825): xyr = n x 3 ints (x, y relative to minBorder, response). */
+int sindyn_orb_get_candidates(sindyn_orb_handle h, int level, int *xyr, int capacity, int *n_out);
 int sindyn_orb_set_stream(sindyn_orb_handle h, void *cuda_stream);
 unsigned long long sindyn_orb_launch_count(sindyn_orb_handle h);
 const char *sindyn_orb_last_error(sindyn_orb_handle h);

@@ -85,6 +85,7 @@ SIGNATURES = {
     "sindyn_orb_destroy": (_i, [_vp]),
     "sindyn_orb_extract": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _i, _ip]),
     "sindyn_orb_get_pyramid_level": (_i, [_vp, _i, _vp, _ip, _ip]),
+    "sindyn_orb_get_candidates": (_i, [_vp, _i, _vp, _i, _ip]),
     "sindyn_orb_set_stream": (_i, [_vp, _vp]),
     "sindyn_orb_launch_count": (C.c_ulonglong, [_vp]),
     "sindyn_orb_last_error": (C.c_char_p, [_vp]),
@@ -411,6 +412,14 @@ class Orb:
             raise SindynError(f"orb_extract: {STATUS.get(st, st)}: {self.lib.sindyn_orb_last_error(self.h).decode()}")
         arr = np.frombuffer(kps, dtype=np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")]))[:n.value].copy()
         return arr, desc[:n.value].copy()
+
+    def candidates(self, level, capacity=16384):
+        buf = np.zeros((capacity, 3), np.int32)
+        n = C.c_int(0)
+        st = self.lib.sindyn_orb_get_candidates(self.h, level, _p(buf), capacity, C.byref(n))
+        if st != 0:
+            raise SindynError("orb candidates")
+        return buf[:n.value].copy()
 
     def pyramid_level(self, level):
         out = np.zeros(self.W * self.H, np.uint8)

@@ -1,0 +1,798 @@
+// orb.cu -- the masked ORB extractor of SInDSLAM (ORB_SLAM2::ORBextractor, ORB_SLAM2/src/ORBextractor.cc,
+// include/ORBextractor.h) as sm_100a kernels behind the C ABI of include/sindyn.h:
+//   pyramid (8 levels, OpenCV-exact u8 bilinear, +19 px REFLECT_101)            ORBextractor.cc:1166-1191
+//   FAST-9/16 score map, per-cell two-threshold detection with in-window NMS    :765-829
+//   quadtree distribution (one CTA per level, list order emulated in shared memory) :481-763
+//   intensity-centroid orientation (one warp per keypoint, fastAtan2 polynomial)    :77-104
+//   dynamic-mask erasure with the < 250 fallback                                    :1058-1116
+//   7x7 sigma-2 Gaussian blur (fixed point, exact) + 256-bit steered BRIEF          :108-147,1135-1151
+// All control (counts, offsets, list surgery) stays on the device; the host reads back one counter.
+#include "common.cuh"
+#include "preproc.cuh"
+
+#include <math.h>
+
+#define ORB_MAX_LEVELS 12
+#define ORB_EDGE 19              // EDGE_THRESHOLD
+#define ORB_HALF_PATCH 15
+#define ORB_KMAX 16384           // FAST candidates per level handled by the quadtree
+#define ORB_NODES 4096           // quadtree node pool per level
+#define ORB_MAX_CELLS 2048       // cells per level
+#define ORB_OUT_MAX 8192         // keypoints over all levels
+
+__constant__ signed char c_orb_pattern[256 * 4] = {
+#include "orb_pattern.inc"
+};
+__constant__ int c_umax[ORB_HALF_PATCH + 1];
+
+struct OrbLevel {
+    int w, h, pitch;             // unpadded size, padded row pitch (w + 38)
+    size_t pad_off;              // offset of the padded image inside pyr
+    size_t img_off;              // offset of the unpadded planes (score / blurred)
+    int min_b, max_bx, max_by;   // minBorder = 16, maxBorder = size - 16
+    int n_cols, n_rows, w_cell, h_cell, cell_off;
+    int quota;                   // mnFeaturesPerLevel
+    float scale, mask_scale, size;
+};
+
+struct OrbCand { unsigned short x, y; unsigned short resp, pad; };   // relative to minBorder
+
+struct OrbKp { float x, y, angle, resp; int level; int keep; };
+
+struct OrbControl {
+    int cand_count[ORB_MAX_LEVELS];
+    int kp_count[ORB_MAX_LEVELS];
+    int overflow;
+    int n_out, n_total;
+};
+
+struct sindyn_orb : sindyn_base {
+    int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0, W = 0, H = 0;
+    float scale_factor = 0.f;
+    OrbLevel lv[ORB_MAX_LEVELS];
+    OrbLevel *lv_dev = nullptr;
+    ResizePlanU8 plan[ORB_MAX_LEVELS];
+    uint8_t *pyr = nullptr, *score = nullptr, *blur = nullptr, *mask = nullptr;
+    int *cell_count = nullptr, *cell_offs = nullptr;    // nlevels x ORB_MAX_CELLS
+    OrbCand *cand = nullptr;                            // nlevels x ORB_KMAX
+    OrbKp *kps = nullptr, *out = nullptr;               // nlevels x ORB_NODES ; ORB_OUT_MAX
+    uint8_t *desc = nullptr;
+    sindyn_keypoint *out_host_fmt = nullptr;
+    OrbControl *ctl = nullptr, *ctl_host = nullptr;
+    size_t pad_total = 0, img_total = 0;
+};
+
+// ------------------------------------------------------------------ pyramid
+__global__ void k_orb_pad(uint8_t *__restrict__ pad, int w, int h, int pitch)
+{
+    // fill the 19-px frame of a padded level from its interior (BORDER_REFLECT_101)
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int pw = w + 2 * ORB_EDGE, ph = h + 2 * ORB_EDGE;
+    if (x >= pw || y >= ph) return;
+    int sx = x - ORB_EDGE, sy = y - ORB_EDGE;
+    if (sx >= 0 && sx < w && sy >= 0 && sy < h) return;
+    sx = sx < 0 ? -sx : (sx >= w ? 2 * w - 2 - sx : sx);
+    sy = sy < 0 ? -sy : (sy >= h ? 2 * h - 2 - sy : sy);
+    pad[(size_t)y * pitch + x] = pad[(size_t)(sy + ORB_EDGE) * pitch + sx + ORB_EDGE];
+}
+
+// ------------------------------------------------------------------ FAST-9/16 score
+__global__ void k_orb_fast_score(const uint8_t *__restrict__ pad, int w, int h, int pitch, uint8_t *__restrict__ score)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t *c = pad + (size_t)(y + ORB_EDGE) * pitch + x + ORB_EDGE;
+    const int v = c[0];
+    const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    int d[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = v - (int)c[dy[k] * pitch + dx[k]];
+    // quick reject: a 9-arc always contains one of each opposite pair at distance 8
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        int mn = d[k], mx = d[k];
+#pragma unroll
+        for (int j = 1; j < 9; ++j) { int t = d[(k + j) & 15]; mn = min(mn, t); mx = max(mx, t); }
+        best = max(best, max(mn, -mx));
+    }
+    score[(size_t)y * w + x] = (uint8_t)best;
+}
+
+// One CTA per cell window (ORBextractor.cc:787-828).  WRITE = false: count; WRITE = true: emit in raster order.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_orb_cells(const uint8_t *__restrict__ score_all, const OrbLevel *__restrict__ lvs, int level, int ini_th,
+                                                   int min_th, int *__restrict__ cell_count, const int *__restrict__ cell_offs,
+                                                   OrbCand *__restrict__ cand_all, OrbControl *ctl)
+{
+    const OrbLevel L = lvs[level];
+    const int j = blockIdx.x, i = blockIdx.y;
+    const int cell = i * L.n_cols + j;
+    int *my_count = cell_count + level * ORB_MAX_CELLS + cell;
+    const float iniY = (float)(L.min_b + i * L.h_cell), iniX = (float)(L.min_b + j * L.w_cell);
+    float maxY = iniY + (float)L.h_cell + 6.0f, maxX = iniX + (float)L.w_cell + 6.0f;
+    const bool skip = iniY >= (float)(L.max_by - 3) || iniX >= (float)(L.max_bx - 6);
+    if (skip) { if (!WRITE && threadIdx.x == 0) *my_count = 0; return; }
+    if (maxY > (float)L.max_by) maxY = (float)L.max_by;
+    if (maxX > (float)L.max_bx) maxX = (float)L.max_bx;
+    const int x0 = (int)iniX, y0 = (int)iniY, x1 = (int)maxX, y1 = (int)maxY;
+    const int ww = x1 - x0, wh = y1 - y0;          // window size (<= 64 x 64)
+    __shared__ uint8_t s[66][68];
+    __shared__ int s_cnt[2];
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const uint8_t *score = score_all + L.img_off;
+    // scores of the window interior (3-px margin), zero elsewhere, with a 1-px zero ring for the NMS
+    for (int t = threadIdx.x; t < (wh + 2) * (ww + 2); t += 256) {
+        const int ty = t / (ww + 2), tx = t - ty * (ww + 2);
+        const int lx = tx - 1, ly = ty - 1;
+        uint8_t v = 0;
+        if (lx >= 3 && lx < ww - 3 && ly >= 3 && ly < wh - 3) v = score[(size_t)(y0 + ly) * L.w + x0 + lx];
+        s[ty][tx] = v;
+    }
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    auto is_kp = [&](int lx, int ly, int th) -> bool {
+        const int v = s[ly + 1][lx + 1];
+        if (v <= th) return false;
+        // strict maximum over the 8 neighbours; neighbours that are not corners at this threshold count as 0 < v
+        return v > s[ly][lx] && v > s[ly][lx + 1] && v > s[ly][lx + 2] && v > s[ly + 1][lx] && v > s[ly + 1][lx + 2] &&
+               v > s[ly + 2][lx] && v > s[ly + 2][lx + 1] && v > s[ly + 2][lx + 2];
+    };
+    const int npx = ww * wh;
+    int c0 = 0, c1 = 0;
+    for (int t = threadIdx.x; t < npx; t += 256) {
+        const int ly = t / ww, lx = t - ly * ww;
+        c0 += is_kp(lx, ly, ini_th);
+        c1 += is_kp(lx, ly, min_th);
+    }
+    if (c0) atomicAdd(&s_cnt[0], c0);
+    if (c1) atomicAdd(&s_cnt[1], c1);
+    __syncthreads();
+    const int th = s_cnt[0] > 0 ? ini_th : min_th;
+    const int total = s_cnt[0] > 0 ? s_cnt[0] : s_cnt[1];
+    if (!WRITE) { if (threadIdx.x == 0) *my_count = total; return; }
+    if (total == 0) return;
+    const int base0 = cell_offs[level * ORB_MAX_CELLS + cell];
+    OrbCand *out = cand_all + (size_t)level * ORB_KMAX;
+    if (threadIdx.x == 0) s_base = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t0 = 0; t0 < npx; t0 += 256) {
+        __syncthreads();
+        const int t = t0 + threadIdx.x;
+        bool f = false;
+        int lx = 0, ly = 0;
+        if (t < npx) { ly = t / ww; lx = t - ly * ww; f = is_kp(lx, ly, th); }
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, tile_total = 0;
+        for (int k = 0; k < 8; ++k) { if (k < warp) before += s_warp[k]; tile_total += s_warp[k]; }
+        const int pos = base0 + s_base + before + __popc(m & ((1u << lane) - 1u));
+        if (f) {
+            if (pos < ORB_KMAX) {
+                OrbCand c;
+                c.x = (unsigned short)(x0 + lx - L.min_b);
+                c.y = (unsigned short)(y0 + ly - L.min_b);
+                c.resp = (unsigned short)(s[ly + 1][lx + 1] - 1);
+                c.pad = 0;
+                out[pos] = c;
+            } else ctl->overflow = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tile_total;
+    }
+}
+
+// exclusive scan of the cell counts of every level (one CTA per level)
+__global__ void k_orb_cell_scan(const OrbLevel *__restrict__ lvs, const int *__restrict__ cell_count, int *__restrict__ cell_offs, OrbControl *ctl)
+{
+    const int level = blockIdx.x;
+    const OrbLevel L = lvs[level];
+    const int n = L.n_cols * L.n_rows;
+    __shared__ int s_part[256];
+    const int per = (n + 255) / 256;
+    int sum = 0;
+    for (int k = 0; k < per; ++k) { int idx = threadIdx.x * per + k; if (idx < n) sum += cell_count[level * ORB_MAX_CELLS + idx]; }
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    int base = 0;
+    for (int k = 0; k < threadIdx.x; ++k) base += s_part[k];
+    for (int k = 0; k < per; ++k) {
+        int idx = threadIdx.x * per + k;
+        if (idx < n) { cell_offs[level * ORB_MAX_CELLS + idx] = base; base += cell_count[level * ORB_MAX_CELLS + idx]; }
+    }
+    if (threadIdx.x == 255) {
+        ctl->cand_count[level] = base > ORB_KMAX ? ORB_KMAX : base;
+        if (base > ORB_KMAX) ctl->overflow = 1;
+    }
+}
+
+// ------------------------------------------------------------------ quadtree (DistributeOctTree)
+struct QNode { short x0, y0, x1, y1; unsigned short prev, next, cbase; unsigned short flags; int count; };
+#define QN_NONE 0xFFFFu
+#define QF_NOMORE 1u
+#define QF_MARK 2u      // considered for division in the current batch
+#define QF_DIVIDED 4u   // actually divided in the current batch
+
+struct QState {
+    int head, tail, size, n_nodes, overflow;
+    int n_batch;
+};
+
+__device__ __forceinline__ int q_quadrant(const QNode &p, int kx, int ky)
+{
+    // DivideNode (ORBextractor.cc:481-537): halfX = ceil((UR.x - UL.x) / 2), halfY = ceil((BR.y - UL.y) / 2)
+    const int mx = p.x0 + (int)ceilf((float)(p.x1 - p.x0) / 2.0f), my = p.y0 + (int)ceilf((float)(p.y1 - p.y0) / 2.0f);
+    return kx < mx ? (ky < my ? 0 : 2) : (ky < my ? 1 : 3);
+}
+
+__global__ void __launch_bounds__(512) k_orb_quadtree(const OrbLevel *__restrict__ lvs, const OrbCand *__restrict__ cand_all, OrbControl *ctl,
+                                                      OrbKp *__restrict__ kps_all)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int level = blockIdx.x;
+    const OrbLevel L = lvs[level];
+    const int K = ctl->cand_count[level];
+    const int N = L.quota;
+    QNode *nodes = (QNode *)smem_raw;                                   // ORB_NODES
+    unsigned short *knode = (unsigned short *)(nodes + ORB_NODES);      // ORB_KMAX
+    unsigned int *kxy = (unsigned int *)(knode + ORB_KMAX);             // ORB_KMAX  (y << 16 | x)
+    unsigned int *best = (unsigned int *)(kxy + ORB_KMAX);              // ORB_NODES
+    unsigned short *batch = (unsigned short *)(best + ORB_NODES);       // ORB_NODES: vSizeAndPointerToNode
+    unsigned short *batch2 = batch + ORB_NODES;
+    __shared__ QState st;
+    const OrbCand *cand = cand_all + (size_t)level * ORB_KMAX;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    OrbKp *kps = kps_all + (size_t)level * ORB_NODES;
+
+    // ---- initial nodes (ORBextractor.cc:543-584)
+    const int dx = L.max_bx - L.min_b, dy = L.max_by - L.min_b;
+    const int nIni = (int)roundf((float)dx / (float)dy);
+    const float hX = (float)dx / (float)nIni;
+    if (tid == 0) {
+        st.head = QN_NONE; st.tail = QN_NONE; st.size = 0; st.n_nodes = nIni; st.overflow = 0; st.n_batch = 0;
+        for (int i = 0; i < nIni; ++i) {
+            QNode n;
+            n.x0 = (short)(int)(hX * (float)i); n.x1 = (short)(int)(hX * (float)(i + 1)); n.y0 = 0; n.y1 = (short)dy;
+            n.prev = n.next = QN_NONE; n.cbase = 0; n.flags = 0; n.count = 0;
+            nodes[i] = n;
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) {
+        const OrbCand c = cand[k];
+        int ni = (int)((float)c.x / hX);
+        ni = ni < nIni ? ni : nIni - 1;
+        knode[k] = (unsigned short)ni;
+        kxy[k] = ((unsigned int)c.y << 16) | c.x;
+        atomicAdd(&nodes[ni].count, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 0; i < nIni; ++i) {             // push_back order; empty nodes are erased
+            if (nodes[i].count == 0) continue;
+            if (nodes[i].count == 1) nodes[i].flags = QF_NOMORE;
+            nodes[i].prev = (unsigned short)st.tail; nodes[i].next = QN_NONE;
+            if (st.tail != (int)QN_NONE) nodes[st.tail].next = (unsigned short)i; else st.head = i;
+            st.tail = i;
+            ++st.size;
+        }
+    }
+    __syncthreads();
+
+    // list helpers (thread 0 only)
+    auto push_front = [&](int id) {
+        nodes[id].prev = QN_NONE; nodes[id].next = (unsigned short)st.head;
+        if (st.head != (int)QN_NONE) nodes[st.head].prev = (unsigned short)id; else st.tail = id;
+        st.head = id; ++st.size;
+    };
+    auto erase = [&](int id) {
+        const int p = nodes[id].prev, n = nodes[id].next;
+        if (p != (int)QN_NONE) nodes[p].next = (unsigned short)n; else st.head = n;
+        if (n != (int)QN_NONE) nodes[n].prev = (unsigned short)p; else st.tail = p;
+        --st.size;
+    };
+    // allocate the four children of `id` (geometry only; counts are filled by the parallel pass)
+    auto alloc_children = [&](int id) -> bool {
+        if (st.n_nodes + 4 > ORB_NODES) { st.overflow = 1; return false; }
+        const QNode p = nodes[id];
+        const int hx = (int)ceilf((float)(p.x1 - p.x0) / 2.0f), hy = (int)ceilf((float)(p.y1 - p.y0) / 2.0f);
+        const int cb = st.n_nodes;
+        st.n_nodes += 4;
+        for (int q = 0; q < 4; ++q) {
+            QNode c;
+            c.x0 = (short)((q & 1) ? p.x0 + hx : p.x0); c.x1 = (short)((q & 1) ? p.x1 : p.x0 + hx);
+            c.y0 = (short)((q & 2) ? p.y0 + hy : p.y0); c.y1 = (short)((q & 2) ? p.y1 : p.y0 + hy);
+            c.prev = c.next = QN_NONE; c.cbase = 0; c.flags = 0; c.count = 0;
+            nodes[cb + q] = c;
+        }
+        nodes[id].cbase = (unsigned short)cb;
+        nodes[id].flags |= QF_MARK;
+        return true;
+    };
+    // parallel passes over the keys
+    auto count_children = [&]() {
+        for (int k = tid; k < K; k += nt) {
+            const QNode p = nodes[knode[k]];
+            if (p.flags & QF_MARK) atomicAdd(&nodes[p.cbase + q_quadrant(p, kxy[k] & 0xffff, kxy[k] >> 16)].count, 1);
+        }
+    };
+    auto move_keys = [&]() {
+        for (int k = tid; k < K; k += nt) {
+            const QNode p = nodes[knode[k]];
+            if (p.flags & QF_DIVIDED) knode[k] = (unsigned short)(p.cbase + q_quadrant(p, kxy[k] & 0xffff, kxy[k] >> 16));
+        }
+    };
+
+    __shared__ int s_finish, s_phase2, s_nexp, s_prev;
+    if (tid == 0) { s_finish = 0; s_phase2 = 0; }
+    __syncthreads();
+    while (!s_finish && !st.overflow) {
+        // ---- phase 1 pass: divide every node that holds more than one key (ORBextractor.cc:603-663)
+        if (tid == 0) {
+            s_prev = st.size;
+            for (int id = st.head; id != (int)QN_NONE; id = nodes[id].next)
+                if (!(nodes[id].flags & QF_NOMORE)) { if (!alloc_children(id)) break; }
+        }
+        __syncthreads();
+        count_children();
+        __syncthreads();
+        if (tid == 0) {
+            int nexp = 0, nb = 0;
+            int id = st.head;
+            while (id != (int)QN_NONE) {
+                const int nx = nodes[id].next;
+                if (nodes[id].flags & QF_MARK) {
+                    const int cb = nodes[id].cbase;
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = cb + q;
+                        if (nodes[c].count > 0) {
+                            push_front(c);
+                            if (nodes[c].count > 1) { ++nexp; batch[nb++] = (unsigned short)c; }
+                            else nodes[c].flags = QF_NOMORE;
+                        }
+                    }
+                    erase(id);
+                    nodes[id].flags = (nodes[id].flags & ~QF_MARK) | QF_DIVIDED;
+                }
+                id = nx;
+            }
+            s_nexp = nexp; st.n_batch = nb;
+        }
+        __syncthreads();
+        move_keys();
+        __syncthreads();
+        for (int i = tid; i < st.n_nodes; i += nt) nodes[i].flags &= ~(QF_MARK | QF_DIVIDED);
+        if (tid == 0) {
+            if (st.size >= N || st.size == s_prev) s_finish = 1;
+            else if (st.size + s_nexp * 3 > N) s_phase2 = 1;
+        }
+        __syncthreads();
+        // ---- phase 2: expand the largest nodes first until N is reached (ORBextractor.cc:671-735)
+        while (s_phase2 && !s_finish && !st.overflow) {
+            const int nb = st.n_batch;
+            // sort (size, creation order) ascending, walk from the end = descending
+            for (int a = tid; a < nb; a += nt) {
+                const int ia = batch[a];
+                const long long ka = ((long long)nodes[ia].count << 16) | ia;
+                int rank = 0;
+                for (int b = 0; b < nb; ++b) { const int ib = batch[b]; rank += ((((long long)nodes[ib].count << 16) | ib) > ka); }
+                batch2[rank] = (unsigned short)ia;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                s_prev = st.size;
+                for (int a = 0; a < nb; ++a) if (!alloc_children(batch2[a])) break;
+            }
+            __syncthreads();
+            count_children();
+            __syncthreads();
+            if (tid == 0) {
+                int nb2 = 0;
+                for (int a = 0; a < nb; ++a) {
+                    const int id = batch2[a];
+                    if (!(nodes[id].flags & QF_MARK)) break;
+                    const int cb = nodes[id].cbase;
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = cb + q;
+                        if (nodes[c].count > 0) {
+                            push_front(c);
+                            if (nodes[c].count > 1) batch[nb2++] = (unsigned short)c;
+                            else nodes[c].flags = QF_NOMORE;
+                        }
+                    }
+                    erase(id);
+                    nodes[id].flags |= QF_DIVIDED;
+                    if (st.size >= N) break;
+                }
+                st.n_batch = nb2;
+            }
+            __syncthreads();
+            move_keys();
+            __syncthreads();
+            for (int i = tid; i < st.n_nodes; i += nt) nodes[i].flags &= ~(QF_MARK | QF_DIVIDED);
+            if (tid == 0 && (st.size >= N || st.size == s_prev)) s_finish = 1;
+            __syncthreads();
+        }
+    }
+    // ---- best response per node, first maximum in candidate order (ORBextractor.cc:738-760)
+    for (int i = tid; i < st.n_nodes; i += nt) best[i] = 0u;
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) atomicMax(&best[knode[k]], ((unsigned int)cand[k].resp << 14) | (unsigned int)(ORB_KMAX - 1 - k));
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int id = st.head; id != (int)QN_NONE; id = nodes[id].next) batch[n++] = (unsigned short)id;
+        ctl->kp_count[level] = n;
+        if (st.overflow) ctl->overflow = 1;
+        st.n_batch = n;
+    }
+    __syncthreads();
+    for (int i = tid; i < st.n_batch; i += nt) {
+        const int k = ORB_KMAX - 1 - (int)(best[batch[i]] & (ORB_KMAX - 1));
+        const OrbCand c = cand[k];
+        OrbKp o;
+        o.x = (float)(c.x + L.min_b); o.y = (float)(c.y + L.min_b);   // keypoints[i].pt += minBorder (ORBextractor.cc:842-843)
+        o.angle = 0.f; o.resp = (float)c.resp; o.level = level; o.keep = 1;
+        kps[i] = o;
+    }
+}
+
+// ------------------------------------------------------------------ orientation (IC_Angle) + mask test
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    // cv::fastAtan2
+    const float p1 = 0.9997878412794807f * 57.29577951308232f, p3 = -0.3258083974640975f * 57.29577951308232f;
+    const float p5 = 0.1555786518463281f * 57.29577951308232f, p7 = -0.04432655554792128f * 57.29577951308232f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + 2.220446049250313e-16f);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + 2.220446049250313e-16f);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+__global__ void k_orb_orient(const uint8_t *__restrict__ pyr, const OrbLevel *__restrict__ lvs, const OrbControl *__restrict__ ctl,
+                             OrbKp *__restrict__ kps_all, const uint8_t *__restrict__ mask, int mask_w)
+{
+    const int level = blockIdx.y;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= ctl->kp_count[level]) return;
+    const OrbLevel L = lvs[level];
+    OrbKp *kp = kps_all + (size_t)level * ORB_NODES + warp;
+    const int cx = __float2int_rn(kp->x), cy = __float2int_rn(kp->y);
+    const uint8_t *center = pyr + L.pad_off + (size_t)(cy + ORB_EDGE) * L.pitch + cx + ORB_EDGE;
+    int m01 = 0, m10 = 0;
+    const int u = lane - ORB_HALF_PATCH;
+    if (lane < 31) {
+        m10 = u * (int)center[u];
+        for (int v = 1; v <= ORB_HALF_PATCH; ++v) {
+            if (u >= -c_umax[v] && u <= c_umax[v]) {
+                const int vp = center[u + v * L.pitch], vm = center[u - v * L.pitch];
+                m01 += v * (vp - vm);
+                m10 += u * (vp + vm);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { m01 += __shfl_xor_sync(0xffffffffu, m01, o); m10 += __shfl_xor_sync(0xffffffffu, m10, o); }
+    if (lane == 0) {
+        kp->angle = fast_atan2_deg((float)m01, (float)m10);
+        int keep = 1;
+        if (mask) {   // DynaMask.at<uchar>(pt.y * scale, pt.x * scale) == 255 (ORBextractor.cc:1073-1075)
+            const int my = (int)(kp->y * L.mask_scale), mx = (int)(kp->x * L.mask_scale);
+            keep = mask[(size_t)my * mask_w + mx] != 255;
+        }
+        kp->keep = keep;
+    }
+}
+
+// erase + "< 250 -> restore" + level-ordered output (ORBextractor.cc:1063-1116,1154-1162); single CTA
+__global__ void __launch_bounds__(1024) k_orb_select(const OrbLevel *__restrict__ lvs, int nlevels, OrbControl *ctl, const OrbKp *__restrict__ kps_all,
+                                                     OrbKp *__restrict__ out)
+{
+    __shared__ int s_kept, s_total, s_base;
+    __shared__ int s_warp[32];
+    if (threadIdx.x == 0) { s_kept = 0; s_total = 0; s_base = 0; }
+    __syncthreads();
+    int kept = 0, total = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        const int n = ctl->kp_count[l];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { kept += kps_all[(size_t)l * ORB_NODES + i].keep; ++total; }
+    }
+    if (kept) atomicAdd(&s_kept, kept);
+    if (total) atomicAdd(&s_total, total);
+    __syncthreads();
+    const bool all = s_kept < 250;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int l = 0; l < nlevels; ++l) {
+        const int n = ctl->kp_count[l];
+        const float sc = lvs[l].scale;
+        for (int t0 = 0; t0 < n; t0 += blockDim.x) {
+            __syncthreads();
+            const int i = t0 + threadIdx.x;
+            OrbKp k;
+            bool f = false;
+            if (i < n) { k = kps_all[(size_t)l * ORB_NODES + i]; f = all || k.keep; }
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) s_warp[warp] = __popc(m);
+            __syncthreads();
+            int before = 0, tile = 0;
+            for (int w = 0; w < 32; ++w) { if (w < warp) before += s_warp[w]; tile += s_warp[w]; }
+            const int pos = s_base + before + __popc(m & ((1u << lane) - 1u));
+            if (f) { if (pos < ORB_OUT_MAX) out[pos] = k; else ctl->overflow = 1; }
+            (void)sc;
+            __syncthreads();
+            if (threadIdx.x == 0) s_base += tile;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { ctl->n_out = s_base > ORB_OUT_MAX ? ORB_OUT_MAX : s_base; ctl->n_total = s_total; }
+}
+
+// ------------------------------------------------------------------ blur + descriptors
+// GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) on u8: kernel [18 34 48 56 48 34 18]/256,
+// horizontal 8.8 fixed point, vertical 16.16, (v + 32768) >> 16.  Reads the padded level (its frame IS the reflection).
+__global__ void k_orb_blur(const uint8_t *__restrict__ pad, int w, int h, int pitch, uint8_t *__restrict__ dst)
+{
+    __shared__ int hs[8 + 6][32];
+    const int kx[7] = {18, 34, 48, 56, 48, 34, 18};
+    const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 8;
+    for (int r = threadIdx.y; r < 14; r += 8) {
+        const int y = y0 + r - 3;
+        int acc = 0;
+        if (x < w && y >= -ORB_EDGE && y < h + ORB_EDGE) {
+            const uint8_t *row = pad + (size_t)(y + ORB_EDGE) * pitch + x + ORB_EDGE;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) acc += kx[k] * (int)row[k - 3];
+        }
+        hs[r][threadIdx.x] = acc;
+    }
+    __syncthreads();
+    const int y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v += kx[k] * hs[threadIdx.y + k][threadIdx.x];
+    dst[(size_t)y * w + x] = (uint8_t)((v + 32768) >> 16);
+}
+
+// computeOrbDescriptor (ORBextractor.cc:108-147): one warp per keypoint, lane = descriptor byte
+__global__ void k_orb_desc(const uint8_t *__restrict__ blur, const OrbLevel *__restrict__ lvs, const OrbControl *__restrict__ ctl,
+                           const OrbKp *__restrict__ out, uint8_t *__restrict__ desc, sindyn_keypoint *__restrict__ kp_out)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= ctl->n_out) return;
+    const OrbKp k = out[warp];
+    const OrbLevel L = lvs[k.level];
+    const float angle = k.angle * (float)(3.14159265358979323846 / 180.f);
+    const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    const uint8_t *img = blur + L.img_off;
+    const int cx = __float2int_rn(k.x), cy = __float2int_rn(k.y);
+    int val = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const signed char *p = c_orb_pattern + (lane * 8 + t) * 4;
+        const float x0 = (float)p[0], y0 = (float)p[1], x1 = (float)p[2], y1 = (float)p[3];
+        const int r0 = __float2int_rn(x0 * b + y0 * a), c0 = __float2int_rn(x0 * a - y0 * b);
+        const int r1 = __float2int_rn(x1 * b + y1 * a), c1 = __float2int_rn(x1 * a - y1 * b);
+        const int t0 = img[(size_t)(cy + r0) * L.w + cx + c0], t1 = img[(size_t)(cy + r1) * L.w + cx + c1];
+        val |= (t0 < t1) << t;
+    }
+    desc[(size_t)warp * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        sindyn_keypoint o;
+        o.x = k.level ? k.x * L.scale : k.x;     // keypoint->pt *= scale for level != 0 (ORBextractor.cc:1154-1160)
+        o.y = k.level ? k.y * L.scale : k.y;
+        o.size = L.size; o.angle = k.angle; o.response = k.resp; o.octave = k.level;
+        kp_out[warp] = o;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+extern "C" int sindyn_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int width, int height,
+                                 int device, sindyn_orb_handle *out)
+{
+    if (!out || nlevels < 1 || nlevels > ORB_MAX_LEVELS || nfeatures < 1 || width < 64 || height < 64 || scale_factor <= 1.0f) return SINDYN_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) return SINDYN_ERR_NO_DEVICE;
+    sindyn_orb *o = new sindyn_orb();
+    *out = o;
+    o->device = device;
+    o->nfeatures = nfeatures; o->nlevels = nlevels; o->ini_th = ini_th_fast; o->min_th = min_th_fast; o->W = width; o->H = height;
+    o->scale_factor = scale_factor;
+    if (cudaSetDevice(device) != cudaSuccess) { o->err = "cudaSetDevice failed"; return SINDYN_ERR_CUDA; }
+    CU_CHECK(o, cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
+    o->stream = o->own_stream;
+    // scale tables and feature quotas (ORBextractor.cc:415-447)
+    float sf[ORB_MAX_LEVELS];
+    sf[0] = 1.0f;
+    for (int i = 1; i < nlevels; ++i) sf[i] = sf[i - 1] * scale_factor;
+    const float factor = 1.0f / scale_factor;
+    float nd = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    int quota[ORB_MAX_LEVELS];
+    for (int l = 0; l < nlevels - 1; ++l) { quota[l] = cv_round_f(nd); sum += quota[l]; nd *= factor; }
+    quota[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    size_t pad_off = 0, img_off = 0;
+    int cell_off = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        OrbLevel &L = o->lv[l];
+        const float inv = 1.0f / sf[l];
+        L.w = cv_round_f((float)width * inv); L.h = cv_round_f((float)height * inv);    // ORBextractor.cc:1171
+        L.pitch = L.w + 2 * ORB_EDGE;
+        L.pad_off = pad_off; pad_off += (size_t)L.pitch * (L.h + 2 * ORB_EDGE);
+        L.img_off = img_off; img_off += (size_t)L.w * L.h;
+        L.min_b = ORB_EDGE - 3; L.max_bx = L.w - ORB_EDGE + 3; L.max_by = L.h - ORB_EDGE + 3;
+        const float fw = (float)(L.max_bx - L.min_b), fh = (float)(L.max_by - L.min_b);
+        L.n_cols = (int)(fw / 30.0f); L.n_rows = (int)(fh / 30.0f);                       // ORBextractor.cc:769-785
+        if (L.n_cols < 1 || L.n_rows < 1) { o->err = "orb: pyramid level too small"; return SINDYN_ERR_INVALID; }
+        L.w_cell = (int)ceilf(fw / (float)L.n_cols); L.h_cell = (int)ceilf(fh / (float)L.n_rows);
+        if (L.n_cols * L.n_rows > ORB_MAX_CELLS || L.w_cell + 6 > 64 || L.h_cell + 6 > 64) { o->err = "orb: cell grid out of range"; return SINDYN_ERR_INVALID; }
+        L.cell_off = cell_off; cell_off += L.n_cols * L.n_rows;
+        L.quota = quota[l];
+        if (L.quota + 8 > ORB_NODES / 4) { o->err = "orb: nfeatures too large for the node pool"; return SINDYN_ERR_INVALID; }
+        L.scale = sf[l];
+        L.mask_scale = (float)pow((double)scale_factor, (double)l);                       // ORBextractor.cc:1074
+        L.size = (float)(int)(31.0f * sf[l]);                                             // scaledPatchSize (:837)
+    }
+    o->pad_total = pad_off; o->img_total = img_off;
+    SD_CHECK(o->dalloc(&o->pyr, pad_off));
+    SD_CHECK(o->dalloc(&o->score, img_off));
+    SD_CHECK(o->dalloc(&o->blur, img_off));
+    SD_CHECK(o->dalloc(&o->mask, (size_t)width * height));
+    SD_CHECK(o->dalloc(&o->lv_dev, ORB_MAX_LEVELS));
+    SD_CHECK(o->dalloc(&o->cell_count, (size_t)nlevels * ORB_MAX_CELLS));
+    SD_CHECK(o->dalloc(&o->cell_offs, (size_t)nlevels * ORB_MAX_CELLS));
+    SD_CHECK(o->dalloc(&o->cand, (size_t)nlevels * ORB_KMAX));
+    SD_CHECK(o->dalloc(&o->kps, (size_t)nlevels * ORB_NODES));
+    SD_CHECK(o->dalloc(&o->out, ORB_OUT_MAX));
+    SD_CHECK(o->dalloc(&o->desc, (size_t)ORB_OUT_MAX * 32));
+    SD_CHECK(o->dalloc(&o->out_host_fmt, ORB_OUT_MAX));
+    SD_CHECK(o->dalloc(&o->ctl, 1));
+    SD_CHECK(o->halloc(&o->ctl_host, 1));
+    CU_CHECK(o, cudaMemcpyAsync(o->lv_dev, o->lv, sizeof(OrbLevel) * ORB_MAX_LEVELS, cudaMemcpyHostToDevice, o->stream));
+    for (int l = 1; l < nlevels; ++l) SD_CHECK(resize_plan_init(o, &o->plan[l], o->lv[l - 1].w, o->lv[l - 1].h, o->lv[l].w, o->lv[l].h));
+    // umax (ORBextractor.cc:450-467)
+    int umax[ORB_HALF_PATCH + 1];
+    {
+        int v, v0;
+        const int vmax = (int)floorf(ORB_HALF_PATCH * sqrtf(2.f) / 2 + 1), vmin = (int)ceilf(ORB_HALF_PATCH * sqrtf(2.f) / 2);
+        const double hp2 = ORB_HALF_PATCH * ORB_HALF_PATCH;
+        for (v = 0; v <= vmax; ++v) umax[v] = (int)lrint(sqrt(hp2 - v * v));
+        for (v = ORB_HALF_PATCH, v0 = 0; v >= vmin; --v) {
+            while (umax[v0] == umax[v0 + 1]) ++v0;
+            umax[v] = v0;
+            ++v0;
+        }
+    }
+    CU_CHECK(o, cudaMemcpyToSymbolAsync(c_umax, umax, sizeof umax, 0, cudaMemcpyHostToDevice, o->stream));
+    const size_t qsmem = sizeof(QNode) * ORB_NODES + 2 * ORB_KMAX + 4 * ORB_KMAX + 4 * ORB_NODES + 2 * 2 * ORB_NODES;
+    CU_CHECK(o, cudaFuncSetAttribute(k_orb_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));
+    CU_CHECK(o, cudaStreamSynchronize(o->stream));
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_orb_destroy(sindyn_orb_handle h)
+{
+    if (!h) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->free_all();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_orb_set_stream(sindyn_orb_handle h, void *s)
+{
+    if (!h) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return SINDYN_OK;
+}
+
+extern "C" unsigned long long sindyn_orb_launch_count(sindyn_orb_handle h) { return h ? h->launches : 0ull; }
+extern "C" const char *sindyn_orb_last_error(sindyn_orb_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+// all kernels of one extraction; gray / mask already on the device (level-0 interior of pyr, o->mask)
+static int orb_enqueue(sindyn_orb *o, bool have_mask)
+{
+    const dim3 blk(32, 8);
+    const size_t qsmem = sizeof(QNode) * ORB_NODES + 2 * ORB_KMAX + 4 * ORB_KMAX + 4 * ORB_NODES + 2 * 2 * ORB_NODES;
+    CU_CHECK(o, cudaMemsetAsync(o->ctl, 0, sizeof(OrbControl), o->stream));
+    for (int l = 0; l < o->nlevels; ++l) {
+        const OrbLevel &L = o->lv[l];
+        uint8_t *pad = o->pyr + L.pad_off;
+        if (l > 0) {
+            const OrbLevel &P = o->lv[l - 1];
+            SD_CHECK(launch_resize_u8(o, &o->plan[l], o->pyr + P.pad_off + (size_t)ORB_EDGE * P.pitch + ORB_EDGE, P.pitch,
+                                      pad + (size_t)ORB_EDGE * L.pitch + ORB_EDGE, L.pitch, nullptr, 0.f));
+        }
+        LAUNCH(o, k_orb_pad, dim3(cdiv(L.pitch, 32), cdiv(L.h + 2 * ORB_EDGE, 8)), blk, 0, pad, L.w, L.h, L.pitch);
+        LAUNCH(o, k_orb_fast_score, dim3(cdiv(L.w, 32), cdiv(L.h, 8)), blk, 0, pad, L.w, L.h, L.pitch, o->score + L.img_off);
+        LAUNCH(o, k_orb_blur, dim3(cdiv(L.w, 32), cdiv(L.h, 8)), blk, 0, pad, L.w, L.h, L.pitch, o->blur + L.img_off);
+        LAUNCH(o, (k_orb_cells<false>), dim3(L.n_cols, L.n_rows), 256, 0, o->score, o->lv_dev, l, o->ini_th, o->min_th, o->cell_count,
+               o->cell_offs, o->cand, o->ctl);
+    }
+    LAUNCH(o, k_orb_cell_scan, o->nlevels, 256, 0, o->lv_dev, o->cell_count, o->cell_offs, o->ctl);
+    for (int l = 0; l < o->nlevels; ++l) {
+        const OrbLevel &L = o->lv[l];
+        LAUNCH(o, (k_orb_cells<true>), dim3(L.n_cols, L.n_rows), 256, 0, o->score, o->lv_dev, l, o->ini_th, o->min_th, o->cell_count,
+               o->cell_offs, o->cand, o->ctl);
+    }
+    LAUNCH(o, k_orb_quadtree, o->nlevels, 512, qsmem, o->lv_dev, o->cand, o->ctl, o->kps);
+    LAUNCH(o, k_orb_orient, dim3(cdiv(ORB_NODES * 32, 256), o->nlevels), 256, 0, o->pyr, o->lv_dev, o->ctl, o->kps,
+           have_mask ? o->mask : (const uint8_t *)nullptr, o->W);
+    LAUNCH(o, k_orb_select, 1, 1024, 0, o->lv_dev, o->nlevels, o->ctl, o->kps, o->out);
+    LAUNCH(o, k_orb_desc, cdiv(ORB_OUT_MAX * 32, 256), 256, 0, o->blur, o->lv_dev, o->ctl, o->out, o->desc, o->out_host_fmt);
+    LAUNCH_CHECK(o);
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_orb_extract(sindyn_orb_handle h, const uint8_t *gray, size_t gray_step, const uint8_t *mask, size_t mask_step,
+                                  sindyn_keypoint *kps, uint8_t *desc, int capacity, int *n_out)
+{
+    if (!h || !n_out) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    *n_out = 0;
+    if (!gray) return SINDYN_OK;   // operator() returns silently on an empty image (ORBextractor.cc:1046-1047)
+    const OrbLevel &L0 = h->lv[0];
+    CU_CHECK(h, cudaMemcpy2DAsync(h->pyr + (size_t)ORB_EDGE * L0.pitch + ORB_EDGE, L0.pitch, gray, gray_step ? gray_step : (size_t)h->W, h->W, h->H,
+                                  cudaMemcpyHostToDevice, h->stream));
+    if (mask) CU_CHECK(h, cudaMemcpy2DAsync(h->mask, h->W, mask, mask_step ? mask_step : (size_t)h->W, h->W, h->H, cudaMemcpyHostToDevice, h->stream));
+    SD_CHECK(orb_enqueue(h, mask != nullptr));
+    CU_CHECK(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(OrbControl), cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    if (h->ctl_host->overflow) { h->err = "orb: a fixed-capacity list overflowed (candidates / nodes / output)"; return SINDYN_ERR_CAPACITY; }
+    const int n = h->ctl_host->n_out;
+    *n_out = n;
+    if (n > capacity) { h->err = "orb: output capacity too small"; return SINDYN_ERR_CAPACITY; }
+    if (n && kps) CU_CHECK(h, cudaMemcpyAsync(kps, h->out_host_fmt, sizeof(sindyn_keypoint) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (n && desc) CU_CHECK(h, cudaMemcpyAsync(desc, h->desc, (size_t)32 * n, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_orb_get_pyramid_level(sindyn_orb_handle h, int level, uint8_t *out, int *w_out, int *h_out)
+{
+    if (!h || level < 0 || level >= h->nlevels) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const OrbLevel &L = h->lv[level];
+    if (w_out) *w_out = L.w;
+    if (h_out) *h_out = L.h;
+    if (out) {
+        CU_CHECK(h, cudaMemcpy2DAsync(out, L.w, h->pyr + L.pad_off + (size_t)ORB_EDGE * L.pitch + ORB_EDGE, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost,
+                                      h->stream));
+        CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    }
+    return SINDYN_OK;
+}
+
+// test hook: FAST candidates of one level in distribution order (x, y relative to minBorder, response)
+extern "C" int sindyn_orb_get_candidates(sindyn_orb_handle h, int level, int *xyr, int capacity, int *n_out)
+{
+    if (!h || level < 0 || level >= h->nlevels || !n_out) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    OrbControl c;
+    CU_CHECK(h, cudaMemcpy(&c, h->ctl, sizeof c, cudaMemcpyDeviceToHost));
+    const int n = c.cand_count[level];
+    *n_out = n;
+    if (n > capacity) return SINDYN_ERR_CAPACITY;
+    std::vector<OrbCand> tmp(n);
+    if (n) CU_CHECK(h, cudaMemcpy(tmp.data(), h->cand + (size_t)level * ORB_KMAX, sizeof(OrbCand) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) { xyr[3 * i] = tmp[i].x; xyr[3 * i + 1] = tmp[i].y; xyr[3 * i + 2] = tmp[i].resp; }
+    return SINDYN_OK;
+}
