@@ -233,6 +233,8 @@ int sindyn_orb_get_pyramid_level(sindyn_orb_handle h, int level, uint8_t *out, i
 /* Test hook: FAST candidates of one level after the last extract, in distribution order (vToDistributeKeys,
  * ORBextractor.cc:820-825): xyr = n x 3 ints (x, y relative to minBorder, response). */
 int sindyn_orb_get_candidates(sindyn_orb_handle h, int level, int *xyr, int capacity, int *n_out);
+/* Test hook: raw device planes of one level: which = 0 padded image (w+38 x h+38), 1 FAST score map, 2 blurred image. */
+int sindyn_orb_get_plane(sindyn_orb_handle h, int level, int which, uint8_t *out, int *w_out, int *h_out);
 int sindyn_orb_set_stream(sindyn_orb_handle h, void *cuda_stream);
 unsigned long long sindyn_orb_launch_count(sindyn_orb_handle h);
 const char *sindyn_orb_last_error(sindyn_orb_handle h);

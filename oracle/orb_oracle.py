@@ -46,7 +46,7 @@ class OrbOracle:
         self.inv_scale = [f32(f32(1.0) / s) for s in sf]
         self.sigma2 = [f32(s * s) for s in sf]
         self.inv_sigma2 = [f32(f32(1.0) / s) for s in self.sigma2]
-        factor = f32(f32(1.0) / self.scale_factor)
+        factor = f32(1.0 / float(self.scale_factor))   # 1.0f / (double)scaleFactor, stored as float (ORBextractor.cc:433)
         nd = f32(f32(nfeatures) * f32(f32(1) - factor) / f32(f32(1) - f32(math.pow(float(factor), float(nlevels)))))
         self.per_level = []
         tot = 0

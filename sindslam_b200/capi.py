@@ -86,6 +86,7 @@ SIGNATURES = {
     "sindyn_orb_extract": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _i, _ip]),
     "sindyn_orb_get_pyramid_level": (_i, [_vp, _i, _vp, _ip, _ip]),
     "sindyn_orb_get_candidates": (_i, [_vp, _i, _vp, _i, _ip]),
+    "sindyn_orb_get_plane": (_i, [_vp, _i, _i, _vp, _ip, _ip]),
     "sindyn_orb_set_stream": (_i, [_vp, _vp]),
     "sindyn_orb_launch_count": (C.c_ulonglong, [_vp]),
     "sindyn_orb_last_error": (C.c_char_p, [_vp]),
@@ -420,6 +421,14 @@ class Orb:
         if st != 0:
             raise SindynError("orb candidates")
         return buf[:n.value].copy()
+
+    def plane(self, level, which):
+        out = np.zeros((self.W + 38) * (self.H + 38), np.uint8)
+        w, h = C.c_int(0), C.c_int(0)
+        st = self.lib.sindyn_orb_get_plane(self.h, level, which, _p(out), C.byref(w), C.byref(h))
+        if st != 0:
+            raise SindynError("orb plane")
+        return out[: w.value * h.value].reshape(h.value, w.value).copy()
 
     def pyramid_level(self, level):
         out = np.zeros(self.W * self.H, np.uint8)

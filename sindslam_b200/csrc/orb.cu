@@ -88,15 +88,20 @@ __global__ void k_orb_fast_score(const uint8_t *__restrict__ pad, int w, int h, 
     int d[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) d[k] = v - (int)c[dy[k] * pitch + dx[k]];
-    // quick reject: a 9-arc always contains one of each opposite pair at distance 8
-    int best = 0;
+    // NOTE: keep the bright and dark arc extrema in SEPARATE accumulators.  The obvious form
+    //   best = max(best, max(mn, -mx))
+    // is miscompiled by nvcc 12.9 for sm_100a (min/max/negate fusion into VIMNMX3; repro: tools/ptxas_minmax_repro.cu,
+    // 97 % wrong scores on a B200) -- found through the bit-exact FAST parity test.
+    int bb = -255, bd = 255;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         int mn = d[k], mx = d[k];
 #pragma unroll
         for (int j = 1; j < 9; ++j) { int t = d[(k + j) & 15]; mn = min(mn, t); mx = max(mx, t); }
-        best = max(best, max(mn, -mx));
+        bb = max(bb, mn);
+        bd = min(bd, mx);
     }
+    const int best = max(0, max(bb, -bd));
     score[(size_t)y * w + x] = (uint8_t)best;
 }
 
@@ -619,7 +624,7 @@ extern "C" int sindyn_orb_create(int nfeatures, float scale_factor, int nlevels,
     float sf[ORB_MAX_LEVELS];
     sf[0] = 1.0f;
     for (int i = 1; i < nlevels; ++i) sf[i] = sf[i - 1] * scale_factor;
-    const float factor = 1.0f / scale_factor;
+    const float factor = (float)(1.0 / (double)scale_factor);   // the reference member is a double holding the float
     float nd = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
     int sum = 0;
     int quota[ORB_MAX_LEVELS];
@@ -794,5 +799,19 @@ extern "C" int sindyn_orb_get_candidates(sindyn_orb_handle h, int level, int *xy
     std::vector<OrbCand> tmp(n);
     if (n) CU_CHECK(h, cudaMemcpy(tmp.data(), h->cand + (size_t)level * ORB_KMAX, sizeof(OrbCand) * n, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) { xyr[3 * i] = tmp[i].x; xyr[3 * i + 1] = tmp[i].y; xyr[3 * i + 2] = tmp[i].resp; }
+    return SINDYN_OK;
+}
+
+// test hook: raw planes of one level: which = 0 padded image, 1 FAST score map, 2 blurred image
+extern "C" int sindyn_orb_get_plane(sindyn_orb_handle h, int level, int which, uint8_t *out, int *w_out, int *h_out)
+{
+    if (!h || level < 0 || level >= h->nlevels || !out) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const OrbLevel &L = h->lv[level];
+    const int w = which == 0 ? L.pitch : L.w, hh = which == 0 ? L.h + 2 * ORB_EDGE : L.h;
+    const uint8_t *src = which == 0 ? h->pyr + L.pad_off : (which == 1 ? h->score + L.img_off : h->blur + L.img_off);
+    if (w_out) *w_out = w;
+    if (h_out) *h_out = hh;
+    CU_CHECK(h, cudaMemcpy(out, src, (size_t)w * hh, cudaMemcpyDeviceToHost));
     return SINDYN_OK;
 }

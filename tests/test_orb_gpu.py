@@ -53,11 +53,16 @@ def test_orb_bit_exact_c1(seq_c1):
 def test_orb_other_parameters_and_flat_image():
     from sindslam_b200.capi import Orb
     rng = np.random.default_rng(3)
-    img = cv2.GaussianBlur((rng.random((480, 848)) * 255).astype(np.uint8), (0, 0), 1.2)
-    img = np.clip((img.astype(np.int32) - 128) * 4 + 128, 0, 255).astype(np.uint8)
+    noise = (rng.random((480, 848)) * 255).astype(np.uint8)
+    img = cv2.GaussianBlur(noise, (0, 0), 2.5)
+    img = np.clip((img.astype(np.int32) - 128) * 5 + 128, 0, 255).astype(np.uint8)
     o = oo.OrbOracle(1000, 1.2, 8, 20, 7)          # TUM1.yaml values on an 848x480 (D455-shaped) frame
     orb = Orb(1000, 1.2, 8, 20, 7, 848, 480)
     _check(orb, o, img, None)
+    # white noise: more FAST corners than the fixed-capacity candidate list holds -> a clean CAPACITY error, no crash
+    from sindslam_b200.capi import SindynError
+    with pytest.raises(SindynError, match="CAPACITY"):
+        orb.extract(noise, None)
     flat = np.full((480, 848), 90, np.uint8)        # no corners at all
     k, d = orb.extract(flat, None)
     assert len(k) == 0 and d.shape == (0, 32)
