@@ -70,7 +70,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_examples(force)
     return LIB
+
+
+EXAMPLE_BIN = os.path.join(HERE, "bin", "rgbd_tum_noros")
+
+
+def build_examples(force: bool = False) -> str:
+    """The reference-shaped C++ driver (examples/rgbd_tum_noros.cpp) on top of include/sindyn_classes.hpp."""
+    src = os.path.join(HERE, "..", "examples", "rgbd_tum_noros.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "sindyn_classes.hpp"), os.path.join(HERE, "..", "include", "sindyn.h"), LIB]
+    os.makedirs(os.path.dirname(EXAMPLE_BIN), exist_ok=True)
+    if not force and os.path.exists(EXAMPLE_BIN) and os.path.getmtime(EXAMPLE_BIN) >= max(os.path.getmtime(d) for d in deps):
+        return EXAMPLE_BIN
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", src, "-o", EXAMPLE_BIN, "-L" + HERE, "-lsindyn_cuda", "-Wl,-rpath," + HERE,
+           "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed for the example driver:\n%s\n%s" % (r.stdout, r.stderr))
+    return EXAMPLE_BIN
 
 
 if __name__ == "__main__":

@@ -261,8 +261,9 @@ def _quat(R):
     return x, y, zq, w
 
 
-def write_tum_sequence(root: str, frames, cam: CameraConfig):
-    """Write rgb/, depth/, associations.txt, groundtruth.txt (TUM format)."""
+def write_tum_sequence(root: str, frames, cam: CameraConfig, raw: bool = False):
+    """Write rgb/, depth/, associations.txt, groundtruth.txt (TUM format).  raw=True additionally writes every image
+    as binary PPM (B,G,R byte order, what cv::imread delivers) / 16-bit big-endian PGM for the OpenCV-free C++ driver."""
     import cv2
     os.makedirs(os.path.join(root, "rgb"), exist_ok=True)
     os.makedirs(os.path.join(root, "depth"), exist_ok=True)
@@ -272,6 +273,12 @@ def write_tum_sequence(root: str, frames, cam: CameraConfig):
             ts = "%.6f" % f.timestamp
             cv2.imwrite(os.path.join(root, "rgb", ts + ".png"), f.bgr)
             cv2.imwrite(os.path.join(root, "depth", ts + ".png"), f.depth)
+            if raw:
+                h, w = f.depth.shape
+                with open(os.path.join(root, "rgb", ts + ".ppm"), "wb") as fp:
+                    fp.write(b"P6\n%d %d\n255\n" % (w, h) + np.ascontiguousarray(f.bgr).tobytes())
+                with open(os.path.join(root, "depth", ts + ".pgm"), "wb") as fp:
+                    fp.write(b"P5\n%d %d\n65535\n" % (w, h) + f.depth.astype(">u2").tobytes())
             fa.write(f"{ts} rgb/{ts}.png {ts} depth/{ts}.png\n")
             q = _quat(f.T_wc[:3, :3])
             p = f.T_wc[:3, 3]
