@@ -121,6 +121,14 @@ __global__ void k_brox_deriv2(const float *__restrict__ Ix, const float *__restr
 }
 
 // ------------------------------------------------------------------ the solver kernel
+// One launch = (n_inner) lagged-nonlinearity iterations x (nsweeps) red-black SOR sweeps on one tile:
+//   * the tile plus a `halo`-pixel ring lives in shared memory; results of the fused sweeps are exact because a pixel at
+//     distance d from a halo edge stays valid for d half-sweeps (temporal blocking) and only the interior is written;
+//   * red and black pixels are stored DE-INTERLEAVED (two arrays of 37-wide rows), so the stride-2 access pattern of a
+//     red-black sweep becomes stride-1 and bank-conflict free; (du,dv) and the two edge weights are float2 -> LDS.64;
+//   * every thread owns a FIXED set of 5 red + 5 black pixels for the whole launch: the 2x2 system of a pixel
+//     (j12, b1, b2, 1/d1, 1/d2) and its current (du,dv) stay in registers, only neighbour values go through shared memory;
+//   * levels that fit into one tile (<= 74 x 66, the 7 coarsest of 15) run all inner iterations in ONE launch (halo 0).
 struct BroxInnerP {
     const float *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz, *u, *v;
     const float *dub, *dvb;  // increment at the start of this lagged-nonlinearity iteration (coefficients)
@@ -129,123 +137,221 @@ struct BroxInnerP {
     int w, h;
     float alpha, gamma, omega;
     int nsweeps;
+    int tw, th, halo, n_inner;
 };
 
-constexpr int BROX_TW = 32, BROX_TH = 24, BROX_SMAX = 10, BROX_NT = 512;
+constexpr int BROX_SMAX = 10, BROX_NT = 512;
 constexpr int BROX_RMAX = 2 * BROX_SMAX + 1;
-constexpr int BROX_PW = BROX_TW + 2 * BROX_RMAX, BROX_PH = BROX_TH + 2 * BROX_RMAX;
-constexpr int BROX_PP = BROX_PW * BROX_PH;
-constexpr size_t BROX_SMEM = (size_t)BROX_PP * 8 * sizeof(float);
+// Tile menu: a level uses the smallest tile whose grid still fits into one wave of 148 SMs -- the time of a launch is
+// the time of ONE CTA, which is proportional to the staged region (tile + 2 x 21 halo), so mid-size levels run on
+// many small tiles instead of a few large ones.
+template <int TW_, int TH_> struct BroxTile {
+    static constexpr int TW = TW_, TH = TH_;
+    static constexpr int PW = TW + 2 * BROX_RMAX, PH = TH + 2 * BROX_RMAX;   // staged region
+    static constexpr int HW = PW / 2;                                        // pixels of one colour per row
+    static constexpr int NPC = PH * HW;                                      // pixels per colour
+    static constexpr int M = (NPC + BROX_NT - 1) / BROX_NT;                  // owned pixels per colour and thread
+    static constexpr int PP = PW * PH;
+    static constexpr int G = HW + 1;                 // zero guard before / after every colour array (wrapped neighbour reads)
+    static constexpr int NPCP = NPC + 2 * G;
+    static constexpr size_t SMEM = sizeof(float2) * 4 * NPCP + sizeof(float) * 3 * PP;
+    static_assert((PW & 1) == 0, "de-interleaving needs an even region width");
+    static_assert(NPC < 4096, "pixel index must fit into 12 bits");
+};
+typedef BroxTile<32, 24> BroxTileL;   // 74 x 66 region: also the single-tile mode of the coarse levels
 
+template <class T>
 __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
 {
-    extern __shared__ float sm[];
-    float *s_du = sm, *s_dv = sm + BROX_PP, *s_ps = sm + 2 * BROX_PP, *s_j12 = sm + 3 * BROX_PP;
-    float *s_b1 = sm + 4 * BROX_PP, *s_b2 = sm + 5 * BROX_PP, *s_d1 = sm + 6 * BROX_PP, *s_d2 = sm + 7 * BROX_PP;
-    const int gx0 = blockIdx.x * BROX_TW, gy0 = blockIdx.y * BROX_TH;
-    const int ox = gx0 - BROX_RMAX, oy = gy0 - BROX_RMAX;
+    constexpr int BROX_PW = T::PW, BROX_PH = T::PH, BROX_HW = T::HW, BROX_NPC = T::NPC, BROX_M = T::M, BROX_PP = T::PP, BROX_G = T::G,
+                  BROX_NPCP = T::NPCP;
+    extern __shared__ float4 sm4[];
+    // colour arrays are padded by BROX_G zero elements on both sides: neighbour reads that fall off a row / the region
+    // land on a zero weight (never on a NaN) instead of needing per-pixel bounds logic in the sweep
+    float2 *s_uv = (float2 *)sm4 + BROX_G;      // [2][NPCP]  (du, dv) by colour
+    float2 *s_w = s_uv + 2 * BROX_NPCP;         // [2][NPCP]  (weight to the right neighbour, weight to the lower neighbour)
+    float *s_ta = (float *)((float2 *)sm4 + 4 * BROX_NPCP);  // [PP] u + du_base
+    float *s_tb = s_ta + BROX_PP;               // [PP] v + dv_base
+    float *s_ps = s_tb + BROX_PP;               // [PP] smoothness diffusivity
     const int w = p.w, h = p.h;
-    const int ns2 = 2 * p.nsweeps;
+    const int gx0 = blockIdx.x * p.tw, gy0 = blockIdx.y * p.th;
+    const int ox = gx0 - p.halo, oy = gy0 - p.halo;   // ox + oy is even in both modes: local colour == global colour
     const int tid = threadIdx.x;
-#define SIDX(gx, gy) (((gy)-oy) * BROX_PW + ((gx)-ox))
-#define REGION(r)                                                                             \
-    const int xa = max(0, gx0 - (r)), xb = min(w - 1, gx0 + BROX_TW - 1 + (r));                \
-    const int ya = max(0, gy0 - (r)), yb = min(h - 1, gy0 + BROX_TH - 1 + (r));                \
-    const int rw = xb - xa + 1, rh = yb - ya + 1;
+    const int ns2 = 2 * p.nsweeps;
+    const float alpha = p.alpha, gamma = p.gamma, omega = p.omega, om1 = 1.0f - p.omega;
+    // rows of the staged region that can hold image pixels (coarse levels use a fraction of the region)
+    const int row_hi = min(BROX_PH, h - oy);
+    const int pp_used = (row_hi > 0 ? row_hi : 0) * BROX_PW;
 
-    {   // phase 0: stage (du,dv) and the total flow Uc = u + du_base (scratch in s_b1/s_b2), radius 2ns+1
-        REGION(ns2 + 1)
-        for (int i = tid; i < rw * rh; i += BROX_NT) {
-            int y = ya + i / rw, x = xa + i % rw;
-            int g = y * w + x, s = SIDX(x, y);
-            s_du[s] = p.dui[g];
-            s_dv[s] = p.dvi[g];
-            s_b1[s] = p.u[g] + p.dub[g];
-            s_b2[s] = p.v[g] + p.dvb[g];
+    // ---- per-thread pixel table: pk = idx (12 bits) | parity << 12 | interior << 13 | live << 14 | dist << 16
+    unsigned pk[2][BROX_M];
+    float cj12[2][BROX_M], cb1[2][BROX_M], cb2[2][BROX_M], cd1[2][BROX_M], cd2[2][BROX_M], rdu[2][BROX_M], rdv[2][BROX_M];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int m = 0; m < BROX_M; ++m) {
+            const int q = tid + BROX_NT * m;
+            unsigned v = 0;
+            if (q < BROX_NPC) {
+                const int ly = q / BROX_HW, i = q - ly * BROX_HW;
+                const int par = (ly + c) & 1, lx = 2 * i + par;
+                const int x = ox + lx, y = oy + ly;
+                const bool inside = x >= 0 && x < w && y >= 0 && y < h;
+                int dist = 255;
+                if (ox > 0) dist = min(dist, lx);
+                if (oy > 0) dist = min(dist, ly);
+                if (ox + BROX_PW < w) dist = min(dist, BROX_PW - 1 - lx);
+                if (oy + BROX_PH < h) dist = min(dist, BROX_PH - 1 - ly);
+                const bool interior = inside && x >= gx0 && x < gx0 + p.tw && y >= gy0 && y < gy0 + p.th;
+                const bool live = inside && dist >= (p.halo > ns2 ? p.halo - ns2 : 0) + 1;   // updated by at least the first half-sweep
+                v = (unsigned)q | ((unsigned)par << 12) | ((unsigned)interior << 13) | ((unsigned)live << 14) | ((unsigned)dist << 16);
+            }
+            pk[c][m] = v;
+            cj12[c][m] = cb1[c][m] = cb2[c][m] = cd1[c][m] = cd2[c][m] = rdu[c][m] = rdv[c][m] = 0.0f;
         }
-    }
+
+    for (int r = tid; r < 4 * BROX_NPCP; r += BROX_NT) ((float2 *)sm4)[r] = make_float2(0.0f, 0.0f);   // guards (and everything else)
     __syncthreads();
-    {   // phase 1: smoothness diffusivity psi'_s from the gradient of the total flow, radius 2ns
-        REGION(ns2)
-        for (int i = tid; i < rw * rh; i += BROX_NT) {
-            int y = ya + i / rw, x = xa + i % rw;
-            int xm = max(x - 1, 0), xp = min(x + 1, w - 1), ym = max(y - 1, 0), yp = min(y + 1, h - 1);
-            float ux = 0.5f * (s_b1[SIDX(xp, y)] - s_b1[SIDX(xm, y)]), uy = 0.5f * (s_b1[SIDX(x, yp)] - s_b1[SIDX(x, ym)]);
-            float vx = 0.5f * (s_b2[SIDX(xp, y)] - s_b2[SIDX(xm, y)]), vy = 0.5f * (s_b2[SIDX(x, yp)] - s_b2[SIDX(x, ym)]);
-            s_ps[SIDX(x, y)] = 0.5f / sqrtf(ux * ux + uy * uy + vx * vx + vy * vy + BROX_EPS2);
-        }
-    }
-    __syncthreads();
-    {   // phase 2: data-term weights and the per-pixel 2x2 system, radius 2ns-1
-        REGION(ns2 - 1)
-        const float alpha = p.alpha, gamma = p.gamma;
-        for (int i = tid; i < rw * rh; i += BROX_NT) {
-            int y = ya + i / rw, x = xa + i % rw;
-            int g = y * w + x, s = SIDX(x, y);
-            float ix = p.Ix[g], iy = p.Iy[g], iz = p.Iz[g], ixx = p.Ixx[g], ixy = p.Ixy[g], iyy = p.Iyy[g], ixz = p.Ixz[g], iyz = p.Iyz[g];
-            float dub = p.dub[g], dvb = p.dvb[g];
-            float q0 = iz + ix * dub + iy * dvb;
-            float q1 = ixz + ixx * dub + ixy * dvb;
-            float q2 = iyz + ixy * dub + iyy * dvb;
-            float psid = 0.5f / sqrtf(q0 * q0 + gamma * (q1 * q1 + q2 * q2) + BROX_EPS2);
-            float j11 = psid * (ix * ix + gamma * (ixx * ixx + ixy * ixy));
-            float j12 = psid * (ix * iy + gamma * (ixx * ixy + ixy * iyy));
-            float j22 = psid * (iy * iy + gamma * (ixy * ixy + iyy * iyy));
-            float j13 = psid * (ix * iz + gamma * (ixx * ixz + ixy * iyz));
-            float j23 = psid * (iy * iz + gamma * (ixy * ixz + iyy * iyz));
-            float ps = s_ps[s];
-            float uc = p.u[g], vc = p.v[g];
-            float su = 0.0f, sv = 0.0f, sw_ = 0.0f;
-            if (x > 0) { float wl = alpha * 0.5f * (ps + s_ps[s - 1]); su += wl * (p.u[g - 1] - uc); sv += wl * (p.v[g - 1] - vc); sw_ = wl; }
-            float wr = 0.0f, wu = 0.0f, wd = 0.0f;
-            if (x < w - 1) { wr = alpha * 0.5f * (ps + s_ps[s + 1]); su += wr * (p.u[g + 1] - uc); sv += wr * (p.v[g + 1] - vc); }
-            if (y > 0) { wu = alpha * 0.5f * (ps + s_ps[s - BROX_PW]); su += wu * (p.u[g - w] - uc); sv += wu * (p.v[g - w] - vc); }
-            if (y < h - 1) { wd = alpha * 0.5f * (ps + s_ps[s + BROX_PW]); su += wd * (p.u[g + w] - uc); sv += wd * (p.v[g + w] - vc); }
-            sw_ = sw_ + wr + wu + wd;
-            s_j12[s] = j12;
-            s_b1[s] = su - j13;
-            s_b2[s] = sv - j23;
-            s_d1[s] = 1.0f / (j11 + sw_);
-            s_d2[s] = 1.0f / (j22 + sw_);
-        }
-    }
-    __syncthreads();
-    // red-black SOR: half-sweep k updates colour (k-1)&1 inside radius 2ns-k
-    const float alpha = p.alpha, omega = p.omega, om1 = 1.0f - p.omega;
-    for (int k = 1; k <= ns2; ++k) {
-        REGION(ns2 - k)
-        const int color = (k - 1) & 1;
-        const int hc = (rw + 1) >> 1;
-        for (int i = tid; i < hc * rh; i += BROX_NT) {
-            int y = ya + i / hc;
-            int x = xa + 2 * (i % hc) + ((xa + y + color) & 1);
-            if (x > xb) continue;
-            int s = SIDX(x, y);
-            float ps = s_ps[s];
-            float su = 0.0f, sv = 0.0f;
-            if (x > 0) { float wl = alpha * 0.5f * (ps + s_ps[s - 1]); su += wl * s_du[s - 1]; sv += wl * s_dv[s - 1]; }
-            if (x < w - 1) { float wr = alpha * 0.5f * (ps + s_ps[s + 1]); su += wr * s_du[s + 1]; sv += wr * s_dv[s + 1]; }
-            if (y > 0) { float wu = alpha * 0.5f * (ps + s_ps[s - BROX_PW]); su += wu * s_du[s - BROX_PW]; sv += wu * s_dv[s - BROX_PW]; }
-            if (y < h - 1) { float wd = alpha * 0.5f * (ps + s_ps[s + BROX_PW]); su += wd * s_du[s + BROX_PW]; sv += wd * s_dv[s + BROX_PW]; }
-            float j12 = s_j12[s];
-            float du_new = om1 * s_du[s] + omega * (s_b1[s] - j12 * s_dv[s] + su) * s_d1[s];
-            float dv_new = om1 * s_dv[s] + omega * (s_b2[s] - j12 * du_new + sv) * s_d2[s];
-            s_du[s] = du_new;
-            s_dv[s] = dv_new;
+    for (int it = 0; it < p.n_inner; ++it) {
+        // ---- phase 0: stage (du,dv) and the total flow u + du_base (radius = whole region)
+        for (int r = tid; r < pp_used; r += BROX_NT) {
+            const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
+            const int x = ox + lx, y = oy + ly;
+            const int ci = ((lx + ly) & 1) * BROX_NPCP + ly * BROX_HW + (lx >> 1);
+            float ta = 0.0f, tb = 0.0f;
+            if (x >= 0 && x < w && y >= 0 && y < h) {
+                const int g = y * w + x;
+                if (it == 0) {
+                    s_uv[ci] = make_float2(p.dui[g], p.dvi[g]);
+                    ta = p.u[g] + p.dub[g];
+                    tb = p.v[g] + p.dvb[g];
+                } else {   // single-tile mode: the increment of the previous inner iteration is already in shared memory
+                    const float2 d = s_uv[ci];
+                    ta = p.u[g] + d.x;
+                    tb = p.v[g] + d.y;
+                }
+            } else if (it == 0) {
+                s_uv[ci] = make_float2(0.0f, 0.0f);
+            }
+            s_ta[r] = ta;
+            s_tb[r] = tb;
         }
         __syncthreads();
-    }
-    {
-        REGION(0)
-        for (int i = tid; i < rw * rh; i += BROX_NT) {
-            int y = ya + i / rw, x = xa + i % rw;
-            int g = y * w + x, s = SIDX(x, y);
-            p.duo[g] = s_du[s];
-            p.dvo[g] = s_dv[s];
+        // ---- phase 1: smoothness diffusivity psi'_s from the gradient of the total flow
+        for (int r = tid; r < pp_used; r += BROX_NT) {
+            const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
+            const int x = ox + lx, y = oy + ly;
+            float ps = 0.0f;
+            if (x >= 0 && x < w && y >= 0 && y < h) {
+                const int rm = (x > 0 && lx > 0) ? r - 1 : r, rp = (x < w - 1 && lx < BROX_PW - 1) ? r + 1 : r;
+                const int ru = (y > 0 && ly > 0) ? r - BROX_PW : r, rd = (y < h - 1 && ly < BROX_PH - 1) ? r + BROX_PW : r;
+                const float ux = 0.5f * (s_ta[rp] - s_ta[rm]), uy = 0.5f * (s_ta[rd] - s_ta[ru]);
+                const float vx = 0.5f * (s_tb[rp] - s_tb[rm]), vy = 0.5f * (s_tb[rd] - s_tb[ru]);
+                ps = 0.5f / sqrtf(ux * ux + uy * uy + vx * vx + vy * vy + BROX_EPS2);
+            }
+            s_ps[r] = ps;
         }
+        __syncthreads();
+        // ---- phase 2a: edge weights (right, down) of every pixel; zero across the image border (Neumann)
+        for (int r = tid; r < pp_used; r += BROX_NT) {
+            const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
+            const int x = ox + lx, y = oy + ly;
+            float wr = 0.0f, wd = 0.0f;
+            if (x >= 0 && x < w && y >= 0 && y < h) {
+                const float ps = s_ps[r];
+                if (x < w - 1 && lx < BROX_PW - 1) wr = alpha * 0.5f * (ps + s_ps[r + 1]);
+                if (y < h - 1 && ly < BROX_PH - 1) wd = alpha * 0.5f * (ps + s_ps[r + BROX_PW]);
+            }
+            s_w[((lx + ly) & 1) * BROX_NPCP + ly * BROX_HW + (lx >> 1)] = make_float2(wr, wd);
+        }
+        __syncthreads();
+        // ---- phase 2b: data term and the 2x2 system of the owned pixels -> registers
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int m = 0; m < BROX_M; ++m) {
+                const unsigned k = pk[c][m];
+                if (!((k >> 14) & 1u)) continue;
+                const int idx = k & 0xfff, par = (k >> 12) & 1;
+                const int ly = idx / BROX_HW, lx = 2 * (idx - ly * BROX_HW) + par;
+                const int x = ox + lx, y = oy + ly, g = y * w + x;
+                const float2 *wo = s_w + (c ^ 1) * BROX_NPCP;
+                const float2 wown = s_w[c * BROX_NPCP + idx];
+                const float wl = x > 0 ? wo[idx - 1 + par].x : 0.0f, wr = wown.x;
+                const float wu = y > 0 ? wo[idx - BROX_HW].y : 0.0f, wd = wown.y;
+                const float2 own = s_uv[c * BROX_NPCP + idx];
+                float dub, dvb;
+                if (it == 0) { dub = p.dub[g]; dvb = p.dvb[g]; } else { dub = own.x; dvb = own.y; }
+                rdu[c][m] = own.x;
+                rdv[c][m] = own.y;
+                const float ix = p.Ix[g], iy = p.Iy[g], iz = p.Iz[g], ixx = p.Ixx[g], ixy = p.Ixy[g], iyy = p.Iyy[g], ixz = p.Ixz[g], iyz = p.Iyz[g];
+                const float q0 = iz + ix * dub + iy * dvb;
+                const float q1 = ixz + ixx * dub + ixy * dvb;
+                const float q2 = iyz + ixy * dub + iyy * dvb;
+                const float psid = 0.5f / sqrtf(q0 * q0 + gamma * (q1 * q1 + q2 * q2) + BROX_EPS2);
+                const float j11 = psid * (ix * ix + gamma * (ixx * ixx + ixy * ixy));
+                const float j12 = psid * (ix * iy + gamma * (ixx * ixy + ixy * iyy));
+                const float j22 = psid * (iy * iy + gamma * (ixy * ixy + iyy * iyy));
+                const float j13 = psid * (ix * iz + gamma * (ixx * ixz + ixy * iyz));
+                const float j23 = psid * (iy * iz + gamma * (ixy * ixz + iyy * iyz));
+                const float uc = p.u[g], vc = p.v[g];
+                float su = 0.0f, sv = 0.0f;
+                if (x > 0) { su += wl * (p.u[g - 1] - uc); sv += wl * (p.v[g - 1] - vc); }
+                if (x < w - 1) { su += wr * (p.u[g + 1] - uc); sv += wr * (p.v[g + 1] - vc); }
+                if (y > 0) { su += wu * (p.u[g - w] - uc); sv += wu * (p.v[g - w] - vc); }
+                if (y < h - 1) { su += wd * (p.u[g + w] - uc); sv += wd * (p.v[g + w] - vc); }
+                const float sw_ = wl + wr + wu + wd;
+                cj12[c][m] = j12;
+                cb1[c][m] = su - j13;
+                cb2[c][m] = sv - j23;
+                cd1[c][m] = 1.0f / (j11 + sw_);
+                cd2[c][m] = 1.0f / (j22 + sw_);
+            }
+        // (no barrier needed: the sweeps below read only s_uv / s_w, which are complete)
+        // ---- red-black SOR: half-sweep k updates colour (k-1)&1 where the halo distance allows it
+        const unsigned thr0 = (unsigned)(p.halo > ns2 ? p.halo - ns2 : 0);
+#define BROX_HALF(C, K)                                                                                           \
+    {                                                                                                             \
+        const float2 *uo = s_uv + ((C) ^ 1) * BROX_NPCP;                                                           \
+        const float2 *wo = s_w + ((C) ^ 1) * BROX_NPCP;                                                            \
+        _Pragma("unroll") for (int m = 0; m < BROX_M; ++m)                                                        \
+        {                                                                                                         \
+            const unsigned k_ = pk[C][m];                                                                         \
+            if (((k_ >> 14) & 1u) && (k_ >> 16) >= thr0 + (unsigned)(K)) {                                        \
+                const int idx = k_ & 0xfff, par = (k_ >> 12) & 1;                                                 \
+                const float2 l = uo[idx - 1 + par], r = uo[idx + par], u_ = uo[idx - BROX_HW], d = uo[idx + BROX_HW]; \
+                const float2 wown = s_w[(C) * BROX_NPCP + idx];                                                    \
+                const float wl = wo[idx - 1 + par].x, wu = wo[idx - BROX_HW].y;                                   \
+                const float su = wl * l.x + wown.x * r.x + wu * u_.x + wown.y * d.x;                              \
+                const float sv = wl * l.y + wown.x * r.y + wu * u_.y + wown.y * d.y;                              \
+                const float du_new = om1 * rdu[C][m] + omega * (cb1[C][m] - cj12[C][m] * rdv[C][m] + su) * cd1[C][m]; \
+                const float dv_new = om1 * rdv[C][m] + omega * (cb2[C][m] - cj12[C][m] * du_new + sv) * cd2[C][m]; \
+                rdu[C][m] = du_new;                                                                               \
+                rdv[C][m] = dv_new;                                                                               \
+                s_uv[(C) * BROX_NPCP + idx] = make_float2(du_new, dv_new);                                         \
+            }                                                                                                     \
+        }                                                                                                         \
+        __syncthreads();                                                                                          \
     }
-#undef SIDX
-#undef REGION
+        for (int sw = 0; sw < p.nsweeps; ++sw) {
+            BROX_HALF(0, 2 * sw + 1)
+            BROX_HALF(1, 2 * sw + 2)
+        }
+#undef BROX_HALF
+    }
+    // ---- write the interior from registers
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int m = 0; m < BROX_M; ++m) {
+            const unsigned k = pk[c][m];
+            if (!((k >> 13) & 1u)) continue;
+            const int idx = k & 0xfff, par = (k >> 12) & 1;
+            const int ly = idx / BROX_HW, lx = 2 * (idx - ly * BROX_HW) + par;
+            const int g = (oy + ly) * w + ox + lx;
+            p.duo[g] = rdu[c][m];
+            p.dvo[g] = rdv[c][m];
+        }
 }
 
 // level -> finer level: (u+du, v+dv) bilinear, scaled by the size ratios
@@ -313,8 +419,18 @@ int brox_init(sindyn_base *ctx, BroxSolver *b, int w, int h, float alpha, float 
     float **planes[] = {&b->A, &b->Iz, &b->Ix, &b->Iy, &b->Ixz, &b->Iyz, &b->Ixx, &b->Ixy, &b->Iyy,
                         &b->u[0], &b->u[1], &b->v[0], &b->v[1], &b->du[0], &b->du[1], &b->du[2], &b->dv[0], &b->dv[1], &b->dv[2]};
     for (float **pp : planes) SD_CHECK(ctx->dalloc(pp, n));
-    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BROX_SMEM));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner<BroxTile<8, 8>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<8, 8>::SMEM));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner<BroxTile<16, 12>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<16, 12>::SMEM));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner<BroxTile<24, 16>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<24, 16>::SMEM));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner<BroxTileL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTileL::SMEM));
     return SINDYN_OK;
+}
+
+template <class T> static bool brox_tile_fits(int w, int h) { return cdiv(w, T::TW) * cdiv(h, T::TH) <= SINDYN_NUM_SMS_B200; }
+template <class T> static void brox_launch_tiled(sindyn_base *ctx, BroxInnerP &p)
+{
+    p.tw = T::TW; p.th = T::TH; p.halo = BROX_RMAX; p.n_inner = 1;
+    LAUNCH(ctx, k_brox_inner<T>, dim3(cdiv(p.w, T::TW), cdiv(p.h, T::TH)), BROX_NT, T::SMEM, p);
 }
 
 static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const float *I1, float *flow_out, float sign)
@@ -343,28 +459,47 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
         LAUNCH(ctx, k_brox_warp, grd, blk, 0, L0, L1, b->u[cur], b->v[cur], w, h, b->A, b->Iz, b->du[base], b->dv[base]);
         LAUNCH(ctx, k_brox_deriv1, grd, blk, 0, b->A, b->Iz, w, h, b->Ix, b->Iy, b->Ixz, b->Iyz);
         LAUNCH(ctx, k_brox_deriv2, grd, blk, 0, b->Ix, b->Iy, w, h, b->Ixx, b->Ixy, b->Iyy);
-        dim3 tgrd(cdiv(w, BROX_TW), cdiv(h, BROX_TH));
-        for (int it = 0; it < b->inner; ++it) {
-            int in = base, remaining = b->solver;
-            while (remaining > 0) {
-                int ns = remaining < BROX_SMAX ? remaining : BROX_SMAX;
-                int out = 0;
-                while (out == base || out == in) ++out;
-                BroxInnerP p;
-                p.Ix = b->Ix; p.Iy = b->Iy; p.Iz = b->Iz; p.Ixx = b->Ixx; p.Ixy = b->Ixy; p.Iyy = b->Iyy; p.Ixz = b->Ixz; p.Iyz = b->Iyz;
-                p.u = b->u[cur]; p.v = b->v[cur];
-                p.dub = b->du[base]; p.dvb = b->dv[base];
-                p.dui = b->du[in]; p.dvi = b->dv[in];
-                p.duo = b->du[out]; p.dvo = b->dv[out];
-                p.w = w; p.h = h; p.alpha = b->alpha; p.gamma = b->gamma; p.omega = b->omega; p.nsweeps = ns;
-                const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
-                if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
-                LAUNCH(ctx, k_brox_inner, tgrd, BROX_NT, BROX_SMEM, p);
-                if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h; }
-                in = out;
-                remaining -= ns;
+        BroxInnerP p;
+        p.Ix = b->Ix; p.Iy = b->Iy; p.Iz = b->Iz; p.Ixx = b->Ixx; p.Ixy = b->Ixy; p.Iyy = b->Iyy; p.Ixz = b->Ixz; p.Iyz = b->Iyz;
+        p.u = b->u[cur]; p.v = b->v[cur];
+        p.w = w; p.h = h; p.alpha = b->alpha; p.gamma = b->gamma; p.omega = b->omega;
+        if (w <= BroxTileL::PW && h <= BroxTileL::PH && b->solver <= BROX_SMAX) {
+            // the whole level fits into one tile: all lagged-nonlinearity iterations in ONE launch, no halo
+            const int out = 1;
+            p.dub = p.dui = b->du[base]; p.dvb = p.dvi = b->dv[base];
+            p.duo = b->du[out]; p.dvo = b->dv[out];
+            p.nsweeps = b->solver; p.tw = BroxTileL::PW; p.th = BroxTileL::PH; p.halo = 0; p.n_inner = b->inner;
+            const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
+            if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
+            LAUNCH(ctx, k_brox_inner<BroxTileL>, dim3(1, 1), BROX_NT, BroxTileL::SMEM, p);
+            if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h * b->inner; }
+            base = out;
+        } else {
+            const int tile = brox_tile_fits<BroxTile<8, 8>>(w, h) ? 0 : brox_tile_fits<BroxTile<16, 12>>(w, h) ? 1 : brox_tile_fits<BroxTile<24, 16>>(w, h) ? 2 : 3;
+            for (int it = 0; it < b->inner; ++it) {
+                int in = base, remaining = b->solver;
+                while (remaining > 0) {
+                    int ns = remaining < BROX_SMAX ? remaining : BROX_SMAX;
+                    int out = 0;
+                    while (out == base || out == in) ++out;
+                    p.dub = b->du[base]; p.dvb = b->dv[base];
+                    p.dui = b->du[in]; p.dvi = b->dv[in];
+                    p.duo = b->du[out]; p.dvo = b->dv[out];
+                    p.nsweeps = ns;
+                    const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
+                    if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
+                    switch (tile) {
+                    case 0: brox_launch_tiled<BroxTile<8, 8>>(ctx, p); break;
+                    case 1: brox_launch_tiled<BroxTile<16, 12>>(ctx, p); break;
+                    case 2: brox_launch_tiled<BroxTile<24, 16>>(ctx, p); break;
+                    default: brox_launch_tiled<BroxTileL>(ctx, p); break;
+                    }
+                    if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h; }
+                    in = out;
+                    remaining -= ns;
+                }
+                base = in;
             }
-            base = in;
         }
         if (k > 0) {
             const int fw = b->ws[k - 1], fh = b->hs[k - 1];

@@ -206,20 +206,26 @@ __global__ void __launch_bounds__(256) k_homog_hypotheses(const float2 *__restri
     }
 }
 
-// single CTA: best consensus, then Gauss-Newton on the inliers (re-selected every iteration)
-__global__ void __launch_bounds__(1024) k_homog_select_refine(const float2 *__restrict__ pts, const float2 *__restrict__ pts_last,
-                                                              const int *__restrict__ n_ptr, const double *__restrict__ Hs,
-                                                              const int *__restrict__ scores, double *__restrict__ H_out,
-                                                              int *__restrict__ info)
+// single CTA: best consensus, then Gauss-Newton on the inliers (re-selected every iteration).
+// 256 threads: the 45 normal-equation accumulators of a thread stay in registers (no local-memory spills), the
+// cross-warp reduction is done by 45 threads in parallel, and the loop stops once the update is below 1e-12.
+#define HG_RT 256
+__global__ void __launch_bounds__(HG_RT) k_homog_select_refine(const float2 *__restrict__ pts, const float2 *__restrict__ pts_last,
+                                                               const int *__restrict__ n_ptr, const double *__restrict__ Hs,
+                                                               const int *__restrict__ scores, double *__restrict__ H_out,
+                                                               int *__restrict__ info)
 {
-    __shared__ int s_best[32], s_bidx[32];
-    __shared__ double s_acc[32][45];
+    constexpr int NW = HG_RT / 32;
+    __shared__ int s_best[NW], s_bidx[NW];
+    __shared__ double s_acc[NW][45];
+    __shared__ double s_tot[45];
     __shared__ double s_h[8];
-    __shared__ int s_nin;
+    __shared__ int s_nin[NW];
+    __shared__ int s_done;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = *n_ptr;
     int best = -2, bidx = 0;
-    for (int m = tid; m < HG_M; m += blockDim.x)
+    for (int m = tid; m < HG_M; m += HG_RT)
         if (scores[m] > best) { best = scores[m]; bidx = m; }
     for (int o = 16; o > 0; o >>= 1) {
         int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bidx, o);
@@ -228,64 +234,75 @@ __global__ void __launch_bounds__(1024) k_homog_select_refine(const float2 *__re
     if (lane == 0) { s_best[wid] = best; s_bidx[wid] = bidx; }
     __syncthreads();
     if (tid == 0) {
-        for (int w2 = 1; w2 < 32; ++w2)
+        for (int w2 = 1; w2 < NW; ++w2)
             if (s_best[w2] > best || (s_best[w2] == best && s_bidx[w2] < bidx)) { best = s_best[w2]; bidx = s_bidx[w2]; }
         if (best >= 4) for (int c = 0; c < 8; ++c) s_h[c] = Hs[bidx * 8 + c];
         else { for (int c = 0; c < 8; ++c) s_h[c] = 0.0; s_h[0] = 1.0; s_h[4] = 1.0; }  // identity when no consensus
         info[0] = best;
         info[1] = bidx;
         s_best[0] = best;
+        s_done = 0;
     }
     __syncthreads();
     best = s_best[0];
     for (int iter = 0; iter < HG_GN_ITERS && best >= 4; ++iter) {
+        if (s_done) break;
         double acc[45];
+#pragma unroll
         for (int k = 0; k < 45; ++k) acc[k] = 0.0;
         int nin = 0;
         double h[8];
+#pragma unroll
         for (int c = 0; c < 8; ++c) h[c] = s_h[c];
-        for (int i = tid; i < n; i += blockDim.x) {
-            double x = pts[i].x, y = pts[i].y;
-            double w = h[6] * x + h[7] * y + 1.0;
-            double iw = 1.0 / w;
-            double uh = (h[0] * x + h[1] * y + h[2]) * iw, vh = (h[3] * x + h[4] * y + h[5]) * iw;
-            double rx = pts_last[i].x - uh, ry = pts_last[i].y - vh;
+        for (int i = tid; i < n; i += HG_RT) {
+            const float2 pp = pts[i], pl = pts_last[i];
+            const double x = pp.x, y = pp.y;
+            const double w = h[6] * x + h[7] * y + 1.0;
+            const double iw = 1.0 / w;
+            const double uh = (h[0] * x + h[1] * y + h[2]) * iw, vh = (h[3] * x + h[4] * y + h[5]) * iw;
+            const double rx = pl.x - uh, ry = pl.y - vh;
             if (!(w > 1e-9) || rx * rx + ry * ry > HG_THR2) continue;
             ++nin;
-            double Ju[8] = {x * iw, y * iw, iw, 0, 0, 0, -uh * x * iw, -uh * y * iw};
-            double Jv[8] = {0, 0, 0, x * iw, y * iw, iw, -vh * x * iw, -vh * y * iw};
+            const double Ju[8] = {x * iw, y * iw, iw, 0, 0, 0, -uh * x * iw, -uh * y * iw};
+            const double Jv[8] = {0, 0, 0, x * iw, y * iw, iw, -vh * x * iw, -vh * y * iw};
             int k = 0;
+#pragma unroll
             for (int a = 0; a < 8; ++a)
+#pragma unroll
                 for (int b = a; b < 8; ++b) acc[k++] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+#pragma unroll
             for (int a = 0; a < 8; ++a) acc[36 + a] += Ju[a] * rx + Jv[a] * ry;
             acc[44] += rx * rx + ry * ry;
         }
+#pragma unroll
         for (int k = 0; k < 45; ++k) {
             double v = acc[k];
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) s_acc[wid][k] = v;
         }
         for (int o = 16; o > 0; o >>= 1) nin += __shfl_xor_sync(0xffffffffu, nin, o);
-        if (tid == 0) s_nin = 0;
+        if (lane == 0) s_nin[wid] = nin;
         __syncthreads();
-        if (lane == 0) atomicAdd(&s_nin, nin);
+        if (tid < 45) { double v = 0; for (int w2 = 0; w2 < NW; ++w2) v += s_acc[w2][tid]; s_tot[tid] = v; }
         __syncthreads();
         if (tid == 0) {
-            double tot[45];
-            for (int k = 0; k < 45; ++k) { double v = 0; for (int w2 = 0; w2 < 32; ++w2) v += s_acc[w2][k]; tot[k] = v; }
-            if (s_nin >= 8) {
+            int tn = 0;
+            for (int w2 = 0; w2 < NW; ++w2) tn += s_nin[w2];
+            if (tn >= 8) {
                 double A[8][9];
                 int k = 0;
                 for (int a = 0; a < 8; ++a)
-                    for (int b = a; b < 8; ++b) { A[a][b] = tot[k]; A[b][a] = tot[k]; ++k; }
-                for (int a = 0; a < 8; ++a) { A[a][8] = tot[36 + a]; A[a][a] *= 1.0 + 1e-9; }
+                    for (int b = a; b < 8; ++b) { A[a][b] = s_tot[k]; A[b][a] = s_tot[k]; ++k; }
+                for (int a = 0; a < 8; ++a) { A[a][8] = s_tot[36 + a]; A[a][a] *= 1.0 + 1e-9; }
                 if (solve8(A)) {
                     bool fin = true;
-                    for (int c = 0; c < 8; ++c) fin = fin && isfinite(A[c][8]);
+                    double mx = 0.0;
+                    for (int c = 0; c < 8; ++c) { fin = fin && isfinite(A[c][8]); mx = fmax(mx, fabs(A[c][8])); }
                     if (fin) for (int c = 0; c < 8; ++c) s_h[c] += A[c][8];
-                }
-            }
-            info[2] = s_nin;
+                    if (fin && mx < 1e-12) s_done = 1;
+                } else s_done = 1;
+            } else s_done = 1;
+            info[2] = tn;
         }
         __syncthreads();
     }
@@ -324,7 +341,7 @@ int homography_estimate(sindyn_base *ctx, HomographyStage *g)
 {
     LAUNCH(ctx, k_homog_hypotheses, cdiv(HG_M * 32, 256), 256, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs,
            g->scores);
-    LAUNCH(ctx, k_homog_select_refine, 1, 1024, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs, g->scores,
+    LAUNCH(ctx, k_homog_select_refine, 1, HG_RT, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs, g->scores,
            g->H_dev, g->n_pairs + 1);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;

@@ -175,7 +175,11 @@ __global__ void k_thresholds(const unsigned int *__restrict__ hist, const unsign
                              float *__restrict__ thr)
 {
     __shared__ int scratch[256];
+    __shared__ unsigned int sh[256];
+    for (int j = threadIdx.x; j < 256; j += blockDim.x) sh[j] = hist[j];   // one coalesced read instead of ~1500 serial global loads
+    __syncthreads();
     if (threadIdx.x != 0) return;
+    hist = sh;
     const int total = W * H;
     float thred1 = (float)otsu_8u(hist, total);
     float thred2 = (float)triangle_8u(hist, scratch);
