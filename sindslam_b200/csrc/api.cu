@@ -20,7 +20,7 @@ extern "C" void sindyn_default_config(sindyn_config *c, int width, int height)
     c->brox_alpha = 0.197f; c->brox_gamma = 50.0f; c->brox_pyr_scale = 0.8f;
     c->brox_inner = 10; c->brox_outer = 77; c->brox_solver = 10;
     c->brox_omega = 1.99f;
-    c->refine = 0;   // cv::VariationalRefinement pass (DynaDetect.cc:1133-1143): set to 1 once varref.cu is built
+    c->refine = 1;   // cv::VariationalRefinement pass (DynaDetect.cc:1133-1143)
     c->n_row_cluster = 3; c->n_col_cluster = 4;
     c->depth_weight = 1.5f;
     c->device = 0;

@@ -206,17 +206,33 @@ __global__ void __launch_bounds__(256) k_homog_hypotheses(const float2 *__restri
     }
 }
 
-// single CTA: best consensus, then Gauss-Newton on the inliers (re-selected every iteration).
-// 256 threads: the 45 normal-equation accumulators of a thread stay in registers (no local-memory spills), the
-// cross-warp reduction is done by 45 threads in parallel, and the loop stops once the update is below 1e-12.
+// ------------------------------------------------------------------ locally optimised consensus search
+// rank of every hypothesis by inlier count (ties: lower index first); the HG_TOPK best go on to refinement
+__global__ void __launch_bounds__(256) k_homog_rank(const int *__restrict__ scores, int *__restrict__ top)
+{
+    __shared__ int sc[HG_M];
+    for (int i = threadIdx.x; i < HG_M; i += blockDim.x) sc[i] = scores[i];
+    __syncthreads();
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= HG_M) return;
+    const int mine = sc[m];
+    int rank = 0;
+    for (int j = 0; j < HG_M; ++j) rank += (sc[j] > mine) || (sc[j] == mine && j < m);
+    if (rank < HG_TOPK) top[rank] = m;
+}
+
+// One CTA per candidate: Gauss-Newton on the reprojection error of the inliers (re-selected every iteration), then the
+// final consensus size.  A minimal-sample hypothesis that looks second best can refine into the largest consensus set
+// (two competing planes), which is what the reference's RHO estimator returns -- hence HG_TOPK candidates, not one.
+// 256 threads: the 45 normal-equation accumulators of a thread stay in registers, the cross-warp reduction is done by
+// 45 threads in parallel, and the loop stops once the update is below 1e-12.
 #define HG_RT 256
-__global__ void __launch_bounds__(HG_RT) k_homog_select_refine(const float2 *__restrict__ pts, const float2 *__restrict__ pts_last,
-                                                               const int *__restrict__ n_ptr, const double *__restrict__ Hs,
-                                                               const int *__restrict__ scores, double *__restrict__ H_out,
-                                                               int *__restrict__ info)
+__global__ void __launch_bounds__(HG_RT) k_homog_refine(const float2 *__restrict__ pts, const float2 *__restrict__ pts_last,
+                                                        const int *__restrict__ n_ptr, const double *__restrict__ Hs,
+                                                        const int *__restrict__ scores, const int *__restrict__ top,
+                                                        double *__restrict__ Hc, double *__restrict__ cand_cost)
 {
     constexpr int NW = HG_RT / 32;
-    __shared__ int s_best[NW], s_bidx[NW];
     __shared__ double s_acc[NW][45];
     __shared__ double s_tot[45];
     __shared__ double s_h[8];
@@ -224,29 +240,20 @@ __global__ void __launch_bounds__(HG_RT) k_homog_select_refine(const float2 *__r
     __shared__ int s_done;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = *n_ptr;
-    int best = -2, bidx = 0;
-    for (int m = tid; m < HG_M; m += HG_RT)
-        if (scores[m] > best) { best = scores[m]; bidx = m; }
-    for (int o = 16; o > 0; o >>= 1) {
-        int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-    }
-    if (lane == 0) { s_best[wid] = best; s_bidx[wid] = bidx; }
-    __syncthreads();
+    const int cand = blockIdx.x;
+    const int m = top[cand];
+    const int best = scores[m];
     if (tid == 0) {
-        for (int w2 = 1; w2 < NW; ++w2)
-            if (s_best[w2] > best || (s_best[w2] == best && s_bidx[w2] < bidx)) { best = s_best[w2]; bidx = s_bidx[w2]; }
-        if (best >= 4) for (int c = 0; c < 8; ++c) s_h[c] = Hs[bidx * 8 + c];
+        if (best >= 4) for (int c = 0; c < 8; ++c) s_h[c] = Hs[m * 8 + c];
         else { for (int c = 0; c < 8; ++c) s_h[c] = 0.0; s_h[0] = 1.0; s_h[4] = 1.0; }  // identity when no consensus
-        info[0] = best;
-        info[1] = bidx;
-        s_best[0] = best;
-        s_done = 0;
+        s_done = best >= 4 ? 0 : 1;
     }
     __syncthreads();
-    best = s_best[0];
-    for (int iter = 0; iter < HG_GN_ITERS && best >= 4; ++iter) {
-        if (s_done) break;
+    int final_n = 0;
+    double final_sse = 0.0;
+    for (int iter = 0; iter <= HG_GN_ITERS; ++iter) {
+        // the last pass (iter == HG_GN_ITERS, or right after convergence) only evaluates the consensus of the final H
+        const bool last = iter == HG_GN_ITERS || s_done;
         double acc[45];
 #pragma unroll
         for (int k = 0; k < 45; ++k) acc[k] = 0.0;
@@ -263,6 +270,8 @@ __global__ void __launch_bounds__(HG_RT) k_homog_select_refine(const float2 *__r
             const double rx = pl.x - uh, ry = pl.y - vh;
             if (!(w > 1e-9) || rx * rx + ry * ry > HG_THR2) continue;
             ++nin;
+            acc[44] += rx * rx + ry * ry;
+            if (last) continue;
             const double Ju[8] = {x * iw, y * iw, iw, 0, 0, 0, -uh * x * iw, -uh * y * iw};
             const double Jv[8] = {0, 0, 0, x * iw, y * iw, iw, -vh * x * iw, -vh * y * iw};
             int k = 0;
@@ -272,7 +281,6 @@ __global__ void __launch_bounds__(HG_RT) k_homog_select_refine(const float2 *__r
                 for (int b = a; b < 8; ++b) acc[k++] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
 #pragma unroll
             for (int a = 0; a < 8; ++a) acc[36 + a] += Ju[a] * rx + Jv[a] * ry;
-            acc[44] += rx * rx + ry * ry;
         }
 #pragma unroll
         for (int k = 0; k < 45; ++k) {
@@ -285,9 +293,12 @@ __global__ void __launch_bounds__(HG_RT) k_homog_select_refine(const float2 *__r
         __syncthreads();
         if (tid < 45) { double v = 0; for (int w2 = 0; w2 < NW; ++w2) v += s_acc[w2][tid]; s_tot[tid] = v; }
         __syncthreads();
+        int tn = 0;
+        for (int w2 = 0; w2 < NW; ++w2) tn += s_nin[w2];
+        final_n = tn;
+        final_sse = s_tot[44];
+        if (last) break;
         if (tid == 0) {
-            int tn = 0;
-            for (int w2 = 0; w2 < NW; ++w2) tn += s_nin[w2];
             if (tn >= 8) {
                 double A[8][9];
                 int k = 0;
@@ -299,17 +310,32 @@ __global__ void __launch_bounds__(HG_RT) k_homog_select_refine(const float2 *__r
                     double mx = 0.0;
                     for (int c = 0; c < 8; ++c) { fin = fin && isfinite(A[c][8]); mx = fmax(mx, fabs(A[c][8])); }
                     if (fin) for (int c = 0; c < 8; ++c) s_h[c] += A[c][8];
-                    if (fin && mx < 1e-12) s_done = 1;
+                    if (!fin || mx < 1e-12) s_done = 1;
                 } else s_done = 1;
             } else s_done = 1;
-            info[2] = tn;
         }
         __syncthreads();
     }
     if (tid == 0) {
-        for (int c = 0; c < 8; ++c) H_out[c] = s_h[c];
-        H_out[8] = 1.0;
+        for (int c = 0; c < 8; ++c) Hc[cand * 8 + c] = s_h[c];
+        cand_cost[cand * 2] = best >= 4 ? (double)final_n : -1.0;
+        cand_cost[cand * 2 + 1] = final_sse;
     }
+}
+
+// largest refined consensus (ties: smaller squared error, then better original rank)
+__global__ void k_homog_pick(const double *__restrict__ Hc, const double *__restrict__ cand_cost, const int *__restrict__ top,
+                             const int *__restrict__ scores, double *__restrict__ H_out, int *__restrict__ info)
+{
+    if (threadIdx.x) return;
+    int bi = 0;
+    for (int c = 1; c < HG_TOPK; ++c)
+        if (cand_cost[2 * c] > cand_cost[2 * bi] || (cand_cost[2 * c] == cand_cost[2 * bi] && cand_cost[2 * c + 1] < cand_cost[2 * bi + 1])) bi = c;
+    for (int c = 0; c < 8; ++c) H_out[c] = Hc[bi * 8 + c];
+    H_out[8] = 1.0;
+    info[0] = scores[top[0]];
+    info[1] = top[bi];
+    info[2] = (int)cand_cost[2 * bi];
 }
 
 int homography_init(sindyn_base *ctx, HomographyStage *g, int W, int H)
@@ -324,6 +350,9 @@ int homography_init(sindyn_base *ctx, HomographyStage *g, int W, int H)
     SD_CHECK(ctx->dalloc(&g->Hs, 8 * HG_M));
     SD_CHECK(ctx->dalloc(&g->scores, HG_M));
     SD_CHECK(ctx->dalloc(&g->H_dev, 9));
+    SD_CHECK(ctx->dalloc(&g->top, HG_TOPK));
+    SD_CHECK(ctx->dalloc(&g->Hc, 8 * HG_TOPK));
+    SD_CHECK(ctx->dalloc(&g->cand_cost, 2 * HG_TOPK));
     return SINDYN_OK;
 }
 
@@ -341,8 +370,10 @@ int homography_estimate(sindyn_base *ctx, HomographyStage *g)
 {
     LAUNCH(ctx, k_homog_hypotheses, cdiv(HG_M * 32, 256), 256, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs,
            g->scores);
-    LAUNCH(ctx, k_homog_select_refine, 1, HG_RT, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs, g->scores,
-           g->H_dev, g->n_pairs + 1);
+    LAUNCH(ctx, k_homog_rank, cdiv(HG_M, 256), 256, 0, g->scores, g->top);
+    LAUNCH(ctx, k_homog_refine, HG_TOPK, HG_RT, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs, g->scores, g->top,
+           g->Hc, g->cand_cost);
+    LAUNCH(ctx, k_homog_pick, 1, 32, 0, g->Hc, g->cand_cost, g->top, g->scores, g->H_dev, g->n_pairs + 1);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }

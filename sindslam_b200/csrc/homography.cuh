@@ -7,6 +7,7 @@
 #define HG_M 2048             // hypotheses
 #define HG_THR2 9.0           // (3 px)^2: cv::findHomography's default ransacReprojThreshold
 #define HG_GN_ITERS 10
+#define HG_TOPK 64             // best minimal-sample hypotheses that are refined before the final choice
 
 struct HomographyStage {
     int W = 0, H = 0;
@@ -16,6 +17,8 @@ struct HomographyStage {
     double *Hs = nullptr;
     int *scores = nullptr;
     double *H_dev = nullptr;     // 3x3 row-major result
+    int *top = nullptr;          // HG_TOPK best hypotheses
+    double *Hc = nullptr, *cand_cost = nullptr;  // refined candidates: 8 parameters; (consensus size, squared error)
 };
 
 int homography_init(sindyn_base *ctx, HomographyStage *g, int W, int H);

@@ -7,6 +7,7 @@ struct VarRefStage {
     bool built = false;
     float *buf = nullptr;
     float *planes[32] = {};
+    float **planes_dev = nullptr;   // device copy of the plane table
 };
 
 int varref_init(sindyn_base *ctx, VarRefStage *v, int w, int h);

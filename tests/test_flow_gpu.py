@@ -103,3 +103,24 @@ def test_residual_pose_variant(sd, seq_c1):
     assert np.median(mag[stat]) < 0.5 < np.median(mag[dyn])
     agree = (lo == olo).mean()
     assert agree > 0.9999
+
+
+def test_variational_refinement_vs_cv2(seq_c1):
+    """sindyn_flow_refine = cv::VariationalRefinement::create()->calc (DynaDetect.cc:1133-1143) against the real OpenCV
+    solver on the reference's actual input: 0.6x gray frames and the NEGATED Brox flow (quirk B#1)."""
+    from sindslam_b200.capi import SinDyn
+    _, frames = seq_c1
+    cam = synth.TUM3
+    sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor)
+    g = [orc.gray_small(orc.bgr2gray(f.bgr)) for f in frames[:3]]
+    rng = np.random.default_rng(1)
+    for k, flow in enumerate((
+            -orc.brox_flow(g[2].astype(np.float32) / 255, g[0].astype(np.float32) / 255),
+            np.zeros(g[0].shape + (2,), np.float32),
+            (rng.standard_normal(g[0].shape + (2,)) * 3).astype(np.float32))):
+        ref = orc.variational_refine(g[2], g[0], flow)
+        got = sd.flow_refine(g[2], g[0], flow)
+        err = np.abs(got - ref).max(-1)
+        print("case %d: max |gpu - cv2| %.2e px, mean %.2e, refinement moved the flow by max %.3f px" % (k, err.max(), err.mean(), np.abs(ref - flow).max()))
+        assert err.mean() < 1e-4 and err.max() < 5e-2     # tolerance parity (float rounding order / FMA), stated in DESIGN.md
+    sd.close()
