@@ -179,9 +179,10 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
     const int tid = threadIdx.x;
     const int ns2 = 2 * p.nsweeps;
     const float alpha = p.alpha, gamma = p.gamma, omega = p.omega, om1 = 1.0f - p.omega;
+    const bool same_base = p.dui == p.dub && p.dvi == p.dvb;   // one SOR chunk per inner iteration: the usual case
     // rows of the staged region that can hold image pixels (coarse levels use a fraction of the region)
     const int row_hi = min(BROX_PH, h - oy);
-    const int pp_used = (row_hi > 0 ? row_hi : 0) * BROX_PW;
+    const int pp_used = p.halo == 0 ? (row_hi > 0 ? row_hi : 0) * BROX_PW : BROX_PP;
 
     // ---- per-thread pixel table: pk = idx (12 bits) | parity << 12 | interior << 13 | live << 14 | dist << 16
     unsigned pk[2][BROX_M];
@@ -210,7 +211,14 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
             cj12[c][m] = cb1[c][m] = cb2[c][m] = cd1[c][m] = cd2[c][m] = rdu[c][m] = rdv[c][m] = 0.0f;
         }
 
-    for (int r = tid; r < 4 * BROX_NPCP; r += BROX_NT) ((float2 *)sm4)[r] = make_float2(0.0f, 0.0f);   // guards (and everything else)
+    if (p.halo == 0) {   // single-tile mode stages only the rows the level has: clear everything once
+        for (int r = tid; r < 4 * BROX_NPCP; r += BROX_NT) ((float2 *)sm4)[r] = make_float2(0.0f, 0.0f);
+    } else {             // tiled mode rewrites the whole region every launch: only the guards need zeros
+        for (int r = tid; r < 8 * BROX_G; r += BROX_NT) {
+            const int a = r / (2 * BROX_G), o = r - a * 2 * BROX_G;
+            ((float2 *)sm4)[a * BROX_NPCP + (o < BROX_G ? o : BROX_NPC + o)] = make_float2(0.0f, 0.0f);
+        }
+    }
     __syncthreads();
     for (int it = 0; it < p.n_inner; ++it) {
         // ---- phase 0: stage (du,dv) and the total flow u + du_base (radius = whole region)
@@ -222,9 +230,10 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
             if (x >= 0 && x < w && y >= 0 && y < h) {
                 const int g = y * w + x;
                 if (it == 0) {
-                    s_uv[ci] = make_float2(p.dui[g], p.dvi[g]);
-                    ta = p.u[g] + p.dub[g];
-                    tb = p.v[g] + p.dvb[g];
+                    const float bu = p.dub[g], bv = p.dvb[g];
+                    s_uv[ci] = same_base ? make_float2(bu, bv) : make_float2(p.dui[g], p.dvi[g]);
+                    ta = p.u[g] + bu;
+                    tb = p.v[g] + bv;
                 } else {   // single-tile mode: the increment of the previous inner iteration is already in shared memory
                     const float2 d = s_uv[ci];
                     ta = p.u[g] + d.x;
@@ -312,15 +321,19 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
         const unsigned thr0 = (unsigned)(p.halo > ns2 ? p.halo - ns2 : 0);
 #define BROX_HALF(C, K)                                                                                           \
     {                                                                                                             \
-        const float2 *uo = s_uv + ((C) ^ 1) * BROX_NPCP;                                                           \
-        const float2 *wo = s_w + ((C) ^ 1) * BROX_NPCP;                                                            \
+        const float2 *__restrict__ uo = s_uv + ((C) ^ 1) * BROX_NPCP;                                              \
+        float2 *__restrict__ uc_ = s_uv + (C) * BROX_NPCP;                                                         \
+        const float2 *__restrict__ wo = s_w + ((C) ^ 1) * BROX_NPCP;                                               \
+        const float2 *__restrict__ wc_ = s_w + (C) * BROX_NPCP;                                                    \
         _Pragma("unroll") for (int m = 0; m < BROX_M; ++m)                                                        \
         {                                                                                                         \
             const unsigned k_ = pk[C][m];                                                                         \
+            /* measured: skipping inactive pixels (whole warps near the region border) beats unconditional, */    \
+            /* fully predicated slots by ~15 % on the 74 x 66 tile */                                              \
             if (((k_ >> 14) & 1u) && (k_ >> 16) >= thr0 + (unsigned)(K)) {                                        \
                 const int idx = k_ & 0xfff, par = (k_ >> 12) & 1;                                                 \
                 const float2 l = uo[idx - 1 + par], r = uo[idx + par], u_ = uo[idx - BROX_HW], d = uo[idx + BROX_HW]; \
-                const float2 wown = s_w[(C) * BROX_NPCP + idx];                                                    \
+                const float2 wown = wc_[idx];                                                                     \
                 const float wl = wo[idx - 1 + par].x, wu = wo[idx - BROX_HW].y;                                   \
                 const float su = wl * l.x + wown.x * r.x + wu * u_.x + wown.y * d.x;                              \
                 const float sv = wl * l.y + wown.x * r.y + wu * u_.y + wown.y * d.y;                              \
@@ -328,7 +341,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 const float dv_new = om1 * rdv[C][m] + omega * (cb2[C][m] - cj12[C][m] * du_new + sv) * cd2[C][m]; \
                 rdu[C][m] = du_new;                                                                               \
                 rdv[C][m] = dv_new;                                                                               \
-                s_uv[(C) * BROX_NPCP + idx] = make_float2(du_new, dv_new);                                         \
+                uc_[idx] = make_float2(du_new, dv_new);                                                           \
             }                                                                                                     \
         }                                                                                                         \
         __syncthreads();                                                                                          \
