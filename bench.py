@@ -173,12 +173,49 @@ def workload_config(cam, extra=None):
     return c
 
 
+def full_pipeline_stats(cam, frames, device, refine):
+    """BASELINE configs[2] in miniature (reported next to the headline, not the headline): the whole per-frame path --
+    sindyn_detect (flow + residual + k-means + depth edges + re-clustering + decision), 15x15 dilation and the masked ORB
+    extraction -- through the host C ABI, with per-stage device milliseconds."""
+    import cv2
+    from sindslam_b200.capi import Orb, SinDyn
+    sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=device, refine=refine, stage_timing=1)
+    orb = Orb(1500, 1.2, 8, 15, 5, cam.width, cam.height, device=device)
+    sd.set_prev_frames(frames[1].bgr, frames[0].bgr)
+    grays = [cv2.cvtColor(f.bgr, cv2.COLOR_RGB2GRAY) for f in frames]
+    acc = np.zeros(16)
+    n = 0
+    t_det = t_orb = 0.0
+    nkp = 0
+    for k in range(2, len(frames)):
+        t0 = time.perf_counter()
+        mask, label = sd.detect(frames[k].bgr, frames[k].depth, k)
+        mask = sd.morph_ellipse(mask, 15, 0)
+        t1 = time.perf_counter()
+        kps, _ = orb.extract(grays[k], mask)
+        t2 = time.perf_counter()
+        if k >= 4:
+            acc += sd.stage_ms()
+            t_det += t1 - t0
+            t_orb += t2 - t1
+            nkp += len(kps)
+            n += 1
+    sd.close()
+    orb.close()
+    acc /= max(n, 1)
+    names = ["upload_gray_resize", "brox", "largemotion_refine_upsample", "homography", "residual_masks", "kmeans", "depth_edges",
+             "plane_edge_filter", "recluster", "decide", "total_device"]
+    return {"workload": "sindyn_detect + 15x15 dilation + masked ORB (1500 features, 8 levels) per frame, host buffers",
+            "pairs_per_s": n / (t_det + t_orb), "detect_ms_wall": 1e3 * t_det / n, "orb_ms_wall": 1e3 * t_orb / n,
+            "keypoints_per_frame": nkp / n, "stage_ms_device": {nm: float(acc[i]) for i, nm in enumerate(names)},
+            "plane_edges": False}
+
+
 def run_ours(args):
     import torch
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from sindslam_b200 import replicas
+    rank, world, local = replicas.rank_info()
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -186,7 +223,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from sindslam_b200.capi import SinDyn
 
-    cam, frames = make_frames(rank)
+    cam, frames = make_frames(replicas.sequence_seed_index(rank))
     refine = 0 if args.no_refine else 1
     sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=local, refine=refine)
     stream = torch.cuda.current_stream()
@@ -243,13 +280,10 @@ def run_ours(args):
     e2e_ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
 
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms = replicas.max_over_ranks([dev_ms, e2e_ms], dist, "cuda")
     if rank == 0:
-        value = world * args.steps / (dev_ms * 1e-3)
-        e2e = world * args.steps / (e2e_ms * 1e-3)
+        value = replicas.aggregate_throughput(world, args.steps, dev_ms)
+        e2e = replicas.aggregate_throughput(world, args.steps, e2e_ms)
         prof = sd.brox_profile()
         prof = sd.brox_profile()  # second call: warm
         peak, which = peaks()
@@ -264,6 +298,7 @@ def run_ours(args):
                 acc += stage.stage_ms()
         acc /= 6
         stage.close()
+        full = full_pipeline_stats(cam, frames, local, refine)
         cpu_v, cpu_n, cpu_dt = cpu_pairs_per_s(frames, "brox", budget_s=12.0, max_pairs=200)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -282,6 +317,7 @@ def run_ours(args):
                          "homography": float(acc[3]), "residual_masks": float(acc[4]), "total": float(acc[10])},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": f"{cpu_n} frame pairs in {cpu_dt:.1f} s: oracle/brox_cpu.c (OpenMP) + cv2 refinement/RHO/thresholds"},
+            "full_pipeline": full,
             "clocks": clk,
         }
         print(json.dumps(line))
