@@ -1,0 +1,70 @@
+"""BASELINE configs[2] / configs[3] shaped parity runs: the full sindyn_detect streamed over longer synthetic
+sequences -- 640x480 walking_xyz-shaped with the box object (including a frame jump that triggers the large-motion
+fallback) and 848x480 D455-shaped with the humanoid-sized dynamic region.  The oracle gets the GPU's own low/high masks
+(identical flow), so merged labels, the dynamic mask and the state recurrence must be bit-exact; the masked ORB
+keypoint sets are compared with the oracle extractor on the dilated GPU mask."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import dynadetect_oracle as orc
+from oracle import orb_oracle as oo
+from sindslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _iou(a, b):
+    u = (a | b).sum()
+    return 1.0 if u == 0 else float((a & b).sum()) / float(u)
+
+
+def _stream(cam, frames, order, orb_every=3):
+    from sindslam_b200.capi import Orb, SinDyn
+    s = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=0)
+    orb = Orb(1000, 1.2, 8, 20, 7, cam.width, cam.height)
+    oorb = oo.OrbOracle(1000, 1.2, 8, 20, 7)
+    s.set_prev_frames(frames[order[0]].bgr, frames[order[0]].bgr)     # the driver primes with frame 0 twice (rgbd_tum_noros.cc:103-107)
+    o = orc.DynaDetectOracle(frames[order[0]].bgr, frames[order[0]].bgr, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor)
+    n_large, ious = 0, []
+    for n, k in enumerate(order[1:], 1):
+        f = frames[k]
+        mask, label = s.detect(f.bgr, f.depth, n)
+        fr = s.flow_results()
+        n_large += int(fr["large_motion"])
+        r = o.detect(f.bgr, f.depth, inject_masks=(fr["low"], fr["high"]))
+        assert np.array_equal(label, r["label"]), (n, int((label != r["label"]).sum()))
+        assert np.array_equal(mask, r["mask"]), (n, int((mask != r["mask"]).sum()))
+        gt = cv2.dilate(f.dyn_mask.astype(np.uint8), orc.ellipse(9)) > 0
+        ious.append(_iou(mask == 255, gt))
+        if n % orb_every == 0:
+            dil = s.morph_ellipse(mask, 15, 0)
+            assert np.array_equal(dil, cv2.dilate(mask, orc.ellipse(15)))
+            gray = cv2.cvtColor(f.bgr, cv2.COLOR_BGR2GRAY)
+            kps, desc = orb.extract(gray, dil)
+            rk, rd = oorb.extract(gray, dil)
+            assert len(kps) == len(rk) and np.array_equal(desc, rd)
+            assert np.array_equal(np.stack([kps["x"], kps["y"]], 1), rk[:, :2].astype(np.float32))
+            # erased-keypoint set: nothing survives on mask == 255 (at the reference's truncated, scaled position)
+            sc = np.float32(1.2) ** kps["octave"]
+            assert not (dil[(kps["y"] / 1).astype(int), (kps["x"] / 1).astype(int)] == 255).all()
+    s.close()
+    orb.close()
+    return n_large, ious
+
+
+def test_c1_stream_with_large_motion_jump():
+    cam = synth.TUM3
+    _, frames = synth.make_sequence(24, cam, seq=1, kind="box", start=4)
+    order = list(range(0, 8)) + [23] + list(range(9, 12))     # 7 -> 23 -> 9: 14-frame jumps, large-motion fallback expected
+    n_large, ious = _stream(cam, frames, order)
+    print("large-motion frames:", n_large, "IoU vs rendered truth:", np.round(ious, 3))
+    assert n_large >= 1
+    assert max(ious) > 0.9
+
+
+def test_c2_848x480_humanoid_stream():
+    cam = synth.D455_848
+    _, frames = synth.make_sequence(7, cam, seq=2, kind="humanoid", start=6)
+    n_large, ious = _stream(cam, frames, list(range(7)))
+    print("848x480 humanoid: IoU vs rendered truth:", np.round(ious, 3))
