@@ -208,7 +208,7 @@ def full_pipeline_stats(cam, frames, device, refine):
     return {"workload": "sindyn_detect + 15x15 dilation + masked ORB (1500 features, 8 levels) per frame, host buffers",
             "pairs_per_s": n / (t_det + t_orb), "detect_ms_wall": 1e3 * t_det / n, "orb_ms_wall": 1e3 * t_orb / n,
             "keypoints_per_frame": nkp / n, "stage_ms_device": {nm: float(acc[i]) for i, nm in enumerate(names)},
-            "plane_edges": False}
+            "plane_edges": True}
 
 
 def run_ours(args):

@@ -180,6 +180,10 @@ int sindyn_depth_edges(sindyn_handle h, const uint16_t *depth, size_t depth_step
  * plane_edges_out: W x H u8 (imgEdgeByPlane before filtering). */
 int sindyn_plane_edges(sindyn_handle h, const uint16_t *depth, size_t depth_step, uint8_t *plane_edges_out);
 
+/* Test hook: final plane membership image of the last PEAC run (W x H ints: final plane id or -1), the planes extracted
+ * by the block-level clustering (n x 3 ints: root block id, point count, final plane id; capacity 64), and the counts. */
+int sindyn_get_peac_debug(sindyn_handle h, int *membership_out, int *planes_rid_n_final, int *n_planes_out, int *n_final_out);
+
 /* Plane-edge filtering + imgOccluded1/2 (DynaDetect.cc:598-641). Inputs: plane edges (raw),
  * gradient edges, end points. Outputs occluded1 (all edges, CLOSE 3x3) and occluded2 (plane edges kept). */
 int sindyn_filter_plane_edges(sindyn_handle h, const uint8_t *plane_edges, const uint8_t *grad_edges,

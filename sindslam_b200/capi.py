@@ -75,6 +75,7 @@ SIGNATURES = {
     "sindyn_cluster_order": (_i, [_vp, _vp, _vp, _ip]),
     "sindyn_depth_edges": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _i, _ip]),
     "sindyn_plane_edges": (_i, [_vp, _vp, _sz, _vp]),
+    "sindyn_get_peac_debug": (_i, [_vp, _vp, _vp, _ip, _ip]),
     "sindyn_filter_plane_edges": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sindyn_recluster": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _ip]),
     "sindyn_dynamic_decide": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -336,6 +337,13 @@ class SinDyn:
         out = np.empty((self.H, self.W), np.uint8)
         self._ck(self.lib.sindyn_plane_edges(self.h, _p(depth), depth.strides[0], _p(out)), "plane_edges")
         return out
+
+    def peac_debug(self):
+        member = np.zeros((self.H, self.W), np.int32)
+        planes = np.zeros((64, 3), np.int32)
+        n, nf = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.sindyn_get_peac_debug(self.h, _p(member), _p(planes), C.byref(n), C.byref(nf)), "get_peac_debug")
+        return dict(member=member, planes=planes[:n.value].copy(), n_final=nf.value)
 
     def filter_plane_edges(self, plane_edges, grad_edges, endpoints):
         pe, ge = _u8(plane_edges), _u8(grad_edges)

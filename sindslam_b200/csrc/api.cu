@@ -25,7 +25,7 @@ extern "C" void sindyn_default_config(sindyn_config *c, int width, int height)
     c->depth_weight = 1.5f;
     c->device = 0;
     c->use_graphs = 1;
-    c->plane_edges = 0;   // PEAC plane-contour edges (DynaDetect.cc:592-593): set to 1 once peac.cu is built
+    c->plane_edges = 1;   // PEAC plane-contour edges (DynaDetect.cc:592-593)
 }
 
 

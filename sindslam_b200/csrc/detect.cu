@@ -28,7 +28,7 @@ static int cluster_branch(sindyn_ctx *c)
     SD_CHECK(edges_run(c, &c->edges, c->depth, c->cfg.depth_scale));
     MARK(c, 12);
     if (c->cfg.plane_edges)
-        SD_CHECK(peac_run(c, &c->peac, c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges));
+        SD_CHECK(peac_run(c, &c->peac, &c->rc, c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges));
     else
         CU_CHECK(c, cudaMemsetAsync(c->plane_edges, 0, c->N, c->stream));
     SD_CHECK(plane_edge_filter_run(c, &c->rc, c->plane_edges, c->edges.grad_edges, c->edges.ep_xy, c->edges.scalars + 2));
@@ -148,7 +148,7 @@ extern "C" int sindyn_plane_edges(sindyn_handle h, const uint16_t *depth, size_t
     H_CHECK(h);
     if (!depth || !plane_edges_out) return SINDYN_ERR_INVALID;
     CU_CHECK(h, copy_in_2d(h->depth, depth, depth_step, (size_t)h->W * 2, h->H, h->stream));
-    SD_CHECK(peac_run(h, &h->peac, h->depth, h->cfg.fx, h->cfg.fy, h->cfg.cx, h->cfg.cy, h->cfg.depth_scale, h->plane_edges));
+    SD_CHECK(peac_run(h, &h->peac, &h->rc, h->depth, h->cfg.fx, h->cfg.fy, h->cfg.cx, h->cfg.cy, h->cfg.depth_scale, h->plane_edges));
     CU_CHECK(h, cudaMemcpyAsync(plane_edges_out, h->plane_edges, h->N, cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     return SINDYN_OK;
@@ -229,4 +229,11 @@ extern "C" int sindyn_dynamic_decide(sindyn_handle h, const uint8_t *mask_low, c
     if (dyna_out) CU_CHECK(h, cudaMemcpyAsync(dyna_out, h->dd.out, h->N, cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     return SINDYN_OK;
+}
+
+// test hook for the PEAC stage: final plane membership image and the extracted planes of the last sindyn_plane_edges / detect
+extern "C" int sindyn_get_peac_debug(sindyn_handle h, int *membership_out, int *planes_rid_n_final, int *n_planes_out, int *n_final_out)
+{
+    H_CHECK(h);
+    return peac_get_debug(h, &h->peac, membership_out, planes_rid_n_final, n_planes_out, n_final_out);
 }

@@ -1,9 +1,646 @@
-// peac.cu -- placeholder until the AHC plane-fitter kernels land (fails loudly; create the handle with plane_edges = 0).
+// peac.cu -- PEAC plane-contour edges of DynaDetect::CalOccluded (ORB_SLAM2/src/DynaDetect.cc:558-593) on the device:
+// the agglomerative hierarchical clustering plane fitter of ORB_SLAM2/include/PEAC (AHCPlaneFitter.hpp, AHCPlaneSeg.hpp,
+// AHCParamSet.hpp, DisjointSet.hpp) with the parameters actually in force (16x16 blocks, INIT_STRICT, minSupport 2000,
+// metre coordinates against mm-tuned thresholds), followed by per-plane CLOSE 3x3 + external contours
+// drawn with thickness 2 (AHCPlaneFitter.hpp:366-399).
+//
+//   k_peac_blocks      one thread per 16x16 block: the nine second-order sums in double, accumulated in the reference's
+//                      raster order (bit-identical statistics), PCA plane (Jacobi 3x3) -> node table
+//   k_peac_ahc         ONE CTA: initial graph edges, min-MSE binary heap in shared memory, union-find by size.  The serial
+//                      control (pop / merge / extract) runs on thread 0; the candidate evaluation of a pop (all graph
+//                      neighbours: merged statistics + eigen solve) is spread over the CTA's threads.
+//   k_peac_blockmap    block erosion (ERODE_ALL_BORDER) and the initial membership image
+//   k_peac_grow        pixel-level region growing as a parallel min-distance label relaxation (tile-local iterations in
+//                      shared memory).  The reference grows with ONE serial FIFO queue (AHCPlaneFitter.hpp:546-594), whose
+//                      result depends on the visiting order at pixels contested by two planes; the relaxation converges
+//                      to the order-independent fixed point instead (documented deviation; plane-edge
+//                      agreement with the serial oracle is measured in tests/test_peac_gpu.py).
+//   k_peac_merge       final re-merge of planes that met during growing (serial, <= 64 planes) + relabel map
+//   plane_contours_run (recluster.cu) CLOSE 3x3, external contours, thickness-2 drawing on membership bitsets
 #include "peac.cuh"
 
-int peac_init(sindyn_base *, PeacStage *p, int W, int H) { p->W = W; p->H = H; return SINDYN_OK; }
-int peac_run(sindyn_base *ctx, PeacStage *, const uint16_t *, float, float, float, float, float, uint8_t *)
+#include "recluster.cuh"
+
+#define PEAC_WIN 16
+#define PEAC_MAXB 2048          // blocks (53 x 30 = 1590 at 848 x 480)
+#define PEAC_MAXP 64            // extracted planes
+#define PEAC_MIN_SUPPORT 2000
+#define PEAC_HEAP (2 * PEAC_MAXB)
+#define PEAC_MAXE (2 * PEAC_MAXB)
+
+struct PeacNode {               // ahc::PlaneSeg (AHCPlaneSeg.hpp:29-188), indexed by root block id
+    double st[9];               // sx sy sz sxx syy szz sxy syz sxz
+    double center[3], normal[3], mse;
+    int N, version, alive, valid;
+};
+
+struct PeacPlane { double center[3], normal[3], mse, thr; int N, rid, valid, final_id; double st[9]; };
+
+struct PeacControl {
+    int n_planes, n_final, overflow, grow_changed;
+    int grow_flag[128];                      // launch i of the region growing changed something
+    int parent[PEAC_MAXB], size[PEAC_MAXB];
+    int blk_map[PEAC_MAXB];
+    PeacPlane pl[PEAC_MAXP];
+    unsigned long long conn[PEAC_MAXP];      // planes that met during region growing with similar normals
+};
+
+struct PeacImpl {
+    PeacNode *nodes = nullptr;
+    PeacControl *ctl = nullptr;
+    int *label = nullptr;        // membershipImg
+    float *dist = nullptr;
+    ulonglong2 *PB = nullptr;    // final plane membership bitset
+    int Nw = 0, Nh = 0;
+};
+
+// ---------------------------------------------------------------- small dense eigen solver
+// eigen decomposition of a symmetric 3x3 (cyclic Jacobi, double): returns the smallest eigenvalue and its vector.
+// (reference: Eigen::SelfAdjointEigenSolver through LA::eig33sym, eig33sym.hpp:45-51 -- un-vendored; results agree to
+// a few ulp of the largest eigenvalue)
+__device__ void eig33_min(const double K[3][3], double &lmin, double v[3], double ev[3])
 {
-    ctx->err = "PEAC plane edges are not built yet; create the handle with plane_edges = 0";
-    return SINDYN_ERR_STATE;
+    double a[3][3] = {{K[0][0], K[0][1], K[0][2]}, {K[0][1], K[1][1], K[1][2]}, {K[0][2], K[1][2], K[2][2]}};
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (off <= 1e-40 * diag || off == 0.0) break;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int p = r == 2 ? 1 : 0, q = r == 0 ? 1 : 2;   // (0,1) (0,2) (1,2)
+            if (a[p][q] == 0.0) continue;
+            const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+            const double app = a[p][p], aqq = a[q][q], apq = a[p][q];
+            a[p][p] = app - t * apq;
+            a[q][q] = aqq + t * apq;
+            a[p][q] = a[q][p] = 0.0;
+            const int k = 3 - p - q;
+            const double akp = a[k][p], akq = a[k][q];
+            a[k][p] = a[p][k] = c * akp - s * akq;
+            a[k][q] = a[q][k] = s * akp + c * akq;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double vip = V[i][p], viq = V[i][q];
+                V[i][p] = c * vip - s * viq;
+                V[i][q] = s * vip + c * viq;
+            }
+        }
+    }
+    int m = 0;
+    if (a[1][1] < a[m][m]) m = 1;
+    if (a[2][2] < a[m][m]) m = 2;
+    lmin = a[m][m];
+    v[0] = V[0][m]; v[1] = V[1][m]; v[2] = V[2][m];
+    ev[0] = a[0][0]; ev[1] = a[1][1]; ev[2] = a[2][2];
+}
+
+// Stats::compute (AHCPlaneSeg.hpp:84-116)
+__device__ void peac_compute(const double st[9], int N, double center[3], double normal[3], double &mse)
+{
+    const double sc = 1.0 / (double)N;
+    center[0] = st[0] * sc; center[1] = st[1] * sc; center[2] = st[2] * sc;
+    double K[3][3];
+    K[0][0] = st[3] - st[0] * st[0] * sc; K[0][1] = st[6] - st[0] * st[1] * sc; K[0][2] = st[8] - st[0] * st[2] * sc;
+    K[1][1] = st[4] - st[1] * st[1] * sc; K[1][2] = st[7] - st[1] * st[2] * sc;
+    K[2][2] = st[5] - st[2] * st[2] * sc;
+    K[1][0] = K[0][1]; K[2][0] = K[0][2]; K[2][1] = K[1][2];
+    double l, v[3], ev[3];
+    eig33_min(K, l, v, ev);
+    const double d = v[0] * center[0] + v[1] * center[1] + v[2] * center[2];
+    const double sgn = d <= 0 ? 1.0 : -1.0;     // normal points towards the camera
+    normal[0] = sgn * v[0]; normal[1] = sgn * v[1]; normal[2] = sgn * v[2];
+    mse = l * sc;
+}
+
+__device__ __forceinline__ double peac_t_mse(bool init, double z)
+{
+    const double t = 3e-6 * z * z + (init ? 10.0 : 17.0);
+    return t * t;
+}
+__device__ __forceinline__ double peac_t_ang_init(double z)
+{
+    const double z_near = 500.0, z_far = 6000.0, a_near = 10.0 * 3.14159265358979323846 / 180.0, a_far = 20.0 * 3.14159265358979323846 / 180.0;
+    const double cz = fmin(fmax(z, z_near), z_far);
+    const double factor = (a_far - a_near) / (z_far - z_near);
+    return cos(factor * cz + a_near - factor * z_near);
+}
+#define PEAC_SIM_MERGE 0.96592582628906831   /* cos 15 deg */
+#define PEAC_SIM_REFINE 0.93969262078590843  /* cos 20 deg */
+
+// organised cloud point (DynaDetect.cc:562-587): float arithmetic, then widened to double by OrganizedImage3D::get
+__device__ __forceinline__ bool peac_point(const uint16_t *__restrict__ depth, int W, int x, int y, float fx, float fy, float cx, float cy,
+                                           float inv_scale, double p[3])
+{
+    const float d = (float)depth[y * W + x];
+    if (d < 1e-3f) return false;
+    const float z = d * inv_scale;
+    const float px = ((float)x - cx) * z / fx, py = ((float)y - cy) * z / fy;
+    p[0] = px; p[1] = py; p[2] = z;
+    return true;
+}
+
+// ---------------------------------------------------------------- block statistics (PlaneSeg constructor)
+__global__ void k_peac_blocks(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy, float inv_scale, int Nw, int Nh,
+                              PeacNode *__restrict__ nodes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= Nw * Nh) return;
+    const int by = b / Nw, bx = b - by * Nw;
+    double st[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool ok = true;
+    for (int i = 0; i < PEAC_WIN && ok; ++i)
+        for (int j = 0; j < PEAC_WIN; ++j) {
+            double p[3];
+            if (!peac_point(depth, W, bx * PEAC_WIN + j, by * PEAC_WIN + i, fx, fy, cx, cy, inv_scale, p)) { ok = false; break; }   // INIT_STRICT
+            // depthDisContinuous: |dz| > 0.04 |z| + 20 can never hold for metre coordinates
+            st[0] += p[0]; st[1] += p[1]; st[2] += p[2];
+            st[3] += p[0] * p[0]; st[4] += p[1] * p[1]; st[5] += p[2] * p[2];
+            st[6] += p[0] * p[1]; st[7] += p[1] * p[2]; st[8] += p[0] * p[2];
+        }
+    PeacNode n;
+    for (int k = 0; k < 9; ++k) n.st[k] = ok ? st[k] : 0.0;
+    n.N = ok ? PEAC_WIN * PEAC_WIN : 0;
+    n.version = 0;
+    n.mse = 0; n.center[0] = n.center[1] = n.center[2] = 0; n.normal[0] = n.normal[1] = n.normal[2] = 0;
+    bool valid = ok;
+    if (ok) {
+        peac_compute(n.st, n.N, n.center, n.normal, n.mse);
+        valid = n.mse < peac_t_mse(true, n.center[2]);
+    }
+    n.valid = valid ? 1 : 0;
+    n.alive = valid ? 1 : 0;
+    nodes[b] = n;
+}
+
+// ---------------------------------------------------------------- AHC (Algorithm 2 edges + Algorithm 3 clustering)
+struct HeapItem { double mse; int seq, rid, version; };
+__device__ __forceinline__ bool heap_less(const HeapItem &a, const HeapItem &b) { return a.mse < b.mse || (a.mse == b.mse && a.seq < b.seq); }
+
+__global__ void __launch_bounds__(256) k_peac_ahc(PeacNode *__restrict__ nodes, PeacControl *ctl, int Nw, int Nh)
+{
+    extern __shared__ unsigned char smraw[];
+    HeapItem *heap = (HeapItem *)smraw;                     // PEAC_HEAP
+    int *parent = (int *)(heap + PEAC_HEAP);                // PEAC_MAXB
+    int *ssize = parent + PEAC_MAXB;                        // PEAC_MAXB
+    unsigned short *eu = (unsigned short *)(ssize + PEAC_MAXB), *ev = eu + PEAC_MAXE;   // edges
+    __shared__ int s_ne, s_nheap, s_seq, s_p, s_done, s_best_o, s_nex;
+    __shared__ double s_best_mse;
+    __shared__ int s_ex[PEAC_MAXP];
+    __shared__ double w_mse[8];
+    __shared__ int w_o[8];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int NB = Nw * Nh;
+    for (int b = tid; b < NB; b += nt) { parent[b] = b; ssize[b] = 1; }
+    if (tid == 0) { s_ne = 0; s_nheap = 0; s_seq = 0; s_done = 0; s_nex = 0; }
+    __syncthreads();
+    auto sim = [&](int a, int b) {
+        return fabs(nodes[a].normal[0] * nodes[b].normal[0] + nodes[a].normal[1] * nodes[b].normal[1] + nodes[a].normal[2] * nodes[b].normal[2]);
+    };
+    auto add_edge = [&](int a, int b) {
+        int e = atomicAdd(&s_ne, 1);
+        if (e < PEAC_MAXE) { eu[e] = (unsigned short)a; ev[e] = (unsigned short)b; }
+    };
+    // initGraph edges (AHCPlaneFitter.hpp:958-1014): rows and columns are independent, one thread each
+    if (tid < Nh) {
+        const int i = tid;
+        for (int j = 1; j < Nw; j += 2) {
+            const int c = i * Nw + j;
+            if (!nodes[c - 1].valid) { --j; continue; }
+            if (!nodes[c].valid) continue;
+            if (j < Nw - 1 && !nodes[c + 1].valid) { ++j; continue; }
+            const double th = peac_t_ang_init(nodes[c].center[2]);
+            if ((j < Nw - 1 && sim(c - 1, c + 1) >= th) || (j == Nw - 1 && sim(c, c - 1) >= th)) {
+                add_edge(c, c - 1);
+                if (j < Nw - 1) add_edge(c, c + 1);
+            } else --j;
+        }
+    }
+    if (tid >= 64 && tid - 64 < Nw) {
+        const int j = tid - 64;
+        for (int i = 1; i < Nh; i += 2) {
+            const int c = i * Nw + j;
+            if (!nodes[c - Nw].valid) { --i; continue; }
+            if (!nodes[c].valid) continue;
+            if (i < Nh - 1 && !nodes[c + Nw].valid) { ++i; continue; }
+            const double th = peac_t_ang_init(nodes[c].center[2]);
+            if ((i < Nh - 1 && sim(c - Nw, c + Nw) >= th) || (i == Nh - 1 && sim(c, c - Nw) >= th)) {
+                add_edge(c, c - Nw);
+                if (i < Nh - 1) add_edge(c, c + Nw);
+            } else --i;
+        }
+    }
+    __syncthreads();
+    const int NE = min(s_ne, PEAC_MAXE);
+    // heap helpers (thread 0)
+    auto heap_push = [&](HeapItem it) {
+        int i = s_nheap++;
+        while (i > 0) {
+            const int par = (i - 1) >> 1;
+            if (!heap_less(it, heap[par])) break;
+            heap[i] = heap[par];
+            i = par;
+        }
+        heap[i] = it;
+    };
+    auto heap_pop = [&]() -> HeapItem {
+        HeapItem top = heap[0];
+        HeapItem last = heap[--s_nheap];
+        int i = 0;
+        for (;;) {
+            int l = 2 * i + 1, r = l + 1;
+            if (l >= s_nheap) break;
+            int c = (r < s_nheap && heap_less(heap[r], heap[l])) ? r : l;
+            if (!heap_less(heap[c], last)) break;
+            heap[i] = heap[c];
+            i = c;
+        }
+        if (s_nheap > 0) heap[i] = last;
+        return top;
+    };
+    auto find = [&](int x) { while (parent[x] != x) x = parent[x]; return x; };
+    if (tid == 0) {
+        for (int b = 0; b < NB; ++b)
+            if (nodes[b].valid) heap_push(HeapItem{nodes[b].mse, s_seq++, b, 0});
+        if (s_ne > PEAC_MAXE) ctl->overflow = 1;
+    }
+    __syncthreads();
+    for (;;) {
+        if (tid == 0) {
+            s_p = -1;
+            while (s_nheap > 0) {
+                HeapItem it = heap_pop();
+                if (nodes[it.rid].alive && nodes[it.rid].version == it.version && parent[it.rid] == it.rid) { s_p = it.rid; break; }
+            }
+            if (s_p < 0) s_done = 1;
+        }
+        __syncthreads();
+        if (s_done) break;
+        const int p = s_p;
+        // ---- candidate merges with every live graph neighbour (AHCPlaneFitter.hpp:1092-1117)
+        double best = 1e300;
+        int best_o = -1;
+        for (int e = tid; e < NE; e += nt) {
+            const int ru = find(eu[e]), rv = find(ev[e]);
+            if (ru == rv) continue;
+            const int o = ru == p ? rv : (rv == p ? ru : -1);
+            if (o < 0 || !nodes[o].alive) continue;
+            if (sim(p, o) < PEAC_SIM_MERGE) continue;
+            double st[9], c[3], n[3], mse;
+            for (int k = 0; k < 9; ++k) st[k] = nodes[p].st[k] + nodes[o].st[k];
+            peac_compute(st, nodes[p].N + nodes[o].N, c, n, mse);
+            if (mse < best || (mse == best && o < best_o)) { best = mse; best_o = o; }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            const double om = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oo = __shfl_xor_sync(0xffffffffu, best_o, off);
+            if (oo >= 0 && (best_o < 0 || om < best || (om == best && oo < best_o))) { best = om; best_o = oo; }
+        }
+        if ((tid & 31) == 0) { w_mse[tid >> 5] = best; w_o[tid >> 5] = best_o; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < nt / 32; ++k)
+                if (w_o[k] >= 0 && (best_o < 0 || w_mse[k] < best || (w_mse[k] == best && w_o[k] < best_o))) { best = w_mse[k]; best_o = w_o[k]; }
+            bool merged = false;
+            if (best_o >= 0) {
+                const int o = best_o;
+                double st[9], c[3], n[3], mse;
+                for (int k = 0; k < 9; ++k) st[k] = nodes[p].st[k] + nodes[o].st[k];
+                const int N = nodes[p].N + nodes[o].N;
+                peac_compute(st, N, c, n, mse);
+                if (mse < peac_t_mse(false, c[2])) {
+                    // PlaneSeg(pa, pb): rid of the larger parent; DisjointSet::Union by size keeps the same root
+                    const int win = nodes[p].N >= nodes[o].N ? p : o, lose = win == p ? o : p;
+                    parent[lose] = win;
+                    ssize[win] += ssize[lose];
+                    PeacNode &w = nodes[win];
+                    for (int k = 0; k < 9; ++k) w.st[k] = st[k];
+                    for (int k = 0; k < 3; ++k) { w.center[k] = c[k]; w.normal[k] = n[k]; }
+                    w.mse = mse; w.N = N; w.version += 1; w.alive = 1;
+                    nodes[lose].alive = 0;
+                    heap_push(HeapItem{mse, s_seq++, win, w.version});
+                    merged = true;
+                }
+            }
+            if (!merged) {   // extract p (or drop it) and cut it out of the graph
+                if (nodes[p].N >= PEAC_MIN_SUPPORT) {
+                    if (s_nex < PEAC_MAXP) s_ex[s_nex++] = p; else ctl->overflow = 1;
+                }
+                nodes[p].alive = 0;
+            }
+        }
+        __syncthreads();
+    }
+    // extractedPlanes sorted by size, stable (PlaneSegSizeCmp, AHCPlaneFitter.hpp:1251-1254)
+    if (tid == 0) {
+        const int n = s_nex;
+        for (int a = 1; a < n; ++a) {
+            const int v = s_ex[a];
+            int b = a - 1;
+            while (b >= 0 && nodes[s_ex[b]].N < nodes[v].N) { s_ex[b + 1] = s_ex[b]; --b; }
+            s_ex[b + 1] = v;
+        }
+        ctl->n_planes = n;
+        for (int k = 0; k < n; ++k) {
+            const PeacNode &nd = nodes[s_ex[k]];
+            PeacPlane &pl = ctl->pl[k];
+            for (int d = 0; d < 3; ++d) { pl.center[d] = nd.center[d]; pl.normal[d] = nd.normal[d]; }
+            for (int d = 0; d < 9; ++d) pl.st[d] = nd.st[d];
+            pl.mse = nd.mse; pl.thr = 9.0 * nd.mse + 1e-5; pl.N = nd.N; pl.rid = s_ex[k]; pl.valid = 0; pl.final_id = -1;
+            ctl->conn[k] = 0ull;
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < NB; b += nt) { ctl->parent[b] = parent[b]; ctl->size[b] = ssize[b]; }
+}
+
+// ---------------------------------------------------------------- block erosion (findBlockMembership)
+__global__ void k_peac_blockmap(PeacControl *ctl, int Nw, int Nh)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= Nw * Nh) return;
+    auto find = [&](int x) { while (ctl->parent[x] != x) x = ctl->parent[x]; return x; };
+    const int i = b / Nw, j = b - i * Nw;
+    const int setid = find(b);
+    int plid = -1;
+    if (ctl->size[setid] * PEAC_WIN * PEAC_WIN >= PEAC_MIN_SUPPORT) {
+        bool same = true;   // ERODE_ALL_BORDER: every 4-neighbour block must be in the same set
+        if (j > 0) same &= find(b - 1) == setid;
+        if (j < Nw - 1) same &= find(b + 1) == setid;
+        if (i > 0) same &= find(b - Nw) == setid;
+        if (i < Nh - 1) same &= find(b + Nw) == setid;
+        if (same)
+            for (int k = 0; k < ctl->n_planes; ++k)
+                if (ctl->pl[k].rid == setid) { plid = k; break; }
+    }
+    ctl->blk_map[b] = plid;
+    if (plid >= 0) ctl->pl[plid].valid = 1;
+}
+
+__global__ void k_peac_init_labels(const PeacControl *__restrict__ ctl, int W, int H, int Nw, int *__restrict__ label, float *__restrict__ dist)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    label[y * W + x] = ctl->blk_map[(y / PEAC_WIN) * Nw + x / PEAC_WIN];
+    dist[y * W + x] = 3.402823466e+38f;
+}
+
+// ---------------------------------------------------------------- region growing (floodFill) as label relaxation
+#define PG_T 32
+#define PG_ITERS 24
+__global__ void __launch_bounds__(PG_T *PG_T / 4) k_peac_grow(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy,
+                                                              float inv_scale, int Nw, PeacControl *ctl, int *__restrict__ label, float *__restrict__ dist,
+                                                              int launch_idx)
+{
+    if (launch_idx > 0 && ctl->grow_flag[launch_idx - 1] == 0) return;   // converged: the remaining launches fall through
+    // tile of PG_T x PG_T pixels + 1-px halo; every thread owns 4 pixels of the tile
+    __shared__ int s_l[PG_T + 2][PG_T + 2];
+    __shared__ int s_changed;
+    const int tx0 = blockIdx.x * PG_T, ty0 = blockIdx.y * PG_T;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    for (int t = tid; t < (PG_T + 2) * (PG_T + 2); t += nt) {
+        const int ly = t / (PG_T + 2), lx = t - ly * (PG_T + 2);
+        const int x = tx0 + lx - 1, y = ty0 + ly - 1;
+        s_l[ly][lx] = (x >= 0 && x < W && y >= 0 && y < H) ? label[y * W + x] : -1;
+    }
+    // per-thread pixels
+    int px[4], py[4], lab[4];
+    float dd[4];
+    bool grow[4];
+    double P[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int t = tid + k * nt;
+        const int ly = t / PG_T, lx = t - ly * PG_T;
+        px[k] = tx0 + lx; py[k] = ty0 + ly;
+        grow[k] = false;
+        lab[k] = -1; dd[k] = 3.402823466e+38f;
+        if (px[k] < W && py[k] < H) {
+            const int i = py[k] * W + px[k];
+            lab[k] = label[i];
+            dd[k] = dist[i];
+            // only pixels of "black" blocks grow (AHCPlaneFitter.hpp:567-568), and only where the depth is valid
+            grow[k] = ctl->blk_map[(py[k] / PEAC_WIN) * Nw + px[k] / PEAC_WIN] < 0 && peac_point(depth, W, px[k], py[k], fx, fy, cx, cy, inv_scale, P[k]);
+        }
+    }
+    __syncthreads();
+    bool any_change = false;
+    for (int it = 0; it < PG_ITERS; ++it) {
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        int nl[4];
+        float nd[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            nl[k] = lab[k]; nd[k] = dd[k];
+            if (!grow[k]) continue;
+            const int lx = px[k] - tx0 + 1, ly = py[k] - ty0 + 1;
+            const int nb[4] = {s_l[ly][lx - 1], s_l[ly][lx + 1], s_l[ly - 1][lx], s_l[ly + 1][lx]};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int pl = nb[q];
+                if (pl < 0 || pl == nl[k]) continue;
+                bool seen = false;
+                for (int r = 0; r < q; ++r) seen |= nb[r] == pl;
+                if (seen) continue;
+                const PeacPlane &pp = ctl->pl[pl];
+                const float cd = (float)fabs(pp.normal[0] * (P[k][0] - pp.center[0]) + pp.normal[1] * (P[k][1] - pp.center[1]) +
+                                             pp.normal[2] * (P[k][2] - pp.center[2]));
+                if (!((double)cd * (double)cd < pp.thr)) continue;     // point-plane distance within 3 sigma
+                if (lab[k] >= 0 && lab[k] != pl) {                     // two planes meet: potential merge (:575-580)
+                    const PeacPlane &pa = ctl->pl[lab[k]];
+                    const double s = fabs(pa.normal[0] * pp.normal[0] + pa.normal[1] * pp.normal[1] + pa.normal[2] * pp.normal[2]);
+                    if (s >= PEAC_SIM_REFINE && !((ctl->conn[lab[k]] >> pl) & 1ull)) {
+                        atomicOr(&ctl->conn[lab[k]], 1ull << pl);
+                        atomicOr(&ctl->conn[pl], 1ull << lab[k]);
+                    }
+                }
+                if (cd < nd[k] || (cd == nd[k] && pl < nl[k])) { nd[k] = cd; nl[k] = pl; }
+            }
+        }
+        __syncthreads();
+        bool ch = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (grow[k] && nl[k] != lab[k]) {
+                lab[k] = nl[k]; dd[k] = nd[k];
+                s_l[py[k] - ty0 + 1][px[k] - tx0 + 1] = lab[k];
+                ch = true;
+            }
+        if (ch) { s_changed = 1; any_change = true; }
+        __syncthreads();
+        if (!s_changed) break;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (grow[k] && px[k] < W && py[k] < H) {
+            const int i = py[k] * W + px[k];
+            label[i] = lab[k];
+            dist[i] = dd[k];
+        }
+    if (any_change) ctl->grow_flag[launch_idx] = 1;
+}
+
+// ---------------------------------------------------------------- final re-merge (second ahCluster) + relabel map
+__global__ void k_peac_merge(PeacControl *ctl)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const int n0 = ctl->n_planes;
+    // nodes: 0..n0-1 = extracted planes, merged nodes appended
+    const int MAXN = 2 * PEAC_MAXP;
+    double st[MAXN][9], nrm[MAXN][3], mse[MAXN], cz[MAXN];
+    int N[MAXN], rid[MAXN], seq[MAXN];
+    bool alive[MAXN], inq[MAXN];
+    unsigned long long adj[MAXN][2];
+    int parent[PEAC_MAXP];     // union-find over the OLD plane ids (stands for ds->Union on their root block ids)
+    int psize[PEAC_MAXP];
+    int nn = n0;
+    for (int k = 0; k < n0; ++k) {
+        const PeacPlane &p = ctl->pl[k];
+        for (int d = 0; d < 9; ++d) st[k][d] = p.st[d];
+        for (int d = 0; d < 3; ++d) nrm[k][d] = p.normal[d];
+        mse[k] = p.mse; cz[k] = p.center[2]; N[k] = p.N; rid[k] = k; seq[k] = k;
+        alive[k] = p.valid != 0; inq[k] = alive[k];
+        adj[k][0] = p.valid ? ctl->conn[k] : 0ull; adj[k][1] = 0ull;
+        parent[k] = k; psize[k] = p.N / (PEAC_WIN * PEAC_WIN);   // DisjointSet sizes count blocks
+    }
+    for (int k = 0; k < n0; ++k)      // connections only between valid planes
+        for (int j = 0; j < n0; ++j)
+            if (!(ctl->pl[j].valid) || !(ctl->pl[k].valid)) adj[k][0] &= ~(1ull << j);
+    auto has = [&](int a, int b) { return (adj[a][b >> 6] >> (b & 63)) & 1ull; };
+    auto setb = [&](int a, int b) { adj[a][b >> 6] |= 1ull << (b & 63); };
+    auto clrb = [&](int a, int b) { adj[a][b >> 6] &= ~(1ull << (b & 63)); };
+    auto find = [&](int x) { while (parent[x] != x) x = parent[x]; return x; };
+    int n_final_nodes = 0;
+    for (;;) {
+        int p = -1;   // min-MSE live queue entry
+        for (int k = 0; k < nn; ++k)
+            if (inq[k] && alive[k] && (p < 0 || mse[k] < mse[p] || (mse[k] == mse[p] && seq[k] < seq[p]))) p = k;
+        if (p < 0) break;
+        inq[p] = false;
+        int best = -1;
+        double bst[9], bc[3], bn[3], bm = 0;
+        for (int o = 0; o < nn; ++o) {
+            if (!has(p, o) || !alive[o]) continue;
+            const double s = fabs(nrm[p][0] * nrm[o][0] + nrm[p][1] * nrm[o][1] + nrm[p][2] * nrm[o][2]);
+            if (s < PEAC_SIM_MERGE) continue;
+            double s9[9], c[3], n[3], m;
+            for (int d = 0; d < 9; ++d) s9[d] = st[p][d] + st[o][d];
+            peac_compute(s9, N[p] + N[o], c, n, m);
+            if (best < 0 || bm > m) { best = o; bm = m; for (int d = 0; d < 9; ++d) bst[d] = s9[d]; for (int d = 0; d < 3; ++d) { bc[d] = c[d]; bn[d] = n[d]; } }
+        }
+        if (best >= 0 && bm < peac_t_mse(false, bc[2]) && nn < MAXN) {
+            const int o = best, q = nn++;
+            for (int d = 0; d < 9; ++d) st[q][d] = bst[d];
+            for (int d = 0; d < 3; ++d) nrm[q][d] = bn[d];
+            mse[q] = bm; cz[q] = bc[2]; N[q] = N[p] + N[o]; seq[q] = q;
+            rid[q] = N[p] >= N[o] ? rid[p] : rid[o];
+            // ds->Union(pa.rid, pb.rid) by set size (block counts are proportional to N for INIT_STRICT blocks)
+            {
+                const int a = find(rid[p]), b = find(rid[o]);
+                if (a != b) { if (psize[a] < psize[b]) { parent[a] = b; psize[b] += psize[a]; } else { parent[b] = a; psize[a] += psize[b]; } }
+            }
+            adj[q][0] = (adj[p][0] | adj[o][0]); adj[q][1] = (adj[p][1] | adj[o][1]);
+            clrb(q, p); clrb(q, o);
+            for (int k = 0; k < nn; ++k) {
+                if (has(k, p) || has(k, o)) { clrb(k, p); clrb(k, o); if (k != q) setb(k, q); }
+            }
+            adj[p][0] = adj[p][1] = adj[o][0] = adj[o][1] = 0ull;
+            alive[p] = alive[o] = false;
+            alive[q] = true; inq[q] = true;
+        } else {
+            if (N[p] >= PEAC_MIN_SUPPORT) ++n_final_nodes;
+            for (int k = 0; k < nn; ++k) clrb(k, p);
+            adj[p][0] = adj[p][1] = 0ull;
+            alive[p] = false;
+        }
+    }
+    // plidmap (AHCPlaneFitter.hpp:304-323); psize here counts planes, the reference's set sizes count blocks: use N
+    // the root of a merged set in the reference is the root block id of the side with more blocks at every union
+    int nf = 0;
+    int plidmap[PEAC_MAXP];
+    for (int k = 0; k < n0; ++k) plidmap[k] = -1;
+    for (int i = 0; i < n0; ++i) {
+        if (!ctl->pl[i].valid) continue;
+        const int root = find(i);
+        if (root == i) { if (plidmap[i] < 0) plidmap[i] = nf++; }
+        else if (plidmap[root] < 0) { plidmap[i] = plidmap[root] = nf++; }
+        else plidmap[i] = plidmap[root];
+    }
+    for (int k = 0; k < n0; ++k) ctl->pl[k].final_id = plidmap[k];
+    ctl->n_final = nf;
+    (void)n_final_nodes; (void)cz;
+}
+
+__global__ void k_peac_bits(const int *__restrict__ label, int n, const PeacControl *__restrict__ ctl, ulonglong2 *__restrict__ PB)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = label[i];
+    ulonglong2 b = make_ulonglong2(0ull, 0ull);
+    if (l >= 0) {
+        const int f = ctl->pl[l].final_id;
+        if (f >= 0 && f < 64) b.x = 1ull << f;
+    }
+    PB[i] = b;
+}
+
+// ---------------------------------------------------------------- host side
+int peac_init(sindyn_base *ctx, PeacStage *p, int W, int H)
+{
+    p->W = W; p->H = H;
+    PeacImpl *im = new PeacImpl();
+    p->impl = im;
+    im->Nw = W / PEAC_WIN; im->Nh = H / PEAC_WIN;
+    if (im->Nw * im->Nh > PEAC_MAXB || im->Nw > 128 || im->Nh > 64) { ctx->err = "peac: image too large for the block tables"; return SINDYN_ERR_INVALID; }
+    SD_CHECK(ctx->dalloc(&im->nodes, PEAC_MAXB));
+    SD_CHECK(ctx->dalloc(&im->ctl, 1));
+    SD_CHECK(ctx->dalloc(&im->label, (size_t)W * H));
+    SD_CHECK(ctx->dalloc(&im->dist, (size_t)W * H));
+    SD_CHECK(ctx->dalloc(&im->PB, (size_t)W * H));
+    const size_t smem = sizeof(HeapItem) * PEAC_HEAP + sizeof(int) * 2 * PEAC_MAXB + sizeof(unsigned short) * 2 * PEAC_MAXE;
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_peac_ahc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p->built = true;
+    return SINDYN_OK;
+}
+
+int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t *depth, float fx, float fy, float cx, float cy, float depth_scale,
+             uint8_t *plane_edges_out)
+{
+    PeacImpl *im = (PeacImpl *)p->impl;
+    const int W = p->W, H = p->H, Nw = im->Nw, Nh = im->Nh, NB = Nw * Nh;
+    const float inv_scale = 1.0f / depth_scale;
+    const size_t smem = sizeof(HeapItem) * PEAC_HEAP + sizeof(int) * 2 * PEAC_MAXB + sizeof(unsigned short) * 2 * PEAC_MAXE;
+    CU_CHECK(ctx, cudaMemsetAsync(im->ctl, 0, (4 + 128) * sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_peac_blocks, cdiv(NB, 64), 64, 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->nodes);
+    LAUNCH(ctx, k_peac_ahc, 1, 256, smem, im->nodes, im->ctl, Nw, Nh);
+    LAUNCH(ctx, k_peac_blockmap, cdiv(NB, 128), 128, 0, im->ctl, Nw, Nh);
+    const dim3 blk(32, 8), grd(cdiv(W, 32), cdiv(H, 8));
+    LAUNCH(ctx, k_peac_init_labels, grd, blk, 0, im->ctl, W, H, Nw, im->label, im->dist);
+    // growth distance per launch >= PG_ITERS pixels along straight paths; black regions are bounded by the image size
+    const int n_launch = min(2 * cdiv(W > H ? W : H, PG_ITERS) + 4, 128);
+    for (int it = 0; it < n_launch; ++it)
+        LAUNCH(ctx, k_peac_grow, dim3(cdiv(W, PG_T), cdiv(H, PG_T)), dim3(32, 8), 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, im->ctl, im->label, im->dist, it);
+    LAUNCH(ctx, k_peac_merge, 1, 32, 0, im->ctl);
+    LAUNCH(ctx, k_peac_bits, cdiv(W * H, 256), 256, 0, im->label, W * H, im->ctl, im->PB);
+    LAUNCH_CHECK(ctx);
+    return plane_contours_run(ctx, rc, im->PB, &im->ctl->n_final, plane_edges_out);
+}
+
+int peac_get_debug(sindyn_base *ctx, PeacStage *p, int *label_out, int *planes_rid_n, int *n_planes, int *n_final)
+{
+    PeacImpl *im = (PeacImpl *)p->impl;
+    static PeacControl host;   // large struct: keep it off the stack
+    CU_CHECK(ctx, cudaMemcpyAsync(&host, im->ctl, sizeof host, cudaMemcpyDeviceToHost, ctx->stream));
+    if (label_out) CU_CHECK(ctx, cudaMemcpyAsync(label_out, im->label, sizeof(int) * p->W * p->H, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_planes) *n_planes = host.n_planes;
+    if (n_final) *n_final = host.n_final;
+    if (planes_rid_n)
+        for (int k = 0; k < host.n_planes && k < PEAC_MAXP; ++k) { planes_rid_n[3 * k] = host.pl[k].rid; planes_rid_n[3 * k + 1] = host.pl[k].N; planes_rid_n[3 * k + 2] = host.pl[k].final_id; }
+    if (label_out)   // map grown labels to final plane ids like the oracle's membership image
+        for (int i = 0; i < p->W * p->H; ++i) label_out[i] = label_out[i] >= 0 ? host.pl[label_out[i]].final_id : -1;
+    return host.overflow ? SINDYN_ERR_CAPACITY : SINDYN_OK;
 }

@@ -3,6 +3,8 @@
 #pragma once
 #include "common.cuh"
 
+struct ReclusterStage;
+
 struct PeacStage {
     int W = 0, H = 0;
     bool built = false;
@@ -11,5 +13,8 @@ struct PeacStage {
 
 int peac_init(sindyn_base *ctx, PeacStage *p, int W, int H);
 // depth: W x H u16 device; plane_edges_out: W x H u8 device (imgEdgeByPlane)
-int peac_run(sindyn_base *ctx, PeacStage *p, const uint16_t *depth, float fx, float fy, float cx, float cy, float depth_scale,
-             uint8_t *plane_edges_out);
+// rc: scratch planes / CCL buffers of the re-clustering stage (the contour drawing reuses them)
+int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t *depth, float fx, float fy, float cx, float cy,
+             float depth_scale, uint8_t *plane_edges_out);
+// test hook: final membership image (final plane id or -1), extracted planes (rid, N, final id), counts
+int peac_get_debug(sindyn_base *ctx, PeacStage *p, int *label_out, int *planes_rid_n, int *n_planes, int *n_final);

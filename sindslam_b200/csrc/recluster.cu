@@ -616,3 +616,48 @@ int plane_edge_filter_run(sindyn_base *ctx, ReclusterStage *r, const uint8_t *pl
     SD_CHECK(morph_run(ctx, r->tmp8, r->occl1, r->tmp8b, W, H, 3, MORPH_CLOSE));
     return SINDYN_OK;
 }
+
+// ------------------------------------------------------------------ plane contours (PEAC output stage)
+__global__ void k_pl_expand(const B128 *__restrict__ bits, int n, const int *__restrict__ n_planes, uint8_t *__restrict__ cls)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int np = min(*n_planes, RC_MAXC);
+    const B128 b = bits[i];
+    for (int c = 0; c < np; ++c) cls[(size_t)c * n + i] = btest(b, c) ? 1 : 0;
+}
+
+__global__ void k_pl_fill(const int *__restrict__ top, int n, const int *__restrict__ n_planes, B128 *__restrict__ F)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int np = min(*n_planes, RC_MAXC);
+    B128 b = b0();
+    for (int c = 0; c < np; ++c)
+        if (top[(size_t)c * n + i] >= 0) b = bor(b, bbit(c));
+    F[i] = b;
+}
+
+__global__ void k_pl_any(const B128 *__restrict__ bits, int n, uint8_t *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = bany(bits[i]) ? 255 : 0;
+}
+
+int plane_contours_run(sindyn_base *ctx, ReclusterStage *r, const ulonglong2 *PB, const int *n_planes_dev, uint8_t *out)
+{
+    const int W = r->W, H = r->H, N = W * H;
+    const dim3 blk2(32, 8), grd2(cdiv(W, 32), cdiv(H, 8));
+    SD_CHECK(morph_bits_run(ctx, PB, r->tmpb, W, H, 3, false, 16));       // MORPH_CLOSE 3x3 of every plane image at once
+    SD_CHECK(morph_bits_run(ctx, r->tmpb, r->tmpb2, W, H, 3, true, 16));
+    LAUNCH(ctx, k_pl_expand, cdiv(N, 256), 256, 0, r->tmpb2, N, n_planes_dev, r->cls);
+    SD_CHECK(ccl_run(ctx, r->cls, r->labels, W, H, RC_MAXC, CCL_REGION, n_planes_dev));
+    SD_CHECK(ccl_top_image(ctx, r->labels, r->top, W, H, RC_MAXC, n_planes_dev, nullptr));
+    LAUNCH(ctx, k_pl_fill, cdiv(N, 256), 256, 0, r->top, N, n_planes_dev, r->F);
+    LAUNCH(ctx, k_rc_bnd, grd2, blk2, 0, r->F, W, H, r->tmpb, r->tmpb2);
+    LAUNCH(ctx, k_rc_thick2, grd2, blk2, 0, r->tmpb, r->tmpb2, W, H, (const uint8_t *)nullptr, (const uint8_t *)nullptr, r->T1, (int *)nullptr);
+    LAUNCH(ctx, k_pl_any, cdiv(N, 256), 256, 0, r->T1, N, out);
+    LAUNCH_CHECK(ctx);
+    return SINDYN_OK;
+}

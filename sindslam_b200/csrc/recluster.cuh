@@ -63,3 +63,6 @@ int plane_edge_filter_run(sindyn_base *ctx, ReclusterStage *r, const uint8_t *pl
 // labels / order / seg_edge (undilated) / points from the k-means stage; occl1/occl2 W x H u8 device. Result: r->label_out.
 int recluster_run(sindyn_base *ctx, ReclusterStage *r, const KmeansStage *km, const uint8_t *occl1, const uint8_t *occl2,
                   const uint16_t *depth);
+// PEAC output stage (AHCPlaneFitter.hpp:366-399): per-plane membership bitset PB (bit f = final plane f, *n_planes_dev
+// planes) -> CLOSE 3x3 -> external contours -> drawContours(thickness 2) of all planes into out (0/255).
+int plane_contours_run(sindyn_base *ctx, ReclusterStage *r, const ulonglong2 *PB, const int *n_planes_dev, uint8_t *out);

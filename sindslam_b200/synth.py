@@ -210,7 +210,7 @@ def render_frame(scene: Scene, cam: CameraConfig, idx: int, rng_seed: int | None
     if noise:
         bgr = bgr + rng.normal(0.0, 1.5, bgr.shape).astype(np.float32)
         z = z + rng.normal(0.0, 1.0, z.shape) * (0.0012 * z * z)
-        holes = rng.random(z.shape) < 0.015
+        holes = rng.random(z.shape) < getattr(scene, "hole_rate", 0.015)
         # 2-px zero band on the left (shadow) side of depth discontinuities
         jump = np.zeros_like(holes)
         dz = z[:, 1:] - z[:, :-1]
@@ -248,8 +248,11 @@ def gt_flow(scene: Scene, cam: CameraConfig, idx_cur: int, idx_old: int, cur: Fr
     return np.stack([u.reshape(H, W) - uu, v.reshape(H, W) - vv], -1).astype(np.float32)
 
 
-def make_sequence(n_frames: int, cam: CameraConfig = TUM3, seq: int = 0, kind: str = "box", start: int = 0):
+def make_sequence(n_frames: int, cam: CameraConfig = TUM3, seq: int = 0, kind: str = "box", start: int = 0, hole_rate: float = 0.015):
+    """hole_rate: probability of an isolated zero-depth pixel (1.5 %).  The PEAC plane fitter rejects every
+    16x16 block that contains a hole (INIT_STRICT), so its tests use a sensor-like low rate of isolated holes."""
     scene = Scene(BASE_SEED + seq, kind)
+    scene.hole_rate = hole_rate
     return scene, [render_frame(scene, cam, start + i) for i in range(n_frames)]
 
 
