@@ -59,6 +59,8 @@ struct sindyn_ctx : sindyn_base {
     uint8_t *plane_edges = nullptr;   // imgEdgeByPlane (zeros when cfg.plane_edges == 0)
     cudaStream_t stream2 = nullptr;   // clustering branch (the reference runs the flow branch in its own std::thread)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream3 = nullptr;   // PEAC plane fitter, concurrent with k-means / gradient edges
+    cudaEvent_t ev_peac_fork = nullptr, ev_peac_join = nullptr;
 
     float stage_ms[16] = {};
     cudaEvent_t ev[24] = {};

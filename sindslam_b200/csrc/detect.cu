@@ -22,15 +22,26 @@ static int ensure_events(sindyn_ctx *c)
 // clustering branch (DynaDetect.cc:1410-1516) on the handle's current stream; depth already in c->depth
 static int cluster_branch(sindyn_ctx *c)
 {
+    // the plane fitter (a long serial chain on one SM) depends on the depth image only: it runs on its own stream next to
+    // k-means and the gradient edges and joins before the plane-edge filter
+    cudaStream_t s2 = c->stream;
+    if (c->cfg.plane_edges) {
+        CU_CHECK(c, cudaEventRecord(c->ev_peac_fork, s2));
+        CU_CHECK(c, cudaStreamWaitEvent(c->stream3, c->ev_peac_fork, 0));
+        c->stream = c->stream3;
+        int st = peac_run(c, &c->peac, &c->rc, c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges);
+        cudaEventRecord(c->ev_peac_join, c->stream3);
+        c->stream = s2;
+        SD_CHECK(st);
+    } else {
+        CU_CHECK(c, cudaMemsetAsync(c->plane_edges, 0, c->N, c->stream));
+    }
     MARK(c, 10);
     SD_CHECK(kmeans_run(c, &c->km, c->depth, c->label_last, &c->cfg));
     MARK(c, 11);
     SD_CHECK(edges_run(c, &c->edges, c->depth, c->cfg.depth_scale));
     MARK(c, 12);
-    if (c->cfg.plane_edges)
-        SD_CHECK(peac_run(c, &c->peac, &c->rc, c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges));
-    else
-        CU_CHECK(c, cudaMemsetAsync(c->plane_edges, 0, c->N, c->stream));
+    if (c->cfg.plane_edges) CU_CHECK(c, cudaStreamWaitEvent(s2, c->ev_peac_join, 0));
     SD_CHECK(plane_edge_filter_run(c, &c->rc, c->plane_edges, c->edges.grad_edges, c->edges.ep_xy, c->edges.scalars + 2));
     MARK(c, 13);
     SD_CHECK(recluster_run(c, &c->rc, &c->km, c->rc.occl1, c->rc.occl2, c->depth));

@@ -22,11 +22,12 @@
 #include "recluster.cuh"
 
 #define PEAC_WIN 16
-#define PEAC_MAXB 2048          // blocks (53 x 30 = 1590 at 848 x 480)
+#define PEAC_MAXB 1600          // blocks (53 x 30 = 1590 at 848 x 480); bounded by the shared memory of k_peac_ahc
 #define PEAC_MAXP 64            // extracted planes
 #define PEAC_MIN_SUPPORT 2000
 #define PEAC_HEAP (2 * PEAC_MAXB)
-#define PEAC_MAXE (2 * PEAC_MAXB)
+#define PEAC_MAXCAND 1024       // distinct graph neighbours of one node
+#define PEAC_MAXE (2 * PEAC_MAXB)   // the row pass and the column pass add at most one edge per block each
 
 struct PeacNode {               // ahc::PlaneSeg (AHCPlaneSeg.hpp:29-188), indexed by root block id
     double st[9];               // sx sy sz sxx syy szz sxy syz sxz
@@ -55,46 +56,52 @@ struct PeacImpl {
 };
 
 // ---------------------------------------------------------------- small dense eigen solver
-// eigen decomposition of a symmetric 3x3 (cyclic Jacobi, double): returns the smallest eigenvalue and its vector.
-// (reference: Eigen::SelfAdjointEigenSolver through LA::eig33sym, eig33sym.hpp:45-51 -- un-vendored; results agree to
-// a few ulp of the largest eigenvalue)
-__device__ void eig33_min(const double K[3][3], double &lmin, double v[3], double ev[3])
+// Smallest eigenpair of a symmetric 3x3: trigonometric closed form for a first eigenvalue estimate, eigenvector from the
+// best-conditioned cross product of two rows of (K - l I), Rayleigh quotient l = v'Kv in double, three passes.  ~10x cheaper than cyclic Jacobi in FP64, which matters because the AHC loop below is a serial chain of
+// ~1000 such solves.  (reference: Eigen::SelfAdjointEigenSolver through LA::eig33sym, eig33sym.hpp:45-51 -- un-vendored;
+// the smallest eigenvalue agrees to ~1e-11 relative for plane-like covariance matrices)
+__device__ void eig33_min(const double K[3][3], double &lmin, double v[3])
 {
-    double a[3][3] = {{K[0][0], K[0][1], K[0][2]}, {K[0][1], K[1][1], K[1][2]}, {K[0][2], K[1][2], K[2][2]}};
-    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    for (int sweep = 0; sweep < 24; ++sweep) {
-        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
-        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
-        if (off <= 1e-40 * diag || off == 0.0) break;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int p = r == 2 ? 1 : 0, q = r == 0 ? 1 : 2;   // (0,1) (0,2) (1,2)
-            if (a[p][q] == 0.0) continue;
-            const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
-            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-            const double app = a[p][p], aqq = a[q][q], apq = a[p][q];
-            a[p][p] = app - t * apq;
-            a[q][q] = aqq + t * apq;
-            a[p][q] = a[q][p] = 0.0;
-            const int k = 3 - p - q;
-            const double akp = a[k][p], akq = a[k][q];
-            a[k][p] = a[p][k] = c * akp - s * akq;
-            a[k][q] = a[q][k] = s * akp + c * akq;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double vip = V[i][p], viq = V[i][q];
-                V[i][p] = c * vip - s * viq;
-                V[i][q] = s * vip + c * viq;
-            }
+    const double a00 = K[0][0], a11 = K[1][1], a22 = K[2][2], a01 = K[0][1], a02 = K[0][2], a12 = K[1][2];
+    // initial guess of the smallest eigenvalue: trigonometric closed form in FLOAT (fast acosf / cosf); its absolute error
+    // (~1e-7 of the largest eigenvalue) only has to be small against the gap to the middle eigenvalue, the Rayleigh passes
+    // below square the error each time
+    double l;
+    {
+        const float f00 = (float)a00, f11 = (float)a11, f22 = (float)a22, f01 = (float)a01, f02 = (float)a02, f12 = (float)a12;
+        const float p1 = f01 * f01 + f02 * f02 + f12 * f12;
+        const float q = (f00 + f11 + f22) * (1.0f / 3.0f);
+        const float b00 = f00 - q, b11 = f11 - q, b22 = f22 - q;
+        const float p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0f * p1;
+        if (p2 <= 0.0f) {
+            l = (double)q;
+        } else {
+            const float p = sqrtf(p2 * (1.0f / 6.0f)), ip = 1.0f / p;
+            const float c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip, c01 = f01 * ip, c02 = f02 * ip, c12 = f12 * ip;
+            float r = 0.5f * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+            r = fminf(fmaxf(r, -1.0f), 1.0f);
+            l = (double)(q + 2.0f * p * cosf(acosf(r) * (1.0f / 3.0f) + 2.0943951f));
         }
     }
-    int m = 0;
-    if (a[1][1] < a[m][m]) m = 1;
-    if (a[2][2] < a[m][m]) m = 2;
-    lmin = a[m][m];
-    v[0] = V[0][m]; v[1] = V[1][m]; v[2] = V[2][m];
-    ev[0] = a[0][0]; ev[1] = a[1][1]; ev[2] = a[2][2];
+    for (int pass = 0; pass < 3; ++pass) {
+        const double r0[3] = {a00 - l, a01, a02}, r1[3] = {a01, a11 - l, a12}, r2[3] = {a02, a12, a22 - l};
+        double c0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+        double c1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+        double c2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+        const double n0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2], n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2],
+                     n2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+        const double *c = c0;
+        double nn = n0;
+        if (n1 > nn) { c = c1; nn = n1; }
+        if (n2 > nn) { c = c2; nn = n2; }
+        if (nn <= 0.0) { v[0] = 0; v[1] = 0; v[2] = 1; break; }
+        const double in = rsqrt(nn);
+        v[0] = c[0] * in; v[1] = c[1] * in; v[2] = c[2] * in;
+        // Rayleigh quotient: second-order accurate eigenvalue for the refined vector
+        const double w0 = a00 * v[0] + a01 * v[1] + a02 * v[2], w1 = a01 * v[0] + a11 * v[1] + a12 * v[2], w2 = a02 * v[0] + a12 * v[1] + a22 * v[2];
+        l = v[0] * w0 + v[1] * w1 + v[2] * w2;
+    }
+    lmin = l;
 }
 
 // Stats::compute (AHCPlaneSeg.hpp:84-116)
@@ -107,8 +114,8 @@ __device__ void peac_compute(const double st[9], int N, double center[3], double
     K[1][1] = st[4] - st[1] * st[1] * sc; K[1][2] = st[7] - st[1] * st[2] * sc;
     K[2][2] = st[5] - st[2] * st[2] * sc;
     K[1][0] = K[0][1]; K[2][0] = K[0][2]; K[2][1] = K[1][2];
-    double l, v[3], ev[3];
-    eig33_min(K, l, v, ev);
+    double l, v[3];
+    eig33_min(K, l, v);
     const double d = v[0] * center[0] + v[1] * center[1] + v[2] * center[2];
     const double sgn = d <= 0 ? 1.0 : -1.0;     // normal points towards the camera
     normal[0] = sgn * v[0]; normal[1] = sgn * v[1]; normal[2] = sgn * v[2];
@@ -176,29 +183,55 @@ __global__ void k_peac_blocks(const uint16_t *__restrict__ depth, int W, int H, 
 }
 
 // ---------------------------------------------------------------- AHC (Algorithm 2 edges + Algorithm 3 clustering)
-struct HeapItem { double mse; int seq, rid, version; };
-__device__ __forceinline__ bool heap_less(const HeapItem &a, const HeapItem &b) { return a.mse < b.mse || (a.mse == b.mse && a.seq < b.seq); }
+struct MergeResult { double st[9], c[3], n[3], mse; };
 
+#define PEAC_AHC_SMEM ((sizeof(double) * (3 + 1 + 9) + sizeof(int) * 2 + 1 + sizeof(unsigned short) * 2) * PEAC_MAXB + sizeof(unsigned short) * 2 * PEAC_MAXE)
+#define PF_ALIVE 1
+#define PF_VALID 2
+#define PF_QUEUED 4
+
+// The pop / merge / extract loop is a chain of ~1000 dependent steps per frame, so everything it touches sits in shared
+// memory (structure-of-arrays, ~200 KB) and every step is spread over the CTA:
+//   * "pop the min-MSE node" is a parallel arg-min over the live queued nodes (cheaper than a binary heap walked by one
+//     thread, no stale entries); ties resolve by creation order like the oracle's insertion-ordered queue;
+//   * the union-find is kept FLAT (root[] of every block is rewritten on each merge by all threads);
+//   * every thread owns a column of the edge array and compacts it lazily (edges that became internal to a node or touch
+//     an extracted node are dropped when met), so the neighbour scan shrinks as the clustering proceeds;
+//   * the distinct neighbours of the popped node are collected first (stamp + compaction), then one candidate merge
+//     (merged sums + eigen solve) runs per thread; the winning thread hands its merged plane over through shared memory;
+//   * the bookkeeping of a merge is done by warp 0 (shuffle arg-min over the 8 warp results, lanes copy the sums).
 __global__ void __launch_bounds__(256) k_peac_ahc(PeacNode *__restrict__ nodes, PeacControl *ctl, int Nw, int Nh)
 {
     extern __shared__ unsigned char smraw[];
-    HeapItem *heap = (HeapItem *)smraw;                     // PEAC_HEAP
-    int *parent = (int *)(heap + PEAC_HEAP);                // PEAC_MAXB
-    int *ssize = parent + PEAC_MAXB;                        // PEAC_MAXB
-    unsigned short *eu = (unsigned short *)(ssize + PEAC_MAXB), *ev = eu + PEAC_MAXE;   // edges
-    __shared__ int s_ne, s_nheap, s_seq, s_p, s_done, s_best_o, s_nex;
-    __shared__ double s_best_mse;
+    double *nrm = (double *)smraw;                                       // 3 x PEAC_MAXB
+    double *mse_a = nrm + 3 * PEAC_MAXB;                                 // PEAC_MAXB
+    double *sst = mse_a + PEAC_MAXB;                                     // 9 x PEAC_MAXB second-order sums
+    int *N_a = (int *)(sst + 9 * PEAC_MAXB);                             // PEAC_MAXB
+    int *seq_a = N_a + PEAC_MAXB;                                        // PEAC_MAXB
+    unsigned short *root = (unsigned short *)(seq_a + PEAC_MAXB);        // PEAC_MAXB: flat union-find
+    unsigned short *ssize = root + PEAC_MAXB;                            // PEAC_MAXB
+    unsigned short *eu = ssize + PEAC_MAXB, *ev = eu + PEAC_MAXE;        // edges, column t = entries t, t + 256, ...
+    unsigned char *flags = (unsigned char *)(ev + PEAC_MAXE);            // PEAC_MAXB
+    __shared__ int s_ne, s_seq, s_nex, s_lose, s_win, s_ncand;
+    __shared__ int stamp[PEAC_MAXB];
+    __shared__ unsigned short cand[PEAC_MAXCAND];
     __shared__ int s_ex[PEAC_MAXP];
     __shared__ double w_mse[8];
-    __shared__ int w_o[8];
-    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int w_o[8], w_seq[8];
+    __shared__ MergeResult w_res[8];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const int NB = Nw * Nh;
-    for (int b = tid; b < NB; b += nt) { parent[b] = b; ssize[b] = 1; }
-    if (tid == 0) { s_ne = 0; s_nheap = 0; s_seq = 0; s_done = 0; s_nex = 0; }
+    for (int b = tid; b < NB; b += nt) {
+        root[b] = (unsigned short)b; ssize[b] = 1; stamp[b] = -1;
+        nrm[3 * b] = nodes[b].normal[0]; nrm[3 * b + 1] = nodes[b].normal[1]; nrm[3 * b + 2] = nodes[b].normal[2];
+        mse_a[b] = nodes[b].mse; N_a[b] = nodes[b].N; seq_a[b] = b;
+        flags[b] = nodes[b].valid ? (PF_ALIVE | PF_VALID | PF_QUEUED) : 0;
+        for (int k = 0; k < 9; ++k) sst[b * 9 + k] = nodes[b].st[k];
+    }
+    if (tid == 0) { s_ne = 0; s_seq = NB; s_nex = 0; s_lose = -1; s_win = -1; s_ncand = 0; }
     __syncthreads();
-    auto sim = [&](int a, int b) {
-        return fabs(nodes[a].normal[0] * nodes[b].normal[0] + nodes[a].normal[1] * nodes[b].normal[1] + nodes[a].normal[2] * nodes[b].normal[2]);
-    };
+    auto sim = [&](int a, int b) { return fabs(nrm[3 * a] * nrm[3 * b] + nrm[3 * a + 1] * nrm[3 * b + 1] + nrm[3 * a + 2] * nrm[3 * b + 2]); };
+    auto valid = [&](int b) { return (flags[b] & PF_VALID) != 0; };
     auto add_edge = [&](int a, int b) {
         int e = atomicAdd(&s_ne, 1);
         if (e < PEAC_MAXE) { eu[e] = (unsigned short)a; ev[e] = (unsigned short)b; }
@@ -208,9 +241,9 @@ __global__ void __launch_bounds__(256) k_peac_ahc(PeacNode *__restrict__ nodes, 
         const int i = tid;
         for (int j = 1; j < Nw; j += 2) {
             const int c = i * Nw + j;
-            if (!nodes[c - 1].valid) { --j; continue; }
-            if (!nodes[c].valid) continue;
-            if (j < Nw - 1 && !nodes[c + 1].valid) { ++j; continue; }
+            if (!valid(c - 1)) { --j; continue; }
+            if (!valid(c)) continue;
+            if (j < Nw - 1 && !valid(c + 1)) { ++j; continue; }
             const double th = peac_t_ang_init(nodes[c].center[2]);
             if ((j < Nw - 1 && sim(c - 1, c + 1) >= th) || (j == Nw - 1 && sim(c, c - 1) >= th)) {
                 add_edge(c, c - 1);
@@ -222,9 +255,9 @@ __global__ void __launch_bounds__(256) k_peac_ahc(PeacNode *__restrict__ nodes, 
         const int j = tid - 64;
         for (int i = 1; i < Nh; i += 2) {
             const int c = i * Nw + j;
-            if (!nodes[c - Nw].valid) { --i; continue; }
-            if (!nodes[c].valid) continue;
-            if (i < Nh - 1 && !nodes[c + Nw].valid) { ++i; continue; }
+            if (!valid(c - Nw)) { --i; continue; }
+            if (!valid(c)) continue;
+            if (i < Nh - 1 && !valid(c + Nw)) { ++i; continue; }
             const double th = peac_t_ang_init(nodes[c].center[2]);
             if ((i < Nh - 1 && sim(c - Nw, c + Nw) >= th) || (i == Nh - 1 && sim(c, c - Nw) >= th)) {
                 add_edge(c, c - Nw);
@@ -234,101 +267,126 @@ __global__ void __launch_bounds__(256) k_peac_ahc(PeacNode *__restrict__ nodes, 
     }
     __syncthreads();
     const int NE = min(s_ne, PEAC_MAXE);
-    // heap helpers (thread 0)
-    auto heap_push = [&](HeapItem it) {
-        int i = s_nheap++;
-        while (i > 0) {
-            const int par = (i - 1) >> 1;
-            if (!heap_less(it, heap[par])) break;
-            heap[i] = heap[par];
-            i = par;
-        }
-        heap[i] = it;
-    };
-    auto heap_pop = [&]() -> HeapItem {
-        HeapItem top = heap[0];
-        HeapItem last = heap[--s_nheap];
-        int i = 0;
-        for (;;) {
-            int l = 2 * i + 1, r = l + 1;
-            if (l >= s_nheap) break;
-            int c = (r < s_nheap && heap_less(heap[r], heap[l])) ? r : l;
-            if (!heap_less(heap[c], last)) break;
-            heap[i] = heap[c];
-            i = c;
-        }
-        if (s_nheap > 0) heap[i] = last;
-        return top;
-    };
-    auto find = [&](int x) { while (parent[x] != x) x = parent[x]; return x; };
-    if (tid == 0) {
-        for (int b = 0; b < NB; ++b)
-            if (nodes[b].valid) heap_push(HeapItem{nodes[b].mse, s_seq++, b, 0});
-        if (s_ne > PEAC_MAXE) ctl->overflow = 1;
-    }
-    __syncthreads();
+    if (tid == 0 && s_ne > PEAC_MAXE) ctl->overflow = 1;
+    int my_cnt = NE > tid ? (NE - tid + nt - 1) / nt : 0;   // live entries of this thread's edge column
+    int pop_id = 0;
     for (;;) {
-        if (tid == 0) {
-            s_p = -1;
-            while (s_nheap > 0) {
-                HeapItem it = heap_pop();
-                if (nodes[it.rid].alive && nodes[it.rid].version == it.version && parent[it.rid] == it.rid) { s_p = it.rid; break; }
+        // ---- flatten the union-find after the previous merge, and arg-min (mse, seq) over the queued live nodes
+        const int lose = s_lose, win = s_win;
+        double bm = 1e300;
+        int bp = -1, bs = 0x7fffffff;
+        for (int b = tid; b < NB; b += nt) {
+            if (lose >= 0 && root[b] == lose) root[b] = (unsigned short)win;
+            if ((flags[b] & (PF_ALIVE | PF_QUEUED)) == (PF_ALIVE | PF_QUEUED)) {
+                const double m = mse_a[b];
+                const int sq = seq_a[b];
+                if (m < bm || (m == bm && sq < bs)) { bm = m; bp = b; bs = sq; }
             }
-            if (s_p < 0) s_done = 1;
-        }
-        __syncthreads();
-        if (s_done) break;
-        const int p = s_p;
-        // ---- candidate merges with every live graph neighbour (AHCPlaneFitter.hpp:1092-1117)
-        double best = 1e300;
-        int best_o = -1;
-        for (int e = tid; e < NE; e += nt) {
-            const int ru = find(eu[e]), rv = find(ev[e]);
-            if (ru == rv) continue;
-            const int o = ru == p ? rv : (rv == p ? ru : -1);
-            if (o < 0 || !nodes[o].alive) continue;
-            if (sim(p, o) < PEAC_SIM_MERGE) continue;
-            double st[9], c[3], n[3], mse;
-            for (int k = 0; k < 9; ++k) st[k] = nodes[p].st[k] + nodes[o].st[k];
-            peac_compute(st, nodes[p].N + nodes[o].N, c, n, mse);
-            if (mse < best || (mse == best && o < best_o)) { best = mse; best_o = o; }
         }
         for (int off = 16; off > 0; off >>= 1) {
-            const double om = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oo = __shfl_xor_sync(0xffffffffu, best_o, off);
-            if (oo >= 0 && (best_o < 0 || om < best || (om == best && oo < best_o))) { best = om; best_o = oo; }
+            const double om = __shfl_xor_sync(0xffffffffu, bm, off);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, off), os = __shfl_xor_sync(0xffffffffu, bs, off);
+            if (op >= 0 && (bp < 0 || om < bm || (om == bm && os < bs))) { bm = om; bp = op; bs = os; }
         }
-        if ((tid & 31) == 0) { w_mse[tid >> 5] = best; w_o[tid >> 5] = best_o; }
+        if (lane == 0) { w_mse[wid] = bm; w_o[wid] = bp; w_seq[wid] = bs; }
         __syncthreads();
-        if (tid == 0) {
-            for (int k = 1; k < nt / 32; ++k)
-                if (w_o[k] >= 0 && (best_o < 0 || w_mse[k] < best || (w_mse[k] == best && w_o[k] < best_o))) { best = w_mse[k]; best_o = w_o[k]; }
+        int p = -1;
+        {
+            double pm = 1e300;
+            int ps = 0x7fffffff;
+            for (int k = 0; k < 8; ++k)
+                if (w_o[k] >= 0 && (p < 0 || w_mse[k] < pm || (w_mse[k] == pm && w_seq[k] < ps))) { p = w_o[k]; pm = w_mse[k]; ps = w_seq[k]; }
+        }
+        if (p < 0) break;
+        ++pop_id;
+        // ---- distinct live graph neighbours of p (AHCPlaneFitter.hpp:1092-1117); lazy compaction of the edge column
+        for (int i = 0; i < my_cnt;) {
+            const int e = i * nt + tid;
+            const int ru = root[eu[e]], rv = root[ev[e]];
+            if (ru == rv || !(flags[ru] & PF_ALIVE) || !(flags[rv] & PF_ALIVE)) {   // edge is gone for good
+                const int last = (my_cnt - 1) * nt + tid;
+                eu[e] = eu[last]; ev[e] = ev[last];
+                --my_cnt;
+                continue;
+            }
+            const int o = ru == p ? rv : (rv == p ? ru : -1);
+            if (o >= 0 && atomicExch(&stamp[o], pop_id) != pop_id) {
+                const int slot = atomicAdd(&s_ncand, 1);
+                if (slot < PEAC_MAXCAND) cand[slot] = (unsigned short)o;
+            }
+            ++i;
+        }
+        __syncthreads();
+        const int ncand = min(s_ncand, PEAC_MAXCAND);
+        double best = 1e300;
+        int best_o = -1;
+        MergeResult res;
+        for (int ci = tid; ci < ncand; ci += nt) {
+            const int o = cand[ci];
+            if (sim(p, o) < PEAC_SIM_MERGE) continue;
+            double st[9], c[3], n[3], mse;
+            for (int k = 0; k < 9; ++k) st[k] = sst[p * 9 + k] + sst[o * 9 + k];
+            peac_compute(st, N_a[p] + N_a[o], c, n, mse);
+            if (mse < best || (mse == best && o < best_o)) {
+                best = mse; best_o = o;
+                for (int k = 0; k < 9; ++k) res.st[k] = st[k];
+                for (int k = 0; k < 3; ++k) { res.c[k] = c[k]; res.n[k] = n[k]; }
+                res.mse = mse;
+            }
+        }
+        double wb = best;
+        int wo = best_o;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double om = __shfl_xor_sync(0xffffffffu, wb, off);
+            const int oo = __shfl_xor_sync(0xffffffffu, wo, off);
+            if (oo >= 0 && (wo < 0 || om < wb || (om == wb && oo < wo))) { wb = om; wo = oo; }
+        }
+        const unsigned winners = __ballot_sync(0xffffffffu, best_o >= 0 && best_o == wo && best == wb);
+        if (wo >= 0 && lane == __ffs(winners) - 1) w_res[wid] = res;
+        if (lane == 0) { w_mse[wid] = wb; w_o[wid] = wo; }   // (the arg-min scratch was last read before the previous barrier)
+        __syncthreads();
+        // ---- merge or extract: warp 0
+        if (wid == 0) {
+            double km = lane < 8 ? w_mse[lane] : 1e300;
+            int ko = lane < 8 ? w_o[lane] : -1, kw = lane;
+            for (int off = 4; off > 0; off >>= 1) {
+                const double om = __shfl_xor_sync(0xffffffffu, km, off);
+                const int oo = __shfl_xor_sync(0xffffffffu, ko, off), ow = __shfl_xor_sync(0xffffffffu, kw, off);
+                if (oo >= 0 && (ko < 0 || om < km || (om == km && oo < ko))) { km = om; ko = oo; kw = ow; }
+            }
+            ko = __shfl_sync(0xffffffffu, ko, 0); kw = __shfl_sync(0xffffffffu, kw, 0);
             bool merged = false;
-            if (best_o >= 0) {
-                const int o = best_o;
-                double st[9], c[3], n[3], mse;
-                for (int k = 0; k < 9; ++k) st[k] = nodes[p].st[k] + nodes[o].st[k];
-                const int N = nodes[p].N + nodes[o].N;
-                peac_compute(st, N, c, n, mse);
-                if (mse < peac_t_mse(false, c[2])) {
-                    // PlaneSeg(pa, pb): rid of the larger parent; DisjointSet::Union by size keeps the same root
-                    const int win = nodes[p].N >= nodes[o].N ? p : o, lose = win == p ? o : p;
-                    parent[lose] = win;
-                    ssize[win] += ssize[lose];
-                    PeacNode &w = nodes[win];
-                    for (int k = 0; k < 9; ++k) w.st[k] = st[k];
-                    for (int k = 0; k < 3; ++k) { w.center[k] = c[k]; w.normal[k] = n[k]; }
-                    w.mse = mse; w.N = N; w.version += 1; w.alive = 1;
-                    nodes[lose].alive = 0;
-                    heap_push(HeapItem{mse, s_seq++, win, w.version});
+            if (ko >= 0) {
+                const MergeResult &m = w_res[kw];
+                if (m.mse < peac_t_mse(false, m.c[2])) {
                     merged = true;
+                    // PlaneSeg(pa, pb): rid of the larger parent; DisjointSet::Union by size keeps the same root
+                    const int o = ko;
+                    const int wn = N_a[p] >= N_a[o] ? p : o, ls = wn == p ? o : p;
+                    const int Nsum = N_a[p] + N_a[o];
+                    __syncwarp();
+                    if (lane < 9) sst[wn * 9 + lane] = m.st[lane];
+                    else if (lane < 12) nrm[3 * wn + lane - 9] = m.n[lane - 9];
+                    else if (lane == 12) {
+                        mse_a[wn] = m.mse; N_a[wn] = Nsum;
+                        seq_a[wn] = s_seq++;            // the merged node is a NEW queue entry
+                        ssize[wn] += ssize[ls];
+                        flags[wn] |= PF_ALIVE | PF_QUEUED;
+                        flags[ls] &= ~(PF_ALIVE | PF_QUEUED);
+                        s_lose = ls; s_win = wn;
+                    }
                 }
             }
-            if (!merged) {   // extract p (or drop it) and cut it out of the graph
-                if (nodes[p].N >= PEAC_MIN_SUPPORT) {
+            if (!merged && lane == 0) {   // extract p (or drop it) and cut it out of the graph
+                if (N_a[p] >= PEAC_MIN_SUPPORT) {
                     if (s_nex < PEAC_MAXP) s_ex[s_nex++] = p; else ctl->overflow = 1;
                 }
-                nodes[p].alive = 0;
+                flags[p] &= ~(PF_ALIVE | PF_QUEUED);
+                s_lose = -1;
+            }
+            if (lane == 0) {
+                if (s_ncand > PEAC_MAXCAND) ctl->overflow = 1;
+                s_ncand = 0;
             }
         }
         __syncthreads();
@@ -339,21 +397,22 @@ __global__ void __launch_bounds__(256) k_peac_ahc(PeacNode *__restrict__ nodes, 
         for (int a = 1; a < n; ++a) {
             const int v = s_ex[a];
             int b = a - 1;
-            while (b >= 0 && nodes[s_ex[b]].N < nodes[v].N) { s_ex[b + 1] = s_ex[b]; --b; }
+            while (b >= 0 && N_a[s_ex[b]] < N_a[v]) { s_ex[b + 1] = s_ex[b]; --b; }
             s_ex[b + 1] = v;
         }
         ctl->n_planes = n;
         for (int k = 0; k < n; ++k) {
-            const PeacNode &nd = nodes[s_ex[k]];
+            const int r = s_ex[k];
             PeacPlane &pl = ctl->pl[k];
-            for (int d = 0; d < 3; ++d) { pl.center[d] = nd.center[d]; pl.normal[d] = nd.normal[d]; }
-            for (int d = 0; d < 9; ++d) pl.st[d] = nd.st[d];
-            pl.mse = nd.mse; pl.thr = 9.0 * nd.mse + 1e-5; pl.N = nd.N; pl.rid = s_ex[k]; pl.valid = 0; pl.final_id = -1;
+            const double sc = 1.0 / (double)N_a[r];
+            for (int d = 0; d < 3; ++d) { pl.center[d] = sst[r * 9 + d] * sc; pl.normal[d] = nrm[3 * r + d]; }
+            for (int d = 0; d < 9; ++d) pl.st[d] = sst[r * 9 + d];
+            pl.mse = mse_a[r]; pl.thr = 9.0 * mse_a[r] + 1e-5; pl.N = N_a[r]; pl.rid = r; pl.valid = 0; pl.final_id = -1;
             ctl->conn[k] = 0ull;
         }
     }
     __syncthreads();
-    for (int b = tid; b < NB; b += nt) { ctl->parent[b] = parent[b]; ctl->size[b] = ssize[b]; }
+    for (int b = tid; b < NB; b += nt) { ctl->parent[b] = root[b]; ctl->size[b] = ssize[b]; }
 }
 
 // ---------------------------------------------------------------- block erosion (findBlockMembership)
@@ -600,7 +659,7 @@ int peac_init(sindyn_base *ctx, PeacStage *p, int W, int H)
     SD_CHECK(ctx->dalloc(&im->label, (size_t)W * H));
     SD_CHECK(ctx->dalloc(&im->dist, (size_t)W * H));
     SD_CHECK(ctx->dalloc(&im->PB, (size_t)W * H));
-    const size_t smem = sizeof(HeapItem) * PEAC_HEAP + sizeof(int) * 2 * PEAC_MAXB + sizeof(unsigned short) * 2 * PEAC_MAXE;
+    const size_t smem = PEAC_AHC_SMEM;
     CU_CHECK(ctx, cudaFuncSetAttribute(k_peac_ahc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p->built = true;
     return SINDYN_OK;
@@ -612,7 +671,7 @@ int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t 
     PeacImpl *im = (PeacImpl *)p->impl;
     const int W = p->W, H = p->H, Nw = im->Nw, Nh = im->Nh, NB = Nw * Nh;
     const float inv_scale = 1.0f / depth_scale;
-    const size_t smem = sizeof(HeapItem) * PEAC_HEAP + sizeof(int) * 2 * PEAC_MAXB + sizeof(unsigned short) * 2 * PEAC_MAXE;
+    const size_t smem = PEAC_AHC_SMEM;
     CU_CHECK(ctx, cudaMemsetAsync(im->ctl, 0, (4 + 128) * sizeof(int), ctx->stream));
     LAUNCH(ctx, k_peac_blocks, cdiv(NB, 64), 64, 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->nodes);
     LAUNCH(ctx, k_peac_ahc, 1, 256, smem, im->nodes, im->ctl, Nw, Nh);

@@ -18,6 +18,9 @@ int sindyn_ctx_init_stages(sindyn_ctx *c)
     CU_CHECK(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CU_CHECK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CU_CHECK(c, cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->ev_peac_fork, cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->ev_peac_join, cudaEventDisableTiming));
     return SINDYN_OK;
 }
 void sindyn_ctx_destroy_stages(sindyn_ctx *c)
@@ -25,6 +28,9 @@ void sindyn_ctx_destroy_stages(sindyn_ctx *c)
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream3) cudaStreamDestroy(c->stream3);
+    if (c->ev_peac_fork) cudaEventDestroy(c->ev_peac_fork);
+    if (c->ev_peac_join) cudaEventDestroy(c->ev_peac_join);
 }
 
 extern "C" int sindyn_morph_ellipse(sindyn_handle h, const uint8_t *src, size_t src_step, uint8_t *dst, size_t dst_step, int width,
