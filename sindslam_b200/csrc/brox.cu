@@ -154,7 +154,7 @@ template <int TW_, int TH_> struct BroxTile {
     static constexpr int PP = PW * PH;
     static constexpr int G = HW + 1;                 // zero guard before / after every colour array (wrapped neighbour reads)
     static constexpr int NPCP = NPC + 2 * G;
-    static constexpr size_t SMEM = sizeof(float2) * 4 * NPCP + sizeof(float) * 3 * PP;
+    static constexpr size_t SMEM = sizeof(float2) * 4 * NPCP + sizeof(float) * 5 * PP;
     static_assert((PW & 1) == 0, "de-interleaving needs an even region width");
     static_assert(NPC < 4096, "pixel index must fit into 12 bits");
 };
@@ -173,6 +173,8 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
     float *s_ta = (float *)((float2 *)sm4 + 4 * BROX_NPCP);  // [PP] u + du_base
     float *s_tb = s_ta + BROX_PP;               // [PP] v + dv_base
     float *s_ps = s_tb + BROX_PP;               // [PP] smoothness diffusivity
+    float *s_u = s_ps + BROX_PP;                // [PP] flow of this level (u, v): neighbours for the right-hand side
+    float *s_v = s_u + BROX_PP;
     const int w = p.w, h = p.h;
     const int gx0 = blockIdx.x * p.tw, gy0 = blockIdx.y * p.th;
     const int ox = gx0 - p.halo, oy = gy0 - p.halo;   // ox + oy is even in both modes: local colour == global colour
@@ -231,16 +233,21 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 const int g = y * w + x;
                 if (it == 0) {
                     const float bu = p.dub[g], bv = p.dvb[g];
+                    const float uu = p.u[g], vv = p.v[g];
                     s_uv[ci] = same_base ? make_float2(bu, bv) : make_float2(p.dui[g], p.dvi[g]);
-                    ta = p.u[g] + bu;
-                    tb = p.v[g] + bv;
+                    s_u[r] = uu;
+                    s_v[r] = vv;
+                    ta = uu + bu;
+                    tb = vv + bv;
                 } else {   // single-tile mode: the increment of the previous inner iteration is already in shared memory
                     const float2 d = s_uv[ci];
-                    ta = p.u[g] + d.x;
-                    tb = p.v[g] + d.y;
+                    ta = s_u[r] + d.x;
+                    tb = s_v[r] + d.y;
                 }
             } else if (it == 0) {
                 s_uv[ci] = make_float2(0.0f, 0.0f);
+                s_u[r] = 0.0f;
+                s_v[r] = 0.0f;
             }
             s_ta[r] = ta;
             s_tb[r] = tb;
@@ -303,12 +310,13 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 const float j22 = psid * (iy * iy + gamma * (ixy * ixy + iyy * iyy));
                 const float j13 = psid * (ix * iz + gamma * (ixx * ixz + ixy * iyz));
                 const float j23 = psid * (iy * iz + gamma * (ixy * ixz + iyy * iyz));
-                const float uc = p.u[g], vc = p.v[g];
+                const int r = ly * BROX_PW + lx;   // live pixels have all four neighbours inside the staged region
+                const float uc = s_u[r], vc = s_v[r];
                 float su = 0.0f, sv = 0.0f;
-                if (x > 0) { su += wl * (p.u[g - 1] - uc); sv += wl * (p.v[g - 1] - vc); }
-                if (x < w - 1) { su += wr * (p.u[g + 1] - uc); sv += wr * (p.v[g + 1] - vc); }
-                if (y > 0) { su += wu * (p.u[g - w] - uc); sv += wu * (p.v[g - w] - vc); }
-                if (y < h - 1) { su += wd * (p.u[g + w] - uc); sv += wd * (p.v[g + w] - vc); }
+                if (x > 0) { su += wl * (s_u[r - 1] - uc); sv += wl * (s_v[r - 1] - vc); }
+                if (x < w - 1) { su += wr * (s_u[r + 1] - uc); sv += wr * (s_v[r + 1] - vc); }
+                if (y > 0) { su += wu * (s_u[r - BROX_PW] - uc); sv += wu * (s_v[r - BROX_PW] - vc); }
+                if (y < h - 1) { su += wd * (s_u[r + BROX_PW] - uc); sv += wd * (s_v[r + BROX_PW] - vc); }
                 const float sw_ = wl + wr + wu + wd;
                 cj12[c][m] = j12;
                 cb1[c][m] = su - j13;
@@ -476,7 +484,9 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
         p.Ix = b->Ix; p.Iy = b->Iy; p.Iz = b->Iz; p.Ixx = b->Ixx; p.Ixy = b->Ixy; p.Iyy = b->Iyy; p.Ixz = b->Ixz; p.Iyz = b->Iyz;
         p.u = b->u[cur]; p.v = b->v[cur];
         p.w = w; p.h = h; p.alpha = b->alpha; p.gamma = b->gamma; p.omega = b->omega;
-        if (w <= BroxTileL::PW && h <= BroxTileL::PH && b->solver <= BROX_SMAX) {
+        // One CTA is faster than a grid only while the level is tiny (<= ~1200 px: the 4 coarsest of 15 levels): above that
+        // 10 launches on 8x8 tiles spread over 35-90 SMs win over 10 inner iterations serialised on one SM.
+        if (w <= BroxTileL::PW && h <= BroxTileL::PH && w * h <= 1200 && b->solver <= BROX_SMAX) {
             // the whole level fits into one tile: all lagged-nonlinearity iterations in ONE launch, no halo
             const int out = 1;
             p.dub = p.dui = b->du[base]; p.dvb = p.dvi = b->dv[base];
