@@ -53,6 +53,10 @@ extern "C" int sindyn_create(const sindyn_config *cfg, sindyn_handle *out)
         SD_CHECK(c->dalloc(&c->gsmall_f[i], NF));
     }
     SD_CHECK(c->dalloc(&c->depth, N));
+    SD_CHECK(c->halloc(&c->pin_bgr, N * 3));
+    SD_CHECK(c->halloc(&c->pin_depth, N));
+    SD_CHECK(c->halloc(&c->pin_out0, N));
+    SD_CHECK(c->halloc(&c->pin_out1, N));
     SD_CHECK(c->dalloc(&c->dyna_last, N));
     SD_CHECK(c->dalloc(&c->high_last, N));
     SD_CHECK(c->dalloc(&c->label_last, N));

@@ -93,6 +93,37 @@ struct sindyn_base {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Pageable host memory makes cudaMemcpyAsync a slow, synchronous, driver-staged copy (~0.5 ms for one 640x480 BGR frame).
+// Callers of the reference interface hand over cv::Mat buffers (pageable), so the per-frame entry points stage them
+// through pinned bounce buffers owned by the handle: one host memcpy at memory bandwidth, then a true async DMA.
+static inline bool host_ptr_is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+// host (pitched) -> device (dense)
+static inline cudaError_t stage_in_2d(void *dst_dev, const void *src, size_t src_step, size_t row_bytes, int rows, void *pinned, cudaStream_t s)
+{
+    if (!src_step) src_step = row_bytes;
+    if (!pinned || host_ptr_is_pinned(src))
+        return cudaMemcpy2DAsync(dst_dev, row_bytes, src, src_step, row_bytes, rows, cudaMemcpyHostToDevice, s);
+    if (src_step == row_bytes) memcpy(pinned, src, row_bytes * rows);
+    else for (int r = 0; r < rows; ++r) memcpy((char *)pinned + r * row_bytes, (const char *)src + r * src_step, row_bytes);
+    return cudaMemcpyAsync(dst_dev, pinned, row_bytes * rows, cudaMemcpyHostToDevice, s);
+}
+// device (dense) -> pinned bounce buffer; finish with stage_out_finish after the stream has been synchronised
+static inline cudaError_t stage_out_begin(void *pinned, const void *src_dev, size_t bytes, cudaStream_t s)
+{
+    return cudaMemcpyAsync(pinned, src_dev, bytes, cudaMemcpyDeviceToHost, s);
+}
+static inline void stage_out_finish(void *dst, size_t dst_step, const void *pinned, size_t row_bytes, int rows)
+{
+    if (!dst_step) dst_step = row_bytes;
+    if (dst_step == row_bytes) memcpy(dst, pinned, row_bytes * rows);
+    else for (int r = 0; r < rows; ++r) memcpy((char *)dst + r * dst_step, (const char *)pinned + r * row_bytes, row_bytes);
+}
+
 // pitched host <-> dense device copies
 static inline cudaError_t copy_in_2d(void *dst, const void *src, size_t src_step, size_t row_bytes, int rows, cudaStream_t s)
 {

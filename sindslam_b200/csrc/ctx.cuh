@@ -27,6 +27,9 @@ struct sindyn_ctx : sindyn_base {
     float *gsmall_f[3] = {nullptr, nullptr, nullptr};
     int i_cur = 0, i_last = 1, i_lastlast = 2;
     uint16_t *depth = nullptr;
+    // pinned bounce buffers of the per-frame entry points (see stage_in_2d)
+    uint8_t *pin_bgr = nullptr, *pin_out0 = nullptr, *pin_out1 = nullptr;
+    uint16_t *pin_depth = nullptr;
     // device-resident staging slots for kernel-only timing
     uint8_t *slot_bgr[SINDYN_MAX_SLOTS] = {};
     uint16_t *slot_depth[SINDYN_MAX_SLOTS] = {};

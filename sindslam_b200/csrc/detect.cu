@@ -125,12 +125,14 @@ extern "C" int sindyn_detect(sindyn_handle h, const uint8_t *bgr, size_t bgr_ste
     (void)frame_idx;   // nImg only divides the reference's running time sums (DynaDetect.cc:1647)
     H_CHECK(h);
     if (!bgr || !depth) return SINDYN_ERR_INVALID;
-    CU_CHECK(h, copy_in_2d(h->bgr[h->i_cur], bgr, bgr_step, (size_t)h->W * 3, h->H, h->stream));
-    CU_CHECK(h, copy_in_2d(h->depth, depth, depth_step, (size_t)h->W * 2, h->H, h->stream));
+    CU_CHECK(h, stage_in_2d(h->bgr[h->i_cur], bgr, bgr_step, (size_t)h->W * 3, h->H, h->pin_bgr, h->stream));
+    CU_CHECK(h, stage_in_2d(h->depth, depth, depth_step, (size_t)h->W * 2, h->H, h->pin_depth, h->stream));
     SD_CHECK(detect_run(h));
-    if (mask_out) CU_CHECK(h, copy_out_2d(mask_out, mask_step, h->dd.out, h->W, h->H, h->stream));
-    if (label_out) CU_CHECK(h, copy_out_2d(label_out, label_step, h->rc.label_out, h->W, h->H, h->stream));
-    SD_CHECK(check_capacity(h));
+    if (mask_out) CU_CHECK(h, stage_out_begin(h->pin_out0, h->dd.out, h->N, h->stream));
+    if (label_out) CU_CHECK(h, stage_out_begin(h->pin_out1, h->rc.label_out, h->N, h->stream));
+    SD_CHECK(check_capacity(h));   // synchronises the stream
+    if (mask_out) stage_out_finish(mask_out, mask_step, h->pin_out0, h->W, h->H);
+    if (label_out) stage_out_finish(label_out, label_step, h->pin_out1, h->W, h->H);
     return collect_detect_ms(h);
 }
 

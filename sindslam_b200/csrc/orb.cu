@@ -59,6 +59,9 @@ struct sindyn_orb : sindyn_base {
     uint8_t *desc = nullptr;
     sindyn_keypoint *out_host_fmt = nullptr;
     OrbControl *ctl = nullptr, *ctl_host = nullptr;
+    uint8_t *pin_gray = nullptr, *pin_mask = nullptr;   // pinned bounce buffers (see stage_in_2d)
+    sindyn_keypoint *pin_kp = nullptr;
+    uint8_t *pin_desc = nullptr;
     size_t pad_total = 0, img_total = 0;
 };
 
@@ -667,6 +670,10 @@ extern "C" int sindyn_orb_create(int nfeatures, float scale_factor, int nlevels,
     SD_CHECK(o->dalloc(&o->out_host_fmt, ORB_OUT_MAX));
     SD_CHECK(o->dalloc(&o->ctl, 1));
     SD_CHECK(o->halloc(&o->ctl_host, 1));
+    SD_CHECK(o->halloc(&o->pin_gray, (size_t)width * height));
+    SD_CHECK(o->halloc(&o->pin_mask, (size_t)width * height));
+    SD_CHECK(o->halloc(&o->pin_kp, ORB_OUT_MAX));
+    SD_CHECK(o->halloc(&o->pin_desc, (size_t)ORB_OUT_MAX * 32));
     CU_CHECK(o, cudaMemcpyAsync(o->lv_dev, o->lv, sizeof(OrbLevel) * ORB_MAX_LEVELS, cudaMemcpyHostToDevice, o->stream));
     for (int l = 1; l < nlevels; ++l) SD_CHECK(resize_plan_init(o, &o->plan[l], o->lv[l - 1].w, o->lv[l - 1].h, o->lv[l].w, o->lv[l].h));
     // umax (ORBextractor.cc:450-467)
@@ -755,9 +762,16 @@ extern "C" int sindyn_orb_extract(sindyn_orb_handle h, const uint8_t *gray, size
     *n_out = 0;
     if (!gray) return SINDYN_OK;   // operator() returns silently on an empty image (ORBextractor.cc:1046-1047)
     const OrbLevel &L0 = h->lv[0];
-    CU_CHECK(h, cudaMemcpy2DAsync(h->pyr + (size_t)ORB_EDGE * L0.pitch + ORB_EDGE, L0.pitch, gray, gray_step ? gray_step : (size_t)h->W, h->W, h->H,
-                                  cudaMemcpyHostToDevice, h->stream));
-    if (mask) CU_CHECK(h, cudaMemcpy2DAsync(h->mask, h->W, mask, mask_step ? mask_step : (size_t)h->W, h->W, h->H, cudaMemcpyHostToDevice, h->stream));
+    {   // gray -> interior of the padded level 0 (pitched destination), through the pinned bounce buffer
+        const void *src = gray;
+        size_t step = gray_step ? gray_step : (size_t)h->W;
+        if (!host_ptr_is_pinned(gray)) {
+            for (int r = 0; r < h->H; ++r) memcpy(h->pin_gray + (size_t)r * h->W, gray + r * step, h->W);
+            src = h->pin_gray; step = h->W;
+        }
+        CU_CHECK(h, cudaMemcpy2DAsync(h->pyr + (size_t)ORB_EDGE * L0.pitch + ORB_EDGE, L0.pitch, src, step, h->W, h->H, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (mask) CU_CHECK(h, stage_in_2d(h->mask, mask, mask_step, h->W, h->H, h->pin_mask, h->stream));
     SD_CHECK(orb_enqueue(h, mask != nullptr));
     CU_CHECK(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(OrbControl), cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
@@ -765,9 +779,11 @@ extern "C" int sindyn_orb_extract(sindyn_orb_handle h, const uint8_t *gray, size
     const int n = h->ctl_host->n_out;
     *n_out = n;
     if (n > capacity) { h->err = "orb: output capacity too small"; return SINDYN_ERR_CAPACITY; }
-    if (n && kps) CU_CHECK(h, cudaMemcpyAsync(kps, h->out_host_fmt, sizeof(sindyn_keypoint) * n, cudaMemcpyDeviceToHost, h->stream));
-    if (n && desc) CU_CHECK(h, cudaMemcpyAsync(desc, h->desc, (size_t)32 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (n && kps) CU_CHECK(h, cudaMemcpyAsync(h->pin_kp, h->out_host_fmt, sizeof(sindyn_keypoint) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (n && desc) CU_CHECK(h, cudaMemcpyAsync(h->pin_desc, h->desc, (size_t)32 * n, cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    if (n && kps) memcpy(kps, h->pin_kp, sizeof(sindyn_keypoint) * n);
+    if (n && desc) memcpy(desc, h->pin_desc, (size_t)32 * n);
     return SINDYN_OK;
 }
 

@@ -82,11 +82,14 @@ extern "C" int sindyn_flow_residual(sindyn_handle h, const uint8_t *bgr, size_t 
 {
     H_CHECK(h);
     if (!bgr) return SINDYN_ERR_INVALID;
-    CU_CHECK(h, copy_in_2d(h->bgr[h->i_cur], bgr, bgr_step, (size_t)h->W * 3, h->H, h->stream));
+    CU_CHECK(h, stage_in_2d(h->bgr[h->i_cur], bgr, bgr_step, (size_t)h->W * 3, h->H, h->pin_bgr, h->stream));
     SD_CHECK(flow_residual_run(h, h->bgr[h->i_cur], roll != 0));
-    if (mask_low) CU_CHECK(h, cudaMemcpyAsync(mask_low, h->mask_low, h->N, cudaMemcpyDeviceToHost, h->stream));
-    if (mask_high) CU_CHECK(h, cudaMemcpyAsync(mask_high, h->mask_high, h->N, cudaMemcpyDeviceToHost, h->stream));
+    const bool lo_direct = mask_low && host_ptr_is_pinned(mask_low), hi_direct = mask_high && host_ptr_is_pinned(mask_high);
+    if (mask_low) CU_CHECK(h, stage_out_begin(lo_direct ? (void *)mask_low : (void *)h->pin_out0, h->mask_low, h->N, h->stream));
+    if (mask_high) CU_CHECK(h, stage_out_begin(hi_direct ? (void *)mask_high : (void *)h->pin_out1, h->mask_high, h->N, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    if (mask_low && !lo_direct) stage_out_finish(mask_low, 0, h->pin_out0, h->N, 1);
+    if (mask_high && !hi_direct) stage_out_finish(mask_high, 0, h->pin_out1, h->N, 1);
     return collect_stage_ms(h, 5);
 }
 
