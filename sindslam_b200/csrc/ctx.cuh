@@ -62,6 +62,10 @@ struct sindyn_ctx : sindyn_base {
     uint8_t *plane_edges = nullptr;   // imgEdgeByPlane (zeros when cfg.plane_edges == 0)
     cudaStream_t stream2 = nullptr;   // clustering branch (the reference runs the flow branch in its own std::thread)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_flag = nullptr;    // large-motion flag has arrived on the host
+    cudaGraphExec_t cluster_graph = nullptr;   // captured clustering branch (three streams, no host decisions)
+    cudaStream_t cluster_graph_stream = nullptr;
+    unsigned long long cluster_graph_launches = 0;
     cudaStream_t stream3 = nullptr;   // PEAC plane fitter, concurrent with k-means / gradient edges
     cudaEvent_t ev_peac_fork = nullptr, ev_peac_join = nullptr;
 
@@ -75,6 +79,8 @@ struct sindyn_ctx : sindyn_base {
 int sindyn_prep_frame(sindyn_ctx *c, int idx);          // api.cu: BGR -> gray -> 0.6x gray (u8 + float)
 int flow_branch_init(sindyn_ctx *c);                    // flow.cu
 int flow_branch_run(sindyn_ctx *c, int *large_motion);  // flow.cu
+int flow_branch_begin(sindyn_ctx *c);                   // flow.cu
+int flow_branch_finish(sindyn_ctx *c, int *large_motion);  // flow.cu
 int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll);  // pipeline.cu
 int sindyn_ctx_init_stages(sindyn_ctx *c);              // stages.cu
 void sindyn_ctx_destroy_stages(sindyn_ctx *c);          // stages.cu

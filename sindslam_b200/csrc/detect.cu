@@ -72,18 +72,46 @@ static int detect_run(sindyn_ctx *c)
     cudaStream_t main_s = c->stream;
     MARK(c, 0);
     CU_CHECK(c, cudaEventRecord(c->ev_fork, main_s));
-    // ---- clustering branch, enqueued first (fully asynchronous)
-    CU_CHECK(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-    c->stream = c->stream2;
-    int st = cluster_branch(c);
-    cudaEventRecord(c->ev_join, c->stream2);
-    c->stream = main_s;
-    SD_CHECK(st);
-    // ---- flow branch
+    // ---- flow branch, first part: the Brox solve is one graph launch, so the GPU starts on the critical path at once
     SD_CHECK(sindyn_prep_frame(c, c->i_cur));
     MARK(c, 1);
+    SD_CHECK(flow_branch_begin(c));      // marks ev[2] after the first Brox solve
+    // ---- clustering branch on stream2 (+ stream3 for the plane fitter): ~300 launches without a host decision.  With
+    // use_graphs it is captured once (cross-stream fork / join included) and replayed as ONE graph launch per frame.
+    CU_CHECK(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    const bool graph = c->cfg.use_graphs && !c->cfg.stage_timing;
+    if (graph && c->cluster_graph && c->cluster_graph_stream == c->stream2) {
+        CU_CHECK(c, cudaGraphLaunch(c->cluster_graph, c->stream2));
+        c->launches += c->cluster_graph_launches;
+    } else {
+        c->stream = c->stream2;
+        int st = SINDYN_OK;
+        cudaGraph_t gr = nullptr;
+        const unsigned long long before = c->launches;
+        if (graph) {
+            if (c->cluster_graph) { cudaGraphExecDestroy(c->cluster_graph); c->cluster_graph = nullptr; }
+            if (cudaStreamBeginCapture(c->stream2, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { c->stream = main_s; c->err = "cluster graph capture failed to start"; return SINDYN_ERR_CUDA; }
+        }
+        st = cluster_branch(c);
+        if (graph) {
+            cudaError_t e = cudaStreamEndCapture(c->stream2, &gr);
+            c->stream = main_s;
+            SD_CHECK(st);
+            CU_CHECK(c, e);
+            CU_CHECK(c, cudaGraphInstantiate(&c->cluster_graph, gr, 0));
+            cudaGraphDestroy(gr);
+            c->cluster_graph_stream = c->stream2;
+            c->cluster_graph_launches = c->launches - before;
+            CU_CHECK(c, cudaGraphLaunch(c->cluster_graph, c->stream2));
+        } else {
+            c->stream = main_s;
+            SD_CHECK(st);
+        }
+    }
+    CU_CHECK(c, cudaEventRecord(c->ev_join, c->stream2));
+    // ---- flow branch, second part (contains the one host decision, large motion)
     int lm = 0;
-    SD_CHECK(flow_branch_run(c, &lm));   // marks ev[2] after the first Brox solve
+    SD_CHECK(flow_branch_finish(c, &lm));
     c->large_motion_last = lm;
     MARK(c, 3);
     SD_CHECK(homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last));

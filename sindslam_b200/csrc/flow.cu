@@ -64,11 +64,16 @@ int flow_branch_init(sindyn_ctx *c)
     SD_CHECK(c->halloc(&c->fb_flag_host, 4));
     SD_CHECK(homography_init(c, &c->homog, c->W, c->H));
     SD_CHECK(varref_init(c, &c->varref, c->fw, c->fh));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
     return SINDYN_OK;
 }
 
 // Runs on the handle's resident frames (gsmall_f / gsmall of cur, last, lastlast). Result: c->flow_full.
-int flow_branch_run(sindyn_ctx *c, int *large_motion)
+// Split in two so that a caller can enqueue other work between the first Brox solve and the host decision:
+//   flow_branch_begin: Brox(cur, lastlast), large-motion statistics, asynchronous copy of the flag
+//   flow_branch_finish: wait for the flag (the only host decision of the flow branch; the reference does the same D2H + sync,
+//                       DynaDetect.cc:1073), optional Brox(cur, last), refinement, up-sampling
+int flow_branch_begin(sindyn_ctx *c)
 {
     const bool g = c->cfg.use_graphs != 0;
     const int nf = c->fw * c->fh;
@@ -80,9 +85,15 @@ int flow_branch_run(sindyn_ctx *c, int *large_motion)
     LAUNCH(c, k_u8_hist, SINDYN_NUM_SMS_B200, 256, 0, c->fb_mag, nf, gmax, c->fb_hist);
     LAUNCH(c, k_large_motion, 1, 32, 0, c->fb_hist, gmax, c->W, c->H, c->cfg.flow_scale, c->fb_flag);
     LAUNCH_CHECK(c);
-    // the only host decision of the flow branch (the reference does the same D2H + sync, DynaDetect.cc:1073)
     CU_CHECK(c, cudaMemcpyAsync(c->fb_flag_host, c->fb_flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    CU_CHECK(c, cudaEventRecord(c->ev_flag, c->stream));
+    return SINDYN_OK;
+}
+
+int flow_branch_finish(sindyn_ctx *c, int *large_motion)
+{
+    const bool g = c->cfg.use_graphs != 0;
+    CU_CHECK(c, cudaEventSynchronize(c->ev_flag));
     const int lm = c->fb_flag_host[0];
     if (large_motion) *large_motion = lm;
     int i_ref = c->i_lastlast;
@@ -95,6 +106,12 @@ int flow_branch_run(sindyn_ctx *c, int *large_motion)
     SD_CHECK(launch_resize_flow(c, c->flow_small, c->fw, c->fh, c->flow_full, c->W, c->H, 1.0f / c->cfg.flow_scale));
     LAUNCH_CHECK(c);
     return SINDYN_OK;
+}
+
+int flow_branch_run(sindyn_ctx *c, int *large_motion)
+{
+    SD_CHECK(flow_branch_begin(c));
+    return flow_branch_finish(c, large_motion);
 }
 
 extern "C" int sindyn_flow_branch(sindyn_handle h, const uint8_t *bgr_cur, size_t step_cur, float *flow_out, int *large_motion_out)

@@ -25,6 +25,8 @@ int sindyn_ctx_init_stages(sindyn_ctx *c)
 }
 void sindyn_ctx_destroy_stages(sindyn_ctx *c)
 {
+    if (c->cluster_graph) cudaGraphExecDestroy(c->cluster_graph);
+    if (c->ev_flag) cudaEventDestroy(c->ev_flag);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
