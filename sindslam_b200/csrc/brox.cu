@@ -4,13 +4,11 @@
 // (ORB_SLAM2/src/DynaDetect.cc:1029,1072,1124).  Algorithm = oracle/brox_cpu.c (Brox et al. ECCV'04
 // with the reference's parameters); the flow-parity gate is a mean end-point-error tolerance.
 //
-// B200 design: the problem (110 592 px at level 0, 15 levels) is latency- not bandwidth-bound, so
-// the solver_iterations red-black SOR sweeps of one lagged-nonlinearity iteration run INSIDE ONE
-// launch: each CTA stages its tile plus a (2*sweeps+1)-pixel halo of (du,dv) and the six per-pixel
-// system coefficients in shared memory (156 KB of the 227 KB), performs all sweeps there with a
-// shrinking valid region (temporal blocking: results are identical to global sweeps), and writes
-// only its interior.  32x24 interiors give 144 CTAs at 384x288 = one wave on 148 SMs.  The whole
-// pyramid (about 210 launches) is captured in one CUDA graph.
+// B200 design: the problem (110 592 px at level 0, 15 levels) is latency- not bandwidth-bound, so the
+// solver_iterations red-black SOR sweeps of one lagged-nonlinearity iteration run INSIDE ONE launch (temporal
+// blocking in shared memory, see k_brox_inner); levels pick the smallest tile that still fits one wave of 148 SMs,
+// the coarsest levels run all inner iterations in a single launch, and the whole pyramid (about 200 launches) is
+// captured in one CUDA graph.
 #include "brox.cuh"
 
 #include <math.h>
