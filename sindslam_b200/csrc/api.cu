@@ -90,6 +90,7 @@ extern "C" int sindyn_destroy(sindyn_handle h)
     cudaStreamSynchronize(h->stream);
     brox_destroy(&h->brox);
     brox_destroy(&h->brox_lm);
+    flow_tail_drop_graphs(h);
     sindyn_ctx_destroy_stages(h);
     h->free_all();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -108,6 +109,7 @@ extern "C" int sindyn_set_stream(sindyn_handle h, void *s)
         h->stream = ns;
         h->brox.graph_ok = false;
         h->brox_lm.graph_ok = false;  // graphs are stream-agnostic, but re-capture keeps capture semantics simple
+        flow_tail_drop_graphs(h);
     }
     return SINDYN_OK;
 }

@@ -63,6 +63,9 @@ struct sindyn_ctx : sindyn_base {
     cudaStream_t stream2 = nullptr;   // clustering branch (the reference runs the flow branch in its own std::thread)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_flag = nullptr;    // large-motion flag has arrived on the host
+    struct TailGraph { cudaGraphExec_t exec = nullptr; const uint8_t *k0 = nullptr, *k1 = nullptr; cudaStream_t stream = nullptr; unsigned long long launches = 0; };
+    TailGraph tail[8];                // captured post-decision part of the flow branch, per frame-ring position
+    int tail_next = 0;
     cudaGraphExec_t cluster_graph = nullptr;   // captured clustering branch (three streams, no host decisions)
     cudaStream_t cluster_graph_stream = nullptr;
     unsigned long long cluster_graph_launches = 0;
@@ -81,6 +84,8 @@ int flow_branch_init(sindyn_ctx *c);                    // flow.cu
 int flow_branch_run(sindyn_ctx *c, int *large_motion);  // flow.cu
 int flow_branch_begin(sindyn_ctx *c);                   // flow.cu
 int flow_branch_finish(sindyn_ctx *c, int *large_motion);  // flow.cu
+int flow_finish_all(sindyn_ctx *c, int *large_motion);     // flow.cu: finish + homography + residual/masks (marks ev[3..5])
+void flow_tail_drop_graphs(sindyn_ctx *c);                 // flow.cu
 int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll);  // pipeline.cu
 int sindyn_ctx_init_stages(sindyn_ctx *c);              // stages.cu
 void sindyn_ctx_destroy_stages(sindyn_ctx *c);          // stages.cu

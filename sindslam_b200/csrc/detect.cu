@@ -111,14 +111,8 @@ static int detect_run(sindyn_ctx *c)
     CU_CHECK(c, cudaEventRecord(c->ev_join, c->stream2));
     // ---- flow branch, second part (contains the one host decision, large motion)
     int lm = 0;
-    SD_CHECK(flow_branch_finish(c, &lm));
+    SD_CHECK(flow_finish_all(c, &lm));   // marks ev[3], ev[4], ev[5]
     c->large_motion_last = lm;
-    MARK(c, 3);
-    SD_CHECK(homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last));
-    SD_CHECK(homography_estimate(c, &c->homog));
-    MARK(c, 4);
-    SD_CHECK(residual_homography_run_dev(c, &c->resid, c->flow_full, c->homog.H_dev, c->mask_low, c->mask_high));
-    MARK(c, 5);
     // ---- join + decision (DynaDetect.cc:1543-1636)
     CU_CHECK(c, cudaStreamWaitEvent(main_s, c->ev_join, 0));
     MARK(c, 6);

@@ -90,6 +90,15 @@ int flow_branch_begin(sindyn_ctx *c)
     return SINDYN_OK;
 }
 
+// refinement + up-sampling (DynaDetect.cc:1133-1147)
+static int flow_refine_upsample(sindyn_ctx *c, int i_ref)
+{
+    if (c->cfg.refine) SD_CHECK(varref_run(c, &c->varref, c->gsmall[c->i_cur], c->gsmall[i_ref], c->flow_small));
+    SD_CHECK(launch_resize_flow(c, c->flow_small, c->fw, c->fh, c->flow_full, c->W, c->H, 1.0f / c->cfg.flow_scale));
+    LAUNCH_CHECK(c);
+    return SINDYN_OK;
+}
+
 int flow_branch_finish(sindyn_ctx *c, int *large_motion)
 {
     const bool g = c->cfg.use_graphs != 0;
@@ -102,9 +111,71 @@ int flow_branch_finish(sindyn_ctx *c, int *large_motion)
         SD_CHECK(brox_run(c, &c->brox_lm, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_last], c->flow_small, -1.0f, g));
         i_ref = c->i_last;
     }
-    if (c->cfg.refine) SD_CHECK(varref_run(c, &c->varref, c->gsmall[c->i_cur], c->gsmall[i_ref], c->flow_small));
-    SD_CHECK(launch_resize_flow(c, c->flow_small, c->fw, c->fh, c->flow_full, c->W, c->H, 1.0f / c->cfg.flow_scale));
-    LAUNCH_CHECK(c);
+    return flow_refine_upsample(c, i_ref);
+}
+
+// Everything after the large-motion decision up to the two masks (DynaDetect.cc:1121-1367): optional second Brox solve,
+// refinement, up-sampling, sample weighting + homography, residual + thresholds.  ~90 small launches whose host enqueue
+// time would otherwise starve the GPU right after the host wait; with use_graphs they are captured once per frame-ring
+// position (the key is the pair of gray images the refinement reads) and replayed as ONE graph launch.
+void flow_tail_drop_graphs(sindyn_ctx *c)
+{
+    for (auto &t : c->tail) {
+        if (t.exec) cudaGraphExecDestroy(t.exec);
+        t = sindyn_ctx::TailGraph();
+    }
+    c->tail_next = 0;
+}
+
+int flow_finish_all(sindyn_ctx *c, int *large_motion)
+{
+    const bool timing = c->cfg.stage_timing && c->ev_ok;
+    const bool g = c->cfg.use_graphs != 0 && !c->cfg.stage_timing;
+    CU_CHECK(c, cudaEventSynchronize(c->ev_flag));
+    const int lm = c->fb_flag_host[0];
+    if (large_motion) *large_motion = lm;
+    int i_ref = c->i_lastlast;
+    if (lm) {
+        SD_CHECK(brox_run(c, &c->brox_lm, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_last], c->flow_small, -1.0f, c->cfg.use_graphs != 0));
+        i_ref = c->i_last;
+    }
+    if (g) {
+        const uint8_t *k0 = c->gsmall[c->i_cur], *k1 = c->gsmall[i_ref];
+        sindyn_ctx::TailGraph *t = nullptr;
+        for (auto &q : c->tail)
+            if (q.exec && q.k0 == k0 && q.k1 == k1 && q.stream == c->stream) t = &q;
+        if (!t) {
+            t = &c->tail[c->tail_next];
+            c->tail_next = (c->tail_next + 1) % 8;
+            if (t->exec) cudaGraphExecDestroy(t->exec);
+            *t = sindyn_ctx::TailGraph();
+            const unsigned long long before = c->launches;
+            cudaGraph_t gr = nullptr;
+            CU_CHECK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int st = flow_refine_upsample(c, i_ref);
+            if (st == SINDYN_OK) st = homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last);
+            if (st == SINDYN_OK) st = homography_estimate(c, &c->homog);
+            if (st == SINDYN_OK) st = residual_homography_run_dev(c, &c->resid, c->flow_full, c->homog.H_dev, c->mask_low, c->mask_high);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &gr);
+            t->launches = c->launches - before;
+            c->launches = before;
+            SD_CHECK(st);
+            CU_CHECK(c, e);
+            CU_CHECK(c, cudaGraphInstantiate(&t->exec, gr, 0));
+            cudaGraphDestroy(gr);
+            t->k0 = k0; t->k1 = k1; t->stream = c->stream;
+        }
+        CU_CHECK(c, cudaGraphLaunch(t->exec, c->stream));
+        c->launches += t->launches;
+        return SINDYN_OK;
+    }
+    SD_CHECK(flow_refine_upsample(c, i_ref));
+    if (timing) CU_CHECK(c, cudaEventRecord(c->ev[3], c->stream));
+    SD_CHECK(homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last));
+    SD_CHECK(homography_estimate(c, &c->homog));
+    if (timing) CU_CHECK(c, cudaEventRecord(c->ev[4], c->stream));
+    SD_CHECK(residual_homography_run_dev(c, &c->resid, c->flow_full, c->homog.H_dev, c->mask_low, c->mask_high));
+    if (timing) CU_CHECK(c, cudaEventRecord(c->ev[5], c->stream));
     return SINDYN_OK;
 }
 

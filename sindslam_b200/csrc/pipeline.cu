@@ -32,14 +32,9 @@ int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll)
     SD_CHECK(sindyn_prep_frame(c, c->i_cur));
     STAGE_MARK(c, 1);
     int lm = 0;
-    SD_CHECK(flow_branch_run(c, &lm));   // marks ev[2] (after Brox) itself
+    SD_CHECK(flow_branch_begin(c));      // marks ev[2] (after Brox) itself
+    SD_CHECK(flow_finish_all(c, &lm));   // marks ev[3], ev[4], ev[5]
     c->large_motion_last = lm;
-    STAGE_MARK(c, 3);
-    SD_CHECK(homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last));
-    SD_CHECK(homography_estimate(c, &c->homog));
-    STAGE_MARK(c, 4);
-    SD_CHECK(residual_homography_run_dev(c, &c->resid, c->flow_full, c->homog.H_dev, c->mask_low, c->mask_high));
-    STAGE_MARK(c, 5);
     if (roll) {  // imgRGBLastLast <- imgRGBLast <- cur (DynaDetect.cc:1661-1662): index rotation, no copies
         int t = c->i_lastlast;
         c->i_lastlast = c->i_last;
