@@ -23,24 +23,31 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b)
 }
 
 // one warp = 32 consecutive pixels of a row: label = first pixel of the horizontal run inside the segment
+// All CCL kernels are launched with gridDim.z = capacity planes but only *active planes do work: a fixed, small number
+// of blocks per plane walks the plane with a grid-stride loop, so that inactive planes cost a handful of empty blocks
+// instead of N/256 of them (the decision stage launches 128 planes for ~10 active ones).
+#define CCL_BPP 96   // blocks per plane
+
 __global__ void k_ccl_init(const uint8_t *__restrict__ cls, int *__restrict__ labels, int W, int H, const int *__restrict__ active)
 {
     const int plane = blockIdx.z;
     if (active && plane >= *active) return;
     const int N = W * H;
     const int segs = (W + 31) >> 5;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= segs * H) return;
-    const int y = warp / segs, x = (warp - y * segs) * 32 + lane;
+    const int lane = threadIdx.x & 31;
     const uint8_t *c = cls + (size_t)plane * N;
     int *L = labels + (size_t)plane * (N + 1);
-    int v = x < W ? c[y * W + x] : 256 + lane;  // out-of-row lanes never match
-    int pv = __shfl_up_sync(0xffffffffu, v, 1);
-    bool start = lane == 0 || pv != v;
-    unsigned m = __ballot_sync(0xffffffffu, start);
-    int sl = 31 - __clz(m & (0xffffffffu >> (31 - lane)));
-    if (x < W) L[y * W + x] = y * W + (x - lane + sl);
-    if (warp == 0 && lane == 0) L[N] = N;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < segs * H; warp += nwarps) {
+        const int y = warp / segs, x = (warp - y * segs) * 32 + lane;
+        int v = x < W ? c[y * W + x] : 256 + lane;  // out-of-row lanes never match
+        int pv = __shfl_up_sync(0xffffffffu, v, 1);
+        bool start = lane == 0 || pv != v;
+        unsigned m = __ballot_sync(0xffffffffu, start);
+        int sl = 31 - __clz(m & (0xffffffffu >> (31 - lane)));
+        if (x < W) L[y * W + x] = y * W + (x - lane + sl);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) L[N] = N;
 }
 
 __global__ void k_ccl_merge(const uint8_t *__restrict__ cls, int *__restrict__ labels, int W, int H, int mode, const int *__restrict__ active)
@@ -48,27 +55,27 @@ __global__ void k_ccl_merge(const uint8_t *__restrict__ cls, int *__restrict__ l
     const int plane = blockIdx.z;
     if (active && plane >= *active) return;
     const int N = W * H;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
     const uint8_t *c = cls + (size_t)plane * N;
     int *L = labels + (size_t)plane * (N + 1);
-    const int p = y * W + x;
-    const int v = c[p];
-    if (mode == CCL_KEY8 && v == 255) return;
-    const bool eight = (mode == CCL_KEY8) || v == 1;
-    const int vl = x > 0 ? c[p - 1] : -1, vu = y > 0 ? c[p - W] : -1;
-    const int vul = (x > 0 && y > 0) ? c[p - W - 1] : -1, vur = (x < W - 1 && y > 0) ? c[p - W + 1] : -1;
-    const int vr = x < W - 1 ? c[p + 1] : -1;
-    if ((x & 31) == 0 && vl == v) uf_union(L, p, p - 1);                 // runs are cut at 32-px segment starts
-    if (vu == v && !(vl == v && vul == v)) uf_union(L, p, p - W);         // a new vertical contact begins here
-    if (eight) {
-        if (vul == v && vu != v && vl != v) uf_union(L, p, p - W - 1);
-        if (vur == v && vu != v && vr != v) uf_union(L, p, p - W + 1);
-    }
-    if (mode == CCL_REGION && v == 0 && (x == 0 || y == 0 || x == W - 1 || y == H - 1)) {
-        // background on the image border belongs to the exterior; one union per border run is enough
-        bool first = (y == 0 || y == H - 1) ? (x == 0 || vl != 0) : true;
-        if (first) uf_union(L, p, N);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+        const int y = p / W, x = p - y * W;
+        const int v = c[p];
+        if (mode == CCL_KEY8 && v == 255) continue;
+        const bool eight = (mode == CCL_KEY8) || v == 1;
+        const int vl = x > 0 ? c[p - 1] : -1, vu = y > 0 ? c[p - W] : -1;
+        const int vul = (x > 0 && y > 0) ? c[p - W - 1] : -1, vur = (x < W - 1 && y > 0) ? c[p - W + 1] : -1;
+        const int vr = x < W - 1 ? c[p + 1] : -1;
+        if ((x & 31) == 0 && vl == v) uf_union(L, p, p - 1);                 // runs are cut at 32-px segment starts
+        if (vu == v && !(vl == v && vul == v)) uf_union(L, p, p - W);         // a new vertical contact begins here
+        if (eight) {
+            if (vul == v && vu != v && vl != v) uf_union(L, p, p - W - 1);
+            if (vur == v && vu != v && vr != v) uf_union(L, p, p - W + 1);
+        }
+        if (mode == CCL_REGION && v == 0 && (x == 0 || y == 0 || x == W - 1 || y == H - 1)) {
+            // background on the image border belongs to the exterior; one union per border run is enough
+            bool first = (y == 0 || y == H - 1) ? (x == 0 || vl != 0) : true;
+            if (first) uf_union(L, p, N);
+        }
     }
 }
 
@@ -77,20 +84,18 @@ __global__ void k_ccl_flatten(int *__restrict__ labels, int N, const int *__rest
     const int plane = blockIdx.z;
     if (active && plane >= *active) return;
     int *L = labels + (size_t)plane * (N + 1);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= N) L[i] = uf_find(L, i);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= N; i += gridDim.x * blockDim.x) L[i] = uf_find(L, i);
 }
+
+static inline int ccl_blocks(int work_items) { int b = cdiv(work_items, 256); return b < CCL_BPP ? b : CCL_BPP; }
 
 int ccl_run(sindyn_base *ctx, const uint8_t *cls, int *labels, int W, int H, int planes, int mode, const int *active_planes)
 {
     const int N = W * H;
     const int segs = (W + 31) >> 5;
-    dim3 g1(cdiv(segs * H * 32, 256), 1, planes);
-    LAUNCH(ctx, k_ccl_init, g1, 256, 0, cls, labels, W, H, active_planes);
-    dim3 blk(32, 8), g2(cdiv(W, 32), cdiv(H, 8), planes);
-    LAUNCH(ctx, k_ccl_merge, g2, blk, 0, cls, labels, W, H, mode, active_planes);
-    dim3 g3(cdiv(N + 1, 256), 1, planes);
-    LAUNCH(ctx, k_ccl_flatten, g3, 256, 0, labels, N, active_planes);
+    LAUNCH(ctx, k_ccl_init, dim3(ccl_blocks(segs * H * 32), 1, planes), 256, 0, cls, labels, W, H, active_planes);
+    LAUNCH(ctx, k_ccl_merge, dim3(ccl_blocks(N), 1, planes), 256, 0, cls, labels, W, H, mode, active_planes);
+    LAUNCH(ctx, k_ccl_flatten, dim3(ccl_blocks(N + 1), 1, planes), 256, 0, labels, N, active_planes);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }
@@ -101,20 +106,19 @@ __global__ void k_ccl_top(const int *__restrict__ labels, int *__restrict__ top,
     const int plane = blockIdx.z;
     if (active && plane >= *active) return;
     const int N = W * H;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
     const int *L = labels + (size_t)plane * (N + 1);
-    int t = rc_top(L, N, W, i);
-    top[(size_t)plane * N + i] = t;
-    // statistics are accumulated only at region roots: clear those entries here instead of a full memset
-    if (zero_stats && L[i] == i) { RegionStats z; z.steps = 0; z.area2 = 0; zero_stats[(size_t)plane * N + i] = z; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        int t = rc_top(L, N, W, i);
+        top[(size_t)plane * N + i] = t;
+        // statistics are accumulated only at region roots: clear those entries here instead of a full memset
+        if (zero_stats && L[i] == i) { RegionStats z; z.steps = 0; z.area2 = 0; zero_stats[(size_t)plane * N + i] = z; }
+    }
 }
 
 int ccl_top_image(sindyn_base *ctx, const int *labels, int *top, int W, int H, int planes, const int *active_planes,
                   RegionStats *zero_stats)
 {
-    dim3 g(cdiv(W * H, 256), 1, planes);
-    LAUNCH(ctx, k_ccl_top, g, 256, 0, labels, top, W, H, active_planes, zero_stats);
+    LAUNCH(ctx, k_ccl_top, dim3(ccl_blocks(W * H), 1, planes), 256, 0, labels, top, W, H, active_planes, zero_stats);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }
@@ -163,17 +167,17 @@ __global__ void k_quad_external(const int *__restrict__ top, RegionStats *__rest
     const int plane = blockIdx.z;
     if (active && plane >= *active) return;
     const int N = W * H;
-    // quads have top-left pixel (x, y) with x in [-1, W-1], y in [-1, H-1]
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1, y = (int)(blockIdx.y * blockDim.y + threadIdx.y) - 1;
-    if (x >= W || y >= H) return;
     const int *T = top + (size_t)plane * N;
+    // quads have top-left pixel (x, y) with x in [-1, W-1], y in [-1, H-1]
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < (W + 1) * (H + 1); q += gridDim.x * blockDim.x) {
+    const int y = q / (W + 1) - 1, x = q - (y + 1) * (W + 1) - 1;
     auto at = [&](int xx, int yy) -> int { return (xx >= 0 && xx < W && yy >= 0 && yy < H) ? T[yy * W + xx] : -1; };
     const int ta = at(x, y), tb = at(x + 1, y), tc = at(x, y + 1), td = at(x + 1, y + 1);
     int X = ta >= 0 ? ta : (tb >= 0 ? tb : (tc >= 0 ? tc : td));
-    if (X < 0) return;
+    if (X < 0) continue;
     // different top-level components are never 8-adjacent, so every non-negative id in the quad equals X
     int m = (ta == X) | ((tb == X) << 1) | ((tc == X) << 2) | ((td == X) << 3);
-    if (m == 0xF) return;
+    if (m == 0xF) continue;
     int axis = 0, diag = 0;
     long long g = 0;
     quad_outer(m, x, y, axis, diag, g);
@@ -182,12 +186,12 @@ __global__ void k_quad_external(const int *__restrict__ top, RegionStats *__rest
         atomicAdd(&s->steps, (unsigned long long)axis | ((unsigned long long)diag << 32));
         if (g) atomicAdd((unsigned long long *)&s->area2, (unsigned long long)g);
     }
+    }
 }
 
 int ccl_quad_stats_external(sindyn_base *ctx, const int *top, RegionStats *stats, int W, int H, int planes, const int *active_planes)
 {
-    dim3 blk(32, 8), g(cdiv(W + 1, 32), cdiv(H + 1, 8), planes);
-    LAUNCH(ctx, k_quad_external, g, blk, 0, top, stats, W, H, active_planes);
+    LAUNCH(ctx, k_quad_external, dim3(ccl_blocks((W + 1) * (H + 1)), 1, planes), 256, 0, top, stats, W, H, active_planes);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }
@@ -198,11 +202,11 @@ __global__ void k_quad_ccomp(const uint8_t *__restrict__ cls, const int *__restr
     const int plane = blockIdx.z;
     if (active && plane >= *active) return;
     const int N = W * H;
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1, y = (int)(blockIdx.y * blockDim.y + threadIdx.y) - 1;
-    if (x >= W || y >= H) return;
     const int *L = labels + (size_t)plane * (N + 1);
     const uint8_t *c = cls + (size_t)plane * N;
     const int ext = L[N];
+    for (int q_ = blockIdx.x * blockDim.x + threadIdx.x; q_ < (W + 1) * (H + 1); q_ += gridDim.x * blockDim.x) {
+    const int y = q_ / (W + 1) - 1, x = q_ - (y + 1) * (W + 1) - 1;
     int r[4], par[4], fgv[4];
     const int xs[4] = {x, x + 1, x, x + 1}, ys[4] = {y, y, y + 1, y + 1};
 #pragma unroll
@@ -235,13 +239,13 @@ __global__ void k_quad_ccomp(const uint8_t *__restrict__ cls, const int *__restr
             if (g) atomicAdd((unsigned long long *)&s->area2, (unsigned long long)g);
         }
     }
+    }
 }
 
 int ccl_quad_stats_ccomp(sindyn_base *ctx, const uint8_t *cls, const int *labels, RegionStats *stats, int W, int H, int planes,
                          const int *active_planes)
 {
-    dim3 blk(32, 8), g(cdiv(W + 1, 32), cdiv(H + 1, 8), planes);
-    LAUNCH(ctx, k_quad_ccomp, g, blk, 0, cls, labels, stats, W, H, active_planes);
+    LAUNCH(ctx, k_quad_ccomp, dim3(ccl_blocks((W + 1) * (H + 1)), 1, planes), 256, 0, cls, labels, stats, W, H, active_planes);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }

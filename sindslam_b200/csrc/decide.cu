@@ -79,28 +79,28 @@ __global__ void k_dd_seeds(const uint8_t *__restrict__ cls, const int *__restric
     const int pl = blockIdx.z;
     if (pl >= ctl->nmax) return;
     const int N = W * H;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
     const int *L = L_all + (size_t)pl * (N + 1);
-    if (L[i] != i || i == L[N]) return;                 // not a root, or the exterior
     const uint8_t *fg = cls + (size_t)pl * N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    if (L[i] != i || i == L[N]) continue;               // not a root, or the exterior
     const bool is_hole = fg[i] == 0;
     const RegionStats s = stats[(size_t)pl * N + i];
     const double axis = (double)(s.steps & 0xffffffffull), diag = (double)(s.steps >> 32);
     const double area = (double)(s.area2 < 0 ? -s.area2 : s.area2) * 0.5;
     const double len = axis + diag * (double)1.41421354f;   // arcLength: float segment lengths summed in double
     const double roundness = (4.0 * 3.141592653589793 * area) / (len * len);
-    if (!((area > 100.0 && roundness > 0.2) || area > 2000.0)) return;
+    if (!((area > 100.0 && roundness > 0.2) || area > 2000.0)) continue;
     const int start = is_hole ? i - 1 : i;
     int seed = rc_trace_first_hit(fg, W, H, start, is_hole, [&](int p) { return low[p] == 128; });
     int plane2 = 0;
     if (seed < 0) {
         // cv::Point2f seedPoint stays (0,0): floodFill starts there if the cluster contains that pixel
-        if (labels[0] != pl + 1) return;
+        if (labels[0] != pl + 1) continue;
         seed = 0;
         plane2 = low[0] == 128 ? 0 : 1;
     }
     seedflag[(size_t)plane2 * N + keyL[(size_t)plane2 * (N + 1) + seed]] = 1;
+    }
 }
 
 __global__ void k_dd_filled(const uint8_t *__restrict__ labels, const uint8_t *__restrict__ low, const int *__restrict__ keyL,
@@ -178,7 +178,7 @@ int decide_run(sindyn_base *ctx, DecideStage *d, uint8_t *cls, int *labelsL, Reg
     SD_CHECK(ccl_quad_stats_ccomp(ctx, cls, labelsL, stats, W, H, DD_MAXL, &ctl->nmax));
     SD_CHECK(ccl_run(ctx, d->key, d->keyL, W, H, 2, CCL_KEY8, nullptr));
     CU_CHECK(ctx, cudaMemsetAsync(d->seedflag, 0, 2 * (size_t)N, ctx->stream));
-    LAUNCH(ctx, k_dd_seeds, dim3(cdiv(N, 256), 1, DD_MAXL), 256, 0, cls, labelsL, stats, d->low, labels, d->keyL, W, H, ctl, d->seedflag);
+    LAUNCH(ctx, k_dd_seeds, dim3(96, 1, DD_MAXL), 256, 0, cls, labelsL, stats, d->low, labels, d->keyL, W, H, ctl, d->seedflag);
     LAUNCH(ctx, k_dd_filled, SINDYN_NUM_SMS_B200 * 2, 256, 0, labels, d->low, d->keyL, d->seedflag, N, ctl, d->filled);
     LAUNCH(ctx, k_dd_dyna, cdiv(N, 256), 256, 0, labels, d->filled, N, ctl, d->dyna);
     SD_CHECK(morph_run(ctx, d->dyna, d->filled, d->tmp, W, H, 9, MORPH_DILATE));
