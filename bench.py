@@ -337,9 +337,12 @@ def run_ours(args):
                 acc += stage.stage_ms()
         acc /= 6
         stage.close()
-        full = full_pipeline_stats(cam, frames, local, refine)
-        multi = multi_sequence_stats(cam, local, refine)
-        cpu_v, cpu_n, cpu_dt = cpu_pairs_per_s(frames, "brox", budget_s=12.0, max_pairs=200)
+        if args.headline_only:
+            full, multi, (cpu_v, cpu_n, cpu_dt) = None, None, (None, 0, 0.0)
+        else:
+            full = full_pipeline_stats(cam, frames, local, refine)
+            multi = multi_sequence_stats(cam, local, refine)
+            cpu_v, cpu_n, cpu_dt = cpu_pairs_per_s(frames, "brox", budget_s=12.0, max_pairs=200)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -375,6 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-refine", action="store_true", help="skip the VariationalRefinement-equivalent pass (diagnostics only)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the full-pipeline / multi-sequence / CPU-baseline extras (ncu runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

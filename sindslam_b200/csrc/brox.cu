@@ -167,8 +167,10 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
     // colour arrays are padded by BROX_G zero elements on both sides: neighbour reads that fall off a row / the region
     // land on a zero weight (never on a NaN) instead of needing per-pixel bounds logic in the sweep
     float2 *s_uv = (float2 *)sm4 + BROX_G;      // [2][NPCP]  (du, dv) by colour
-    float2 *s_w = s_uv + 2 * BROX_NPCP;         // [2][NPCP]  (weight to the right neighbour, weight to the lower neighbour)
-    float *s_ta = (float *)((float2 *)sm4 + 4 * BROX_NPCP);  // [PP] u + du_base
+    // edge weights as two separate float arrays (32-bit loads of one component of a float2 array are 2-way bank conflicted)
+    float *s_wr = (float *)((float2 *)sm4 + 2 * BROX_NPCP) + BROX_G;   // [2][NPCP] weight to the right neighbour
+    float *s_wd = s_wr + 2 * BROX_NPCP;                                 // [2][NPCP] weight to the lower neighbour
+    float *s_ta = (float *)((float2 *)sm4 + 4 * BROX_NPCP);  // [PP] u + du_base (the weight arrays take 4*NPCP floats = 2*NPCP float2)
     float *s_tb = s_ta + BROX_PP;               // [PP] v + dv_base
     float *s_ps = s_tb + BROX_PP;               // [PP] smoothness diffusivity
     float *s_u = s_ps + BROX_PP;                // [PP] flow of this level (u, v): neighbours for the right-hand side
@@ -214,41 +216,63 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
     if (p.halo == 0) {   // single-tile mode stages only the rows the level has: clear everything once
         for (int r = tid; r < 4 * BROX_NPCP; r += BROX_NT) ((float2 *)sm4)[r] = make_float2(0.0f, 0.0f);
     } else {             // tiled mode rewrites the whole region every launch: only the guards need zeros
-        for (int r = tid; r < 8 * BROX_G; r += BROX_NT) {
-            const int a = r / (2 * BROX_G), o = r - a * 2 * BROX_G;
-            ((float2 *)sm4)[a * BROX_NPCP + (o < BROX_G ? o : BROX_NPC + o)] = make_float2(0.0f, 0.0f);
+        for (int r = tid; r < 12 * BROX_G; r += BROX_NT) {
+            const int a = r / (2 * BROX_G), o = r - a * 2 * BROX_G;       // a: 0,1 = uv colours; 2..5 = wr c0, wr c1, wd c0, wd c1
+            const int off = o < BROX_G ? o - BROX_G : BROX_NPC + (o - BROX_G);   // relative to the array base (which sits BROX_G after its start)
+            if (a < 2) s_uv[a * BROX_NPCP + off] = make_float2(0.0f, 0.0f);
+            else s_wr[(a - 2) * BROX_NPCP + off] = 0.0f;                  // s_wd follows s_wr contiguously
         }
     }
     __syncthreads();
     for (int it = 0; it < p.n_inner; ++it) {
-        // ---- phase 0: stage (du,dv) and the total flow u + du_base (radius = whole region)
-        for (int r = tid; r < pp_used; r += BROX_NT) {
-            const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
-            const int x = ox + lx, y = oy + ly;
-            const int ci = ((lx + ly) & 1) * BROX_NPCP + ly * BROX_HW + (lx >> 1);
-            float ta = 0.0f, tb = 0.0f;
-            if (x >= 0 && x < w && y >= 0 && y < h) {
-                const int g = y * w + x;
+        // ---- phase 0: stage (du,dv), the level's flow (u,v) and the total flow u + du_base (radius = whole region).
+        // Four region pixels per thread and pass: the global loads of all four are issued before the first use (the
+        // phase is bound by L2 latency with only 16 warps per SM).
+        for (int r0 = tid; r0 < pp_used; r0 += 4 * BROX_NT) {
+            int g[4], ci[4];
+            bool in[4];
+            float bu[4], bv[4], uu[4], vv[4], iu[4], iv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = r0 + k * BROX_NT;
+                in[k] = false; g[k] = 0; ci[k] = 0;
+                if (r < pp_used) {
+                    const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
+                    const int x = ox + lx, y = oy + ly;
+                    ci[k] = ((lx + ly) & 1) * BROX_NPCP + ly * BROX_HW + (lx >> 1);
+                    in[k] = x >= 0 && x < w && y >= 0 && y < h;
+                    g[k] = y * w + x;
+                }
+            }
+            if (it == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    bu[k] = bv[k] = uu[k] = vv[k] = iu[k] = iv[k] = 0.0f;
+                    if (in[k]) {
+                        bu[k] = p.dub[g[k]]; bv[k] = p.dvb[g[k]]; uu[k] = p.u[g[k]]; vv[k] = p.v[g[k]];
+                        if (!same_base) { iu[k] = p.dui[g[k]]; iv[k] = p.dvi[g[k]]; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = r0 + k * BROX_NT;
+                if (r >= pp_used) continue;
+                float ta = 0.0f, tb = 0.0f;
                 if (it == 0) {
-                    const float bu = p.dub[g], bv = p.dvb[g];
-                    const float uu = p.u[g], vv = p.v[g];
-                    s_uv[ci] = same_base ? make_float2(bu, bv) : make_float2(p.dui[g], p.dvi[g]);
-                    s_u[r] = uu;
-                    s_v[r] = vv;
-                    ta = uu + bu;
-                    tb = vv + bv;
-                } else {   // single-tile mode: the increment of the previous inner iteration is already in shared memory
-                    const float2 d = s_uv[ci];
+                    s_uv[ci[k]] = same_base ? make_float2(bu[k], bv[k]) : make_float2(iu[k], iv[k]);   // zeros outside the image
+                    s_u[r] = uu[k];
+                    s_v[r] = vv[k];
+                    ta = uu[k] + bu[k];
+                    tb = vv[k] + bv[k];
+                } else if (in[k]) {   // single-tile mode: the increment of the previous inner iteration is already in shared memory
+                    const float2 d = s_uv[ci[k]];
                     ta = s_u[r] + d.x;
                     tb = s_v[r] + d.y;
                 }
-            } else if (it == 0) {
-                s_uv[ci] = make_float2(0.0f, 0.0f);
-                s_u[r] = 0.0f;
-                s_v[r] = 0.0f;
+                s_ta[r] = ta;
+                s_tb[r] = tb;
             }
-            s_ta[r] = ta;
-            s_tb[r] = tb;
         }
         __syncthreads();
         // ---- phase 1: smoothness diffusivity psi'_s from the gradient of the total flow
@@ -276,7 +300,9 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 if (x < w - 1 && lx < BROX_PW - 1) wr = alpha * 0.5f * (ps + s_ps[r + 1]);
                 if (y < h - 1 && ly < BROX_PH - 1) wd = alpha * 0.5f * (ps + s_ps[r + BROX_PW]);
             }
-            s_w[((lx + ly) & 1) * BROX_NPCP + ly * BROX_HW + (lx >> 1)] = make_float2(wr, wd);
+            const int wi = ((lx + ly) & 1) * BROX_NPCP + ly * BROX_HW + (lx >> 1);
+            s_wr[wi] = wr;
+            s_wd[wi] = wd;
         }
         __syncthreads();
         // ---- phase 2b: data term and the 2x2 system of the owned pixels -> registers
@@ -289,10 +315,8 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 const int idx = k & 0xfff, par = (k >> 12) & 1;
                 const int ly = idx / BROX_HW, lx = 2 * (idx - ly * BROX_HW) + par;
                 const int x = ox + lx, y = oy + ly, g = y * w + x;
-                const float2 *wo = s_w + (c ^ 1) * BROX_NPCP;
-                const float2 wown = s_w[c * BROX_NPCP + idx];
-                const float wl = x > 0 ? wo[idx - 1 + par].x : 0.0f, wr = wown.x;
-                const float wu = y > 0 ? wo[idx - BROX_HW].y : 0.0f, wd = wown.y;
+                const float wl = x > 0 ? s_wr[(c ^ 1) * BROX_NPCP + idx - 1 + par] : 0.0f, wr = s_wr[c * BROX_NPCP + idx];
+                const float wu = y > 0 ? s_wd[(c ^ 1) * BROX_NPCP + idx - BROX_HW] : 0.0f, wd = s_wd[c * BROX_NPCP + idx];
                 const float2 own = s_uv[c * BROX_NPCP + idx];
                 float dub, dvb;
                 if (it == 0) { dub = p.dub[g]; dvb = p.dvb[g]; } else { dub = own.x; dvb = own.y; }
@@ -322,15 +346,17 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 cd1[c][m] = 1.0f / (j11 + sw_);
                 cd2[c][m] = 1.0f / (j22 + sw_);
             }
-        // (no barrier needed: the sweeps below read only s_uv / s_w, which are complete)
+        // (no barrier needed: the sweeps below read only s_uv / s_wr / s_wd, which are complete)
         // ---- red-black SOR: half-sweep k updates colour (k-1)&1 where the halo distance allows it
         const unsigned thr0 = (unsigned)(p.halo > ns2 ? p.halo - ns2 : 0);
 #define BROX_HALF(C, K)                                                                                           \
     {                                                                                                             \
         const float2 *__restrict__ uo = s_uv + ((C) ^ 1) * BROX_NPCP;                                              \
         float2 *__restrict__ uc_ = s_uv + (C) * BROX_NPCP;                                                         \
-        const float2 *__restrict__ wo = s_w + ((C) ^ 1) * BROX_NPCP;                                               \
-        const float2 *__restrict__ wc_ = s_w + (C) * BROX_NPCP;                                                    \
+        const float *__restrict__ wro = s_wr + ((C) ^ 1) * BROX_NPCP;                                              \
+        const float *__restrict__ wdo = s_wd + ((C) ^ 1) * BROX_NPCP;                                              \
+        const float *__restrict__ wrc = s_wr + (C) * BROX_NPCP;                                                    \
+        const float *__restrict__ wdc = s_wd + (C) * BROX_NPCP;                                                    \
         _Pragma("unroll") for (int m = 0; m < BROX_M; ++m)                                                        \
         {                                                                                                         \
             const unsigned k_ = pk[C][m];                                                                         \
@@ -339,10 +365,10 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
             if (((k_ >> 14) & 1u) && (k_ >> 16) >= thr0 + (unsigned)(K)) {                                        \
                 const int idx = k_ & 0xfff, par = (k_ >> 12) & 1;                                                 \
                 const float2 l = uo[idx - 1 + par], r = uo[idx + par], u_ = uo[idx - BROX_HW], d = uo[idx + BROX_HW]; \
-                const float2 wown = wc_[idx];                                                                     \
-                const float wl = wo[idx - 1 + par].x, wu = wo[idx - BROX_HW].y;                                   \
-                const float su = wl * l.x + wown.x * r.x + wu * u_.x + wown.y * d.x;                              \
-                const float sv = wl * l.y + wown.x * r.y + wu * u_.y + wown.y * d.y;                              \
+                const float wr_ = wrc[idx], wd_ = wdc[idx];                                                       \
+                const float wl = wro[idx - 1 + par], wu = wdo[idx - BROX_HW];                                     \
+                const float su = wl * l.x + wr_ * r.x + wu * u_.x + wd_ * d.x;                                    \
+                const float sv = wl * l.y + wr_ * r.y + wu * u_.y + wd_ * d.y;                                    \
                 const float du_new = om1 * rdu[C][m] + omega * (cb1[C][m] - cj12[C][m] * rdv[C][m] + su) * cd1[C][m]; \
                 const float dv_new = om1 * rdv[C][m] + omega * (cb2[C][m] - cj12[C][m] * du_new + sv) * cd2[C][m]; \
                 rdu[C][m] = du_new;                                                                               \
