@@ -138,7 +138,7 @@ struct BroxInnerP {
     int tw, th, halo, n_inner;
 };
 
-constexpr int BROX_SMAX = 10, BROX_NT = 512;
+constexpr int BROX_SMAX = 10, BROX_NT = 1024;
 constexpr int BROX_RMAX = 2 * BROX_SMAX + 1;
 // Tile menu: a level uses the smallest tile whose grid still fits into one wave of 148 SMs -- the time of a launch is
 // the time of ONE CTA, which is proportional to the staged region (tile + 2 x 21 halo), so mid-size levels run on
@@ -152,7 +152,9 @@ template <int TW_, int TH_> struct BroxTile {
     static constexpr int PP = PW * PH;
     static constexpr int G = HW + 1;                 // zero guard before / after every colour array (wrapped neighbour reads)
     static constexpr int NPCP = NPC + 2 * G;
-    static constexpr size_t SMEM = sizeof(float2) * 4 * NPCP + sizeof(float) * 5 * PP;
+    // (du,dv) + edge weights | per-pixel 2x2 systems (5 floats; the staging planes ta / tb / ps alias their start) | u, v
+    static constexpr size_t SMEM = sizeof(float2) * 4 * NPCP + sizeof(float) * 10 * NPC + sizeof(float) * 2 * PP;
+    static_assert(3 * PP <= 10 * NPC, "ta / tb / ps must fit into the coefficient area they alias");
     static_assert((PW & 1) == 0, "de-interleaving needs an even region width");
     static_assert(NPC < 4096, "pixel index must fit into 12 bits");
 };
@@ -170,10 +172,14 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
     // edge weights as two separate float arrays (32-bit loads of one component of a float2 array are 2-way bank conflicted)
     float *s_wr = (float *)((float2 *)sm4 + 2 * BROX_NPCP) + BROX_G;   // [2][NPCP] weight to the right neighbour
     float *s_wd = s_wr + 2 * BROX_NPCP;                                 // [2][NPCP] weight to the lower neighbour
-    float *s_ta = (float *)((float2 *)sm4 + 4 * BROX_NPCP);  // [PP] u + du_base (the weight arrays take 4*NPCP floats = 2*NPCP float2)
+    // per-pixel 2x2 systems (j12, b1, b2, 1/d1 | 1/d2) by colour: with 1024 threads (64 registers each) they live in shared
+    // memory; they are written after ta / tb / ps are dead, so those staging planes alias the same bytes
+    float4 *s_c4 = (float4 *)((float2 *)sm4 + 4 * BROX_NPCP);   // [2][NPC]
+    float *s_c1 = (float *)(s_c4 + 2 * BROX_NPC);                // [2][NPC]
+    float *s_ta = (float *)s_c4;                // [PP] u + du_base
     float *s_tb = s_ta + BROX_PP;               // [PP] v + dv_base
     float *s_ps = s_tb + BROX_PP;               // [PP] smoothness diffusivity
-    float *s_u = s_ps + BROX_PP;                // [PP] flow of this level (u, v): neighbours for the right-hand side
+    float *s_u = (float *)s_c4 + 10 * BROX_NPC; // [PP] flow of this level (u, v): neighbours for the right-hand side
     float *s_v = s_u + BROX_PP;
     const int w = p.w, h = p.h;
     const int gx0 = blockIdx.x * p.tw, gy0 = blockIdx.y * p.th;
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
 
     // ---- per-thread pixel table: pk = idx (12 bits) | parity << 12 | interior << 13 | live << 14 | dist << 16
     unsigned pk[2][BROX_M];
-    float cj12[2][BROX_M], cb1[2][BROX_M], cb2[2][BROX_M], cd1[2][BROX_M], cd2[2][BROX_M], rdu[2][BROX_M], rdv[2][BROX_M];
+    float rdu[2][BROX_M], rdv[2][BROX_M];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 v = (unsigned)q | ((unsigned)par << 12) | ((unsigned)interior << 13) | ((unsigned)live << 14) | ((unsigned)dist << 16);
             }
             pk[c][m] = v;
-            cj12[c][m] = cb1[c][m] = cb2[c][m] = cd1[c][m] = cd2[c][m] = rdu[c][m] = rdv[c][m] = 0.0f;
+            rdu[c][m] = rdv[c][m] = 0.0f;
         }
 
     if (p.halo == 0) {   // single-tile mode stages only the rows the level has: clear everything once
@@ -340,13 +346,10 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 if (y > 0) { su += wu * (s_u[r - BROX_PW] - uc); sv += wu * (s_v[r - BROX_PW] - vc); }
                 if (y < h - 1) { su += wd * (s_u[r + BROX_PW] - uc); sv += wd * (s_v[r + BROX_PW] - vc); }
                 const float sw_ = wl + wr + wu + wd;
-                cj12[c][m] = j12;
-                cb1[c][m] = su - j13;
-                cb2[c][m] = sv - j23;
-                cd1[c][m] = 1.0f / (j11 + sw_);
-                cd2[c][m] = 1.0f / (j22 + sw_);
+                s_c4[c * BROX_NPC + idx] = make_float4(j12, su - j13, sv - j23, 1.0f / (j11 + sw_));
+                s_c1[c * BROX_NPC + idx] = 1.0f / (j22 + sw_);
             }
-        // (no barrier needed: the sweeps below read only s_uv / s_wr / s_wd, which are complete)
+        // (no barrier needed: the sweeps below read s_uv / s_wr / s_wd, which are complete, and the thread's own systems)
         // ---- red-black SOR: half-sweep k updates colour (k-1)&1 where the halo distance allows it
         const unsigned thr0 = (unsigned)(p.halo > ns2 ? p.halo - ns2 : 0);
 #define BROX_HALF(C, K)                                                                                           \
@@ -369,8 +372,10 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 const float wl = wro[idx - 1 + par], wu = wdo[idx - BROX_HW];                                     \
                 const float su = wl * l.x + wr_ * r.x + wu * u_.x + wd_ * d.x;                                    \
                 const float sv = wl * l.y + wr_ * r.y + wu * u_.y + wd_ * d.y;                                    \
-                const float du_new = om1 * rdu[C][m] + omega * (cb1[C][m] - cj12[C][m] * rdv[C][m] + su) * cd1[C][m]; \
-                const float dv_new = om1 * rdv[C][m] + omega * (cb2[C][m] - cj12[C][m] * du_new + sv) * cd2[C][m]; \
+                const float4 cf = s_c4[(C) * BROX_NPC + idx];                                                     \
+                const float cd2_ = s_c1[(C) * BROX_NPC + idx];                                                    \
+                const float du_new = om1 * rdu[C][m] + omega * (cf.y - cf.x * rdv[C][m] + su) * cf.w;             \
+                const float dv_new = om1 * rdv[C][m] + omega * (cf.z - cf.x * du_new + sv) * cd2_;                \
                 rdu[C][m] = du_new;                                                                               \
                 rdv[C][m] = dv_new;                                                                               \
                 uc_[idx] = make_float2(du_new, dv_new);                                                           \
