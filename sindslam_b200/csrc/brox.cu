@@ -124,8 +124,8 @@ __global__ void k_brox_deriv2(const float *__restrict__ Ix, const float *__restr
 //     distance d from a halo edge stays valid for d half-sweeps (temporal blocking) and only the interior is written;
 //   * red and black pixels are stored DE-INTERLEAVED (two arrays of 37-wide rows), so the stride-2 access pattern of a
 //     red-black sweep becomes stride-1 and bank-conflict free; (du,dv) and the two edge weights are float2 -> LDS.64;
-//   * every thread owns a FIXED set of 5 red + 5 black pixels for the whole launch: the 2x2 system of a pixel
-//     (j12, b1, b2, 1/d1, 1/d2) and its current (du,dv) stay in registers, only neighbour values go through shared memory;
+//   * every thread owns a FIXED set of <= 3 red + 3 black pixels for the whole launch: their current (du,dv) stay in
+//     registers, the 2x2 system of a pixel (j12, b1, b2, 1/d1, 1/d2) in shared memory (1024 threads, 64 registers each);
 //   * levels that fit into one tile (<= 74 x 66, the 7 coarsest of 15) run all inner iterations in ONE launch (halo 0).
 struct BroxInnerP {
     const float *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz, *u, *v;
