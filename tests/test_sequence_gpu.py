@@ -68,3 +68,48 @@ def test_c2_848x480_humanoid_stream():
     _, frames = synth.make_sequence(7, cam, seq=2, kind="humanoid", start=6)
     n_large, ious = _stream(cam, frames, list(range(7)))
     print("848x480 humanoid: IoU vs rendered truth:", np.round(ious, 3))
+
+
+def test_long_stream_invariants():
+    """BASELINE configs[2] shape (long walking_xyz-like sequence), at full size through size-independent properties: 120
+    frames through sindyn_detect + dilation + masked ORB (graph replay, state recurrence, fixed-capacity lists) must keep
+    every invariant of the reference outputs; every 30th frame is additionally checked bit-exactly against the oracle
+    fed with the device's state and masks."""
+    from sindslam_b200.capi import Orb, SinDyn
+    cam = synth.TUM3
+    n = 120
+    _, frames = synth.make_sequence(n, cam, seq=4, kind="box", start=0, hole_rate=0.002)
+    s = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor)
+    orb = Orb(1500, 1.2, 8, 15, 5, cam.width, cam.height)
+    s.set_prev_frames(frames[0].bgr, frames[0].bgr)
+    ious, n_kp = [], []
+    for k in range(1, n):
+        check = k % 30 == 0
+        if check:
+            st = [s.get_state(i) for i in range(5)]
+        mask, label = s.detect(frames[k].bgr, frames[k].depth, k)
+        assert set(np.unique(mask)) <= {0, 125, 255}
+        assert int(label.max()) < 128 and not ((label > 0) & (mask == 0)).all()
+        if check:
+            fr = s.flow_results()
+            o = orc.DynaDetectOracle(st[3], st[4], cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=False)
+            o.dyna_last, o.high_last, o.label_last = st[0], st[1], st[2]
+            s2 = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=0)
+            s2.set_state(3, st[3]); s2.set_state(4, st[4]); s2.set_state(0, st[0]); s2.set_state(1, st[1]); s2.set_state(2, st[2])
+            m2, l2 = s2.detect(frames[k].bgr, frames[k].depth, k)
+            f2 = s2.flow_results()
+            r = o.detect(frames[k].bgr, frames[k].depth, inject_masks=(f2["low"], f2["high"]))
+            assert np.array_equal(m2, r["mask"]) and np.array_equal(l2, r["label"]), k
+            s2.close()
+        dil = s.morph_ellipse(mask, 15, 0)
+        kps, desc = orb.extract(cv2.cvtColor(frames[k].bgr, cv2.COLOR_RGB2GRAY), dil)
+        assert 250 <= len(kps) <= 1500 + 8 and desc.shape == (len(kps), 32)
+        n_kp.append(len(kps))
+        if k >= 3:
+            gt = cv2.dilate(frames[k].dyn_mask.astype(np.uint8), orc.ellipse(9)) > 0
+            ious.append(_iou(mask == 255, gt))
+    print("120-frame stream: median IoU vs rendered truth %.3f (p10 %.3f), keypoints %d..%d" % (
+        float(np.median(ious)), float(np.quantile(ious, 0.1)), min(n_kp), max(n_kp)))
+    assert np.median(ious) > 0.8
+    s.close()
+    orb.close()
