@@ -243,6 +243,24 @@ int sindyn_orb_set_stream(sindyn_orb_handle h, void *cuda_stream);
 unsigned long long sindyn_orb_launch_count(sindyn_orb_handle h);
 const char *sindyn_orb_last_error(sindyn_orb_handle h);
 
+/* SURVEY.md 8(f) row f2 -- what ORB_SLAM2::Frame does with the keypoints right after the extraction (src/Frame.cc:143-170),
+ * on the keypoints that are still resident on the device: UndistortKeyPoints (Frame.cc:714-753), ComputeImageBounds
+ * (:507-535), ComputeStereoFromRGBD (depth lookup at the distorted keypoint, virtual right coordinate u - bf/d) and
+ * AssignFeaturesToGrid / PosInGrid (:453-463; 64 x 48 cells).
+ * depth_raw: 16UC1 raw depth of the frame; depth_map_factor = 1 / DepthMapFactor (Tracking.cc:142-146).
+ * Outputs (any may be NULL): keys_un n x 2 (mvKeysUn), depth n (mvDepth, -1 = none), u_right n (mvuRight), bounds[4] =
+ * {mnMinX, mnMaxX, mnMinY, mnMaxY}, grid as CSR: cell (i, j) = mGrid[i][j] holds grid_indices[grid_offsets[i*48+j] ..
+ * grid_offsets[i*48+j+1]) in push_back order. */
+typedef struct sindyn_frame_params {
+    float fx, fy, cx, cy;          /* mK */
+    float k1, k2, p1, p2, k3;      /* mDistCoef (Tracking.cc:60-75) */
+    float bf;                      /* mbf */
+    float depth_map_factor;        /* mDepthMapFactor */
+} sindyn_frame_params;
+int sindyn_orb_frame_features(sindyn_orb_handle h, const uint16_t *depth_raw, size_t depth_step, const sindyn_frame_params *params,
+                              float *keys_un, float *depth_out, float *u_right_out, float *bounds_out, int *grid_offsets,
+                              int *grid_indices, int capacity, int *n_out);
+
 const char *sindyn_version(void);
 
 #ifdef __cplusplus

@@ -230,6 +230,26 @@ public:
     }
 #endif
 
+    // what Frame::Frame does with the keypoints right after the extraction (Frame.cc:143-170), computed on
+    // the device while the keypoints are still resident: mvKeysUn, mvDepth, mvuRight, image bounds and the 64 x 48 mGrid (CSR).
+    struct FrameFeatures {
+        std::vector<float> keysUn, depth, uRight;   // n x 2, n, n
+        float bounds[4];                            // mnMinX, mnMaxX, mnMinY, mnMaxY
+        std::vector<int> gridOffsets, gridIndices;  // mGrid[i][j] = gridIndices[gridOffsets[i*48+j] .. gridOffsets[i*48+j+1])
+    };
+    void ComputeFrameFeatures(const sindyn::ImageView &imDepthRaw, const sindyn_frame_params &p, FrameFeatures &out)
+    {
+        if (!h_) throw sindyn::Error(SINDYN_ERR_STATE, "ComputeFrameFeatures: call operator() first");
+        const int cap = nfeatures * 2 + 64;
+        out.keysUn.resize((size_t)cap * 2); out.depth.resize(cap); out.uRight.resize(cap);
+        out.gridOffsets.resize(64 * 48 + 1); out.gridIndices.resize(cap);
+        int n = 0;
+        int st = sindyn_orb_frame_features(h_, (const uint16_t *)imDepthRaw.data, imDepthRaw.step, &p, out.keysUn.data(), out.depth.data(),
+                                           out.uRight.data(), out.bounds, out.gridOffsets.data(), out.gridIndices.data(), cap, &n);
+        if (st != SINDYN_OK) throw sindyn::Error(st, std::string("sindyn_orb_frame_features: ") + sindyn_orb_last_error(h_));
+        out.keysUn.resize((size_t)n * 2); out.depth.resize(n); out.uRight.resize(n); out.gridIndices.resize(out.gridOffsets.back());
+    }
+
     int inline GetLevels() { return nlevels; }
     float inline GetScaleFactor() { return (float)scaleFactor; }
     std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }

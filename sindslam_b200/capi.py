@@ -34,6 +34,10 @@ class Config(C.Structure):
     ]
 
 
+class FrameParams(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3", "bf", "depth_map_factor")]
+
+
 class Keypoint(C.Structure):
     _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
                 ("response", C.c_float), ("octave", C.c_int)]
@@ -88,6 +92,7 @@ SIGNATURES = {
     "sindyn_orb_get_pyramid_level": (_i, [_vp, _i, _vp, _ip, _ip]),
     "sindyn_orb_get_candidates": (_i, [_vp, _i, _vp, _i, _ip]),
     "sindyn_orb_get_plane": (_i, [_vp, _i, _i, _vp, _ip, _ip]),
+    "sindyn_orb_frame_features": (_i, [_vp, _vp, _sz, C.POINTER(FrameParams), _vp, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
     "sindyn_orb_set_stream": (_i, [_vp, _vp]),
     "sindyn_orb_launch_count": (C.c_ulonglong, [_vp]),
     "sindyn_orb_last_error": (C.c_char_p, [_vp]),
@@ -421,6 +426,25 @@ class Orb:
             raise SindynError(f"orb_extract: {STATUS.get(st, st)}: {self.lib.sindyn_orb_last_error(self.h).decode()}")
         arr = np.frombuffer(kps, dtype=np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")]))[:n.value].copy()
         return arr, desc[:n.value].copy()
+
+    def frame_features(self, depth_raw, fx, fy, cx, cy, dist, bf, depth_map_factor):
+        """Frame.cc:143-170 on the keypoints of the last extract(): (keys_un, depth, u_right, bounds, offsets, indices)."""
+        depth_raw = np.ascontiguousarray(depth_raw, np.uint16)
+        p = FrameParams(fx, fy, cx, cy, *[float(v) for v in dist], bf, depth_map_factor)
+        cap = self.nfeatures * 2 + 64
+        un = np.zeros((cap, 2), np.float32)
+        dep = np.zeros(cap, np.float32)
+        ur = np.zeros(cap, np.float32)
+        b = np.zeros(4, np.float32)
+        off = np.zeros(64 * 48 + 1, np.int32)
+        idx = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        st = self.lib.sindyn_orb_frame_features(self.h, _p(depth_raw), depth_raw.strides[0], C.byref(p), _p(un), _p(dep), _p(ur), _p(b),
+                                                _p(off), _p(idx), cap, C.byref(n))
+        if st != 0:
+            raise SindynError(f"orb_frame_features: {STATUS.get(st, st)}: {self.lib.sindyn_orb_last_error(self.h).decode()}")
+        k = n.value
+        return un[:k].copy(), dep[:k].copy(), ur[:k].copy(), b, off, idx[:int(off[-1])].copy()
 
     def candidates(self, level, capacity=16384):
         buf = np.zeros((capacity, 3), np.int32)

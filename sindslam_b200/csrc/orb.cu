@@ -62,6 +62,10 @@ struct sindyn_orb : sindyn_base {
     uint8_t *pin_gray = nullptr, *pin_mask = nullptr;   // pinned bounce buffers (see stage_in_2d)
     sindyn_keypoint *pin_kp = nullptr;
     uint8_t *pin_desc = nullptr;
+    // Frame construction
+    uint16_t *depth = nullptr, *pin_depth = nullptr;
+    float *fr_un = nullptr, *fr_depth = nullptr, *fr_uright = nullptr, *fr_bounds = nullptr;
+    int *fr_offsets = nullptr, *fr_indices = nullptr;
     size_t pad_total = 0, img_total = 0;
 };
 
@@ -674,6 +678,14 @@ extern "C" int sindyn_orb_create(int nfeatures, float scale_factor, int nlevels,
     SD_CHECK(o->halloc(&o->pin_mask, (size_t)width * height));
     SD_CHECK(o->halloc(&o->pin_kp, ORB_OUT_MAX));
     SD_CHECK(o->halloc(&o->pin_desc, (size_t)ORB_OUT_MAX * 32));
+    SD_CHECK(o->dalloc(&o->depth, (size_t)width * height));
+    SD_CHECK(o->halloc(&o->pin_depth, (size_t)width * height));
+    SD_CHECK(o->dalloc(&o->fr_un, 2 * ORB_OUT_MAX));
+    SD_CHECK(o->dalloc(&o->fr_depth, ORB_OUT_MAX));
+    SD_CHECK(o->dalloc(&o->fr_uright, ORB_OUT_MAX));
+    SD_CHECK(o->dalloc(&o->fr_bounds, 4));
+    SD_CHECK(o->dalloc(&o->fr_offsets, 64 * 48 + 1));
+    SD_CHECK(o->dalloc(&o->fr_indices, ORB_OUT_MAX));
     CU_CHECK(o, cudaMemcpyAsync(o->lv_dev, o->lv, sizeof(OrbLevel) * ORB_MAX_LEVELS, cudaMemcpyHostToDevice, o->stream));
     for (int l = 1; l < nlevels; ++l) SD_CHECK(resize_plan_init(o, &o->plan[l], o->lv[l - 1].w, o->lv[l - 1].h, o->lv[l].w, o->lv[l].h));
     // umax (ORBextractor.cc:450-467)
@@ -829,5 +841,110 @@ extern "C" int sindyn_orb_get_plane(sindyn_orb_handle h, int level, int which, u
     if (w_out) *w_out = w;
     if (h_out) *h_out = hh;
     CU_CHECK(h, cudaMemcpy(out, src, (size_t)w * hh, cudaMemcpyDeviceToHost));
+    return SINDYN_OK;
+}
+
+// ------------------------------------------------------------------ Frame construction right after ORB (row f2)
+// ORB_SLAM2::Frame (Frame.cc:143-170): UndistortKeyPoints (:714-753), ComputeImageBounds (:507-535),
+// ComputeStereoFromRGBD (depth lookup + virtual right coordinate), AssignFeaturesToGrid / PosInGrid (:453-463).
+// The keypoints stay on the device between sindyn_orb_extract and this call.
+#define FR_COLS 64
+#define FR_ROWS 48
+
+// cv::undistortPoints(pts, K, dist, noArray(), K): 5 fixed-point iterations in double (verified bit-exact against cv2)
+__device__ __forceinline__ void fr_undistort(float u, float v, const sindyn_frame_params &P, float &uo, float &vo)
+{
+    const double fx = P.fx, fy = P.fy, cx = P.cx, cy = P.cy;
+    const double k1 = P.k1, k2 = P.k2, p1 = P.p1, p2 = P.p2, k3 = P.k3;
+    const double x0 = ((double)u - cx) / fx, y0 = ((double)v - cy) / fy;
+    double x = x0, y = y0;
+    for (int it = 0; it < 5; ++it) {
+        const double r2 = x * x + y * y;
+        double icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2);
+        if (icdist < 0) icdist = 1.0;
+        const double dx = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x), dy = p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+        x = (x0 - dx) * icdist;
+        y = (y0 - dy) * icdist;
+    }
+    uo = (float)(x * fx + cx);
+    vo = (float)(y * fy + cy);
+}
+
+__global__ void __launch_bounds__(1024) k_orb_frame(const sindyn_keypoint *__restrict__ kps, const OrbControl *__restrict__ ctl,
+                                                     const uint16_t *__restrict__ depth, int W, int H, sindyn_frame_params P,
+                                                     float *__restrict__ un, float *__restrict__ dep, float *__restrict__ uright,
+                                                     float *__restrict__ bounds, int *__restrict__ offsets, int *__restrict__ indices)
+{
+    __shared__ float s_b[4];
+    __shared__ int s_cnt[FR_COLS * FR_ROWS];
+    __shared__ short s_cell[ORB_OUT_MAX];
+    const int n = ctl->n_out;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int c = tid; c < FR_COLS * FR_ROWS; c += nt) s_cnt[c] = 0;
+    if (tid == 0) {
+        if (P.k1 != 0.0f) {   // ComputeImageBounds: undistorted image corners
+            float x[4], y[4];
+            const float cxs[4] = {0.f, (float)W, 0.f, (float)W}, cys[4] = {0.f, 0.f, (float)H, (float)H};
+            for (int k = 0; k < 4; ++k) fr_undistort(cxs[k], cys[k], P, x[k], y[k]);
+            s_b[0] = fminf(x[0], x[2]); s_b[1] = fmaxf(x[1], x[3]); s_b[2] = fminf(y[0], y[1]); s_b[3] = fmaxf(y[2], y[3]);
+        } else {
+            s_b[0] = 0.f; s_b[1] = (float)W; s_b[2] = 0.f; s_b[3] = (float)H;
+        }
+        for (int k = 0; k < 4; ++k) bounds[k] = s_b[k];
+    }
+    __syncthreads();
+    const float inv_w = (float)FR_COLS / (s_b[1] - s_b[0]), inv_h = (float)FR_ROWS / (s_b[3] - s_b[2]);
+    for (int i = tid; i < n; i += nt) {
+        const sindyn_keypoint k = kps[i];
+        float ux = k.x, uy = k.y;
+        if (P.k1 != 0.0f) fr_undistort(k.x, k.y, P, ux, uy);
+        un[2 * i] = ux; un[2 * i + 1] = uy;
+        // imDepth.at<float>(v, u): float -> int truncation of the DISTORTED keypoint; depth = raw * (1 / DepthMapFactor)
+        const float d = (float)depth[(int)k.y * W + (int)k.x] * P.depth_map_factor;
+        dep[i] = d > 0.f ? d : -1.0f;
+        uright[i] = d > 0.f ? ux - P.bf / d : -1.0f;
+        // PosInGrid: C round() of float products
+        const int px = (int)round((double)((ux - s_b[0]) * inv_w)), py = (int)round((double)((uy - s_b[2]) * inv_h));
+        int cell = -1;
+        if (px >= 0 && px < FR_COLS && py >= 0 && py < FR_ROWS) { cell = px * FR_ROWS + py; atomicAdd(&s_cnt[cell], 1); }
+        s_cell[i] = (short)cell;
+    }
+    __syncthreads();
+    if (tid == 0) {   // exclusive scan over the 3072 cells (mGrid[i][j] order: column-major in i)
+        int acc = 0;
+        for (int c = 0; c < FR_COLS * FR_ROWS; ++c) { const int v = s_cnt[c]; offsets[c] = acc; s_cnt[c] = acc; acc += v; }
+        offsets[FR_COLS * FR_ROWS] = acc;
+    }
+    __syncthreads();
+    // stable fill: keypoint i goes after every j < i of the same cell (push_back order of AssignFeaturesToGrid)
+    for (int i = tid; i < n; i += nt) {
+        const int cell = s_cell[i];
+        if (cell < 0) continue;
+        int before = 0;
+        for (int j = 0; j < i; ++j) before += s_cell[j] == cell;
+        indices[s_cnt[cell] + before] = i;
+    }
+}
+
+extern "C" int sindyn_orb_frame_features(sindyn_orb_handle h, const uint16_t *depth_raw, size_t depth_step, const sindyn_frame_params *params,
+                                         float *keys_un, float *depth_out, float *u_right_out, float *bounds_out, int *grid_offsets,
+                                         int *grid_indices, int capacity, int *n_out)
+{
+    if (!h || !depth_raw || !params || !n_out) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const int n = h->ctl_host->n_out;   // result of the last sindyn_orb_extract
+    *n_out = n;
+    if (n > capacity) { h->err = "orb frame: output capacity too small"; return SINDYN_ERR_CAPACITY; }
+    CU_CHECK(h, stage_in_2d(h->depth, depth_raw, depth_step, (size_t)h->W * 2, h->H, h->pin_depth, h->stream));
+    LAUNCH(h, k_orb_frame, 1, 1024, 0, h->out_host_fmt, h->ctl, h->depth, h->W, h->H, *params, h->fr_un, h->fr_depth, h->fr_uright, h->fr_bounds,
+           h->fr_offsets, h->fr_indices);
+    LAUNCH_CHECK(h);
+    if (keys_un && n) CU_CHECK(h, cudaMemcpyAsync(keys_un, h->fr_un, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (depth_out && n) CU_CHECK(h, cudaMemcpyAsync(depth_out, h->fr_depth, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (u_right_out && n) CU_CHECK(h, cudaMemcpyAsync(u_right_out, h->fr_uright, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (bounds_out) CU_CHECK(h, cudaMemcpyAsync(bounds_out, h->fr_bounds, sizeof(float) * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (grid_offsets) CU_CHECK(h, cudaMemcpyAsync(grid_offsets, h->fr_offsets, sizeof(int) * (FR_COLS * FR_ROWS + 1), cudaMemcpyDeviceToHost, h->stream));
+    if (grid_indices && n) CU_CHECK(h, cudaMemcpyAsync(grid_indices, h->fr_indices, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
     return SINDYN_OK;
 }

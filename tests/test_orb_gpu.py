@@ -67,3 +67,28 @@ def test_orb_other_parameters_and_flat_image():
     k, d = orb.extract(flat, None)
     assert len(k) == 0 and d.shape == (0, 32)
     orb.close()
+
+
+@pytest.mark.parametrize("dist", [(0.0, 0.0, 0.0, 0.0, 0.0), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)])   # TUM3.yaml / TUM1.yaml
+def test_frame_features_after_orb(seq_c1, dist):
+    """Frame.cc:143-170 (undistortion, RGB-D stereo coordinates, 64 x 48 grid) on the device-resident
+    keypoints, bit-exact against the oracle (real cv2.undistortPoints)."""
+    from oracle import frame_oracle as fo
+    from sindslam_b200.capi import Orb
+    _, frames = seq_c1
+    cam = synth.TUM3
+    orb = Orb(1000, 1.2, 8, 20, 7, 640, 480)
+    gray = cv2.cvtColor(frames[1].bgr, cv2.COLOR_BGR2GRAY)
+    kps, _ = orb.extract(gray, None)
+    bf, dmf = 40.0, 1.0 / 5000.0
+    un, dep, ur, b, off, idx = orb.frame_features(frames[1].depth, cam.fx, cam.fy, cam.cx, cam.cy, dist, bf, dmf)
+    r = fo.frame_features(np.stack([kps["x"], kps["y"]], 1), frames[1].depth, 640, 480, cam.fx, cam.fy, cam.cx, cam.cy, dist, bf, dmf)
+    assert np.array_equal(b, r["bounds"])
+    assert np.array_equal(un, r["keys_un"])
+    assert np.array_equal(dep, r["depth"]) and np.array_equal(ur, r["u_right"])
+    for i in range(64):
+        for j in range(48):
+            c = i * 48 + j
+            assert list(idx[off[c]:off[c + 1]]) == r["grid"][i][j], (i, j)
+    assert (dep > 0).mean() > 0.9 and off[-1] >= len(kps) - 5
+    orb.close()
