@@ -9,8 +9,8 @@
 //   Ix Iy Ixz Iyz and Ixx Ixy Iyy; then per fixed-point iteration: normalised brightness + gradient constancy data terms
 //   (robust weights delta/2, gamma/2), smoothness weights alpha/2 / sqrt(|grad(W + dW)|^2 + eps^2) from FORWARD
 //   differences (one weight per pixel, shared by its right and lower edge), and red-black SOR sweeps on (dWu, dWv).
-// The red-black sweeps are global (one launch per colour): 110 592 pixels x 50 half-sweeps is ~0.2 ms, far below the
-// Brox solve it follows.
+// The 10 red-black half-sweeps of one fixed-point iteration run in one temporally blocked launch (k_vr_sor_fused);
+// k_vr_sor is the plain one-colour-per-launch sweep kept for reference.
 #include "varref.cuh"
 
 #define VR_FP 5
@@ -22,7 +22,7 @@
 #define VR_ZETA 0.1f
 #define VR_EPS 0.001f
 
-enum { P_A = 0, P_IZ, P_IX, P_IY, P_IXZ, P_IYZ, P_IXX, P_IXY, P_IYY, P_WU, P_WV, P_DU, P_DV, P_WGT, P_A11, P_A12, P_A22, P_B1, P_B2, P_COUNT };
+enum { P_A = 0, P_IZ, P_IX, P_IY, P_IXZ, P_IYZ, P_IXX, P_IXY, P_IYY, P_WU, P_WV, P_DU, P_DV, P_WGT, P_A11, P_A12, P_A22, P_B1, P_B2, P_DU2, P_DV2, P_COUNT };
 
 // cv::remap(I1 as float, x + u, y + v, INTER_LINEAR, BORDER_REPLICATE) + averaged image + temporal difference
 __global__ void k_vr_warp(const uint8_t *__restrict__ I0, const uint8_t *__restrict__ I1, const float2 *__restrict__ flow, int w, int h,
@@ -148,6 +148,71 @@ __global__ void k_vr_sor(float *const *__restrict__ P, int w, int h, int colour)
     dv[i] = v;
 }
 
+// All VR_SOR red-black sweeps of one fixed-point iteration in ONE launch (temporal blocking, like k_brox_inner): a CTA
+// stages its 32x24 tile plus a 2*VR_SOR-px halo of (du, dv) and the six per-pixel system planes in shared memory, sweeps
+// there with a shrinking valid region (bit-identical to global sweeps) and writes only its interior.
+constexpr int VRT_W = 32, VRT_H = 24, VRT_R = 2 * VR_SOR, VRT_PW = VRT_W + 2 * VRT_R, VRT_PH = VRT_H + 2 * VRT_R, VRT_PP = VRT_PW * VRT_PH;
+constexpr int VRT_NT = 512;
+constexpr size_t VRT_SMEM = sizeof(float) * 8 * VRT_PP;
+
+__global__ void __launch_bounds__(VRT_NT) k_vr_sor_fused(float *const *__restrict__ P, int w, int h)
+{
+    extern __shared__ float vsm[];
+    float *s_du = vsm, *s_dv = vsm + VRT_PP, *s_w = vsm + 2 * VRT_PP, *s_a11 = vsm + 3 * VRT_PP, *s_a12 = vsm + 4 * VRT_PP, *s_a22 = vsm + 5 * VRT_PP,
+          *s_b1 = vsm + 6 * VRT_PP, *s_b2 = vsm + 7 * VRT_PP;
+    const int gx0 = blockIdx.x * VRT_W, gy0 = blockIdx.y * VRT_H, ox = gx0 - VRT_R, oy = gy0 - VRT_R;
+    const int tid = threadIdx.x;
+    for (int r = tid; r < VRT_PP; r += VRT_NT) {
+        const int ly = r / VRT_PW, lx = r - ly * VRT_PW;
+        const int x = ox + lx, y = oy + ly;
+        if (x >= 0 && x < w && y >= 0 && y < h) {
+            const int g = y * w + x;
+            s_du[r] = P[P_DU][g]; s_dv[r] = P[P_DV][g]; s_w[r] = P[P_WGT][g];
+            s_a11[r] = P[P_A11][g]; s_a12[r] = P[P_A12][g]; s_a22[r] = P[P_A22][g]; s_b1[r] = P[P_B1][g]; s_b2[r] = P[P_B2][g];
+        } else {
+            s_du[r] = s_dv[r] = s_w[r] = s_a12[r] = s_b1[r] = s_b2[r] = 0.0f;
+            s_a11[r] = s_a22[r] = 1.0f;
+        }
+    }
+    __syncthreads();
+    for (int k = 1; k <= 2 * VR_SOR; ++k) {
+        // half-sweep k is valid inside radius VRT_R - k around the tile (clipped to the image)
+        const int rad = VRT_R - k;
+        const int xa = max(0, gx0 - rad), xb = min(w - 1, gx0 + VRT_W - 1 + rad), ya = max(0, gy0 - rad), yb = min(h - 1, gy0 + VRT_H - 1 + rad);
+        const int rw = xb - xa + 1, rh = yb - ya + 1, hc = (rw + 1) >> 1;
+        const int colour = (k - 1) & 1;
+        for (int i = tid; i < hc * rh; i += VRT_NT) {
+            const int yy = i / hc, y = ya + yy;
+            const int x = xa + 2 * (i - yy * hc) + ((xa + y + colour) & 1);
+            if (x > xb) continue;
+            const int s = (y - oy) * VRT_PW + (x - ox);
+            const float wc = s_w[s];
+            float sU = 0.f, sV = 0.f;
+            if (x > 0) { const float wl = s_w[s - 1]; sU += wl * s_du[s - 1]; sV += wl * s_dv[s - 1]; }
+            if (x < w - 1) { sU += wc * s_du[s + 1]; sV += wc * s_dv[s + 1]; }
+            if (y > 0) { const float wu = s_w[s - VRT_PW]; sU += wu * s_du[s - VRT_PW]; sV += wu * s_dv[s - VRT_PW]; }
+            if (y < h - 1) { sU += wc * s_du[s + VRT_PW]; sV += wc * s_dv[s + VRT_PW]; }
+            const float a12 = s_a12[s];
+            float u = s_du[s], v = s_dv[s];
+            u += VR_OMEGA * ((sU + s_b1[s] - v * a12) / s_a11[s] - u);
+            v += VR_OMEGA * ((sV + s_b2[s] - u * a12) / s_a22[s] - v);
+            s_du[s] = u;
+            s_dv[s] = v;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < VRT_W * VRT_H; i += VRT_NT) {
+        const int ly = i / VRT_W, lx = i - ly * VRT_W;
+        const int x = gx0 + lx, y = gy0 + ly;
+        if (x < w && y < h) {
+            const int s = (y - oy) * VRT_PW + (x - ox);
+            // results go to the second pair of increment planes: neighbouring CTAs still read the old ones as their halo
+            P[P_DU2][y * w + x] = s_du[s];
+            P[P_DV2][y * w + x] = s_dv[s];
+        }
+    }
+}
+
 __global__ void k_vr_final(float *const *__restrict__ P, int n, float2 *__restrict__ flow)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,11 +226,17 @@ int varref_init(sindyn_base *ctx, VarRefStage *v, int w, int h)
     const size_t n = (size_t)w * h;
     SD_CHECK(ctx->dalloc(&v->buf, n * P_COUNT));
     for (int k = 0; k < P_COUNT; ++k) v->planes[k] = v->buf + n * k;
+    // two plane tables: the fused SOR kernel reads (DU, DV) and writes (DU2, DV2), so the tables swap those pairs
     float **tab = nullptr;
-    SD_CHECK(ctx->dalloc(&tab, 32));
-    CU_CHECK(ctx, cudaMemcpyAsync(tab, v->planes, sizeof(float *) * 32, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CHECK(ctx->dalloc(&tab, 64));
+    float *host_tab[64] = {};
+    for (int k = 0; k < P_COUNT; ++k) host_tab[k] = host_tab[32 + k] = v->planes[k];
+    host_tab[32 + P_DU] = v->planes[P_DU2]; host_tab[32 + P_DV] = v->planes[P_DV2];
+    host_tab[32 + P_DU2] = v->planes[P_DU]; host_tab[32 + P_DV2] = v->planes[P_DV];
+    CU_CHECK(ctx, cudaMemcpyAsync(tab, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     v->planes_dev = tab;
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_vr_sor_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VRT_SMEM));
     v->built = true;
     return SINDYN_OK;
 }
@@ -173,20 +244,21 @@ int varref_init(sindyn_base *ctx, VarRefStage *v, int w, int h)
 int varref_run(sindyn_base *ctx, VarRefStage *v, const uint8_t *I0, const uint8_t *I1, float *flow)
 {
     const int w = v->w, h = v->h;
-    const dim3 blk(32, 8), grd(cdiv(w, 32), cdiv(h, 8)), grdh(cdiv((w + 1) / 2, 32), cdiv(h, 8));
+    const dim3 blk(32, 8), grd(cdiv(w, 32), cdiv(h, 8));
     float **p = v->planes;
     LAUNCH(ctx, k_vr_warp, grd, blk, 0, I0, I1, (const float2 *)flow, w, h, p[P_A], p[P_IZ], p[P_WU], p[P_WV], p[P_DU], p[P_DV]);
     LAUNCH(ctx, k_vr_deriv1, grd, blk, 0, p[P_A], p[P_IZ], w, h, p[P_IX], p[P_IY], p[P_IXZ], p[P_IYZ]);
     LAUNCH(ctx, k_vr_deriv2, grd, blk, 0, p[P_IX], p[P_IY], w, h, p[P_IXX], p[P_IXY], p[P_IYY]);
+    const dim3 grdf(cdiv(w, VRT_W), cdiv(h, VRT_H));
+    int cur = 0;
     for (int it = 0; it < VR_FP; ++it) {
-        LAUNCH(ctx, k_vr_weights, grd, blk, 0, p[P_WU], p[P_WV], p[P_DU], p[P_DV], w, h, p[P_WGT]);
-        LAUNCH(ctx, k_vr_system, grd, blk, 0, v->planes_dev, w, h);
-        for (int s = 0; s < VR_SOR; ++s) {
-            LAUNCH(ctx, k_vr_sor, grdh, blk, 0, v->planes_dev, w, h, 0);
-            LAUNCH(ctx, k_vr_sor, grdh, blk, 0, v->planes_dev, w, h, 1);
-        }
+        float *const *tab = v->planes_dev + 32 * cur;
+        LAUNCH(ctx, k_vr_weights, grd, blk, 0, p[P_WU], p[P_WV], p[cur ? P_DU2 : P_DU], p[cur ? P_DV2 : P_DV], w, h, p[P_WGT]);
+        LAUNCH(ctx, k_vr_system, grd, blk, 0, tab, w, h);
+        LAUNCH(ctx, k_vr_sor_fused, grdf, VRT_NT, VRT_SMEM, tab, w, h);
+        cur ^= 1;
     }
-    LAUNCH(ctx, k_vr_final, cdiv(w * h, 256), 256, 0, v->planes_dev, w * h, (float2 *)flow);
+    LAUNCH(ctx, k_vr_final, cdiv(w * h, 256), 256, 0, v->planes_dev + 32 * cur, w * h, (float2 *)flow);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }
