@@ -154,15 +154,37 @@ template <int TW_, int TH_> struct BroxTile {
     static constexpr int NPCP = NPC + 2 * G;
     // (du,dv) + edge weights | per-pixel 2x2 systems (5 floats; the staging planes ta / tb / ps alias their start) | u, v
     static constexpr size_t SMEM = sizeof(float2) * 4 * NPCP + sizeof(float) * 10 * NPC + sizeof(float) * 2 * PP;
+    static constexpr size_t SMEM_SOR = sizeof(float2) * 4 * NPCP + sizeof(float) * 10 * NPC;   // k_brox_sor: no u / v planes
     static_assert(3 * PP <= 10 * NPC, "ta / tb / ps must fit into the coefficient area they alias");
     static_assert((PW & 1) == 0, "de-interleaving needs an even region width");
     static_assert(NPC < 4096, "pixel index must fit into 12 bits");
 };
 typedef BroxTile<32, 24> BroxTileL;   // 74 x 66 region: also the single-tile mode of the coarse levels
 
+#ifdef SINDYN_BROX_PHASE_CLOCKS
+// developer instrumentation: clock64 deltas of the centre CTA of every tiled 32x24 launch, summed per phase
+__device__ unsigned long long g_brox_clk[16];
+#define BROX_CLK(slot)                                                                                        \
+    if (prof_on) { const long long t_ = clock64(); atomicAdd(&g_brox_clk[slot], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
+extern "C" int sindyn_dbg_brox_phase_clocks(unsigned long long *out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_brox_clk, sizeof(g_brox_clk));
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_brox_clk, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define BROX_CLK(slot)
+#endif
+
 template <class T>
 __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
 {
+#ifdef SINDYN_BROX_PHASE_CLOCKS
+    const bool prof_on = threadIdx.x == 0 && p.halo > 0 && T::TW == 32 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2;
+    long long t_prev = clock64();
+    if (prof_on) atomicAdd(&g_brox_clk[15], 1ull);
+#endif
     constexpr int BROX_PW = T::PW, BROX_PH = T::PH, BROX_HW = T::HW, BROX_NPC = T::NPC, BROX_M = T::M, BROX_PP = T::PP, BROX_G = T::G,
                   BROX_NPCP = T::NPCP;
     extern __shared__ float4 sm4[];
@@ -230,6 +252,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
         }
     }
     __syncthreads();
+    BROX_CLK(0)
     for (int it = 0; it < p.n_inner; ++it) {
         // ---- phase 0: stage (du,dv), the level's flow (u,v) and the total flow u + du_base (radius = whole region).
         // Four region pixels per thread and pass: the global loads of all four are issued before the first use (the
@@ -281,6 +304,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
             }
         }
         __syncthreads();
+        BROX_CLK(1)
         // ---- phase 1: smoothness diffusivity psi'_s from the gradient of the total flow
         for (int r = tid; r < pp_used; r += BROX_NT) {
             const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
@@ -296,6 +320,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
             s_ps[r] = ps;
         }
         __syncthreads();
+        BROX_CLK(2)
         // ---- phase 2a: edge weights (right, down) of every pixel; zero across the image border (Neumann)
         for (int r = tid; r < pp_used; r += BROX_NT) {
             const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
@@ -311,6 +336,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
             s_wd[wi] = wd;
         }
         __syncthreads();
+        BROX_CLK(3)
         // ---- phase 2b: data term and the 2x2 system of the owned pixels -> registers
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -349,6 +375,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 s_c4[c * BROX_NPC + idx] = make_float4(j12, su - j13, sv - j23, 1.0f / (j11 + sw_));
                 s_c1[c * BROX_NPC + idx] = 1.0f / (j22 + sw_);
             }
+        BROX_CLK(4)
         // (no barrier needed: the sweeps below read s_uv / s_wr / s_wd, which are complete, and the thread's own systems)
         // ---- red-black SOR: half-sweep k updates colour (k-1)&1 where the halo distance allows it
         const unsigned thr0 = (unsigned)(p.halo > ns2 ? p.halo - ns2 : 0);
@@ -388,6 +415,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
             BROX_HALF(1, 2 * sw + 2)
         }
 #undef BROX_HALF
+        BROX_CLK(5)
     }
     // ---- write the interior from registers
 #pragma unroll
@@ -398,6 +426,244 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
             if (!((k >> 13) & 1u)) continue;
             const int idx = k & 0xfff, par = (k >> 12) & 1;
             const int ly = idx / BROX_HW, lx = 2 * (idx - ly * BROX_HW) + par;
+            const int g = (oy + ly) * w + ox + lx;
+            p.duo[g] = rdu[c][m];
+            p.dvo[g] = rdv[c][m];
+        }
+    BROX_CLK(6)
+}
+
+// ------------------------------------------------------------------ tiled levels: system kernel + SOR kernel
+// For levels larger than one tile the lagged-nonlinearity coefficients are computed ONCE per pixel by k_brox_system
+// (no halo redundancy: in k_brox_inner's tiled mode phases 0-2 ran on the whole tile + 21-px halo region, 6.4x the
+// pixels of the tile, and took 44 % of the launch) and the temporally blocked sweeps (k_brox_sor) only stage them.
+struct BroxSysP {
+    const float *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz, *u, *v, *dub, *dvb;
+    float2 *W;
+    float4 *C4;
+    float *C1;
+    int w, h;
+    float alpha, gamma;
+};
+constexpr int BSY_W = 32, BSY_H = 8;
+
+__global__ void __launch_bounds__(BSY_W *BSY_H) k_brox_system(BroxSysP p)
+{
+    __shared__ float s_ta[BSY_H + 4][BSY_W + 4], s_tb[BSY_H + 4][BSY_W + 4], s_u[BSY_H + 4][BSY_W + 4], s_v[BSY_H + 4][BSY_W + 4];
+    __shared__ float s_ps[BSY_H + 2][BSY_W + 2];
+    const int w = p.w, h = p.h;
+    const int gx0 = blockIdx.x * BSY_W, gy0 = blockIdx.y * BSY_H;
+    const int tid = threadIdx.y * BSY_W + threadIdx.x;
+    for (int i = tid; i < (BSY_H + 4) * (BSY_W + 4); i += BSY_W * BSY_H) {
+        const int ly = i / (BSY_W + 4), lx = i - ly * (BSY_W + 4);
+        const int x = gx0 - 2 + lx, y = gy0 - 2 + ly;
+        float uu = 0.0f, vv = 0.0f, bu = 0.0f, bv = 0.0f;
+        if (x >= 0 && x < w && y >= 0 && y < h) {
+            const int g = y * w + x;
+            uu = p.u[g]; vv = p.v[g]; bu = p.dub[g]; bv = p.dvb[g];
+        }
+        s_u[ly][lx] = uu; s_v[ly][lx] = vv;
+        s_ta[ly][lx] = uu + bu; s_tb[ly][lx] = vv + bv;
+    }
+    __syncthreads();
+    // smoothness diffusivity psi'_s on the tile + 1 ring (central differences, replicated at the image border)
+    for (int i = tid; i < (BSY_H + 2) * (BSY_W + 2); i += BSY_W * BSY_H) {
+        const int ly = i / (BSY_W + 2), lx = i - ly * (BSY_W + 2);
+        const int x = gx0 - 1 + lx, y = gy0 - 1 + ly;
+        float ps = 0.0f;
+        if (x >= 0 && x < w && y >= 0 && y < h) {
+            const int cy = ly + 1, cx = lx + 1;
+            const int xm = x > 0 ? cx - 1 : cx, xp = x < w - 1 ? cx + 1 : cx, ym = y > 0 ? cy - 1 : cy, yp = y < h - 1 ? cy + 1 : cy;
+            const float ux = 0.5f * (s_ta[cy][xp] - s_ta[cy][xm]), uy = 0.5f * (s_ta[yp][cx] - s_ta[ym][cx]);
+            const float vx = 0.5f * (s_tb[cy][xp] - s_tb[cy][xm]), vy = 0.5f * (s_tb[yp][cx] - s_tb[ym][cx]);
+            ps = 0.5f / sqrtf(ux * ux + uy * uy + vx * vx + vy * vy + BROX_EPS2);
+        }
+        s_ps[ly][lx] = ps;
+    }
+    __syncthreads();
+    const int x = gx0 + threadIdx.x, y = gy0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int g = y * w + x;
+    const int py = threadIdx.y + 1, px = threadIdx.x + 1;   // s_ps coordinates
+    const float ps = s_ps[py][px];
+    // edge weights; zero across the image border (Neumann).  wl / wu are the right / lower weights of the left / upper pixel
+    const float wr = x < w - 1 ? p.alpha * 0.5f * (ps + s_ps[py][px + 1]) : 0.0f;
+    const float wd = y < h - 1 ? p.alpha * 0.5f * (ps + s_ps[py + 1][px]) : 0.0f;
+    const float wl = x > 0 ? p.alpha * 0.5f * (s_ps[py][px - 1] + ps) : 0.0f;
+    const float wu = y > 0 ? p.alpha * 0.5f * (s_ps[py - 1][px] + ps) : 0.0f;
+    const float gamma = p.gamma;
+    const float dub = p.dub[g], dvb = p.dvb[g];
+    const float ix = p.Ix[g], iy = p.Iy[g], iz = p.Iz[g], ixx = p.Ixx[g], ixy = p.Ixy[g], iyy = p.Iyy[g], ixz = p.Ixz[g], iyz = p.Iyz[g];
+    const float q0 = iz + ix * dub + iy * dvb;
+    const float q1 = ixz + ixx * dub + ixy * dvb;
+    const float q2 = iyz + ixy * dub + iyy * dvb;
+    const float psid = 0.5f / sqrtf(q0 * q0 + gamma * (q1 * q1 + q2 * q2) + BROX_EPS2);
+    const float j11 = psid * (ix * ix + gamma * (ixx * ixx + ixy * ixy));
+    const float j12 = psid * (ix * iy + gamma * (ixx * ixy + ixy * iyy));
+    const float j22 = psid * (iy * iy + gamma * (ixy * ixy + iyy * iyy));
+    const float j13 = psid * (ix * iz + gamma * (ixx * ixz + ixy * iyz));
+    const float j23 = psid * (iy * iz + gamma * (ixy * ixz + iyy * iyz));
+    const int cy = threadIdx.y + 2, cx = threadIdx.x + 2;   // s_u coordinates
+    const float uc = s_u[cy][cx], vc = s_v[cy][cx];
+    float su = 0.0f, sv = 0.0f;
+    if (x > 0) { su += wl * (s_u[cy][cx - 1] - uc); sv += wl * (s_v[cy][cx - 1] - vc); }
+    if (x < w - 1) { su += wr * (s_u[cy][cx + 1] - uc); sv += wr * (s_v[cy][cx + 1] - vc); }
+    if (y > 0) { su += wu * (s_u[cy - 1][cx] - uc); sv += wu * (s_v[cy - 1][cx] - vc); }
+    if (y < h - 1) { su += wd * (s_u[cy + 1][cx] - uc); sv += wd * (s_v[cy + 1][cx] - vc); }
+    const float sw_ = wl + wr + wu + wd;
+    p.W[g] = make_float2(wr, wd);
+    p.C4[g] = make_float4(j12, su - j13, sv - j23, 1.0f / (j11 + sw_));
+    p.C1[g] = 1.0f / (j22 + sw_);
+}
+
+struct BroxSorP {
+    const float2 *W;
+    const float4 *C4;
+    const float *C1;
+    const float *dui, *dvi;   // increment at the start of this launch's sweeps
+    float *duo, *dvo;
+    int w, h;
+    float omega;
+    int nsweeps;
+};
+
+// nsweeps (<= 10) red-black SOR sweeps on one tile + 21-px halo (temporal blocking): same data layout and sweep loop as
+// k_brox_inner, the systems come from k_brox_system.
+template <class T>
+__global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
+{
+    constexpr int PW = T::PW, PH = T::PH, HW = T::HW, NPC = T::NPC, M = T::M, PP = T::PP, G = T::G, NPCP = T::NPCP;
+    extern __shared__ float4 sm4[];
+    float2 *s_uv = (float2 *)sm4 + G;                               // [2][NPCP] (du, dv) by colour, zero guards
+    float *s_wr = (float *)((float2 *)sm4 + 2 * NPCP) + G;          // [2][NPCP]
+    float *s_wd = s_wr + 2 * NPCP;                                  // [2][NPCP]
+    float4 *s_c4 = (float4 *)((float2 *)sm4 + 4 * NPCP);            // [2][NPC]  private to the owning thread
+    float *s_c1 = (float *)(s_c4 + 2 * NPC);                        // [2][NPC]
+    const int w = p.w, h = p.h;
+    const int gx0 = blockIdx.x * T::TW, gy0 = blockIdx.y * T::TH;
+    const int ox = gx0 - BROX_RMAX, oy = gy0 - BROX_RMAX;           // ox + oy is even: local colour == global colour
+    const int tid = threadIdx.x;
+    const int ns2 = 2 * p.nsweeps;
+    const float omega = p.omega, om1 = 1.0f - p.omega;
+    const unsigned thr0 = (unsigned)(BROX_RMAX - ns2);
+
+    // guards
+    for (int r = tid; r < 12 * G; r += BROX_NT) {
+        const int a = r / (2 * G), o = r - a * 2 * G;
+        const int off = o < G ? o - G : NPC + (o - G);
+        if (a < 2) s_uv[a * NPCP + off] = make_float2(0.0f, 0.0f);
+        else s_wr[(a - 2) * NPCP + off] = 0.0f;
+    }
+    // ---- stage (du, dv) and the edge weights of the whole region, two pixels per thread and pass
+    for (int r0 = tid; r0 < PP; r0 += 2 * BROX_NT) {
+        int ci[2];
+        float2 wv[2];
+        float du[2], dv[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int r = r0 + k * BROX_NT;
+            wv[k] = make_float2(0.0f, 0.0f); du[k] = dv[k] = 0.0f; ci[k] = -1;
+            if (r < PP) {
+                const int ly = r / PW, lx = r - ly * PW;
+                const int x = ox + lx, y = oy + ly;
+                ci[k] = ((lx + ly) & 1) * NPCP + ly * HW + (lx >> 1);
+                if (x >= 0 && x < w && y >= 0 && y < h) {
+                    const int g = y * w + x;
+                    wv[k] = p.W[g]; du[k] = p.dui[g]; dv[k] = p.dvi[g];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (ci[k] >= 0) {
+                s_uv[ci[k]] = make_float2(du[k], dv[k]);
+                s_wr[ci[k]] = wv[k].x;
+                s_wd[ci[k]] = wv[k].y;
+            }
+    }
+    // ---- owned pixels: table, systems (global -> the thread's private shared-memory slots)
+    unsigned pk[2][M];
+    float rdu[2][M], rdv[2][M];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const int q = tid + BROX_NT * m;
+            unsigned v = 0;
+            if (q < NPC) {
+                const int ly = q / HW, i = q - ly * HW;
+                const int par = (ly + c) & 1, lx = 2 * i + par;
+                const int x = ox + lx, y = oy + ly;
+                const bool inside = x >= 0 && x < w && y >= 0 && y < h;
+                int dist = 255;
+                if (ox > 0) dist = min(dist, lx);
+                if (oy > 0) dist = min(dist, ly);
+                if (ox + PW < w) dist = min(dist, PW - 1 - lx);
+                if (oy + PH < h) dist = min(dist, PH - 1 - ly);
+                const bool interior = inside && x >= gx0 && x < gx0 + T::TW && y >= gy0 && y < gy0 + T::TH;
+                const bool live = inside && dist >= (int)thr0 + 1;   // updated by at least the first half-sweep
+                v = (unsigned)q | ((unsigned)par << 12) | ((unsigned)interior << 13) | ((unsigned)live << 14) | ((unsigned)dist << 16);
+                if (live) {
+                    const int g = y * w + x;
+                    s_c4[c * NPC + q] = p.C4[g];
+                    s_c1[c * NPC + q] = p.C1[g];
+                }
+            }
+            pk[c][m] = v;
+        }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const unsigned k = pk[c][m];
+            float2 own = make_float2(0.0f, 0.0f);
+            if ((k >> 14) & 1u) own = s_uv[c * NPCP + (k & 0xfff)];
+            rdu[c][m] = own.x;
+            rdv[c][m] = own.y;
+        }
+#define BROX_HALF(C, K)                                                                                           \
+    {                                                                                                             \
+        const float2 *__restrict__ uo = s_uv + ((C) ^ 1) * NPCP;                                                   \
+        float2 *__restrict__ uc_ = s_uv + (C) * NPCP;                                                              \
+        const float *__restrict__ wro = s_wr + ((C) ^ 1) * NPCP;                                                   \
+        const float *__restrict__ wdo = s_wd + ((C) ^ 1) * NPCP;                                                   \
+        const float *__restrict__ wrc = s_wr + (C) * NPCP;                                                         \
+        const float *__restrict__ wdc = s_wd + (C) * NPCP;                                                         \
+        _Pragma("unroll") for (int m = 0; m < M; ++m)                                                             \
+        {                                                                                                         \
+            const unsigned k_ = pk[C][m];                                                                         \
+            if (((k_ >> 14) & 1u) && (k_ >> 16) >= thr0 + (unsigned)(K)) {                                        \
+                const int idx = k_ & 0xfff, par = (k_ >> 12) & 1;                                                 \
+                const float2 l = uo[idx - 1 + par], r = uo[idx + par], u_ = uo[idx - HW], d = uo[idx + HW];       \
+                const float wr_ = wrc[idx], wd_ = wdc[idx];                                                       \
+                const float wl = wro[idx - 1 + par], wu = wdo[idx - HW];                                          \
+                const float su = wl * l.x + wr_ * r.x + wu * u_.x + wd_ * d.x;                                    \
+                const float sv = wl * l.y + wr_ * r.y + wu * u_.y + wd_ * d.y;                                    \
+                const float4 cf = s_c4[(C) * NPC + idx];                                                          \
+                const float cd2_ = s_c1[(C) * NPC + idx];                                                         \
+                const float du_new = om1 * rdu[C][m] + omega * (cf.y - cf.x * rdv[C][m] + su) * cf.w;             \
+                const float dv_new = om1 * rdv[C][m] + omega * (cf.z - cf.x * du_new + sv) * cd2_;                \
+                rdu[C][m] = du_new;                                                                               \
+                rdv[C][m] = dv_new;                                                                               \
+                uc_[idx] = make_float2(du_new, dv_new);                                                           \
+            }                                                                                                     \
+        }                                                                                                         \
+        __syncthreads();                                                                                          \
+    }
+    for (int sw = 0; sw < p.nsweeps; ++sw) {
+        BROX_HALF(0, 2 * sw + 1)
+        BROX_HALF(1, 2 * sw + 2)
+    }
+#undef BROX_HALF
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const unsigned k = pk[c][m];
+            if (!((k >> 13) & 1u)) continue;
+            const int idx = k & 0xfff, par = (k >> 12) & 1;
+            const int ly = idx / HW, lx = 2 * (idx - ly * HW) + par;
             const int g = (oy + ly) * w + ox + lx;
             p.duo[g] = rdu[c][m];
             p.dvo[g] = rdv[c][m];
@@ -469,18 +735,21 @@ int brox_init(sindyn_base *ctx, BroxSolver *b, int w, int h, float alpha, float 
     float **planes[] = {&b->A, &b->Iz, &b->Ix, &b->Iy, &b->Ixz, &b->Iyz, &b->Ixx, &b->Ixy, &b->Iyy,
                         &b->u[0], &b->u[1], &b->v[0], &b->v[1], &b->du[0], &b->du[1], &b->du[2], &b->dv[0], &b->dv[1], &b->dv[2]};
     for (float **pp : planes) SD_CHECK(ctx->dalloc(pp, n));
-    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner<BroxTile<8, 8>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<8, 8>::SMEM));
-    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner<BroxTile<16, 12>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<16, 12>::SMEM));
-    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner<BroxTile<24, 16>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<24, 16>::SMEM));
+    SD_CHECK(ctx->dalloc(&b->sysW, n));
+    SD_CHECK(ctx->dalloc(&b->sysC4, n));
+    SD_CHECK(ctx->dalloc(&b->sysC1, n));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTile<8, 8>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<8, 8>::SMEM_SOR));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTile<16, 12>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<16, 12>::SMEM_SOR));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTile<24, 16>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<24, 16>::SMEM_SOR));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTileL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTileL::SMEM_SOR));
     CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner<BroxTileL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTileL::SMEM));
     return SINDYN_OK;
 }
 
 template <class T> static bool brox_tile_fits(int w, int h) { return cdiv(w, T::TW) * cdiv(h, T::TH) <= SINDYN_NUM_SMS_B200; }
-template <class T> static void brox_launch_tiled(sindyn_base *ctx, BroxInnerP &p)
+template <class T> static void brox_launch_sor(sindyn_base *ctx, BroxSorP &p)
 {
-    p.tw = T::TW; p.th = T::TH; p.halo = BROX_RMAX; p.n_inner = 1;
-    LAUNCH(ctx, k_brox_inner<T>, dim3(cdiv(p.w, T::TW), cdiv(p.h, T::TH)), BROX_NT, T::SMEM, p);
+    LAUNCH(ctx, k_brox_sor<T>, dim3(cdiv(p.w, T::TW), cdiv(p.h, T::TH)), BROX_NT, T::SMEM_SOR, p);
 }
 
 static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const float *I1, float *flow_out, float sign)
@@ -528,28 +797,36 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
             base = out;
         } else {
             const int tile = brox_tile_fits<BroxTile<8, 8>>(w, h) ? 0 : brox_tile_fits<BroxTile<16, 12>>(w, h) ? 1 : brox_tile_fits<BroxTile<24, 16>>(w, h) ? 2 : 3;
+            BroxSysP sp;
+            sp.Ix = b->Ix; sp.Iy = b->Iy; sp.Iz = b->Iz; sp.Ixx = b->Ixx; sp.Ixy = b->Ixy; sp.Iyy = b->Iyy; sp.Ixz = b->Ixz; sp.Iyz = b->Iyz;
+            sp.u = b->u[cur]; sp.v = b->v[cur]; sp.W = b->sysW; sp.C4 = b->sysC4; sp.C1 = b->sysC1;
+            sp.w = w; sp.h = h; sp.alpha = b->alpha; sp.gamma = b->gamma;
+            BroxSorP q;
+            q.W = b->sysW; q.C4 = b->sysC4; q.C1 = b->sysC1; q.w = w; q.h = h; q.omega = b->omega;
             for (int it = 0; it < b->inner; ++it) {
                 int in = base, remaining = b->solver;
+                sp.dub = b->du[base]; sp.dvb = b->dv[base];
+                const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
+                if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
+                LAUNCH(ctx, k_brox_system, dim3(cdiv(w, BSY_W), cdiv(h, BSY_H)), dim3(BSY_W, BSY_H), 0, sp);
                 while (remaining > 0) {
                     int ns = remaining < BROX_SMAX ? remaining : BROX_SMAX;
                     int out = 0;
                     while (out == base || out == in) ++out;
-                    p.dub = b->du[base]; p.dvb = b->dv[base];
-                    p.dui = b->du[in]; p.dvi = b->dv[in];
-                    p.duo = b->du[out]; p.dvo = b->dv[out];
-                    p.nsweeps = ns;
-                    const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
-                    if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
+                    q.dui = b->du[in]; q.dvi = b->dv[in];
+                    q.duo = b->du[out]; q.dvo = b->dv[out];
+                    q.nsweeps = ns;
                     switch (tile) {
-                    case 0: brox_launch_tiled<BroxTile<8, 8>>(ctx, p); break;
-                    case 1: brox_launch_tiled<BroxTile<16, 12>>(ctx, p); break;
-                    case 2: brox_launch_tiled<BroxTile<24, 16>>(ctx, p); break;
-                    default: brox_launch_tiled<BroxTileL>(ctx, p); break;
+                    case 0: brox_launch_sor<BroxTile<8, 8>>(ctx, q); break;
+                    case 1: brox_launch_sor<BroxTile<16, 12>>(ctx, q); break;
+                    case 2: brox_launch_sor<BroxTile<24, 16>>(ctx, q); break;
+                    default: brox_launch_sor<BroxTileL>(ctx, q); break;
                     }
-                    if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h; }
                     in = out;
                     remaining -= ns;
                 }
+                // one profile interval = one inner iteration (system + sweeps)
+                if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h; }
                 base = in;
             }
         }
