@@ -21,7 +21,7 @@ LIB = os.path.join(HERE, "libsindyn_cuda.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-ccbin", "/usr/bin/g++"]
-# developer builds only (e.g. SINDYN_NVCC_EXTRA=-DSINDYN_BROX_PHASE_CLOCKS for the phase-clock instrumentation of k_brox_inner)
+# developer builds only (e.g. SINDYN_NVCC_EXTRA=-DSINDYN_BROX_PHASE_CLOCKS for the phase-clock instrumentation of k_brox_sor)
 COMMON += os.environ.get("SINDYN_NVCC_EXTRA", "").split()
 # Bit-exact integer/label stages are compiled without FMA contraction so that float/double
 # expressions evaluate like the reference's plain IEEE arithmetic; the flow solvers (tolerance

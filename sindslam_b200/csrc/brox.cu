@@ -6,9 +6,10 @@
 //
 // B200 design: the problem (110 592 px at level 0, 15 levels) is latency- not bandwidth-bound, so the
 // solver_iterations red-black SOR sweeps of one lagged-nonlinearity iteration run INSIDE ONE launch (temporal
-// blocking in shared memory, see k_brox_inner); levels pick the smallest tile that still fits one wave of 148 SMs,
-// the coarsest levels run all inner iterations in a single launch, and the whole pyramid (about 200 launches) is
-// captured in one CUDA graph.
+// blocking in shared memory, k_brox_sor) after one k_brox_system launch that prepares the per-pixel systems without halo
+// redundancy; levels pick the smallest tile that still fits one wave of 148 SMs, the six coarsest levels (<= 2100 px) run
+// all inner iterations in a single one-CTA launch (k_brox_level), and the whole pyramid (about 270 launches) is captured
+// in one CUDA graph.
 #include "brox.cuh"
 
 #include <math.h>
@@ -118,24 +119,40 @@ __global__ void k_brox_deriv2(const float *__restrict__ Ix, const float *__restr
     Iyy[i] = d5y(Iy, w, h, x, y);
 }
 
-// ------------------------------------------------------------------ the solver kernel
-// One launch = (n_inner) lagged-nonlinearity iterations x (nsweeps) red-black SOR sweeps on one tile:
-//   * the tile plus a `halo`-pixel ring lives in shared memory; results of the fused sweeps are exact because a pixel at
-//     distance d from a halo edge stays valid for d half-sweeps (temporal blocking) and only the interior is written;
-//   * red and black pixels are stored DE-INTERLEAVED (two arrays of 37-wide rows), so the stride-2 access pattern of a
-//     red-black sweep becomes stride-1 and bank-conflict free; (du,dv) and the two edge weights are float2 -> LDS.64;
+// ------------------------------------------------------------------ the solver kernels
+// Shared design of the sweep kernels (k_brox_level: small levels, one CTA, all inner iterations in one launch;
+// k_brox_sor: tiles of larger levels, one inner iteration per launch, systems precomputed by k_brox_system):
+//   * red and black pixels are stored DE-INTERLEAVED (two arrays of half-width rows), so the stride-2 access pattern of a
+//     red-black sweep becomes stride-1 and bank-conflict free; (du,dv) is a float2 -> LDS.64, the two edge weights are two
+//     float arrays; zero guards around every colour array replace bounds logic in the sweep;
 //   * every thread owns a FIXED set of <= 3 red + 3 black pixels for the whole launch: their current (du,dv) stay in
-//     registers, the 2x2 system of a pixel (j12, b1, b2, 1/d1, 1/d2) in shared memory (1024 threads, 64 registers each);
-//   * levels that fit into one tile (<= 74 x 66, the 7 coarsest of 15) run all inner iterations in ONE launch (halo 0).
+//     registers, the 2x2 system of a pixel (j12, b1, b2, 1/d1 | 1/d2) in the thread's private shared-memory slots
+//     (1024 threads, 64 registers each);
+//   * tiles: the tile plus a 21-pixel ring lives in shared memory; the 10 fused sweeps are exact because a pixel at
+//     distance d from a halo edge stays valid for d half-sweeps (temporal blocking) and only the interior is written.
+#ifdef SINDYN_BROX_PHASE_CLOCKS
+// developer instrumentation: clock64 deltas of the centre CTA of every 32x24-tile k_brox_sor launch, summed per phase
+__device__ unsigned long long g_brox_clk[16];
+#define BROX_CLK(slot)                                                                                        \
+    if (prof_on) { const long long t_ = clock64(); atomicAdd(&g_brox_clk[slot], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
+extern "C" int sindyn_dbg_brox_phase_clocks(unsigned long long *out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_brox_clk, sizeof(g_brox_clk));
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_brox_clk, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define BROX_CLK(slot)
+#endif
+
 struct BroxInnerP {
     const float *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz, *u, *v;
-    const float *dub, *dvb;  // increment at the start of this lagged-nonlinearity iteration (coefficients)
-    const float *dui, *dvi;  // increment at the start of this launch's sweeps
+    const float *dub, *dvb;  // increment at the start of the launch
     float *duo, *dvo;
     int w, h;
     float alpha, gamma, omega;
-    int nsweeps;
-    int tw, th, halo, n_inner;
+    int nsweeps, n_inner;
 };
 
 constexpr int BROX_SMAX = 10, BROX_NT = 1024;
@@ -161,158 +178,83 @@ template <int TW_, int TH_> struct BroxTile {
 };
 typedef BroxTile<32, 24> BroxTileL;   // 74 x 66 region: also the single-tile mode of the coarse levels
 
-#ifdef SINDYN_BROX_PHASE_CLOCKS
-// developer instrumentation: clock64 deltas of the centre CTA of every tiled 32x24 launch, summed per phase
-__device__ unsigned long long g_brox_clk[16];
-#define BROX_CLK(slot)                                                                                        \
-    if (prof_on) { const long long t_ = clock64(); atomicAdd(&g_brox_clk[slot], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
-extern "C" int sindyn_dbg_brox_phase_clocks(unsigned long long *out, int reset)
-{
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, g_brox_clk, sizeof(g_brox_clk));
-    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_brox_clk, z, sizeof(z)); }
-    return 0;
-}
-#else
-#define BROX_CLK(slot)
-#endif
 
-template <class T>
-__global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
+// Whole level in ONE CTA (levels of up to 1024 * M pixels per colour): all n_inner lagged-nonlinearity iterations x nsweeps
+// red-black sweeps in one launch, no halo.  The geometry is a run-time parameter (region = the level itself, width rounded
+// up to even plus a dead column) so that the owned pixels are packed into the first warps with full lanes; the block is sized to the level.
+template <int M>
+__global__ void __launch_bounds__(BROX_NT, 1) k_brox_level(BroxInnerP p)
 {
-#ifdef SINDYN_BROX_PHASE_CLOCKS
-    const bool prof_on = threadIdx.x == 0 && p.halo > 0 && T::TW == 32 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2;
-    long long t_prev = clock64();
-    if (prof_on) atomicAdd(&g_brox_clk[15], 1ull);
-#endif
-    constexpr int BROX_PW = T::PW, BROX_PH = T::PH, BROX_HW = T::HW, BROX_NPC = T::NPC, BROX_M = T::M, BROX_PP = T::PP, BROX_G = T::G,
-                  BROX_NPCP = T::NPCP;
-    extern __shared__ float4 sm4[];
-    // colour arrays are padded by BROX_G zero elements on both sides: neighbour reads that fall off a row / the region
-    // land on a zero weight (never on a NaN) instead of needing per-pixel bounds logic in the sweep
-    float2 *s_uv = (float2 *)sm4 + BROX_G;      // [2][NPCP]  (du, dv) by colour
-    // edge weights as two separate float arrays (32-bit loads of one component of a float2 array are 2-way bank conflicted)
-    float *s_wr = (float *)((float2 *)sm4 + 2 * BROX_NPCP) + BROX_G;   // [2][NPCP] weight to the right neighbour
-    float *s_wd = s_wr + 2 * BROX_NPCP;                                 // [2][NPCP] weight to the lower neighbour
-    // per-pixel 2x2 systems (j12, b1, b2, 1/d1 | 1/d2) by colour: with 1024 threads (64 registers each) they live in shared
-    // memory; they are written after ta / tb / ps are dead, so those staging planes alias the same bytes
-    float4 *s_c4 = (float4 *)((float2 *)sm4 + 4 * BROX_NPCP);   // [2][NPC]
-    float *s_c1 = (float *)(s_c4 + 2 * BROX_NPC);                // [2][NPC]
-    float *s_ta = (float *)s_c4;                // [PP] u + du_base
-    float *s_tb = s_ta + BROX_PP;               // [PP] v + dv_base
-    float *s_ps = s_tb + BROX_PP;               // [PP] smoothness diffusivity
-    float *s_u = (float *)s_c4 + 10 * BROX_NPC; // [PP] flow of this level (u, v): neighbours for the right-hand side
-    float *s_v = s_u + BROX_PP;
     const int w = p.w, h = p.h;
-    const int gx0 = blockIdx.x * p.tw, gy0 = blockIdx.y * p.th;
-    const int ox = gx0 - p.halo, oy = gy0 - p.halo;   // ox + oy is even in both modes: local colour == global colour
+    // at least one dead column ends every row: with rows packed back to back the element before a row's first pixel is the
+    // previous row's last one, and the sweeps rely on its weights being zero
+    const int PW = (w + 2) & ~1, HW = PW >> 1, PH = h, NPC = PH * HW, PP = PW * PH, G = HW + 1, NPCP = NPC + 2 * G;
+    const int NT = blockDim.x;
+    extern __shared__ float4 sm4[];
+    float2 *s_uv = (float2 *)sm4 + G;                                  // [2][NPCP] (du, dv) by colour, zero guards
+    float *s_wr = (float *)((float2 *)sm4 + 2 * NPCP) + G;             // [2][NPCP] weight to the right neighbour
+    float *s_wd = s_wr + 2 * NPCP;                                     // [2][NPCP] weight to the lower neighbour
+    float4 *s_c4 = (float4 *)((float2 *)sm4 + 4 * NPCP);               // [2][NPC]  (j12, b1, b2, 1/d1), private to the owner
+    float *s_c1 = (float *)(s_c4 + 2 * NPC);                           // [2][NPC]  1/d2
+    float *s_ta = (float *)s_c4, *s_tb = s_ta + PP, *s_ps = s_tb + PP; // staging planes alias the systems (3 PP <= 10 NPC)
+    float *s_u = (float *)s_c4 + 10 * NPC, *s_v = s_u + PP;            // [PP] flow of this level
     const int tid = threadIdx.x;
-    const int ns2 = 2 * p.nsweeps;
     const float alpha = p.alpha, gamma = p.gamma, omega = p.omega, om1 = 1.0f - p.omega;
-    const bool same_base = p.dui == p.dub && p.dvi == p.dvb;   // one SOR chunk per inner iteration: the usual case
-    // rows of the staged region that can hold image pixels (coarse levels use a fraction of the region)
-    const int row_hi = min(BROX_PH, h - oy);
-    const int pp_used = p.halo == 0 ? (row_hi > 0 ? row_hi : 0) * BROX_PW : BROX_PP;
+    const float inv_pw = 1.0f / (float)PW, inv_hw = 1.0f / (float)HW;   // exact row index for the index ranges used here
 
-    // ---- per-thread pixel table: pk = idx (12 bits) | parity << 12 | interior << 13 | live << 14 | dist << 16
-    unsigned pk[2][BROX_M];
-    float rdu[2][BROX_M], rdv[2][BROX_M];
+    // ---- per-thread pixel table: pk = idx | parity << 12 | live << 14
+    unsigned pk[2][M];
+    float rdu[2][M], rdv[2][M];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int m = 0; m < BROX_M; ++m) {
-            const int q = tid + BROX_NT * m;
+        for (int m = 0; m < M; ++m) {
+            const int q = tid + NT * m;
             unsigned v = 0;
-            if (q < BROX_NPC) {
-                const int ly = q / BROX_HW, i = q - ly * BROX_HW;
+            if (q < NPC) {
+                const int ly = (int)(((float)q + 0.5f) * inv_hw), i = q - ly * HW;
                 const int par = (ly + c) & 1, lx = 2 * i + par;
-                const int x = ox + lx, y = oy + ly;
-                const bool inside = x >= 0 && x < w && y >= 0 && y < h;
-                int dist = 255;
-                if (ox > 0) dist = min(dist, lx);
-                if (oy > 0) dist = min(dist, ly);
-                if (ox + BROX_PW < w) dist = min(dist, BROX_PW - 1 - lx);
-                if (oy + BROX_PH < h) dist = min(dist, BROX_PH - 1 - ly);
-                const bool interior = inside && x >= gx0 && x < gx0 + p.tw && y >= gy0 && y < gy0 + p.th;
-                const bool live = inside && dist >= (p.halo > ns2 ? p.halo - ns2 : 0) + 1;   // updated by at least the first half-sweep
-                v = (unsigned)q | ((unsigned)par << 12) | ((unsigned)interior << 13) | ((unsigned)live << 14) | ((unsigned)dist << 16);
+                v = (unsigned)q | ((unsigned)par << 12) | ((unsigned)(lx < w) << 14);
             }
             pk[c][m] = v;
             rdu[c][m] = rdv[c][m] = 0.0f;
         }
-
-    if (p.halo == 0) {   // single-tile mode stages only the rows the level has: clear everything once
-        for (int r = tid; r < 4 * BROX_NPCP; r += BROX_NT) ((float2 *)sm4)[r] = make_float2(0.0f, 0.0f);
-    } else {             // tiled mode rewrites the whole region every launch: only the guards need zeros
-        for (int r = tid; r < 12 * BROX_G; r += BROX_NT) {
-            const int a = r / (2 * BROX_G), o = r - a * 2 * BROX_G;       // a: 0,1 = uv colours; 2..5 = wr c0, wr c1, wd c0, wd c1
-            const int off = o < BROX_G ? o - BROX_G : BROX_NPC + (o - BROX_G);   // relative to the array base (which sits BROX_G after its start)
-            if (a < 2) s_uv[a * BROX_NPCP + off] = make_float2(0.0f, 0.0f);
-            else s_wr[(a - 2) * BROX_NPCP + off] = 0.0f;                  // s_wd follows s_wr contiguously
-        }
-    }
+    for (int r = tid; r < 4 * NPCP; r += NT) ((float2 *)sm4)[r] = make_float2(0.0f, 0.0f);
     __syncthreads();
-    BROX_CLK(0)
     for (int it = 0; it < p.n_inner; ++it) {
-        // ---- phase 0: stage (du,dv), the level's flow (u,v) and the total flow u + du_base (radius = whole region).
-        // Four region pixels per thread and pass: the global loads of all four are issued before the first use (the
-        // phase is bound by L2 latency with only 16 warps per SM).
-        for (int r0 = tid; r0 < pp_used; r0 += 4 * BROX_NT) {
-            int g[4], ci[4];
-            bool in[4];
-            float bu[4], bv[4], uu[4], vv[4], iu[4], iv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int r = r0 + k * BROX_NT;
-                in[k] = false; g[k] = 0; ci[k] = 0;
-                if (r < pp_used) {
-                    const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
-                    const int x = ox + lx, y = oy + ly;
-                    ci[k] = ((lx + ly) & 1) * BROX_NPCP + ly * BROX_HW + (lx >> 1);
-                    in[k] = x >= 0 && x < w && y >= 0 && y < h;
-                    g[k] = y * w + x;
-                }
-            }
-            if (it == 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    bu[k] = bv[k] = uu[k] = vv[k] = iu[k] = iv[k] = 0.0f;
-                    if (in[k]) {
-                        bu[k] = p.dub[g[k]]; bv[k] = p.dvb[g[k]]; uu[k] = p.u[g[k]]; vv[k] = p.v[g[k]];
-                        if (!same_base) { iu[k] = p.dui[g[k]]; iv[k] = p.dvi[g[k]]; }
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int r = r0 + k * BROX_NT;
-                if (r >= pp_used) continue;
-                float ta = 0.0f, tb = 0.0f;
+        // ---- phase 0: (du, dv), the level's flow (u, v) and the total flow
+        for (int r = tid; r < PP; r += NT) {
+            const int ly = (int)(((float)r + 0.5f) * inv_pw), lx = r - ly * PW;
+            const int ci = ((lx + ly) & 1) * NPCP + ly * HW + (lx >> 1);
+            float ta = 0.0f, tb = 0.0f;
+            if (lx < w) {
                 if (it == 0) {
-                    s_uv[ci[k]] = same_base ? make_float2(bu[k], bv[k]) : make_float2(iu[k], iv[k]);   // zeros outside the image
-                    s_u[r] = uu[k];
-                    s_v[r] = vv[k];
-                    ta = uu[k] + bu[k];
-                    tb = vv[k] + bv[k];
-                } else if (in[k]) {   // single-tile mode: the increment of the previous inner iteration is already in shared memory
-                    const float2 d = s_uv[ci[k]];
+                    const int g = ly * w + lx;
+                    const float bu = p.dub[g], bv = p.dvb[g], uu = p.u[g], vv = p.v[g];
+                    s_uv[ci] = make_float2(bu, bv);
+                    s_u[r] = uu;
+                    s_v[r] = vv;
+                    ta = uu + bu;
+                    tb = vv + bv;
+                } else {   // the increment of the previous inner iteration is already in shared memory
+                    const float2 d = s_uv[ci];
                     ta = s_u[r] + d.x;
                     tb = s_v[r] + d.y;
                 }
-                s_ta[r] = ta;
-                s_tb[r] = tb;
+            } else if (it == 0) {
+                s_u[r] = 0.0f;
+                s_v[r] = 0.0f;
             }
+            s_ta[r] = ta;
+            s_tb[r] = tb;
         }
         __syncthreads();
-        BROX_CLK(1)
         // ---- phase 1: smoothness diffusivity psi'_s from the gradient of the total flow
-        for (int r = tid; r < pp_used; r += BROX_NT) {
-            const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
-            const int x = ox + lx, y = oy + ly;
+        for (int r = tid; r < PP; r += NT) {
+            const int y = (int)(((float)r + 0.5f) * inv_pw), x = r - y * PW;
             float ps = 0.0f;
-            if (x >= 0 && x < w && y >= 0 && y < h) {
-                const int rm = (x > 0 && lx > 0) ? r - 1 : r, rp = (x < w - 1 && lx < BROX_PW - 1) ? r + 1 : r;
-                const int ru = (y > 0 && ly > 0) ? r - BROX_PW : r, rd = (y < h - 1 && ly < BROX_PH - 1) ? r + BROX_PW : r;
+            if (x < w) {
+                const int rm = x > 0 ? r - 1 : r, rp = x < w - 1 ? r + 1 : r, ru = y > 0 ? r - PW : r, rd = y < h - 1 ? r + PW : r;
                 const float ux = 0.5f * (s_ta[rp] - s_ta[rm]), uy = 0.5f * (s_ta[rd] - s_ta[ru]);
                 const float vx = 0.5f * (s_tb[rp] - s_tb[rm]), vy = 0.5f * (s_tb[rd] - s_tb[ru]);
                 ps = 0.5f / sqrtf(ux * ux + uy * uy + vx * vx + vy * vy + BROX_EPS2);
@@ -320,40 +262,36 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
             s_ps[r] = ps;
         }
         __syncthreads();
-        BROX_CLK(2)
         // ---- phase 2a: edge weights (right, down) of every pixel; zero across the image border (Neumann)
-        for (int r = tid; r < pp_used; r += BROX_NT) {
-            const int ly = r / BROX_PW, lx = r - ly * BROX_PW;
-            const int x = ox + lx, y = oy + ly;
+        for (int r = tid; r < PP; r += NT) {
+            const int y = (int)(((float)r + 0.5f) * inv_pw), x = r - y * PW;
             float wr = 0.0f, wd = 0.0f;
-            if (x >= 0 && x < w && y >= 0 && y < h) {
+            if (x < w) {
                 const float ps = s_ps[r];
-                if (x < w - 1 && lx < BROX_PW - 1) wr = alpha * 0.5f * (ps + s_ps[r + 1]);
-                if (y < h - 1 && ly < BROX_PH - 1) wd = alpha * 0.5f * (ps + s_ps[r + BROX_PW]);
+                if (x < w - 1) wr = alpha * 0.5f * (ps + s_ps[r + 1]);
+                if (y < h - 1) wd = alpha * 0.5f * (ps + s_ps[r + PW]);
             }
-            const int wi = ((lx + ly) & 1) * BROX_NPCP + ly * BROX_HW + (lx >> 1);
+            const int wi = ((x + y) & 1) * NPCP + y * HW + (x >> 1);
             s_wr[wi] = wr;
             s_wd[wi] = wd;
         }
         __syncthreads();
-        BROX_CLK(3)
-        // ---- phase 2b: data term and the 2x2 system of the owned pixels -> registers
+        // ---- phase 2b: data term and the 2x2 system of the owned pixels
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int m = 0; m < BROX_M; ++m) {
+            for (int m = 0; m < M; ++m) {
                 const unsigned k = pk[c][m];
                 if (!((k >> 14) & 1u)) continue;
                 const int idx = k & 0xfff, par = (k >> 12) & 1;
-                const int ly = idx / BROX_HW, lx = 2 * (idx - ly * BROX_HW) + par;
-                const int x = ox + lx, y = oy + ly, g = y * w + x;
-                const float wl = x > 0 ? s_wr[(c ^ 1) * BROX_NPCP + idx - 1 + par] : 0.0f, wr = s_wr[c * BROX_NPCP + idx];
-                const float wu = y > 0 ? s_wd[(c ^ 1) * BROX_NPCP + idx - BROX_HW] : 0.0f, wd = s_wd[c * BROX_NPCP + idx];
-                const float2 own = s_uv[c * BROX_NPCP + idx];
-                float dub, dvb;
-                if (it == 0) { dub = p.dub[g]; dvb = p.dvb[g]; } else { dub = own.x; dvb = own.y; }
+                const int y = (int)(((float)idx + 0.5f) * inv_hw), x = 2 * (idx - y * HW) + par;
+                const int g = y * w + x;
+                const float wl = x > 0 ? s_wr[(c ^ 1) * NPCP + idx - 1 + par] : 0.0f, wr = s_wr[c * NPCP + idx];
+                const float wu = y > 0 ? s_wd[(c ^ 1) * NPCP + idx - HW] : 0.0f, wd = s_wd[c * NPCP + idx];
+                const float2 own = s_uv[c * NPCP + idx];
                 rdu[c][m] = own.x;
                 rdv[c][m] = own.y;
+                const float dub = own.x, dvb = own.y;   // == the increment at the start of this inner iteration
                 const float ix = p.Ix[g], iy = p.Iy[g], iz = p.Iz[g], ixx = p.Ixx[g], ixy = p.Ixy[g], iyy = p.Iyy[g], ixz = p.Ixz[g], iyz = p.Iyz[g];
                 const float q0 = iz + ix * dub + iy * dvb;
                 const float q1 = ixz + ixx * dub + ixy * dvb;
@@ -364,43 +302,40 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
                 const float j22 = psid * (iy * iy + gamma * (ixy * ixy + iyy * iyy));
                 const float j13 = psid * (ix * iz + gamma * (ixx * ixz + ixy * iyz));
                 const float j23 = psid * (iy * iz + gamma * (ixy * ixz + iyy * iyz));
-                const int r = ly * BROX_PW + lx;   // live pixels have all four neighbours inside the staged region
+                const int r = y * PW + x;
                 const float uc = s_u[r], vc = s_v[r];
                 float su = 0.0f, sv = 0.0f;
                 if (x > 0) { su += wl * (s_u[r - 1] - uc); sv += wl * (s_v[r - 1] - vc); }
                 if (x < w - 1) { su += wr * (s_u[r + 1] - uc); sv += wr * (s_v[r + 1] - vc); }
-                if (y > 0) { su += wu * (s_u[r - BROX_PW] - uc); sv += wu * (s_v[r - BROX_PW] - vc); }
-                if (y < h - 1) { su += wd * (s_u[r + BROX_PW] - uc); sv += wd * (s_v[r + BROX_PW] - vc); }
+                if (y > 0) { su += wu * (s_u[r - PW] - uc); sv += wu * (s_v[r - PW] - vc); }
+                if (y < h - 1) { su += wd * (s_u[r + PW] - uc); sv += wd * (s_v[r + PW] - vc); }
                 const float sw_ = wl + wr + wu + wd;
-                s_c4[c * BROX_NPC + idx] = make_float4(j12, su - j13, sv - j23, 1.0f / (j11 + sw_));
-                s_c1[c * BROX_NPC + idx] = 1.0f / (j22 + sw_);
+                s_c4[c * NPC + idx] = make_float4(j12, su - j13, sv - j23, 1.0f / (j11 + sw_));
+                s_c1[c * NPC + idx] = 1.0f / (j22 + sw_);
             }
-        BROX_CLK(4)
-        // (no barrier needed: the sweeps below read s_uv / s_wr / s_wd, which are complete, and the thread's own systems)
-        // ---- red-black SOR: half-sweep k updates colour (k-1)&1 where the halo distance allows it
-        const unsigned thr0 = (unsigned)(p.halo > ns2 ? p.halo - ns2 : 0);
-#define BROX_HALF(C, K)                                                                                           \
+        // (no barrier needed: phase 2b reads none of the planes the systems alias, and the sweeps read s_uv / s_wr / s_wd,
+        //  complete since the last barrier, plus the thread's own systems)
+        // ---- red-black SOR
+#define BROX_HALF(C)                                                                                              \
     {                                                                                                             \
-        const float2 *__restrict__ uo = s_uv + ((C) ^ 1) * BROX_NPCP;                                              \
-        float2 *__restrict__ uc_ = s_uv + (C) * BROX_NPCP;                                                         \
-        const float *__restrict__ wro = s_wr + ((C) ^ 1) * BROX_NPCP;                                              \
-        const float *__restrict__ wdo = s_wd + ((C) ^ 1) * BROX_NPCP;                                              \
-        const float *__restrict__ wrc = s_wr + (C) * BROX_NPCP;                                                    \
-        const float *__restrict__ wdc = s_wd + (C) * BROX_NPCP;                                                    \
-        _Pragma("unroll") for (int m = 0; m < BROX_M; ++m)                                                        \
+        const float2 *__restrict__ uo = s_uv + ((C) ^ 1) * NPCP;                                                   \
+        float2 *__restrict__ uc_ = s_uv + (C) * NPCP;                                                              \
+        const float *__restrict__ wro = s_wr + ((C) ^ 1) * NPCP;                                                   \
+        const float *__restrict__ wdo = s_wd + ((C) ^ 1) * NPCP;                                                   \
+        const float *__restrict__ wrc = s_wr + (C) * NPCP;                                                         \
+        const float *__restrict__ wdc = s_wd + (C) * NPCP;                                                         \
+        _Pragma("unroll") for (int m = 0; m < M; ++m)                                                             \
         {                                                                                                         \
             const unsigned k_ = pk[C][m];                                                                         \
-            /* measured: skipping inactive pixels (whole warps near the region border) beats unconditional, */    \
-            /* fully predicated slots by ~15 % on the 74 x 66 tile */                                              \
-            if (((k_ >> 14) & 1u) && (k_ >> 16) >= thr0 + (unsigned)(K)) {                                        \
+            if ((k_ >> 14) & 1u) {                                                                                \
                 const int idx = k_ & 0xfff, par = (k_ >> 12) & 1;                                                 \
-                const float2 l = uo[idx - 1 + par], r = uo[idx + par], u_ = uo[idx - BROX_HW], d = uo[idx + BROX_HW]; \
+                const float2 l = uo[idx - 1 + par], r = uo[idx + par], u_ = uo[idx - HW], d = uo[idx + HW];       \
                 const float wr_ = wrc[idx], wd_ = wdc[idx];                                                       \
-                const float wl = wro[idx - 1 + par], wu = wdo[idx - BROX_HW];                                     \
+                const float wl = wro[idx - 1 + par], wu = wdo[idx - HW];                                          \
                 const float su = wl * l.x + wr_ * r.x + wu * u_.x + wd_ * d.x;                                    \
                 const float sv = wl * l.y + wr_ * r.y + wu * u_.y + wd_ * d.y;                                    \
-                const float4 cf = s_c4[(C) * BROX_NPC + idx];                                                     \
-                const float cd2_ = s_c1[(C) * BROX_NPC + idx];                                                    \
+                const float4 cf = s_c4[(C) * NPC + idx];                                                          \
+                const float cd2_ = s_c1[(C) * NPC + idx];                                                         \
                 const float du_new = om1 * rdu[C][m] + omega * (cf.y - cf.x * rdv[C][m] + su) * cf.w;             \
                 const float dv_new = om1 * rdv[C][m] + omega * (cf.z - cf.x * du_new + sv) * cd2_;                \
                 rdu[C][m] = du_new;                                                                               \
@@ -411,31 +346,28 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_inner(BroxInnerP p)
         __syncthreads();                                                                                          \
     }
         for (int sw = 0; sw < p.nsweeps; ++sw) {
-            BROX_HALF(0, 2 * sw + 1)
-            BROX_HALF(1, 2 * sw + 2)
+            BROX_HALF(0)
+            BROX_HALF(1)
         }
 #undef BROX_HALF
-        BROX_CLK(5)
     }
-    // ---- write the interior from registers
+    // ---- write the level from registers
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int m = 0; m < BROX_M; ++m) {
+        for (int m = 0; m < M; ++m) {
             const unsigned k = pk[c][m];
-            if (!((k >> 13) & 1u)) continue;
+            if (!((k >> 14) & 1u)) continue;
             const int idx = k & 0xfff, par = (k >> 12) & 1;
-            const int ly = idx / BROX_HW, lx = 2 * (idx - ly * BROX_HW) + par;
-            const int g = (oy + ly) * w + ox + lx;
-            p.duo[g] = rdu[c][m];
-            p.dvo[g] = rdv[c][m];
+            const int y = (int)(((float)idx + 0.5f) * inv_hw), x = 2 * (idx - y * HW) + par;
+            p.duo[y * w + x] = rdu[c][m];
+            p.dvo[y * w + x] = rdv[c][m];
         }
-    BROX_CLK(6)
 }
 
 // ------------------------------------------------------------------ tiled levels: system kernel + SOR kernel
 // For levels larger than one tile the lagged-nonlinearity coefficients are computed ONCE per pixel by k_brox_system
-// (no halo redundancy: in k_brox_inner's tiled mode phases 0-2 ran on the whole tile + 21-px halo region, 6.4x the
+// (no halo redundancy: computed inside the sweep kernel they ran on the whole tile + 21-px halo region, 6.4x the
 // pixels of the tile, and took 44 % of the launch) and the temporally blocked sweeps (k_brox_sor) only stage them.
 struct BroxSysP {
     const float *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz, *u, *v, *dub, *dvb;
@@ -516,6 +448,16 @@ __global__ void __launch_bounds__(BSY_W *BSY_H) k_brox_system(BroxSysP p)
     p.C1[g] = 1.0f / (j22 + sw_);
 }
 
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 struct BroxSorP {
     const float2 *W;
     const float4 *C4;
@@ -528,7 +470,7 @@ struct BroxSorP {
 };
 
 // nsweeps (<= 10) red-black SOR sweeps on one tile + 21-px halo (temporal blocking): same data layout and sweep loop as
-// k_brox_inner, the systems come from k_brox_system.
+// k_brox_level, the systems come from k_brox_system.
 template <class T>
 __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
 {
@@ -546,6 +488,11 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
     const int ns2 = 2 * p.nsweeps;
     const float omega = p.omega, om1 = 1.0f - p.omega;
     const unsigned thr0 = (unsigned)(BROX_RMAX - ns2);
+#ifdef SINDYN_BROX_PHASE_CLOCKS
+    const bool prof_on = threadIdx.x == 0 && T::TW == 32 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2;
+    long long t_prev = clock64();
+    if (prof_on) atomicAdd(&g_brox_clk[15], 1ull);
+#endif
 
     // guards
     for (int r = tid; r < 12 * G; r += BROX_NT) {
@@ -554,33 +501,25 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
         if (a < 2) s_uv[a * NPCP + off] = make_float2(0.0f, 0.0f);
         else s_wr[(a - 2) * NPCP + off] = 0.0f;
     }
-    // ---- stage (du, dv) and the edge weights of the whole region, two pixels per thread and pass
-    for (int r0 = tid; r0 < PP; r0 += 2 * BROX_NT) {
-        int ci[2];
-        float2 wv[2];
-        float du[2], dv[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int r = r0 + k * BROX_NT;
-            wv[k] = make_float2(0.0f, 0.0f); du[k] = dv[k] = 0.0f; ci[k] = -1;
-            if (r < PP) {
-                const int ly = r / PW, lx = r - ly * PW;
-                const int x = ox + lx, y = oy + ly;
-                ci[k] = ((lx + ly) & 1) * NPCP + ly * HW + (lx >> 1);
-                if (x >= 0 && x < w && y >= 0 && y < h) {
-                    const int g = y * w + x;
-                    wv[k] = p.W[g]; du[k] = p.dui[g]; dv[k] = p.dvi[g];
-                }
-            }
+    // ---- stage (du, dv) and the edge weights of the whole region with asynchronous global -> shared copies (no register
+    // staging: every copy of the thread is in flight at once, the pixel table below is computed underneath them)
+    for (int r = tid; r < PP; r += BROX_NT) {
+        const int ly = r / PW, lx = r - ly * PW;
+        const int x = ox + lx, y = oy + ly;
+        const int ci = ((lx + ly) & 1) * NPCP + ly * HW + (lx >> 1);
+        if (x >= 0 && x < w && y >= 0 && y < h) {
+            const int g = y * w + x;
+            cp_async4(&s_uv[ci].x, p.dui + g);
+            cp_async4(&s_uv[ci].y, p.dvi + g);
+            cp_async4(&s_wr[ci], &p.W[g].x);
+            cp_async4(&s_wd[ci], &p.W[g].y);
+        } else {
+            s_uv[ci] = make_float2(0.0f, 0.0f);
+            s_wr[ci] = 0.0f;
+            s_wd[ci] = 0.0f;
         }
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-            if (ci[k] >= 0) {
-                s_uv[ci[k]] = make_float2(du[k], dv[k]);
-                s_wr[ci[k]] = wv[k].x;
-                s_wd[ci[k]] = wv[k].y;
-            }
     }
+    BROX_CLK(0)
     // ---- owned pixels: table, systems (global -> the thread's private shared-memory slots)
     unsigned pk[2][M];
     float rdu[2][M], rdv[2][M];
@@ -605,13 +544,15 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
                 v = (unsigned)q | ((unsigned)par << 12) | ((unsigned)interior << 13) | ((unsigned)live << 14) | ((unsigned)dist << 16);
                 if (live) {
                     const int g = y * w + x;
-                    s_c4[c * NPC + q] = p.C4[g];
-                    s_c1[c * NPC + q] = p.C1[g];
+                    cp_async16(&s_c4[c * NPC + q], p.C4 + g);
+                    cp_async4(&s_c1[c * NPC + q], p.C1 + g);
                 }
             }
             pk[c][m] = v;
         }
+    cp_async_wait_all();
     __syncthreads();
+    BROX_CLK(1)
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -656,6 +597,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
         BROX_HALF(1, 2 * sw + 2)
     }
 #undef BROX_HALF
+    BROX_CLK(2)
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -668,6 +610,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
             p.duo[g] = rdu[c][m];
             p.dvo[g] = rdv[c][m];
         }
+    BROX_CLK(3)
 }
 
 // level -> finer level: (u+du, v+dv) bilinear, scaled by the size ratios
@@ -704,6 +647,15 @@ __global__ void k_brox_final(const float *__restrict__ u, const float *__restric
 }
 
 // ------------------------------------------------------------------ host side
+// shared memory of k_brox_level for a w x h level
+static size_t brox_level_smem(int w, int h)
+{
+    const size_t pw = (size_t)(w + 2) & ~(size_t)1, hw = pw / 2, npc = hw * h, npcp = npc + 2 * (hw + 1);
+    return 32 * npcp + 40 * npc + 8 * pw * h;
+}
+constexpr int BROX_LEVEL_MAX_PX = 2100;
+
+constexpr size_t BROX_SMEM_MAX = 227 * 1024;
 int brox_num_levels_host(int w, int h, float scale, int outer, int *ws, int *hs)
 {
     int n = 0;
@@ -742,7 +694,8 @@ int brox_init(sindyn_base *ctx, BroxSolver *b, int w, int h, float alpha, float 
     CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTile<16, 12>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<16, 12>::SMEM_SOR));
     CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTile<24, 16>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<24, 16>::SMEM_SOR));
     CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTileL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTileL::SMEM_SOR));
-    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_inner<BroxTileL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTileL::SMEM));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_level<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BROX_SMEM_MAX));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_level<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BROX_SMEM_MAX));
     return SINDYN_OK;
 }
 
@@ -782,18 +735,17 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
         p.Ix = b->Ix; p.Iy = b->Iy; p.Iz = b->Iz; p.Ixx = b->Ixx; p.Ixy = b->Ixy; p.Iyy = b->Iyy; p.Ixz = b->Ixz; p.Iyz = b->Iyz;
         p.u = b->u[cur]; p.v = b->v[cur];
         p.w = w; p.h = h; p.alpha = b->alpha; p.gamma = b->gamma; p.omega = b->omega;
-        // One CTA is faster than a grid only while the level is tiny (<= ~1200 px: the 4 coarsest of 15 levels): above that
-        // 10 launches on 8x8 tiles spread over 35-90 SMs win over 10 inner iterations serialised on one SM.
-        if (w <= BroxTileL::PW && h <= BroxTileL::PH && w * h <= 1200 && b->solver <= BROX_SMAX) {
-            // the whole level fits into one tile: all lagged-nonlinearity iterations in ONE launch, no halo
+        // One CTA is faster than a grid while the level is small: above BROX_LEVEL_MAX_PX the tiled path (system + SOR
+        // launch per inner iteration, spread over up to 148 SMs) wins over 10 inner iterations serialised on one SM.
+        const int npc = h * (w / 2 + 1);   // pixels per colour in k_brox_level's packed layout
+        if (w * h <= BROX_LEVEL_MAX_PX && npc <= 2 * BROX_NT && brox_level_smem(w, h) <= BROX_SMEM_MAX) {
             const int out = 1;
-            p.dub = p.dui = b->du[base]; p.dvb = p.dvi = b->dv[base];
+            p.dub = b->du[base]; p.dvb = b->dv[base];
             p.duo = b->du[out]; p.dvo = b->dv[out];
-            p.nsweeps = b->solver; p.tw = BroxTileL::PW; p.th = BroxTileL::PH; p.halo = 0; p.n_inner = b->inner;
-            const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
-            if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
-            LAUNCH(ctx, k_brox_inner<BroxTileL>, dim3(1, 1), BROX_NT, BroxTileL::SMEM, p);
-            if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h * b->inner; }
+            p.nsweeps = b->solver; p.n_inner = b->inner;
+            const size_t smem = brox_level_smem(w, h);
+            if (npc <= BROX_NT) LAUNCH(ctx, k_brox_level<1>, dim3(1, 1), max(128, (npc + 31) & ~31), smem, p);
+            else LAUNCH(ctx, k_brox_level<2>, dim3(1, 1), ((npc + 1) / 2 + 31) & ~31, smem, p);
             base = out;
         } else {
             const int tile = brox_tile_fits<BroxTile<8, 8>>(w, h) ? 0 : brox_tile_fits<BroxTile<16, 12>>(w, h) ? 1 : brox_tile_fits<BroxTile<24, 16>>(w, h) ? 2 : 3;
@@ -806,8 +758,6 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
             for (int it = 0; it < b->inner; ++it) {
                 int in = base, remaining = b->solver;
                 sp.dub = b->du[base]; sp.dvb = b->dv[base];
-                const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
-                if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
                 LAUNCH(ctx, k_brox_system, dim3(cdiv(w, BSY_W), cdiv(h, BSY_H)), dim3(BSY_W, BSY_H), 0, sp);
                 while (remaining > 0) {
                     int ns = remaining < BROX_SMAX ? remaining : BROX_SMAX;
@@ -816,17 +766,19 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
                     q.dui = b->du[in]; q.dvi = b->dv[in];
                     q.duo = b->du[out]; q.dvo = b->dv[out];
                     q.nsweeps = ns;
+                    // measurement hook: every k_brox_sor launch is bracketed by events
+                    const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
+                    if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
                     switch (tile) {
                     case 0: brox_launch_sor<BroxTile<8, 8>>(ctx, q); break;
                     case 1: brox_launch_sor<BroxTile<16, 12>>(ctx, q); break;
                     case 2: brox_launch_sor<BroxTile<24, 16>>(ctx, q); break;
                     default: brox_launch_sor<BroxTileL>(ctx, q); break;
                     }
+                    if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h; }
                     in = out;
                     remaining -= ns;
                 }
-                // one profile interval = one inner iteration (system + sweeps)
-                if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h; }
                 base = in;
             }
         }

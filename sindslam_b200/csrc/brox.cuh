@@ -32,7 +32,7 @@ struct BroxSolver {
     } slots[4];
     int next_slot = 0;
     bool graph_ok = false;  // set to false to drop every cached graph (stream change)
-    // measurement hook (sindyn_brox_profile): when non-null, every SOR-kernel launch is bracketed by events
+    // measurement hook (sindyn_brox_profile): when non-null, every k_brox_sor launch is bracketed by events
     cudaEvent_t *prof_ev = nullptr;
     int prof_n = 0, prof_cap = 0;
     long long prof_px = 0;

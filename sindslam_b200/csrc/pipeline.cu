@@ -1,6 +1,8 @@
 // pipeline.cu -- fused per-frame entry points: the flow + residual branch
 // (DynaDetect::DetectDynaByDenseOpticalFLow, ORB_SLAM2/src/DynaDetect.cc:1023-1374), device-resident frame
 // slots for kernel-only timing, and the Brox measurement hook.
+#include <cstdio>
+#include <cstdlib>
 #include "ctx.cuh"
 
 #define H_CHECK(h)                       \
@@ -130,7 +132,12 @@ extern "C" int sindyn_brox_profile(sindyn_handle h, double *out4)
     double sor = 0.0;
     float ms = 0.f;
     if (st == SINDYN_OK) {
-        for (int i = 0; i + 1 < n; i += 2) { cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); sor += ms; }
+        const bool trace = getenv("SINDYN_BROX_TRACE") != nullptr;   // developer aid: per-interval times on stderr
+        for (int i = 0; i + 1 < n; i += 2) {
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            sor += ms;
+            if (trace) fprintf(stderr, "brox interval %d: %.1f us\n", i / 2, 1e3 * ms);
+        }
         cudaEventElapsedTime(&ms, ev[cap], ev[cap + 1]);
     }
     for (auto &e : ev) cudaEventDestroy(e);

@@ -1,4 +1,4 @@
-"""Per-phase clock breakdown of k_brox_inner; needs a build with SINDYN_NVCC_EXTRA=-DSINDYN_BROX_PHASE_CLOCKS."""
+"""Per-phase clock breakdown of k_brox_sor (32x24 tiles); needs a build with SINDYN_NVCC_EXTRA=-DSINDYN_BROX_PHASE_CLOCKS."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sindslam_b200 import synth, capi
@@ -14,7 +14,7 @@ lib.sindyn_dbg_brox_phase_clocks(buf, 1)
 for _ in range(5): sd.brox_profile()
 lib.sindyn_dbg_brox_phase_clocks(buf, 0)
 n = buf[15]
-names = ["setup", "phase0", "phase1", "phase2a", "phase2b", "sweeps", "write"]
-tot = sum(buf[i] for i in range(7))
-for i, nm in enumerate(names): print("%-8s %8.0f cyc/launch  %5.1f %%" % (nm, buf[i] / n, 100.0 * buf[i] / tot))
+names = ["stage (cp.async issue)", "table + systems + wait", "sweeps", "write"]
+tot = sum(buf[i] for i in range(4))
+for i, nm in enumerate(names): print("%-26s %8.0f cyc/launch  %5.1f %%" % (nm, buf[i] / n, 100.0 * buf[i] / tot))
 print("launches", n, "total cyc/launch", tot / n)
