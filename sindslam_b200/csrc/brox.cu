@@ -43,6 +43,8 @@ int launch_resample_f32(sindyn_base *ctx, const float *src, int sw, int sh, floa
 __global__ void k_brox_pyr_down(const float *__restrict__ s0, const float *__restrict__ s1, int sw, int sh,
                                 float *__restrict__ d0, float *__restrict__ d1, int dw, int dh, float fx, float fy)
 {
+    pdl_wait();
+    pdl_trigger();
     const float *src = blockIdx.z ? s1 : s0;
     float *dst = blockIdx.z ? d1 : d0;
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -74,6 +76,8 @@ __global__ void k_brox_warp(const float *__restrict__ I0, const float *__restric
                             const float *__restrict__ v, int w, int h, float *__restrict__ A, float *__restrict__ Iz,
                             float *__restrict__ du, float *__restrict__ dv)
 {
+    pdl_wait();
+    pdl_trigger();
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
     int i = y * w + x;
@@ -99,6 +103,8 @@ __device__ __forceinline__ float d5y(const float *__restrict__ f, int w, int h, 
 __global__ void k_brox_deriv1(const float *__restrict__ A, const float *__restrict__ Iz, int w, int h,
                               float *__restrict__ Ix, float *__restrict__ Iy, float *__restrict__ Ixz, float *__restrict__ Iyz)
 {
+    pdl_wait();
+    pdl_trigger();
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
     int i = y * w + x;
@@ -111,6 +117,8 @@ __global__ void k_brox_deriv1(const float *__restrict__ A, const float *__restri
 __global__ void k_brox_deriv2(const float *__restrict__ Ix, const float *__restrict__ Iy, int w, int h,
                               float *__restrict__ Ixx, float *__restrict__ Ixy, float *__restrict__ Iyy)
 {
+    pdl_wait();
+    pdl_trigger();
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
     int i = y * w + x;
@@ -220,6 +228,8 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_level(BroxInnerP p)
             rdu[c][m] = rdv[c][m] = 0.0f;
         }
     for (int r = tid; r < 4 * NPCP; r += NT) ((float2 *)sm4)[r] = make_float2(0.0f, 0.0f);
+    pdl_wait();      // everything above is independent of the previous kernel's output
+    pdl_trigger();
     __syncthreads();
     for (int it = 0; it < p.n_inner; ++it) {
         // ---- phase 0: (du, dv), the level's flow (u, v) and the total flow
@@ -381,6 +391,8 @@ constexpr int BSY_W = 32, BSY_H = 8;
 
 __global__ void __launch_bounds__(BSY_W *BSY_H) k_brox_system(BroxSysP p)
 {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float s_ta[BSY_H + 4][BSY_W + 4], s_tb[BSY_H + 4][BSY_W + 4], s_u[BSY_H + 4][BSY_W + 4], s_v[BSY_H + 4][BSY_W + 4];
     __shared__ float s_ps[BSY_H + 2][BSY_W + 2];
     const int w = p.w, h = p.h;
@@ -501,26 +513,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
         if (a < 2) s_uv[a * NPCP + off] = make_float2(0.0f, 0.0f);
         else s_wr[(a - 2) * NPCP + off] = 0.0f;
     }
-    // ---- stage (du, dv) and the edge weights of the whole region with asynchronous global -> shared copies (no register
-    // staging: every copy of the thread is in flight at once, the pixel table below is computed underneath them)
-    for (int r = tid; r < PP; r += BROX_NT) {
-        const int ly = r / PW, lx = r - ly * PW;
-        const int x = ox + lx, y = oy + ly;
-        const int ci = ((lx + ly) & 1) * NPCP + ly * HW + (lx >> 1);
-        if (x >= 0 && x < w && y >= 0 && y < h) {
-            const int g = y * w + x;
-            cp_async4(&s_uv[ci].x, p.dui + g);
-            cp_async4(&s_uv[ci].y, p.dvi + g);
-            cp_async4(&s_wr[ci], &p.W[g].x);
-            cp_async4(&s_wd[ci], &p.W[g].y);
-        } else {
-            s_uv[ci] = make_float2(0.0f, 0.0f);
-            s_wr[ci] = 0.0f;
-            s_wd[ci] = 0.0f;
-        }
-    }
-    BROX_CLK(0)
-    // ---- owned pixels: table, systems (global -> the thread's private shared-memory slots)
+    // ---- owned pixels: table (independent of the previous kernel's output: runs under its tail, see pdl_wait)
     unsigned pk[2][M];
     float rdu[2][M], rdv[2][M];
 #pragma unroll
@@ -542,13 +535,41 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
                 const bool interior = inside && x >= gx0 && x < gx0 + T::TW && y >= gy0 && y < gy0 + T::TH;
                 const bool live = inside && dist >= (int)thr0 + 1;   // updated by at least the first half-sweep
                 v = (unsigned)q | ((unsigned)par << 12) | ((unsigned)interior << 13) | ((unsigned)live << 14) | ((unsigned)dist << 16);
-                if (live) {
-                    const int g = y * w + x;
-                    cp_async16(&s_c4[c * NPC + q], p.C4 + g);
-                    cp_async4(&s_c1[c * NPC + q], p.C1 + g);
-                }
             }
             pk[c][m] = v;
+        }
+    pdl_wait();
+    pdl_trigger();
+    BROX_CLK(0)
+    // ---- stage (du, dv) and the edge weights of the whole region and the systems of the owned pixels with asynchronous
+    // global -> shared copies (no register staging: every copy of the thread is in flight at once)
+    for (int r = tid; r < PP; r += BROX_NT) {
+        const int ly = r / PW, lx = r - ly * PW;
+        const int x = ox + lx, y = oy + ly;
+        const int ci = ((lx + ly) & 1) * NPCP + ly * HW + (lx >> 1);
+        if (x >= 0 && x < w && y >= 0 && y < h) {
+            const int g = y * w + x;
+            cp_async4(&s_uv[ci].x, p.dui + g);
+            cp_async4(&s_uv[ci].y, p.dvi + g);
+            cp_async4(&s_wr[ci], &p.W[g].x);
+            cp_async4(&s_wd[ci], &p.W[g].y);
+        } else {
+            s_uv[ci] = make_float2(0.0f, 0.0f);
+            s_wr[ci] = 0.0f;
+            s_wd[ci] = 0.0f;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const unsigned k = pk[c][m];
+            if (!((k >> 14) & 1u)) continue;
+            const int idx = k & 0xfff, par = (k >> 12) & 1;
+            const int ly = idx / HW, lx = 2 * (idx - ly * HW) + par;
+            const int g = (oy + ly) * w + ox + lx;
+            cp_async16(&s_c4[c * NPC + idx], p.C4 + g);
+            cp_async4(&s_c1[c * NPC + idx], p.C1 + g);
         }
     cp_async_wait_all();
     __syncthreads();
@@ -618,6 +639,8 @@ __global__ void k_brox_prolong(const float *__restrict__ u, const float *__restr
                                const float *__restrict__ dv, int sw, int sh, float *__restrict__ u2, float *__restrict__ v2,
                                int dw, int dh, float fx, float fy, float mulx, float muly)
 {
+    pdl_wait();
+    pdl_trigger();
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh) return;
     float sy = ((float)y + 0.5f) * fy - 0.5f, sx = ((float)x + 0.5f) * fx - 0.5f;
@@ -641,6 +664,8 @@ __global__ void k_brox_prolong(const float *__restrict__ u, const float *__restr
 __global__ void k_brox_final(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ du,
                              const float *__restrict__ dv, int n, float2 *__restrict__ out, float sign)
 {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = make_float2(sign * (u[i] + du[i]), sign * (v[i] + dv[i]));
@@ -702,7 +727,7 @@ int brox_init(sindyn_base *ctx, BroxSolver *b, int w, int h, float alpha, float 
 template <class T> static bool brox_tile_fits(int w, int h) { return cdiv(w, T::TW) * cdiv(h, T::TH) <= SINDYN_NUM_SMS_B200; }
 template <class T> static void brox_launch_sor(sindyn_base *ctx, BroxSorP &p)
 {
-    LAUNCH(ctx, k_brox_sor<T>, dim3(cdiv(p.w, T::TW), cdiv(p.h, T::TH)), BROX_NT, T::SMEM_SOR, p);
+    LAUNCH_PDL(ctx, k_brox_sor<T>, dim3(cdiv(p.w, T::TW), cdiv(p.h, T::TH)), BROX_NT, T::SMEM_SOR, p);
 }
 
 static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const float *I1, float *flow_out, float sign)
@@ -712,7 +737,7 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
     for (int k = 1; k < b->nl; ++k) {
         const float *s0 = k == 1 ? I0 : b->pyr0 + b->off[k - 1], *s1 = k == 1 ? I1 : b->pyr1 + b->off[k - 1];
         dim3 grd(cdiv(b->ws[k], 32), cdiv(b->hs[k], 8), 2);
-        LAUNCH(ctx, k_brox_pyr_down, grd, blk, 0, s0, s1, b->ws[k - 1], b->hs[k - 1], b->pyr0 + b->off[k], b->pyr1 + b->off[k],
+        LAUNCH_PDL(ctx, k_brox_pyr_down, grd, blk, 0, s0, s1, b->ws[k - 1], b->hs[k - 1], b->pyr0 + b->off[k], b->pyr1 + b->off[k],
                b->ws[k], b->hs[k], (float)b->ws[k - 1] / (float)b->ws[k], (float)b->hs[k - 1] / (float)b->hs[k]);
     }
     int cur = 0;  // u[cur], v[cur] hold the flow of the current level
@@ -728,9 +753,9 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
         const float *L0 = k == 0 ? I0 : b->pyr0 + b->off[k], *L1 = k == 0 ? I1 : b->pyr1 + b->off[k];
         dim3 grd(cdiv(w, 32), cdiv(h, 8));
         int base = 0;
-        LAUNCH(ctx, k_brox_warp, grd, blk, 0, L0, L1, b->u[cur], b->v[cur], w, h, b->A, b->Iz, b->du[base], b->dv[base]);
-        LAUNCH(ctx, k_brox_deriv1, grd, blk, 0, b->A, b->Iz, w, h, b->Ix, b->Iy, b->Ixz, b->Iyz);
-        LAUNCH(ctx, k_brox_deriv2, grd, blk, 0, b->Ix, b->Iy, w, h, b->Ixx, b->Ixy, b->Iyy);
+        LAUNCH_PDL(ctx, k_brox_warp, grd, blk, 0, L0, L1, b->u[cur], b->v[cur], w, h, b->A, b->Iz, b->du[base], b->dv[base]);
+        LAUNCH_PDL(ctx, k_brox_deriv1, grd, blk, 0, b->A, b->Iz, w, h, b->Ix, b->Iy, b->Ixz, b->Iyz);
+        LAUNCH_PDL(ctx, k_brox_deriv2, grd, blk, 0, b->Ix, b->Iy, w, h, b->Ixx, b->Ixy, b->Iyy);
         BroxInnerP p;
         p.Ix = b->Ix; p.Iy = b->Iy; p.Iz = b->Iz; p.Ixx = b->Ixx; p.Ixy = b->Ixy; p.Iyy = b->Iyy; p.Ixz = b->Ixz; p.Iyz = b->Iyz;
         p.u = b->u[cur]; p.v = b->v[cur];
@@ -744,8 +769,8 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
             p.duo = b->du[out]; p.dvo = b->dv[out];
             p.nsweeps = b->solver; p.n_inner = b->inner;
             const size_t smem = brox_level_smem(w, h);
-            if (npc <= BROX_NT) LAUNCH(ctx, k_brox_level<1>, dim3(1, 1), max(128, (npc + 31) & ~31), smem, p);
-            else LAUNCH(ctx, k_brox_level<2>, dim3(1, 1), ((npc + 1) / 2 + 31) & ~31, smem, p);
+            if (npc <= BROX_NT) LAUNCH_PDL(ctx, k_brox_level<1>, dim3(1, 1), max(128, (npc + 31) & ~31), smem, p);
+            else LAUNCH_PDL(ctx, k_brox_level<2>, dim3(1, 1), ((npc + 1) / 2 + 31) & ~31, smem, p);
             base = out;
         } else {
             const int tile = brox_tile_fits<BroxTile<8, 8>>(w, h) ? 0 : brox_tile_fits<BroxTile<16, 12>>(w, h) ? 1 : brox_tile_fits<BroxTile<24, 16>>(w, h) ? 2 : 3;
@@ -758,7 +783,7 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
             for (int it = 0; it < b->inner; ++it) {
                 int in = base, remaining = b->solver;
                 sp.dub = b->du[base]; sp.dvb = b->dv[base];
-                LAUNCH(ctx, k_brox_system, dim3(cdiv(w, BSY_W), cdiv(h, BSY_H)), dim3(BSY_W, BSY_H), 0, sp);
+                LAUNCH_PDL(ctx, k_brox_system, dim3(cdiv(w, BSY_W), cdiv(h, BSY_H)), dim3(BSY_W, BSY_H), 0, sp);
                 while (remaining > 0) {
                     int ns = remaining < BROX_SMAX ? remaining : BROX_SMAX;
                     int out = 0;
@@ -785,7 +810,7 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
         if (k > 0) {
             const int fw = b->ws[k - 1], fh = b->hs[k - 1];
             dim3 fgrd(cdiv(fw, 32), cdiv(fh, 8));
-            LAUNCH(ctx, k_brox_prolong, fgrd, blk, 0, b->u[cur], b->v[cur], b->du[base], b->dv[base], w, h, b->u[cur ^ 1],
+            LAUNCH_PDL(ctx, k_brox_prolong, fgrd, blk, 0, b->u[cur], b->v[cur], b->du[base], b->dv[base], w, h, b->u[cur ^ 1],
                    b->v[cur ^ 1], fw, fh, (float)w / (float)fw, (float)h / (float)fh, (float)fw / (float)w, (float)fh / (float)h);
             cur ^= 1;
         } else {
@@ -793,7 +818,7 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
         }
     }
     int n = b->w * b->h;
-    LAUNCH(ctx, k_brox_final, cdiv(n, 256), 256, 0, b->u[cur], b->v[cur], b->du[fin], b->dv[fin], n, (float2 *)flow_out, sign);
+    LAUNCH_PDL(ctx, k_brox_final, cdiv(n, 256), 256, 0, b->u[cur], b->v[cur], b->du[fin], b->dv[fin], n, (float2 *)flow_out, sign);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }

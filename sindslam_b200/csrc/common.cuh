@@ -89,6 +89,31 @@ struct sindyn_base {
         (ctx)->launches++;                                                 \
     } while (0)
 
+// Programmatic dependent launch (sm_90+): a kernel launched with LAUNCH_PDL may become resident and run its input-independent
+// prologue while the previous kernel of the stream is still executing; it must call pdl_wait() before it touches anything
+// the previous kernel wrote (the wait returns when that grid has completed and its writes are visible), and calls
+// pdl_trigger() right after so that its own successor can be scheduled.  Without the launch attribute both are no-ops.
+// Works in stream capture (the graph gets programmatic dependency edges).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+#define LAUNCH_PDL(ctx, kern, grid, block, smem, ...)                                        \
+    do {                                                                                     \
+        cudaLaunchConfig_t cfg_ = {};                                                        \
+        cfg_.gridDim = dim3(grid);                                                           \
+        cfg_.blockDim = dim3(block);                                                         \
+        cfg_.dynamicSmemBytes = (smem);                                                      \
+        cfg_.stream = (ctx)->stream;                                                         \
+        cudaLaunchAttribute at_[1];                                                          \
+        at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                      \
+        at_[0].val.programmaticStreamSerializationAllowed = 1;                               \
+        cfg_.attrs = at_;                                                                    \
+        cfg_.numAttrs = 1;                                                                   \
+        cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__);                                        \
+        (ctx)->launches++;                                                                   \
+    } while (0)
+
 #define LAUNCH_CHECK(ctx) CU_CHECK(ctx, cudaGetLastError())
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: ncu costs ~170 ms per launch on this pool (save/restore of the resident buffers): 3000 launches of the bench = ~9 GPU-minutes.
 # Profiling pass of a round (run on the GPU box through gpurun): launch lists of the bench and of the full per-frame path,
 # one ncu --set full capture of the dominant kernel (k_brox_sor, finest level).  Outputs land in gpurun_out/.
 set -u
@@ -6,7 +7,7 @@ TAG=${1:-r1h}
 OUT=gpurun_out
 mkdir -p $OUT
 python bench.py --steps 3 --warmup 3 --headline-only > $OUT/${TAG}_bench_short.log 2>&1 || { echo "bench failed"; tail -5 $OUT/${TAG}_bench_short.log; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $OUT/${TAG}_launches_bench.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/${TAG}_launches_bench.csv \
     python bench.py --steps 3 --warmup 3 --headline-only > $OUT/${TAG}_ncu_bench.log 2>&1
 echo "bench launch list rc=$?"
 python tools/profile_detect.py 2 > $OUT/${TAG}_detect.log 2>&1 || { echo "profile_detect failed"; tail -5 $OUT/${TAG}_detect.log; exit 1; }
