@@ -14,10 +14,10 @@ value    : pairs/s, frames resident in HBM (device slots), CUDA-event time summe
            between steps (256 MiB write), max over ranks.
 e2e      : pairs/s through the host C-ABI call sindyn_flow_residual with pinned HOST buffers: H2D of the BGR frame
            and D2H of both masks inside the timed region.
-roofline : the temporally blocked red-black SOR kernel (k_brox_sor: 10 sweeps of one lagged-nonlinearity iteration of
+roofline : the temporally blocked red-black SOR kernel (k_brox_sor: 5 sweeps of one lagged-nonlinearity iteration of
            one pyramid level per launch) timed per launch with CUDA events on the handle's stream
-           (sindyn_brox_profile); algorithmic bytes = 10 sweeps x 52 B per pixel x the pixels one
-           launch covers.
+           (sindyn_brox_profile); algorithmic bytes = sweeps of the launch x 52 B per pixel x the
+           pixels one launch covers.
 cpu_baseline / --impl reference: the reference's CPU path restated in oracle/ (checker code), timed on the
            host cores of this box on a bounded sample of the same sequence.
 """
@@ -41,7 +41,7 @@ import numpy as np
 METRIC = "dyn-detect frame pairs/sec @640x480"
 UNIT = "pairs/s"
 N_FRAMES = 16
-ALGO_BYTES_PER_PX_SOR = 520.0   # 10 sweeps x 52 B (the 100 B coefficient preparation is k_brox_system's)
+ALGO_BYTES_PER_PX_SWEEP = 52.0   # 52 B per pixel and red-black sweep (the 100 B coefficient preparation is k_brox_system's)
 
 
 def peaks():
@@ -327,7 +327,7 @@ def run_ours(args):
         prof = sd.brox_profile()
         prof = sd.brox_profile()  # second call: warm
         peak, which = peaks()
-        algo_bytes = ALGO_BYTES_PER_PX_SOR * prof["pixel_levels"]
+        algo_bytes = ALGO_BYTES_PER_PX_SWEEP * prof["pixel_sweeps"]
         ach = algo_bytes / (prof["sor_ms"] * 1e-3) / 1e9
         stage = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=local, refine=refine, stage_timing=1)
         stage.set_prev_frames(frames[1].bgr, frames[0].bgr)
@@ -352,7 +352,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cam.width * cam.height * 3,
                     "d2h_bytes_per_step": 2 * cam.width * cam.height, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "kernel": "k_brox_sor (temporally blocked red-black SOR, 10 sweeps per launch; the 9 finest pyramid levels)",
+            "roofline": {"bound": "hbm", "kernel": "k_brox_sor (temporally blocked red-black SOR, 5 sweeps per launch; the 9 finest pyramid levels)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_from_profile(),
                          "peak_source": which, "algorithmic_bytes_per_launch": algo_bytes / max(prof["sor_launches"], 1),
                          "launches_per_solve": prof["sor_launches"], "avg_launch_us": 1e3 * prof["sor_ms"] / max(prof["sor_launches"], 1),

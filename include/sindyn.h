@@ -108,7 +108,8 @@ int sindyn_get_flow_results(sindyn_handle h, float *flow, double *H_out, float *
 /* Measurement hook (no reference equivalent): runs one Brox solve on the handle's resident frames
  * WITHOUT the CUDA graph, bracketing every launch of the tiled SOR kernel (k_brox_sor) with CUDA events
  * on the handle's stream.  out[0] = summed SOR-kernel ms, out[1] = number of SOR launches,
- * out[2] = whole-solve ms, out[3] = pixel-levels those launches processed (sum over launches of w*h). */
+ * out[2] = whole-solve ms, out[3] = pixel-sweeps those launches processed (sum over launches of
+ * w*h*sweeps of the launch). */
 int sindyn_brox_profile(sindyn_handle h, double *out4);
 
 /* Driver post-step: 15x15 ellipse dilation of the mask (rgbd_tum_noros.cc:108,136-139), and the

@@ -240,7 +240,7 @@ class SinDyn:
     def brox_profile(self):
         out = np.zeros(4, np.float64)
         self._ck(self.lib.sindyn_brox_profile(self.h, _p(out)), "brox_profile")
-        return dict(sor_ms=float(out[0]), sor_launches=int(out[1]), solve_ms=float(out[2]), pixel_levels=int(out[3]))
+        return dict(sor_ms=float(out[0]), sor_launches=int(out[1]), solve_ms=float(out[2]), pixel_sweeps=int(out[3]))
 
     def morph_ellipse(self, img, k, op):
         img = _u8(img)

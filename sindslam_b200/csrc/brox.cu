@@ -163,7 +163,10 @@ struct BroxInnerP {
     int nsweeps, n_inner;
 };
 
-constexpr int BROX_SMAX = 10, BROX_NT = 1024;
+#ifndef SINDYN_BROX_SMAX
+#define SINDYN_BROX_SMAX 5
+#endif
+constexpr int BROX_SMAX = SINDYN_BROX_SMAX, BROX_NT = 1024;   // sweeps fused into one k_brox_sor launch
 constexpr int BROX_RMAX = 2 * BROX_SMAX + 1;
 // Tile menu: a level uses the smallest tile whose grid still fits into one wave of 148 SMs -- the time of a launch is
 // the time of ONE CTA, which is proportional to the staged region (tile + 2 x 21 halo), so mid-size levels run on
@@ -543,20 +546,24 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
     BROX_CLK(0)
     // ---- stage (du, dv) and the edge weights of the whole region and the systems of the owned pixels with asynchronous
     // global -> shared copies (no register staging: every copy of the thread is in flight at once)
-    for (int r = tid; r < PP; r += BROX_NT) {
-        const int ly = r / PW, lx = r - ly * PW;
-        const int x = ox + lx, y = oy + ly;
-        const int ci = ((lx + ly) & 1) * NPCP + ly * HW + (lx >> 1);
-        if (x >= 0 && x < w && y >= 0 && y < h) {
-            const int g = y * w + x;
-            cp_async4(&s_uv[ci].x, p.dui + g);
-            cp_async4(&s_uv[ci].y, p.dvi + g);
-            cp_async4(&s_wr[ci], &p.W[g].x);
-            cp_async4(&s_wd[ci], &p.W[g].y);
-        } else {
-            s_uv[ci] = make_float2(0.0f, 0.0f);
-            s_wr[ci] = 0.0f;
-            s_wd[ci] = 0.0f;
+    // (rows over warps, columns over lanes: no index divisions, the copies of a warp are contiguous in global memory)
+    for (int ly = tid >> 5; ly < PH; ly += BROX_NT / 32) {
+        const int y = oy + ly;
+        const bool row_in = y >= 0 && y < h;
+        for (int lx = tid & 31; lx < PW; lx += 32) {
+            const int x = ox + lx;
+            const int ci = ((lx + ly) & 1) * NPCP + ly * HW + (lx >> 1);
+            if (row_in && x >= 0 && x < w) {
+                const int g = y * w + x;
+                cp_async4(&s_uv[ci].x, p.dui + g);
+                cp_async4(&s_uv[ci].y, p.dvi + g);
+                cp_async4(&s_wr[ci], &p.W[g].x);
+                cp_async4(&s_wd[ci], &p.W[g].y);
+            } else {
+                s_uv[ci] = make_float2(0.0f, 0.0f);
+                s_wr[ci] = 0.0f;
+                s_wd[ci] = 0.0f;
+            }
         }
     }
 #pragma unroll
@@ -785,7 +792,8 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
                 sp.dub = b->du[base]; sp.dvb = b->dv[base];
                 LAUNCH_PDL(ctx, k_brox_system, dim3(cdiv(w, BSY_W), cdiv(h, BSY_H)), dim3(BSY_W, BSY_H), 0, sp);
                 while (remaining > 0) {
-                    int ns = remaining < BROX_SMAX ? remaining : BROX_SMAX;
+                    const int chunks_left = cdiv(remaining, BROX_SMAX);
+                    const int ns = cdiv(remaining, chunks_left);   // balanced chunks of <= BROX_SMAX sweeps (10 -> 5 + 5)
                     int out = 0;
                     while (out == base || out == in) ++out;
                     q.dui = b->du[in]; q.dvi = b->dv[in];
@@ -800,7 +808,7 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
                     case 2: brox_launch_sor<BroxTile<24, 16>>(ctx, q); break;
                     default: brox_launch_sor<BroxTileL>(ctx, q); break;
                     }
-                    if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h; }
+                    if (prof) { cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream); b->prof_px += (long long)w * h * ns; }
                     in = out;
                     remaining -= ns;
                 }

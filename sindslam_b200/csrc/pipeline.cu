@@ -118,7 +118,7 @@ extern "C" int sindyn_brox_profile(sindyn_handle h, double *out4)
     if (!out4) return SINDYN_ERR_INVALID;
     if (!h->have_prev) { h->err = "brox_profile: call sindyn_set_prev_frames first"; return SINDYN_ERR_STATE; }
     BroxSolver *b = &h->brox;
-    const int cap = 2 * (b->nl * b->inner * ((b->solver + 9) / 10) + 4);
+    const int cap = 2 * (b->nl * b->inner * b->solver + 4);   // upper bound: one launch per sweep
     std::vector<cudaEvent_t> ev(cap + 2);
     for (auto &e : ev) CU_CHECK(h, cudaEventCreate(&e));
     b->prof_ev = ev.data(); b->prof_n = 0; b->prof_cap = cap; b->prof_px = 0;

@@ -71,8 +71,8 @@ def test_resident_equals_host_path(seq_c1):
         r = b.flow_results()
         assert np.array_equal(lo, r["low"]) and np.array_equal(hi, r["high"])
     p = b.brox_profile()
-    # k_brox_sor runs the 9 finest of the 15 levels (> 2100 px), one launch per inner iteration; the 6 coarsest levels run
-    # all inner iterations in one k_brox_level launch
-    assert p["sor_launches"] == 90 and p["pixel_levels"] == 10 * 302822 and p["sor_ms"] > 0
+    # k_brox_sor runs the 9 finest of the 15 levels (> 2100 px), two launches of 5 sweeps per inner iteration; the 6 coarsest
+    # levels run all inner iterations in one k_brox_level launch
+    assert p["sor_launches"] == 180 and p["pixel_sweeps"] == 100 * 302822 and p["sor_ms"] > 0
     a.close()
     b.close()
