@@ -116,53 +116,6 @@ __global__ void k_mag_u8_hist(const float *__restrict__ mag, int n, const unsign
         if (sh[j]) atomicAdd(&hist[j], sh[j]);
 }
 
-__device__ double otsu_8u(const unsigned int *h, int total)
-{
-    double mu = 0, scale = 1. / (double)total;
-    for (int i = 0; i < 256; i++) mu += i * (double)h[i];
-    mu *= scale;
-    double mu1 = 0, q1 = 0, max_sigma = 0, max_val = 0;
-    for (int i = 0; i < 256; i++) {
-        double p_i = h[i] * scale;
-        mu1 *= q1;
-        q1 += p_i;
-        double q2 = 1. - q1;
-        if (fmin(q1, q2) < FLT_EPSILON || fmax(q1, q2) > 1. - FLT_EPSILON) continue;
-        mu1 = (mu1 + i * p_i) / q1;
-        double mu2 = (mu - q1 * mu1) / q2;
-        double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
-        if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
-    }
-    return max_val;
-}
-
-__device__ double triangle_8u(const unsigned int *hin, int *h /*256 scratch*/)
-{
-    for (int i = 0; i < 256; i++) h[i] = (int)hin[i];
-    int left_bound = 0, right_bound = 0, max_ind = 0, mx = 0;
-    bool flipped = false;
-    for (int i = 0; i < 256; i++) if (h[i] > 0) { left_bound = i; break; }
-    if (left_bound > 0) left_bound--;
-    for (int i = 255; i > 0; i--) if (h[i] > 0) { right_bound = i; break; }
-    if (right_bound < 255) right_bound++;
-    for (int i = 0; i < 256; i++) if (h[i] > mx) { mx = h[i]; max_ind = i; }
-    if (max_ind - left_bound < right_bound - max_ind) {
-        flipped = true;
-        int i = 0, j = 255;
-        while (i < j) { int t = h[i]; h[i] = h[j]; h[j] = t; i++; j--; }
-        left_bound = 255 - right_bound;
-        max_ind = 255 - max_ind;
-    }
-    double thresh = left_bound, a = mx, b = left_bound - max_ind, dist = 0;
-    for (int i = left_bound + 1; i <= max_ind; i++) {
-        double t = a * i + b * h[i];
-        if (t > dist) { dist = t; thresh = i; }
-    }
-    thresh--;
-    if (flipped) thresh = 255 - thresh;
-    return thresh;
-}
-
 __device__ int count_above(const unsigned int *h, float t)
 {
     int c = 0;
@@ -171,18 +124,108 @@ __device__ int count_above(const unsigned int *h, float t)
 }
 
 // thr[0]=otsu thr[1]=triangle thr[2]=t_low thr[3]=t_high (DynaDetect.cc:1284-1367)
-__global__ void k_thresholds(const unsigned int *__restrict__ hist, const unsigned int *__restrict__ gmax, int W, int H,
-                             float *__restrict__ thr)
+//
+// One CTA of 256 threads.  Otsu's class statistics (q1, mu1) are a serial floating-point recurrence with a division per bin,
+// so bit-exactness pins them to ONE thread; everything around it is order independent and runs in parallel under that
+// chain: the between-class variance of every bin + first-maximum search (all threads, after the chain), and the whole
+// Triangle threshold (warp 1: bounds, first maximum, distance arg-max are exact integer-valued computations).
+__global__ void __launch_bounds__(256) k_thresholds(const unsigned int *__restrict__ hist, const unsigned int *__restrict__ gmax, int W, int H,
+                                                    float *__restrict__ thr)
 {
-    __shared__ int scratch[256];
     __shared__ unsigned int sh[256];
-    for (int j = threadIdx.x; j < 256; j += blockDim.x) sh[j] = hist[j];   // one coalesced read instead of ~1500 serial global loads
+    __shared__ double s_q1[256], s_mu1[256];
+    __shared__ unsigned char s_ok[256];
+    __shared__ double s_sig[8];
+    __shared__ int s_idx[8];
+    __shared__ double s_mu;
+    __shared__ float s_tri;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    sh[tid] = hist[tid];
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    hist = sh;
     const int total = W * H;
-    float thred1 = (float)otsu_8u(hist, total);
-    float thred2 = (float)triangle_8u(hist, scratch);
+    const double scale = 1. / (double)total;
+    if (tid == 0) {
+        // serial part of cv::threshold(THRESH_OTSU) (getThreshVal_Otsu_8u): q1 / mu1 recurrence
+        double mu1 = 0, q1 = 0;
+        for (int i = 0; i < 256; i++) {
+            const double p_i = sh[i] * scale;
+            mu1 *= q1;
+            q1 += p_i;
+            const double q2 = 1. - q1;
+            if (fmin(q1, q2) < FLT_EPSILON || fmax(q1, q2) > 1. - FLT_EPSILON) { s_ok[i] = 0; continue; }
+            mu1 = (mu1 + i * p_i) / q1;
+            s_q1[i] = q1; s_mu1[i] = mu1; s_ok[i] = 1;
+        }
+    } else if (wid == 1) {
+        // cv::threshold(THRESH_TRIANGLE) (getThreshVal_Triangle_8u); lane l owns bins 8l .. 8l+7
+        int first = 256, last = 0, mx = 0, mi = 0;
+        for (int k = 0; k < 8; ++k) {
+            const int i = 8 * lane + k, v = (int)sh[i];
+            if (v > 0) { first = min(first, i); if (i > 0) last = max(last, i); }
+            if (v > mx) { mx = v; mi = i; }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
+            last = max(last, __shfl_xor_sync(0xffffffffu, last, off));
+            const int om = __shfl_xor_sync(0xffffffffu, mx, off), oi = __shfl_xor_sync(0xffffffffu, mi, off);
+            if (om > mx || (om == mx && oi < mi)) { mx = om; mi = oi; }   // first index of the maximum
+        }
+        int left_bound = first < 256 ? first : 0, right_bound = last, max_ind = mi;
+        if (left_bound > 0) left_bound--;
+        if (right_bound < 255) right_bound++;
+        const bool flipped = max_ind - left_bound < right_bound - max_ind;
+        if (flipped) { left_bound = 255 - right_bound; max_ind = 255 - max_ind; }
+        // distance arg-max over (left_bound, max_ind]: a*i + b*h[i] is integer valued (exact in double), first maximum wins,
+        // and it has to exceed 0 to move the threshold off left_bound
+        const double a = mx, b2 = left_bound - max_ind;
+        double bd = 0;
+        int bi = -1;
+        for (int k = 0; k < 8; ++k) {
+            const int i = 8 * lane + k;
+            if (i > left_bound && i <= max_ind) {
+                const double t = a * i + b2 * (double)(int)sh[flipped ? 255 - i : i];
+                if (t > bd) { bd = t; bi = i; }
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (oi >= 0 && (od > bd || (od == bd && (bi < 0 || oi < bi)))) { bd = od; bi = oi; }
+        }
+        double thresh = bi >= 0 ? bi : left_bound;
+        thresh--;
+        if (flipped) thresh = 255 - thresh;
+        if (lane == 0) s_tri = (float)thresh;
+    } else if (wid == 2) {
+        // mean of the histogram: integer-valued partial sums, exact in any order
+        double m = 0;
+        for (int k = 0; k < 8; ++k) m += (8 * lane + k) * (double)sh[8 * lane + k];
+        for (int off = 16; off > 0; off >>= 1) m += __shfl_xor_sync(0xffffffffu, m, off);
+        if (lane == 0) s_mu = m * scale;
+    }
+    __syncthreads();
+    // between-class variance of every bin, first maximum (it has to exceed 0)
+    double sigma = 0;
+    int si = -1;
+    if (s_ok[tid]) {
+        const double q1 = s_q1[tid], mu1 = s_mu1[tid], q2 = 1. - q1;
+        const double mu2 = (s_mu - q1 * mu1) / q2;
+        const double sg = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+        if (sg > 0) { sigma = sg; si = tid; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, sigma, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, si, off);
+        if (oi >= 0 && (os > sigma || (os == sigma && (si < 0 || oi < si)))) { sigma = os; si = oi; }
+    }
+    if (lane == 0) { s_sig[wid] = sigma; s_idx[wid] = si; }
+    __syncthreads();
+    if (tid != 0) return;
+    for (int k = 1; k < 8; ++k)
+        if (s_idx[k] >= 0 && (s_sig[k] > sigma || (s_sig[k] == sigma && (si < 0 || s_idx[k] < si)))) { sigma = s_sig[k]; si = s_idx[k]; }
+    const unsigned int *h = sh;
+    float thred1 = (float)(si >= 0 ? si : 0);
+    float thred2 = s_tri;
     thr[0] = thred1;
     thr[1] = thred2;
     const float maxErrorf = __uint_as_float(*gmax);
@@ -190,7 +233,7 @@ __global__ void k_thresholds(const unsigned int *__restrict__ hist, const unsign
     if (thred1 < thred2) {
         if (thred1 < 1.7f * 255.0f / maxErrorf) thred1 = 1.7f * 255.0f / maxErrorf;
         else if (thred1 > 3.0f * 255.0f / maxErrorf) thred1 = 3.0f * 255.0f / maxErrorf;
-        if ((double)count_above(hist, thred1) > 0.5 * W * H) thred1 = thred1 + 0.2f * 255.0f / maxErrorf;
+        if ((double)count_above(h, thred1) > 0.5 * W * H) thred1 = thred1 + 0.2f * 255.0f / maxErrorf;
         float m = fmaxf(3.0f * 255.0f / maxErrorf, thred1 * 1.2f);
         if (thred2 < m) thred2 = m;
         else if (thred2 > 10.0f * 255.0f / maxErrorf) thred2 = 10.0f * 255.0f / maxErrorf;
@@ -236,7 +279,7 @@ static int residual_tail(sindyn_base *ctx, ResidualStage *r, uint8_t *low, uint8
 {
     const int n = r->W * r->H;
     LAUNCH(ctx, k_mag_u8_hist, SINDYN_NUM_SMS_B200 * 2, 256, 0, r->mag, n, r->gmax, r->m8, r->hist);
-    LAUNCH(ctx, k_thresholds, 1, 32, 0, r->hist, r->gmax, r->W, r->H, r->thr);
+    LAUNCH(ctx, k_thresholds, 1, 256, 0, r->hist, r->gmax, r->W, r->H, r->thr);
     LAUNCH(ctx, k_masks, cdiv(n, 256), 256, 0, r->m8, n, r->thr, low, high);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;

@@ -87,6 +87,39 @@ def test_residual_homography_masks_bit_exact(sd, seq_c1):
         assert np.array_equal(hi, ohi)
 
 
+def test_threshold_histogram_shapes_bit_exact(sd):
+    """Otsu / Triangle / clamp logic (DynaDetect.cc:1284-1367) on residual histograms of very different shapes -- with H = I the
+    flow IS the residual.  Covers the flipped and the non-flipped Triangle branch, a single populated bin, a two-spike
+    histogram, a ramp and heavy tails; thresholds and masks must equal cv2's bit for bit."""
+    H, W = sd.H, sd.W
+    rng = np.random.default_rng(11)
+    n = H * W
+    shapes = {
+        "constant": np.full(n, 3.0),
+        "two_spikes": np.where(rng.random(n) < 0.2, 9.0, 1.0),
+        "ramp": np.linspace(0.0, 12.0, n),
+        "right_peak": 10.0 - np.abs(rng.normal(0, 1.0, n)),           # maximum bin near 255: non-flipped Triangle
+        "left_peak": np.abs(rng.normal(0, 0.4, n)) + (rng.random(n) < 0.01) * 20.0,   # flipped Triangle
+        "exp_tail": rng.exponential(1.5, n),
+        "mostly_zero": (rng.random(n) < 0.03) * rng.uniform(0, 5, n),
+        "majority_high": np.where(rng.random(n) < 0.7, rng.uniform(4, 6, n), rng.uniform(0, 1, n)),   # > 50 % above t_low
+    }
+    for name, m in shapes.items():
+        flow = np.zeros((H, W, 2), np.float32)
+        ang = rng.uniform(0, 2 * np.pi, n)
+        m = np.maximum(m, 0).astype(np.float64)
+        m[rng.integers(0, n)] = max(m.max(), 1e-3)   # keep the maximum positive
+        flow[..., 0] = (m * np.cos(ang)).reshape(H, W)
+        flow[..., 1] = (m * np.sin(ang)).reshape(H, W)
+        mag, lo, hi, thr = sd.residual_homography(flow, np.eye(3))
+        omag = orc.homography_residual(flow, np.eye(3))
+        olo, ohi, othr, _ = orc.threshold_masks(omag)
+        print(name, "thr gpu", thr, "oracle", othr)
+        assert np.array_equal(mag, omag)
+        assert np.array_equal(thr, othr), name
+        assert np.array_equal(lo, olo) and np.array_equal(hi, ohi), name
+
+
 def test_residual_pose_variant(sd, seq_c1):
     scene, frames = seq_c1
     cam = synth.TUM3
