@@ -262,6 +262,33 @@ int sindyn_orb_frame_features(sindyn_orb_handle h, const uint16_t *depth_raw, si
                               float *keys_un, float *depth_out, float *u_right_out, float *bounds_out, int *grid_offsets,
                               int *grid_indices, int capacity, int *n_out);
 
+/* ---- "next" row f3: per-keyframe point-cloud generation of the dense-map consumer
+ * (octomap_pub/src/pubPointCloud.cc, SubscribeAndPublish::generatePointCloud).  The octree insertion itself
+ * (octomap::ColorOcTree) is third-party host code and stays with the caller.
+ * Point layout: 16 bytes (x, y, z in the world frame, b, g, r); NaN coordinates mark rejected pixels exactly as the
+ * reference's non-dense pcl::PointCloud does.  Poses are row-major 4 x 4 doubles.  intr5 = {fx, fy, cx, cy, depthScale}
+ * as the node reads them (doubles); NULL = the handle's configuration. */
+typedef struct sindyn_point {
+    float x, y, z;
+    uint8_t b, g, r, a;
+} sindyn_point;
+/* Single-frame overload (pubPointCloud.cc:392-470): every 3rd pixel; mask >= 240 or depth outside [0.01, 10] m -> NaN
+ * point; colour from the BGR image; pcl::transformPointCloud by Twc.  points_out holds ceil(H/3)*ceil(W/3) points. */
+int sindyn_cloud_single(sindyn_handle h, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step,
+                        const uint8_t *mask, size_t mask_step, const double *Twc16, const double *intr5, sindyn_point *points_out,
+                        int *n_out);
+/* Cross-frame consistency overload (pubPointCloud.cc:471-678): every 2nd pixel is re-projected into the previous key frame
+ * (T_rel = poseRelative), a pixel votes "occluded" for its K-means cluster when the depths disagree by more than 13 % or the
+ * previous mask was dynamic (> 240); clusters i >= 1 with occlusion_i * 9 > 0.4 * |label == i| are dropped from the cloud
+ * and painted 255 into mask_new (imgDynaMaskNew); the kept clusters are concatenated in cluster order, raster order inside
+ * a cluster, and transformed by Twc.  points_out holds up to ceil(H/2)*ceil(W/2) points.
+ * stats36_out (optional) = occlusion[12] | countNonZero(label == i)[12] | kept[12]; depth_new_out (optional) = imgDepthNew. */
+int sindyn_cloud_consistent(sindyn_handle h, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step,
+                            const uint16_t *depth_last, size_t depth_last_step, const uint8_t *mask, size_t mask_step,
+                            const uint8_t *mask_last, size_t mask_last_step, const uint8_t *label, size_t label_step,
+                            const double *T_rel16, const double *Twc16, const double *intr5, sindyn_point *points_out, int *n_out,
+                            uint8_t *mask_new_out, size_t mask_new_step, int *stats36_out, uint16_t *depth_new_out);
+
 const char *sindyn_version(void);
 
 #ifdef __cplusplus

@@ -285,4 +285,77 @@ protected:
 
 }  // namespace ORB_SLAM2
 
+namespace sindyn {
+
+// Mirrors the two SubscribeAndPublish::generatePointCloud overloads of the dense-map consumer
+// (octomap_pub/src/pubPointCloud.cc:392-470 and :471-678): same argument order and meaning; the result is returned instead of
+// being left in the node's tempCloudOneFrame member, and imgDynaMaskNew (a local of the reference) is handed out on request.
+// Poses are row-major 4 x 4 doubles (Eigen::Isometry3d::matrix() / Eigen::Matrix4d are column-major: pass the transpose or use
+// the Eigen overload a binding adds).
+class PointCloudGenerator {
+public:
+    PointCloudGenerator(int width, int height, double fx, double fy, double cx, double cy, double depthScale, int device = 0)
+    {
+        sindyn_config cfg;
+        sindyn_default_config(&cfg, width, height);
+        cfg.fx = (float)fx; cfg.fy = (float)fy; cfg.cx = (float)cx; cfg.cy = (float)cy; cfg.depth_scale = (float)depthScale;
+        cfg.device = device;
+        cfg.plane_edges = 0; cfg.refine = 0;
+        intr_[0] = fx; intr_[1] = fy; intr_[2] = cx; intr_[3] = cy; intr_[4] = depthScale;
+        int st = sindyn_create(&cfg, &h_);
+        if (st != SINDYN_OK) throw Error(st, std::string("sindyn_create: ") + (h_ ? sindyn_last_error(h_) : "no handle (is a CUDA device present?)"));
+        width_ = width; height_ = height;
+    }
+    ~PointCloudGenerator() { if (h_) sindyn_destroy(h_); }
+    PointCloudGenerator(const PointCloudGenerator &) = delete;
+    PointCloudGenerator &operator=(const PointCloudGenerator &) = delete;
+
+    // pubPointCloud.cc:392-470
+    std::vector<sindyn_point> generatePointCloud(const ImageView &imgRGB, const ImageView &imgDepth, const ImageView &imgDynaMask, const double *Twc)
+    {
+        need(imgRGB, 3, 1, "imgRGB"); need(imgDepth, 1, 2, "imgDepth"); need(imgDynaMask, 1, 1, "imgDynaMask");
+        std::vector<sindyn_point> out((size_t)((height_ + 2) / 3) * ((width_ + 2) / 3));
+        int n = 0;
+        check(sindyn_cloud_single(h_, (const uint8_t *)imgRGB.data, imgRGB.step, (const uint16_t *)imgDepth.data, imgDepth.step,
+                                  (const uint8_t *)imgDynaMask.data, imgDynaMask.step, Twc, intr_, out.data(), &n), "sindyn_cloud_single");
+        out.resize((size_t)n);
+        return out;
+    }
+    // pubPointCloud.cc:471-678
+    std::vector<sindyn_point> generatePointCloud(const ImageView &imgRGB, const ImageView &imgDepth, const ImageView &imgDepthLast,
+                                                 const ImageView &imgDynaMask, const ImageView &imgDynaMaskLast, const ImageView &imgLabel,
+                                                 const double *poseRelative, const double *Twc, Image *imgDynaMaskNew = nullptr)
+    {
+        need(imgRGB, 3, 1, "imgRGB"); need(imgDepth, 1, 2, "imgDepth"); need(imgDepthLast, 1, 2, "imgDepthLast");
+        need(imgDynaMask, 1, 1, "imgDynaMask"); need(imgDynaMaskLast, 1, 1, "imgDynaMaskLast"); need(imgLabel, 1, 1, "imgLabel");
+        std::vector<sindyn_point> out((size_t)((height_ + 1) / 2) * ((width_ + 1) / 2));
+        if (imgDynaMaskNew) imgDynaMaskNew->create(height_, width_);
+        int n = 0;
+        check(sindyn_cloud_consistent(h_, (const uint8_t *)imgRGB.data, imgRGB.step, (const uint16_t *)imgDepth.data, imgDepth.step,
+                                      (const uint16_t *)imgDepthLast.data, imgDepthLast.step, (const uint8_t *)imgDynaMask.data, imgDynaMask.step,
+                                      (const uint8_t *)imgDynaMaskLast.data, imgDynaMaskLast.step, (const uint8_t *)imgLabel.data, imgLabel.step,
+                                      poseRelative, Twc, intr_, out.data(), &n, imgDynaMaskNew ? imgDynaMaskNew->ptr() : nullptr,
+                                      imgDynaMaskNew ? imgDynaMaskNew->step() : 0, nullptr, nullptr),
+              "sindyn_cloud_consistent");
+        out.resize((size_t)n);
+        return out;
+    }
+
+private:
+    void need(const ImageView &v, int ch, int eb, const char *name) const
+    {
+        if (v.empty() || v.rows != height_ || v.cols != width_ || v.channels != ch || v.elem_bytes != eb)
+            throw Error(SINDYN_ERR_INVALID, std::string("generatePointCloud: ") + name + " has the wrong size or type");
+    }
+    void check(int st, const char *what) const
+    {
+        if (st != SINDYN_OK) throw Error(st, std::string(what) + ": " + sindyn_last_error(h_));
+    }
+    sindyn_handle h_ = nullptr;
+    int width_ = 0, height_ = 0;
+    double intr_[5];
+};
+
+}  // namespace sindyn
+
 #endif  // SINDYN_CLASSES_HPP

@@ -93,6 +93,8 @@ SIGNATURES = {
     "sindyn_orb_get_candidates": (_i, [_vp, _i, _vp, _i, _ip]),
     "sindyn_orb_get_plane": (_i, [_vp, _i, _i, _vp, _ip, _ip]),
     "sindyn_orb_frame_features": (_i, [_vp, _vp, _sz, C.POINTER(FrameParams), _vp, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
+    "sindyn_cloud_single": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _ip]),
+    "sindyn_cloud_consistent": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _ip, _vp, _sz, _vp, _vp]),
     "sindyn_orb_set_stream": (_i, [_vp, _vp]),
     "sindyn_orb_launch_count": (C.c_ulonglong, [_vp]),
     "sindyn_orb_last_error": (C.c_char_p, [_vp]),
@@ -247,6 +249,40 @@ class SinDyn:
         out = np.empty_like(img)
         self._ck(self.lib.sindyn_morph_ellipse(self.h, _p(img), img.strides[0], _p(out), out.strides[0], img.shape[1], img.shape[0], k, op), "morph")
         return out
+
+    # -- dense-map consumer (row f3): pubPointCloud.cc generatePointCloud
+    POINT_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("z", np.float32), ("b", np.uint8), ("g", np.uint8), ("r", np.uint8), ("a", np.uint8)])
+
+    @staticmethod
+    def _intr(intr):
+        return None if intr is None else np.ascontiguousarray(intr, np.float64)
+
+    def cloud_single(self, bgr, depth, mask, Twc, intr=None):
+        bgr, depth, mask = _u8(bgr), np.ascontiguousarray(depth, np.uint16), _u8(mask)
+        Twc = np.ascontiguousarray(Twc, np.float64)
+        out = np.empty(((self.H + 2) // 3) * ((self.W + 2) // 3), self.POINT_DTYPE)
+        n = C.c_int(0)
+        k = self._intr(intr)
+        self._ck(self.lib.sindyn_cloud_single(self.h, _p(bgr), bgr.strides[0], _p(depth), depth.strides[0], _p(mask), mask.strides[0], _p(Twc),
+                                              _p(k) if k is not None else None, _p(out), C.byref(n)), "cloud_single")
+        return out[: n.value]
+
+    def cloud_consistent(self, bgr, depth, depth_last, mask, mask_last, label, T_rel, Twc, intr=None):
+        bgr, mask, mask_last, label = _u8(bgr), _u8(mask), _u8(mask_last), _u8(label)
+        depth, depth_last = np.ascontiguousarray(depth, np.uint16), np.ascontiguousarray(depth_last, np.uint16)
+        T_rel, Twc = np.ascontiguousarray(T_rel, np.float64), np.ascontiguousarray(Twc, np.float64)
+        out = np.empty(((self.H + 1) // 2) * ((self.W + 1) // 2), self.POINT_DTYPE)
+        mask_new = np.empty((self.H, self.W), np.uint8)
+        depth_new = np.empty((self.H, self.W), np.uint16)
+        stats = np.zeros(36, np.int32)
+        n = C.c_int(0)
+        k = self._intr(intr)
+        self._ck(self.lib.sindyn_cloud_consistent(self.h, _p(bgr), bgr.strides[0], _p(depth), depth.strides[0], _p(depth_last), depth_last.strides[0],
+                                                  _p(mask), mask.strides[0], _p(mask_last), mask_last.strides[0], _p(label), label.strides[0],
+                                                  _p(T_rel), _p(Twc), _p(k) if k is not None else None, _p(out), C.byref(n), _p(mask_new),
+                                                  mask_new.strides[0], _p(stats), _p(depth_new)), "cloud_consistent")
+        return dict(points=out[: n.value], mask_new=mask_new, occlusion=stats[:12].copy(), label_count=stats[12:24].copy(),
+                    kept=stats[24:36].astype(bool), depth_new=depth_new)
 
     # -- stage level
     def flow_brox(self, I0, I1):

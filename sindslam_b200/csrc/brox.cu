@@ -489,7 +489,7 @@ struct BroxSorP {
 template <class T>
 __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
 {
-    constexpr int PW = T::PW, PH = T::PH, HW = T::HW, NPC = T::NPC, M = T::M, PP = T::PP, G = T::G, NPCP = T::NPCP;
+    constexpr int PW = T::PW, PH = T::PH, HW = T::HW, NPC = T::NPC, M = T::M, G = T::G, NPCP = T::NPCP;
     extern __shared__ float4 sm4[];
     float2 *s_uv = (float2 *)sm4 + G;                               // [2][NPCP] (du, dv) by colour, zero guards
     float *s_wr = (float *)((float2 *)sm4 + 2 * NPCP) + G;          // [2][NPCP]

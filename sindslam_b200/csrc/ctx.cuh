@@ -72,6 +72,8 @@ struct sindyn_ctx : sindyn_base {
     cudaStream_t stream3 = nullptr;   // PEAC plane fitter, concurrent with k-means / gradient edges
     cudaEvent_t ev_peac_fork = nullptr, ev_peac_join = nullptr;
 
+    struct CloudStage *cloud = nullptr;   // dense-map consumer stage (cloud.cu), allocated on first use
+
     float stage_ms[16] = {};
     cudaEvent_t ev[24] = {};
     bool ev_ok = false;
@@ -89,3 +91,4 @@ void flow_tail_drop_graphs(sindyn_ctx *c);                 // flow.cu
 int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll);  // pipeline.cu
 int sindyn_ctx_init_stages(sindyn_ctx *c);              // stages.cu
 void sindyn_ctx_destroy_stages(sindyn_ctx *c);          // stages.cu
+void cloud_stage_destroy(sindyn_ctx *c);                // cloud.cu

@@ -25,6 +25,7 @@ int sindyn_ctx_init_stages(sindyn_ctx *c)
 }
 void sindyn_ctx_destroy_stages(sindyn_ctx *c)
 {
+    cloud_stage_destroy(c);
     if (c->cluster_graph) cudaGraphExecDestroy(c->cluster_graph);
     if (c->ev_flag) cudaEventDestroy(c->ev_flag);
     if (c->stream2) cudaStreamDestroy(c->stream2);
