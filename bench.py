@@ -186,19 +186,44 @@ def full_pipeline_stats(cam, frames, device, refine):
     grays = [cv2.cvtColor(f.bgr, cv2.COLOR_RGB2GRAY) for f in frames]
     acc = np.zeros(16)
     n = 0
-    t_det = t_orb = 0.0
+    t_det = t_orb = t_ff = t_cloud = 0.0
     nkp = 0
+    prev = last_pts = None
+    t_match = 0.0
     for k in range(2, len(frames)):
         t0 = time.perf_counter()
         mask, label = sd.detect(frames[k].bgr, frames[k].depth, k)
         mask = sd.morph_ellipse(mask, 15, 0)
         t1 = time.perf_counter()
-        kps, _ = orb.extract(grays[k], mask)
+        kps, kdesc = orb.extract(grays[k], mask)
         t2 = time.perf_counter()
+        # the "next" rows downstream of the path (not part of pairs_per_s): Frame construction (f2), dense-map cloud (f3)
+        un, dep, _, _, _, _ = orb.frame_features(frames[k].depth, cam.fx, cam.fy, cam.cx, cam.cy, (0.0, 0.0, 0.0, 0.0, 0.0), 40.0, 1.0 / cam.depth_factor)
+        t3 = time.perf_counter()
+        # frame-to-frame descriptor matching (f4) against the previous frame's key points as map points
+        t_m0 = time.perf_counter()
+        if last_pts is not None:
+            orb.search_by_projection(last_pts, np.linalg.inv(frames[k].T_wc), np.linalg.inv(frames[k - 1].T_wc), cam.fx, cam.fy, cam.cx, cam.cy,
+                                     40.0, 40.0 / cam.fx, 15.0)
+        t_m1 = time.perf_counter()
+        nk = len(kps)
+        z = dep[:nk]
+        pc = np.stack([(un[:nk, 0] - cam.cx) * z / cam.fx, (un[:nk, 1] - cam.cy) * z / cam.fy, z, np.ones(nk)], 1)
+        last_pts = dict(xyz_w=(frames[k].T_wc @ pc.T).T[:, :3].astype(np.float32), valid=z > 0, desc=kdesc, octave=kps["octave"], angle=kps["angle"],
+                        observed=np.zeros(nk, bool))
+        t3b = time.perf_counter()
+        if prev is not None:
+            T_rel = np.linalg.inv(frames[prev[0]].T_wc) @ frames[k].T_wc
+            sd.cloud_consistent(frames[k].bgr, frames[k].depth, frames[prev[0]].depth, mask, prev[1], label, T_rel, frames[k].T_wc)
+        t4 = time.perf_counter()
+        prev = (k, mask)
         if k >= 4:
             acc += sd.stage_ms()
             t_det += t1 - t0
             t_orb += t2 - t1
+            t_ff += t3 - t2
+            t_cloud += t4 - t3b
+            t_match += t_m1 - t_m0
             nkp += len(kps)
             n += 1
     sd.close()
@@ -209,7 +234,10 @@ def full_pipeline_stats(cam, frames, device, refine):
     return {"workload": "sindyn_detect + 15x15 dilation + masked ORB (1500 features, 8 levels) per frame, host buffers",
             "pairs_per_s": n / (t_det + t_orb), "detect_ms_wall": 1e3 * t_det / n, "orb_ms_wall": 1e3 * t_orb / n,
             "keypoints_per_frame": nkp / n, "stage_ms_device": {nm: float(acc[i]) for i, nm in enumerate(names)},
-            "plane_edges": True}
+            "plane_edges": True,
+            "next_rows_ms_wall": {"f2_frame_features": 1e3 * t_ff / n, "f3_cloud_consistent": 1e3 * t_cloud / n,
+                                  "f4_search_by_projection": 1e3 * t_match / n,
+                                  "note": "host C-ABI calls with pageable numpy buffers (H2D + D2H inside), not counted in pairs_per_s"}}
 
 
 def multi_sequence_stats(cam, device, refine, n_seq=4, steps=24):

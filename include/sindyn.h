@@ -262,6 +262,34 @@ int sindyn_orb_frame_features(sindyn_orb_handle h, const uint16_t *depth_raw, si
                               float *keys_un, float *depth_out, float *u_right_out, float *bounds_out, int *grid_offsets,
                               int *grid_indices, int capacity, int *n_out);
 
+/* ---- "next" row f4: frame-to-frame descriptor matching of Tracking::TrackWithMotionModel.
+ * Replaces ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+ * (src/ORBmatcher.cc:1328-1470) with ORBmatcher::DescriptorDistance (:1647-1665), ComputeThreeMaxima (:1601-1643) and
+ * Frame::GetFeaturesInArea (src/Frame.cc:398-452).
+ * CurrentFrame = the frame resident in the handle (last sindyn_orb_extract + sindyn_orb_frame_features: mvKeysUn, mvuRight,
+ * mDescriptors, mGrid, image bounds, mvScaleFactors).  LastFrame arrives as arrays over its n_last key points:
+ *   last_valid[i]    = (mvpMapPoints[i] != NULL && !mvbOutlier[i])
+ *   last_xyz_world   = pMP->GetWorldPos()        (n_last x 3 float)
+ *   last_desc        = pMP->GetDescriptor()      (n_last x 32 bytes)
+ *   last_octave[i]   = LastFrame.mvKeys[i].octave,  last_angle[i] = LastFrame.mvKeysUn[i].angle
+ *   last_observed[i] = (pMP->Observations() > 0)
+ * cur_blocked (optional, n_cur bytes) = (CurrentFrame.mvpMapPoints[i2] != NULL && Observations() > 0) on entry; NULL = none
+ * (TrackWithMotionModel clears the vector first, Tracking.cc:876).
+ * match_out[i2] = index i of the last-frame point whose map point was assigned to current key point i2, or -1;
+ * *nmatches_out = the function's return value.  Poses are row-major 4 x 4 floats (cv::Mat CV_32F mTcw). */
+typedef struct sindyn_match_params {
+    float fx, fy, cx, cy;          /* CurrentFrame intrinsics */
+    float bf, b;                   /* mbf, mb */
+    float Tcw_cur[16], Tcw_last[16];
+    float th;                      /* search radius factor (15 for RGB-D, Tracking.cc:884) */
+    int mono;                      /* bMono */
+    int check_orientation;         /* ORBmatcher::mbCheckOrientation */
+} sindyn_match_params;
+int sindyn_orb_search_by_projection(sindyn_orb_handle h, const sindyn_match_params *params, int n_last, const float *last_xyz_world,
+                                    const uint8_t *last_valid, const uint8_t *last_desc, const int *last_octave, const float *last_angle,
+                                    const uint8_t *last_observed, const uint8_t *cur_blocked, int *match_out, int capacity,
+                                    int *n_cur_out, int *nmatches_out);
+
 /* ---- "next" row f3: per-keyframe point-cloud generation of the dense-map consumer
  * (octomap_pub/src/pubPointCloud.cc, SubscribeAndPublish::generatePointCloud).  The octree insertion itself
  * (octomap::ColorOcTree) is third-party host code and stays with the caller.

@@ -256,6 +256,9 @@ public:
     std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+    // the C-ABI handle (the frame of the last operator() / ComputeFrameFeatures call is resident in it) and its key point capacity
+    sindyn_orb_handle handle() const { return h_; }
+    int capacity() const { return nfeatures * 2 + 64; }
 
     std::vector<sindyn::Image> mvImagePyramid;   // ORBextractor.h:88
     bool keepPyramidOnHost = true;               // set to false to skip the device-to-host copy of the 8 levels
@@ -281,6 +284,47 @@ protected:
     int device_ = 0, w_ = 0, h_img_ = 0;
     std::vector<sindyn_keypoint> kp_;
     std::vector<uint8_t> desc_;
+};
+
+// Mirrors ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+// (include/ORBmatcher.h:52-54, src/ORBmatcher.cc:1328-1470).  CurrentFrame is the frame resident in `extractor` (operator() +
+// ComputeFrameFeatures); LastFrame's map points are handed over as arrays (see sindyn_orb_search_by_projection).
+class ORBmatcher {
+public:
+    static const int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 30;   // ORBmatcher.cc:37-39
+    ORBmatcher(float nnratio = 0.6f, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+    struct LastFramePoints {   // one entry per key point of LastFrame
+        std::vector<float> xyz_world;        // 3 per point: pMP->GetWorldPos()
+        std::vector<uint8_t> valid;          // mvpMapPoints[i] != NULL && !mvbOutlier[i]
+        std::vector<uint8_t> desc;           // 32 per point: pMP->GetDescriptor()
+        std::vector<int> octave;             // mvKeys[i].octave
+        std::vector<float> angle;            // mvKeysUn[i].angle
+        std::vector<uint8_t> observed;       // pMP->Observations() > 0
+    };
+    // params: intrinsics / mbf / mb of CurrentFrame and both poses (mono and check_orientation are filled in here).
+    // vMatches[i2] = index into LastFrame of the map point assigned to current key point i2, or -1.  Returns nmatches.
+    int SearchByProjection(ORBextractor &extractor, const LastFramePoints &LastFrame, sindyn_match_params params, const float th, const bool bMono,
+                           std::vector<int> &vMatches, const std::vector<uint8_t> *currentBlocked = nullptr)
+    {
+        const int n_last = (int)LastFrame.valid.size();
+        if ((int)LastFrame.xyz_world.size() != 3 * n_last || (int)LastFrame.desc.size() != 32 * n_last || (int)LastFrame.octave.size() != n_last ||
+            (int)LastFrame.angle.size() != n_last || (int)LastFrame.observed.size() != n_last)
+            throw sindyn::Error(SINDYN_ERR_INVALID, "SearchByProjection: LastFrame arrays disagree in length");
+        params.th = th; params.mono = bMono ? 1 : 0; params.check_orientation = mbCheckOrientation ? 1 : 0;
+        vMatches.assign((size_t)extractor.capacity(), -1);
+        int n_cur = 0, nmatches = 0;
+        const int st = sindyn_orb_search_by_projection(extractor.handle(), &params, n_last, LastFrame.xyz_world.data(), LastFrame.valid.data(),
+                                                       LastFrame.desc.data(), LastFrame.octave.data(), LastFrame.angle.data(), LastFrame.observed.data(),
+                                                       currentBlocked ? currentBlocked->data() : nullptr, vMatches.data(), (int)vMatches.size(), &n_cur,
+                                                       &nmatches);
+        if (st != SINDYN_OK) throw sindyn::Error(st, std::string("sindyn_orb_search_by_projection: ") + sindyn_orb_last_error(extractor.handle()));
+        vMatches.resize((size_t)n_cur);
+        return nmatches;
+    }
+
+protected:
+    float mfNNratio;
+    bool mbCheckOrientation;
 };
 
 }  // namespace ORB_SLAM2

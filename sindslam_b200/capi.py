@@ -16,6 +16,11 @@ LIB_PATH = os.path.join(_HERE, "libsindyn_cuda.so")
 STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NO_DEVICE", 4: "STATE", 5: "CAPACITY"}
 
 
+class MatchParams(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float), ("b", C.c_float),
+                ("Tcw_cur", C.c_float * 16), ("Tcw_last", C.c_float * 16), ("th", C.c_float), ("mono", C.c_int), ("check_orientation", C.c_int)]
+
+
 class SindynError(RuntimeError):
     pass
 
@@ -95,6 +100,7 @@ SIGNATURES = {
     "sindyn_orb_frame_features": (_i, [_vp, _vp, _sz, C.POINTER(FrameParams), _vp, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
     "sindyn_cloud_single": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _ip]),
     "sindyn_cloud_consistent": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _ip, _vp, _sz, _vp, _vp]),
+    "sindyn_orb_search_by_projection": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ip, _ip]),
     "sindyn_orb_set_stream": (_i, [_vp, _vp]),
     "sindyn_orb_launch_count": (C.c_ulonglong, [_vp]),
     "sindyn_orb_last_error": (C.c_char_p, [_vp]),
@@ -462,6 +468,30 @@ class Orb:
             raise SindynError(f"orb_extract: {STATUS.get(st, st)}: {self.lib.sindyn_orb_last_error(self.h).decode()}")
         arr = np.frombuffer(kps, dtype=np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")]))[:n.value].copy()
         return arr, desc[:n.value].copy()
+
+    def search_by_projection(self, last, Tcw_cur, Tcw_last, fx, fy, cx, cy, bf, b, th, mono=False, check_orientation=True, blocked=None):
+        """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) against the frame resident in this handle.
+        last: dict(xyz_w, valid, desc, octave, angle, observed).  Returns (match[n_cur], nmatches)."""
+        p = MatchParams()
+        p.fx, p.fy, p.cx, p.cy, p.bf, p.b, p.th = fx, fy, cx, cy, bf, b, th
+        p.mono, p.check_orientation = int(mono), int(check_orientation)
+        p.Tcw_cur[:] = [float(v) for v in np.asarray(Tcw_cur, np.float32).reshape(-1)]
+        p.Tcw_last[:] = [float(v) for v in np.asarray(Tcw_last, np.float32).reshape(-1)]
+        xyz = np.ascontiguousarray(last["xyz_w"], np.float32).reshape(-1, 3)
+        n_last = len(xyz)
+        valid = np.ascontiguousarray(np.asarray(last["valid"]).astype(np.uint8))
+        observed = np.ascontiguousarray(np.asarray(last["observed"]).astype(np.uint8))
+        desc = _u8(last["desc"]).reshape(-1, 32)
+        octave, angle = np.ascontiguousarray(last["octave"], np.int32), np.ascontiguousarray(last["angle"], np.float32)
+        cap = self.nfeatures * 2 + 64
+        match = np.full(cap, -1, np.int32)
+        n_cur, nm = C.c_int(0), C.c_int(0)
+        blk = np.ascontiguousarray(np.asarray(blocked).astype(np.uint8)) if blocked is not None else None
+        st = self.lib.sindyn_orb_search_by_projection(self.h, C.byref(p), n_last, _p(xyz), _p(valid), _p(desc), _p(octave), _p(angle), _p(observed),
+                                                      _p(blk) if blk is not None else None, _p(match), cap, C.byref(n_cur), C.byref(nm))
+        if st != 0:
+            raise SindynError(f"search_by_projection: {STATUS.get(st, st)}: {self.lib.sindyn_orb_last_error(self.h).decode()}")
+        return match[: n_cur.value].copy(), nm.value
 
     def frame_features(self, depth_raw, fx, fy, cx, cy, dist, bf, depth_map_factor):
         """Frame.cc:143-170 on the keypoints of the last extract(): (keys_un, depth, u_right, bounds, offsets, indices)."""

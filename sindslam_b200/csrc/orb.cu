@@ -66,6 +66,7 @@ struct sindyn_orb : sindyn_base {
     uint16_t *depth = nullptr, *pin_depth = nullptr;
     float *fr_un = nullptr, *fr_depth = nullptr, *fr_uright = nullptr, *fr_bounds = nullptr;
     int *fr_offsets = nullptr, *fr_indices = nullptr;
+    struct MatchStage *match = nullptr;   // descriptor matching (row f4), allocated on first use
     size_t pad_total = 0, img_total = 0;
 };
 
@@ -708,11 +709,14 @@ extern "C" int sindyn_orb_create(int nfeatures, float scale_factor, int nlevels,
     return SINDYN_OK;
 }
 
+static void match_stage_free(sindyn_orb *o);
+
 extern "C" int sindyn_orb_destroy(sindyn_orb_handle h)
 {
     if (!h) return SINDYN_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    match_stage_free(h);
     h->free_all();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -946,5 +950,255 @@ extern "C" int sindyn_orb_frame_features(sindyn_orb_handle h, const uint16_t *de
     if (grid_offsets) CU_CHECK(h, cudaMemcpyAsync(grid_offsets, h->fr_offsets, sizeof(int) * (FR_COLS * FR_ROWS + 1), cudaMemcpyDeviceToHost, h->stream));
     if (grid_indices && n) CU_CHECK(h, cudaMemcpyAsync(grid_indices, h->fr_indices, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    return SINDYN_OK;
+}
+
+// ------------------------------------------------------------------ descriptor matching
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (src/ORBmatcher.cc:1328-1470) of
+// Tracking::TrackWithMotionModel, with Frame::GetFeaturesInArea (src/Frame.cc:398-452), ORBmatcher::DescriptorDistance
+// (:1647-1665) and ComputeThreeMaxima (:1601-1643).  The current frame is the one resident in this handle (last
+// sindyn_orb_extract + sindyn_orb_frame_features); the last frame's map points arrive as plain arrays.
+//   k_match_candidates  one thread per last-frame point: projection, grid window, level / window / right-coordinate tests and the
+//                       256-bit Hamming distance of every surviving candidate, in the reference's visiting order
+//   k_match_assign      one warp walks the last-frame points IN ORDER (the reference's result depends on it: a key point whose
+//                       map point has observations blocks later matches), lanes take the minimum over the candidate list;
+//                       rotation histogram + three-maxima filter
+#define MT_MAXC 512                 // candidates kept per last-frame point (th = 30, the retry of TrackWithMotionModel, needs ~300)
+#define MT_TH_HIGH 100
+#define MT_HISTO 30
+
+struct MatchParams {
+    float fx, fy, cx, cy, bf;
+    float R[9], t[3];               // CurrentFrame.mTcw
+    float th;
+    int mode;                       // 0: octave window [o-1, o+1]; 1: forward (>= o); 2: backward (<= o)
+    int check_ori, nlevels;
+    float scale[ORB_MAX_LEVELS];    // mvScaleFactors
+};
+
+struct MatchStage {
+    float *xyz = nullptr, *angle = nullptr;
+    uint8_t *valid = nullptr, *observed = nullptr, *desc = nullptr, *blocked = nullptr;
+    int *octave = nullptr, *match = nullptr, *ctl = nullptr;   // ctl: nmatches, overflow
+    unsigned short *cand_i2 = nullptr, *cand_d = nullptr, *rec_i2 = nullptr;
+    int *cand_n = nullptr;
+    uint8_t *rec_bin = nullptr;
+};
+
+__device__ __forceinline__ float match_gemv_row(const float *R, const float *x, float t)
+{
+    // cv::Mat float product + addend: double accumulation, one rounding (GEMMSingleMul<float, double>)
+    return (float)(((double)R[0] * (double)x[0] + (double)R[1] * (double)x[1] + (double)R[2] * (double)x[2]) * 1.0 + (double)t * 1.0);
+}
+
+__global__ void k_match_candidates(int n_last, const float *__restrict__ xyz, const uint8_t *__restrict__ valid, const uint8_t *__restrict__ desc_last,
+                                   const int *__restrict__ octave_last, const sindyn_keypoint *__restrict__ kps, const float *__restrict__ un,
+                                   const float *__restrict__ uright, const uint8_t *__restrict__ desc, const float *__restrict__ bounds,
+                                   const int *__restrict__ offsets, const int *__restrict__ indices, MatchParams P,
+                                   unsigned short *__restrict__ cand_i2, unsigned short *__restrict__ cand_d, int *__restrict__ cand_n,
+                                   int *__restrict__ ctl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_last) return;
+    int n = 0;
+    cand_n[i] = 0;
+    if (!valid[i]) return;
+    const float X[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    const float xc = match_gemv_row(P.R, X, P.t[0]), yc = match_gemv_row(P.R + 3, X, P.t[1]), zc = match_gemv_row(P.R + 6, X, P.t[2]);
+    const float invzc = (float)(1.0 / (double)zc);
+    if (invzc < 0) return;
+    const float u = P.fx * xc * invzc + P.cx, v = P.fy * yc * invzc + P.cy;
+    const float minx = bounds[0], maxx = bounds[1], miny = bounds[2], maxy = bounds[3];
+    if (isnan(u) || isnan(v)) return;
+    if (u < minx || u > maxx || v < miny || v > maxy) return;
+    const int o = octave_last[i];
+    const float r = P.th * P.scale[o];
+    const int min_level = P.mode == 2 ? 0 : (P.mode == 1 ? o : o - 1), max_level = P.mode == 1 ? -1 : (P.mode == 2 ? o : o + 1);
+    // Frame::GetFeaturesInArea
+    const float inv_w = (float)FR_COLS / (maxx - minx), inv_h = (float)FR_ROWS / (maxy - miny);
+    const int c0 = max(0, (int)floor((double)((u - minx - r) * inv_w)));
+    if (c0 >= FR_COLS) return;
+    const int c1 = min(FR_COLS - 1, (int)ceil((double)((u - minx + r) * inv_w)));
+    if (c1 < 0) return;
+    const int r0 = max(0, (int)floor((double)((v - miny - r) * inv_h)));
+    if (r0 >= FR_ROWS) return;
+    const int r1 = min(FR_ROWS - 1, (int)ceil((double)((v - miny + r) * inv_h)));
+    if (r1 < 0) return;
+    const bool check = min_level > 0 || max_level >= 0;
+    unsigned dl[8];
+    for (int k = 0; k < 8; ++k) dl[k] = ((const unsigned *)desc_last)[8 * i + k];
+    const float ur = u - P.bf * invzc;
+    for (int ix = c0; ix <= c1; ++ix)
+        for (int iy = r0; iy <= r1; ++iy) {
+            const int c = ix * FR_ROWS + iy;
+            for (int j = offsets[c]; j < offsets[c + 1]; ++j) {
+                const int i2 = indices[j];
+                if (check) {
+                    const int oc = kps[i2].octave;
+                    if (oc < min_level) continue;
+                    if (max_level >= 0 && oc > max_level) continue;
+                }
+                const float dx = un[2 * i2] - u, dy = un[2 * i2 + 1] - v;
+                if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
+                // (the "already matched to an observed map point" test depends on earlier points: k_match_assign)
+                const float urt = uright[i2];
+                if (urt > 0) {
+                    const float er = fabsf(ur - urt);
+                    if (er > r) continue;
+                }
+                int d = 0;
+                for (int k = 0; k < 8; ++k) d += __popc(dl[k] ^ ((const unsigned *)desc)[8 * i2 + k]);
+                if (n < MT_MAXC) { cand_i2[(size_t)i * MT_MAXC + n] = (unsigned short)i2; cand_d[(size_t)i * MT_MAXC + n] = (unsigned short)d; }
+                ++n;
+            }
+        }
+    if (n > MT_MAXC) { ctl[1] = 1; n = MT_MAXC; }
+    cand_n[i] = n;
+}
+
+__global__ void __launch_bounds__(32) k_match_assign(int n_last, int n_cur, const uint8_t *__restrict__ observed, const float *__restrict__ angle_last,
+                                                     const sindyn_keypoint *__restrict__ kps, const unsigned short *__restrict__ cand_i2,
+                                                     const unsigned short *__restrict__ cand_d, const int *__restrict__ cand_n,
+                                                     const uint8_t *__restrict__ blocked_in, int check_ori, int *__restrict__ match,
+                                                     unsigned short *__restrict__ rec_i2, uint8_t *__restrict__ rec_bin, int *__restrict__ ctl)
+{
+    __shared__ uint8_t s_blk[ORB_OUT_MAX];
+    __shared__ int s_hist[MT_HISTO];
+    const int lane = threadIdx.x;
+    for (int k = lane; k < n_cur; k += 32) { s_blk[k] = blocked_in ? blocked_in[k] : 0; match[k] = -1; }
+    if (lane < MT_HISTO) s_hist[lane] = 0;
+    __syncwarp();
+    int nmatches = 0, nrec = 0;
+    const float factor = 1.0f / MT_HISTO;
+    for (int i = 0; i < n_last; ++i) {
+        const int n = cand_n[i];
+        if (n == 0) continue;
+        unsigned best = 0xffffffffu;   // (distance << 16 | position): the minimum is the FIRST candidate with the smallest distance
+        for (int k = lane; k < n; k += 32) {
+            const int i2 = cand_i2[(size_t)i * MT_MAXC + k];
+            if (s_blk[i2]) continue;
+            best = min(best, ((unsigned)cand_d[(size_t)i * MT_MAXC + k] << 16) | (unsigned)k);
+        }
+        for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+        if (best == 0xffffffffu || (best >> 16) > MT_TH_HIGH) continue;
+        const int i2 = cand_i2[(size_t)i * MT_MAXC + (best & 0xffff)];
+        ++nmatches;
+        if (lane == 0) {
+            match[i2] = i;
+            s_blk[i2] = observed[i];
+            if (check_ori) {
+                float rot = angle_last[i] - kps[i2].angle;
+                if (rot < 0.0f) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == MT_HISTO) bin = 0;
+                rec_i2[nrec] = (unsigned short)i2;
+                rec_bin[nrec] = (uint8_t)bin;
+                s_hist[bin]++;
+            }
+        }
+        ++nrec;
+        __syncwarp();
+    }
+    if (check_ori) {
+        __syncwarp();
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        {   // ComputeThreeMaxima (every lane computes the same thing)
+            int max1 = 0, max2 = 0, max3 = 0;
+            for (int k = 0; k < MT_HISTO; ++k) {
+                const int sz = s_hist[k];
+                if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = k; }
+                else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = k; }
+                else if (sz > max3) { max3 = sz; ind3 = k; }
+            }
+            if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+        }
+        int removed = 0;
+        for (int k = lane; k < nrec; k += 32) {
+            const int b = rec_bin[k];
+            if (b != ind1 && b != ind2 && b != ind3) { match[rec_i2[k]] = -1; ++removed; }
+        }
+        for (int off = 16; off > 0; off >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, off);
+        nmatches -= removed;
+    }
+    if (lane == 0) ctl[0] = nmatches;
+}
+
+static void match_stage_free(sindyn_orb *o)
+{
+    delete o->match;   // the device buffers belong to the handle's allocation list
+    o->match = nullptr;
+}
+
+static int match_stage(sindyn_orb *o, MatchStage **out)
+{
+    if (!o->match) {
+        MatchStage *m = new MatchStage();
+        SD_CHECK(o->dalloc(&m->xyz, 3 * ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->angle, ORB_OUT_MAX));
+        SD_CHECK(o->dalloc(&m->valid, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->observed, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->blocked, ORB_OUT_MAX));
+        SD_CHECK(o->dalloc(&m->desc, 32 * ORB_OUT_MAX));
+        SD_CHECK(o->dalloc(&m->octave, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->match, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->ctl, 2));
+        SD_CHECK(o->dalloc(&m->cand_i2, (size_t)ORB_OUT_MAX * MT_MAXC)); SD_CHECK(o->dalloc(&m->cand_d, (size_t)ORB_OUT_MAX * MT_MAXC));
+        SD_CHECK(o->dalloc(&m->cand_n, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->rec_i2, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->rec_bin, ORB_OUT_MAX));
+        o->match = m;
+    }
+    *out = o->match;
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_orb_search_by_projection(sindyn_orb_handle h, const sindyn_match_params *mp, int n_last, const float *last_xyz_world,
+                                               const uint8_t *last_valid, const uint8_t *last_desc, const int *last_octave,
+                                               const float *last_angle, const uint8_t *last_observed, const uint8_t *cur_blocked,
+                                               int *match_out, int capacity, int *n_cur_out, int *nmatches_out)
+{
+    if (!h || !mp || !last_xyz_world || !last_valid || !last_desc || !last_octave || !last_angle || !last_observed || !match_out || !nmatches_out)
+        return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const int n_cur = h->ctl_host->n_out;   // current frame = last sindyn_orb_extract + sindyn_orb_frame_features on this handle
+    if (n_cur_out) *n_cur_out = n_cur;
+    if (n_last < 0 || n_last > ORB_OUT_MAX) { h->err = "search_by_projection: n_last out of range"; return SINDYN_ERR_INVALID; }
+    if (n_cur > capacity) { h->err = "search_by_projection: match_out capacity too small"; return SINDYN_ERR_CAPACITY; }
+    for (int i = 0; i < n_last; ++i)
+        if (last_valid[i] && (last_octave[i] < 0 || last_octave[i] >= h->nlevels)) { h->err = "search_by_projection: octave out of range"; return SINDYN_ERR_INVALID; }
+    MatchStage *m;
+    SD_CHECK(match_stage(h, &m));
+    MatchParams P;
+    P.fx = mp->fx; P.fy = mp->fy; P.cx = mp->cx; P.cy = mp->cy; P.bf = mp->bf; P.th = mp->th;
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) P.R[3 * r + c] = mp->Tcw_cur[4 * r + c]; P.t[r] = mp->Tcw_cur[4 * r + 3]; }
+    // twc = -Rcw^T tcw ; tlc = Rlw twc + tlw (ORBmatcher.cc:1338-1349): forward / backward motion along the optical axis
+    float twc[3], tlc_z;
+    {
+        float nRt[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) nRt[3 * r + c] = -P.R[3 * c + r];
+        for (int r = 0; r < 3; ++r) twc[r] = (float)(((double)nRt[3 * r] * P.t[0] + (double)nRt[3 * r + 1] * P.t[1] + (double)nRt[3 * r + 2] * P.t[2]) * 1.0);
+        const float *L = mp->Tcw_last;
+        tlc_z = (float)(((double)L[8] * twc[0] + (double)L[9] * twc[1] + (double)L[10] * twc[2]) * 1.0 + (double)L[11] * 1.0);
+    }
+    const bool forward = tlc_z > mp->b && !mp->mono, backward = -tlc_z > mp->b && !mp->mono;
+    P.mode = forward ? 1 : (backward ? 2 : 0);
+    P.check_ori = mp->check_orientation; P.nlevels = h->nlevels;
+    for (int l = 0; l < ORB_MAX_LEVELS; ++l) P.scale[l] = l < h->nlevels ? h->lv[l].scale : 1.0f;
+    if (n_last > 0) {
+        CU_CHECK(h, cudaMemcpyAsync(m->xyz, last_xyz_world, sizeof(float) * 3 * n_last, cudaMemcpyHostToDevice, h->stream));
+        CU_CHECK(h, cudaMemcpyAsync(m->valid, last_valid, n_last, cudaMemcpyHostToDevice, h->stream));
+        CU_CHECK(h, cudaMemcpyAsync(m->desc, last_desc, (size_t)32 * n_last, cudaMemcpyHostToDevice, h->stream));
+        CU_CHECK(h, cudaMemcpyAsync(m->octave, last_octave, sizeof(int) * n_last, cudaMemcpyHostToDevice, h->stream));
+        CU_CHECK(h, cudaMemcpyAsync(m->angle, last_angle, sizeof(float) * n_last, cudaMemcpyHostToDevice, h->stream));
+        CU_CHECK(h, cudaMemcpyAsync(m->observed, last_observed, n_last, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (cur_blocked && n_cur > 0) CU_CHECK(h, cudaMemcpyAsync(m->blocked, cur_blocked, n_cur, cudaMemcpyHostToDevice, h->stream));
+    CU_CHECK(h, cudaMemsetAsync(m->ctl, 0, sizeof(int) * 2, h->stream));
+    if (n_last > 0)
+        LAUNCH(h, k_match_candidates, (n_last + 127) / 128, 128, 0, n_last, m->xyz, m->valid, m->desc, m->octave, h->out_host_fmt, h->fr_un, h->fr_uright,
+               h->desc, h->fr_bounds, h->fr_offsets, h->fr_indices, P, m->cand_i2, m->cand_d, m->cand_n, m->ctl);
+    LAUNCH(h, k_match_assign, 1, 32, 0, n_last, n_cur, m->observed, m->angle, h->out_host_fmt, m->cand_i2, m->cand_d, m->cand_n,
+           cur_blocked ? m->blocked : (const uint8_t *)nullptr, P.check_ori, m->match, m->rec_i2, m->rec_bin, m->ctl);
+    LAUNCH_CHECK(h);
+    int ctl_host[2];
+    CU_CHECK(h, cudaMemcpyAsync(ctl_host, m->ctl, sizeof(ctl_host), cudaMemcpyDeviceToHost, h->stream));
+    if (n_cur > 0) CU_CHECK(h, cudaMemcpyAsync(match_out, m->match, sizeof(int) * n_cur, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    if (ctl_host[1]) { h->err = "search_by_projection: more than 512 candidates in one search window"; return SINDYN_ERR_CAPACITY; }
+    *nmatches_out = ctl_host[0];
     return SINDYN_OK;
 }
