@@ -958,9 +958,9 @@ extern "C" int sindyn_orb_frame_features(sindyn_orb_handle h, const uint16_t *de
 // Tracking::TrackWithMotionModel, with Frame::GetFeaturesInArea (src/Frame.cc:398-452), ORBmatcher::DescriptorDistance
 // (:1647-1665) and ComputeThreeMaxima (:1601-1643).  The current frame is the one resident in this handle (last
 // sindyn_orb_extract + sindyn_orb_frame_features); the last frame's map points arrive as plain arrays.
-//   k_match_candidates  one thread per last-frame point: projection, grid window, level / window / right-coordinate tests and the
+//   k_match_candidates  one warp per last-frame point: projection, grid window, level / window / right-coordinate tests and the
 //                       256-bit Hamming distance of every surviving candidate, in the reference's visiting order
-//   k_match_assign      one warp walks the last-frame points IN ORDER (the reference's result depends on it: a key point whose
+//   k_match_assign      one CTA packs the candidate lists into shared memory, then one warp walks the last-frame points IN ORDER (the reference's result depends on it: a key point whose
 //                       map point has observations blocks later matches), lanes take the minimum over the candidate list;
 //                       rotation histogram + three-maxima filter
 #define MT_MAXC 512                 // candidates kept per last-frame point (th = 30, the retry of TrackWithMotionModel, needs ~300)
@@ -980,9 +980,9 @@ struct MatchStage {
     float *xyz = nullptr, *angle = nullptr;
     uint8_t *valid = nullptr, *observed = nullptr, *desc = nullptr, *blocked = nullptr;
     int *octave = nullptr, *match = nullptr, *ctl = nullptr;   // ctl: nmatches, overflow
-    unsigned short *cand_i2 = nullptr, *cand_d = nullptr, *rec_i2 = nullptr;
+    unsigned short *cand_i2 = nullptr, *cand_d = nullptr;
     int *cand_n = nullptr;
-    uint8_t *rec_bin = nullptr;
+    unsigned *best0 = nullptr;
 };
 
 __device__ __forceinline__ float match_gemv_row(const float *R, const float *x, float t)
@@ -991,17 +991,22 @@ __device__ __forceinline__ float match_gemv_row(const float *R, const float *x, 
     return (float)(((double)R[0] * (double)x[0] + (double)R[1] * (double)x[1] + (double)R[2] * (double)x[2]) * 1.0 + (double)t * 1.0);
 }
 
-__global__ void k_match_candidates(int n_last, const float *__restrict__ xyz, const uint8_t *__restrict__ valid, const uint8_t *__restrict__ desc_last,
-                                   const int *__restrict__ octave_last, const sindyn_keypoint *__restrict__ kps, const float *__restrict__ un,
-                                   const float *__restrict__ uright, const uint8_t *__restrict__ desc, const float *__restrict__ bounds,
-                                   const int *__restrict__ offsets, const int *__restrict__ indices, MatchParams P,
-                                   unsigned short *__restrict__ cand_i2, unsigned short *__restrict__ cand_d, int *__restrict__ cand_n,
-                                   int *__restrict__ ctl)
+// One WARP per last-frame point.  The CSR grid stores cell (ix, iy) at ix * 48 + iy, so the cells iy = r0 .. r1 of one grid column
+// are ONE contiguous index run in the reference's visiting order: lanes take consecutive entries of the run, a ballot keeps the
+// order when the survivors are appended to the candidate list.  best0 = first minimum over the candidates that are not blocked
+// on entry (k_match_assign re-scans a list only when that candidate was taken by an earlier point in the meantime).
+__global__ void __launch_bounds__(128) k_match_candidates(int n_last, const float *__restrict__ xyz, const uint8_t *__restrict__ valid,
+                                                          const uint8_t *__restrict__ desc_last, const int *__restrict__ octave_last,
+                                                          const sindyn_keypoint *__restrict__ kps, const float *__restrict__ un,
+                                                          const float *__restrict__ uright, const uint8_t *__restrict__ desc,
+                                                          const float *__restrict__ bounds, const int *__restrict__ offsets,
+                                                          const int *__restrict__ indices, const uint8_t *__restrict__ blocked_in, MatchParams P,
+                                                          unsigned short *__restrict__ cand_i2, unsigned short *__restrict__ cand_d,
+                                                          int *__restrict__ cand_n, unsigned *__restrict__ best0, int *__restrict__ ctl)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n_last) return;
-    int n = 0;
-    cand_n[i] = 0;
+    if (lane == 0) { cand_n[i] = 0; best0[i] = 0xffffffffu; }
     if (!valid[i]) return;
     const float X[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
     const float xc = match_gemv_row(P.R, X, P.t[0]), yc = match_gemv_row(P.R + 3, X, P.t[1]), zc = match_gemv_row(P.R + 6, X, P.t[2]);
@@ -1028,81 +1033,139 @@ __global__ void k_match_candidates(int n_last, const float *__restrict__ xyz, co
     unsigned dl[8];
     for (int k = 0; k < 8; ++k) dl[k] = ((const unsigned *)desc_last)[8 * i + k];
     const float ur = u - P.bf * invzc;
-    for (int ix = c0; ix <= c1; ++ix)
-        for (int iy = r0; iy <= r1; ++iy) {
-            const int c = ix * FR_ROWS + iy;
-            for (int j = offsets[c]; j < offsets[c + 1]; ++j) {
-                const int i2 = indices[j];
+    int n = 0;
+    unsigned best = 0xffffffffu;
+    for (int ix = c0; ix <= c1; ++ix) {
+        const int j0 = offsets[ix * FR_ROWS + r0], j1 = offsets[ix * FR_ROWS + r1 + 1];
+        for (int jb = j0; jb < j1; jb += 32) {
+            const int j = jb + lane;
+            bool pass = false;
+            int i2 = 0, d = 0;
+            if (j < j1) {
+                i2 = indices[j];
+                pass = true;
                 if (check) {
                     const int oc = kps[i2].octave;
-                    if (oc < min_level) continue;
-                    if (max_level >= 0 && oc > max_level) continue;
+                    if (oc < min_level || (max_level >= 0 && oc > max_level)) pass = false;
                 }
-                const float dx = un[2 * i2] - u, dy = un[2 * i2 + 1] - v;
-                if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
+                if (pass) {
+                    const float dx = un[2 * i2] - u, dy = un[2 * i2 + 1] - v;
+                    pass = fabsf(dx) < r && fabsf(dy) < r;
+                }
                 // (the "already matched to an observed map point" test depends on earlier points: k_match_assign)
-                const float urt = uright[i2];
-                if (urt > 0) {
-                    const float er = fabsf(ur - urt);
-                    if (er > r) continue;
+                if (pass) {
+                    const float urt = uright[i2];
+                    if (urt > 0 && fabsf(ur - urt) > r) pass = false;
                 }
-                int d = 0;
-                for (int k = 0; k < 8; ++k) d += __popc(dl[k] ^ ((const unsigned *)desc)[8 * i2 + k]);
-                if (n < MT_MAXC) { cand_i2[(size_t)i * MT_MAXC + n] = (unsigned short)i2; cand_d[(size_t)i * MT_MAXC + n] = (unsigned short)d; }
-                ++n;
+                if (pass)
+                    for (int k = 0; k < 8; ++k) d += __popc(dl[k] ^ ((const unsigned *)desc)[8 * i2 + k]);
             }
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+                const int pos = n + __popc(m & ((1u << lane) - 1u));
+                if (pos < MT_MAXC) {
+                    cand_i2[(size_t)i * MT_MAXC + pos] = (unsigned short)i2;
+                    cand_d[(size_t)i * MT_MAXC + pos] = (unsigned short)d;
+                    if (!(blocked_in && blocked_in[i2])) best = min(best, ((unsigned)d << 16) | (unsigned)pos);
+                }
+            }
+            n += __popc(m);
         }
-    if (n > MT_MAXC) { ctl[1] = 1; n = MT_MAXC; }
-    cand_n[i] = n;
+    }
+    for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if (lane == 0) {
+        if (n > MT_MAXC) { ctl[1] = 1; n = MT_MAXC; }
+        cand_n[i] = n;
+        best0[i] = best;
+    }
 }
 
-__global__ void __launch_bounds__(32) k_match_assign(int n_last, int n_cur, const uint8_t *__restrict__ observed, const float *__restrict__ angle_last,
-                                                     const sindyn_keypoint *__restrict__ kps, const unsigned short *__restrict__ cand_i2,
-                                                     const unsigned short *__restrict__ cand_d, const int *__restrict__ cand_n,
-                                                     const uint8_t *__restrict__ blocked_in, int check_ori, int *__restrict__ match,
-                                                     unsigned short *__restrict__ rec_i2, uint8_t *__restrict__ rec_bin, int *__restrict__ ctl)
+// The ordered pass is a chain of n_last dependent steps, so everything a step touches sits in shared memory: the first-minimum
+// candidate of every point (best0 and its key point), the blocked flags, the result.  A point whose first-minimum candidate is
+// still free takes it (the minimum over a subset that contains the old minimum is the old minimum); only when an earlier point
+// with observations took it in the meantime is the list re-scanned from global memory.  All 32 lanes of warp 0 execute the chain
+// redundantly (same-value stores), so no step needs a warp barrier; the rotation histogram, the three-maxima filter and the
+// write-back are order independent and run on the whole CTA afterwards.
+#define MT_NT 1024
+
+__global__ void __launch_bounds__(MT_NT) k_match_assign(int n_last, int n_cur, const uint8_t *__restrict__ observed, const float *__restrict__ angle_last,
+                                                        const sindyn_keypoint *__restrict__ kps, const unsigned short *__restrict__ cand_i2,
+                                                        const unsigned short *__restrict__ cand_d, const int *__restrict__ cand_n,
+                                                        const unsigned *__restrict__ best0, const uint8_t *__restrict__ blocked_in, int check_ori,
+                                                        int *__restrict__ match, int *__restrict__ ctl)
 {
+    extern __shared__ unsigned mt_sm[];
+    unsigned *s_best = mt_sm;                                            // [n_last] distance << 16 | position
+    float *s_ang = (float *)(mt_sm + ORB_OUT_MAX);                       // [n_cur]  mvKeysUn[i2].angle
+    float *s_angl = s_ang + ORB_OUT_MAX;                                 // [n_last] LastFrame.mvKeysUn[i].angle
+    unsigned short *s_bi2 = (unsigned short *)(s_angl + ORB_OUT_MAX);    // [n_last] key point of the first-minimum candidate | observed << 15
+    unsigned short *s_n = s_bi2 + ORB_OUT_MAX;                           // [n_last] list length
+    short *s_match = (short *)(s_n + ORB_OUT_MAX);                       // [n_cur]  result
+    unsigned short *s_rec = (unsigned short *)(s_match + ORB_OUT_MAX);   // [n_last] accepted matches in order: key point
+    unsigned short *s_reci = s_rec + ORB_OUT_MAX;                        // [n_last]                            last-frame point
+    uint8_t *s_rbin = (uint8_t *)(s_reci + ORB_OUT_MAX);                 // [n_last] rotation bin of every accepted match
     __shared__ uint8_t s_blk[ORB_OUT_MAX];
     __shared__ int s_hist[MT_HISTO];
-    const int lane = threadIdx.x;
-    for (int k = lane; k < n_cur; k += 32) { s_blk[k] = blocked_in ? blocked_in[k] : 0; match[k] = -1; }
-    if (lane < MT_HISTO) s_hist[lane] = 0;
-    __syncwarp();
-    int nmatches = 0, nrec = 0;
-    const float factor = 1.0f / MT_HISTO;
-    for (int i = 0; i < n_last; ++i) {
-        const int n = cand_n[i];
-        if (n == 0) continue;
-        unsigned best = 0xffffffffu;   // (distance << 16 | position): the minimum is the FIRST candidate with the smallest distance
-        for (int k = lane; k < n; k += 32) {
-            const int i2 = cand_i2[(size_t)i * MT_MAXC + k];
-            if (s_blk[i2]) continue;
-            best = min(best, ((unsigned)cand_d[(size_t)i * MT_MAXC + k] << 16) | (unsigned)k);
-        }
-        for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
-        if (best == 0xffffffffu || (best >> 16) > MT_TH_HIGH) continue;
-        const int i2 = cand_i2[(size_t)i * MT_MAXC + (best & 0xffff)];
-        ++nmatches;
-        if (lane == 0) {
-            match[i2] = i;
-            s_blk[i2] = observed[i];
-            if (check_ori) {
-                float rot = angle_last[i] - kps[i2].angle;
-                if (rot < 0.0f) rot += 360.0f;
-                int bin = (int)roundf(rot * factor);
-                if (bin == MT_HISTO) bin = 0;
-                rec_i2[nrec] = (unsigned short)i2;
-                rec_bin[nrec] = (uint8_t)bin;
-                s_hist[bin]++;
-            }
-        }
-        ++nrec;
-        __syncwarp();
+    __shared__ int s_nrec, s_removed;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int k = tid; k < n_cur; k += MT_NT) { s_blk[k] = blocked_in ? blocked_in[k] : 0; s_match[k] = -1; s_ang[k] = kps[k].angle; }
+    for (int i = tid; i < n_last; i += MT_NT) {
+        const unsigned b = best0[i];
+        s_best[i] = b;
+        s_n[i] = (unsigned short)cand_n[i];
+        s_angl[i] = angle_last[i];
+        s_bi2[i] = (unsigned short)((b != 0xffffffffu ? cand_i2[(size_t)i * MT_MAXC + (b & 0xffff)] : 0) | (observed[i] ? 0x8000u : 0u));
     }
+    if (tid < MT_HISTO) s_hist[tid] = 0;
+    if (tid == 0) s_removed = 0;
+    __syncthreads();
+    if (tid < 32) {
+        int nrec = 0;
+        // (next point's first-minimum candidate is fetched one step ahead: the chain of a step is one s_blk read)
+        unsigned nbest = n_last > 0 ? s_best[0] : 0xffffffffu;
+        unsigned nbi2 = n_last > 0 ? s_bi2[0] : 0;
+        for (int i = 0; i < n_last; ++i) {
+            unsigned best = nbest;
+            const unsigned pk = nbi2;                     // key point | observed << 15
+            if (i + 1 < n_last) { nbest = s_best[i + 1]; nbi2 = s_bi2[i + 1]; }
+            if (best == 0xffffffffu) continue;            // no candidate that was free on entry (the blocked set only grows)
+            int i2 = pk & 0x7fff;
+            if (s_blk[i2]) {                              // taken by an earlier point with observations: re-scan the list
+                const int n = s_n[i];
+                best = 0xffffffffu;
+                for (int k = lane; k < n; k += 32) {
+                    const int c2 = cand_i2[(size_t)i * MT_MAXC + k];
+                    if (s_blk[c2]) continue;
+                    best = min(best, ((unsigned)cand_d[(size_t)i * MT_MAXC + k] << 16) | (unsigned)k);
+                }
+                for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+                if (best == 0xffffffffu) continue;
+                i2 = cand_i2[(size_t)i * MT_MAXC + (best & 0xffff)];
+            }
+            if ((best >> 16) > MT_TH_HIGH) continue;
+            s_match[i2] = (short)i;                        // (a later point may overwrite it: the reference counts both)
+            if (pk >> 15) s_blk[i2] = 1;
+            s_rec[nrec] = (unsigned short)i2;
+            s_reci[nrec] = (unsigned short)i;
+            ++nrec;
+        }
+        if (lane == 0) s_nrec = nrec;
+    }
+    __syncthreads();
+    const int nrec = s_nrec;
     if (check_ori) {
-        __syncwarp();
+        const float factor = 1.0f / MT_HISTO;
+        for (int k = tid; k < nrec; k += MT_NT) {
+            float rot = s_angl[s_reci[k]] - s_ang[s_rec[k]];
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == MT_HISTO) bin = 0;
+            s_rbin[k] = (uint8_t)bin;
+            atomicAdd(&s_hist[bin], 1);
+        }
+        __syncthreads();
         int ind1 = -1, ind2 = -1, ind3 = -1;
-        {   // ComputeThreeMaxima (every lane computes the same thing)
+        {   // ComputeThreeMaxima (every thread computes the same thing)
             int max1 = 0, max2 = 0, max3 = 0;
             for (int k = 0; k < MT_HISTO; ++k) {
                 const int sz = s_hist[k];
@@ -1113,16 +1176,17 @@ __global__ void __launch_bounds__(32) k_match_assign(int n_last, int n_cur, cons
             if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
             else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
         }
-        int removed = 0;
-        for (int k = lane; k < nrec; k += 32) {
-            const int b = rec_bin[k];
-            if (b != ind1 && b != ind2 && b != ind3) { match[rec_i2[k]] = -1; ++removed; }
+        for (int k = tid; k < nrec; k += MT_NT) {
+            const int b = s_rbin[k];
+            if (b != ind1 && b != ind2 && b != ind3) { s_match[s_rec[k]] = -1; atomicAdd(&s_removed, 1); }
         }
-        for (int off = 16; off > 0; off >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, off);
-        nmatches -= removed;
+        __syncthreads();
     }
-    if (lane == 0) ctl[0] = nmatches;
+    for (int k = tid; k < n_cur; k += MT_NT) match[k] = s_match[k];
+    if (tid == 0) ctl[0] = nrec - s_removed;
 }
+#define MT_ASSIGN_SMEM ((sizeof(unsigned) + 2 * sizeof(float) + 5 * sizeof(unsigned short) + 1) * ORB_OUT_MAX)
+static_assert(ORB_OUT_MAX <= 0x8000, "key point index and the observed flag share 16 bits");
 
 static void match_stage_free(sindyn_orb *o)
 {
@@ -1139,7 +1203,8 @@ static int match_stage(sindyn_orb *o, MatchStage **out)
         SD_CHECK(o->dalloc(&m->desc, 32 * ORB_OUT_MAX));
         SD_CHECK(o->dalloc(&m->octave, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->match, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->ctl, 2));
         SD_CHECK(o->dalloc(&m->cand_i2, (size_t)ORB_OUT_MAX * MT_MAXC)); SD_CHECK(o->dalloc(&m->cand_d, (size_t)ORB_OUT_MAX * MT_MAXC));
-        SD_CHECK(o->dalloc(&m->cand_n, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->rec_i2, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->rec_bin, ORB_OUT_MAX));
+        SD_CHECK(o->dalloc(&m->cand_n, ORB_OUT_MAX)); SD_CHECK(o->dalloc(&m->best0, ORB_OUT_MAX));
+        CU_CHECK(o, cudaFuncSetAttribute(k_match_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_ASSIGN_SMEM));
         o->match = m;
     }
     *out = o->match;
@@ -1188,11 +1253,12 @@ extern "C" int sindyn_orb_search_by_projection(sindyn_orb_handle h, const sindyn
     }
     if (cur_blocked && n_cur > 0) CU_CHECK(h, cudaMemcpyAsync(m->blocked, cur_blocked, n_cur, cudaMemcpyHostToDevice, h->stream));
     CU_CHECK(h, cudaMemsetAsync(m->ctl, 0, sizeof(int) * 2, h->stream));
+    const uint8_t *blk = cur_blocked ? m->blocked : (const uint8_t *)nullptr;
     if (n_last > 0)
-        LAUNCH(h, k_match_candidates, (n_last + 127) / 128, 128, 0, n_last, m->xyz, m->valid, m->desc, m->octave, h->out_host_fmt, h->fr_un, h->fr_uright,
-               h->desc, h->fr_bounds, h->fr_offsets, h->fr_indices, P, m->cand_i2, m->cand_d, m->cand_n, m->ctl);
-    LAUNCH(h, k_match_assign, 1, 32, 0, n_last, n_cur, m->observed, m->angle, h->out_host_fmt, m->cand_i2, m->cand_d, m->cand_n,
-           cur_blocked ? m->blocked : (const uint8_t *)nullptr, P.check_ori, m->match, m->rec_i2, m->rec_bin, m->ctl);
+        LAUNCH(h, k_match_candidates, (n_last + 3) / 4, 128, 0, n_last, m->xyz, m->valid, m->desc, m->octave, h->out_host_fmt, h->fr_un, h->fr_uright,
+               h->desc, h->fr_bounds, h->fr_offsets, h->fr_indices, blk, P, m->cand_i2, m->cand_d, m->cand_n, m->best0, m->ctl);
+    LAUNCH(h, k_match_assign, 1, MT_NT, MT_ASSIGN_SMEM, n_last, n_cur, m->observed, m->angle, h->out_host_fmt, m->cand_i2, m->cand_d, m->cand_n, m->best0,
+           blk, P.check_ori, m->match, m->ctl);
     LAUNCH_CHECK(h);
     int ctl_host[2];
     CU_CHECK(h, cudaMemcpyAsync(ctl_host, m->ctl, sizeof(ctl_host), cudaMemcpyDeviceToHost, h->stream));
