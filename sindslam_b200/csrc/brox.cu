@@ -166,14 +166,18 @@ struct BroxInnerP {
 #ifndef SINDYN_BROX_SMAX
 #define SINDYN_BROX_SMAX 5
 #endif
-constexpr int BROX_SMAX = SINDYN_BROX_SMAX, BROX_NT = 1024;   // sweeps fused into one k_brox_sor launch
-constexpr int BROX_RMAX = 2 * BROX_SMAX + 1;
+#ifndef SINDYN_BROX_SMAX_SMALL
+#define SINDYN_BROX_SMAX_SMALL 5
+#endif
+// sweeps fused into one k_brox_sor launch: levels on the three larger tiles / levels on 8x8 tiles (where the fixed cost of a
+// launch weighs more than the halo redundancy)
+constexpr int BROX_SMAX = SINDYN_BROX_SMAX, BROX_SMAX_SMALL = SINDYN_BROX_SMAX_SMALL, BROX_NT = 1024;
 // Tile menu: a level uses the smallest tile whose grid still fits into one wave of 148 SMs -- the time of a launch is
 // the time of ONE CTA, which is proportional to the staged region (tile + 2 x 21 halo), so mid-size levels run on
 // many small tiles instead of a few large ones.
-template <int TW_, int TH_> struct BroxTile {
-    static constexpr int TW = TW_, TH = TH_;
-    static constexpr int PW = TW + 2 * BROX_RMAX, PH = TH + 2 * BROX_RMAX;   // staged region
+template <int TW_, int TH_, int SMAX_ = BROX_SMAX> struct BroxTile {
+    static constexpr int TW = TW_, TH = TH_, SMAX = SMAX_, R = 2 * SMAX_ + 1;
+    static constexpr int PW = TW + 2 * R, PH = TH + 2 * R;   // staged region
     static constexpr int HW = PW / 2;                                        // pixels of one colour per row
     static constexpr int NPC = PH * HW;                                      // pixels per colour
     static constexpr int M = (NPC + BROX_NT - 1) / BROX_NT;                  // owned pixels per colour and thread
@@ -187,6 +191,7 @@ template <int TW_, int TH_> struct BroxTile {
     static_assert((PW & 1) == 0, "de-interleaving needs an even region width");
     static_assert(NPC < 4096, "pixel index must fit into 12 bits");
 };
+typedef BroxTile<8, 8, BROX_SMAX_SMALL> BroxTileS;
 typedef BroxTile<32, 24> BroxTileL;   // 74 x 66 region: also the single-tile mode of the coarse levels
 
 
@@ -216,6 +221,10 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_level(BroxInnerP p)
     // ---- per-thread pixel table: pk = idx | parity << 12 | live << 14
     unsigned pk[2][M];
     float rdu[2][M], rdv[2][M];
+    // image derivatives of the owned pixels: constant over the inner iterations, kept in registers when one pixel per colour is
+    // owned (with two the kernel would spill: they are re-read from L2 every iteration)
+    constexpr bool KEEP = M == 1;
+    float dI[2][KEEP ? M : 1][8];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -233,6 +242,20 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_level(BroxInnerP p)
     for (int r = tid; r < 4 * NPCP; r += NT) ((float2 *)sm4)[r] = make_float2(0.0f, 0.0f);
     pdl_wait();      // everything above is independent of the previous kernel's output
     pdl_trigger();
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int m = 0; m < (KEEP ? M : 0); ++m) {
+            const unsigned k = pk[c][m];
+            int g = 0;
+            if ((k >> 14) & 1u) {
+                const int idx = k & 0xfff, par = (k >> 12) & 1;
+                const int y = (int)(((float)idx + 0.5f) * inv_hw), x = 2 * (idx - y * HW) + par;
+                g = y * w + x;
+            }
+            dI[c][m][0] = p.Ix[g]; dI[c][m][1] = p.Iy[g]; dI[c][m][2] = p.Iz[g]; dI[c][m][3] = p.Ixx[g];
+            dI[c][m][4] = p.Ixy[g]; dI[c][m][5] = p.Iyy[g]; dI[c][m][6] = p.Ixz[g]; dI[c][m][7] = p.Iyz[g];
+        }
     __syncthreads();
     for (int it = 0; it < p.n_inner; ++it) {
         // ---- phase 0: (du, dv), the level's flow (u, v) and the total flow
@@ -298,14 +321,20 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_level(BroxInnerP p)
                 if (!((k >> 14) & 1u)) continue;
                 const int idx = k & 0xfff, par = (k >> 12) & 1;
                 const int y = (int)(((float)idx + 0.5f) * inv_hw), x = 2 * (idx - y * HW) + par;
-                const int g = y * w + x;
                 const float wl = x > 0 ? s_wr[(c ^ 1) * NPCP + idx - 1 + par] : 0.0f, wr = s_wr[c * NPCP + idx];
                 const float wu = y > 0 ? s_wd[(c ^ 1) * NPCP + idx - HW] : 0.0f, wd = s_wd[c * NPCP + idx];
                 const float2 own = s_uv[c * NPCP + idx];
                 rdu[c][m] = own.x;
                 rdv[c][m] = own.y;
                 const float dub = own.x, dvb = own.y;   // == the increment at the start of this inner iteration
-                const float ix = p.Ix[g], iy = p.Iy[g], iz = p.Iz[g], ixx = p.Ixx[g], ixy = p.Ixy[g], iyy = p.Iyy[g], ixz = p.Ixz[g], iyz = p.Iyz[g];
+                float ix, iy, iz, ixx, ixy, iyy, ixz, iyz;
+                if (KEEP) {
+                    ix = dI[c][KEEP ? m : 0][0]; iy = dI[c][KEEP ? m : 0][1]; iz = dI[c][KEEP ? m : 0][2]; ixx = dI[c][KEEP ? m : 0][3];
+                    ixy = dI[c][KEEP ? m : 0][4]; iyy = dI[c][KEEP ? m : 0][5]; ixz = dI[c][KEEP ? m : 0][6]; iyz = dI[c][KEEP ? m : 0][7];
+                } else {
+                    const int g = y * w + x;
+                    ix = p.Ix[g]; iy = p.Iy[g]; iz = p.Iz[g]; ixx = p.Ixx[g]; ixy = p.Ixy[g]; iyy = p.Iyy[g]; ixz = p.Ixz[g]; iyz = p.Iyz[g];
+                }
                 const float q0 = iz + ix * dub + iy * dvb;
                 const float q1 = ixz + ixx * dub + ixy * dvb;
                 const float q2 = iyz + ixy * dub + iyy * dvb;
@@ -401,6 +430,12 @@ __global__ void __launch_bounds__(BSY_W *BSY_H) k_brox_system(BroxSysP p)
     const int w = p.w, h = p.h;
     const int gx0 = blockIdx.x * BSY_W, gy0 = blockIdx.y * BSY_H;
     const int tid = threadIdx.y * BSY_W + threadIdx.x;
+    // the thread's own pixel: its image derivatives are loaded first, their latency overlaps the two staging phases below
+    const int x = gx0 + threadIdx.x, y = gy0 + threadIdx.y;
+    const bool own = x < w && y < h;
+    const int g = own ? y * w + x : 0;
+    const float dub = p.dub[g], dvb = p.dvb[g];
+    const float ix = p.Ix[g], iy = p.Iy[g], iz = p.Iz[g], ixx = p.Ixx[g], ixy = p.Ixy[g], iyy = p.Iyy[g], ixz = p.Ixz[g], iyz = p.Iyz[g];
     for (int i = tid; i < (BSY_H + 4) * (BSY_W + 4); i += BSY_W * BSY_H) {
         const int ly = i / (BSY_W + 4), lx = i - ly * (BSY_W + 4);
         const int x = gx0 - 2 + lx, y = gy0 - 2 + ly;
@@ -428,9 +463,7 @@ __global__ void __launch_bounds__(BSY_W *BSY_H) k_brox_system(BroxSysP p)
         s_ps[ly][lx] = ps;
     }
     __syncthreads();
-    const int x = gx0 + threadIdx.x, y = gy0 + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const int g = y * w + x;
+    if (!own) return;
     const int py = threadIdx.y + 1, px = threadIdx.x + 1;   // s_ps coordinates
     const float ps = s_ps[py][px];
     // edge weights; zero across the image border (Neumann).  wl / wu are the right / lower weights of the left / upper pixel
@@ -439,8 +472,6 @@ __global__ void __launch_bounds__(BSY_W *BSY_H) k_brox_system(BroxSysP p)
     const float wl = x > 0 ? p.alpha * 0.5f * (s_ps[py][px - 1] + ps) : 0.0f;
     const float wu = y > 0 ? p.alpha * 0.5f * (s_ps[py - 1][px] + ps) : 0.0f;
     const float gamma = p.gamma;
-    const float dub = p.dub[g], dvb = p.dvb[g];
-    const float ix = p.Ix[g], iy = p.Iy[g], iz = p.Iz[g], ixx = p.Ixx[g], ixy = p.Ixy[g], iyy = p.Iyy[g], ixz = p.Ixz[g], iyz = p.Iyz[g];
     const float q0 = iz + ix * dub + iy * dvb;
     const float q1 = ixz + ixx * dub + ixy * dvb;
     const float q2 = iyz + ixy * dub + iyy * dvb;
@@ -498,11 +529,11 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
     float *s_c1 = (float *)(s_c4 + 2 * NPC);                        // [2][NPC]
     const int w = p.w, h = p.h;
     const int gx0 = blockIdx.x * T::TW, gy0 = blockIdx.y * T::TH;
-    const int ox = gx0 - BROX_RMAX, oy = gy0 - BROX_RMAX;           // ox + oy is even: local colour == global colour
+    const int ox = gx0 - T::R, oy = gy0 - T::R;                     // ox + oy is even: local colour == global colour
     const int tid = threadIdx.x;
     const int ns2 = 2 * p.nsweeps;
     const float omega = p.omega, om1 = 1.0f - p.omega;
-    const unsigned thr0 = (unsigned)(BROX_RMAX - ns2);
+    const unsigned thr0 = (unsigned)(T::R - ns2);
 #ifdef SINDYN_BROX_PHASE_CLOCKS
     const bool prof_on = threadIdx.x == 0 && T::TW == 32 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2;
     long long t_prev = clock64();
@@ -722,7 +753,7 @@ int brox_init(sindyn_base *ctx, BroxSolver *b, int w, int h, float alpha, float 
     SD_CHECK(ctx->dalloc(&b->sysW, n));
     SD_CHECK(ctx->dalloc(&b->sysC4, n));
     SD_CHECK(ctx->dalloc(&b->sysC1, n));
-    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTile<8, 8>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<8, 8>::SMEM_SOR));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTileS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTileS::SMEM_SOR));
     CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTile<16, 12>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<16, 12>::SMEM_SOR));
     CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTile<24, 16>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTile<24, 16>::SMEM_SOR));
     CU_CHECK(ctx, cudaFuncSetAttribute(k_brox_sor<BroxTileL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BroxTileL::SMEM_SOR));
@@ -780,7 +811,7 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
             else LAUNCH_PDL(ctx, k_brox_level<2>, dim3(1, 1), ((npc + 1) / 2 + 31) & ~31, smem, p);
             base = out;
         } else {
-            const int tile = brox_tile_fits<BroxTile<8, 8>>(w, h) ? 0 : brox_tile_fits<BroxTile<16, 12>>(w, h) ? 1 : brox_tile_fits<BroxTile<24, 16>>(w, h) ? 2 : 3;
+            const int tile = brox_tile_fits<BroxTileS>(w, h) ? 0 : brox_tile_fits<BroxTile<16, 12>>(w, h) ? 1 : brox_tile_fits<BroxTile<24, 16>>(w, h) ? 2 : 3;
             BroxSysP sp;
             sp.Ix = b->Ix; sp.Iy = b->Iy; sp.Iz = b->Iz; sp.Ixx = b->Ixx; sp.Ixy = b->Ixy; sp.Iyy = b->Iyy; sp.Ixz = b->Ixz; sp.Iyz = b->Iyz;
             sp.u = b->u[cur]; sp.v = b->v[cur]; sp.W = b->sysW; sp.C4 = b->sysC4; sp.C1 = b->sysC1;
@@ -792,7 +823,7 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
                 sp.dub = b->du[base]; sp.dvb = b->dv[base];
                 LAUNCH_PDL(ctx, k_brox_system, dim3(cdiv(w, BSY_W), cdiv(h, BSY_H)), dim3(BSY_W, BSY_H), 0, sp);
                 while (remaining > 0) {
-                    const int chunks_left = cdiv(remaining, BROX_SMAX);
+                    const int chunks_left = cdiv(remaining, tile == 0 ? BROX_SMAX_SMALL : BROX_SMAX);
                     const int ns = cdiv(remaining, chunks_left);   // balanced chunks of <= BROX_SMAX sweeps (10 -> 5 + 5)
                     int out = 0;
                     while (out == base || out == in) ++out;
@@ -803,7 +834,7 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
                     const bool prof = b->prof_ev && b->prof_n + 2 <= b->prof_cap;
                     if (prof) cudaEventRecord(b->prof_ev[b->prof_n++], ctx->stream);
                     switch (tile) {
-                    case 0: brox_launch_sor<BroxTile<8, 8>>(ctx, q); break;
+                    case 0: brox_launch_sor<BroxTileS>(ctx, q); break;
                     case 1: brox_launch_sor<BroxTile<16, 12>>(ctx, q); break;
                     case 2: brox_launch_sor<BroxTile<24, 16>>(ctx, q); break;
                     default: brox_launch_sor<BroxTileL>(ctx, q); break;
