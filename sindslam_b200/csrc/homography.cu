@@ -122,27 +122,51 @@ __global__ void __launch_bounds__(1024) k_sample_pairs(const float2 *__restrict_
 }
 
 // ---------------------------------------------------------------- minimal solver
-__device__ bool solve8(double A[8][9])
+// 8 x 8 Gaussian elimination with partial pivoting (first largest pivot) + back substitution, spread over a warp: lane r (< 8)
+// owns row r of the augmented matrix in registers, pivot search / row swap / pivot-row broadcast go through shuffles.  Every
+// element sees exactly the operations of the textbook serial elimination in the same order (results verified bit-identical to
+// the serial version this replaced); the system never touches local memory and the row updates of a column run in parallel.
+// All 32 lanes must call it (lanes >= 8 only take part in the shuffles); the solution is returned in every lane.
+__device__ bool solve8_warp(double row[9], double x[8])
 {
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+#pragma unroll
     for (int c = 0; c < 8; ++c) {
-        int piv = c;
-        double best = fabs(A[c][c]);
-        for (int r = c + 1; r < 8; ++r)
-            if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
-        if (!(best > 1e-12)) return false;
-        if (piv != c)
-            for (int k = c; k < 9; ++k) { double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
-        double inv = 1.0 / A[c][c];
-        for (int r = c + 1; r < 8; ++r) {
-            double f = A[r][c] * inv;
-            if (f != 0.0)
-                for (int k = c; k < 9; ++k) A[r][k] -= f * A[c][k];
+        // first row r >= c with the largest |A[r][c]|
+        double best = (lane >= c && lane < 8) ? fabs(row[c]) : -1.0;
+        int piv = lane;
+        for (int o = 4; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int op = __shfl_xor_sync(0xffffffffu, piv, o);
+            if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+        }
+        best = __shfl_sync(0xffffffffu, best, 0);
+        piv = __shfl_sync(0xffffffffu, piv, 0);
+        if (!(best > 1e-12)) { ok = false; break; }
+        const int src = lane == c ? piv : (lane == piv ? c : lane);
+        double inv = 0.0, f = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) row[k] = __shfl_sync(0xffffffffu, row[k], src);   // swap rows c and piv (whole rows: columns < c are dead)
+        {
+            const double pc = __shfl_sync(0xffffffffu, row[c], c);
+            inv = 1.0 / pc;
+            f = row[c] * inv;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const double pk = __shfl_sync(0xffffffffu, row[k], c);
+            if (k >= c && lane > c && lane < 8 && f != 0.0) row[k] -= f * pk;
         }
     }
+    if (!ok) return false;
+#pragma unroll
     for (int r = 7; r >= 0; --r) {
-        double s = A[r][8];
-        for (int k = r + 1; k < 8; ++k) s -= A[r][k] * A[k][8];
-        A[r][8] = s / A[r][r];
+        double s = row[8];
+#pragma unroll
+        for (int k = r + 1; k < 8; ++k) s -= row[k] * x[k];
+        const double xr = s / row[r];
+        x[r] = __shfl_sync(0xffffffffu, xr, r);
     }
     return true;
 }
@@ -178,15 +202,15 @@ __global__ void __launch_bounds__(256) k_homog_hypotheses(const float2 *__restri
                 if (!dup) break;
             }
         }
-        double A[8][9];
-        for (int k = 0; k < 4; ++k) {
-            double x = pts[idx[k]].x, y = pts[idx[k]].y, u = pts_last[idx[k]].x, v = pts_last[idx[k]].y;
-            double r0[9] = {x, y, 1, 0, 0, 0, -u * x, -u * y, u};
-            double r1[9] = {0, 0, 0, x, y, 1, -v * x, -v * y, v};
-            for (int c = 0; c < 9; ++c) { A[2 * k][c] = r0[c]; A[2 * k + 1][c] = r1[c]; }
+        // DLT rows: lane 2k holds the u-equation of sample k, lane 2k + 1 its v-equation
+        double row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (lane < 8) {
+            const int k = lane >> 1;
+            const double x = pts[idx[k]].x, y = pts[idx[k]].y, u = pts_last[idx[k]].x, v = pts_last[idx[k]].y;
+            if (lane & 1) { row[3] = x; row[4] = y; row[5] = 1; row[6] = -v * x; row[7] = -v * y; row[8] = v; }
+            else { row[0] = x; row[1] = y; row[2] = 1; row[6] = -u * x; row[7] = -u * y; row[8] = u; }
         }
-        ok = solve8(A);
-        for (int c = 0; c < 8; ++c) h[c] = A[c][8];
+        ok = solve8_warp(row, h);
         for (int c = 0; c < 8; ++c) ok = ok && isfinite(h[c]);
     }
     int cnt = 0;
@@ -298,21 +322,31 @@ __global__ void __launch_bounds__(HG_RT) k_homog_refine(const float2 *__restrict
         final_n = tn;
         final_sse = s_tot[44];
         if (last) break;
-        if (tid == 0) {
+        if (wid == 0) {   // normal equations: warp-cooperative solve (bit-identical to the serial elimination)
             if (tn >= 8) {
-                double A[8][9];
-                int k = 0;
-                for (int a = 0; a < 8; ++a)
-                    for (int b = a; b < 8; ++b) { A[a][b] = s_tot[k]; A[b][a] = s_tot[k]; ++k; }
-                for (int a = 0; a < 8; ++a) { A[a][8] = s_tot[36 + a]; A[a][a] *= 1.0 + 1e-9; }
-                if (solve8(A)) {
+                double row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, dx[8];
+                if (lane < 8) {
+                    const int a = lane;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        const int lo = a < b ? a : b, hi = a < b ? b : a;
+                        row[b] = s_tot[lo * 8 - (lo * (lo - 1)) / 2 + (hi - lo)];
+                    }
+                    row[8] = s_tot[36 + a];
+                }
+#pragma unroll
+                for (int b = 0; b < 8; ++b)
+                    if (lane == b) row[b] *= 1.0 + 1e-9;
+                if (solve8_warp(row, dx)) {
                     bool fin = true;
                     double mx = 0.0;
-                    for (int c = 0; c < 8; ++c) { fin = fin && isfinite(A[c][8]); mx = fmax(mx, fabs(A[c][8])); }
-                    if (fin) for (int c = 0; c < 8; ++c) s_h[c] += A[c][8];
-                    if (!fin || mx < 1e-12) s_done = 1;
-                } else s_done = 1;
-            } else s_done = 1;
+                    for (int c = 0; c < 8; ++c) { fin = fin && isfinite(dx[c]); mx = fmax(mx, fabs(dx[c])); }
+                    if (lane == 0) {
+                        if (fin) for (int c = 0; c < 8; ++c) s_h[c] += dx[c];
+                        if (!fin || mx < 1e-12) s_done = 1;
+                    }
+                } else if (lane == 0) s_done = 1;
+            } else if (lane == 0) s_done = 1;
         }
         __syncthreads();
     }
