@@ -58,7 +58,15 @@ __global__ void __launch_bounds__(1024) k_sample_pairs(const float2 *__restrict_
         cw[i] = i >= 1 ? (float)counts[16 + i] / ((float)counts[i] + 1.0f) : 0.0f;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < HG_MAX_SAMPLES; k += blockDim.x) {
+    // Bitonic sort of HG_MAX_SAMPLES (weight desc, index) keys, 4 consecutive keys per thread: compare-exchange distances 1-2
+    // stay in the thread's registers, 4-64 are warp shuffles, only distances >= 128 go through shared memory (15 of the 78
+    // stages).  The keys are unique (the index is part of the key), so the order equals std::sort's on distinct weights and
+    // the stable order on equal ones.
+    static_assert(HG_MAX_SAMPLES == 4096, "4 keys per thread x 1024 threads");
+    unsigned long long e[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int k = 4 * threadIdx.x + m;
         unsigned long long key = ~0ull;
         if (k < ns) {
             int r = k / ncol, c = k - r * ncol;
@@ -71,21 +79,46 @@ __global__ void __launch_bounds__(1024) k_sample_pairs(const float2 *__restrict_
             else w = randomd + 0.4f;
             key = ((unsigned long long)f2ord_desc(w) << 32) | (unsigned)k;
         }
-        keys[k] = key;
+        e[m] = key;
     }
-    __syncthreads();
     for (int k = 2; k <= HG_MAX_SAMPLES; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < HG_MAX_SAMPLES; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = keys[i], b = keys[ixj];
-                    bool up = (i & k) == 0;
-                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+            if (j >= 128) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) keys[4 * threadIdx.x + m] = e[m];
+                __syncthreads();
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int i = 4 * threadIdx.x + m;
+                    const unsigned long long o = keys[i ^ j];
+                    const bool take_min = ((i & j) == 0) == ((i & k) == 0);
+                    e[m] = take_min ? (o < e[m] ? o : e[m]) : (o > e[m] ? o : e[m]);
                 }
+                __syncthreads();
+            } else if (j >= 4) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int i = 4 * threadIdx.x + m;
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, e[m], j >> 2);
+                    const bool take_min = ((i & j) == 0) == ((i & k) == 0);
+                    e[m] = take_min ? (o < e[m] ? o : e[m]) : (o > e[m] ? o : e[m]);
+                }
+            } else {
+                // (distances 1 and 2 spelled out: a run-time register index would push e[] into local memory)
+#define HG_CE(A, B)                                                                      \
+    {                                                                                    \
+        const bool up = ((4 * threadIdx.x + (A)) & k) == 0;                              \
+        const unsigned long long a_ = e[A], b_ = e[B];                                   \
+        if ((a_ > b_) == up) { e[A] = b_; e[B] = a_; }                                   \
+    }
+                if (j == 2) { HG_CE(0, 2) HG_CE(1, 3) }
+                else { HG_CE(0, 1) HG_CE(2, 3) }
+#undef HG_CE
             }
-            __syncthreads();
         }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) keys[4 * threadIdx.x + m] = e[m];
+    __syncthreads();
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     for (int start = 0; start < ns; start += blockDim.x) {
