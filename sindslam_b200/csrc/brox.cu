@@ -71,62 +71,6 @@ __device__ __forceinline__ float bilinear_clamped(const float *__restrict__ img,
     return top + ty * (bot - top);
 }
 
-// warp I1 by (u,v); A = (I0 + I1w)/2, Iz = I1w - I0; reset the increment
-__global__ void k_brox_warp(const float *__restrict__ I0, const float *__restrict__ I1, const float *__restrict__ u,
-                            const float *__restrict__ v, int w, int h, float *__restrict__ A, float *__restrict__ Iz,
-                            float *__restrict__ du, float *__restrict__ dv)
-{
-    pdl_wait();
-    pdl_trigger();
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    int i = y * w + x;
-    float iw = bilinear_clamped(I1, w, h, (float)x + u[i], (float)y + v[i]);
-    float i0 = I0[i];
-    A[i] = 0.5f * (i0 + iw);
-    Iz[i] = iw - i0;
-    du[i] = 0.0f;
-    dv[i] = 0.0f;
-}
-
-__device__ __forceinline__ float d5x(const float *__restrict__ f, int w, int x, int y)
-{
-    const float *r = f + y * w;
-    return (r[max(x - 2, 0)] - 8.0f * r[max(x - 1, 0)] + 8.0f * r[min(x + 1, w - 1)] - r[min(x + 2, w - 1)]) * (1.0f / 12.0f);
-}
-__device__ __forceinline__ float d5y(const float *__restrict__ f, int w, int h, int x, int y)
-{
-    return (f[max(y - 2, 0) * w + x] - 8.0f * f[max(y - 1, 0) * w + x] + 8.0f * f[min(y + 1, h - 1) * w + x]
-            - f[min(y + 2, h - 1) * w + x]) * (1.0f / 12.0f);
-}
-
-__global__ void k_brox_deriv1(const float *__restrict__ A, const float *__restrict__ Iz, int w, int h,
-                              float *__restrict__ Ix, float *__restrict__ Iy, float *__restrict__ Ixz, float *__restrict__ Iyz)
-{
-    pdl_wait();
-    pdl_trigger();
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    int i = y * w + x;
-    Ix[i] = d5x(A, w, x, y);
-    Iy[i] = d5y(A, w, h, x, y);
-    Ixz[i] = d5x(Iz, w, x, y);
-    Iyz[i] = d5y(Iz, w, h, x, y);
-}
-
-__global__ void k_brox_deriv2(const float *__restrict__ Ix, const float *__restrict__ Iy, int w, int h,
-                              float *__restrict__ Ixx, float *__restrict__ Ixy, float *__restrict__ Iyy)
-{
-    pdl_wait();
-    pdl_trigger();
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    int i = y * w + x;
-    Ixx[i] = d5x(Ix, w, x, y);
-    Ixy[i] = d5y(Ix, w, h, x, y);
-    Iyy[i] = d5y(Iy, w, h, x, y);
-}
-
 // ------------------------------------------------------------------ the solver kernels
 // Shared design of the sweep kernels (k_brox_level: small levels, one CTA, all inner iterations in one launch;
 // k_brox_sor: tiles of larger levels, one inner iteration per launch, systems precomputed by k_brox_system):
@@ -138,6 +82,71 @@ __global__ void k_brox_deriv2(const float *__restrict__ Ix, const float *__restr
 //     (1024 threads, 64 registers each);
 //   * tiles: the tile plus a 21-pixel ring lives in shared memory; the 10 fused sweeps are exact because a pixel at
 //     distance d from a halo edge stays valid for d half-sweeps (temporal blocking) and only the interior is written.
+// Warp I1 by (u, v): A = (I0 + I1w) / 2, Iz = I1w - I0; 5-tap first derivatives of A and Iz, second derivatives of A; reset the
+// increment -- one launch: a 32 x 8 tile warps its pixels plus a 4-pixel ring into shared
+// memory (the 5-tap second derivatives reach 4 pixels out; 2.5x redundant bilinear fetches, no intermediate planes through
+// L2, two launches less per pyramid level).  Border handling equals the separate kernels: every stencil tap clamps its
+// coordinate into the image, and a derivative "at" a clamped coordinate is the derivative of that border pixel.
+constexpr int BWD_W = 32, BWD_H = 8, BWD_R = 4, BWD_PW = BWD_W + 2 * BWD_R, BWD_PH = BWD_H + 2 * BWD_R;
+
+__global__ void __launch_bounds__(BWD_W *BWD_H) k_brox_warp_deriv(const float *__restrict__ I0, const float *__restrict__ I1, const float *__restrict__ u,
+                                                                  const float *__restrict__ v, int w, int h, float *__restrict__ A,
+                                                                  float *__restrict__ Iz, float *__restrict__ Ix, float *__restrict__ Iy,
+                                                                  float *__restrict__ Ixz, float *__restrict__ Iyz, float *__restrict__ Ixx,
+                                                                  float *__restrict__ Ixy, float *__restrict__ Iyy, float *__restrict__ du,
+                                                                  float *__restrict__ dv)
+{
+    __shared__ float s_A[BWD_PH][BWD_PW], s_Iz[BWD_PH][BWD_PW], s_Ix[BWD_PH][BWD_PW], s_Iy[BWD_PH][BWD_PW];
+    pdl_wait();
+    pdl_trigger();
+    const int tx0 = blockIdx.x * BWD_W - BWD_R, ty0 = blockIdx.y * BWD_H - BWD_R;   // image coordinate of shared (0, 0)
+    const int tid = threadIdx.y * BWD_W + threadIdx.x;
+    for (int i = tid; i < BWD_PW * BWD_PH; i += BWD_W * BWD_H) {
+        const int ly = i / BWD_PW, lx = i - ly * BWD_PW;
+        const int x = tx0 + lx, y = ty0 + ly;
+        if (x >= 0 && x < w && y >= 0 && y < h) {
+            const int g = y * w + x;
+            const float iw = bilinear_clamped(I1, w, h, (float)x + u[g], (float)y + v[g]);
+            const float i0 = I0[g];
+            s_A[ly][lx] = 0.5f * (i0 + iw);
+            s_Iz[ly][lx] = iw - i0;
+        }
+    }
+    __syncthreads();
+    // taps at clamped image coordinates (a clamped coordinate of a pixel within 2 of this tile's 2-ring lies inside the staged region)
+#define BWD_D5X(P, X, Y)                                                                                                       \
+    (((P)[(Y) - ty0][max((X) - 2, 0) - tx0] - 8.0f * (P)[(Y) - ty0][max((X) - 1, 0) - tx0] + 8.0f * (P)[(Y) - ty0][min((X) + 1, w - 1) - tx0] - \
+      (P)[(Y) - ty0][min((X) + 2, w - 1) - tx0]) * (1.0f / 12.0f))
+#define BWD_D5Y(P, X, Y)                                                                                                       \
+    (((P)[max((Y) - 2, 0) - ty0][(X) - tx0] - 8.0f * (P)[max((Y) - 1, 0) - ty0][(X) - tx0] + 8.0f * (P)[min((Y) + 1, h - 1) - ty0][(X) - tx0] - \
+      (P)[min((Y) + 2, h - 1) - ty0][(X) - tx0]) * (1.0f / 12.0f))
+    for (int i = tid; i < (BWD_W + 4) * (BWD_H + 4); i += BWD_W * BWD_H) {
+        const int ly = i / (BWD_W + 4) + 2, lx = i - (ly - 2) * (BWD_W + 4) + 2;
+        const int x = tx0 + lx, y = ty0 + ly;
+        if (x >= 0 && x < w && y >= 0 && y < h) {
+            s_Ix[ly][lx] = BWD_D5X(s_A, x, y);
+            s_Iy[ly][lx] = BWD_D5Y(s_A, x, y);
+        }
+    }
+    __syncthreads();
+    const int x = tx0 + BWD_R + threadIdx.x, y = ty0 + BWD_R + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int g = y * w + x;
+    A[g] = s_A[y - ty0][x - tx0];
+    Iz[g] = s_Iz[y - ty0][x - tx0];
+    Ix[g] = s_Ix[y - ty0][x - tx0];
+    Iy[g] = s_Iy[y - ty0][x - tx0];
+    Ixz[g] = BWD_D5X(s_Iz, x, y);
+    Iyz[g] = BWD_D5Y(s_Iz, x, y);
+    Ixx[g] = BWD_D5X(s_Ix, x, y);
+    Ixy[g] = BWD_D5Y(s_Ix, x, y);
+    Iyy[g] = BWD_D5Y(s_Iy, x, y);
+    du[g] = 0.0f;
+    dv[g] = 0.0f;
+#undef BWD_D5X
+#undef BWD_D5Y
+}
+
 #ifdef SINDYN_BROX_PHASE_CLOCKS
 // developer instrumentation: clock64 deltas of the centre CTA of every 32x24-tile k_brox_sor launch, summed per phase
 __device__ unsigned long long g_brox_clk[16];
@@ -791,9 +800,8 @@ static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const 
         const float *L0 = k == 0 ? I0 : b->pyr0 + b->off[k], *L1 = k == 0 ? I1 : b->pyr1 + b->off[k];
         dim3 grd(cdiv(w, 32), cdiv(h, 8));
         int base = 0;
-        LAUNCH_PDL(ctx, k_brox_warp, grd, blk, 0, L0, L1, b->u[cur], b->v[cur], w, h, b->A, b->Iz, b->du[base], b->dv[base]);
-        LAUNCH_PDL(ctx, k_brox_deriv1, grd, blk, 0, b->A, b->Iz, w, h, b->Ix, b->Iy, b->Ixz, b->Iyz);
-        LAUNCH_PDL(ctx, k_brox_deriv2, grd, blk, 0, b->Ix, b->Iy, w, h, b->Ixx, b->Ixy, b->Iyy);
+        LAUNCH_PDL(ctx, k_brox_warp_deriv, dim3(cdiv(w, BWD_W), cdiv(h, BWD_H)), dim3(BWD_W, BWD_H), 0, L0, L1, b->u[cur], b->v[cur], w, h, b->A, b->Iz,
+                   b->Ix, b->Iy, b->Ixz, b->Iyz, b->Ixx, b->Ixy, b->Iyy, b->du[base], b->dv[base]);
         BroxInnerP p;
         p.Ix = b->Ix; p.Iy = b->Iy; p.Iz = b->Iz; p.Ixx = b->Ixx; p.Ixy = b->Ixy; p.Iyy = b->Iyy; p.Ixz = b->Ixz; p.Iyz = b->Iyz;
         p.u = b->u[cur]; p.v = b->v[cur];
