@@ -8,7 +8,7 @@
 // solver_iterations red-black SOR sweeps of one lagged-nonlinearity iteration run INSIDE ONE launch (temporal
 // blocking in shared memory, k_brox_sor) after one k_brox_system launch that prepares the per-pixel systems without halo
 // redundancy; levels pick the smallest tile that still fits one wave of 148 SMs, the six coarsest levels (<= 2100 px) run
-// all inner iterations in a single one-CTA launch (k_brox_level), and the whole pyramid (about 270 launches) is captured
+// all inner iterations in a single one-CTA launch (k_brox_level), and the whole pyramid (about 320 launches) is captured
 // in one CUDA graph.
 #include "brox.cuh"
 
