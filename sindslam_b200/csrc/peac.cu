@@ -99,7 +99,10 @@ __device__ void eig33_min(const double K[3][3], double &lmin, double v[3])
         v[0] = c[0] * in; v[1] = c[1] * in; v[2] = c[2] * in;
         // Rayleigh quotient: second-order accurate eigenvalue for the refined vector
         const double w0 = a00 * v[0] + a01 * v[1] + a02 * v[2], w1 = a01 * v[0] + a11 * v[1] + a12 * v[2], w2 = a02 * v[0] + a12 * v[1] + a22 * v[2];
-        l = v[0] * w0 + v[1] * w1 + v[2] * w2;
+        const double ln = v[0] * w0 + v[1] * w1 + v[2] * w2;
+        const bool converged = pass > 0 && fabs(ln - l) <= 1e-14 * fabs(ln);   // the third pass would not move it any more
+        l = ln;
+        if (converged) break;
     }
     lmin = l;
 }
@@ -182,6 +185,14 @@ __global__ void k_peac_blocks(const uint16_t *__restrict__ depth, int W, int H, 
     nodes[b] = n;
 }
 
+// unsigned key with the order of the double (x == y <=> same key, -0 folded into +0): lets the arg-min use integer warp reductions
+__device__ __forceinline__ unsigned long long peac_key(double m)
+{
+    if (m == 0.0) m = 0.0;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(m);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
 // ---------------------------------------------------------------- AHC (Algorithm 2 edges + Algorithm 3 clustering)
 struct MergeResult { double st[9], c[3], n[3], mse; };
 
@@ -193,14 +204,17 @@ struct MergeResult { double st[9], c[3], n[3], mse; };
 // The pop / merge / extract loop is a chain of ~1000 dependent steps per frame, so everything it touches sits in shared
 // memory (structure-of-arrays, ~200 KB) and every step is spread over the CTA:
 //   * "pop the min-MSE node" is a parallel arg-min over the live queued nodes (cheaper than a binary heap walked by one
-//     thread, no stale entries); ties resolve by creation order like the oracle's insertion-ordered queue;
+//     thread, no stale entries): every thread caches the minimum of the nodes it owns and re-scans them only after one of
+//     them changed, warps reduce with three integer redux operations on an order-preserving key; ties resolve by creation
+//     order like the oracle's insertion-ordered queue;
 //   * the union-find is kept FLAT (root[] of every block is rewritten on each merge by all threads);
 //   * every thread owns a column of the edge array and compacts it lazily (edges that became internal to a node or touch
 //     an extracted node are dropped when met), so the neighbour scan shrinks as the clustering proceeds;
 //   * the distinct neighbours of the popped node are collected first (stamp + compaction), then one candidate merge
 //     (merged sums + eigen solve) runs per thread; the winning thread hands its merged plane over through shared memory;
 //   * the bookkeeping of a merge is done by warp 0 (shuffle arg-min over the 8 warp results, lanes copy the sums).
-__global__ void __launch_bounds__(256) k_peac_ahc(PeacNode *__restrict__ nodes, PeacControl *ctl, int Nw, int Nh)
+#define PEAC_AHC_NT 256   // threads of k_peac_ahc (a power of two: node b is owned by thread b & (PEAC_AHC_NT - 1))
+__global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(PeacNode *__restrict__ nodes, PeacControl *ctl, int Nw, int Nh)
 {
     extern __shared__ unsigned char smraw[];
     double *nrm = (double *)smraw;                                       // 3 x PEAC_MAXB
@@ -217,9 +231,10 @@ __global__ void __launch_bounds__(256) k_peac_ahc(PeacNode *__restrict__ nodes, 
     __shared__ unsigned short cand[PEAC_MAXCAND];
     __shared__ int s_ex[PEAC_MAXP];
     __shared__ double w_mse[8];
+    __shared__ unsigned long long w_key[8];
     __shared__ int w_o[8], w_seq[8];
     __shared__ MergeResult w_res[8];
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, nt = PEAC_AHC_NT, lane = tid & 31, wid = tid >> 5;
     const int NB = Nw * Nh;
     for (int b = tid; b < NB; b += nt) {
         root[b] = (unsigned short)b; ssize[b] = 1; stamp[b] = -1;
@@ -270,51 +285,83 @@ __global__ void __launch_bounds__(256) k_peac_ahc(PeacNode *__restrict__ nodes, 
     if (tid == 0 && s_ne > PEAC_MAXE) ctl->overflow = 1;
     int my_cnt = NE > tid ? (NE - tid + nt - 1) / nt : 0;   // live entries of this thread's edge column
     int pop_id = 0;
+    // arg-min state of this thread over the nodes it owns (b = tid, tid + nt, ...): recomputed only after one of them changed
+    unsigned long long my_key = ~0ull;   // order-preserving bit pattern of the mse (peac_key)
+    int my_p = -1, my_s = 0x7fffffff;
+    bool my_dirty = true;
+    int prev_p = -1;
     for (;;) {
         // ---- flatten the union-find after the previous merge, and arg-min (mse, seq) over the queued live nodes
         const int lose = s_lose, win = s_win;
-        double bm = 1e300;
-        int bp = -1, bs = 0x7fffffff;
-        for (int b = tid; b < NB; b += nt) {
-            if (lose >= 0 && root[b] == lose) root[b] = (unsigned short)win;
-            if ((flags[b] & (PF_ALIVE | PF_QUEUED)) == (PF_ALIVE | PF_QUEUED)) {
-                const double m = mse_a[b];
-                const int sq = seq_a[b];
-                if (m < bm || (m == bm && sq < bs)) { bm = m; bp = b; bs = sq; }
-            }
+        if (lose >= 0) {
+            for (int b = tid; b < NB; b += nt)
+                if (root[b] == lose) root[b] = (unsigned short)win;
+            if ((lose & (PEAC_AHC_NT - 1)) == tid || (win & (PEAC_AHC_NT - 1)) == tid) my_dirty = true;
         }
-        for (int off = 16; off > 0; off >>= 1) {
-            const double om = __shfl_xor_sync(0xffffffffu, bm, off);
-            const int op = __shfl_xor_sync(0xffffffffu, bp, off), os = __shfl_xor_sync(0xffffffffu, bs, off);
-            if (op >= 0 && (bp < 0 || om < bm || (om == bm && os < bs))) { bm = om; bp = op; bs = os; }
+        if (prev_p >= 0 && (prev_p & (PEAC_AHC_NT - 1)) == tid) my_dirty = true;
+        if (my_dirty) {
+            my_key = ~0ull; my_p = -1; my_s = 0x7fffffff;
+            for (int b = tid; b < NB; b += nt)
+                if ((flags[b] & (PF_ALIVE | PF_QUEUED)) == (PF_ALIVE | PF_QUEUED)) {
+                    const unsigned long long kb = peac_key(mse_a[b]);
+                    const int sq = seq_a[b];
+                    if (kb < my_key || (kb == my_key && sq < my_s)) { my_key = kb; my_p = b; my_s = sq; }
+                }
+            my_dirty = false;
         }
-        if (lane == 0) { w_mse[wid] = bm; w_o[wid] = bp; w_seq[wid] = bs; }
+        // lexicographic (mse bits, seq) minimum of the warp with three hardware reductions; seq is unique
+        auto warp_argmin = [&](unsigned long long key, int sq, int node) -> int {
+            const unsigned hi = node >= 0 ? (unsigned)(key >> 32) : 0xffffffffu, lo = (unsigned)key;
+            const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+            bool c = node >= 0 && hi == mh;
+            const unsigned ml = __reduce_min_sync(0xffffffffu, c ? lo : 0xffffffffu);
+            c = c && lo == ml;
+            const unsigned ms = __reduce_min_sync(0xffffffffu, c ? (unsigned)sq : 0xffffffffu);
+            const unsigned who = __ballot_sync(0xffffffffu, c && (unsigned)sq == ms);
+            return who ? __ffs(who) - 1 : -1;   // lane that holds the minimum, -1 = no live node in this warp
+        };
+        {
+            const int wl = warp_argmin(my_key, my_s, my_p);
+            const int src = wl >= 0 ? wl : 0;
+            const unsigned long long k0 = __shfl_sync(0xffffffffu, my_key, src);
+            const int p0 = __shfl_sync(0xffffffffu, my_p, src), s0 = __shfl_sync(0xffffffffu, my_s, src);
+            if (lane == 0) { w_key[wid] = k0; w_o[wid] = wl >= 0 ? p0 : -1; w_seq[wid] = s0; }
+        }
         __syncthreads();
         int p = -1;
         {
-            double pm = 1e300;
-            int ps = 0x7fffffff;
-            for (int k = 0; k < 8; ++k)
-                if (w_o[k] >= 0 && (p < 0 || w_mse[k] < pm || (w_mse[k] == pm && w_seq[k] < ps))) { p = w_o[k]; pm = w_mse[k]; ps = w_seq[k]; }
+            const int o8 = lane < 8 ? w_o[lane] : -1;
+            const int wl = warp_argmin(lane < 8 ? w_key[lane] : ~0ull, lane < 8 ? w_seq[lane] : 0x7fffffff, o8);
+            p = wl >= 0 ? __shfl_sync(0xffffffffu, o8, wl) : -1;
         }
+        prev_p = p;
         if (p < 0) break;
         ++pop_id;
-        // ---- distinct live graph neighbours of p (AHCPlaneFitter.hpp:1092-1117); lazy compaction of the edge column
-        for (int i = 0; i < my_cnt;) {
+        // ---- distinct live graph neighbours of p (AHCPlaneFitter.hpp:1092-1117).  The scan itself has independent iterations
+        // (the loads of several edges are in flight together); dead edges (internal to a node, or touching an extracted
+        // node) are only skipped here and compacted out of the thread's edge column every 16th pop.
+        if ((pop_id & 15) == 0) {
+            for (int i = 0; i < my_cnt;) {
+                const int e = i * nt + tid;
+                const int ru = root[eu[e]], rv = root[ev[e]];
+                if (ru == rv || !(flags[ru] & PF_ALIVE) || !(flags[rv] & PF_ALIVE)) {   // edge is gone for good
+                    const int last = (my_cnt - 1) * nt + tid;
+                    eu[e] = eu[last]; ev[e] = ev[last];
+                    --my_cnt;
+                    continue;
+                }
+                ++i;
+            }
+        }
+#pragma unroll 4
+        for (int i = 0; i < my_cnt; ++i) {
             const int e = i * nt + tid;
             const int ru = root[eu[e]], rv = root[ev[e]];
-            if (ru == rv || !(flags[ru] & PF_ALIVE) || !(flags[rv] & PF_ALIVE)) {   // edge is gone for good
-                const int last = (my_cnt - 1) * nt + tid;
-                eu[e] = eu[last]; ev[e] = ev[last];
-                --my_cnt;
-                continue;
-            }
             const int o = ru == p ? rv : (rv == p ? ru : -1);
-            if (o >= 0 && atomicExch(&stamp[o], pop_id) != pop_id) {
+            if (o >= 0 && o != p && (flags[o] & PF_ALIVE) && atomicExch(&stamp[o], pop_id) != pop_id) {
                 const int slot = atomicAdd(&s_ncand, 1);
                 if (slot < PEAC_MAXCAND) cand[slot] = (unsigned short)o;
             }
-            ++i;
         }
         __syncthreads();
         const int ncand = min(s_ncand, PEAC_MAXCAND);
@@ -674,7 +721,7 @@ int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t 
     const size_t smem = PEAC_AHC_SMEM;
     CU_CHECK(ctx, cudaMemsetAsync(im->ctl, 0, (4 + 128) * sizeof(int), ctx->stream));
     LAUNCH(ctx, k_peac_blocks, cdiv(NB, 64), 64, 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->nodes);
-    LAUNCH(ctx, k_peac_ahc, 1, 256, smem, im->nodes, im->ctl, Nw, Nh);
+    LAUNCH(ctx, k_peac_ahc, 1, PEAC_AHC_NT, smem, im->nodes, im->ctl, Nw, Nh);
     LAUNCH(ctx, k_peac_blockmap, cdiv(NB, 128), 128, 0, im->ctl, Nw, Nh);
     const dim3 blk(32, 8), grd(cdiv(W, 32), cdiv(H, 8));
     LAUNCH(ctx, k_peac_init_labels, grd, blk, 0, im->ctl, W, H, Nw, im->label, im->dist);
