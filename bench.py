@@ -240,7 +240,7 @@ def full_pipeline_stats(cam, frames, device, refine):
                                   "note": "host C-ABI calls with pageable numpy buffers (H2D + D2H inside), not counted in pairs_per_s"}}
 
 
-def multi_sequence_stats(cam, device, refine, n_seq=4, steps=24):
+def multi_sequence_stats(cam, device, refine, n_seq=8, steps=24):
     """Batched throughput ('report both single-frame latency and batched throughput'): n_seq independent
     sequences on ONE GPU, one handle + stream + host thread each, device-resident frames.  A single sequence leaves most
     of the chip idle (the coarse pyramid levels run on a handful of SMs), so concurrent sequences overlap."""
@@ -294,7 +294,10 @@ def run_ours(args):
     cam, frames = make_frames(replicas.sequence_seed_index(rank))
     refine = 0 if args.no_refine else 1
     sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=local, refine=refine)
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream for the handle, the L2 flush and the timing events: torch's default stream has handle
+    # 0, which sindyn_set_stream reads as "use the handle's own stream" -- events recorded there would not bracket the work
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     sd.set_stream(stream.cuda_stream)
     for i, f in enumerate(frames):
         sd.upload_frame(i, f.bgr, f.depth)

@@ -97,8 +97,9 @@ int sindyn_get_detect_results(sindyn_handle h, uint8_t *mask, uint8_t *labels);
  * roll != 0 additionally rolls imgRGBLastLast <- imgRGBLast <- cur (DynaDetect.cc:1661-1662) so that a
  * sequence can be streamed through this entry point alone (BASELINE config "flow + residual"). */
 int sindyn_flow_residual(sindyn_handle h, const uint8_t *bgr, size_t bgr_step, uint8_t *mask_low, uint8_t *mask_high, int roll);
-/* Same on a frame staged with sindyn_upload_frame: no host traffic, no synchronize except the
- * large-motion decision (which the reference also takes on the host, DynaDetect.cc:1073-1114). */
+/* Same on a frame staged with sindyn_upload_frame: no host traffic and no synchronisation -- with use_graphs the
+ * whole flow branch is one CUDA graph whose large-motion decision (taken on the host by the reference,
+ * DynaDetect.cc:1073-1114) is a conditional node; the flag is reported by sindyn_get_flow_results. */
 int sindyn_flow_residual_resident(sindyn_handle h, int slot, int roll);
 /* Copy out the device-resident results of the last flow_residual call (any pointer may be NULL):
  * flow W x H x 2 float, H 3x3 double, thresholds[4], masks. */

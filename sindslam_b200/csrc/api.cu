@@ -91,6 +91,7 @@ extern "C" int sindyn_destroy(sindyn_handle h)
     brox_destroy(&h->brox);
     brox_destroy(&h->brox_lm);
     flow_tail_drop_graphs(h);
+    flow_graph_drop(h);
     sindyn_ctx_destroy_stages(h);
     h->free_all();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -110,6 +111,7 @@ extern "C" int sindyn_set_stream(sindyn_handle h, void *s)
         h->brox.graph_ok = false;
         h->brox_lm.graph_ok = false;  // graphs are stream-agnostic, but re-capture keeps capture semantics simple
         flow_tail_drop_graphs(h);
+        flow_graph_drop(h);
     }
     return SINDYN_OK;
 }

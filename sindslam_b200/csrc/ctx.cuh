@@ -66,6 +66,11 @@ struct sindyn_ctx : sindyn_base {
     struct TailGraph { cudaGraphExec_t exec = nullptr; const uint8_t *k0 = nullptr, *k1 = nullptr; cudaStream_t stream = nullptr; unsigned long long launches = 0; };
     TailGraph tail[8];                // captured post-decision part of the flow branch, per frame-ring position
     int tail_next = 0;
+    struct FlowGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; const uint8_t *k0 = nullptr, *k1 = nullptr, *k2 = nullptr; cudaStream_t stream = nullptr; unsigned long long launches = 0, body_launches = 0; };
+    FlowGraph flow_graph[4];          // the whole flow branch incl. the device-side large-motion decision (flow.cu), per ring position
+    FlowGraph *flow_graph_last = nullptr;
+    int flow_graph_next = 0;
+    bool flow_one_graph = true, flow_graph_broken = false, flow_graph_active = false, flow_flag_pending = false;
     cudaGraphExec_t cluster_graph = nullptr;   // captured clustering branch (three streams, no host decisions)
     cudaStream_t cluster_graph_stream = nullptr;
     unsigned long long cluster_graph_launches = 0;
@@ -88,6 +93,8 @@ int flow_branch_begin(sindyn_ctx *c);                   // flow.cu
 int flow_branch_finish(sindyn_ctx *c, int *large_motion);  // flow.cu
 int flow_finish_all(sindyn_ctx *c, int *large_motion);     // flow.cu: finish + homography + residual/masks (marks ev[3..5])
 void flow_tail_drop_graphs(sindyn_ctx *c);                 // flow.cu
+void flow_graph_drop(sindyn_ctx *c);                       // flow.cu
+void flow_collect_flag(sindyn_ctx *c);                     // flow.cu: large-motion flag of the last flow-graph launch (after a sync)
 int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll);  // pipeline.cu
 int sindyn_ctx_init_stages(sindyn_ctx *c);              // stages.cu
 void sindyn_ctx_destroy_stages(sindyn_ctx *c);          // stages.cu

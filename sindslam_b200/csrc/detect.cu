@@ -56,6 +56,7 @@ static int check_capacity(sindyn_ctx *c)
     CU_CHECK(c, cudaMemcpyAsync(&ctl, c->rc.ctl, sizeof ctl, cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaMemcpyAsync(sc, c->edges.scalars, sizeof sc, cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    flow_collect_flag(c);
     if (ctl.overflow) { c->err = "recluster: more than RC_MAXC components"; return SINDYN_ERR_CAPACITY; }
     if (ctl.pf_overflow) { c->err = "plane-edge filter: more than RC_PF_MAXC contours"; return SINDYN_ERR_CAPACITY; }
     if (sc[3]) { c->err = "depth_edges: more than EDGE_EP_CAP candidate end points"; return SINDYN_ERR_CAPACITY; }

@@ -3,6 +3,8 @@
 // refinement -> up-sample x 1/0.6 -> sample weighting -> homography.
 #include "ctx.cuh"
 
+#include <cstdio>
+
 #define H_CHECK(h)                       \
     if (!(h)) return SINDYN_ERR_INVALID; \
     cudaSetDevice((h)->device)
@@ -37,8 +39,9 @@ __global__ void k_u8_hist(const float *__restrict__ mag, int n, const unsigned i
 }
 
 // DynaDetect.cc:1097-1114
+// cond / use_cond: inside the captured flow graph the flag also drives the IF node that holds the second Brox solve
 __global__ void k_large_motion(const unsigned int *__restrict__ hist, const unsigned int *__restrict__ gmax, int W, int H, float scale_element,
-                               int *__restrict__ out)
+                               int *__restrict__ out, cudaGraphConditionalHandle cond, int use_cond)
 {
     if (threadIdx.x || blockIdx.x) return;
     double maxFlow = (double)__uint_as_float(*gmax);
@@ -54,6 +57,7 @@ __global__ void k_large_motion(const unsigned int *__restrict__ hist, const unsi
     out[0] = endFlow2 > endFlow ? 1 : 0;
     out[1] = endFlow;
     out[2] = endFlow2;
+    if (use_cond) cudaGraphSetConditional(cond, endFlow2 > endFlow ? 1u : 0u);
 }
 
 int flow_branch_init(sindyn_ctx *c)
@@ -68,6 +72,138 @@ int flow_branch_init(sindyn_ctx *c)
     return SINDYN_OK;
 }
 
+// ---------------------------------------------------------------- the whole flow branch as ONE graph
+// Brox(cur, lastlast) -> large-motion statistics -> IF(large motion) { Brox(cur, last) } -> refinement (reference image chosen by
+// the same device flag) -> up-sampling -> sample weighting + homography -> residual + thresholds -> masks.  The large-motion
+// decision, which the reference takes on the host after a D2H copy (DynaDetect.cc:1073-1114), is a conditional graph node:
+// no host round trip in the middle of the frame, one graph launch per frame.  One graph per frame-ring position (the key is
+// the triple of resident gray images).  Graph construction mixes stream capture with one explicitly added IF node.
+void flow_graph_drop(sindyn_ctx *c)
+{
+    for (auto &t : c->flow_graph) {
+        if (t.exec) cudaGraphExecDestroy(t.exec);
+        if (t.graph) cudaGraphDestroy(t.graph);
+        t = sindyn_ctx::FlowGraph();
+    }
+    c->flow_graph_next = 0;
+}
+
+static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t)
+{
+    const int nf = c->fw * c->fh;
+    cudaGraph_t g = nullptr;
+    CU_CHECK(c, cudaGraphCreate(&g, 0));
+    t->graph = g;
+    cudaGraphConditionalHandle cond;
+    CU_CHECK(c, cudaGraphConditionalHandleCreate(&cond, g, 0, cudaGraphCondAssignDefault));
+    const unsigned long long before = c->launches;
+    CU_CHECK(c, cudaStreamBeginCaptureToGraph(c->stream, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    int st = brox_run(c, &c->brox, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_lastlast], c->flow_small, -1.0f, false);
+    unsigned int *gmax = c->fb_hist + 256;
+    cudaGraphNode_t cnode = nullptr;
+    cudaGraph_t body = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (st == SINDYN_OK) {
+        e = cudaMemsetAsync(c->fb_hist, 0, sizeof(unsigned int) * 260, c->stream);
+        LAUNCH(c, k_flow_mag, cdiv(nf, 256), 256, 0, (const float2 *)c->flow_small, nf, c->fb_mag, gmax);
+        LAUNCH(c, k_u8_hist, SINDYN_NUM_SMS_B200, 256, 0, c->fb_mag, nf, gmax, c->fb_hist);
+        LAUNCH(c, k_large_motion, 1, 32, 0, c->fb_hist, gmax, c->W, c->H, c->cfg.flow_scale, c->fb_flag, cond, 1);
+        // the IF node hangs off everything captured so far; what is captured next hangs off the IF node
+        cudaStreamCaptureStatus cs;
+        const cudaGraphNode_t *deps = nullptr;
+        size_t ndeps = 0;
+        if (e == cudaSuccess) e = cudaStreamGetCaptureInfo_v2(c->stream, &cs, nullptr, nullptr, &deps, &ndeps);
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};   // (aggregate initialisation: the union member has no default constructor)
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = cond;
+        cp.conditional.type = cudaGraphCondTypeIf;
+        cp.conditional.size = 1;
+        if (e == cudaSuccess) e = cudaGraphAddNode(&cnode, g, deps, ndeps, &cp);
+        if (e == cudaSuccess) body = cp.conditional.phGraph_out[0];
+        if (e == cudaSuccess) e = cudaStreamUpdateCaptureDependencies(c->stream, &cnode, 1, cudaStreamSetCaptureDependencies);
+    }
+    if (st == SINDYN_OK && e == cudaSuccess) {
+        if (c->cfg.refine)
+            st = varref_run_sel(c, &c->varref, c->gsmall[c->i_cur], c->gsmall[c->i_lastlast], c->gsmall[c->i_last], c->fb_flag, c->flow_small);
+        if (st == SINDYN_OK) st = launch_resize_flow(c, c->flow_small, c->fw, c->fh, c->flow_full, c->W, c->H, 1.0f / c->cfg.flow_scale);
+        if (st == SINDYN_OK) st = homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last);
+        if (st == SINDYN_OK) st = homography_estimate(c, &c->homog);
+        if (st == SINDYN_OK) st = residual_homography_run_dev(c, &c->resid, c->flow_full, c->homog.H_dev, c->mask_low, c->mask_high);
+        if (st == SINDYN_OK) e = cudaMemcpyAsync(c->fb_flag_host, c->fb_flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream);
+    }
+    cudaGraph_t g_out = nullptr;
+    const cudaError_t e_end = cudaStreamEndCapture(c->stream, &g_out);
+    t->launches = c->launches - before;
+    // body of the IF node: the second Brox solve (its own solver object: both flows' scratch stays alive)
+    cudaError_t e_body = cudaSuccess;
+    unsigned long long body_launches = 0;
+    if (st == SINDYN_OK && e == cudaSuccess && e_end == cudaSuccess && body) {
+        const unsigned long long b0 = c->launches;
+        e_body = cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+        if (e_body == cudaSuccess) {
+            st = brox_run(c, &c->brox_lm, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_last], c->flow_small, -1.0f, false);
+            cudaGraph_t b_out = nullptr;
+            e_body = cudaStreamEndCapture(c->stream, &b_out);
+        }
+        body_launches = c->launches - b0;
+    }
+    c->launches = before;
+    SD_CHECK(st);
+    CU_CHECK(c, e);
+    CU_CHECK(c, e_end);
+    CU_CHECK(c, e_body);
+    CU_CHECK(c, cudaGraphInstantiate(&t->exec, g, 0));
+    t->body_launches = body_launches;
+    t->k0 = c->gsmall[c->i_cur]; t->k1 = c->gsmall[c->i_last]; t->k2 = c->gsmall[c->i_lastlast]; t->stream = c->stream;
+    return SINDYN_OK;
+}
+
+// launches the flow graph of the current frame-ring position; returns SINDYN_OK with *launched = false when this device /
+// driver cannot build it (the caller then takes the two-graph path with the host decision)
+static int flow_graph_launch(sindyn_ctx *c, bool *launched)
+{
+    *launched = false;
+    if (c->flow_graph_broken) return SINDYN_OK;
+    const uint8_t *k0 = c->gsmall[c->i_cur], *k1 = c->gsmall[c->i_last], *k2 = c->gsmall[c->i_lastlast];
+    sindyn_ctx::FlowGraph *t = nullptr;
+    for (auto &q : c->flow_graph)
+        if (q.exec && q.k0 == k0 && q.k1 == k1 && q.k2 == k2 && q.stream == c->stream) t = &q;
+    if (!t) {
+        t = &c->flow_graph[c->flow_graph_next];
+        c->flow_graph_next = (c->flow_graph_next + 1) % 4;
+        if (t->exec) cudaGraphExecDestroy(t->exec);
+        if (t->graph) cudaGraphDestroy(t->graph);
+        *t = sindyn_ctx::FlowGraph();
+        if (flow_graph_build(c, t) != SINDYN_OK) {
+            // leave capture mode if the failure happened inside it, remember not to try again
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(c->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(c->stream, &junk); }
+            cudaGetLastError();
+            if (t->exec) cudaGraphExecDestroy(t->exec);
+            if (t->graph) cudaGraphDestroy(t->graph);
+            *t = sindyn_ctx::FlowGraph();
+            c->flow_graph_broken = true;
+            fprintf(stderr, "sindyn: one-graph flow branch unavailable (%s); using the two-graph path with the host decision\n", c->err.c_str());
+            return SINDYN_OK;
+        }
+    }
+    CU_CHECK(c, cudaGraphLaunch(t->exec, c->stream));
+    c->launches += t->launches;   // (+ t->body_launches on large-motion frames: added when the flag is read)
+    c->flow_graph_last = t;
+    c->flow_flag_pending = true;
+    *launched = true;
+    return SINDYN_OK;
+}
+
+// the large-motion flag of the last flow-graph launch, valid after the stream has been synchronised
+void flow_collect_flag(sindyn_ctx *c)
+{
+    if (!c->flow_flag_pending) return;
+    c->flow_flag_pending = false;
+    c->large_motion_last = c->fb_flag_host[0];
+    if (c->large_motion_last && c->flow_graph_last) c->launches += c->flow_graph_last->body_launches;
+}
+
 // Runs on the handle's resident frames (gsmall_f / gsmall of cur, last, lastlast). Result: c->flow_full.
 // Split in two so that a caller can enqueue other work between the first Brox solve and the host decision:
 //   flow_branch_begin: Brox(cur, lastlast), large-motion statistics, asynchronous copy of the flag
@@ -77,13 +213,19 @@ int flow_branch_begin(sindyn_ctx *c)
 {
     const bool g = c->cfg.use_graphs != 0;
     const int nf = c->fw * c->fh;
+    c->flow_graph_active = false;
+    if (g && !c->cfg.stage_timing && c->flow_one_graph) {
+        bool launched = false;
+        SD_CHECK(flow_graph_launch(c, &launched));
+        if (launched) { c->flow_graph_active = true; return SINDYN_OK; }
+    }
     SD_CHECK(brox_run(c, &c->brox, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_lastlast], c->flow_small, -1.0f, g));
     if (c->cfg.stage_timing && c->ev_ok) CU_CHECK(c, cudaEventRecord(c->ev[2], c->stream));
     CU_CHECK(c, cudaMemsetAsync(c->fb_hist, 0, sizeof(unsigned int) * 260, c->stream));
     unsigned int *gmax = c->fb_hist + 256;
     LAUNCH(c, k_flow_mag, cdiv(nf, 256), 256, 0, (const float2 *)c->flow_small, nf, c->fb_mag, gmax);
     LAUNCH(c, k_u8_hist, SINDYN_NUM_SMS_B200, 256, 0, c->fb_mag, nf, gmax, c->fb_hist);
-    LAUNCH(c, k_large_motion, 1, 32, 0, c->fb_hist, gmax, c->W, c->H, c->cfg.flow_scale, c->fb_flag);
+    LAUNCH(c, k_large_motion, 1, 32, 0, c->fb_hist, gmax, c->W, c->H, c->cfg.flow_scale, c->fb_flag, (cudaGraphConditionalHandle)0, 0);
     LAUNCH_CHECK(c);
     CU_CHECK(c, cudaMemcpyAsync(c->fb_flag_host, c->fb_flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaEventRecord(c->ev_flag, c->stream));
@@ -129,6 +271,10 @@ void flow_tail_drop_graphs(sindyn_ctx *c)
 
 int flow_finish_all(sindyn_ctx *c, int *large_motion)
 {
+    if (c->flow_graph_active) {   // everything is already enqueued; the flag arrives with the next synchronisation
+        if (large_motion) *large_motion = c->large_motion_last;
+        return SINDYN_OK;
+    }
     const bool timing = c->cfg.stage_timing && c->ev_ok;
     const bool g = c->cfg.use_graphs != 0 && !c->cfg.stage_timing;
     CU_CHECK(c, cudaEventSynchronize(c->ev_flag));

@@ -85,6 +85,7 @@ extern "C" int sindyn_flow_residual(sindyn_handle h, const uint8_t *bgr, size_t 
     if (mask_low) CU_CHECK(h, stage_out_begin(lo_direct ? (void *)mask_low : (void *)h->pin_out0, h->mask_low, h->N, h->stream));
     if (mask_high) CU_CHECK(h, stage_out_begin(hi_direct ? (void *)mask_high : (void *)h->pin_out1, h->mask_high, h->N, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    flow_collect_flag(h);
     if (mask_low && !lo_direct) stage_out_finish(mask_low, 0, h->pin_out0, h->N, 1);
     if (mask_high && !hi_direct) stage_out_finish(mask_high, 0, h->pin_out1, h->N, 1);
     return collect_stage_ms(h, 5);
@@ -107,6 +108,7 @@ extern "C" int sindyn_get_flow_results(sindyn_handle h, float *flow, double *H_o
     if (mask_low) CU_CHECK(h, cudaMemcpyAsync(mask_low, h->mask_low, h->N, cudaMemcpyDeviceToHost, h->stream));
     if (mask_high) CU_CHECK(h, cudaMemcpyAsync(mask_high, h->mask_high, h->N, cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    flow_collect_flag(h);
     if (large_motion) *large_motion = h->large_motion_last;
     if (h->cfg.stage_timing) collect_stage_ms(h, 5);
     return SINDYN_OK;

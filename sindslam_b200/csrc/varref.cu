@@ -25,10 +25,14 @@
 enum { P_A = 0, P_IZ, P_IX, P_IY, P_IXZ, P_IYZ, P_IXX, P_IXY, P_IYY, P_WU, P_WV, P_DU, P_DV, P_WGT, P_A11, P_A12, P_A22, P_B1, P_B2, P_DU2, P_DV2, P_COUNT };
 
 // cv::remap(I1 as float, x + u, y + v, INTER_LINEAR, BORDER_REPLICATE) + averaged image + temporal difference
-__global__ void k_vr_warp(const uint8_t *__restrict__ I0, const uint8_t *__restrict__ I1, const float2 *__restrict__ flow, int w, int h,
+// (I1_alt, sel): when sel is non-null and *sel != 0 the reference image is I1_alt -- the large-motion decision taken on the
+// device inside the captured flow graph (flow.cu)
+__global__ void k_vr_warp(const uint8_t *__restrict__ I0, const uint8_t *__restrict__ I1_def, const uint8_t *__restrict__ I1_alt,
+                          const int *__restrict__ sel, const float2 *__restrict__ flow, int w, int h,
                           float *__restrict__ A, float *__restrict__ Iz, float *__restrict__ Wu, float *__restrict__ Wv, float *__restrict__ du,
                           float *__restrict__ dv)
 {
+    const uint8_t *__restrict__ I1 = (sel && *sel) ? I1_alt : I1_def;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
     const int i = y * w + x;
@@ -241,12 +245,14 @@ int varref_init(sindyn_base *ctx, VarRefStage *v, int w, int h)
     return SINDYN_OK;
 }
 
-int varref_run(sindyn_base *ctx, VarRefStage *v, const uint8_t *I0, const uint8_t *I1, float *flow)
+int varref_run(sindyn_base *ctx, VarRefStage *v, const uint8_t *I0, const uint8_t *I1, float *flow) { return varref_run_sel(ctx, v, I0, I1, nullptr, nullptr, flow); }
+
+int varref_run_sel(sindyn_base *ctx, VarRefStage *v, const uint8_t *I0, const uint8_t *I1, const uint8_t *I1_alt, const int *sel, float *flow)
 {
     const int w = v->w, h = v->h;
     const dim3 blk(32, 8), grd(cdiv(w, 32), cdiv(h, 8));
     float **p = v->planes;
-    LAUNCH(ctx, k_vr_warp, grd, blk, 0, I0, I1, (const float2 *)flow, w, h, p[P_A], p[P_IZ], p[P_WU], p[P_WV], p[P_DU], p[P_DV]);
+    LAUNCH(ctx, k_vr_warp, grd, blk, 0, I0, I1, I1_alt, sel, (const float2 *)flow, w, h, p[P_A], p[P_IZ], p[P_WU], p[P_WV], p[P_DU], p[P_DV]);
     LAUNCH(ctx, k_vr_deriv1, grd, blk, 0, p[P_A], p[P_IZ], w, h, p[P_IX], p[P_IY], p[P_IXZ], p[P_IYZ]);
     LAUNCH(ctx, k_vr_deriv2, grd, blk, 0, p[P_IX], p[P_IY], w, h, p[P_IXX], p[P_IXY], p[P_IYY]);
     const dim3 grdf(cdiv(w, VRT_W), cdiv(h, VRT_H));

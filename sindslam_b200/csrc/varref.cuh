@@ -13,3 +13,5 @@ struct VarRefStage {
 int varref_init(sindyn_base *ctx, VarRefStage *v, int w, int h);
 // I0, I1: u8 w x h device images (I0 = current); flow: w x h x 2 interleaved, refined in place
 int varref_run(sindyn_base *ctx, VarRefStage *v, const uint8_t *I0, const uint8_t *I1, float *flow);
+// same with the reference image chosen on the device: I1_alt when *sel != 0 (sel may be null)
+int varref_run_sel(sindyn_base *ctx, VarRefStage *v, const uint8_t *I0, const uint8_t *I1, const uint8_t *I1_alt, const int *sel, float *flow);
