@@ -72,7 +72,11 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (host time of arrival, csv line)
+        self.t_begin = None      # samples before this host time are dropped (nvidia-smi is started early: it needs ~0.5 s to come up)
+
+    def begin_window(self):
+        self.t_begin = time.perf_counter()
 
     def start(self):
         try:
@@ -84,7 +88,7 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -92,7 +96,9 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if self.t_begin is not None and t < self.t_begin:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -311,14 +317,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     order = [(2 + i) % N_FRAMES for i in range(args.warmup + args.steps)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.6)          # let nvidia-smi come up so that short runs still get samples under load
+        clocks.begin_window()    # window = warm-up steps + both timed regions: one stretch of continuous load
     # ---------------- device-resident throughput
     for i in range(args.warmup):
         flush.fill_(i & 255)
         sd.flow_residual_resident(order[i], roll=True)
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = sd.launches
     n_large = 0
