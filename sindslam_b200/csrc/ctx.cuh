@@ -89,7 +89,7 @@ struct sindyn_ctx : sindyn_base {
 int sindyn_prep_frame(sindyn_ctx *c, int idx);          // api.cu: BGR -> gray -> 0.6x gray (u8 + float)
 int flow_branch_init(sindyn_ctx *c);                    // flow.cu
 int flow_branch_run(sindyn_ctx *c, int *large_motion);  // flow.cu
-int flow_branch_begin(sindyn_ctx *c);                   // flow.cu
+int flow_branch_begin(sindyn_ctx *c, bool whole_frame);  // flow.cu
 int flow_branch_finish(sindyn_ctx *c, int *large_motion);  // flow.cu
 int flow_finish_all(sindyn_ctx *c, int *large_motion);     // flow.cu: finish + homography + residual/masks (marks ev[3..5])
 void flow_tail_drop_graphs(sindyn_ctx *c);                 // flow.cu

@@ -76,7 +76,7 @@ static int detect_run(sindyn_ctx *c)
     // ---- flow branch, first part: the Brox solve is one graph launch, so the GPU starts on the critical path at once
     SD_CHECK(sindyn_prep_frame(c, c->i_cur));
     MARK(c, 1);
-    SD_CHECK(flow_branch_begin(c));      // marks ev[2] after the first Brox solve
+    SD_CHECK(flow_branch_begin(c, true));      // marks ev[2] after the first Brox solve
     // ---- clustering branch on stream2 (+ stream3 for the plane fitter): ~300 launches without a host decision.  With
     // use_graphs it is captured once (cross-stream fork / join included) and replayed as ONE graph launch per frame.
     CU_CHECK(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));

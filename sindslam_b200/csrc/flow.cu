@@ -209,12 +209,14 @@ void flow_collect_flag(sindyn_ctx *c)
 //   flow_branch_begin: Brox(cur, lastlast), large-motion statistics, asynchronous copy of the flag
 //   flow_branch_finish: wait for the flag (the only host decision of the flow branch; the reference does the same D2H + sync,
 //                       DynaDetect.cc:1073), optional Brox(cur, last), refinement, up-sampling
-int flow_branch_begin(sindyn_ctx *c)
+// whole_frame: the caller will go on with flow_finish_all (homography, residual, masks), so the entire flow branch may be
+// launched as the one captured graph; the stage-level entry point (flow only) passes false
+int flow_branch_begin(sindyn_ctx *c, bool whole_frame)
 {
     const bool g = c->cfg.use_graphs != 0;
     const int nf = c->fw * c->fh;
     c->flow_graph_active = false;
-    if (g && !c->cfg.stage_timing && c->flow_one_graph) {
+    if (whole_frame && g && !c->cfg.stage_timing && c->flow_one_graph) {
         bool launched = false;
         SD_CHECK(flow_graph_launch(c, &launched));
         if (launched) { c->flow_graph_active = true; return SINDYN_OK; }
@@ -327,7 +329,7 @@ int flow_finish_all(sindyn_ctx *c, int *large_motion)
 
 int flow_branch_run(sindyn_ctx *c, int *large_motion)
 {
-    SD_CHECK(flow_branch_begin(c));
+    SD_CHECK(flow_branch_begin(c, false));
     return flow_branch_finish(c, large_motion);
 }
 

@@ -34,7 +34,7 @@ int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll)
     SD_CHECK(sindyn_prep_frame(c, c->i_cur));
     STAGE_MARK(c, 1);
     int lm = 0;
-    SD_CHECK(flow_branch_begin(c));      // marks ev[2] (after Brox) itself
+    SD_CHECK(flow_branch_begin(c, true));      // marks ev[2] (after Brox) itself
     SD_CHECK(flow_finish_all(c, &lm));   // marks ev[3], ev[4], ev[5]
     c->large_motion_last = lm;
     if (roll) {  // imgRGBLastLast <- imgRGBLast <- cur (DynaDetect.cc:1661-1662): index rotation, no copies
