@@ -1,30 +1,40 @@
 #!/usr/bin/env python
-"""bench.py -- dyn-detect frame pairs/s at 640x480 (BASELINE.json metric).
+"""bench.py -- dyn-detect frame pairs/s at 640x480 (BASELINE.json metric) on the metric's workload.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--sequences S]
 
-Workload (BASELINE.json configs[1]): one 640x480 frame pair per step through the flow + ego-motion
-residual branch (DynaDetect::DetectDynaByDenseOpticalFLow, DynaDetect.cc:1023-1374): gray/resize, Brox dense
-flow with the reference's parameters, large-motion test, variational refinement, up-sampling, sample weighting,
-robust homography, residual, Otsu/Triangle thresholds, two masks.  A synthetic TUM-format RGB-D sequence is
-streamed in order (one per rank, seed 20241108 + rank); the wrap-around of the frame cycle triggers the
-reference's large-motion fallback (a second Brox solve) exactly as a real sequence would.
+Workload (BASELINE.json configs[2]): the FULL per-frame dynamic-region pipeline of the driver loop
+(rgbd_tum_noros.cc:113-192) over a 300-frame synthetic walking_xyz-shaped 640x480 TUM-format sequence:
+DynaDetect::DetectDynaArea (DynaDetect.cc:1377-1666: gray/resize, Brox dense flow with the reference's parameters,
+large-motion test, variational refinement, up-sampling, sample weighting, robust homography, residual, Otsu/Triangle
+masks || 4-level k-means, gradient depth edges, PEAC plane edges, plane-edge filter, split / RAG / merge re-clustering ||
+per-cluster decision, final mask, state roll), the driver's 15x15 dilation (rgbd_tum_noros.cc:136-139) and the masked
+ORBextractor::operator() (ORBextractor.cc:1043-1164; 1500 features, 8 levels, TUM3.yaml).  Depth holes are isolated
+pixels at a 0.05 % rate, so the PEAC plane fitter has planes to fit (it rejects every 16x16 block containing a hole)
+and is busy on every frame.
 
-value    : pairs/s, frames resident in HBM (device slots), CUDA-event time summed over the K steps, L2 flushed
-           between steps (256 MiB write), max over ranks.
-e2e      : pairs/s through the host C-ABI call sindyn_flow_residual with pinned HOST buffers: H2D of the BGR frame
-           and D2H of both masks inside the timed region.
-roofline : the temporally blocked red-black SOR kernel (k_brox_sor: 5 sweeps of one lagged-nonlinearity iteration of
-           one pyramid level per launch) timed per launch with CUDA events on the handle's stream
-           (sindyn_brox_profile); algorithmic bytes = sweeps of the launch x 52 B per pixel x the
-           pixels one launch covers.
-cpu_baseline / --impl reference: the reference's CPU path restated in oracle/ (checker code), timed on the
-           host cores of this box on a bounded sample of the same sequence.
+One STEP = FRAMES_PER_STEP (15) consecutive frame pairs of the sequence; the sequence is played forward and then
+backward (a camera walking back the same path), so K = 20 steps cover the 300-frame sequence once and no artificial
+frame jump is introduced.  value = pairs/s = frames / time.
+
+value    : frames resident in HBM (device slots, 300 x 1.5 MB = 460 MB per sequence, larger than the 126 MB L2 and each
+           read once per pass; a 256 MiB flush is written between steps as well), one call sindyn_track_frame_resident per
+           frame, CUDA events on the handle's stream around every step, summed; max over ranks.
+e2e      : the same frames through the host C-ABI call sindyn_track_frame (what the C++ classes of
+           include/sindyn_classes.hpp call) with pinned HOST buffers: H2D of the BGR + depth frame and D2H of the dilated
+           mask, the label image, the key points and the descriptors inside the timed region.
+roofline : the dominant kernel, k_brox_sor (temporally blocked red-black SOR), timed per launch with CUDA events on the
+           handle's stream (sindyn_brox_profile); algorithmic bytes = 52 B per pixel and sweep.
+roofline_per_stage: SURVEY.md 8(d) algorithmic bytes of every stage / its device ms / the measured HBM peak.
+cpu_baseline / --impl reference: the reference's CPU path restated in oracle/ (checker code): the full oracle pipeline
+           (flow + k-means + edges + PEAC + merge + decision + dilation + masked ORB) on the host cores of this box, on a
+           bounded sample of the same sequence.
+--sequences S: BASELINE configs[4] as written -- S independent sequences spread over the N GPUs (S/N per GPU, strong
+           scaling of a fixed job); default S = N (one sequence per GPU, weak scaling).
 """
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -40,8 +50,26 @@ import numpy as np
 
 METRIC = "dyn-detect frame pairs/sec @640x480"
 UNIT = "pairs/s"
-N_FRAMES = 16
-ALGO_BYTES_PER_PX_SWEEP = 52.0   # 52 B per pixel and red-black sweep (the 100 B coefficient preparation is k_brox_system's)
+N_FRAMES = 300               # BASELINE.json configs[2]
+FRAMES_PER_STEP = 15
+HOLE_RATE = 0.0005
+SEQ_BASE = 3                 # sequence s of rank r uses seed BASE_SEED + SEQ_BASE + ...
+ORB_CFG = (1500, 1.2, 8, 15, 5)   # TUM3.yaml ORBextractor.*
+ALGO_BYTES_PER_PX_SWEEP = 52.0    # 52 B per pixel and red-black sweep
+
+# SURVEY.md 8(d) algorithmic bytes per frame pair at 640x480 (C1), per stage
+STAGE_BYTES_C1 = {
+    "gray_resize_upsample": 4.0e6,
+    "brox": 1.925e9,
+    "refine_largemotion": 0.197e9,
+    "homography": 2961 * 2 * 2 * 4.0,
+    "residual_masks": 7.7e6,
+    "kmeans": 45.7e6,
+    "depth_edges": 3.7e6,
+    "plane_edges_peac": 0.9e6,
+    "filter_recluster_decide": 24.6e6,
+    "orb": 5.7e6 + 0.8e6,
+}
 
 
 def peaks():
@@ -114,25 +142,57 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_frames(rank):
+def make_frames(seq_index, n=N_FRAMES, workers=None):
     from sindslam_b200 import synth
     cam = synth.TUM3
-    scene, frames = synth.make_sequence(N_FRAMES, cam, seq=rank, kind="box", start=8)
+    _, frames = synth.make_sequence_parallel(n, cam, seq=SEQ_BASE + seq_index, kind="box", start=0, hole_rate=HOLE_RATE, workers=workers)
     return cam, frames
 
 
-def cpu_pairs_per_s(frames, engine, budget_s, max_pairs):
-    """The reference's CPU flow+residual path (oracle restatement) on a bounded sample: frames 2.. of the sequence."""
+def frame_order(n_frames, count):
+    """Indices of `count` consecutive frames: 1, 2, ..., n-1, n-2, ..., 0, 1, ... (forward, then backward: no jumps)."""
+    period = list(range(1, n_frames)) + list(range(n_frames - 2, -1, -1))
+    return [period[i % len(period)] for i in range(count)]
+
+
+def workload_config(cam, extra=None):
+    c = {"workload": "configs[2]: full dynamic-region pipeline (DetectDynaArea: Brox flow alpha 0.197 gamma 50 scale 0.8 10 inner 77 outer 10 SOR "
+                     "+ refinement + RHO homography ego-motion residual + Otsu/Triangle masks, 4-level k-means re-clustering, depth edges, "
+                     "PEAC plane edges, split/RAG/merge, per-cluster decision, mask morphology; 15x15 dilation; masked ORB 1500 features "
+                     f"x 8 levels with key-point erasure) over a {N_FRAMES}-frame synthetic walking_xyz-shaped 640x480 sequence per GPU; "
+                     f"one step = {FRAMES_PER_STEP} consecutive frame pairs",
+         "width": cam.width, "height": cam.height, "flow_grid": "384x288", "frames": N_FRAMES, "frames_per_step": FRAMES_PER_STEP,
+         "depth_hole_rate": HOLE_RATE, "plane_edges": True,
+         "l2": "inputs (460 MB of resident frames per sequence, each read once per pass) exceed the 126 MB L2; a 256 MiB device write "
+               "also flushes it between timed steps",
+         "parallelism": "replicas (independent sequences per GPU, no collectives)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ----------------------------------------------------------------------------- CPU arms (oracle = checker code)
+def cpu_full_pipeline(frames, cam, engine, kmeans_impl, budget_s, max_pairs, start=1):
+    """The reference's whole per-frame path restated in oracle/ on a bounded sample: DetectDynaArea (oracle flow engine,
+    k-means, edges, PEAC, merge, decision) + 15x15 dilation + masked ORB (oracle extractor).  Returns (pairs/s, n, seconds)."""
     import cv2
     from oracle import dynadetect_oracle as orc
-    cv2.setNumThreads(os.cpu_count() or 1)
-    z = np.zeros(frames[0].bgr.shape[:2], np.uint8)
-    orc.flow_residual_cpu(frames[2].bgr, frames[1].bgr, frames[0].bgr, z, z, engine)  # warm-up (thread pools, lib load)
+    from oracle import orb_oracle as oo
+    o = orc.DynaDetectOracle(frames[start - 1].bgr, frames[start - 1].bgr, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor,
+                             plane_edges=True, engine=engine, refine=True, kmeans_impl=kmeans_impl)
+    orb = oo.OrbOracle(*ORB_CFG)
+    el = orc.ellipse(15)
+
+    def one(f):
+        r = o.detect(f.bgr, f.depth)
+        dil = cv2.dilate(r["mask"], el)
+        orb.extract(cv2.cvtColor(f.bgr, cv2.COLOR_RGB2GRAY), dil)
+
+    one(frames[start])      # warm-up (thread pools, library loads); also moves the state off the all-zero first frame
     t0 = time.perf_counter()
     n = 0
-    for i in range(2, 2 + max_pairs):
-        k = 2 + (i - 2) % (len(frames) - 2)
-        orc.flow_residual_cpu(frames[k].bgr, frames[k - 1].bgr, frames[k - 2].bgr, z, z, engine)
+    for k in range(start + 1, min(start + 1 + max_pairs, len(frames))):
+        one(frames[k])
         n += 1
         if time.perf_counter() - t0 > budget_s:
             break
@@ -144,145 +204,97 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cam, frames = make_frames(0)
-    per_step = []
-    n_pairs = 0
-    for s in range(args.warmup + args.steps):
-        v, n, dt = cpu_pairs_per_s(frames, "deepflow", budget_s=min(3.0, 150.0 / (args.warmup + args.steps)), max_pairs=12)
+    import cv2
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)     # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses all host threads at every N
+    cv2.setNumThreads(cores)
+    total = args.warmup + args.steps
+    per = 2                                         # bounded sample: 2 frame pairs of the step's 15 (+1 warm-up pair per step)
+    need = min(N_FRAMES, 2 + total * per + 2)
+    cam, frames = make_frames(0, n=need)
+    per_step, n_pairs = [], 0
+    for s in range(total):
+        a = 1 + (s * per) % max(1, need - per - 2)
+        v, n, dt = cpu_full_pipeline(frames, cam, "deepflow", "cv2", budget_s=20.0, max_pairs=per, start=a)
         if s >= args.warmup:
             per_step.append(dt / n)
             n_pairs += n
     sec_per_pair = float(np.mean(per_step))
     value = 1.0 / sec_per_pair
-    cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec_per_pair * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": sec_per_pair * 1e3 * FRAMES_PER_STEP, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(cam, extra={"engine": "DeepFlow-restated (cv2.VariationalRefinement pyramid; optflow not in cv2-headless) "
-                                               "+ cv2 refinement/RHO homography/Otsu/Triangle, all host threads"}),
+        "config": workload_config(cam),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_pairs} frame pairs of the synthetic 640x480 sequence (each step = up to 12 pairs / 3 s)"},
+                         "sample": f"{n_pairs} frame pairs ({per} of every step's {FRAMES_PER_STEP}) of the same synthetic sequence through the full oracle "
+                                   "pipeline: DeepFlow-restated flow (the reference's default CPU engine; cv2.VariationalRefinement pyramid, optflow is "
+                                   "not in cv2-headless) + cv2 refinement / RHO / Otsu / Triangle + cv2.kmeans + depth edges + oracle/peac_cpu.c + "
+                                   "split/RAG/merge + decision + 15x15 dilation + oracle ORB extractor; ms_per_step is scaled to the step's 15 pairs"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(cam, extra=None):
-    c = {"workload": "configs[1]: single 640x480 frame pair, Brox dense flow (alpha 0.197, gamma 50, scale 0.8, 10 inner, 77 outer, "
-                     "10 SOR) + refinement + homography ego-motion residual + thresholds -> two masks, streamed over a "
-                     f"{N_FRAMES}-frame synthetic TUM-format sequence per GPU",
-         "width": cam.width, "height": cam.height, "flow_grid": "384x288", "frames": N_FRAMES,
-         "l2": "flushed between timed steps (256 MiB device write)", "parallelism": "replicas (one sequence per GPU, no collectives)"}
-    if extra:
-        c.update(extra)
-    return c
+# ----------------------------------------------------------------------------- GPU arm
+STAGE_NAMES = ["upload_gray_resize", "brox", "largemotion_refine_upsample", "homography", "residual_masks", "kmeans", "depth_edges",
+               "plane_edge_filter", "recluster", "decide", "total_device", "plane_edges_peac"]
 
 
-def full_pipeline_stats(cam, frames, device, refine):
-    """BASELINE configs[2] in miniature (reported next to the headline, not the headline): the whole per-frame path --
-    sindyn_detect (flow + residual + k-means + depth edges + re-clustering + decision), 15x15 dilation and the masked ORB
-    extraction -- through the host C ABI, with per-stage device milliseconds."""
-    import cv2
+def stage_profile(cam, frames, device, n=24):
+    """Per-stage device ms (CUDA events inside the library, stage_timing=1: classic launch path, no graphs) and the ORB time,
+    averaged over n frames of the sequence."""
+    import torch
     from sindslam_b200.capi import Orb, SinDyn
-    sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=device, refine=refine, stage_timing=1)
-    orb = Orb(1500, 1.2, 8, 15, 5, cam.width, cam.height, device=device)
-    sd.set_prev_frames(frames[1].bgr, frames[0].bgr)
-    grays = [cv2.cvtColor(f.bgr, cv2.COLOR_RGB2GRAY) for f in frames]
+    sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=device, refine=1, plane_edges=1, stage_timing=1)
+    orb = Orb(*ORB_CFG, cam.width, cam.height, device=device)
+    st = torch.cuda.Stream(device=device)
+    orb.set_stream(st.cuda_stream)
+    sd.set_prev_frames(frames[0].bgr, frames[0].bgr)
+    import cv2
     acc = np.zeros(16)
-    n = 0
-    t_det = t_orb = t_ff = t_cloud = 0.0
-    nkp = 0
-    prev = last_pts = None
-    t_match = 0.0
-    for k in range(2, len(frames)):
-        t0 = time.perf_counter()
+    orb_ms, cnt = 0.0, 0
+    for k in range(1, n + 4):
         mask, label = sd.detect(frames[k].bgr, frames[k].depth, k)
-        mask = sd.morph_ellipse(mask, 15, 0)
-        t1 = time.perf_counter()
-        kps, kdesc = orb.extract(grays[k], mask)
-        t2 = time.perf_counter()
-        # the "next" rows downstream of the path (not part of pairs_per_s): Frame construction (f2), dense-map cloud (f3)
-        un, dep, _, _, _, _ = orb.frame_features(frames[k].depth, cam.fx, cam.fy, cam.cx, cam.cy, (0.0, 0.0, 0.0, 0.0, 0.0), 40.0, 1.0 / cam.depth_factor)
-        t3 = time.perf_counter()
-        # frame-to-frame descriptor matching (f4) against the previous frame's key points as map points
-        t_m0 = time.perf_counter()
-        if last_pts is not None:
-            orb.search_by_projection(last_pts, np.linalg.inv(frames[k].T_wc), np.linalg.inv(frames[k - 1].T_wc), cam.fx, cam.fy, cam.cx, cam.cy,
-                                     40.0, 40.0 / cam.fx, 15.0)
-        t_m1 = time.perf_counter()
-        nk = len(kps)
-        z = dep[:nk]
-        pc = np.stack([(un[:nk, 0] - cam.cx) * z / cam.fx, (un[:nk, 1] - cam.cy) * z / cam.fy, z, np.ones(nk)], 1)
-        last_pts = dict(xyz_w=(frames[k].T_wc @ pc.T).T[:, :3].astype(np.float32), valid=z > 0, desc=kdesc, octave=kps["octave"], angle=kps["angle"],
-                        observed=np.zeros(nk, bool))
-        t3b = time.perf_counter()
-        if prev is not None:
-            T_rel = np.linalg.inv(frames[prev[0]].T_wc) @ frames[k].T_wc
-            sd.cloud_consistent(frames[k].bgr, frames[k].depth, frames[prev[0]].depth, mask, prev[1], label, T_rel, frames[k].T_wc)
-        t4 = time.perf_counter()
-        prev = (k, mask)
+        dil = sd.morph_ellipse(mask, 15, 0)
+        gray = cv2.cvtColor(frames[k].bgr, cv2.COLOR_RGB2GRAY)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        orb.extract(gray, dil)
+        e1.record(st)
+        e1.synchronize()
         if k >= 4:
             acc += sd.stage_ms()
-            t_det += t1 - t0
-            t_orb += t2 - t1
-            t_ff += t3 - t2
-            t_cloud += t4 - t3b
-            t_match += t_m1 - t_m0
-            nkp += len(kps)
-            n += 1
+            orb_ms += e0.elapsed_time(e1)
+            cnt += 1
     sd.close()
     orb.close()
-    acc /= max(n, 1)
-    names = ["upload_gray_resize", "brox", "largemotion_refine_upsample", "homography", "residual_masks", "kmeans", "depth_edges",
-             "plane_edge_filter", "recluster", "decide", "total_device"]
-    return {"workload": "sindyn_detect + 15x15 dilation + masked ORB (1500 features, 8 levels) per frame, host buffers",
-            "pairs_per_s": n / (t_det + t_orb), "detect_ms_wall": 1e3 * t_det / n, "orb_ms_wall": 1e3 * t_orb / n,
-            "keypoints_per_frame": nkp / n, "stage_ms_device": {nm: float(acc[i]) for i, nm in enumerate(names)},
-            "plane_edges": True,
-            "next_rows_ms_wall": {"f2_frame_features": 1e3 * t_ff / n, "f3_cloud_consistent": 1e3 * t_cloud / n,
-                                  "f4_search_by_projection": 1e3 * t_match / n,
-                                  "note": "host C-ABI calls with pageable numpy buffers (H2D + D2H inside), not counted in pairs_per_s"}}
+    acc /= cnt
+    ms = {nm: float(acc[i]) for i, nm in enumerate(STAGE_NAMES)}
+    ms["orb_extract_incl_copies"] = orb_ms / cnt
+    return ms
 
 
-def multi_sequence_stats(cam, device, refine, n_seq=8, steps=24):
-    """Batched throughput ('report both single-frame latency and batched throughput'): n_seq independent
-    sequences on ONE GPU, one handle + stream + host thread each, device-resident frames.  A single sequence leaves most
-    of the chip idle (the coarse pyramid levels run on a handful of SMs), so concurrent sequences overlap."""
-    import torch
-    from sindslam_b200 import synth
-    from sindslam_b200.capi import SinDyn
-    handles = []
-    for s in range(n_seq):
-        _, fr = synth.make_sequence(N_FRAMES, cam, seq=100 + s, kind="box", start=8)
-        sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=device, refine=refine)
-        for i, f in enumerate(fr):
-            sd.upload_frame(i, f.bgr, f.depth)
-        sd.set_prev_frames(fr[1].bgr, fr[0].bgr)
-        for i in range(3):
-            sd.flow_residual_resident(2 + i, roll=True)
-        sd.synchronize()
-        handles.append(sd)
-
-    def work(sd):
-        for i in range(steps):
-            sd.flow_residual_resident(5 + i % (N_FRAMES - 5), roll=True)
-        sd.synchronize()
-
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    th = [threading.Thread(target=work, args=(sd,)) for sd in handles]
-    for t in th:
-        t.start()
-    for t in th:
-        t.join()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    for sd in handles:
-        sd.close()
-    return {"sequences_per_gpu": n_seq, "pairs_per_s": n_seq * steps / dt, "steps_per_sequence": steps,
-            "note": "same flow + residual workload as the headline, host wall clock, n_seq concurrent handles on one GPU"}
+def roofline_per_stage(ms, peak):
+    t = {
+        "gray_resize_upsample": ms["upload_gray_resize"],
+        "brox": ms["brox"],
+        "refine_largemotion": ms["largemotion_refine_upsample"],
+        "homography": ms["homography"],
+        "residual_masks": ms["residual_masks"],
+        "kmeans": ms["kmeans"],
+        "depth_edges": ms["depth_edges"],
+        "plane_edges_peac": ms["plane_edges_peac"],
+        "filter_recluster_decide": ms["plane_edge_filter"] + ms["recluster"] + ms["decide"],
+        "orb": ms["orb_extract_incl_copies"],
+    }
+    out = {}
+    for k, b in STAGE_BYTES_C1.items():
+        if t[k] > 0:
+            gbs = b / (t[k] * 1e-3) / 1e9
+            out[k] = {"ms": round(t[k], 4), "algorithmic_bytes": b, "achieved_gbs": round(gbs, 2), "frac": round(gbs / peak, 5)}
+    return out
 
 
 def run_ours(args):
@@ -294,20 +306,31 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from sindslam_b200.capi import SinDyn
+        # replicas only: the process group carries the barrier and the max-over-ranks of the timings, nothing on the data path
+        dist.init_process_group("gloo")
+    from sindslam_b200.capi import Orb, SinDyn
 
-    cam, frames = make_frames(replicas.sequence_seed_index(rank))
-    refine = 0 if args.no_refine else 1
-    sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=local, refine=refine)
-    # one explicit (non-default) stream for the handle, the L2 flush and the timing events: torch's default stream has handle
-    # 0, which sindyn_set_stream reads as "use the handle's own stream" -- events recorded there would not bracket the work
-    stream = torch.cuda.Stream(device=local)
-    torch.cuda.set_stream(stream)
-    sd.set_stream(stream.cuda_stream)
-    for i, f in enumerate(frames):
-        sd.upload_frame(i, f.bgr, f.depth)
-    sd.set_prev_frames(frames[1].bgr, frames[0].bgr)
+    n_seq_total = args.sequences if args.sequences else world
+    my_seqs = [s for s in range(n_seq_total) if s % world == rank]
+    cam = None
+    seqs = []
+    workers = max(1, (os.cpu_count() or 1) // world)
+    for s in my_seqs:
+        cam, frames = make_frames(s, workers=workers)
+        seqs.append(frames)
+    assert seqs, "more ranks than sequences"
+
+    # one explicit (non-default) stream per sequence for the handle, the L2 flush and the timing events
+    handles = []
+    for frames in seqs:
+        sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=local, refine=1, plane_edges=1)
+        orb = Orb(*ORB_CFG, cam.width, cam.height, device=local)
+        stream = torch.cuda.Stream(device=local)
+        sd.set_stream(stream.cuda_stream)
+        for i, f in enumerate(frames):
+            sd.upload_frame(i, f.bgr, f.depth)
+        sd.set_prev_frames(frames[0].bgr, frames[0].bgr)          # rgbd_tum_noros.cc:103-107
+        handles.append((sd, orb, stream, frames))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -316,96 +339,136 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    order = [(2 + i) % N_FRAMES for i in range(args.warmup + args.steps)]
+    total_steps = args.warmup + args.steps
+    order = frame_order(N_FRAMES, total_steps * FRAMES_PER_STEP)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-        time.sleep(0.6)          # let nvidia-smi come up so that short runs still get samples under load
-        clocks.begin_window()    # window = warm-up steps + both timed regions: one stretch of continuous load
-    # ---------------- device-resident throughput
-    for i in range(args.warmup):
-        flush.fill_(i & 255)
-        sd.flow_residual_resident(order[i], roll=True)
+        time.sleep(0.6)
+        clocks.begin_window()
+
+    # ---------------- device-resident throughput (value)
+    def run_steps_resident(sd, orb, stream, s0, s1, ev):
+        for s in range(s0, s1):
+            with torch.cuda.stream(stream):
+                flush.fill_(s & 255)
+            if ev is not None:
+                ev[s - s0][0].record(stream)
+            for j in range(FRAMES_PER_STEP):
+                orb.track_frame_resident(sd, order[s * FRAMES_PER_STEP + j], s * FRAMES_PER_STEP + j)
+            if ev is not None:
+                ev[s - s0][1].record(stream)
+
+    def over_handles(fn):
+        if len(handles) == 1:
+            fn(handles[0])
+            return
+        th = [threading.Thread(target=fn, args=(h,)) for h in handles]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    over_handles(lambda h: run_steps_resident(h[0], h[1], h[2], 0, args.warmup, None))
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    l0 = sd.launches
-    n_large = 0
-    for i in range(args.steps):
-        flush.fill_(i & 255)
-        ev[i][0].record(stream)
-        sd.flow_residual_resident(order[args.warmup + i], roll=True)
-        ev[i][1].record(stream)
+    l0 = sum(h[0].launches + h[1].launches for h in handles)
+    evs = {id(h[0]): [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)] for h in handles}
+    t_host0 = time.perf_counter()
+    over_handles(lambda h: run_steps_resident(h[0], h[1], h[2], args.warmup, total_steps, evs[id(h[0])]))
     barrier()
-    gpu_launches = sd.launches - l0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t_host1 = time.perf_counter()
+    gpu_launches = sum(h[0].launches + h[1].launches for h in handles) - l0
+    # one sequence: summed per-step event times (flush excluded); several concurrent sequences on one GPU: the wall time of
+    # the region (events of different streams overlap)
+    if len(handles) == 1:
+        dev_ms = sum(a.elapsed_time(b) for a, b in evs[id(handles[0][0])])
+    else:
+        dev_ms = (t_host1 - t_host0) * 1e3
+    for h in handles:   # surface capacity errors of the resident path
+        h[1].track_results(h[0])
+
     # ---------------- end to end through the host C-ABI (pinned host buffers)
-    pin_in = [torch.from_numpy(np.ascontiguousarray(f.bgr)).pin_memory() for f in frames]
-    pin_lo = torch.empty((cam.height, cam.width), dtype=torch.uint8).pin_memory()
-    pin_hi = torch.empty((cam.height, cam.width), dtype=torch.uint8).pin_memory()
-    lo_np, hi_np = pin_lo.numpy(), pin_hi.numpy()
-    in_np = [t.numpy() for t in pin_in]
-    for i in range(args.warmup):
-        sd.flow_residual(in_np[order[i]], True, lo_np, hi_np)
+    sd, orb, stream, frames = handles[0]
+    pin_bgr = [torch.from_numpy(np.ascontiguousarray(f.bgr)).pin_memory() for f in frames]
+    pin_dep = [torch.from_numpy(np.ascontiguousarray(f.depth).view(np.int16)).pin_memory() for f in frames]
+    bgr_np = [t.numpy() for t in pin_bgr]
+    dep_np = [t.numpy().view(np.uint16) for t in pin_dep]
+    cap = ORB_CFG[0] * 2 + 64
+    pin_mask = torch.empty((cam.height, cam.width), dtype=torch.uint8).pin_memory().numpy()
+    pin_label = torch.empty((cam.height, cam.width), dtype=torch.uint8).pin_memory().numpy()
+    pin_kps = torch.empty(cap * 24, dtype=torch.uint8).pin_memory().numpy().view(Orb.KP_DTYPE)
+    pin_desc = torch.empty((cap, 32), dtype=torch.uint8).pin_memory().numpy()
+    # the e2e stream continues the sequence where the resident run stopped (same state recurrence)
+    order2 = frame_order(N_FRAMES, 2 * total_steps * FRAMES_PER_STEP)[total_steps * FRAMES_PER_STEP:]
+    n_kp = 0
+
+    def e2e_steps(s0, s1):
+        nonlocal n_kp
+        for s in range(s0, s1):
+            for j in range(FRAMES_PER_STEP):
+                k = order2[s * FRAMES_PER_STEP + j]
+                _, _, kps, _ = orb.track_frame(sd, bgr_np[k], dep_np[k], k, mask_out=pin_mask, label_out=pin_label, kps_out=pin_kps, desc_out=pin_desc)
+                n_kp += len(kps)
+
+    e2e_steps(0, args.warmup)
     barrier()
+    n_kp = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lm_flag = ctypes.c_int(0)
     e0.record(stream)
-    for i in range(args.steps):
-        sd.flow_residual(in_np[order[args.warmup + i]], True, lo_np, hi_np)
-        sd.lib.sindyn_get_flow_results(sd.h, None, None, None, None, None, ctypes.byref(lm_flag))
-        n_large += lm_flag.value
+    e2e_steps(args.warmup, total_steps)
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
+    kp_per_frame = n_kp / max(1, args.steps * FRAMES_PER_STEP)
 
-    dev_ms, e2e_ms = replicas.max_over_ranks([dev_ms, e2e_ms], dist, "cuda")
+    dev_ms, e2e_ms = replicas.max_over_ranks([dev_ms, e2e_ms], dist, "cpu" if dist is not None else "cuda")
     if rank == 0:
-        value = replicas.aggregate_throughput(world, args.steps, dev_ms)
-        e2e = replicas.aggregate_throughput(world, args.steps, e2e_ms)
+        frames_per_rank_value = args.steps * FRAMES_PER_STEP * len(handles)
+        value = world * frames_per_rank_value / (dev_ms * 1e-3)
+        e2e = world * args.steps * FRAMES_PER_STEP / (e2e_ms * 1e-3)
         prof = sd.brox_profile()
         prof = sd.brox_profile()  # second call: warm
         peak, which = peaks()
         algo_bytes = ALGO_BYTES_PER_PX_SWEEP * prof["pixel_sweeps"]
         ach = algo_bytes / (prof["sor_ms"] * 1e-3) / 1e9
-        stage = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=local, refine=refine, stage_timing=1)
-        stage.set_prev_frames(frames[1].bgr, frames[0].bgr)
-        acc = np.zeros(16)
-        for k in range(2, 10):
-            stage.flow_residual(frames[k].bgr, True)
-            if k >= 4:
-                acc += stage.stage_ms()
-        acc /= 6
-        stage.close()
-        if args.headline_only:
-            full, multi, (cpu_v, cpu_n, cpu_dt) = None, None, (None, 0, 0.0)
+        extras = {}
+        if not args.headline_only:
+            ms = stage_profile(cam, frames, local)
+            extras["stage_ms_device"] = ms
+            extras["roofline_per_stage"] = roofline_per_stage(ms, peak)
+            cpu_v, cpu_n, cpu_dt = cpu_full_pipeline(frames, cam, "brox", "fx", budget_s=15.0, max_pairs=40)
+            extras["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                      "sample": f"{cpu_n} frame pairs in {cpu_dt:.1f} s through the full oracle pipeline (oracle/brox_cpu.c OpenMP Brox + cv2 "
+                                                "refinement/RHO/thresholds + fixed-point k-means + edges + oracle/peac_cpu.c + merge + decision + dilation + "
+                                                "oracle ORB); the reference's default CPU engine (DeepFlow) is timed by --impl reference"}
         else:
-            full = full_pipeline_stats(cam, frames, local, refine)
-            multi = multi_sequence_stats(cam, local, refine)
-            cpu_v, cpu_n, cpu_dt = cpu_pairs_per_s(frames, "brox", budget_s=12.0, max_pairs=200)
+            extras["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "skipped (--headline-only)"}
+        d2h = 2 * cam.width * cam.height + int(round(kp_per_frame * (24 + 32)))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak" if not args.sequences else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cam, extra={"refine": bool(refine), "large_motion_steps": n_large}),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cam.width * cam.height * 3,
-                    "d2h_bytes_per_step": 2 * cam.width * cam.height, "ms_per_step": e2e_ms / args.steps},
+            "config": workload_config(cam, extra={"refine": True, "sequences_total": n_seq_total, "sequences_per_gpu": len(handles),
+                                                  "keypoints_per_frame": round(kp_per_frame, 1)}),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * cam.width * cam.height * 5,
+                    "d2h_bytes_per_step": FRAMES_PER_STEP * d2h, "ms_per_step": e2e_ms / args.steps,
+                    "note": "one sequence per GPU through sindyn_track_frame (host buffers)"},
+            "ms_per_frame": dev_ms / (args.steps * FRAMES_PER_STEP),
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "kernel": "k_brox_sor (temporally blocked red-black SOR, 5 sweeps per launch; the 9 finest pyramid levels)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_from_profile(),
                          "peak_source": which, "algorithmic_bytes_per_launch": algo_bytes / max(prof["sor_launches"], 1),
                          "launches_per_solve": prof["sor_launches"], "avg_launch_us": 1e3 * prof["sor_ms"] / max(prof["sor_launches"], 1),
                          "sor_share_of_solve": prof["sor_ms"] / prof["solve_ms"]},
-            "stage_ms": {"prep": float(acc[0]), "brox": float(acc[1]), "largemotion_refine_upsample": float(acc[2]),
-                         "homography": float(acc[3]), "residual_masks": float(acc[4]), "total": float(acc[10])},
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{cpu_n} frame pairs in {cpu_dt:.1f} s: oracle/brox_cpu.c (OpenMP) + cv2 refinement/RHO/thresholds"},
-            "full_pipeline": full,
-            "multi_sequence": multi,
             "clocks": clk,
         }
+        line.update(extras)
         print(json.dumps(line))
-    sd.close()
+    for h in handles:
+        h[1].close()
+        h[0].close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -414,11 +477,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-refine", action="store_true", help="skip the VariationalRefinement-equivalent pass (diagnostics only)")
-    ap.add_argument("--headline-only", action="store_true", help="skip the full-pipeline / multi-sequence / CPU-baseline extras (ncu runs)")
+    ap.add_argument("--sequences", type=int, default=0, help="total number of independent sequences spread over the GPUs (default: one per GPU)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the per-stage profile and the CPU baseline (ncu runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

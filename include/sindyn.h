@@ -81,7 +81,7 @@ int sindyn_detect(sindyn_handle h, const uint8_t *bgr, size_t bgr_step, const ui
 /* Device-resident variant used for kernel-only timing: frames are staged once into `slot`
  * (0 <= slot < SINDYN_MAX_SLOTS) and detect runs without host traffic; results stay on the
  * device until sindyn_get_buffer. */
-#define SINDYN_MAX_SLOTS 32
+#define SINDYN_MAX_SLOTS 512
 int sindyn_upload_frame(sindyn_handle h, int slot, const uint8_t *bgr, size_t bgr_step,
                         const uint16_t *depth, size_t depth_step);
 int sindyn_detect_resident(sindyn_handle h, int slot, int frame_idx);
@@ -105,6 +105,12 @@ int sindyn_flow_residual_resident(sindyn_handle h, int slot, int roll);
  * flow W x H x 2 float, H 3x3 double, thresholds[4], masks. */
 int sindyn_get_flow_results(sindyn_handle h, float *flow, double *H_out, float *thresholds, uint8_t *mask_low, uint8_t *mask_high,
                             int *large_motion);
+/* Diagnostics (no reference equivalent): which launch path the LAST whole-frame call (sindyn_detect / sindyn_flow_residual*)
+ * took.  info[0] = 1 if the flow branch ran as the one captured CUDA graph whose large-motion decision
+ * (DynaDetect.cc:1097-1114) is a conditional node, 0 = classic path with the host decision; info[1] = 1 if the one-graph
+ * path has been disabled for this handle (capture failed); info[2] = 1 if the clustering branch was replayed as a graph;
+ * info[3] = reserved.  Used by the tests that compare the graph path with the classic path bit for bit. */
+int sindyn_get_path_info(sindyn_handle h, int info[4]);
 
 /* Measurement hook (no reference equivalent): runs one Brox solve on the handle's resident frames
  * WITHOUT the CUDA graph, bracketing every launch of the tiled SOR kernel (k_brox_sor) with CUDA events
@@ -234,6 +240,22 @@ int sindyn_orb_destroy(sindyn_orb_handle h);
  * kps: capacity entries; desc: capacity x 32 bytes. *n_out = number of keypoints written. */
 int sindyn_orb_extract(sindyn_orb_handle h, const uint8_t *gray, size_t gray_step, const uint8_t *mask, size_t mask_step,
                        sindyn_keypoint *kps, uint8_t *desc, int capacity, int *n_out);
+/* One iteration of the driver loop, fused: replaces rgbd_tum_noros.cc:132-139 (DynaDetect::DetectDynaArea followed by the
+ * dilate_k x dilate_k elliptic dilation of the mask, 15 in the reference) plus the part of System::TrackRGBD that produces the
+ * key points: Tracking::GrabImageRGBD's colour conversion (Tracking.cc:246-252; rgb_order != 0 = Camera.RGB: 1 = CV_RGB2GRAY,
+ * 0 = CV_BGR2GRAY) and Frame::ExtractORB2 -> ORBextractor::operator()(gray, dilated mask) (Frame.cc:300-317,
+ * ORBextractor.cc:1043-1164).  Same results as sindyn_detect + sindyn_morph_ellipse + sindyn_orb_extract called one after the
+ * other; the frame is uploaded once, the mask never leaves the device between the stages, and the mask-independent half of
+ * the extraction overlaps the detection.  mask_out receives the DILATED mask (what the driver hands to TrackRGBD). */
+int sindyn_track_frame(sindyn_handle h, sindyn_orb_handle o, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step,
+                       int rgb_order, int dilate_k, uint8_t *mask_out, size_t mask_step, uint8_t *label_out, size_t label_step,
+                       sindyn_keypoint *kps, uint8_t *desc, int capacity, int *n_out, int frame_idx);
+/* Same on a frame staged with sindyn_upload_frame: no host traffic, no synchronisation (kernel-only timing; the extractor's
+ * stream is joined into the detector handle's stream).  Results via sindyn_track_get_results. */
+int sindyn_track_frame_resident(sindyn_handle h, sindyn_orb_handle o, int slot, int rgb_order, int dilate_k, int frame_idx);
+int sindyn_track_get_results(sindyn_handle h, sindyn_orb_handle o, uint8_t *mask_dilated, uint8_t *labels, sindyn_keypoint *kps, uint8_t *desc,
+                             int capacity, int *n_out);
+
 /* mvImagePyramid[level] (include/ORBextractor.h:88): copies level image (without the 19-px pad). */
 int sindyn_orb_get_pyramid_level(sindyn_orb_handle h, int level, uint8_t *out, int *w_out, int *h_out);
 /* Test hook: FAST candidates of one level after the last extract, in distribution order (vToDistributeKeys,

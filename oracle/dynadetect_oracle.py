@@ -789,11 +789,11 @@ def flow_residual_cpu(bgr_cur, bgr_last, bgr_lastlast, dyna_last, label_last, en
 class DynaDetectOracle:
     """ORB_SLAM2::DynaDetect (DynaDetect.h:95-189): constructor state + DetectDynaArea (DynaDetect.cc:1377-1666)."""
 
-    def __init__(self, bgr_last, bgr_lastlast, fx, fy, cx, cy, depth_scale, plane_edges=False, engine="brox", refine=True):
+    def __init__(self, bgr_last, bgr_lastlast, fx, fy, cx, cy, depth_scale, plane_edges=False, engine="brox", refine=True, kmeans_impl="fx"):
         H, W = bgr_last.shape[:2]
         self.W, self.H = W, H
         self.fx, self.fy, self.cx, self.cy, self.depth_scale = fx, fy, cx, cy, depth_scale
-        self.plane_edges, self.engine, self.refine = plane_edges, engine, refine
+        self.plane_edges, self.engine, self.refine, self.kmeans_impl = plane_edges, engine, refine, kmeans_impl
         self.rgb_last, self.rgb_lastlast = bgr_last.copy(), bgr_lastlast.copy()
         z = np.zeros((H, W), np.uint8)
         self.dyna_last, self.high_last, self.label_last = z.copy(), z.copy(), z.copy()
@@ -808,7 +808,7 @@ class DynaDetectOracle:
             out["flow"] = fr
         else:
             low, high = inject_masks
-        labels_km, points, centers = seg_by_kmeans(depth, self.label_last, self.fx, self.fy, self.cx, self.cy, self.depth_scale, "fx")
+        labels_km, points, centers = seg_by_kmeans(depth, self.label_last, self.fx, self.fy, self.cx, self.cy, self.depth_scale, self.kmeans_impl)
         kept, seg, _ = cluster_order(labels_km, centers)
         total_area, grad, ep = depth_edges(depth, self.depth_scale)
         if self.plane_edges:

@@ -336,11 +336,54 @@ def plane_fit(pts):
     return out, n_final, dict(coarse=coarse, blk_map=np.array(blk_map, np.int32).reshape(Nh, Nw), grown=member.copy(), n_final_sorted=len(final))
 
 
-def plane_edges(depth, fx, fy, cx, cy, depth_scale, debug=None):
+_peac_c = None
+
+
+def _peac_lib():
+    global _peac_c
+    if _peac_c is None:
+        import ctypes
+        import os
+        here = os.path.dirname(os.path.abspath(__file__))
+        path = os.path.join(here, "_build", "libpeac_cpu.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-C", here])
+        lib = ctypes.CDLL(path)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        lib.peac_plane_fit.argtypes = [vp, ci, ci, vp, vp, vp, vp, ci, vp, vp]
+        lib.peac_plane_fit.restype = ci
+        _peac_c = lib
+    return _peac_c
+
+
+def plane_fit_c(pts):
+    """Same as plane_fit, executed by oracle/peac_cpu.c (the C restatement of the same reference code; ~1000x faster than the
+    Python loops above, which stay as the readable statement and are compared with it in tests/test_peac_cpu.py)."""
+    import ctypes
+    H, W = pts.shape[:2]
+    Nh, Nw = H // WIN, W // WIN
+    pts = np.ascontiguousarray(pts, np.float32)
+    member = np.empty((H, W), np.int32)
+    grown = np.empty((H, W), np.int32)
+    blk = np.empty((Nh, Nw), np.int32)
+    coarse = np.zeros((256, 2), np.int32)
+    nc = ctypes.c_int(0)
+    stats = np.zeros(8, np.int64)
+    n = _peac_lib().peac_plane_fit(pts.ctypes.data, W, H, member.ctypes.data, grown.ctypes.data, blk.ctypes.data, coarse.ctypes.data, 256,
+                                   ctypes.byref(nc), stats.ctypes.data)
+    if n < 0:
+        raise MemoryError("peac_plane_fit")
+    names = ("pops", "seeds", "queue_entries", "levels", "max_level", "valid_blocks", "coarse_planes", "final_planes")
+    return member, n, dict(coarse=[(int(r), int(c)) for r, c in coarse[:nc.value]], blk_map=blk, grown=grown,
+                           stats={k: int(v) for k, v in zip(names, stats)})
+
+
+def plane_edges(depth, fx, fy, cx, cy, depth_scale, debug=None, impl="c"):
     """imgEdgeByPlane of DynaDetect.cc:558-593: every final plane -> CLOSE 3x3 -> external contours, thickness 2
-    (AHCPlaneFitter.hpp:366-399)."""
+    (AHCPlaneFitter.hpp:366-399).  impl: 'c' (oracle/peac_cpu.c) or 'py' (the loops in this file) -- same restatement."""
     pts = organized_cloud(depth, fx, fy, cx, cy, depth_scale)
-    member, n, dbg = plane_fit(pts)
+    member, n, dbg = plane_fit_c(pts) if impl == "c" else plane_fit(pts)
     H, W = depth.shape
     out = np.zeros((H, W), np.uint8)
     se = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (3, 3))

@@ -70,6 +70,7 @@ SIGNATURES = {
     "sindyn_flow_residual": (_i, [_vp, _vp, _sz, _vp, _vp, _i]),
     "sindyn_flow_residual_resident": (_i, [_vp, _i, _i]),
     "sindyn_get_flow_results": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ip]),
+    "sindyn_get_path_info": (_i, [_vp, _vp]),
     "sindyn_brox_profile": (_i, [_vp, _vp]),
     "sindyn_morph_ellipse": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _i, _i]),
     "sindyn_flow_brox": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
@@ -94,6 +95,9 @@ SIGNATURES = {
     "sindyn_orb_create": (_i, [_i, _f, _i, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "sindyn_orb_destroy": (_i, [_vp]),
     "sindyn_orb_extract": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _i, _ip]),
+    "sindyn_track_frame": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _vp, _i, _ip, _i]),
+    "sindyn_track_frame_resident": (_i, [_vp, _vp, _i, _i, _i, _i]),
+    "sindyn_track_get_results": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
     "sindyn_orb_get_pyramid_level": (_i, [_vp, _i, _vp, _ip, _ip]),
     "sindyn_orb_get_candidates": (_i, [_vp, _i, _vp, _i, _ip]),
     "sindyn_orb_get_plane": (_i, [_vp, _i, _i, _vp, _ip, _ip]),
@@ -244,6 +248,11 @@ class SinDyn:
         lm = C.c_int(0)
         self._ck(self.lib.sindyn_get_flow_results(self.h, _p(flow), _p(Hm), _p(thr), _p(lo), _p(hi), C.byref(lm)), "get_flow_results")
         return dict(flow=flow, H=Hm, thr=thr, low=lo, high=hi, large_motion=bool(lm.value))
+
+    def path_info(self):
+        info = np.zeros(4, np.int32)
+        self._ck(self.lib.sindyn_get_path_info(self.h, _p(info)), "get_path_info")
+        return dict(flow_one_graph=bool(info[0]), flow_graph_broken=bool(info[1]), cluster_graph=bool(info[2]))
 
     def brox_profile(self):
         out = np.zeros(4, np.float64)
@@ -468,6 +477,42 @@ class Orb:
             raise SindynError(f"orb_extract: {STATUS.get(st, st)}: {self.lib.sindyn_orb_last_error(self.h).decode()}")
         arr = np.frombuffer(kps, dtype=np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")]))[:n.value].copy()
         return arr, desc[:n.value].copy()
+
+    KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")])
+
+    def track_frame(self, sd, bgr, depth, frame_idx, rgb_order=1, dilate_k=15, mask_out=None, label_out=None, kps_out=None, desc_out=None):
+        """rgbd_tum_noros.cc:132-139 + Tracking::GrabImageRGBD + ORBextractor::operator() in one call (sindyn_track_frame).
+        Returns (dilated mask, labels, key points, descriptors)."""
+        bgr = _u8(bgr)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        cap = self.nfeatures * 2 + 64
+        mask = np.empty((self.H, self.W), np.uint8) if mask_out is None else mask_out
+        label = np.empty((self.H, self.W), np.uint8) if label_out is None else label_out
+        kps = np.zeros(cap, self.KP_DTYPE) if kps_out is None else kps_out
+        desc = np.zeros((cap, 32), np.uint8) if desc_out is None else desc_out
+        n = C.c_int(0)
+        st = self.lib.sindyn_track_frame(sd.h, self.h, _p(bgr), bgr.strides[0], _p(depth), depth.strides[0], int(rgb_order), int(dilate_k),
+                                         _p(mask), mask.strides[0], _p(label), label.strides[0], _p(kps), _p(desc), cap, C.byref(n), frame_idx)
+        if st != 0:
+            raise SindynError(f"track_frame: {STATUS.get(st, st)}: {sd.lib.sindyn_last_error(sd.h).decode()}")
+        return mask, label, kps[: n.value], desc[: n.value]
+
+    def track_frame_resident(self, sd, slot, frame_idx, rgb_order=1, dilate_k=15):
+        st = self.lib.sindyn_track_frame_resident(sd.h, self.h, slot, int(rgb_order), int(dilate_k), frame_idx)
+        if st != 0:
+            raise SindynError(f"track_frame_resident: {STATUS.get(st, st)}: {sd.lib.sindyn_last_error(sd.h).decode()}")
+
+    def track_results(self, sd):
+        cap = self.nfeatures * 2 + 64
+        mask = np.empty((self.H, self.W), np.uint8)
+        label = np.empty((self.H, self.W), np.uint8)
+        kps = np.zeros(cap, self.KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        st = self.lib.sindyn_track_get_results(sd.h, self.h, _p(mask), _p(label), _p(kps), _p(desc), cap, C.byref(n))
+        if st != 0:
+            raise SindynError(f"track_get_results: {STATUS.get(st, st)}: {sd.lib.sindyn_last_error(sd.h).decode()}")
+        return mask, label, kps[: n.value].copy(), desc[: n.value].copy()
 
     def search_by_projection(self, last, Tcw_cur, Tcw_last, fx, fy, cx, cy, bf, b, th, mono=False, check_orientation=True, blocked=None):
         """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) against the frame resident in this handle.

@@ -29,7 +29,9 @@ static int cluster_branch(sindyn_ctx *c)
         CU_CHECK(c, cudaEventRecord(c->ev_peac_fork, s2));
         CU_CHECK(c, cudaStreamWaitEvent(c->stream3, c->ev_peac_fork, 0));
         c->stream = c->stream3;
+        if (c->cfg.stage_timing) cudaEventRecord(c->ev[15], c->stream3);
         int st = peac_run(c, &c->peac, &c->rc, c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges);
+        if (c->cfg.stage_timing) cudaEventRecord(c->ev[16], c->stream3);
         cudaEventRecord(c->ev_peac_join, c->stream3);
         c->stream = s2;
         SD_CHECK(st);
@@ -131,6 +133,9 @@ static int detect_run(sindyn_ctx *c)
     return SINDYN_OK;
 }
 
+int detect_run_public(sindyn_ctx *c) { return detect_run(c); }
+int detect_check_capacity(sindyn_ctx *c) { return check_capacity(c); }
+
 static int collect_detect_ms(sindyn_ctx *c)
 {
     if (!c->cfg.stage_timing) return SINDYN_OK;
@@ -139,6 +144,7 @@ static int collect_detect_ms(sindyn_ctx *c)
     c->stage_ms[0] = el(0, 1); c->stage_ms[1] = el(1, 2); c->stage_ms[2] = el(2, 3); c->stage_ms[3] = el(3, 4); c->stage_ms[4] = el(4, 5);
     c->stage_ms[5] = el(10, 11); c->stage_ms[6] = el(11, 12); c->stage_ms[7] = el(12, 13); c->stage_ms[8] = el(13, 14);
     c->stage_ms[9] = el(6, 7); c->stage_ms[10] = el(0, 7);
+    c->stage_ms[11] = c->cfg.plane_edges ? el(15, 16) : 0.f;   // PEAC plane edges (own stream, concurrent with k-means / gradient edges)
     return SINDYN_OK;
 }
 

@@ -7,8 +7,7 @@
 //   dynamic-mask erasure with the < 250 fallback                                    :1058-1116
 //   7x7 sigma-2 Gaussian blur (fixed point, exact) + 256-bit steered BRIEF          :108-147,1135-1151
 // All control (counts, offsets, list surgery) stays on the device; the host reads back one counter.
-#include "common.cuh"
-#include "preproc.cuh"
+#include "ctx.cuh"
 
 #include <math.h>
 
@@ -67,6 +66,7 @@ struct sindyn_orb : sindyn_base {
     float *fr_un = nullptr, *fr_depth = nullptr, *fr_uright = nullptr, *fr_bounds = nullptr;
     int *fr_offsets = nullptr, *fr_indices = nullptr;
     struct MatchStage *match = nullptr;   // descriptor matching (row f4), allocated on first use
+    void *track = nullptr;                // events of the fused per-frame entry (sindyn_track_frame)
     size_t pad_total = 0, img_total = 0;
 };
 
@@ -711,12 +711,14 @@ extern "C" int sindyn_orb_create(int nfeatures, float scale_factor, int nlevels,
 
 static void match_stage_free(sindyn_orb *o);
 
+static void track_free(sindyn_orb *o);
 extern "C" int sindyn_orb_destroy(sindyn_orb_handle h)
 {
     if (!h) return SINDYN_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     match_stage_free(h);
+    track_free(h);
     h->free_all();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -735,8 +737,8 @@ extern "C" int sindyn_orb_set_stream(sindyn_orb_handle h, void *s)
 extern "C" unsigned long long sindyn_orb_launch_count(sindyn_orb_handle h) { return h ? h->launches : 0ull; }
 extern "C" const char *sindyn_orb_last_error(sindyn_orb_handle h) { return h ? h->err.c_str() : "null handle"; }
 
-// all kernels of one extraction; gray / mask already on the device (level-0 interior of pyr, o->mask)
-static int orb_enqueue(sindyn_orb *o, bool have_mask)
+// first half of one extraction (pyramid, FAST, cells, quadtree): needs the gray image only (level-0 interior of pyr)
+static int orb_enqueue_unmasked(sindyn_orb *o)
 {
     const dim3 blk(32, 8);
     const size_t qsmem = sizeof(QNode) * ORB_NODES + 2 * ORB_KMAX + 4 * ORB_KMAX + 4 * ORB_NODES + 2 * 2 * ORB_NODES;
@@ -762,6 +764,13 @@ static int orb_enqueue(sindyn_orb *o, bool have_mask)
                o->cell_offs, o->cand, o->ctl);
     }
     LAUNCH(o, k_orb_quadtree, o->nlevels, 512, qsmem, o->lv_dev, o->cand, o->ctl, o->kps);
+    LAUNCH_CHECK(o);
+    return SINDYN_OK;
+}
+
+// second half: everything that needs the dynamic mask (erasure inside k_orb_orient) and follows it
+static int orb_enqueue_masked(sindyn_orb *o, bool have_mask)
+{
     LAUNCH(o, k_orb_orient, dim3(cdiv(ORB_NODES * 32, 256), o->nlevels), 256, 0, o->pyr, o->lv_dev, o->ctl, o->kps,
            have_mask ? o->mask : (const uint8_t *)nullptr, o->W);
     LAUNCH(o, k_orb_select, 1, 1024, 0, o->lv_dev, o->nlevels, o->ctl, o->kps, o->out);
@@ -788,7 +797,8 @@ extern "C" int sindyn_orb_extract(sindyn_orb_handle h, const uint8_t *gray, size
         CU_CHECK(h, cudaMemcpy2DAsync(h->pyr + (size_t)ORB_EDGE * L0.pitch + ORB_EDGE, L0.pitch, src, step, h->W, h->H, cudaMemcpyHostToDevice, h->stream));
     }
     if (mask) CU_CHECK(h, stage_in_2d(h->mask, mask, mask_step, h->W, h->H, h->pin_mask, h->stream));
-    SD_CHECK(orb_enqueue(h, mask != nullptr));
+    SD_CHECK(orb_enqueue_unmasked(h));
+    SD_CHECK(orb_enqueue_masked(h, mask != nullptr));
     CU_CHECK(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(OrbControl), cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     if (h->ctl_host->overflow) { h->err = "orb: a fixed-capacity list overflowed (candidates / nodes / output)"; return SINDYN_ERR_CAPACITY; }
@@ -800,6 +810,145 @@ extern "C" int sindyn_orb_extract(sindyn_orb_handle h, const uint8_t *gray, size
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     if (n && kps) memcpy(kps, h->pin_kp, sizeof(sindyn_keypoint) * n);
     if (n && desc) memcpy(desc, h->pin_desc, (size_t)32 * n);
+    return SINDYN_OK;
+}
+
+// ------------------------------------------------------------------ one driver iteration: DetectDynaArea + dilation + masked ORB
+// rgbd_tum_noros.cc:132-139 (DetectDynaArea, 15x15 dilation of the mask) followed by what System::TrackRGBD does with the frame
+// up to the key points: Tracking::GrabImageRGBD's colour conversion (Tracking.cc:246-252: RGB2GRAY when Camera.RGB is set,
+// else BGR2GRAY) and Frame::ExtractORB2 -> ORBextractor::operator() on the dilated mask (Frame.cc:300-317).
+// The ORB pyramid / FAST / quadtree half needs the frame only, so it runs on the extractor's stream concurrently with the
+// detection; the erasure half waits for the dilated mask.
+__global__ void k_orb_gray_in(const uint8_t *__restrict__ bgr, int W, int H, int rgb_order, uint8_t *__restrict__ dst, int pitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const uint8_t *p = bgr + 3 * ((size_t)y * W + x);
+    // cvtColor: gray = (c0 * 3735 + c1 * 19235 + c2 * 9798 + 16384) >> 15 with (c0, c2) = (B, R); RGB2GRAY reads the same bytes
+    // as (R, G, B), i.e. the outer weights swap
+    const int w0 = rgb_order ? 9798 : 3735, w2 = rgb_order ? 3735 : 9798;
+    dst[(size_t)y * pitch + x] = (uint8_t)((p[0] * w0 + p[1] * 19235 + p[2] * w2 + 16384) >> 15);
+}
+
+int detect_run_public(sindyn_ctx *c);        // detect.cu
+int detect_check_capacity(sindyn_ctx *c);    // detect.cu (synchronises the handle's stream)
+
+struct TrackSync { cudaEvent_t ev_in = nullptr, ev_mask = nullptr, ev_orb_done = nullptr; };
+static TrackSync *track_sync(sindyn_orb *o)
+{
+    if (!o->track) {
+        TrackSync *t = new TrackSync();
+        cudaEventCreateWithFlags(&t->ev_in, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&t->ev_mask, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&t->ev_orb_done, cudaEventDisableTiming);
+        cudaEventRecord(t->ev_orb_done, o->stream);
+        o->track = t;
+    }
+    return (TrackSync *)o->track;
+}
+
+static void track_free(sindyn_orb *o)
+{
+    TrackSync *t = (TrackSync *)o->track;
+    if (!t) return;
+    cudaEventDestroy(t->ev_in); cudaEventDestroy(t->ev_mask); cudaEventDestroy(t->ev_orb_done);
+    delete t;
+    o->track = nullptr;
+}
+
+// inputs already in c->bgr[c->i_cur] / c->depth (enqueued on c->stream).  Leaves the dilated mask in o->mask, labels in
+// c->rc.label_out, key points / descriptors in o->out_host_fmt / o->desc; nothing is synchronised.
+static int track_enqueue(sindyn_ctx *c, sindyn_orb *o, int rgb_order, int dilate_k)
+{
+    if (o->device != c->device || o->W != c->W || o->H != c->H) { c->err = "track_frame: the two handles differ in device or image size"; return SINDYN_ERR_INVALID; }
+    if (dilate_k < 0 || dilate_k > MORPH_MAX_K) { c->err = "track_frame: dilate_k out of range"; return SINDYN_ERR_INVALID; }
+    TrackSync *t = track_sync(o);
+    const OrbLevel &L0 = o->lv[0];
+    const uint8_t *bgr = c->bgr[c->i_cur];
+    CU_CHECK(c, cudaEventRecord(t->ev_in, c->stream));
+    CU_CHECK(o, cudaStreamWaitEvent(o->stream, t->ev_in, 0));
+    LAUNCH(o, k_orb_gray_in, dim3(cdiv(o->W, 32), cdiv(o->H, 8)), dim3(32, 8), 0, bgr, o->W, o->H, rgb_order,
+           o->pyr + (size_t)ORB_EDGE * L0.pitch + ORB_EDGE, L0.pitch);
+    SD_CHECK(orb_enqueue_unmasked(o));
+    SD_CHECK(detect_run_public(c));
+    // the previous frame's erasure half may still be reading o->mask
+    CU_CHECK(c, cudaStreamWaitEvent(c->stream, t->ev_orb_done, 0));
+    if (dilate_k > 1) SD_CHECK(morph_run(c, c->dd.out, o->mask, nullptr, c->W, c->H, dilate_k, MORPH_DILATE));
+    else CU_CHECK(c, cudaMemcpyAsync(o->mask, c->dd.out, c->N, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH_CHECK(c);
+    CU_CHECK(c, cudaEventRecord(t->ev_mask, c->stream));
+    CU_CHECK(o, cudaStreamWaitEvent(o->stream, t->ev_mask, 0));
+    SD_CHECK(orb_enqueue_masked(o, true));
+    CU_CHECK(o, cudaEventRecord(t->ev_orb_done, o->stream));
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_track_frame(sindyn_handle h, sindyn_orb_handle o, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step,
+                                  int rgb_order, int dilate_k, uint8_t *mask_out, size_t mask_step, uint8_t *label_out, size_t label_step,
+                                  sindyn_keypoint *kps, uint8_t *desc, int capacity, int *n_out, int frame_idx)
+{
+    (void)frame_idx;
+    if (!h || !o || !bgr || !depth || !n_out) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    *n_out = 0;
+    CU_CHECK(h, stage_in_2d(h->bgr[h->i_cur], bgr, bgr_step, (size_t)h->W * 3, h->H, h->pin_bgr, h->stream));
+    CU_CHECK(h, stage_in_2d(h->depth, depth, depth_step, (size_t)h->W * 2, h->H, h->pin_depth, h->stream));
+    SD_CHECK(track_enqueue(h, o, rgb_order, dilate_k));
+    // outputs in pinned caller memory are written by the DMA directly, pageable ones go through the handle's bounce buffers
+    const bool m_direct = mask_out && (mask_step == 0 || mask_step == (size_t)h->W) && host_ptr_is_pinned(mask_out);
+    const bool l_direct = label_out && (label_step == 0 || label_step == (size_t)h->W) && host_ptr_is_pinned(label_out);
+    const bool k_direct = kps && host_ptr_is_pinned(kps), d_direct = desc && host_ptr_is_pinned(desc);
+    if (mask_out) CU_CHECK(h, stage_out_begin(m_direct ? (void *)mask_out : (void *)h->pin_out0, o->mask, h->N, h->stream));
+    if (label_out) CU_CHECK(h, stage_out_begin(l_direct ? (void *)label_out : (void *)h->pin_out1, h->rc.label_out, h->N, h->stream));
+    // key points: the full fixed-capacity buffers are small next to the frame (ORB_OUT_MAX x (24 + 32) B would be 458 KB), so
+    // read the count first and then exactly n entries
+    CU_CHECK(o, cudaMemcpyAsync(o->ctl_host, o->ctl, sizeof(OrbControl), cudaMemcpyDeviceToHost, o->stream));
+    CU_CHECK(o, cudaStreamSynchronize(o->stream));
+    if (o->ctl_host->overflow) { h->err = o->err = "orb: a fixed-capacity list overflowed (candidates / nodes / output)"; return SINDYN_ERR_CAPACITY; }
+    const int n = o->ctl_host->n_out;
+    *n_out = n;
+    if (n > capacity) { h->err = o->err = "orb: output capacity too small"; return SINDYN_ERR_CAPACITY; }
+    if (n && kps) CU_CHECK(o, cudaMemcpyAsync(k_direct ? (void *)kps : (void *)o->pin_kp, o->out_host_fmt, sizeof(sindyn_keypoint) * n, cudaMemcpyDeviceToHost, o->stream));
+    if (n && desc) CU_CHECK(o, cudaMemcpyAsync(d_direct ? (void *)desc : (void *)o->pin_desc, o->desc, (size_t)32 * n, cudaMemcpyDeviceToHost, o->stream));
+    SD_CHECK(detect_check_capacity(h));   // synchronises h->stream (mask / label copies included)
+    CU_CHECK(o, cudaStreamSynchronize(o->stream));
+    if (mask_out && !m_direct) stage_out_finish(mask_out, mask_step, h->pin_out0, h->W, h->H);
+    if (label_out && !l_direct) stage_out_finish(label_out, label_step, h->pin_out1, h->W, h->H);
+    if (n && kps && !k_direct) memcpy(kps, o->pin_kp, sizeof(sindyn_keypoint) * n);
+    if (n && desc && !d_direct) memcpy(desc, o->pin_desc, (size_t)32 * n);
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_track_frame_resident(sindyn_handle h, sindyn_orb_handle o, int slot, int rgb_order, int dilate_k, int frame_idx)
+{
+    (void)frame_idx;
+    if (!h || !o) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    if (slot < 0 || slot >= SINDYN_MAX_SLOTS || !h->slot_bgr[slot]) { h->err = "track_frame_resident: empty slot"; return SINDYN_ERR_INVALID; }
+    CU_CHECK(h, cudaMemcpyAsync(h->bgr[h->i_cur], h->slot_bgr[slot], (size_t)h->N * 3, cudaMemcpyDeviceToDevice, h->stream));
+    CU_CHECK(h, cudaMemcpyAsync(h->depth, h->slot_depth[slot], (size_t)h->N * 2, cudaMemcpyDeviceToDevice, h->stream));
+    SD_CHECK(track_enqueue(h, o, rgb_order, dilate_k));
+    // join: the caller synchronises / times on the detector handle's stream only
+    CU_CHECK(h, cudaStreamWaitEvent(h->stream, ((TrackSync *)o->track)->ev_orb_done, 0));
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_track_get_results(sindyn_handle h, sindyn_orb_handle o, uint8_t *mask_dilated, uint8_t *labels, sindyn_keypoint *kps, uint8_t *desc,
+                                        int capacity, int *n_out)
+{
+    if (!h || !o || !n_out) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CU_CHECK(o, cudaStreamSynchronize(o->stream));
+    if (mask_dilated) CU_CHECK(h, cudaMemcpyAsync(mask_dilated, o->mask, h->N, cudaMemcpyDeviceToHost, h->stream));
+    if (labels) CU_CHECK(h, cudaMemcpyAsync(labels, h->rc.label_out, h->N, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaMemcpyAsync(o->ctl_host, o->ctl, sizeof(OrbControl), cudaMemcpyDeviceToHost, h->stream));
+    SD_CHECK(detect_check_capacity(h));
+    if (o->ctl_host->overflow) { h->err = o->err = "orb: a fixed-capacity list overflowed (candidates / nodes / output)"; return SINDYN_ERR_CAPACITY; }
+    const int n = o->ctl_host->n_out;
+    *n_out = n;
+    if (n > capacity) { h->err = "orb: output capacity too small"; return SINDYN_ERR_CAPACITY; }
+    if (n && kps) CU_CHECK(h, cudaMemcpy(kps, o->out_host_fmt, sizeof(sindyn_keypoint) * n, cudaMemcpyDeviceToHost));
+    if (n && desc) CU_CHECK(h, cudaMemcpy(desc, o->desc, (size_t)32 * n, cudaMemcpyDeviceToHost));
     return SINDYN_OK;
 }
 

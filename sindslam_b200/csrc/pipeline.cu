@@ -114,6 +114,17 @@ extern "C" int sindyn_get_flow_results(sindyn_handle h, float *flow, double *H_o
     return SINDYN_OK;
 }
 
+extern "C" int sindyn_get_path_info(sindyn_handle h, int info[4])
+{
+    H_CHECK(h);
+    if (!info) return SINDYN_ERR_INVALID;
+    info[0] = h->flow_graph_active ? 1 : 0;
+    info[1] = h->flow_graph_broken ? 1 : 0;
+    info[2] = (h->cluster_graph != nullptr) ? 1 : 0;
+    info[3] = 0;
+    return SINDYN_OK;
+}
+
 extern "C" int sindyn_brox_profile(sindyn_handle h, double *out4)
 {
     H_CHECK(h);

@@ -297,3 +297,53 @@ def load_tum_sequence(root: str):
             if len(s) >= 4:
                 ts.append(float(s[0])); rgb.append(os.path.join(root, s[1])); dep.append(os.path.join(root, s[3]))
     return rgb, dep, ts
+
+
+
+def make_sequence_parallel(n_frames: int, cam: CameraConfig = TUM3, seq: int = 0, kind: str = "box", start: int = 0, hole_rate: float = 0.015,
+                           workers: int | None = None):
+    """Same frames as :func:`make_sequence` (every frame is rendered independently from (seed, index)), rendered by worker
+    PROCESSES -- long sequences (BASELINE.json configs[2]: 300 frames) take ~0.9 s per frame on one core.  The workers are
+    plain `python -m sindslam_b200.synth` subprocesses writing .npz chunks: no fork of a process that may hold a CUDA context.
+    Frames come back without points_w / obj_id."""
+    import subprocess
+    import sys
+    import tempfile
+    workers = max(1, min(workers or (os.cpu_count() or 1), 32, n_frames // 2))
+    scene = Scene(BASE_SEED + seq, kind)
+    scene.hole_rate = hole_rate
+    if workers <= 1:
+        return scene, [render_frame(scene, cam, start + i) for i in range(n_frames)]
+    bounds = np.linspace(0, n_frames, workers + 1).astype(int)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = []
+        for w in range(workers):
+            a, b = int(bounds[w]), int(bounds[w + 1])
+            out = os.path.join(tmp, "chunk%03d.npz" % w)
+            cmd = [sys.executable, "-m", "sindslam_b200.synth", "--render", str(seq), kind, repr(hole_rate), cam.name, str(start + a), str(b - a), out]
+            procs.append((subprocess.Popen(cmd, cwd=root, env=dict(os.environ, OMP_NUM_THREADS="1")), out))
+        frames = []
+        for p, out in procs:
+            if p.wait(timeout=1800) != 0:
+                raise RuntimeError("synth worker failed")
+            z = np.load(out)
+            for i in range(len(z["timestamp"])):
+                frames.append(Frame(z["bgr"][i], z["depth"][i], float(z["timestamp"][i]), z["T_wc"][i], z["dyn"][i]))
+    return scene, frames
+
+
+def _worker_main(argv):
+    seq, kind, hole, cam_name, a, n, out = int(argv[0]), argv[1], float(argv[2]), argv[3], int(argv[4]), int(argv[5]), argv[6]
+    cam = {c.name: c for c in (TUM3, D455_848)}[cam_name]
+    scene = Scene(BASE_SEED + seq, kind)
+    scene.hole_rate = hole
+    fr = [render_frame(scene, cam, a + i) for i in range(n)]
+    np.savez(out, bgr=np.stack([f.bgr for f in fr]), depth=np.stack([f.depth for f in fr]), dyn=np.stack([f.dyn_mask for f in fr]),
+             T_wc=np.stack([f.T_wc for f in fr]), timestamp=np.array([f.timestamp for f in fr], np.float64))
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) >= 9 and sys.argv[1] == "--render":
+        _worker_main(sys.argv[2:])

@@ -76,3 +76,41 @@ def test_resident_equals_host_path(seq_c1):
     assert p["sor_launches"] == 180 and p["pixel_sweeps"] == 100 * 302822 and p["sor_ms"] > 0
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("entry", ["detect", "flow_residual"])
+def test_one_graph_flow_branch_equals_classic_path(entry):
+    """The default path (use_graphs=1, stage_timing=0) runs the whole flow branch as ONE CUDA graph: the large-motion decision
+    (DynaDetect.cc:1097-1114) is a conditional IF node whose body is the second Brox solve, and the refinement picks its
+    reference image from the device flag.  It must be bit-identical, frame by frame, to the classic path (use_graphs=0:
+    host decision after a D2H copy, like the reference, DynaDetect.cc:1073) on a sequence WITH a large-motion frame jump
+    (7 -> 23 -> 9) and refine=1: flow, H, thresholds, both masks, the large-motion flag -- and for sindyn_detect the final
+    mask and labels."""
+    from sindslam_b200.capi import SinDyn
+    cam = synth.TUM3
+    _, frames = synth.make_sequence(24, cam, seq=1, kind="box", start=4)
+    order = list(range(0, 8)) + [23] + list(range(9, 12))
+    mk = lambda **kw: SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, refine=1, plane_edges=0, **kw)
+    a, b = mk(), mk(use_graphs=0)
+    for s in (a, b):
+        s.set_prev_frames(frames[order[0]].bgr, frames[order[0]].bgr)
+    n_large = n_graph = 0
+    for n, k in enumerate(order[1:], 1):
+        f = frames[k]
+        if entry == "detect":
+            ra, rb = a.detect(f.bgr, f.depth, n), b.detect(f.bgr, f.depth, n)
+        else:
+            ra, rb = a.flow_residual(f.bgr, roll=True), b.flow_residual(f.bgr, roll=True)
+        pa, pb = a.path_info(), b.path_info()
+        fa, fb = a.flow_results(), b.flow_results()
+        assert not pb["flow_one_graph"] and not pa["flow_graph_broken"]
+        n_graph += int(pa["flow_one_graph"])
+        assert fa["large_motion"] == fb["large_motion"], n
+        n_large += int(fa["large_motion"])
+        for key in ("flow", "H", "thr", "low", "high"):
+            assert np.array_equal(fa[key], fb[key]), (n, key)
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), n
+    assert n_large >= 1, "the frame jump must trigger the large-motion fallback (second Brox solve inside the IF node)"
+    assert n_graph == len(order) - 1, "the default handle must take the one-graph path on every frame"
+    a.close()
+    b.close()
