@@ -37,20 +37,31 @@ struct PeacNode {               // ahc::PlaneSeg (AHCPlaneSeg.hpp:29-188), index
 
 struct PeacPlane { double center[3], normal[3], mse, thr; int N, rid, valid, final_id; double st[9]; };
 
+struct PeacExtract { double st[9], normal[3], mse, pop_key; int N, rid; };   // one extracted plane of one graph component, unsorted
+
 struct PeacControl {
-    int n_planes, n_final, overflow, grow_changed;
-    int grow_flag[128];                      // launch i of the region growing changed something
+    int n_planes, n_final, overflow, n_ex;      // header (16 ints), zeroed every frame
+    int done, n_comp, grow_levels, grow_entries;
+    int hdr_pad[8];
     int parent[PEAC_MAXB], size[PEAC_MAXB];
     int blk_map[PEAC_MAXB];
+    PeacExtract ex[PEAC_MAXP];
     PeacPlane pl[PEAC_MAXP];
     unsigned long long conn[PEAC_MAXP];      // planes that met during region growing with similar normals
 };
+
+#define PG_CAP 131072          // entries of one FIFO level of the region growing (observed: <= 12 k at 848 x 480)
 
 struct PeacImpl {
     PeacNode *nodes = nullptr;
     PeacControl *ctl = nullptr;
     int *label = nullptr;        // membershipImg
     float *dist = nullptr;
+    int *head = nullptr;         // per pixel: head of the list of this level's visits
+    int *qa = nullptr, *qb = nullptr;                                        // FIFO level n / n + 1: (plane << 20) | pixel
+    int *v_pix = nullptr, *v_info = nullptr, *v_next = nullptr;              // visit records of one level, slot = 4 * entry + direction
+    float *v_dist = nullptr;
+    unsigned char *v_push = nullptr;
     ulonglong2 *PB = nullptr;    // final plane membership bitset
     int Nw = 0, Nh = 0;
 };
@@ -214,7 +225,18 @@ struct MergeResult { double st[9], c[3], n[3], mse; };
 //     (merged sums + eigen solve) runs per thread; the winning thread hands its merged plane over through shared memory;
 //   * the bookkeeping of a merge is done by warp 0 (shuffle arg-min over the 8 warp results, lanes copy the sums).
 #define PEAC_AHC_NT 256   // threads of k_peac_ahc (a power of two: node b is owned by thread b & (PEAC_AHC_NT - 1))
-__global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(PeacNode *__restrict__ nodes, PeacControl *ctl, int Nw, int Nh)
+#define PEAC_AHC_CTAS 32  // CTAs of k_peac_ahc: one connected component of the block graph each (more components: round robin)
+
+// Edges exist only between blocks of one connected component of the initial graph and every later edge is inherited from
+// them, so the clustering of one component never reads or writes another one: the global pop order of the reference's
+// single queue only INTERLEAVES the components.  Every CTA therefore rebuilds the (tiny) initial graph, labels its
+// connected components and clusters the components blockIdx.x, blockIdx.x + gridDim.x, ... on its own SM; components of
+// fewer than minSupport / 256 blocks can never reach minSupport and are skipped.  The serial chain of a frame shrinks from
+// "all valid blocks" (~1000 pops) to "the blocks of the largest component".  The order in which the reference extracts
+// planes (it only matters for the stable size sort, AHCPlaneFitter.hpp:1251-1254) is recovered from the MSE of the
+// extracted node: the popped MSEs of the single queue are non-decreasing (a merged node is never better than the popped
+// minimum it contains), so "extraction order" == "ascending pop MSE".
+__global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__restrict__ nodes, PeacControl *ctl, int Nw, int Nh)
 {
     extern __shared__ unsigned char smraw[];
     double *nrm = (double *)smraw;                                       // 3 x PEAC_MAXB
@@ -226,240 +248,344 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(PeacNode *__restrict__
     unsigned short *ssize = root + PEAC_MAXB;                            // PEAC_MAXB
     unsigned short *eu = ssize + PEAC_MAXB, *ev = eu + PEAC_MAXE;        // edges, column t = entries t, t + 256, ...
     unsigned char *flags = (unsigned char *)(ev + PEAC_MAXE);            // PEAC_MAXB
-    __shared__ int s_ne, s_seq, s_nex, s_lose, s_win, s_ncand;
-    __shared__ int stamp[PEAC_MAXB];
+    __shared__ int s_ne, s_seq, s_nex, s_lose, s_win, s_ncand, s_changed, s_nactive;
+    __shared__ int stamp[PEAC_MAXB];          // component label while the graph is set up, candidate stamp during the clustering
     __shared__ unsigned short cand[PEAC_MAXCAND];
+    __shared__ unsigned short s_active[PEAC_MAXB / 8 + 1];
     __shared__ int s_ex[PEAC_MAXP];
+    __shared__ double s_exkey[PEAC_MAXP];
     __shared__ double w_mse[8];
     __shared__ unsigned long long w_key[8];
     __shared__ int w_o[8], w_seq[8];
     __shared__ MergeResult w_res[8];
     const int tid = threadIdx.x, nt = PEAC_AHC_NT, lane = tid & 31, wid = tid >> 5;
     const int NB = Nw * Nh;
-    for (int b = tid; b < NB; b += nt) {
-        root[b] = (unsigned short)b; ssize[b] = 1; stamp[b] = -1;
-        nrm[3 * b] = nodes[b].normal[0]; nrm[3 * b + 1] = nodes[b].normal[1]; nrm[3 * b + 2] = nodes[b].normal[2];
-        mse_a[b] = nodes[b].mse; N_a[b] = nodes[b].N; seq_a[b] = b;
-        flags[b] = nodes[b].valid ? (PF_ALIVE | PF_VALID | PF_QUEUED) : 0;
-        for (int k = 0; k < 9; ++k) sst[b * 9 + k] = nodes[b].st[k];
-    }
-    if (tid == 0) { s_ne = 0; s_seq = NB; s_nex = 0; s_lose = -1; s_win = -1; s_ncand = 0; }
-    __syncthreads();
     auto sim = [&](int a, int b) { return fabs(nrm[3 * a] * nrm[3 * b] + nrm[3 * a + 1] * nrm[3 * b + 1] + nrm[3 * a + 2] * nrm[3 * b + 2]); };
-    auto valid = [&](int b) { return (flags[b] & PF_VALID) != 0; };
     auto add_edge = [&](int a, int b) {
         int e = atomicAdd(&s_ne, 1);
         if (e < PEAC_MAXE) { eu[e] = (unsigned short)a; ev[e] = (unsigned short)b; }
     };
-    // initGraph edges (AHCPlaneFitter.hpp:958-1014): rows and columns are independent, one thread each
-    if (tid < Nh) {
-        const int i = tid;
-        for (int j = 1; j < Nw; j += 2) {
-            const int c = i * Nw + j;
-            if (!valid(c - 1)) { --j; continue; }
-            if (!valid(c)) continue;
-            if (j < Nw - 1 && !valid(c + 1)) { ++j; continue; }
-            const double th = peac_t_ang_init(nodes[c].center[2]);
-            if ((j < Nw - 1 && sim(c - 1, c + 1) >= th) || (j == Nw - 1 && sim(c, c - 1) >= th)) {
-                add_edge(c, c - 1);
-                if (j < Nw - 1) add_edge(c, c + 1);
-            } else --j;
+    for (int round = 0;; ++round) {
+        __syncthreads();
+        for (int b = tid; b < NB; b += nt) {
+            root[b] = (unsigned short)b; ssize[b] = 1; stamp[b] = b;
+            nrm[3 * b] = nodes[b].normal[0]; nrm[3 * b + 1] = nodes[b].normal[1]; nrm[3 * b + 2] = nodes[b].normal[2];
+            mse_a[b] = nodes[b].mse; N_a[b] = nodes[b].N; seq_a[b] = 0;
+            flags[b] = nodes[b].valid ? PF_VALID : 0;
+            for (int k = 0; k < 9; ++k) sst[b * 9 + k] = nodes[b].st[k];
         }
-    }
-    if (tid >= 64 && tid - 64 < Nw) {
-        const int j = tid - 64;
-        for (int i = 1; i < Nh; i += 2) {
-            const int c = i * Nw + j;
-            if (!valid(c - Nw)) { --i; continue; }
-            if (!valid(c)) continue;
-            if (i < Nh - 1 && !valid(c + Nw)) { ++i; continue; }
-            const double th = peac_t_ang_init(nodes[c].center[2]);
-            if ((i < Nh - 1 && sim(c - Nw, c + Nw) >= th) || (i == Nh - 1 && sim(c, c - Nw) >= th)) {
-                add_edge(c, c - Nw);
-                if (i < Nh - 1) add_edge(c, c + Nw);
-            } else --i;
+        if (tid == 0) { s_ne = 0; s_seq = NB; s_nex = 0; s_lose = -1; s_win = -1; s_ncand = 0; s_nactive = 0; }
+        __syncthreads();
+        auto valid = [&](int b) { return (flags[b] & PF_VALID) != 0; };
+        // initGraph edges (AHCPlaneFitter.hpp:958-1014): rows and columns are independent, one thread each
+        if (tid < Nh) {
+            const int i = tid;
+            for (int j = 1; j < Nw; j += 2) {
+                const int c = i * Nw + j;
+                if (!valid(c - 1)) { --j; continue; }
+                if (!valid(c)) continue;
+                if (j < Nw - 1 && !valid(c + 1)) { ++j; continue; }
+                const double th = peac_t_ang_init(nodes[c].center[2]);
+                if ((j < Nw - 1 && sim(c - 1, c + 1) >= th) || (j == Nw - 1 && sim(c, c - 1) >= th)) {
+                    add_edge(c, c - 1);
+                    if (j < Nw - 1) add_edge(c, c + 1);
+                } else --j;
+            }
         }
-    }
-    __syncthreads();
-    const int NE = min(s_ne, PEAC_MAXE);
-    if (tid == 0 && s_ne > PEAC_MAXE) ctl->overflow = 1;
-    int my_cnt = NE > tid ? (NE - tid + nt - 1) / nt : 0;   // live entries of this thread's edge column
-    int pop_id = 0;
-    // arg-min state of this thread over the nodes it owns (b = tid, tid + nt, ...): recomputed only after one of them changed
-    unsigned long long my_key = ~0ull;   // order-preserving bit pattern of the mse (peac_key)
-    int my_p = -1, my_s = 0x7fffffff;
-    bool my_dirty = true;
-    int prev_p = -1;
-    for (;;) {
-        // ---- flatten the union-find after the previous merge, and arg-min (mse, seq) over the queued live nodes
-        const int lose = s_lose, win = s_win;
-        if (lose >= 0) {
-            for (int b = tid; b < NB; b += nt)
-                if (root[b] == lose) root[b] = (unsigned short)win;
-            if ((lose & (PEAC_AHC_NT - 1)) == tid || (win & (PEAC_AHC_NT - 1)) == tid) my_dirty = true;
-        }
-        if (prev_p >= 0 && (prev_p & (PEAC_AHC_NT - 1)) == tid) my_dirty = true;
-        if (my_dirty) {
-            my_key = ~0ull; my_p = -1; my_s = 0x7fffffff;
-            for (int b = tid; b < NB; b += nt)
-                if ((flags[b] & (PF_ALIVE | PF_QUEUED)) == (PF_ALIVE | PF_QUEUED)) {
-                    const unsigned long long kb = peac_key(mse_a[b]);
-                    const int sq = seq_a[b];
-                    if (kb < my_key || (kb == my_key && sq < my_s)) { my_key = kb; my_p = b; my_s = sq; }
-                }
-            my_dirty = false;
-        }
-        // lexicographic (mse bits, seq) minimum of the warp with three hardware reductions; seq is unique
-        auto warp_argmin = [&](unsigned long long key, int sq, int node) -> int {
-            const unsigned hi = node >= 0 ? (unsigned)(key >> 32) : 0xffffffffu, lo = (unsigned)key;
-            const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-            bool c = node >= 0 && hi == mh;
-            const unsigned ml = __reduce_min_sync(0xffffffffu, c ? lo : 0xffffffffu);
-            c = c && lo == ml;
-            const unsigned ms = __reduce_min_sync(0xffffffffu, c ? (unsigned)sq : 0xffffffffu);
-            const unsigned who = __ballot_sync(0xffffffffu, c && (unsigned)sq == ms);
-            return who ? __ffs(who) - 1 : -1;   // lane that holds the minimum, -1 = no live node in this warp
-        };
-        {
-            const int wl = warp_argmin(my_key, my_s, my_p);
-            const int src = wl >= 0 ? wl : 0;
-            const unsigned long long k0 = __shfl_sync(0xffffffffu, my_key, src);
-            const int p0 = __shfl_sync(0xffffffffu, my_p, src), s0 = __shfl_sync(0xffffffffu, my_s, src);
-            if (lane == 0) { w_key[wid] = k0; w_o[wid] = wl >= 0 ? p0 : -1; w_seq[wid] = s0; }
+        if (tid >= 64 && tid - 64 < Nw) {
+            const int j = tid - 64;
+            for (int i = 1; i < Nh; i += 2) {
+                const int c = i * Nw + j;
+                if (!valid(c - Nw)) { --i; continue; }
+                if (!valid(c)) continue;
+                if (i < Nh - 1 && !valid(c + Nw)) { ++i; continue; }
+                const double th = peac_t_ang_init(nodes[c].center[2]);
+                if ((i < Nh - 1 && sim(c - Nw, c + Nw) >= th) || (i == Nh - 1 && sim(c, c - Nw) >= th)) {
+                    add_edge(c, c - Nw);
+                    if (i < Nh - 1) add_edge(c, c + Nw);
+                } else --i;
+            }
         }
         __syncthreads();
-        int p = -1;
-        {
-            const int o8 = lane < 8 ? w_o[lane] : -1;
-            const int wl = warp_argmin(lane < 8 ? w_key[lane] : ~0ull, lane < 8 ? w_seq[lane] : 0x7fffffff, o8);
-            p = wl >= 0 ? __shfl_sync(0xffffffffu, o8, wl) : -1;
+        const int NE = min(s_ne, PEAC_MAXE);
+        if (tid == 0 && s_ne > PEAC_MAXE) ctl->overflow = 1;
+        // ---- connected components of the initial graph: minimum-label propagation over the edges + pointer jumping
+        int *comp = stamp;
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) s_changed = 0;
+            __syncthreads();
+            bool ch = false;
+            for (int e = tid; e < NE; e += nt) {
+                const int u = eu[e], v = ev[e];
+                const int a = comp[u], b = comp[v];
+                if (a < b) { atomicMin(&comp[v], a); atomicMin(&comp[b], a); ch = true; }
+                else if (b < a) { atomicMin(&comp[u], b); atomicMin(&comp[a], b); ch = true; }
+            }
+            if (ch) s_changed = 1;
+            __syncthreads();
+            for (int b = tid; b < NB; b += nt) {
+                int c = comp[b];
+                while (comp[c] != c) c = comp[c];
+                comp[b] = c;     // racing writers only ever move a label further down its own chain
+            }
+            __syncthreads();
+            if (!s_changed) break;
         }
-        prev_p = p;
-        if (p < 0) break;
-        ++pop_id;
-        // ---- distinct live graph neighbours of p (AHCPlaneFitter.hpp:1092-1117).  The scan itself has independent iterations
-        // (the loads of several edges are in flight together); dead edges (internal to a node, or touching an extracted
-        // node) are only skipped here and compacted out of the thread's edge column every 16th pop.
-        if ((pop_id & 15) == 0) {
-            for (int i = 0; i < my_cnt;) {
+        // component sizes (seq_a as scratch) and the ascending list of components that can reach minSupport
+        for (int b = tid; b < NB; b += nt)
+            if (valid(b)) atomicAdd(&seq_a[comp[b]], 1);
+        __syncthreads();
+        if (wid == 0) {
+            int n = 0;
+            for (int b0 = 0; b0 < NB; b0 += 32) {
+                const int b = b0 + lane;
+                const bool is = b < NB && valid(b) && comp[b] == b && seq_a[b] * PEAC_WIN * PEAC_WIN >= PEAC_MIN_SUPPORT;
+                const unsigned m = __ballot_sync(0xffffffffu, is);
+                if (is) s_active[n + __popc(m & ((1u << lane) - 1))] = (unsigned short)b;
+                n += __popc(m);
+            }
+            if (lane == 0) s_nactive = n;
+        }
+        __syncthreads();
+        const int n_active = s_nactive;
+        if (round == 0 && blockIdx.x == 0) {
+            // blocks outside the clustered components stay singletons (their sets can never reach minSupport)
+            for (int b = tid; b < NB; b += nt) {
+                const int c = comp[b];
+                if (!(valid(b) && seq_a[c] * PEAC_WIN * PEAC_WIN >= PEAC_MIN_SUPPORT)) { ctl->parent[b] = b; ctl->size[b] = 1; }
+            }
+            if (tid == 0) ctl->n_comp = n_active;
+        }
+        const int ci = blockIdx.x + round * gridDim.x;
+        if (ci >= n_active) break;
+        const int my_comp = s_active[ci];
+        __syncthreads();
+        for (int b = tid; b < NB; b += nt) {
+            const bool mine = valid(b) && comp[b] == my_comp;
+            flags[b] = mine ? (PF_ALIVE | PF_VALID | PF_QUEUED) : 0;
+            seq_a[b] = b;
+        }
+        __syncthreads();
+        // edges of the other components go away in the first compaction; from here on stamp[] is the candidate stamp
+        int my_cnt = NE > tid ? (NE - tid + nt - 1) / nt : 0;   // live entries of this thread's edge column
+        for (int i = 0; i < my_cnt;) {
+            const int e = i * nt + tid;
+            if (!(flags[eu[e]] & PF_ALIVE)) {
+                const int last = (my_cnt - 1) * nt + tid;
+                eu[e] = eu[last]; ev[e] = ev[last];
+                --my_cnt;
+                continue;
+            }
+            ++i;
+        }
+        __syncthreads();
+        for (int b = tid; b < NB; b += nt) stamp[b] = -1;
+        int pop_id = 0;
+        // arg-min state of this thread over the nodes it owns (b = tid, tid + nt, ...): recomputed only after one of them changed
+        unsigned long long my_key = ~0ull;   // order-preserving bit pattern of the mse (peac_key)
+        int my_p = -1, my_s = 0x7fffffff;
+        bool my_dirty = true;
+        int prev_p = -1;
+        __syncthreads();
+        for (;;) {
+            // ---- flatten the union-find after the previous merge, and arg-min (mse, seq) over the queued live nodes
+            const int lose = s_lose, win = s_win;
+            if (lose >= 0) {
+                for (int b = tid; b < NB; b += nt)
+                    if (root[b] == lose) root[b] = (unsigned short)win;
+                if ((lose & (PEAC_AHC_NT - 1)) == tid || (win & (PEAC_AHC_NT - 1)) == tid) my_dirty = true;
+            }
+            if (prev_p >= 0 && (prev_p & (PEAC_AHC_NT - 1)) == tid) my_dirty = true;
+            if (my_dirty) {
+                my_key = ~0ull; my_p = -1; my_s = 0x7fffffff;
+                for (int b = tid; b < NB; b += nt)
+                    if ((flags[b] & (PF_ALIVE | PF_QUEUED)) == (PF_ALIVE | PF_QUEUED)) {
+                        const unsigned long long kb = peac_key(mse_a[b]);
+                        const int sq = seq_a[b];
+                        if (kb < my_key || (kb == my_key && sq < my_s)) { my_key = kb; my_p = b; my_s = sq; }
+                    }
+                my_dirty = false;
+            }
+            // lexicographic (mse bits, seq) minimum of the warp with three hardware reductions; seq is unique
+            auto warp_argmin = [&](unsigned long long key, int sq, int node) -> int {
+                const unsigned hi = node >= 0 ? (unsigned)(key >> 32) : 0xffffffffu, lo = (unsigned)key;
+                const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                bool c = node >= 0 && hi == mh;
+                const unsigned ml = __reduce_min_sync(0xffffffffu, c ? lo : 0xffffffffu);
+                c = c && lo == ml;
+                const unsigned ms = __reduce_min_sync(0xffffffffu, c ? (unsigned)sq : 0xffffffffu);
+                const unsigned who = __ballot_sync(0xffffffffu, c && (unsigned)sq == ms);
+                return who ? __ffs(who) - 1 : -1;   // lane that holds the minimum, -1 = no live node in this warp
+            };
+            {
+                const int wl = warp_argmin(my_key, my_s, my_p);
+                const int src = wl >= 0 ? wl : 0;
+                const unsigned long long k0 = __shfl_sync(0xffffffffu, my_key, src);
+                const int p0 = __shfl_sync(0xffffffffu, my_p, src), s0 = __shfl_sync(0xffffffffu, my_s, src);
+                if (lane == 0) { w_key[wid] = k0; w_o[wid] = wl >= 0 ? p0 : -1; w_seq[wid] = s0; }
+            }
+            __syncthreads();
+            int p = -1;
+            {
+                const int o8 = lane < 8 ? w_o[lane] : -1;
+                const int wl = warp_argmin(lane < 8 ? w_key[lane] : ~0ull, lane < 8 ? w_seq[lane] : 0x7fffffff, o8);
+                p = wl >= 0 ? __shfl_sync(0xffffffffu, o8, wl) : -1;
+            }
+            prev_p = p;
+            if (p < 0) break;
+            ++pop_id;
+            // ---- distinct live graph neighbours of p (AHCPlaneFitter.hpp:1092-1117).  The scan itself has independent iterations
+            // (the loads of several edges are in flight together); dead edges (internal to a node, or touching an extracted
+            // node) are only skipped here and compacted out of the thread's edge column every 16th pop.
+            if ((pop_id & 15) == 0) {
+                for (int i = 0; i < my_cnt;) {
+                    const int e = i * nt + tid;
+                    const int ru = root[eu[e]], rv = root[ev[e]];
+                    if (ru == rv || !(flags[ru] & PF_ALIVE) || !(flags[rv] & PF_ALIVE)) {   // edge is gone for good
+                        const int last = (my_cnt - 1) * nt + tid;
+                        eu[e] = eu[last]; ev[e] = ev[last];
+                        --my_cnt;
+                        continue;
+                    }
+                    ++i;
+                }
+            }
+#pragma unroll 4
+            for (int i = 0; i < my_cnt; ++i) {
                 const int e = i * nt + tid;
                 const int ru = root[eu[e]], rv = root[ev[e]];
-                if (ru == rv || !(flags[ru] & PF_ALIVE) || !(flags[rv] & PF_ALIVE)) {   // edge is gone for good
-                    const int last = (my_cnt - 1) * nt + tid;
-                    eu[e] = eu[last]; ev[e] = ev[last];
-                    --my_cnt;
-                    continue;
+                const int o = ru == p ? rv : (rv == p ? ru : -1);
+                if (o >= 0 && o != p && (flags[o] & PF_ALIVE) && atomicExch(&stamp[o], pop_id) != pop_id) {
+                    const int slot = atomicAdd(&s_ncand, 1);
+                    if (slot < PEAC_MAXCAND) cand[slot] = (unsigned short)o;
                 }
-                ++i;
             }
-        }
-#pragma unroll 4
-        for (int i = 0; i < my_cnt; ++i) {
-            const int e = i * nt + tid;
-            const int ru = root[eu[e]], rv = root[ev[e]];
-            const int o = ru == p ? rv : (rv == p ? ru : -1);
-            if (o >= 0 && o != p && (flags[o] & PF_ALIVE) && atomicExch(&stamp[o], pop_id) != pop_id) {
-                const int slot = atomicAdd(&s_ncand, 1);
-                if (slot < PEAC_MAXCAND) cand[slot] = (unsigned short)o;
+            __syncthreads();
+            const int ncand = min(s_ncand, PEAC_MAXCAND);
+            double best = 1e300;
+            int best_o = -1;
+            MergeResult res;
+            for (int ci2 = tid; ci2 < ncand; ci2 += nt) {
+                const int o = cand[ci2];
+                if (sim(p, o) < PEAC_SIM_MERGE) continue;
+                double st[9], c[3], n[3], mse;
+                for (int k = 0; k < 9; ++k) st[k] = sst[p * 9 + k] + sst[o * 9 + k];
+                peac_compute(st, N_a[p] + N_a[o], c, n, mse);
+                if (mse < best || (mse == best && o < best_o)) {
+                    best = mse; best_o = o;
+                    for (int k = 0; k < 9; ++k) res.st[k] = st[k];
+                    for (int k = 0; k < 3; ++k) { res.c[k] = c[k]; res.n[k] = n[k]; }
+                    res.mse = mse;
+                }
             }
-        }
-        __syncthreads();
-        const int ncand = min(s_ncand, PEAC_MAXCAND);
-        double best = 1e300;
-        int best_o = -1;
-        MergeResult res;
-        for (int ci = tid; ci < ncand; ci += nt) {
-            const int o = cand[ci];
-            if (sim(p, o) < PEAC_SIM_MERGE) continue;
-            double st[9], c[3], n[3], mse;
-            for (int k = 0; k < 9; ++k) st[k] = sst[p * 9 + k] + sst[o * 9 + k];
-            peac_compute(st, N_a[p] + N_a[o], c, n, mse);
-            if (mse < best || (mse == best && o < best_o)) {
-                best = mse; best_o = o;
-                for (int k = 0; k < 9; ++k) res.st[k] = st[k];
-                for (int k = 0; k < 3; ++k) { res.c[k] = c[k]; res.n[k] = n[k]; }
-                res.mse = mse;
+            double wb = best;
+            int wo = best_o;
+            for (int off = 16; off > 0; off >>= 1) {
+                const double om = __shfl_xor_sync(0xffffffffu, wb, off);
+                const int oo = __shfl_xor_sync(0xffffffffu, wo, off);
+                if (oo >= 0 && (wo < 0 || om < wb || (om == wb && oo < wo))) { wb = om; wo = oo; }
             }
-        }
-        double wb = best;
-        int wo = best_o;
-        for (int off = 16; off > 0; off >>= 1) {
-            const double om = __shfl_xor_sync(0xffffffffu, wb, off);
-            const int oo = __shfl_xor_sync(0xffffffffu, wo, off);
-            if (oo >= 0 && (wo < 0 || om < wb || (om == wb && oo < wo))) { wb = om; wo = oo; }
-        }
-        const unsigned winners = __ballot_sync(0xffffffffu, best_o >= 0 && best_o == wo && best == wb);
-        if (wo >= 0 && lane == __ffs(winners) - 1) w_res[wid] = res;
-        if (lane == 0) { w_mse[wid] = wb; w_o[wid] = wo; }   // (the arg-min scratch was last read before the previous barrier)
-        __syncthreads();
-        // ---- merge or extract: warp 0
-        if (wid == 0) {
-            double km = lane < 8 ? w_mse[lane] : 1e300;
-            int ko = lane < 8 ? w_o[lane] : -1, kw = lane;
-            for (int off = 4; off > 0; off >>= 1) {
-                const double om = __shfl_xor_sync(0xffffffffu, km, off);
-                const int oo = __shfl_xor_sync(0xffffffffu, ko, off), ow = __shfl_xor_sync(0xffffffffu, kw, off);
-                if (oo >= 0 && (ko < 0 || om < km || (om == km && oo < ko))) { km = om; ko = oo; kw = ow; }
-            }
-            ko = __shfl_sync(0xffffffffu, ko, 0); kw = __shfl_sync(0xffffffffu, kw, 0);
-            bool merged = false;
-            if (ko >= 0) {
-                const MergeResult &m = w_res[kw];
-                if (m.mse < peac_t_mse(false, m.c[2])) {
-                    merged = true;
-                    // PlaneSeg(pa, pb): rid of the larger parent; DisjointSet::Union by size keeps the same root
-                    const int o = ko;
-                    const int wn = N_a[p] >= N_a[o] ? p : o, ls = wn == p ? o : p;
-                    const int Nsum = N_a[p] + N_a[o];
-                    __syncwarp();
-                    if (lane < 9) sst[wn * 9 + lane] = m.st[lane];
-                    else if (lane < 12) nrm[3 * wn + lane - 9] = m.n[lane - 9];
-                    else if (lane == 12) {
-                        mse_a[wn] = m.mse; N_a[wn] = Nsum;
-                        seq_a[wn] = s_seq++;            // the merged node is a NEW queue entry
-                        ssize[wn] += ssize[ls];
-                        flags[wn] |= PF_ALIVE | PF_QUEUED;
-                        flags[ls] &= ~(PF_ALIVE | PF_QUEUED);
-                        s_lose = ls; s_win = wn;
+            const unsigned winners = __ballot_sync(0xffffffffu, best_o >= 0 && best_o == wo && best == wb);
+            if (wo >= 0 && lane == __ffs(winners) - 1) w_res[wid] = res;
+            if (lane == 0) { w_mse[wid] = wb; w_o[wid] = wo; }   // (the arg-min scratch was last read before the previous barrier)
+            __syncthreads();
+            // ---- merge or extract: warp 0
+            if (wid == 0) {
+                double km = lane < 8 ? w_mse[lane] : 1e300;
+                int ko = lane < 8 ? w_o[lane] : -1, kw = lane;
+                for (int off = 4; off > 0; off >>= 1) {
+                    const double om = __shfl_xor_sync(0xffffffffu, km, off);
+                    const int oo = __shfl_xor_sync(0xffffffffu, ko, off), ow = __shfl_xor_sync(0xffffffffu, kw, off);
+                    if (oo >= 0 && (ko < 0 || om < km || (om == km && oo < ko))) { km = om; ko = oo; kw = ow; }
+                }
+                ko = __shfl_sync(0xffffffffu, ko, 0); kw = __shfl_sync(0xffffffffu, kw, 0);
+                bool merged = false;
+                if (ko >= 0) {
+                    const MergeResult &m = w_res[kw];
+                    if (m.mse < peac_t_mse(false, m.c[2])) {
+                        merged = true;
+                        // PlaneSeg(pa, pb): rid of the larger parent; DisjointSet::Union by size keeps the same root
+                        const int o = ko;
+                        const int wn = N_a[p] >= N_a[o] ? p : o, ls = wn == p ? o : p;
+                        const int Nsum = N_a[p] + N_a[o];
+                        __syncwarp();
+                        if (lane < 9) sst[wn * 9 + lane] = m.st[lane];
+                        else if (lane < 12) nrm[3 * wn + lane - 9] = m.n[lane - 9];
+                        else if (lane == 12) {
+                            mse_a[wn] = m.mse; N_a[wn] = Nsum;
+                            seq_a[wn] = s_seq++;            // the merged node is a NEW queue entry
+                            ssize[wn] += ssize[ls];
+                            flags[wn] |= PF_ALIVE | PF_QUEUED;
+                            flags[ls] &= ~(PF_ALIVE | PF_QUEUED);
+                            s_lose = ls; s_win = wn;
+                        }
                     }
                 }
-            }
-            if (!merged && lane == 0) {   // extract p (or drop it) and cut it out of the graph
-                if (N_a[p] >= PEAC_MIN_SUPPORT) {
-                    if (s_nex < PEAC_MAXP) s_ex[s_nex++] = p; else ctl->overflow = 1;
+                if (!merged && lane == 0) {   // extract p (or drop it) and cut it out of the graph
+                    if (N_a[p] >= PEAC_MIN_SUPPORT) {
+                        if (s_nex < PEAC_MAXP) { s_ex[s_nex] = p; s_exkey[s_nex] = mse_a[p]; ++s_nex; } else ctl->overflow = 1;
+                    }
+                    flags[p] &= ~(PF_ALIVE | PF_QUEUED);
+                    s_lose = -1;
                 }
-                flags[p] &= ~(PF_ALIVE | PF_QUEUED);
-                s_lose = -1;
+                if (lane == 0) {
+                    if (s_ncand > PEAC_MAXCAND) ctl->overflow = 1;
+                    s_ncand = 0;
+                }
             }
-            if (lane == 0) {
-                if (s_ncand > PEAC_MAXCAND) ctl->overflow = 1;
-                s_ncand = 0;
-            }
+            __syncthreads();
         }
+        // ---- results of this component: extracted planes (unsorted, global list) and the union-find of its blocks
         __syncthreads();
+        if (tid < s_nex) {
+            const int slot = atomicAdd(&ctl->n_ex, 1);
+            if (slot < PEAC_MAXP) {
+                const int r = s_ex[tid];
+                PeacExtract &x = ctl->ex[slot];
+                for (int d = 0; d < 9; ++d) x.st[d] = sst[r * 9 + d];
+                for (int d = 0; d < 3; ++d) x.normal[d] = nrm[3 * r + d];
+                x.mse = mse_a[r]; x.pop_key = s_exkey[tid]; x.N = N_a[r]; x.rid = r;
+            } else ctl->overflow = 1;
+        }
+        for (int b = tid; b < NB; b += nt)
+            if ((flags[b] & PF_VALID)) { ctl->parent[b] = root[b]; ctl->size[b] = ssize[root[b]]; }
     }
-    // extractedPlanes sorted by size, stable (PlaneSegSizeCmp, AHCPlaneFitter.hpp:1251-1254)
+    // ---- the last CTA to finish orders the planes: size descending, stable in the reference's extraction order
+    __threadfence();
+    __syncthreads();
+    __shared__ int s_last;
+    if (tid == 0) s_last = atomicAdd(&ctl->done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     if (tid == 0) {
-        const int n = s_nex;
+        const int n = min(*(volatile int *)&ctl->n_ex, PEAC_MAXP);
+        int idx[PEAC_MAXP];
+        for (int a = 0; a < n; ++a) idx[a] = a;
+        volatile PeacExtract *ex = ctl->ex;
+        auto before = [&](int a, int b) {   // a sorts before b
+            if (ex[a].N != ex[b].N) return ex[a].N > ex[b].N;
+            if (ex[a].pop_key != ex[b].pop_key) return ex[a].pop_key < ex[b].pop_key;
+            return ex[a].rid < ex[b].rid;
+        };
         for (int a = 1; a < n; ++a) {
-            const int v = s_ex[a];
+            const int v = idx[a];
             int b = a - 1;
-            while (b >= 0 && N_a[s_ex[b]] < N_a[v]) { s_ex[b + 1] = s_ex[b]; --b; }
-            s_ex[b + 1] = v;
+            while (b >= 0 && before(v, idx[b])) { idx[b + 1] = idx[b]; --b; }
+            idx[b + 1] = v;
         }
         ctl->n_planes = n;
         for (int k = 0; k < n; ++k) {
-            const int r = s_ex[k];
+            volatile PeacExtract &x = ex[idx[k]];
             PeacPlane &pl = ctl->pl[k];
-            const double sc = 1.0 / (double)N_a[r];
-            for (int d = 0; d < 3; ++d) { pl.center[d] = sst[r * 9 + d] * sc; pl.normal[d] = nrm[3 * r + d]; }
-            for (int d = 0; d < 9; ++d) pl.st[d] = sst[r * 9 + d];
-            pl.mse = mse_a[r]; pl.thr = 9.0 * mse_a[r] + 1e-5; pl.N = N_a[r]; pl.rid = r; pl.valid = 0; pl.final_id = -1;
+            const double sc = 1.0 / (double)x.N;
+            for (int d = 0; d < 3; ++d) { pl.center[d] = x.st[d] * sc; pl.normal[d] = x.normal[d]; }
+            for (int d = 0; d < 9; ++d) pl.st[d] = x.st[d];
+            pl.mse = x.mse; pl.thr = 9.0 * x.mse + 1e-5; pl.N = x.N; pl.rid = x.rid; pl.valid = 0; pl.final_id = -1;
             ctl->conn[k] = 0ull;
         }
     }
-    __syncthreads();
-    for (int b = tid; b < NB; b += nt) { ctl->parent[b] = root[b]; ctl->size[b] = ssize[b]; }
 }
 
 // ---------------------------------------------------------------- block erosion (findBlockMembership)
@@ -485,108 +611,217 @@ __global__ void k_peac_blockmap(PeacControl *ctl, int Nw, int Nh)
     if (plid >= 0) ctl->pl[plid].valid = 1;
 }
 
-__global__ void k_peac_init_labels(const PeacControl *__restrict__ ctl, int W, int H, int Nw, int *__restrict__ label, float *__restrict__ dist)
+__global__ void k_peac_init_labels(const PeacControl *__restrict__ ctl, int W, int H, int Nw, int Nh, int *__restrict__ label, float *__restrict__ dist,
+                                   int *__restrict__ head)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
-    label[y * W + x] = ctl->blk_map[(y / PEAC_WIN) * Nw + x / PEAC_WIN];
+    const int bx = x / PEAC_WIN, by = y / PEAC_WIN;
+    label[y * W + x] = (bx < Nw && by < Nh) ? ctl->blk_map[by * Nw + bx] : -1;
     dist[y * W + x] = 3.402823466e+38f;
+    head[y * W + x] = -1;
 }
 
-// ---------------------------------------------------------------- region growing (floodFill) as label relaxation
-#define PG_T 32
-#define PG_ITERS 24
-__global__ void __launch_bounds__(PG_T *PG_T / 4) k_peac_grow(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy,
-                                                              float inv_scale, int Nw, PeacControl *ctl, int *__restrict__ label, float *__restrict__ dist,
-                                                              int launch_idx)
+// ---------------------------------------------------------------- region growing (floodFill), order-faithful
+// The reference grows all planes with ONE serial FIFO queue (AHCPlaneFitter.hpp:546-594): pop (pixel s, plane), visit the
+// <= 4 neighbours of s in the order left / right / up / down, and per neighbour c update a small state machine
+// (membershipImg[c], distMap[c]) that may append (c, plane) to the queue.  The outcome at a pixel depends on the ORDER in
+// which the visits reach it (first come first served below 3 sigma, a closer plane may take a pixel over later, five
+// failed visits close it for good), so it is reproduced exactly, level by level:
+//   * a FIFO is processed in levels (the seeds are level 0, the entries appended while level n is processed form level
+//     n + 1), and an entry never reads the state of its OWN pixel -- only visits to a pixel c touch c's state;
+//   * phase A (parallel over the entries of the level): visit slot key = 4 * rank + direction; everything that does not
+//     depend on the order (interior-block test, point validity, point-plane distance) is evaluated, the slot is linked
+//     into the list of visits of pixel c;
+//   * phase B (parallel over pixels): the visit that was linked first owns the pixel; it replays the pixel's visits in
+//     ascending key order -- exactly the order of the serial queue -- through the reference's state machine and flags the
+//     visits that append to the queue;
+//   * phase C: the flagged visits, compacted in key order, are the next level -- the same sequence the serial queue holds.
+// ~200 levels per frame, one 1024-thread CTA (the levels are a dependent chain; a level is 1-10 k entries).
+#define PG_NT 1024
+__device__ __forceinline__ int pg_block_scan(int v, int *s_warp, int &total)
 {
-    if (launch_idx > 0 && ctl->grow_flag[launch_idx - 1] == 0) return;   // converged: the remaining launches fall through
-    // tile of PG_T x PG_T pixels + 1-px halo; every thread owns 4 pixels of the tile
-    __shared__ int s_l[PG_T + 2][PG_T + 2];
-    __shared__ int s_changed;
-    const int tx0 = blockIdx.x * PG_T, ty0 = blockIdx.y * PG_T;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
-    for (int t = tid; t < (PG_T + 2) * (PG_T + 2); t += nt) {
-        const int ly = t / (PG_T + 2), lx = t - ly * (PG_T + 2);
-        const int x = tx0 + lx - 1, y = ty0 + ly - 1;
-        s_l[ly][lx] = (x >= 0 && x < W && y >= 0 && y < H) ? label[y * W + x] : -1;
-    }
-    // per-thread pixels
-    int px[4], py[4], lab[4];
-    float dd[4];
-    bool grow[4];
-    double P[4][3];
+    // exclusive scan of v over the CTA (PG_NT threads); all threads must call
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int t = tid + k * nt;
-        const int ly = t / PG_T, lx = t - ly * PG_T;
-        px[k] = tx0 + lx; py[k] = ty0 + ly;
-        grow[k] = false;
-        lab[k] = -1; dd[k] = 3.402823466e+38f;
-        if (px[k] < W && py[k] < H) {
-            const int i = py[k] * W + px[k];
-            lab[k] = label[i];
-            dd[k] = dist[i];
-            // only pixels of "black" blocks grow (AHCPlaneFitter.hpp:567-568), and only where the depth is valid
-            grow[k] = ctl->blk_map[(py[k] / PEAC_WIN) * Nw + px[k] / PEAC_WIN] < 0 && peac_point(depth, W, px[k], py[k], fx, fy, cx, cy, inv_scale, P[k]);
-        }
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
     }
     __syncthreads();
-    bool any_change = false;
-    for (int it = 0; it < PG_ITERS; ++it) {
-        if (tid == 0) s_changed = 0;
-        __syncthreads();
-        int nl[4];
-        float nd[4];
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_warp[lane];
+        int winc = w;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            nl[k] = lab[k]; nd[k] = dd[k];
-            if (!grow[k]) continue;
-            const int lx = px[k] - tx0 + 1, ly = py[k] - ty0 + 1;
-            const int nb[4] = {s_l[ly][lx - 1], s_l[ly][lx + 1], s_l[ly - 1][lx], s_l[ly + 1][lx]};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int pl = nb[q];
-                if (pl < 0 || pl == nl[k]) continue;
-                bool seen = false;
-                for (int r = 0; r < q; ++r) seen |= nb[r] == pl;
-                if (seen) continue;
-                const PeacPlane &pp = ctl->pl[pl];
-                const float cd = (float)fabs(pp.normal[0] * (P[k][0] - pp.center[0]) + pp.normal[1] * (P[k][1] - pp.center[1]) +
-                                             pp.normal[2] * (P[k][2] - pp.center[2]));
-                if (!((double)cd * (double)cd < pp.thr)) continue;     // point-plane distance within 3 sigma
-                if (lab[k] >= 0 && lab[k] != pl) {                     // two planes meet: potential merge (:575-580)
-                    const PeacPlane &pa = ctl->pl[lab[k]];
-                    const double s = fabs(pa.normal[0] * pp.normal[0] + pa.normal[1] * pp.normal[1] + pa.normal[2] * pp.normal[2]);
-                    if (s >= PEAC_SIM_REFINE && !((ctl->conn[lab[k]] >> pl) & 1ull)) {
-                        atomicOr(&ctl->conn[lab[k]], 1ull << pl);
-                        atomicOr(&ctl->conn[pl], 1ull << lab[k]);
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, off);
+            if (lane >= off) winc += t;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return inc - v + s_warp[wid];
+}
+
+__global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy,
+                                                          float inv_scale, int Nw, int Nh, PeacControl *ctl, int *__restrict__ member,
+                                                          float *__restrict__ dist, int *__restrict__ head, int *qa, int *qb,
+                                                          int *__restrict__ v_pix, int *__restrict__ v_info, float *__restrict__ v_dist,
+                                                          int *__restrict__ v_next, unsigned char *__restrict__ v_push)
+{
+    __shared__ int s_blk[PEAC_MAXB];
+    __shared__ double s_pn[PEAC_MAXP][3], s_pc[PEAC_MAXP][3], s_thr[PEAC_MAXP];
+    __shared__ unsigned long long s_conn[PEAC_MAXP];
+    __shared__ int s_warp[33];
+    const int tid = threadIdx.x, NB = Nw * Nh;
+    const int np = ctl->n_planes;
+    for (int b = tid; b < NB; b += PG_NT) s_blk[b] = ctl->blk_map[b];
+    for (int k = tid; k < np; k += PG_NT) {
+        for (int d = 0; d < 3; ++d) { s_pn[k][d] = ctl->pl[k].normal[d]; s_pc[k][d] = ctl->pl[k].center[d]; }
+        s_thr[k] = ctl->pl[k].thr;
+        s_conn[k] = 0ull;
+    }
+    __syncthreads();
+    // ---- seeds in the order of findBlockMembership (AHCPlaneFitter.hpp:660-703): blocks in raster order, per block the run
+    // along its top edge, then the run along its left edge
+    int *cur = qa, *nxt = qb;
+    int n = 0;
+    {
+        int cnt[2] = {0, 0}, offs[2];
+        for (int r = 0; r < 2; ++r) {
+            const int b = tid * 2 + r;
+            if (b < NB) {
+                const int i = b / Nw, j = b - i * Nw, m = s_blk[b];
+                const bool top = i > 0 && (m < 0 ? s_blk[b - Nw] >= 0 : s_blk[b - Nw] != m);
+                const bool left = j > 0 && (m < 0 ? s_blk[b - 1] >= 0 : s_blk[b - 1] != m);
+                cnt[r] = (PEAC_WIN - 1) * ((top ? 1 : 0) + (left ? 1 : 0));
+            }
+        }
+        int total;
+        const int base = pg_block_scan(cnt[0] + cnt[1], s_warp, total);
+        offs[0] = base; offs[1] = base + cnt[0];
+        n = total;
+        if (n <= PG_CAP)
+            for (int r = 0; r < 2; ++r) {
+                const int b = tid * 2 + r;
+                if (b >= NB || !cnt[r]) continue;
+                const int i = b / Nw, j = b - i * Nw, m = s_blk[b];
+                int o = offs[r];
+                if (m < 0) {
+                    if (i > 0 && s_blk[b - Nw] >= 0) {
+                        const int sp = (i * PEAC_WIN - 1) * W + j * PEAC_WIN, pl = s_blk[b - Nw];
+                        for (int k = 1; k < PEAC_WIN; ++k) cur[o++] = (pl << 20) | (sp + k);
+                    }
+                    if (j > 0 && s_blk[b - 1] >= 0) {
+                        const int sp = (i * PEAC_WIN) * W + j * PEAC_WIN - 1, pl = s_blk[b - 1];
+                        for (int k = 0; k < PEAC_WIN - 1; ++k) cur[o++] = (pl << 20) | (sp + k * W);
+                    }
+                } else {
+                    if (i > 0 && s_blk[b - Nw] != m) {
+                        const int sp = (i * PEAC_WIN) * W + j * PEAC_WIN;
+                        for (int k = 0; k < PEAC_WIN - 1; ++k) cur[o++] = (m << 20) | (sp + k);
+                    }
+                    if (j > 0 && s_blk[b - 1] != m) {
+                        const int sp = (i * PEAC_WIN) * W + j * PEAC_WIN;
+                        for (int k = 1; k < PEAC_WIN; ++k) cur[o++] = (m << 20) | (sp + k * W);
                     }
                 }
-                if (cd < nd[k] || (cd == nd[k] && pl < nl[k])) { nd[k] = cd; nl[k] = pl; }
             }
-        }
-        __syncthreads();
-        bool ch = false;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (grow[k] && nl[k] != lab[k]) {
-                lab[k] = nl[k]; dd[k] = nd[k];
-                s_l[py[k] - ty0 + 1][px[k] - tx0 + 1] = lab[k];
-                ch = true;
-            }
-        if (ch) { s_changed = 1; any_change = true; }
-        __syncthreads();
-        if (!s_changed) break;
     }
+    __syncthreads();
+    int levels = 0, entries = 0;
+    while (n > 0) {
+        if (n > PG_CAP) { if (tid == 0) ctl->overflow = 1; break; }
+        ++levels; entries += n;
+        // ---- phase A
+        for (int e = tid; e < n; e += PG_NT) {
+            const int ent = cur[e];
+            const int s = ent & 0xfffff, plid = ent >> 20;
+            const int sy = s / W, sx = s - sy * W;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (grow[k] && px[k] < W && py[k] < H) {
-            const int i = py[k] * W + px[k];
-            label[i] = lab[k];
-            dist[i] = dd[k];
+            for (int q = 0; q < 4; ++q) {
+                const int key = e * 4 + q;
+                const bool ex = q == 0 ? sx > 0 : (q == 1 ? sx < W - 1 : (q == 2 ? sy > 0 : sy < H - 1));
+                int c = -1;
+                if (ex) {
+                    const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
+                    const int bx = ccx / PEAC_WIN, by = ccy / PEAC_WIN;
+                    if (!(bx < Nw && by < Nh && s_blk[by * Nw + bx] >= 0)) {     // only pixels of "black" blocks grow (:567-568)
+                        c = ccy * W + ccx;
+                        double P[3];
+                        bool ok = false;
+                        float cd = -1.0f;
+                        if (peac_point(depth, W, ccx, ccy, fx, fy, cx, cy, inv_scale, P)) {
+                            cd = (float)fabs(s_pn[plid][0] * (P[0] - s_pc[plid][0]) + s_pn[plid][1] * (P[1] - s_pc[plid][1]) + s_pn[plid][2] * (P[2] - s_pc[plid][2]));
+                            ok = (double)cd * (double)cd < s_thr[plid];       // point-plane distance within 3 sigma
+                        }
+                        v_info[key] = plid | (ok ? 256 : 0);
+                        v_dist[key] = cd;
+                        v_push[key] = 0;
+                        v_next[key] = atomicExch(&head[c], key);
+                    }
+                }
+                v_pix[key] = c;
+            }
         }
-    if (any_change) ctl->grow_flag[launch_idx] = 1;
+        __syncthreads();
+        // ---- phase B: one owner per visited pixel replays its visits in queue order
+        for (int key = tid; key < 4 * n; key += PG_NT) {
+            const int c = v_pix[key];
+            if (c < 0 || v_next[key] != -1) continue;      // the visit linked first (list tail) owns the pixel
+            int trail = member[c];
+            float d = dist[c];
+            const int h0 = head[c];
+            int last = -1;
+            for (;;) {
+                if (trail <= -6) break;                      // visited from 4 neighbours already (:563); nothing can change any more
+                int k = 0x7fffffff;                          // next visit in key order
+                for (int w = h0; w >= 0; w = v_next[w])
+                    if (w > last && w < k) k = w;
+                if (k == 0x7fffffff) break;
+                last = k;
+                const int info = v_info[k], plid = info & 255;
+                if (trail >= 0 && trail == plid) continue;   // visited by the same plane (:564)
+                if (info & 256) {
+                    if (trail >= 0) {                        // two planes meet: potential merge (:575-580)
+                        const double sm = fabs(s_pn[plid][0] * s_pn[trail][0] + s_pn[plid][1] * s_pn[trail][1] + s_pn[plid][2] * s_pn[trail][2]);
+                        if (sm >= PEAC_SIM_REFINE) { atomicOr(&s_conn[trail], 1ull << plid); atomicOr(&s_conn[plid], 1ull << trail); }
+                    }
+                    const float cd = v_dist[k];
+                    if (cd < d) { trail = plid; d = cd; v_push[k] = 1; }
+                    else if (trail < 0) trail -= 1;
+                } else if (trail < 0) trail -= 1;
+            }
+            member[c] = trail;
+            dist[c] = d;
+            head[c] = -1;
+        }
+        __syncthreads();
+        // ---- phase C: the appended entries, in key order, are the next level
+        {
+            const int total_keys = 4 * n;
+            const int L = (total_keys + PG_NT - 1) / PG_NT;
+            const int k0 = min(tid * L, total_keys), k1 = min(k0 + L, total_keys);
+            int cnt = 0;
+            for (int k = k0; k < k1; ++k) cnt += (v_pix[k] >= 0 && v_push[k]) ? 1 : 0;
+            int total;
+            int o = pg_block_scan(cnt, s_warp, total);
+            if (total <= PG_CAP)
+                for (int k = k0; k < k1; ++k)
+                    if (v_pix[k] >= 0 && v_push[k]) nxt[o++] = ((v_info[k] & 255) << 20) | v_pix[k];
+            n = total;
+        }
+        __syncthreads();
+        int *t = cur; cur = nxt; nxt = t;
+    }
+    __syncthreads();
+    for (int k = tid; k < np; k += PG_NT) ctl->conn[k] = s_conn[k];
+    if (tid == 0) { ctl->grow_levels = levels; ctl->grow_entries = entries; }
 }
 
 // ---------------------------------------------------------------- final re-merge (second ahCluster) + relabel map
@@ -705,7 +940,16 @@ int peac_init(sindyn_base *ctx, PeacStage *p, int W, int H)
     SD_CHECK(ctx->dalloc(&im->ctl, 1));
     SD_CHECK(ctx->dalloc(&im->label, (size_t)W * H));
     SD_CHECK(ctx->dalloc(&im->dist, (size_t)W * H));
+    SD_CHECK(ctx->dalloc(&im->head, (size_t)W * H));
+    SD_CHECK(ctx->dalloc(&im->qa, (size_t)PG_CAP));
+    SD_CHECK(ctx->dalloc(&im->qb, (size_t)PG_CAP));
+    SD_CHECK(ctx->dalloc(&im->v_pix, (size_t)4 * PG_CAP));
+    SD_CHECK(ctx->dalloc(&im->v_info, (size_t)4 * PG_CAP));
+    SD_CHECK(ctx->dalloc(&im->v_next, (size_t)4 * PG_CAP));
+    SD_CHECK(ctx->dalloc(&im->v_dist, (size_t)4 * PG_CAP));
+    SD_CHECK(ctx->dalloc(&im->v_push, (size_t)4 * PG_CAP));
     SD_CHECK(ctx->dalloc(&im->PB, (size_t)W * H));
+    if ((size_t)W * H >= (1u << 20)) { ctx->err = "peac: image too large for the packed queue entries"; return SINDYN_ERR_INVALID; }
     const size_t smem = PEAC_AHC_SMEM;
     CU_CHECK(ctx, cudaFuncSetAttribute(k_peac_ahc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p->built = true;
@@ -719,16 +963,14 @@ int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t 
     const int W = p->W, H = p->H, Nw = im->Nw, Nh = im->Nh, NB = Nw * Nh;
     const float inv_scale = 1.0f / depth_scale;
     const size_t smem = PEAC_AHC_SMEM;
-    CU_CHECK(ctx, cudaMemsetAsync(im->ctl, 0, (4 + 128) * sizeof(int), ctx->stream));
+    CU_CHECK(ctx, cudaMemsetAsync(im->ctl, 0, 16 * sizeof(int), ctx->stream));
     LAUNCH(ctx, k_peac_blocks, cdiv(NB, 64), 64, 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->nodes);
-    LAUNCH(ctx, k_peac_ahc, 1, PEAC_AHC_NT, smem, im->nodes, im->ctl, Nw, Nh);
+    LAUNCH(ctx, k_peac_ahc, PEAC_AHC_CTAS, PEAC_AHC_NT, smem, im->nodes, im->ctl, Nw, Nh);
     LAUNCH(ctx, k_peac_blockmap, cdiv(NB, 128), 128, 0, im->ctl, Nw, Nh);
     const dim3 blk(32, 8), grd(cdiv(W, 32), cdiv(H, 8));
-    LAUNCH(ctx, k_peac_init_labels, grd, blk, 0, im->ctl, W, H, Nw, im->label, im->dist);
-    // growth distance per launch >= PG_ITERS pixels along straight paths; black regions are bounded by the image size
-    const int n_launch = min(2 * cdiv(W > H ? W : H, PG_ITERS) + 4, 128);
-    for (int it = 0; it < n_launch; ++it)
-        LAUNCH(ctx, k_peac_grow, dim3(cdiv(W, PG_T), cdiv(H, PG_T)), dim3(32, 8), 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, im->ctl, im->label, im->dist, it);
+    LAUNCH(ctx, k_peac_init_labels, grd, blk, 0, im->ctl, W, H, Nw, Nh, im->label, im->dist, im->head);
+    LAUNCH(ctx, k_peac_grow_fifo, 1, PG_NT, 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->ctl, im->label, im->dist, im->head, im->qa, im->qb,
+           im->v_pix, im->v_info, im->v_dist, im->v_next, im->v_push);
     LAUNCH(ctx, k_peac_merge, 1, 32, 0, im->ctl);
     LAUNCH(ctx, k_peac_bits, cdiv(W * H, 256), 256, 0, im->label, W * H, im->ctl, im->PB);
     LAUNCH_CHECK(ctx);

@@ -1,7 +1,7 @@
 """GPU parity of the PEAC plane-contour edge stage (sindyn_plane_edges = DynaDetect.cc:558-593 + include/PEAC) against
-oracle/peac_oracle.py.  The block-level clustering (which blocks form which plane) must be identical; the pixel-level
-region growing is an order-independent relaxation on the device vs one serial FIFO queue in the reference,
-so membership / edge images are compared by agreement rate and IoU with stated floors."""
+oracle/peac_oracle.py / oracle/peac_cpu.c.  Everything is bit-exact: the block-level clustering (which blocks form which
+plane, in which order), the pixel-level region growing (the device replays the reference's single FIFO queue level by
+level, AHCPlaneFitter.hpp:546-594), the final re-merge, and the u8 plane-edge image."""
 import cv2
 import numpy as np
 import pytest
@@ -12,20 +12,17 @@ from sindslam_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-MEMBER_AGREE_MIN = 0.995     # fraction of pixels with the same final plane (up to a relabelling)
-EDGE_IOU_MIN = 0.90          # IoU of the thickness-2 contour images (1-px shifts of a 3-px line cost ~0.5 IoU locally)
-
 
 def _iou(a, b):
     u = (a | b).sum()
     return 1.0 if u == 0 else float((a & b).sum()) / float(u)
 
 
-@pytest.mark.parametrize("cam_name,kind", [("TUM3", "box"), ("D455_848", "humanoid")])
-def test_plane_edges_vs_oracle(cam_name, kind):
+@pytest.mark.parametrize("cam_name,kind,hole", [("TUM3", "box", 0.0003), ("D455_848", "humanoid", 0.0003), ("TUM3", "box", 0.002), ("D455_848", "humanoid", 0.0)])
+def test_plane_edges_vs_oracle(cam_name, kind, hole):
     from sindslam_b200.capi import SinDyn
     cam = getattr(synth, cam_name)
-    _, frames = synth.make_sequence(2, cam, seq=3, kind=kind, start=8, hole_rate=0.0003)
+    _, frames = synth.make_sequence(3, cam, seq=3, kind=kind, start=8, hole_rate=hole)
     sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=1)
     for f in frames:
         got = sd.plane_edges(f.depth)
@@ -35,21 +32,11 @@ def test_plane_edges_vs_oracle(cam_name, kind):
         # block-level AHC: same extracted planes (root block id, size), same order
         assert [(int(r), int(n)) for r, n, _ in dbg["planes"]] == ref_dbg["coarse"]
         assert dbg["n_final"] == ref_dbg["n"]
-        # membership up to relabelling: match every oracle plane with the GPU plane it overlaps most
         gm, rm = dbg["member"], ref_dbg["member"]
-        agree = (gm < 0) & (rm < 0)
-        for p in range(ref_dbg["n"]):
-            sel = rm == p
-            ids, cnt = np.unique(gm[sel], return_counts=True)
-            agree |= sel & (gm == ids[np.argmax(cnt)])
-        rate = float(agree.mean())
-        iou = _iou(got > 0, ref > 0)
-        # tolerance to 1-px shifts: fraction of oracle edge pixels within 1 px of a GPU edge pixel and vice versa
-        near = lambda a, b: float((a & cv2.dilate(b.astype(np.uint8), np.ones((3, 3), np.uint8)).astype(bool)).sum()) / max(1, int(a.sum()))
-        print("%s: planes %d -> %d, membership agreement %.5f, edge IoU %.4f, edge recall@1px %.4f precision@1px %.4f" % (
-            cam_name, len(ref_dbg["coarse"]), ref_dbg["n"], rate, iou, near(ref > 0, got > 0), near(got > 0, ref > 0)))
-        assert rate >= MEMBER_AGREE_MIN
-        assert iou >= EDGE_IOU_MIN
+        print("%s hole %.4f: planes %d -> %d, membership differing px %d, edge differing px %d, FIFO stats %s" % (
+            cam_name, hole, len(ref_dbg["coarse"]), ref_dbg["n"], int((gm != rm).sum()), int((got != ref).sum()), ref_dbg.get("stats")))
+        assert np.array_equal(gm, rm)          # final plane id of every pixel
+        assert np.array_equal(got, ref)        # imgEdgeByPlane
     sd.close()
 
 
@@ -69,7 +56,6 @@ def test_detect_with_plane_edges_mask_iou(seq_c1):
         iou = _iou(mask == 255, r["mask"] == 255)
         ious.append(iou)
         print("frame %d: mask IoU(255) %.4f, label agreement %.4f, labels %d/%d" % (k, iou, float((label == r["label"]).mean()), int(label.max()), int(r["label"].max())))
-        # keep the recurrence comparable: continue from the oracle's state on both sides
-        s.set_state(0, r["mask"]); s.set_state(1, fr["high"]); s.set_state(2, r["label"])
+        assert np.array_equal(mask, r["mask"]) and np.array_equal(label, r["label"]), k     # free-running state on both sides
     assert min(ious) >= 0.99
     s.close()

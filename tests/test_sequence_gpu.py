@@ -21,11 +21,11 @@ def _iou(a, b):
 
 def _stream(cam, frames, order, orb_every=3):
     from sindslam_b200.capi import Orb, SinDyn
-    s = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=0)
+    s = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=1)
     orb = Orb(1000, 1.2, 8, 20, 7, cam.width, cam.height)
     oorb = oo.OrbOracle(1000, 1.2, 8, 20, 7)
     s.set_prev_frames(frames[order[0]].bgr, frames[order[0]].bgr)     # the driver primes with frame 0 twice (rgbd_tum_noros.cc:103-107)
-    o = orc.DynaDetectOracle(frames[order[0]].bgr, frames[order[0]].bgr, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor)
+    o = orc.DynaDetectOracle(frames[order[0]].bgr, frames[order[0]].bgr, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=True)
     n_large, ious = 0, []
     for n, k in enumerate(order[1:], 1):
         f = frames[k]
@@ -61,7 +61,7 @@ def _stream(cam, frames, order, orb_every=3):
 
 def test_c1_stream_with_large_motion_jump():
     cam = synth.TUM3
-    _, frames = synth.make_sequence(24, cam, seq=1, kind="box", start=4)
+    _, frames = synth.make_sequence(24, cam, seq=1, kind="box", start=4, hole_rate=0.0005)    # sensor-like holes: the PEAC stage has planes to fit
     order = list(range(0, 8)) + [23] + list(range(9, 12))     # 7 -> 23 -> 9: 14-frame jumps, large-motion fallback expected
     n_large, ious = _stream(cam, frames, order)
     print("large-motion frames:", n_large, "IoU vs rendered truth:", np.round(ious, 3))
@@ -71,7 +71,7 @@ def test_c1_stream_with_large_motion_jump():
 
 def test_c2_848x480_humanoid_stream():
     cam = synth.D455_848
-    _, frames = synth.make_sequence(7, cam, seq=2, kind="humanoid", start=6)
+    _, frames = synth.make_sequence(7, cam, seq=2, kind="humanoid", start=6, hole_rate=0.0005)
     n_large, ious = _stream(cam, frames, list(range(7)))
     print("848x480 humanoid: IoU vs rendered truth:", np.round(ious, 3))
 
@@ -98,9 +98,9 @@ def test_long_stream_invariants():
         assert int(label.max()) < 128
         if check:
             fr = s.flow_results()
-            o = orc.DynaDetectOracle(st[3], st[4], cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=False)
+            o = orc.DynaDetectOracle(st[3], st[4], cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=True)
             o.dyna_last, o.high_last, o.label_last = st[0], st[1], st[2]
-            s2 = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=0)
+            s2 = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=1)
             s2.set_state(3, st[3]); s2.set_state(4, st[4]); s2.set_state(0, st[0]); s2.set_state(1, st[1]); s2.set_state(2, st[2])
             m2, l2 = s2.detect(frames[k].bgr, frames[k].depth, k)
             f2 = s2.flow_results()
