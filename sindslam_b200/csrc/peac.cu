@@ -21,6 +21,8 @@
 
 #include "recluster.cuh"
 
+#include <cooperative_groups.h>
+
 #define PEAC_WIN 16
 #define PEAC_MAXB 1600          // blocks (53 x 30 = 1590 at 848 x 480); bounded by the shared memory of k_peac_ahc
 #define PEAC_MAXP 64            // extracted planes
@@ -37,12 +39,15 @@ struct PeacNode {               // ahc::PlaneSeg (AHCPlaneSeg.hpp:29-188), index
 
 struct PeacPlane { double center[3], normal[3], mse, thr; int N, rid, valid, final_id; double st[9]; };
 
+#define PEAC_AHC_CTAS_MAX 64
 struct PeacExtract { double st[9], normal[3], mse, pop_key; int N, rid; };   // one extracted plane of one graph component, unsorted
 
 struct PeacControl {
     int n_planes, n_final, overflow, n_ex;      // header (16 ints), zeroed every frame
     int done, n_comp, grow_levels, grow_entries;
-    int hdr_pad[8];
+    int grow_n, grow_buf, hdr_pad[6];           // frontier handed from the cluster kernel to the single-CTA kernel
+    int grow_tot[16];                           // per-CTA counts of the cluster kernel's ordered compaction
+    long long clk[PEAC_AHC_CTAS_MAX][12];      // PEAC_CLOCKS builds only
     int parent[PEAC_MAXB], size[PEAC_MAXB];
     int blk_map[PEAC_MAXB];
     PeacExtract ex[PEAC_MAXP];
@@ -67,69 +72,90 @@ struct PeacImpl {
 };
 
 // ---------------------------------------------------------------- small dense eigen solver
-// Smallest eigenpair of a symmetric 3x3: trigonometric closed form for a first eigenvalue estimate, eigenvector from the
-// best-conditioned cross product of two rows of (K - l I), Rayleigh quotient l = v'Kv in double, three passes.  ~10x cheaper than cyclic Jacobi in FP64, which matters because the AHC loop below is a serial chain of
-// ~1000 such solves.  (reference: Eigen::SelfAdjointEigenSolver through LA::eig33sym, eig33sym.hpp:45-51 -- un-vendored;
-// the smallest eigenvalue agrees to ~1e-11 relative for plane-like covariance matrices)
-__device__ void eig33_min(const double K[3][3], double &lmin, double v[3])
+// Smallest eigenpair of a symmetric positive semi-definite 3x3 (reference: Eigen::SelfAdjointEigenSolver through
+// LA::eig33sym, eig33sym.hpp:45-51 -- un-vendored).  The clustering loop is a serial chain of ~1000 candidate evaluations
+// that need the smallest eigenVALUE only, so the two halves are separate:
+//   eig33_min_val: Newton's method on the characteristic cubic p(l) = det(K - l I) from l = 0.  For a PSD matrix p is
+//                  positive, decreasing and convex on (-inf, l_min], so the iteration rises monotonically to l_min and
+//                  converges quadratically (3-5 steps, ~10 FP64 operations each; the reciprocal of p' is a float
+//                  approximation with one FP64 Newton correction);
+//   eig33_vec:     the eigenvector from the best-conditioned cross product of two rows of K - l I (winner only).
+// The smallest eigenvalue agrees with numpy.linalg.eigh / cyclic Jacobi to ~1e-11 relative for plane-like covariances.
+struct Sym3 { double a00, a11, a22, a01, a02, a12; };
+
+__device__ __forceinline__ double peac_rcp(double x)
 {
-    const double a00 = K[0][0], a11 = K[1][1], a22 = K[2][2], a01 = K[0][1], a02 = K[0][2], a12 = K[1][2];
-    // initial guess of the smallest eigenvalue: trigonometric closed form in FLOAT (fast acosf / cosf); its absolute error
-    // (~1e-7 of the largest eigenvalue) only has to be small against the gap to the middle eigenvalue, the Rayleigh passes
-    // below square the error each time
-    double l;
+    const double r = (double)__frcp_rn((float)x);
+    return r * (2.0 - x * r);                  // relative error ~1e-14
+}
+
+__device__ __forceinline__ double eig33_min_val(const Sym3 &K)
+{
+    const double m0 = K.a11 * K.a22 - K.a12 * K.a12, m1 = K.a00 * K.a22 - K.a02 * K.a02, m2 = K.a00 * K.a11 - K.a01 * K.a01;
+    const double c2 = K.a00 + K.a11 + K.a22;
+    const double c1 = m0 + m1 + m2;
+    const double c0 = K.a00 * m0 - K.a01 * (K.a01 * K.a22 - K.a12 * K.a02) + K.a02 * (K.a01 * K.a12 - K.a11 * K.a02);
+    // three float iterations from 0 (cheap: the FP64 chain below costs ~20 cycles per dependent operation), then FP64 to convergence.
+    // A float iterate may land slightly right of the root; p < 0 and p' < 0 there, so the FP64 steps walk back onto it.
+    float lf = 0.0f;
     {
-        const float f00 = (float)a00, f11 = (float)a11, f22 = (float)a22, f01 = (float)a01, f02 = (float)a02, f12 = (float)a12;
-        const float p1 = f01 * f01 + f02 * f02 + f12 * f12;
-        const float q = (f00 + f11 + f22) * (1.0f / 3.0f);
-        const float b00 = f00 - q, b11 = f11 - q, b22 = f22 - q;
-        const float p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0f * p1;
-        if (p2 <= 0.0f) {
-            l = (double)q;
-        } else {
-            const float p = sqrtf(p2 * (1.0f / 6.0f)), ip = 1.0f / p;
-            const float c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip, c01 = f01 * ip, c02 = f02 * ip, c12 = f12 * ip;
-            float r = 0.5f * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
-            r = fminf(fmaxf(r, -1.0f), 1.0f);
-            l = (double)(q + 2.0f * p * cosf(acosf(r) * (1.0f / 3.0f) + 2.0943951f));
+        const float f2 = (float)c2, f1 = (float)c1, f0 = (float)c0;
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const float pf = ((f2 - lf) * lf - f1) * lf + f0;
+            const float df = (2.0f * f2 - 3.0f * lf) * lf - f1;
+            if (df < 0.0f) lf -= pf * __frcp_rn(df);
         }
+        if (!(lf >= 0.0f) || !(lf < f2)) lf = 0.0f;     // NaN / runaway guard: restart from the safe side
     }
-    for (int pass = 0; pass < 3; ++pass) {
-        const double r0[3] = {a00 - l, a01, a02}, r1[3] = {a01, a11 - l, a12}, r2[3] = {a02, a12, a22 - l};
-        double c0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
-        double c1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
-        double c2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
-        const double n0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2], n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2],
-                     n2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
-        const double *c = c0;
-        double nn = n0;
-        if (n1 > nn) { c = c1; nn = n1; }
-        if (n2 > nn) { c = c2; nn = n2; }
-        if (nn <= 0.0) { v[0] = 0; v[1] = 0; v[2] = 1; break; }
-        const double in = rsqrt(nn);
-        v[0] = c[0] * in; v[1] = c[1] * in; v[2] = c[2] * in;
-        // Rayleigh quotient: second-order accurate eigenvalue for the refined vector
-        const double w0 = a00 * v[0] + a01 * v[1] + a02 * v[2], w1 = a01 * v[0] + a11 * v[1] + a12 * v[2], w2 = a02 * v[0] + a12 * v[1] + a22 * v[2];
-        const double ln = v[0] * w0 + v[1] * w1 + v[2] * w2;
-        const bool converged = pass > 0 && fabs(ln - l) <= 1e-14 * fabs(ln);   // the third pass would not move it any more
-        l = ln;
-        if (converged) break;
+    double l = (double)lf;
+#pragma unroll 1
+    for (int it = 0; it < 12; ++it) {
+        const double p = ((c2 - l) * l - c1) * l + c0;
+        const double dp = (2.0 * c2 - 3.0 * l) * l - c1;
+        if (!(dp < 0.0)) break;                  // flat cubic (rank-deficient block): keep the current iterate
+        const double dl = p * peac_rcp(dp);
+        l -= dl;
+        if (fabs(dl) <= 4e-16 * fabs(l)) break;
     }
-    lmin = l;
+    return l;
+}
+
+__device__ __forceinline__ void eig33_vec(const Sym3 &K, double l, double v[3])
+{
+    const double r0[3] = {K.a00 - l, K.a01, K.a02}, r1[3] = {K.a01, K.a11 - l, K.a12}, r2[3] = {K.a02, K.a12, K.a22 - l};
+    const double c0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+    const double c1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+    const double c2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+    const double n0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2], n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2],
+                 n2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+    const double *c = c0;
+    double nn = n0;
+    if (n1 > nn) { c = c1; nn = n1; }
+    if (n2 > nn) { c = c2; nn = n2; }
+    if (nn <= 0.0) { v[0] = 0; v[1] = 0; v[2] = 1; return; }
+    const double in = rsqrt(nn);
+    v[0] = c[0] * in; v[1] = c[1] * in; v[2] = c[2] * in;
+}
+
+// scatter matrix of Stats::compute (AHCPlaneSeg.hpp:84-116)
+__device__ __forceinline__ void peac_cov(const double st[9], double sc, double center[3], Sym3 &K)
+{
+    center[0] = st[0] * sc; center[1] = st[1] * sc; center[2] = st[2] * sc;
+    K.a00 = st[3] - st[0] * st[0] * sc; K.a01 = st[6] - st[0] * st[1] * sc; K.a02 = st[8] - st[0] * st[2] * sc;
+    K.a11 = st[4] - st[1] * st[1] * sc; K.a12 = st[7] - st[1] * st[2] * sc;
+    K.a22 = st[5] - st[2] * st[2] * sc;
 }
 
 // Stats::compute (AHCPlaneSeg.hpp:84-116)
 __device__ void peac_compute(const double st[9], int N, double center[3], double normal[3], double &mse)
 {
     const double sc = 1.0 / (double)N;
-    center[0] = st[0] * sc; center[1] = st[1] * sc; center[2] = st[2] * sc;
-    double K[3][3];
-    K[0][0] = st[3] - st[0] * st[0] * sc; K[0][1] = st[6] - st[0] * st[1] * sc; K[0][2] = st[8] - st[0] * st[2] * sc;
-    K[1][1] = st[4] - st[1] * st[1] * sc; K[1][2] = st[7] - st[1] * st[2] * sc;
-    K[2][2] = st[5] - st[2] * st[2] * sc;
-    K[1][0] = K[0][1]; K[2][0] = K[0][2]; K[2][1] = K[1][2];
-    double l, v[3];
-    eig33_min(K, l, v);
+    Sym3 K;
+    peac_cov(st, sc, center, K);
+    const double l = eig33_min_val(K);
+    double v[3];
+    eig33_vec(K, l, v);
     const double d = v[0] * center[0] + v[1] * center[1] + v[2] * center[2];
     const double sgn = d <= 0 ? 1.0 : -1.0;     // normal points towards the camera
     normal[0] = sgn * v[0]; normal[1] = sgn * v[1]; normal[2] = sgn * v[2];
@@ -207,7 +233,8 @@ __device__ __forceinline__ unsigned long long peac_key(double m)
 // ---------------------------------------------------------------- AHC (Algorithm 2 edges + Algorithm 3 clustering)
 struct MergeResult { double st[9], c[3], n[3], mse; };
 
-#define PEAC_AHC_SMEM ((sizeof(double) * (3 + 1 + 9) + sizeof(int) * 2 + 1 + sizeof(unsigned short) * 2) * PEAC_MAXB + sizeof(unsigned short) * 2 * PEAC_MAXE)
+#define PEAC_AHC_SMEM ((sizeof(double) * (3 + 1 + 9) + sizeof(int) * 2 + 1 + sizeof(unsigned short) * 2) * PEAC_MAXB + sizeof(unsigned short) * 2 * PEAC_MAXE + \
+                       sizeof(double) * (PEAC_MAXB + 8))
 #define PF_ALIVE 1
 #define PF_VALID 2
 #define PF_QUEUED 4
@@ -224,6 +251,12 @@ struct MergeResult { double st[9], c[3], n[3], mse; };
 //   * the distinct neighbours of the popped node are collected first (stamp + compaction), then one candidate merge
 //     (merged sums + eigen solve) runs per thread; the winning thread hands its merged plane over through shared memory;
 //   * the bookkeeping of a merge is done by warp 0 (shuffle arg-min over the 8 warp results, lanes copy the sums).
+// developer instrumentation (SINDYN_NVCC_EXTRA=-DPEAC_CLOCKS): cycle counts of the clustering loop's phases, thread 0 of every CTA
+#ifdef PEAC_CLOCKS
+#define PCLK(i) do { if (tid == 0) { const long long t_ = clock64(); clk[i] += t_ - t_last; t_last = t_; } } while (0)
+#else
+#define PCLK(i) do { } while (0)
+#endif
 #define PEAC_AHC_NT 256   // threads of k_peac_ahc (a power of two: node b is owned by thread b & (PEAC_AHC_NT - 1))
 #define PEAC_AHC_CTAS 32  // CTAs of k_peac_ahc: one connected component of the block graph each (more components: round robin)
 
@@ -248,6 +281,7 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
     unsigned short *ssize = root + PEAC_MAXB;                            // PEAC_MAXB
     unsigned short *eu = ssize + PEAC_MAXB, *ev = eu + PEAC_MAXE;        // edges, column t = entries t, t + 256, ...
     unsigned char *flags = (unsigned char *)(ev + PEAC_MAXE);            // PEAC_MAXB
+    double *inv_n = (double *)(flags + PEAC_MAXB);                       // PEAC_MAXB + 1: 1.0 / (256 m), m = blocks of a node
     __shared__ int s_ne, s_seq, s_nex, s_lose, s_win, s_ncand, s_changed, s_nactive;
     __shared__ int stamp[PEAC_MAXB];          // component label while the graph is set up, candidate stamp during the clustering
     __shared__ unsigned short cand[PEAC_MAXCAND];
@@ -257,14 +291,17 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
     __shared__ double w_mse[8];
     __shared__ unsigned long long w_key[8];
     __shared__ int w_o[8], w_seq[8];
-    __shared__ MergeResult w_res[8];
     const int tid = threadIdx.x, nt = PEAC_AHC_NT, lane = tid & 31, wid = tid >> 5;
     const int NB = Nw * Nh;
+#ifdef PEAC_CLOCKS
+    long long clk[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = clock64();
+#endif
     auto sim = [&](int a, int b) { return fabs(nrm[3 * a] * nrm[3 * b] + nrm[3 * a + 1] * nrm[3 * b + 1] + nrm[3 * a + 2] * nrm[3 * b + 2]); };
     auto add_edge = [&](int a, int b) {
         int e = atomicAdd(&s_ne, 1);
         if (e < PEAC_MAXE) { eu[e] = (unsigned short)a; ev[e] = (unsigned short)b; }
     };
+    for (int m = tid; m <= PEAC_MAXB; m += nt) inv_n[m] = m ? 1.0 / (double)(m * PEAC_WIN * PEAC_WIN) : 0.0;
     for (int round = 0;; ++round) {
         __syncthreads();
         for (int b = tid; b < NB; b += nt) {
@@ -309,6 +346,7 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
         __syncthreads();
         const int NE = min(s_ne, PEAC_MAXE);
         if (tid == 0 && s_ne > PEAC_MAXE) ctl->overflow = 1;
+        PCLK(0);   // load + initial edges
         // ---- connected components of the initial graph: minimum-label propagation over the edges + pointer jumping
         int *comp = stamp;
         for (;;) {
@@ -349,6 +387,7 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
         }
         __syncthreads();
         const int n_active = s_nactive;
+        PCLK(1);   // components
         if (round == 0 && blockIdx.x == 0) {
             // blocks outside the clustered components stay singletons (their sets can never reach minSupport)
             for (int b = tid; b < NB; b += nt) {
@@ -388,6 +427,7 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
         bool my_dirty = true;
         int prev_p = -1;
         __syncthreads();
+        PCLK(2);   // component setup
         for (;;) {
             // ---- flatten the union-find after the previous merge, and arg-min (mse, seq) over the queued live nodes
             const int lose = s_lose, win = s_win;
@@ -433,6 +473,7 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                 p = wl >= 0 ? __shfl_sync(0xffffffffu, o8, wl) : -1;
             }
             prev_p = p;
+            PCLK(3);   // flatten + arg-min
             if (p < 0) break;
             ++pop_id;
             // ---- distinct live graph neighbours of p (AHCPlaneFitter.hpp:1092-1117).  The scan itself has independent iterations
@@ -456,27 +497,51 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                 const int e = i * nt + tid;
                 const int ru = root[eu[e]], rv = root[ev[e]];
                 const int o = ru == p ? rv : (rv == p ? ru : -1);
-                if (o >= 0 && o != p && (flags[o] & PF_ALIVE) && atomicExch(&stamp[o], pop_id) != pop_id) {
-                    const int slot = atomicAdd(&s_ncand, 1);
+                // two grown nodes share one edge per pair of adjacent blocks: dozens of threads would hit the same stamp.  Only one
+                // lane per distinct neighbour of the warp tries, and only if the stamp is not set yet.
+                bool fresh = o >= 0 && o != p && (flags[o] & PF_ALIVE) && stamp[o] != pop_id;
+                const unsigned act = __activemask();
+                const unsigned same = __match_any_sync(act, fresh ? o : -1 - lane);
+                fresh = fresh && lane == __ffs(same) - 1 && atomicExch(&stamp[o], pop_id) != pop_id;
+                const unsigned m = __ballot_sync(act, fresh);     // one shared-memory atomic per warp, not per candidate
+                if (fresh) {
+                    const int leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&s_ncand, __popc(m));
+                    base = __shfl_sync(m, base, leader);
+                    const int slot = base + __popc(m & ((1u << lane) - 1));
                     if (slot < PEAC_MAXCAND) cand[slot] = (unsigned short)o;
                 }
             }
             __syncthreads();
             const int ncand = min(s_ncand, PEAC_MAXCAND);
+            PCLK(4);   // edge scan
+#ifdef PEAC_CLOCKS
+            if (tid == 0) { clk[8] += 1; clk[9] += ncand; clk[10] += my_cnt; }
+#endif
+            // candidate merges: every thread evaluates its candidates completely (smallest eigenvalue, and for its best one
+            // the plane normal), so that the winner can commit without another dependent FP64 chain
             double best = 1e300;
             int best_o = -1;
-            MergeResult res;
+            double bst[9], bc2 = 0.0, bn[3] = {0.0, 0.0, 1.0};
             for (int ci2 = tid; ci2 < ncand; ci2 += nt) {
                 const int o = cand[ci2];
                 if (sim(p, o) < PEAC_SIM_MERGE) continue;
-                double st[9], c[3], n[3], mse;
+                double st[9], c[3];
                 for (int k = 0; k < 9; ++k) st[k] = sst[p * 9 + k] + sst[o * 9 + k];
-                peac_compute(st, N_a[p] + N_a[o], c, n, mse);
+                const double sc = inv_n[(N_a[p] + N_a[o]) >> 8];      // 1.0 / N, correctly rounded (table built with IEEE divisions)
+                Sym3 K;
+                peac_cov(st, sc, c, K);
+                const double l = eig33_min_val(K);
+                const double mse = l * sc;
                 if (mse < best || (mse == best && o < best_o)) {
-                    best = mse; best_o = o;
-                    for (int k = 0; k < 9; ++k) res.st[k] = st[k];
-                    for (int k = 0; k < 3; ++k) { res.c[k] = c[k]; res.n[k] = n[k]; }
-                    res.mse = mse;
+                    best = mse; best_o = o; bc2 = c[2];
+                    for (int k = 0; k < 9; ++k) bst[k] = st[k];
+                    double v[3];
+                    eig33_vec(K, l, v);
+                    const double d = v[0] * c[0] + v[1] * c[1] + v[2] * c[2];
+                    const double sgn = d <= 0 ? 1.0 : -1.0;     // normal points towards the camera
+                    bn[0] = sgn * v[0]; bn[1] = sgn * v[1]; bn[2] = sgn * v[2];
                 }
             }
             double wb = best;
@@ -486,55 +551,50 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                 const int oo = __shfl_xor_sync(0xffffffffu, wo, off);
                 if (oo >= 0 && (wo < 0 || om < wb || (om == wb && oo < wo))) { wb = om; wo = oo; }
             }
-            const unsigned winners = __ballot_sync(0xffffffffu, best_o >= 0 && best_o == wo && best == wb);
-            if (wo >= 0 && lane == __ffs(winners) - 1) w_res[wid] = res;
             if (lane == 0) { w_mse[wid] = wb; w_o[wid] = wo; }   // (the arg-min scratch was last read before the previous barrier)
             __syncthreads();
-            // ---- merge or extract: warp 0
-            if (wid == 0) {
-                double km = lane < 8 ? w_mse[lane] : 1e300;
-                int ko = lane < 8 ? w_o[lane] : -1, kw = lane;
-                for (int off = 4; off > 0; off >>= 1) {
-                    const double om = __shfl_xor_sync(0xffffffffu, km, off);
-                    const int oo = __shfl_xor_sync(0xffffffffu, ko, off), ow = __shfl_xor_sync(0xffffffffu, kw, off);
-                    if (oo >= 0 && (ko < 0 || om < km || (om == km && oo < ko))) { km = om; ko = oo; kw = ow; }
+            PCLK(5);   // candidate evaluation + warp reduction
+            // ---- merge or extract.  Every thread finds the winning candidate among the 8 warp results; the thread that
+            // evaluated it applies the merge; without a candidate thread 0 extracts.
+            {
+                double km = 1e300;
+                int ko = -1;
+#pragma unroll
+                for (int w = 0; w < PEAC_AHC_NT / 32; ++w) {
+                    const double om = w_mse[w];
+                    const int oo = w_o[w];
+                    if (oo >= 0 && (ko < 0 || om < km || (om == km && oo < ko))) { km = om; ko = oo; }
                 }
-                ko = __shfl_sync(0xffffffffu, ko, 0); kw = __shfl_sync(0xffffffffu, kw, 0);
-                bool merged = false;
-                if (ko >= 0) {
-                    const MergeResult &m = w_res[kw];
-                    if (m.mse < peac_t_mse(false, m.c[2])) {
-                        merged = true;
+                if (ko >= 0 && best_o == ko && best == km) {   // exactly one thread: candidates are distinct nodes
+                    const int o = ko;
+                    if (best < peac_t_mse(false, bc2)) {
                         // PlaneSeg(pa, pb): rid of the larger parent; DisjointSet::Union by size keeps the same root
-                        const int o = ko;
                         const int wn = N_a[p] >= N_a[o] ? p : o, ls = wn == p ? o : p;
                         const int Nsum = N_a[p] + N_a[o];
-                        __syncwarp();
-                        if (lane < 9) sst[wn * 9 + lane] = m.st[lane];
-                        else if (lane < 12) nrm[3 * wn + lane - 9] = m.n[lane - 9];
-                        else if (lane == 12) {
-                            mse_a[wn] = m.mse; N_a[wn] = Nsum;
-                            seq_a[wn] = s_seq++;            // the merged node is a NEW queue entry
-                            ssize[wn] += ssize[ls];
-                            flags[wn] |= PF_ALIVE | PF_QUEUED;
-                            flags[ls] &= ~(PF_ALIVE | PF_QUEUED);
-                            s_lose = ls; s_win = wn;
-                        }
-                    }
+                        for (int k = 0; k < 9; ++k) sst[wn * 9 + k] = bst[k];
+                        nrm[3 * wn] = bn[0]; nrm[3 * wn + 1] = bn[1]; nrm[3 * wn + 2] = bn[2];
+                        mse_a[wn] = best; N_a[wn] = Nsum;
+                        seq_a[wn] = s_seq++;            // the merged node is a NEW queue entry
+                        ssize[wn] += ssize[ls];
+                        flags[wn] |= PF_ALIVE | PF_QUEUED;
+                        flags[ls] &= ~(PF_ALIVE | PF_QUEUED);
+                        s_lose = ls; s_win = wn;
+                    } else ko = -2;   // candidate fails the MSE threshold: extract p (this thread)
                 }
-                if (!merged && lane == 0) {   // extract p (or drop it) and cut it out of the graph
+                if ((ko == -1 && tid == 0) || ko == -2) {   // extract p (or drop it) and cut it out of the graph
                     if (N_a[p] >= PEAC_MIN_SUPPORT) {
                         if (s_nex < PEAC_MAXP) { s_ex[s_nex] = p; s_exkey[s_nex] = mse_a[p]; ++s_nex; } else ctl->overflow = 1;
                     }
                     flags[p] &= ~(PF_ALIVE | PF_QUEUED);
                     s_lose = -1;
                 }
-                if (lane == 0) {
+                if (tid == 0) {
                     if (s_ncand > PEAC_MAXCAND) ctl->overflow = 1;
-                    s_ncand = 0;
                 }
             }
             __syncthreads();
+            if (tid == 0) s_ncand = 0;    // (read again only after the next arg-min barrier)
+            PCLK(6);   // merge / extract
         }
         // ---- results of this component: extracted planes (unsorted, global list) and the union-find of its blocks
         __syncthreads();
@@ -550,6 +610,11 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
         }
         for (int b = tid; b < NB; b += nt)
             if ((flags[b] & PF_VALID)) { ctl->parent[b] = root[b]; ctl->size[b] = ssize[root[b]]; }
+        PCLK(7);   // outputs
+#ifdef PEAC_CLOCKS
+        if (tid == 0) for (int k = 0; k < 12; ++k) ctl->clk[blockIdx.x][k] = clk[k];
+#endif
+        if ((int)blockIdx.x + (round + 1) * (int)gridDim.x >= n_active) break;   // nothing left for this CTA: skip the rebuild
     }
     // ---- the last CTA to finish orders the planes: size descending, stable in the reference's extraction order
     __threadfence();
@@ -668,27 +733,33 @@ __device__ __forceinline__ int pg_block_scan(int v, int *s_warp, int &total)
     return inc - v + s_warp[wid];
 }
 
-__global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy,
-                                                          float inv_scale, int Nw, int Nh, PeacControl *ctl, int *__restrict__ member,
-                                                          float *__restrict__ dist, int *__restrict__ head, int *qa, int *qb,
-                                                          int *__restrict__ v_pix, int *__restrict__ v_info, float *__restrict__ v_dist,
-                                                          int *__restrict__ v_next, unsigned char *__restrict__ v_push)
+// The first levels after the seeds are large (every boundary of every plane advances one pixel per level through the
+// eroded border blocks: ~8 k entries, 30 k visits per level) and throughput bound on one SM, so they run on a cluster of
+// PG_CL CTAs (phases separated by cluster barriers, everything in global memory, loads of data written by other CTAs
+// bypass L1); as soon as a level fits the shared-memory path the frontier is handed to the single-CTA kernel below.
+#define PG_CL 8
+#define PG_SCAP 2048
+__global__ void __cluster_dims__(PG_CL, 1, 1) __launch_bounds__(PG_NT)
+k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy, float inv_scale, int Nw, int Nh,
+                    PeacControl *ctl, int *member, float *dist, int *head, int *qa, int *qb, int *g_pix, int *g_info, float *g_dist, int *g_next,
+                    unsigned char *g_push)
 {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ int s_blk[PEAC_MAXB];
     __shared__ double s_pn[PEAC_MAXP][3], s_pc[PEAC_MAXP][3], s_thr[PEAC_MAXP];
-    __shared__ unsigned long long s_conn[PEAC_MAXP];
     __shared__ int s_warp[33];
-    const int tid = threadIdx.x, NB = Nw * Nh;
+    const int tid = threadIdx.x, NB = Nw * Nh, rank = (int)cluster.block_rank();
+    const int g = rank * PG_NT + tid, G = PG_CL * PG_NT;
     const int np = ctl->n_planes;
     for (int b = tid; b < NB; b += PG_NT) s_blk[b] = ctl->blk_map[b];
     for (int k = tid; k < np; k += PG_NT) {
         for (int d = 0; d < 3; ++d) { s_pn[k][d] = ctl->pl[k].normal[d]; s_pc[k][d] = ctl->pl[k].center[d]; }
         s_thr[k] = ctl->pl[k].thr;
-        s_conn[k] = 0ull;
     }
     __syncthreads();
     // ---- seeds in the order of findBlockMembership (AHCPlaneFitter.hpp:660-703): blocks in raster order, per block the run
-    // along its top edge, then the run along its left edge
+    // along its top edge, then the run along its left edge (CTA 0; every CTA computes the count)
     int *cur = qa, *nxt = qb;
     int n = 0;
     {
@@ -706,7 +777,7 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
         const int base = pg_block_scan(cnt[0] + cnt[1], s_warp, total);
         offs[0] = base; offs[1] = base + cnt[0];
         n = total;
-        if (n <= PG_CAP)
+        if (rank == 0 && n <= PG_CAP)
             for (int r = 0; r < 2; ++r) {
                 const int b = tid * 2 + r;
                 if (b >= NB || !cnt[r]) continue;
@@ -733,40 +804,203 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
                 }
             }
     }
+    cluster.sync();
+    int levels = 0, entries = 0, buf = 0;
+    while (n > PG_SCAP && n <= PG_CAP) {
+        ++levels; entries += n;
+        // ---- phase A
+        for (int e = g; e < n; e += G) {
+            const int ent = __ldcg(&cur[e]);
+            const int s = ent & 0xfffff, plid = ent >> 20;
+            const int sy = s / W, sx = s - sy * W;
+            int cc[4], link[4];
+            unsigned dv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool ex = q == 0 ? sx > 0 : (q == 1 ? sx < W - 1 : (q == 2 ? sy > 0 : sy < H - 1));
+                cc[q] = -1; link[q] = -1; dv[q] = 0;
+                if (ex) {
+                    const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
+                    const int bx = ccx / PEAC_WIN, by = ccy / PEAC_WIN;
+                    if (!(bx < Nw && by < Nh && s_blk[by * Nw + bx] >= 0)) {
+                        cc[q] = ccy * W + ccx;
+                        link[q] = atomicExch(&head[cc[q]], e * 4 + q);
+                        dv[q] = depth[cc[q]];
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int key = e * 4 + q, c = cc[q];
+                g_pix[key] = c;
+                if (c < 0) continue;
+                const int ccy = c / W, ccx = c - ccy * W;
+                bool ok = false;
+                float cd = -1.0f;
+                const float df = (float)dv[q];
+                if (!(df < 1e-3f)) {
+                    const float z = df * inv_scale;
+                    const double P0 = ((float)ccx - cx) * z / fx, P1 = ((float)ccy - cy) * z / fy, P2 = z;
+                    cd = (float)fabs(s_pn[plid][0] * (P0 - s_pc[plid][0]) + s_pn[plid][1] * (P1 - s_pc[plid][1]) + s_pn[plid][2] * (P2 - s_pc[plid][2]));
+                    ok = (double)cd * (double)cd < s_thr[plid];
+                }
+                g_info[key] = plid | (ok ? 256 : 0);
+                g_dist[key] = cd;
+                g_push[key] = 0;
+                g_next[key] = link[q];
+            }
+        }
+        cluster.sync();
+        // ---- phase B
+        for (int key = g; key < 4 * n; key += G) {
+            const int c = __ldcg(&g_pix[key]);
+            if (c < 0 || __ldcg(&g_next[key]) != -1) continue;
+            int trail = __ldcg(&member[c]);
+            float d = __ldcg(&dist[c]);
+            const int h0 = __ldcg(&head[c]);
+            head[c] = -1;
+            int last = -1;
+            for (;;) {
+                if (trail <= -6) break;
+                int k = 0x7fffffff;
+                for (int w = h0; w >= 0; w = __ldcg(&g_next[w]))
+                    if (w > last && w < k) k = w;
+                if (k == 0x7fffffff) break;
+                last = k;
+                const int info = __ldcg(&g_info[k]), plid = info & 255;
+                if (trail >= 0 && trail == plid) continue;
+                if (info & 256) {
+                    if (trail >= 0) {
+                        const double sm = fabs(s_pn[plid][0] * s_pn[trail][0] + s_pn[plid][1] * s_pn[trail][1] + s_pn[plid][2] * s_pn[trail][2]);
+                        if (sm >= PEAC_SIM_REFINE) { atomicOr(&ctl->conn[trail], 1ull << plid); atomicOr(&ctl->conn[plid], 1ull << trail); }
+                    }
+                    const float cd = __ldcg(&g_dist[k]);
+                    if (cd < d) { trail = plid; d = cd; g_push[k] = 1; }
+                    else if (trail < 0) trail -= 1;
+                } else if (trail < 0) trail -= 1;
+            }
+            member[c] = trail;
+            dist[c] = d;
+        }
+        cluster.sync();
+        // ---- phase C: ordered compaction over the whole cluster
+        {
+            const int total_keys = 4 * n;
+            const int L = (total_keys + G - 1) / G;
+            const int k0 = min(g * L, total_keys), k1 = min(k0 + L, total_keys);
+            int cnt = 0;
+            for (int k = k0; k < k1; ++k) cnt += (__ldcg(&g_pix[k]) >= 0 && __ldcg(&g_push[k])) ? 1 : 0;
+            int total;
+            int o = pg_block_scan(cnt, s_warp, total);
+            if (tid == 0) ctl->grow_tot[rank] = total;
+            cluster.sync();
+            int base = 0, all = 0;
+            for (int r = 0; r < PG_CL; ++r) {
+                const int t = __ldcg(&ctl->grow_tot[r]);
+                if (r < rank) base += t;
+                all += t;
+            }
+            o += base;
+            if (all <= PG_CAP)
+                for (int k = k0; k < k1; ++k)
+                    if (__ldcg(&g_pix[k]) >= 0 && __ldcg(&g_push[k])) nxt[o++] = ((__ldcg(&g_info[k]) & 255) << 20) | __ldcg(&g_pix[k]);
+            n = all;
+        }
+        cluster.sync();
+        int *t = cur; cur = nxt; nxt = t;
+        buf ^= 1;
+    }
+    if (g == 0) {
+        ctl->grow_n = n; ctl->grow_buf = buf; ctl->grow_levels = levels; ctl->grow_entries = entries;
+        if (n > PG_CAP) ctl->overflow = 1;
+    }
+}
+
+// Levels of at most PG_SCAP entries keep the queue and the visit records in shared memory (the common case: a frame has a
+// few levels of 5-10 k entries right after the seeds and then ~200 levels of a few hundred); larger levels use the global
+// buffers.  Only the per-pixel state (membership, distance, list head) lives in global memory: one L2 round trip in phase
+// A (list link + depth, issued together) and one in phase B.
+#define PG_SMEM ((size_t)(2 * PG_SCAP + 4 * PG_SCAP * 4) * 4 + 4 * PG_SCAP)
+__global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy,
+                                                          float inv_scale, int Nw, int Nh, PeacControl *ctl, int *__restrict__ member,
+                                                          float *__restrict__ dist, int *__restrict__ head, int *qa, int *qb,
+                                                          int *g_pix, int *g_info, float *g_dist, int *g_next, unsigned char *g_push)
+{
+    extern __shared__ int pg_dyn[];
+    int *s_q0 = pg_dyn, *s_q1 = s_q0 + PG_SCAP;
+    int *s_pix = s_q1 + PG_SCAP, *s_info = s_pix + 4 * PG_SCAP, *s_next = s_info + 4 * PG_SCAP;
+    float *s_dist = (float *)(s_next + 4 * PG_SCAP);
+    unsigned char *s_push = (unsigned char *)(s_dist + 4 * PG_SCAP);
+    __shared__ int s_blk[PEAC_MAXB];
+    __shared__ double s_pn[PEAC_MAXP][3], s_pc[PEAC_MAXP][3], s_thr[PEAC_MAXP];
+    __shared__ unsigned long long s_conn[PEAC_MAXP];
+    __shared__ int s_warp[33];
+    const int tid = threadIdx.x, NB = Nw * Nh;
+    const int np = ctl->n_planes;
+    for (int b = tid; b < NB; b += PG_NT) s_blk[b] = ctl->blk_map[b];
+    for (int k = tid; k < np; k += PG_NT) {
+        for (int d = 0; d < 3; ++d) { s_pn[k][d] = ctl->pl[k].normal[d]; s_pc[k][d] = ctl->pl[k].center[d]; }
+        s_thr[k] = ctl->pl[k].thr;
+        s_conn[k] = 0ull;
+    }
     __syncthreads();
-    int levels = 0, entries = 0;
+    // ---- the frontier left by k_peac_grow_cluster (seeds + the large levels)
+    int n = ctl->grow_n;
+    int *cur = ctl->grow_buf ? qb : qa, *nxt_g = ctl->grow_buf ? qa : qb;
+    bool nxt_s_is_q1 = true;      // which shared queue buffer is free for the next level
+    if (n > 0 && n <= PG_SCAP) {
+        for (int e = tid; e < n; e += PG_NT) s_q0[e] = cur[e];
+        cur = s_q0;
+    }
+    __syncthreads();
+    int levels = ctl->grow_levels, entries = ctl->grow_entries;
     while (n > 0) {
         if (n > PG_CAP) { if (tid == 0) ctl->overflow = 1; break; }
         ++levels; entries += n;
+        const bool small = n <= PG_SCAP;
+        int *v_pix = small ? s_pix : g_pix, *v_info = small ? s_info : g_info, *v_next = small ? s_next : g_next;
+        float *v_dist = small ? s_dist : g_dist;
+        unsigned char *v_push = small ? s_push : g_push;
         // ---- phase A
         for (int e = tid; e < n; e += PG_NT) {
             const int ent = cur[e];
             const int s = ent & 0xfffff, plid = ent >> 20;
             const int sy = s / W, sx = s - sy * W;
+            int cc[4], link[4];
+            unsigned dv[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int key = e * 4 + q;
                 const bool ex = q == 0 ? sx > 0 : (q == 1 ? sx < W - 1 : (q == 2 ? sy > 0 : sy < H - 1));
-                int c = -1;
+                cc[q] = -1; link[q] = -1; dv[q] = 0;
                 if (ex) {
                     const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
                     const int bx = ccx / PEAC_WIN, by = ccy / PEAC_WIN;
                     if (!(bx < Nw && by < Nh && s_blk[by * Nw + bx] >= 0)) {     // only pixels of "black" blocks grow (:567-568)
-                        c = ccy * W + ccx;
-                        double P[3];
-                        bool ok = false;
-                        float cd = -1.0f;
-                        if (peac_point(depth, W, ccx, ccy, fx, fy, cx, cy, inv_scale, P)) {
-                            cd = (float)fabs(s_pn[plid][0] * (P[0] - s_pc[plid][0]) + s_pn[plid][1] * (P[1] - s_pc[plid][1]) + s_pn[plid][2] * (P[2] - s_pc[plid][2]));
-                            ok = (double)cd * (double)cd < s_thr[plid];       // point-plane distance within 3 sigma
-                        }
-                        v_info[key] = plid | (ok ? 256 : 0);
-                        v_dist[key] = cd;
-                        v_push[key] = 0;
-                        v_next[key] = atomicExch(&head[c], key);
+                        cc[q] = ccy * W + ccx;
+                        link[q] = atomicExch(&head[cc[q]], e * 4 + q);            // link the visit; the depth load below is in flight with it
+                        dv[q] = depth[cc[q]];
                     }
                 }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int key = e * 4 + q, c = cc[q];
                 v_pix[key] = c;
+                if (c < 0) continue;
+                const int ccy = c / W, ccx = c - ccy * W;
+                bool ok = false;
+                float cd = -1.0f;
+                const float df = (float)dv[q];
+                if (!(df < 1e-3f)) {                                              // organised cloud point (DynaDetect.cc:562-587)
+                    const float z = df * inv_scale;
+                    const double P0 = ((float)ccx - cx) * z / fx, P1 = ((float)ccy - cy) * z / fy, P2 = z;
+                    cd = (float)fabs(s_pn[plid][0] * (P0 - s_pc[plid][0]) + s_pn[plid][1] * (P1 - s_pc[plid][1]) + s_pn[plid][2] * (P2 - s_pc[plid][2]));
+                    ok = (double)cd * (double)cd < s_thr[plid];                   // point-plane distance within 3 sigma
+                }
+                v_info[key] = plid | (ok ? 256 : 0);
+                v_dist[key] = cd;
+                v_push[key] = 0;
+                v_next[key] = link[q];
             }
         }
         __syncthreads();
@@ -777,6 +1011,7 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
             int trail = member[c];
             float d = dist[c];
             const int h0 = head[c];
+            head[c] = -1;
             int last = -1;
             for (;;) {
                 if (trail <= -6) break;                      // visited from 4 neighbours already (:563); nothing can change any more
@@ -799,10 +1034,10 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
             }
             member[c] = trail;
             dist[c] = d;
-            head[c] = -1;
         }
         __syncthreads();
         // ---- phase C: the appended entries, in key order, are the next level
+        int *nxt;
         {
             const int total_keys = 4 * n;
             const int L = (total_keys + PG_NT - 1) / PG_NT;
@@ -811,16 +1046,19 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
             for (int k = k0; k < k1; ++k) cnt += (v_pix[k] >= 0 && v_push[k]) ? 1 : 0;
             int total;
             int o = pg_block_scan(cnt, s_warp, total);
+            nxt = total <= PG_SCAP ? (nxt_s_is_q1 ? s_q1 : s_q0) : nxt_g;
             if (total <= PG_CAP)
                 for (int k = k0; k < k1; ++k)
                     if (v_pix[k] >= 0 && v_push[k]) nxt[o++] = ((v_info[k] & 255) << 20) | v_pix[k];
             n = total;
+            if (total <= PG_SCAP) nxt_s_is_q1 = !nxt_s_is_q1;
+            else nxt_g = nxt_g == qa ? qb : qa;
         }
         __syncthreads();
-        int *t = cur; cur = nxt; nxt = t;
+        cur = nxt;
     }
     __syncthreads();
-    for (int k = tid; k < np; k += PG_NT) ctl->conn[k] = s_conn[k];
+    for (int k = tid; k < np; k += PG_NT) ctl->conn[k] |= s_conn[k];
     if (tid == 0) { ctl->grow_levels = levels; ctl->grow_entries = entries; }
 }
 
@@ -952,6 +1190,7 @@ int peac_init(sindyn_base *ctx, PeacStage *p, int W, int H)
     if ((size_t)W * H >= (1u << 20)) { ctx->err = "peac: image too large for the packed queue entries"; return SINDYN_ERR_INVALID; }
     const size_t smem = PEAC_AHC_SMEM;
     CU_CHECK(ctx, cudaFuncSetAttribute(k_peac_ahc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_peac_grow_fifo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PG_SMEM));
     p->built = true;
     return SINDYN_OK;
 }
@@ -969,7 +1208,9 @@ int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t 
     LAUNCH(ctx, k_peac_blockmap, cdiv(NB, 128), 128, 0, im->ctl, Nw, Nh);
     const dim3 blk(32, 8), grd(cdiv(W, 32), cdiv(H, 8));
     LAUNCH(ctx, k_peac_init_labels, grd, blk, 0, im->ctl, W, H, Nw, Nh, im->label, im->dist, im->head);
-    LAUNCH(ctx, k_peac_grow_fifo, 1, PG_NT, 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->ctl, im->label, im->dist, im->head, im->qa, im->qb,
+    LAUNCH(ctx, k_peac_grow_cluster, PG_CL, PG_NT, 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->ctl, im->label, im->dist, im->head, im->qa, im->qb,
+           im->v_pix, im->v_info, im->v_dist, im->v_next, im->v_push);
+    LAUNCH(ctx, k_peac_grow_fifo, 1, PG_NT, PG_SMEM, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->ctl, im->label, im->dist, im->head, im->qa, im->qb,
            im->v_pix, im->v_info, im->v_dist, im->v_next, im->v_push);
     LAUNCH(ctx, k_peac_merge, 1, 32, 0, im->ctl);
     LAUNCH(ctx, k_peac_bits, cdiv(W * H, 256), 256, 0, im->label, W * H, im->ctl, im->PB);
@@ -984,6 +1225,15 @@ int peac_get_debug(sindyn_base *ctx, PeacStage *p, int *label_out, int *planes_r
     CU_CHECK(ctx, cudaMemcpyAsync(&host, im->ctl, sizeof host, cudaMemcpyDeviceToHost, ctx->stream));
     if (label_out) CU_CHECK(ctx, cudaMemcpyAsync(label_out, im->label, sizeof(int) * p->W * p->H, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+#ifdef PEAC_CLOCKS
+    for (int c = 0; c < PEAC_AHC_CTAS; ++c)
+        if (host.clk[c][8]) {
+            fprintf(stderr, "peac ahc cta %2d: pops %lld cand/pop %.1f edges/thread %.1f | kcycles: load %lld comps %lld setup %lld argmin %lld scan %lld cand %lld merge %lld out %lld\n", c,
+                    host.clk[c][8], (double)host.clk[c][9] / host.clk[c][8], (double)host.clk[c][10] / host.clk[c][8], host.clk[c][0] / 1000, host.clk[c][1] / 1000,
+                    host.clk[c][2] / 1000, host.clk[c][3] / 1000, host.clk[c][4] / 1000, host.clk[c][5] / 1000, host.clk[c][6] / 1000, host.clk[c][7] / 1000);
+        }
+    fprintf(stderr, "peac grow: levels %d entries %d\n", host.grow_levels, host.grow_entries);
+#endif
     if (n_planes) *n_planes = host.n_planes;
     if (n_final) *n_final = host.n_final;
     if (planes_rid_n)
