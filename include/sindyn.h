@@ -147,6 +147,13 @@ int sindyn_flow_branch(sindyn_handle h, const uint8_t *bgr_cur, size_t step_cur,
  * (DynaDetect.cc:1133-1143): I0/I1 u8 w x h, flow in/out w x h x 2 float. */
 int sindyn_flow_refine(sindyn_handle h, const uint8_t *I0, const uint8_t *I1, int w, int hgt, float *flow_uv);
 
+/* Replaces: cv::findHomography(srcPoints, dstPoints, cv::noArray(), cv::RHO) (the call of DynaDetect.cc:1235; OpenCV calib3d
+ * rho.cpp, un-vendored) on an arbitrary ORDERED list of n <= 4096 correspondences (x, y floats; the PROSAC sampler of RHO
+ * consumes the order).  H_out: 3x3 row-major doubles, bit-identical to the library's result for n >= 5 (all zeros when fewer
+ * than 4 inliers were found); inlier_mask_out (optional): n bytes; info_out (optional): [0] n, [1] inliers of the best model,
+ * [2] models evaluated, [3] refinement iterations. */
+int sindyn_find_homography_rho(sindyn_handle h, const float *src_xy, const float *dst_xy, int n, double *H_out, uint8_t *inlier_mask_out,
+                               int *info_out);
 /* Sample weighting + sort + in-border filter (DynaDetect.cc:1163-1231) followed by the robust
  * homography that replaces cv::findHomography(pts, ptsLast, noArray(), RHO) (DynaDetect.cc:1235).
  * flow: W x H x 2 float (already up-sampled).  H_out: 3x3 row-major double.  Uses the handle's

@@ -17,7 +17,7 @@
  * OpenCV is an un-vendored dependency of the reference (OpenCV 4.2.0 EXACT, ORB_SLAM2/CMakeLists.txt:44); its source is
  * not in this container.  This restatement is PINNED against the real library: tests/test_rho_cpu.py runs it next to
  * cv2.findHomography(..., cv2.RHO) (cv2 4.13) on the sample lists of synthetic frames and on randomised correspondences
- * and requires the same inlier mask and H to ~1e-5.  The CUDA kernel (sindslam_b200/csrc/homography.cu) follows this
+ * and requires the same inlier mask and a BIT-IDENTICAL H (N >= 5; for N == 4 cv::findHomography bypasses the estimator).  The CUDA kernel (sindslam_b200/csrc/homography.cu) follows this
  * file step by step and is compared with cv2 itself in tests/test_homography_gpu.py.
  *
  * Build: make -C oracle   (-> oracle/_build/librho_cpu.so)
@@ -426,79 +426,44 @@ static int chol8_damped(const float (*A)[8], float lambda, float (*L)[8])
     return 1;
 }
 
-int rho_variant[4] = {0, 0, 0, 0};
-static float prod3(float a, float b, float c, int v) { return v == 0 ? (a * b) * c : (v == 1 ? a * (b * c) : (a * c) * b); }
-/* inverse of a lower-triangular 8x8, recursive block-wise (1x1 -> 2x2 -> 4x4 -> 8x8); L and M may alias */
+/* inverse of a lower-triangular 8x8, recursive block-wise (1x1 -> 2x2 -> 4x4 -> 8x8); L and M may alias.  The association
+ * of every product below was fixed by comparing with cv2.findHomography(RHO) bit for bit (tests/test_rho_cpu.py). */
 static void tr_inv8(const float (*L)[8], float (*M)[8])
 {
     float s[2][2], t[2][2];
     float u[4][4], v[4][4];
-    const int v2 = rho_variant[0], v4 = rho_variant[1], v8 = rho_variant[2];
     M[0][0] = 1.0f / L[0][0]; M[1][1] = 1.0f / L[1][1]; M[2][2] = 1.0f / L[2][2]; M[3][3] = 1.0f / L[3][3];
     M[4][4] = 1.0f / L[4][4]; M[5][5] = 1.0f / L[5][5]; M[6][6] = 1.0f / L[6][6]; M[7][7] = 1.0f / L[7][7];
     /* four 2x2 blocks */
-    if (v2 < 3) {
-        M[1][0] = prod3(-L[1][0], M[0][0], M[1][1], v2);
-        M[3][2] = prod3(-L[3][2], M[2][2], M[3][3], v2);
-        M[5][4] = prod3(-L[5][4], M[4][4], M[5][5], v2);
-        M[7][6] = prod3(-L[7][6], M[6][6], M[7][7], v2);
-    } else {
-        M[1][0] = prod3(-M[1][1], L[1][0], M[0][0], v2 - 3);
-        M[3][2] = prod3(-M[3][3], L[3][2], M[2][2], v2 - 3);
-        M[5][4] = prod3(-M[5][5], L[5][4], M[4][4], v2 - 3);
-        M[7][6] = prod3(-M[7][7], L[7][6], M[6][6], v2 - 3);
-    }
-    /* two 4x4 blocks */
+    M[1][0] = -M[1][1] * L[1][0] * M[0][0];
+    M[3][2] = -M[3][3] * L[3][2] * M[2][2];
+    M[5][4] = -M[5][5] * L[5][4] * M[4][4];
+    M[7][6] = -M[7][7] * L[7][6] * M[6][6];
+    /* two 4x4 blocks: s = -C^-1 B, t = s A^-1 */
     for (int blk = 0; blk < 2; blk++) {
         const int o = 4 * blk;
-        if (v4 == 0) {           /* s = -C^-1 B, t = s A^-1 */
-            s[0][0] = -M[o + 2][o + 2] * L[o + 2][o + 0];
-            s[0][1] = -M[o + 2][o + 2] * L[o + 2][o + 1];
-            s[1][0] = -M[o + 3][o + 2] * L[o + 2][o + 0] + -M[o + 3][o + 3] * L[o + 3][o + 0];
-            s[1][1] = -M[o + 3][o + 2] * L[o + 2][o + 1] + -M[o + 3][o + 3] * L[o + 3][o + 1];
-            t[0][0] = s[0][0] * M[o + 0][o + 0] + s[0][1] * M[o + 1][o + 0];
-            t[0][1] = s[0][1] * M[o + 1][o + 1];
-            t[1][0] = s[1][0] * M[o + 0][o + 0] + s[1][1] * M[o + 1][o + 0];
-            t[1][1] = s[1][1] * M[o + 1][o + 1];
-        } else {                 /* s = B A^-1, t = -C^-1 s */
-            s[0][0] = L[o + 2][o + 0] * M[o + 0][o + 0] + L[o + 2][o + 1] * M[o + 1][o + 0];
-            s[0][1] = L[o + 2][o + 1] * M[o + 1][o + 1];
-            s[1][0] = L[o + 3][o + 0] * M[o + 0][o + 0] + L[o + 3][o + 1] * M[o + 1][o + 0];
-            s[1][1] = L[o + 3][o + 1] * M[o + 1][o + 1];
-            t[0][0] = -M[o + 2][o + 2] * s[0][0];
-            t[0][1] = -M[o + 2][o + 2] * s[0][1];
-            t[1][0] = -M[o + 3][o + 2] * s[0][0] + -M[o + 3][o + 3] * s[1][0];
-            t[1][1] = -M[o + 3][o + 2] * s[0][1] + -M[o + 3][o + 3] * s[1][1];
-        }
+        s[0][0] = -M[o + 2][o + 2] * L[o + 2][o + 0];
+        s[0][1] = -M[o + 2][o + 2] * L[o + 2][o + 1];
+        s[1][0] = -M[o + 3][o + 2] * L[o + 2][o + 0] + -M[o + 3][o + 3] * L[o + 3][o + 0];
+        s[1][1] = -M[o + 3][o + 2] * L[o + 2][o + 1] + -M[o + 3][o + 3] * L[o + 3][o + 1];
+        t[0][0] = s[0][0] * M[o + 0][o + 0] + s[0][1] * M[o + 1][o + 0];
+        t[0][1] = s[0][1] * M[o + 1][o + 1];
+        t[1][0] = s[1][0] * M[o + 0][o + 0] + s[1][1] * M[o + 1][o + 0];
+        t[1][1] = s[1][1] * M[o + 1][o + 1];
         M[o + 2][o + 0] = t[0][0]; M[o + 2][o + 1] = t[0][1]; M[o + 3][o + 0] = t[1][0]; M[o + 3][o + 1] = t[1][1];
     }
-    /* the 8x8 */
-    if (v8 == 0) {               /* u = -C^-1 B, v = u A^-1 */
-        for (int c = 0; c < 4; c++) {
-            u[0][c] = -M[4][4] * L[4][c];
-            u[1][c] = -M[5][4] * L[4][c] + -M[5][5] * L[5][c];
-            u[2][c] = -M[6][4] * L[4][c] + -M[6][5] * L[5][c] + -M[6][6] * L[6][c];
-            u[3][c] = -M[7][4] * L[4][c] + -M[7][5] * L[5][c] + -M[7][6] * L[6][c] + -M[7][7] * L[7][c];
-        }
-        for (int r = 0; r < 4; r++) {
-            v[r][0] = u[r][0] * M[0][0] + u[r][1] * M[1][0] + u[r][2] * M[2][0] + u[r][3] * M[3][0];
-            v[r][1] = u[r][1] * M[1][1] + u[r][2] * M[2][1] + u[r][3] * M[3][1];
-            v[r][2] = u[r][2] * M[2][2] + u[r][3] * M[3][2];
-            v[r][3] = u[r][3] * M[3][3];
-        }
-    } else {                     /* u = B A^-1, v = -C^-1 u */
-        for (int r = 0; r < 4; r++) {
-            u[r][0] = L[4 + r][0] * M[0][0] + L[4 + r][1] * M[1][0] + L[4 + r][2] * M[2][0] + L[4 + r][3] * M[3][0];
-            u[r][1] = L[4 + r][1] * M[1][1] + L[4 + r][2] * M[2][1] + L[4 + r][3] * M[3][1];
-            u[r][2] = L[4 + r][2] * M[2][2] + L[4 + r][3] * M[3][2];
-            u[r][3] = L[4 + r][3] * M[3][3];
-        }
-        for (int c = 0; c < 4; c++) {
-            v[0][c] = -M[4][4] * u[0][c];
-            v[1][c] = -M[5][4] * u[0][c] + -M[5][5] * u[1][c];
-            v[2][c] = -M[6][4] * u[0][c] + -M[6][5] * u[1][c] + -M[6][6] * u[2][c];
-            v[3][c] = -M[7][4] * u[0][c] + -M[7][5] * u[1][c] + -M[7][6] * u[2][c] + -M[7][7] * u[3][c];
-        }
+    /* the 8x8: u = -C^-1 B, v = u A^-1 */
+    for (int c = 0; c < 4; c++) {
+        u[0][c] = -M[4][4] * L[4][c];
+        u[1][c] = -M[5][4] * L[4][c] + -M[5][5] * L[5][c];
+        u[2][c] = -M[6][4] * L[4][c] + -M[6][5] * L[5][c] + -M[6][6] * L[6][c];
+        u[3][c] = -M[7][4] * L[4][c] + -M[7][5] * L[5][c] + -M[7][6] * L[6][c] + -M[7][7] * L[7][c];
+    }
+    for (int r = 0; r < 4; r++) {
+        v[r][0] = u[r][0] * M[0][0] + u[r][1] * M[1][0] + u[r][2] * M[2][0] + u[r][3] * M[3][0];
+        v[r][1] = u[r][1] * M[1][1] + u[r][2] * M[2][1] + u[r][3] * M[3][1];
+        v[r][2] = u[r][2] * M[2][2] + u[r][3] * M[3][2];
+        v[r][3] = u[r][3] * M[3][3];
     }
     for (int r = 0; r < 4; r++)
         for (int c = 0; c < 4; c++) M[4 + r][c] = v[r][c];

@@ -77,6 +77,7 @@ SIGNATURES = {
     "sindyn_gray_resize": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "sindyn_flow_branch": (_i, [_vp, _vp, _sz, _vp, _ip]),
     "sindyn_flow_refine": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "sindyn_find_homography_rho": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "sindyn_estimate_homography": (_i, [_vp, _vp, _vp, _ip]),
     "sindyn_sample_pairs": (_i, [_vp, _vp, _vp, _vp, _i, _ip]),
     "sindyn_residual_homography": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -334,6 +335,16 @@ class SinDyn:
         n = C.c_int(0)
         self._ck(self.lib.sindyn_estimate_homography(self.h, _p(flow), _p(Hm), C.byref(n)), "estimate_homography")
         return Hm, n.value
+
+    def find_homography_rho(self, src, dst):
+        """cv::findHomography(src, dst, noArray(), RHO) on an ordered correspondence list -> (H 3x3 or None, mask n x 1, info)."""
+        src = np.ascontiguousarray(src, np.float32).reshape(-1, 2)
+        dst = np.ascontiguousarray(dst, np.float32).reshape(-1, 2)
+        Hm = np.zeros((3, 3), np.float64)
+        mask = np.zeros(len(src), np.uint8)
+        info = np.zeros(4, np.int32)
+        self._ck(self.lib.sindyn_find_homography_rho(self.h, _p(src), _p(dst), len(src), _p(Hm), _p(mask), _p(info)), "find_homography_rho")
+        return (Hm if info[1] >= 4 else None), mask, info
 
     def sample_pairs(self, flow, capacity=4096):
         flow = np.ascontiguousarray(flow, np.float32)

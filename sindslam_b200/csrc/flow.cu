@@ -376,6 +376,27 @@ extern "C" int sindyn_sample_pairs(sindyn_handle h, const float *flow, float *pt
     return SINDYN_OK;
 }
 
+extern "C" int sindyn_find_homography_rho(sindyn_handle h, const float *src_xy, const float *dst_xy, int n, double *H_out, uint8_t *inlier_mask_out,
+                                          int *info_out)
+{
+    if (!h) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    if (!src_xy || !dst_xy || !H_out || n < 0 || n > HG_MAX_SAMPLES) return SINDYN_ERR_INVALID;
+    int info[4] = {n, 0, 0, 0};
+    CU_CHECK(h, cudaMemcpyAsync(h->homog.n_pairs, info, sizeof info, cudaMemcpyHostToDevice, h->stream));
+    if (n) {
+        CU_CHECK(h, cudaMemcpyAsync(h->homog.pts, src_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+        CU_CHECK(h, cudaMemcpyAsync(h->homog.pts_last, dst_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    }
+    SD_CHECK(homography_estimate(h, &h->homog));
+    CU_CHECK(h, cudaMemcpyAsync(info, h->homog.n_pairs, sizeof info, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaMemcpyAsync(H_out, h->homog.H_dev, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
+    if (inlier_mask_out && n) CU_CHECK(h, cudaMemcpyAsync(inlier_mask_out, h->homog.inl_mask, n, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    if (info_out) for (int k = 0; k < 4; ++k) info_out[k] = info[k];
+    return SINDYN_OK;
+}
+
 extern "C" int sindyn_estimate_homography(sindyn_handle h, const float *flow, double *H_out, int *n_pairs_out)
 {
     H_CHECK(h);

@@ -154,255 +154,569 @@ __global__ void __launch_bounds__(1024) k_sample_pairs(const float2 *__restrict_
     if (threadIdx.x == 0) *n_out = s_base;
 }
 
-// ---------------------------------------------------------------- minimal solver
-// 8 x 8 Gaussian elimination with partial pivoting (first largest pivot) + back substitution, spread over a warp: lane r (< 8)
-// owns row r of the augmented matrix in registers, pivot search / row swap / pivot-row broadcast go through shuffles.  Every
-// element sees exactly the operations of the textbook serial elimination in the same order (results verified bit-identical to
-// the serial version this replaced); the system never touches local memory and the row updates of a column run in parallel.
-// All 32 lanes must call it (lanes >= 8 only take part in the shuffles); the solution is returned in every lane.
-__device__ bool solve8_warp(double row[9], double x[8])
+// ---------------------------------------------------------------- cv::findHomography(..., RHO)
+// OpenCV's RHO estimator (calib3d rho.cpp, class RHO_HEST_REFC as driven by fundam.cpp: reprojection threshold 3 px,
+// 2000 iterations, confidence 0.995, beta 0.35, non-randomness criterion + final refinement), restated operation by
+// operation so that H is BIT-IDENTICAL to the library's on the same ordered sample list (oracle/rho_cpu.c is the same
+// restatement in C, pinned against cv2.findHomography(RHO) in tests/test_rho_cpu.py; this file is compiled without FMA
+// contraction, the float expressions keep the association of the C code).
+//
+// The estimator is a serial chain: every hypothesis depends on the SPRT / PROSAC state the previous ones left behind.  One
+// CTA runs it; thread 0 is the control thread (PROSAC phase + xorshift128+ sampling, degeneracy tests, the unrolled
+// 4-point solve, SPRT bookkeeping, non-randomness optimisation, the 8x8 Cholesky of the refinement) and the data-parallel
+// parts are spread over the CTA:
+//   * model evaluation: all N reprojection tests at once (one ballot word per warp); the sequential probability ratio
+//     lambda is replayed exactly point by point only while a decision can depend on it -- once an upper bound on lambda is
+//     so small that even a word of 32 rejections cannot lift it over the threshold A, whole words are skipped with the
+//     bound alone (if a later word is not safe by the bound, the exact product is replayed from the last exact checkpoint);
+//   * the inlier buffers keep the library's stale-tail behaviour (an evaluation overwrites only the points it tested);
+//   * refinement: the float accumulations of J^T J, J^T e and the squared error run strictly in inlier order (one thread
+//     per accumulator over per-point products staged in shared memory), because float addition is order dependent.
+#define RHO_NT 512
+#define RHO_TILE 512
+#define RHO_ACC 36               // the 27 entries of JtJ the library updates (lower triangle without the zero block), 8 of Jte, S
+#define RHO_WORDS (HG_MAX_SAMPLES / 32)
+#define RHO_SMEM (sizeof(float2) * 2 * HG_MAX_SAMPLES + sizeof(unsigned short) * (2 * HG_MAX_SAMPLES + 8) + sizeof(unsigned) * 3 * RHO_WORDS + \
+                  sizeof(float) * RHO_ACC * (RHO_TILE + 1))
+
+struct RhoPrng { unsigned long long s0, s1; };
+__device__ __forceinline__ double rho_random(RhoPrng &g)
 {
-    const int lane = threadIdx.x & 31;
-    bool ok = true;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        // first row r >= c with the largest |A[r][c]|
-        double best = (lane >= c && lane < 8) ? fabs(row[c]) : -1.0;
-        int piv = lane;
-        for (int o = 4; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int op = __shfl_xor_sync(0xffffffffu, piv, o);
-            if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+    unsigned long long x = g.s0;
+    const unsigned long long y = g.s1;
+    x ^= x << 23;
+    x ^= x >> 17;
+    x ^= y ^ (y >> 26);
+    g.s0 = y;
+    g.s1 = x;
+    const unsigned long long s = x + y;
+    return (double)s * 5.421010862427522e-20;   // 2^-64
+}
+
+__device__ void rho_rnd_smpl(RhoPrng &g, unsigned sampleSize, unsigned *cs, unsigned dataSetSize)
+{
+    unsigned i, j;
+    if (sampleSize * 2 > dataSetSize) {          // selection sampling (Knuth, Algorithm S)
+        for (i = 0, j = 0; i < dataSetSize && j < sampleSize; i++) {
+            const double U = rho_random(g);
+            if ((double)(dataSetSize - i) * U < (double)(sampleSize - j)) cs[j++] = i;
         }
-        best = __shfl_sync(0xffffffffu, best, 0);
-        piv = __shfl_sync(0xffffffffu, piv, 0);
-        if (!(best > 1e-12)) { ok = false; break; }
-        const int src = lane == c ? piv : (lane == piv ? c : lane);
-        double inv = 0.0, f = 0.0;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) row[k] = __shfl_sync(0xffffffffu, row[k], src);   // swap rows c and piv (whole rows: columns < c are dead)
-        {
-            const double pc = __shfl_sync(0xffffffffu, row[c], c);
-            inv = 1.0 / pc;
-            f = row[c] * inv;
-        }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const double pk = __shfl_sync(0xffffffffu, row[k], c);
-            if (k >= c && lane > c && lane < 8 && f != 0.0) row[k] -= f * pk;
+    } else {                                     // draw until distinct
+        for (i = 0; i < sampleSize; i++) {
+            bool inList;
+            do {
+                cs[i] = (unsigned)((double)dataSetSize * rho_random(g));
+                inList = false;
+                for (j = 0; j < i; j++)
+                    if (cs[i] == cs[j]) { inList = true; break; }
+            } while (inList);
         }
     }
-    if (!ok) return false;
-#pragma unroll
-    for (int r = 7; r >= 0; --r) {
-        double s = row[8];
-#pragma unroll
-        for (int k = r + 1; k < 8; ++k) s -= row[k] * x[k];
-        const double xr = s / row[r];
-        x[r] = __shfl_sync(0xffffffffu, xr, r);
+}
+
+__device__ unsigned rho_iter_bound(double confidence, double inlierRate, unsigned maxIterBound)
+{
+    unsigned retVal;
+    const double q = 1. - pow(inlierRate, 4.0);
+    if (q >= 1.) retVal = maxIterBound;
+    else if (q <= 0.) retVal = 1;
+    else retVal = (unsigned)ceil(log(1. - confidence) / log(q));
+    return retVal <= maxIterBound ? retVal : maxIterBound;
+}
+
+__device__ double rho_design_sprt(double delta, double epsilon)
+{
+    const double C = (1 - delta) * log((1 - delta) / (1 - epsilon)) + delta * log(delta / epsilon);
+    const double K = 25.0 * C / 1.0 + 1;        // t_M = 25, m_S = 1
+    double An = K, prevAn;
+    unsigned i = 0;
+    do {
+        prevAn = An;
+        An = K + log(An);
+    } while ((An - prevAn > 1.5e-8) && (++i < 10));
+    return An;
+}
+
+// strong geometric constraint + coincident coordinates (RHO_HEST_REFC::isSampleDegenerate); k = 4 src points, 4 dst points
+__device__ bool rho_sample_degenerate(const float2 *k)
+{
+    if (k[0].x == k[1].x || k[1].x == k[2].x || k[2].x == k[3].x || k[0].x == k[2].x || k[0].x == k[3].x || k[1].x == k[3].x ||
+        k[0].y == k[1].y || k[1].y == k[2].y || k[2].y == k[3].y || k[0].y == k[2].y || k[0].y == k[3].y || k[1].y == k[3].y ||
+        k[4].x == k[5].x || k[5].x == k[6].x || k[6].x == k[7].x || k[4].x == k[6].x || k[4].x == k[7].x || k[5].x == k[7].x ||
+        k[4].y == k[5].y || k[5].y == k[6].y || k[6].y == k[7].y || k[4].y == k[6].y || k[4].y == k[7].y || k[5].y == k[7].y)
+        return true;
+    const float c0s0 = k[0].y - k[1].y, c0s1 = k[1].x - k[0].x, c0s2 = k[0].x * k[1].y - k[0].y * k[1].x;
+    const float dots0 = c0s0 * k[2].x + c0s1 * k[2].y + c0s2;
+    const float c0d0 = k[4].y - k[5].y, c0d1 = k[5].x - k[4].x, c0d2 = k[4].x * k[5].y - k[4].y * k[5].x;
+    const float dotd0 = c0d0 * k[6].x + c0d1 * k[6].y + c0d2;
+    if (((int)dots0 ^ (int)dotd0) < 0) return true;
+    const float dots1 = c0s0 * k[3].x + c0s1 * k[3].y + c0s2;
+    const float dotd1 = c0d0 * k[7].x + c0d1 * k[7].y + c0d2;
+    if (((int)dots1 ^ (int)dotd1) < 0) return true;
+    const float c2s0 = k[2].y - k[3].y, c2s1 = k[3].x - k[2].x, c2s2 = k[2].x * k[3].y - k[2].y * k[3].x;
+    const float dots2 = c2s0 * k[0].x + c2s1 * k[0].y + c2s2;
+    const float c2d0 = k[6].y - k[7].y, c2d1 = k[7].x - k[6].x, c2d2 = k[6].x * k[7].y - k[6].y * k[7].x;
+    const float dotd2 = c2d0 * k[4].x + c2d1 * k[4].y + c2d2;
+    if (((int)dots2 ^ (int)dotd2) < 0) return true;
+    const float dots3 = c2s0 * k[1].x + c2s1 * k[1].y + c2s2;
+    const float dotd3 = c2d0 * k[5].x + c2d1 * k[5].y + c2d2;
+    if (((int)dots3 ^ (int)dotd3) < 0) return true;
+    return false;
+}
+
+// hFuncRefC: hand-unrolled Gaussian elimination of the 8x9 system of a 4-point homography, all in float
+__device__ void rho_h_func(const float2 *k, float *H)
+{
+    const float x0 = k[0].x, y0 = k[0].y, x1 = k[1].x, y1 = k[1].y, x2 = k[2].x, y2 = k[2].y, x3 = k[3].x, y3 = k[3].y;
+    const float X0 = k[4].x, Y0 = k[4].y, X1 = k[5].x, Y1 = k[5].y, X2 = k[6].x, Y2 = k[6].y, X3 = k[7].x, Y3 = k[7].y;
+    const float x0X0 = x0 * X0, x1X1 = x1 * X1, x2X2 = x2 * X2, x3X3 = x3 * X3;
+    const float x0Y0 = x0 * Y0, x1Y1 = x1 * Y1, x2Y2 = x2 * Y2, x3Y3 = x3 * Y3;
+    const float y0X0 = y0 * X0, y1X1 = y1 * X1, y2X2 = y2 * X2, y3X3 = y3 * X3;
+    const float y0Y0 = y0 * Y0, y1Y1 = y1 * Y1, y2Y2 = y2 * Y2, y3Y3 = y3 * Y3;
+    float n00 = x0 - x2, n01 = x1 - x2, n02 = x2, n03 = x3 - x2;
+    float n10 = y0 - y2, n11 = y1 - y2, n12 = y2, n13 = y3 - y2;
+    float a0 = x2X2 - x0X0, a1 = x2X2 - x1X1, a2 = -x2X2, a3 = x2X2 - x3X3, a4 = x2Y2 - x0Y0, a5 = x2Y2 - x1Y1, a6 = -x2Y2, a7 = x2Y2 - x3Y3;
+    float b0 = y2X2 - y0X0, b1 = y2X2 - y1X1, b2 = -y2X2, b3 = y2X2 - y3X3, b4 = y2Y2 - y0Y0, b5 = y2Y2 - y1Y1, b6 = -y2Y2, b7 = y2Y2 - y3Y3;
+    float c0 = (X0 - X2), c1 = (X1 - X2), c2 = (X2), c3 = (X3 - X2), c4 = (Y0 - Y2), c5 = (Y1 - Y2), c6 = (Y2), c7 = (Y3 - Y2);
+    float s1 = n00, s2 = n01;
+    n11 = n11 * s1 - n10 * s2;
+    a1 = a1 * s1 - a0 * s2; b1 = b1 * s1 - b0 * s2; c1 = c1 * s1 - c0 * s2;
+    a5 = a5 * s1 - a4 * s2; b5 = b5 * s1 - b4 * s2; c5 = c5 * s1 - c4 * s2;
+    s2 = n03;
+    n13 = n13 * s1 - n10 * s2;
+    a3 = a3 * s1 - a0 * s2; b3 = b3 * s1 - b0 * s2; c3 = c3 * s1 - c0 * s2;
+    a7 = a7 * s1 - a4 * s2; b7 = b7 * s1 - b4 * s2; c7 = c7 * s1 - c4 * s2;
+    s1 = n11; s2 = n13;
+    a3 = a3 * s1 - a1 * s2; b3 = b3 * s1 - b1 * s2; c3 = c3 * s1 - c1 * s2;
+    a7 = a7 * s1 - a5 * s2; b7 = b7 * s1 - b5 * s2; c7 = c7 * s1 - c5 * s2;
+    s2 = n10;
+    n00 = n00 * s1 - n01 * s2;
+    a0 = a0 * s1 - a1 * s2; b0 = b0 * s1 - b1 * s2; c0 = c0 * s1 - c1 * s2;
+    a4 = a4 * s1 - a5 * s2; b4 = b4 * s1 - b5 * s2; c4 = c4 * s1 - c5 * s2;
+    s1 = 1.0f / n00;
+    a0 *= s1; b0 *= s1; c0 *= s1; a4 *= s1; b4 *= s1; c4 *= s1;
+    s1 = 1.0f / n11;
+    a1 *= s1; b1 *= s1; c1 *= s1; a5 *= s1; b5 *= s1; c5 *= s1;
+    s1 = n02; s2 = n12;
+    a2 -= a0 * s1 + a1 * s2; b2 -= b0 * s1 + b1 * s2; c2 -= c0 * s1 + c1 * s2;
+    a6 -= a4 * s1 + a5 * s2; b6 -= b4 * s1 + b5 * s2; c6 -= c4 * s1 + c5 * s2;
+    s1 = a7;
+    b7 /= s1; c7 /= s1;
+    s1 = a0; b0 -= s1 * b7; c0 -= s1 * c7;
+    s1 = a1; b1 -= s1 * b7; c1 -= s1 * c7;
+    s1 = a2; b2 -= s1 * b7; c2 -= s1 * c7;
+    s1 = a3; b3 -= s1 * b7; c3 -= s1 * c7;
+    s1 = a4; b4 -= s1 * b7; c4 -= s1 * c7;
+    s1 = a5; b5 -= s1 * b7; c5 -= s1 * c7;
+    s1 = a6; b6 -= s1 * b7; c6 -= s1 * c7;
+    s1 = b3;
+    c3 /= s1;
+    s1 = b0; c0 -= s1 * c3;
+    s1 = b1; c1 -= s1 * c3;
+    s1 = b2; c2 -= s1 * c3;
+    s1 = b4; c4 -= s1 * c3;
+    s1 = b5; c5 -= s1 * c3;
+    s1 = b6; c6 -= s1 * c3;
+    s1 = b7; c7 -= s1 * c3;
+    H[0] = c0; H[1] = c1; H[2] = c2; H[3] = c4; H[4] = c5; H[5] = c6; H[6] = c7; H[7] = c3; H[8] = 1.0f;
+}
+
+// sacChol8x8Damped / sacTRInv8x8 / sacTRISolve8x8 (lower triangles only; the association of every product was fixed by
+// comparing with the library bit for bit, see oracle/rho_cpu.c)
+__device__ bool rho_chol8(const float (*A)[8], float lambda, float (*L)[8])
+{
+    const float lambdap1 = lambda + 1.0f;
+    for (int i = 0; i < 8; i++) {
+        for (int j = 0; j < i; j++) {
+            float x = A[i][j];
+            for (int k = 0; k < j; k++) x -= L[i][k] * L[j][k];
+            L[i][j] = x / L[j][j];
+        }
+        float x = A[i][i] * lambdap1;
+        for (int k = 0; k < i; k++) x -= L[i][k] * L[i][k];
+        if (x < 0) return false;
+        L[i][i] = sqrtf(x);
     }
     return true;
 }
-
-__device__ __forceinline__ unsigned int hg_hash(unsigned int x)
+__device__ void rho_tr_inv8(float (*M)[8])     // in place: M = L on entry
 {
-    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    return x;
+    float s[2][2], t[2][2], u[4][4], v[4][4];
+    for (int i = 0; i < 8; i++) M[i][i] = 1.0f / M[i][i];
+    M[1][0] = -M[1][1] * M[1][0] * M[0][0];
+    M[3][2] = -M[3][3] * M[3][2] * M[2][2];
+    M[5][4] = -M[5][5] * M[5][4] * M[4][4];
+    M[7][6] = -M[7][7] * M[7][6] * M[6][6];
+    for (int blk = 0; blk < 2; blk++) {
+        const int o = 4 * blk;
+        s[0][0] = -M[o + 2][o + 2] * M[o + 2][o + 0];
+        s[0][1] = -M[o + 2][o + 2] * M[o + 2][o + 1];
+        s[1][0] = -M[o + 3][o + 2] * M[o + 2][o + 0] + -M[o + 3][o + 3] * M[o + 3][o + 0];
+        s[1][1] = -M[o + 3][o + 2] * M[o + 2][o + 1] + -M[o + 3][o + 3] * M[o + 3][o + 1];
+        t[0][0] = s[0][0] * M[o + 0][o + 0] + s[0][1] * M[o + 1][o + 0];
+        t[0][1] = s[0][1] * M[o + 1][o + 1];
+        t[1][0] = s[1][0] * M[o + 0][o + 0] + s[1][1] * M[o + 1][o + 0];
+        t[1][1] = s[1][1] * M[o + 1][o + 1];
+        M[o + 2][o + 0] = t[0][0]; M[o + 2][o + 1] = t[0][1]; M[o + 3][o + 0] = t[1][0]; M[o + 3][o + 1] = t[1][1];
+    }
+    for (int c = 0; c < 4; c++) {
+        u[0][c] = -M[4][4] * M[4][c];
+        u[1][c] = -M[5][4] * M[4][c] + -M[5][5] * M[5][c];
+        u[2][c] = -M[6][4] * M[4][c] + -M[6][5] * M[5][c] + -M[6][6] * M[6][c];
+        u[3][c] = -M[7][4] * M[4][c] + -M[7][5] * M[5][c] + -M[7][6] * M[6][c] + -M[7][7] * M[7][c];
+    }
+    for (int r = 0; r < 4; r++) {
+        v[r][0] = u[r][0] * M[0][0] + u[r][1] * M[1][0] + u[r][2] * M[2][0] + u[r][3] * M[3][0];
+        v[r][1] = u[r][1] * M[1][1] + u[r][2] * M[2][1] + u[r][3] * M[3][1];
+        v[r][2] = u[r][2] * M[2][2] + u[r][3] * M[3][2];
+        v[r][3] = u[r][3] * M[3][3];
+    }
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) M[4 + r][c] = v[r][c];
+}
+__device__ void rho_tri_solve8(const float (*L)[8], const float *Jte, float *dH)
+{
+    float t[8];
+    for (int i = 0; i < 8; i++) {
+        float v = L[i][0] * Jte[0];
+        for (int k = 1; k <= i; k++) v += L[i][k] * Jte[k];
+        t[i] = v;
+    }
+    for (int i = 0; i < 8; i++) {
+        float v = L[i][i] * t[i];
+        for (int k = i + 1; k < 8; k++) v += L[k][i] * t[k];
+        dH[i] = v;
+    }
 }
 
-// one warp per hypothesis
-__global__ void __launch_bounds__(256) k_homog_hypotheses(const float2 *__restrict__ pts, const float2 *__restrict__ pts_last,
-                                                          const int *__restrict__ n_ptr, double *__restrict__ Hs, int *__restrict__ scores)
+// accumulator a of sacCalcJacobianErrors <-> (row, column) of JtJ (lower triangle, in the library's update order), Jte, S
+__constant__ signed char c_rho_acc_r[27] = {0, 1, 1, 2, 2, 2, 3, 4, 4, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7};
+__constant__ signed char c_rho_acc_c[27] = {0, 0, 1, 0, 1, 2, 3, 3, 4, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 7};
+
+__global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src, const float2 *__restrict__ g_dst, const int *__restrict__ n_ptr,
+                                               double *__restrict__ H_out, int *__restrict__ info_out, unsigned char *__restrict__ mask_out)
 {
-    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (m >= HG_M) return;
-    const int n = *n_ptr;
-    double h[8];
-    bool ok = n >= 4;
-    if (ok) {
-        // PROSAC-style progressive sampling pool: the top T of the weight-sorted list
-        int T = max(8, (int)(((long long)n * (m + 1) + HG_M - 1) / HG_M));
-        T = min(T, n);
-        int idx[4];
-        unsigned int s = hg_hash(0x9e3779b9u * (unsigned)(m + 1));
-        for (int k = 0; k < 4; ++k) {
-            for (int tries = 0; tries < 16; ++tries) {
-                s = hg_hash(s + 0x632be5abu);
-                idx[k] = (int)(s % (unsigned)T);
-                bool dup = false;
-                for (int q = 0; q < k; ++q) dup |= idx[q] == idx[k];
-                if (!dup) break;
+    extern __shared__ unsigned char rho_sm[];
+    float2 *s_src = (float2 *)rho_sm, *s_dst = s_src + HG_MAX_SAMPLES;
+    unsigned short *s_tbl = (unsigned short *)(s_dst + HG_MAX_SAMPLES);     // non-randomness table, N + 1 entries
+    unsigned short *s_idx = s_tbl + HG_MAX_SAMPLES + 8;                      // inlier indexes of the best model, ascending
+    unsigned *s_new = (unsigned *)(s_idx + HG_MAX_SAMPLES), *s_buf0 = s_new + RHO_WORDS, *s_buf1 = s_buf0 + RHO_WORDS;
+    float *s_prod = (float *)(s_buf1 + RHO_WORDS);                           // RHO_ACC x (RHO_TILE + 1)
+    __shared__ float s_H[9], s_acc[RHO_ACC];
+    __shared__ int s_go, s_ninl_list, s_warp_cnt[RHO_WORDS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = min(n_ptr[0], HG_MAX_SAMPLES);
+    const int nwords = (N + 31) >> 5;
+    if (N < 5) {   // fewer than 4 points: failure; exactly 4: cv::findHomography bypasses RHO -- neither occurs on the 2961-sample grid
+        if (tid < 9) H_out[tid] = 0.0;
+        if (tid == 0) { info_out[1] = 0; info_out[2] = 0; info_out[3] = 0; }
+        return;
+    }
+    for (int i = tid; i < N; i += RHO_NT) { s_src[i] = g_src[i]; s_dst[i] = g_dst[i]; }
+    for (int w = tid; w < RHO_WORDS; w += RHO_NT) { s_buf0[w] = 0u; s_buf1[w] = 0u; }
+    {   // sacInitNonRand(beta = 0.35)
+        const double bb = sqrt(0.35 * (1.0 - 0.35)) * 1.645;
+        for (int n = tid; n <= N; n += RHO_NT) {
+            unsigned v = 0;
+            if (n >= 5 && n < N) { const double mu = n * 0.35, sigma = sqrt((double)n) * bb; v = (unsigned)ceil(4 + mu + sigma); }
+            s_tbl[n] = (unsigned short)min(v, 65535u);
+        }
+    }
+    __syncthreads();
+    // ---- control state (thread 0)
+    RhoPrng prng;
+    unsigned it = 0, phNum = 4, phEndI = 1, phMax = N, phNumInl = 0, maxI = 2000, numInl_b = 0, n_models = 0;
+    double phEndFpI = 0, epsilon = 0.1, delta = 0.01, A = 0, lamAcc = 0, lamRej = 0;
+    float Hb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned *cur = s_buf0, *best = s_buf1;
+    if (tid == 0) {
+        prng.s0 = ~0ull; prng.s1 = 0ull;
+        for (int i = 0; i < 20; i++) rho_random(prng);
+        double numer = 1, denom = 1;
+        for (unsigned i = 0; i < 4; i++) { numer *= 4 - i; denom *= N - i; }
+        phEndFpI = 2000 * numer / denom;
+        A = rho_design_sprt(delta, epsilon);
+        lamRej = (1.0 - delta) / (1.0 - epsilon);
+        lamAcc = delta / epsilon;
+    }
+    const float distSq = 3.0f * 3.0f;
+    for (;;) {
+        // ---- hypothesize (thread 0): PROSAC sample until a non-degenerate model or the end of the loop
+        if (tid == 0) {
+            int go = 0;
+            while (it < maxI || it < 100) {
+                if (it >= phEndI && phNum < phMax) {
+                    phNum++;
+                    const double next = (phEndFpI * phNum) / (phNum - 4);
+                    phEndI += (unsigned)ceil(next - phEndFpI);
+                    phEndFpI = next;
+                }
+                unsigned smpl[4];
+                if (it > phEndI) rho_rnd_smpl(prng, 4, smpl, phNum);
+                else { rho_rnd_smpl(prng, 3, smpl, phNum - 1); smpl[3] = phNum - 1; }
+                float2 k[8];
+                for (int q = 0; q < 4; q++) { k[q] = s_src[smpl[q]]; k[4 + q] = s_dst[smpl[q]]; }
+                if (rho_sample_degenerate(k)) { ++it; continue; }
+                float Hc[9];
+                rho_h_func(k, Hc);
+                const float f = Hc[0] + Hc[1] + Hc[2] + Hc[3] + Hc[4] + Hc[5] + Hc[6] + Hc[7];
+                if (f != f) { ++it; continue; }
+                for (int q = 0; q < 9; q++) s_H[q] = Hc[q];
+                go = 1;
+                break;
+            }
+            s_go = go;
+        }
+        __syncthreads();
+        if (!s_go) break;
+        // ---- all reprojection tests of the model (evaluateModelSPRT's per-point arithmetic)
+        {
+            const float h0 = s_H[0], h1 = s_H[1], h2 = s_H[2], h3 = s_H[3], h4 = s_H[4], h5 = s_H[5], h6 = s_H[6], h7 = s_H[7];
+            for (int base = 0; base < nwords * 32; base += RHO_NT) {
+                const int i = base + tid;
+                bool inl = false;
+                if (i < N) {
+                    const float x = s_src[i].x, y = s_src[i].y, X = s_dst[i].x, Y = s_dst[i].y;
+                    float rx = h0 * x + h1 * y + h2;
+                    float ry = h3 * x + h4 * y + h5;
+                    const float rz = h6 * x + h7 * y + 1.0f;
+                    rx /= rz; ry /= rz;
+                    rx -= X; ry -= Y;
+                    rx *= rx; ry *= ry;
+                    inl = (rx + ry) <= distSq;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, inl);
+                if (lane == 0 && (i >> 5) < RHO_WORDS) s_new[i >> 5] = m;
             }
         }
-        // DLT rows: lane 2k holds the u-equation of sample k, lane 2k + 1 its v-equation
-        double row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (lane < 8) {
-            const int k = lane >> 1;
-            const double x = pts[idx[k]].x, y = pts[idx[k]].y, u = pts_last[idx[k]].x, v = pts_last[idx[k]].y;
-            if (lane & 1) { row[3] = x; row[4] = y; row[5] = 1; row[6] = -v * x; row[7] = -v * y; row[8] = v; }
-            else { row[0] = x; row[1] = y; row[2] = 1; row[6] = -u * x; row[7] = -u * y; row[8] = u; }
-        }
-        ok = solve8_warp(row, h);
-        for (int c = 0; c < 8; ++c) ok = ok && isfinite(h[c]);
-    }
-    int cnt = 0;
-    if (ok) {
-        for (int i = lane; i < n; i += 32) {
-            double x = pts[i].x, y = pts[i].y;
-            double w = h[6] * x + h[7] * y + 1.0;
-            double ex = (h[0] * x + h[1] * y + h[2]) / w - pts_last[i].x;
-            double ey = (h[3] * x + h[4] * y + h[5]) / w - pts_last[i].y;
-            cnt += (w > 1e-9 && ex * ex + ey * ey <= HG_THR2) ? 1 : 0;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) {
-        scores[m] = ok ? cnt : -1;
-        for (int c = 0; c < 8; ++c) Hs[m * 8 + c] = ok ? h[c] : 0.0;
-    }
-}
-
-// ------------------------------------------------------------------ locally optimised consensus search
-// rank of every hypothesis by inlier count (ties: lower index first); the HG_TOPK best go on to refinement
-__global__ void __launch_bounds__(256) k_homog_rank(const int *__restrict__ scores, int *__restrict__ top)
-{
-    __shared__ int sc[HG_M];
-    for (int i = threadIdx.x; i < HG_M; i += blockDim.x) sc[i] = scores[i];
-    __syncthreads();
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= HG_M) return;
-    const int mine = sc[m];
-    int rank = 0;
-    for (int j = 0; j < HG_M; ++j) rank += (sc[j] > mine) || (sc[j] == mine && j < m);
-    if (rank < HG_TOPK) top[rank] = m;
-}
-
-// One CTA per candidate: Gauss-Newton on the reprojection error of the inliers (re-selected every iteration), then the
-// final consensus size.  A minimal-sample hypothesis that looks second best can refine into the largest consensus set
-// (two competing planes), which is what the reference's RHO estimator returns -- hence HG_TOPK candidates, not one.
-// 256 threads: the 45 normal-equation accumulators of a thread stay in registers, the cross-warp reduction is done by
-// 45 threads in parallel, and the loop stops once the update is below 1e-12.
-#define HG_RT 256
-__global__ void __launch_bounds__(HG_RT) k_homog_refine(const float2 *__restrict__ pts, const float2 *__restrict__ pts_last,
-                                                        const int *__restrict__ n_ptr, const double *__restrict__ Hs,
-                                                        const int *__restrict__ scores, const int *__restrict__ top,
-                                                        double *__restrict__ Hc, double *__restrict__ cand_cost)
-{
-    constexpr int NW = HG_RT / 32;
-    __shared__ double s_acc[NW][45];
-    __shared__ double s_tot[45];
-    __shared__ double s_h[8];
-    __shared__ int s_nin[NW];
-    __shared__ int s_done;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n = *n_ptr;
-    const int cand = blockIdx.x;
-    const int m = top[cand];
-    const int best = scores[m];
-    if (tid == 0) {
-        if (best >= 4) for (int c = 0; c < 8; ++c) s_h[c] = Hs[m * 8 + c];
-        else { for (int c = 0; c < 8; ++c) s_h[c] = 0.0; s_h[0] = 1.0; s_h[4] = 1.0; }  // identity when no consensus
-        s_done = best >= 4 ? 0 : 1;
-    }
-    __syncthreads();
-    int final_n = 0;
-    double final_sse = 0.0;
-    for (int iter = 0; iter <= HG_GN_ITERS; ++iter) {
-        // the last pass (iter == HG_GN_ITERS, or right after convergence) only evaluates the consensus of the final H
-        const bool last = iter == HG_GN_ITERS || s_done;
-        double acc[45];
-#pragma unroll
-        for (int k = 0; k < 45; ++k) acc[k] = 0.0;
-        int nin = 0;
-        double h[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) h[c] = s_h[c];
-        for (int i = tid; i < n; i += HG_RT) {
-            const float2 pp = pts[i], pl = pts_last[i];
-            const double x = pp.x, y = pp.y;
-            const double w = h[6] * x + h[7] * y + 1.0;
-            const double iw = 1.0 / w;
-            const double uh = (h[0] * x + h[1] * y + h[2]) * iw, vh = (h[3] * x + h[4] * y + h[5]) * iw;
-            const double rx = pl.x - uh, ry = pl.y - vh;
-            if (!(w > 1e-9) || rx * rx + ry * ry > HG_THR2) continue;
-            ++nin;
-            acc[44] += rx * rx + ry * ry;
-            if (last) continue;
-            const double Ju[8] = {x * iw, y * iw, iw, 0, 0, 0, -uh * x * iw, -uh * y * iw};
-            const double Jv[8] = {0, 0, 0, x * iw, y * iw, iw, -vh * x * iw, -vh * y * iw};
-            int k = 0;
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int b = a; b < 8; ++b) acc[k++] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) acc[36 + a] += Ju[a] * rx + Jv[a] * ry;
-        }
-#pragma unroll
-        for (int k = 0; k < 45; ++k) {
-            double v = acc[k];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_acc[wid][k] = v;
-        }
-        for (int o = 16; o > 0; o >>= 1) nin += __shfl_xor_sync(0xffffffffu, nin, o);
-        if (lane == 0) s_nin[wid] = nin;
         __syncthreads();
-        if (tid < 45) { double v = 0; for (int w2 = 0; w2 < NW; ++w2) v += s_acc[w2][tid]; s_tot[tid] = v; }
-        __syncthreads();
-        int tn = 0;
-        for (int w2 = 0; w2 < NW; ++w2) tn += s_nin[w2];
-        final_n = tn;
-        final_sse = s_tot[44];
-        if (last) break;
-        if (wid == 0) {   // normal equations: warp-cooperative solve (bit-identical to the serial elimination)
-            if (tn >= 8) {
-                double row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, dx[8];
-                if (lane < 8) {
-                    const int a = lane;
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) {
-                        const int lo = a < b ? a : b, hi = a < b ? b : a;
-                        row[b] = s_tot[lo * 8 - (lo * (lo - 1)) / 2 + (hi - lo)];
+        // ---- SPRT (thread 0): first point at which lambda exceeds A, replayed exactly only where it can matter
+        if (tid == 0) {
+            ++n_models;
+            const double safe = A * (1.0 - 1e-9);
+            double lamRej32 = 1.0;
+            for (int q = 0; q < 32; q++) lamRej32 *= lamRej;
+            lamRej32 *= 1.0 + 1e-12;
+            int Ntested = N;
+            bool good = true;
+            double ck_lam = 1.0;      // exact lambda at the start of word ck_w
+            int ck_w = 0;
+            bool exact = true;        // processing in exact mode from the checkpoint
+            double U = 1.0;           // upper bound on lambda in bound mode
+            int w = 0;
+            while (w < nwords && good) {
+                const int cnt = min(32, N - 32 * w);
+                const unsigned bits = s_new[w];
+                if (!exact) {
+                    const int k = __popc(bits), m = cnt - k;
+                    double worst = U;
+                    for (int q = 0; q < m; q++) worst *= lamRej;          // all rejections first: the largest prefix product of the word
+                    if (worst * (1.0 + 1e-12) <= safe) {
+                        double nu = worst;
+                        for (int q = 0; q < k; q++) nu *= lamAcc;
+                        U = fmax(nu * (1.0 + 1e-12), 1e-300);
+                        ++w;
+                        continue;
                     }
-                    row[8] = s_tot[36 + a];
+                    exact = true; w = ck_w;                                // not provably safe: replay exactly from the checkpoint
+                    continue;
                 }
-#pragma unroll
-                for (int b = 0; b < 8; ++b)
-                    if (lane == b) row[b] *= 1.0 + 1e-9;
-                if (solve8_warp(row, dx)) {
-                    bool fin = true;
-                    double mx = 0.0;
-                    for (int c = 0; c < 8; ++c) { fin = fin && isfinite(dx[c]); mx = fmax(mx, fabs(dx[c])); }
-                    if (lane == 0) {
-                        if (fin) for (int c = 0; c < 8; ++c) s_h[c] += dx[c];
-                        if (!fin || mx < 1e-12) s_done = 1;
+                double lam = ck_lam;
+                for (int q = 0; q < cnt; q++) {
+                    lam *= ((bits >> q) & 1u) ? lamAcc : lamRej;
+                    if (!(lam <= A)) { good = false; Ntested = 32 * w + q + 1; break; }
+                }
+                if (!good) break;
+                ++w;
+                ck_lam = lam; ck_w = w;
+                if (lam * lamRej32 <= safe) { exact = false; U = fmax(lam * (1.0 + 1e-12), 1e-300); }
+            }
+            // the evaluation overwrote the inlier flags of the points it tested only
+            unsigned numInl_c = 0;
+            {
+                const int full = Ntested >> 5, rem = Ntested & 31;
+                for (int q = 0; q < full; q++) { const unsigned b = s_new[q]; cur[q] = b; numInl_c += __popc(b); }
+                if (rem) {
+                    const unsigned msk = (1u << rem) - 1u, b = s_new[full] & msk;
+                    cur[full] = (cur[full] & ~msk) | b;
+                    numInl_c += __popc(b);
+                }
+            }
+            // updateSPRT
+            if (good) {
+                if (numInl_c > numInl_b) {
+                    epsilon = (double)numInl_c / N;
+                    A = rho_design_sprt(delta, epsilon);
+                    lamRej = (1.0 - delta) / (1.0 - epsilon);
+                    lamAcc = delta / epsilon;
+                }
+            } else {
+                const double newDelta = (double)numInl_c / Ntested;
+                if (newDelta > 0) {
+                    const double relChange = fabs(delta - newDelta) / delta;
+                    if (relChange > 0.1) {
+                        delta = newDelta;
+                        A = rho_design_sprt(delta, epsilon);
+                        lamRej = (1.0 - delta) / (1.0 - epsilon);
+                        lamAcc = delta / epsilon;
                     }
-                } else if (lane == 0) s_done = 1;
-            } else if (lane == 0) s_done = 1;
+                }
+            }
+            if (numInl_c > numInl_b) {      // saveBestModel, updateBounds, nStarOptimize
+                for (int q = 0; q < 9; q++) Hb[q] = s_H[q];
+                unsigned *t = cur; cur = best; best = t;
+                numInl_b = numInl_c;
+                maxI = rho_iter_bound(0.995, (double)numInl_b / N, maxI);
+                unsigned best_n = N, test_n = N, bestNumInl = numInl_b, testNumInl = numInl_b;
+                for (; test_n > 20 && testNumInl; test_n--) {
+                    if (testNumInl * best_n > bestNumInl * test_n) {
+                        if (testNumInl < s_tbl[test_n]) break;
+                        best_n = test_n;
+                        bestNumInl = testNumInl;
+                    }
+                    testNumInl -= (best[(test_n - 1) >> 5] >> ((test_n - 1) & 31)) & 1u;
+                }
+                if (bestNumInl * phMax > phNumInl * best_n) {
+                    phMax = best_n;
+                    phNumInl = bestNumInl;
+                    maxI = rho_iter_bound(0.995, (double)phNumInl / phMax, maxI);
+                }
+            }
+            ++it;
+        }
+    }
+    // ---- final refinement (RHO_HEST_REFC::refine) over the inliers of the best model, canRefine: more than 4 inliers
+    __shared__ int s_nb, s_which, s_lm;
+    if (tid == 0) { s_nb = (int)numInl_b; s_which = best == s_buf1 ? 1 : 0; for (int q = 0; q < 9; q++) s_H[q] = Hb[q]; }
+    __syncthreads();
+    const unsigned *bestb = s_which ? s_buf1 : s_buf0;
+    const int nb = s_nb;
+    if (mask_out)
+        for (int i = tid; i < N; i += RHO_NT) mask_out[i] = nb >= 4 ? (unsigned char)((bestb[i >> 5] >> (i & 31)) & 1u) : 0;
+    int lm_iters = 0;
+    if (nb > 4) {
+        // ascending list of inlier indexes
+        for (int w = tid; w < RHO_WORDS; w += RHO_NT) s_warp_cnt[w] = w < nwords ? __popc(bestb[w]) : 0;
+        __syncthreads();
+        if (tid == 0) { int acc = 0; for (int w = 0; w < nwords; w++) { const int c = s_warp_cnt[w]; s_warp_cnt[w] = acc; acc += c; } s_ninl_list = acc; }
+        __syncthreads();
+        for (int w = tid; w < nwords; w += RHO_NT) {
+            unsigned b = bestb[w];
+            int o = s_warp_cnt[w];
+            while (b) { const int q = __ffs(b) - 1; b &= b - 1; s_idx[o++] = (unsigned short)(32 * w + q); }
         }
         __syncthreads();
+        const int ni = s_ninl_list;
+        // sacCalcJacobianErrors at the homography in s_H: per-point products staged per tile, accumulators summed in inlier order
+        auto eval = [&]() {
+            float acc = 0.0f;
+            for (int t0 = 0; t0 < ni; t0 += RHO_TILE) {
+                const int tn = min(RHO_TILE, ni - t0);
+                __syncthreads();
+                if (tid < tn) {
+                    const int i = s_idx[t0 + tid];
+                    const float x = s_src[i].x, y = s_src[i].y, X = s_dst[i].x, Y = s_dst[i].y;
+                    const float Wd = s_H[6] * x + s_H[7] * y + 1.0f;
+                    const float iW = fabsf(Wd) > 1.1920929e-07f ? 1.0f / Wd : 0;
+                    const float rX = (s_H[0] * x + s_H[1] * y + s_H[2]) * iW;
+                    const float rY = (s_H[3] * x + s_H[4] * y + s_H[5]) * iW;
+                    const float eX = rX - X, eY = rY - Y;
+                    const float e = eX * eX + eY * eY;
+                    const float dxh11 = x * iW, dxh12 = y * iW, dxh13 = iW, dxh31 = -rX * x * iW, dxh32 = -rX * y * iW;
+                    const float dyh21 = x * iW, dyh22 = y * iW, dyh23 = iW, dyh31 = -rY * x * iW, dyh32 = -rY * y * iW;
+                    float *col = s_prod + tid;
+#define RHO_P(a, v) col[(a) * (RHO_TILE + 1)] = (v)
+                    RHO_P(0, dxh11 * dxh11);
+                    RHO_P(1, dxh11 * dxh12); RHO_P(2, dxh12 * dxh12);
+                    RHO_P(3, dxh11 * dxh13); RHO_P(4, dxh12 * dxh13); RHO_P(5, dxh13 * dxh13);
+                    RHO_P(6, dyh21 * dyh21);
+                    RHO_P(7, dyh21 * dyh22); RHO_P(8, dyh22 * dyh22);
+                    RHO_P(9, dyh21 * dyh23); RHO_P(10, dyh22 * dyh23); RHO_P(11, dyh23 * dyh23);
+                    RHO_P(12, dxh11 * dxh31); RHO_P(13, dxh12 * dxh31); RHO_P(14, dxh13 * dxh31);
+                    RHO_P(15, dyh21 * dyh31); RHO_P(16, dyh22 * dyh31); RHO_P(17, dyh23 * dyh31);
+                    RHO_P(18, dxh31 * dxh31 + dyh31 * dyh31);
+                    RHO_P(19, dxh11 * dxh32); RHO_P(20, dxh12 * dxh32); RHO_P(21, dxh13 * dxh32);
+                    RHO_P(22, dyh21 * dyh32); RHO_P(23, dyh22 * dyh32); RHO_P(24, dyh23 * dyh32);
+                    RHO_P(25, dxh31 * dxh32 + dyh31 * dyh32);
+                    RHO_P(26, dxh32 * dxh32 + dyh32 * dyh32);
+                    RHO_P(27, eX * dxh11); RHO_P(28, eX * dxh12); RHO_P(29, eX * dxh13);
+                    RHO_P(30, eY * dyh21); RHO_P(31, eY * dyh22); RHO_P(32, eY * dyh23);
+                    RHO_P(33, eX * dxh31 + eY * dyh31);
+                    RHO_P(34, eX * dxh32 + eY * dyh32);
+                    RHO_P(35, e);
+#undef RHO_P
+                }
+                __syncthreads();
+                if (tid < RHO_ACC) {
+                    const float *row = s_prod + tid * (RHO_TILE + 1);
+                    int q = 0;
+                    for (; q + 8 <= tn; q += 8) {
+                        const float v0 = row[q], v1 = row[q + 1], v2 = row[q + 2], v3 = row[q + 3], v4 = row[q + 4], v5 = row[q + 5], v6 = row[q + 6], v7 = row[q + 7];
+                        acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
+                    }
+                    for (; q < tn; q++) acc += row[q];
+                }
+            }
+            if (tid < RHO_ACC) s_acc[tid] = acc;
+            __syncthreads();
+        };
+        eval();
+        // Levenberg-Marquardt loop: thread 0 holds the state; the candidate is evaluated in full (J^T J, J^T e, S) at once,
+        // which is what the library computes in two calls when the step is accepted
+        float S = 0, L = 100.0f, JtJ[8][8], Jte[8], Hcur[8];
+        if (tid == 0) {
+            for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) JtJ[r][c] = 0.0f;
+            for (int a = 0; a < 27; a++) JtJ[c_rho_acc_r[a]][c_rho_acc_c[a]] = s_acc[a];
+            for (int q = 0; q < 8; q++) { Jte[q] = s_acc[27 + q]; Hcur[q] = s_H[q]; }
+            S = s_acc[35];
+        }
+        float dH[8];
+        for (int i = 0; i < 100; i++) {
+            if (tid == 0) {
+                float T[8][8];
+                while (!rho_chol8(JtJ, L, T)) L *= 2.0f;
+                rho_tr_inv8(T);
+                rho_tri_solve8(T, Jte, dH);
+                for (int q = 0; q < 8; q++) s_H[q] = Hcur[q] - dH[q];
+            }
+            eval();
+            int stop = 0;
+            if (tid == 0) {
+                ++lm_iters;
+                const float newS = s_acc[35];
+                const float dS = S - newS;
+                float dL = 0;
+                for (int q = 0; q < 8; q++) dL += dH[q] * dH[q];
+                dL *= L;
+                for (int q = 0; q < 8; q++) dL += dH[q] * Jte[q];
+                dL *= 0.5f;
+                const float gain = fabsf(dL) < 1.1920929e-07f ? dS : dS / dL;
+                if (gain < 0.25f) {
+                    L *= 8;
+                    if (L > 1000.0f / 1.1920929e-07f) stop = 1;
+                } else if (gain > 0.75f) {
+                    L *= 0.5f;
+                }
+                if (!stop && gain > 0) {
+                    S = newS;
+                    for (int q = 0; q < 8; q++) Hcur[q] = s_H[q];
+                    for (int a = 0; a < 27; a++) JtJ[c_rho_acc_r[a]][c_rho_acc_c[a]] = s_acc[a];
+                    for (int q = 0; q < 8; q++) Jte[q] = s_acc[27 + q];
+                }
+                s_lm = stop;
+            }
+            __syncthreads();
+            if (s_lm) break;
+        }
+        if (tid == 0) for (int q = 0; q < 8; q++) Hb[q] = Hcur[q];
     }
     if (tid == 0) {
-        for (int c = 0; c < 8; ++c) Hc[cand * 8 + c] = s_h[c];
-        cand_cost[cand * 2] = best >= 4 ? (double)final_n : -1.0;
-        cand_cost[cand * 2 + 1] = final_sse;
+        const bool ok = numInl_b >= 4;
+        for (int q = 0; q < 9; q++) H_out[q] = ok ? (double)Hb[q] : 0.0;
+        info_out[1] = ok ? (int)numInl_b : 0;
+        info_out[2] = (int)n_models;
+        info_out[3] = lm_iters;
     }
-}
-
-// largest refined consensus (ties: smaller squared error, then better original rank)
-__global__ void k_homog_pick(const double *__restrict__ Hc, const double *__restrict__ cand_cost, const int *__restrict__ top,
-                             const int *__restrict__ scores, double *__restrict__ H_out, int *__restrict__ info)
-{
-    if (threadIdx.x) return;
-    int bi = 0;
-    for (int c = 1; c < HG_TOPK; ++c)
-        if (cand_cost[2 * c] > cand_cost[2 * bi] || (cand_cost[2 * c] == cand_cost[2 * bi] && cand_cost[2 * c + 1] < cand_cost[2 * bi + 1])) bi = c;
-    for (int c = 0; c < 8; ++c) H_out[c] = Hc[bi * 8 + c];
-    H_out[8] = 1.0;
-    info[0] = scores[top[0]];
-    info[1] = top[bi];
-    info[2] = (int)cand_cost[2 * bi];
 }
 
 int homography_init(sindyn_base *ctx, HomographyStage *g, int W, int H)
@@ -414,12 +728,9 @@ int homography_init(sindyn_base *ctx, HomographyStage *g, int W, int H)
     SD_CHECK(ctx->dalloc(&g->pts, 2 * HG_MAX_SAMPLES));
     SD_CHECK(ctx->dalloc(&g->pts_last, 2 * HG_MAX_SAMPLES));
     SD_CHECK(ctx->dalloc(&g->n_pairs, 4));
-    SD_CHECK(ctx->dalloc(&g->Hs, 8 * HG_M));
-    SD_CHECK(ctx->dalloc(&g->scores, HG_M));
     SD_CHECK(ctx->dalloc(&g->H_dev, 9));
-    SD_CHECK(ctx->dalloc(&g->top, HG_TOPK));
-    SD_CHECK(ctx->dalloc(&g->Hc, 8 * HG_TOPK));
-    SD_CHECK(ctx->dalloc(&g->cand_cost, 2 * HG_TOPK));
+    SD_CHECK(ctx->dalloc(&g->inl_mask, HG_MAX_SAMPLES));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_rho, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RHO_SMEM));
     return SINDYN_OK;
 }
 
@@ -435,12 +746,7 @@ int homography_sample(sindyn_base *ctx, HomographyStage *g, const float *flow, c
 
 int homography_estimate(sindyn_base *ctx, HomographyStage *g)
 {
-    LAUNCH(ctx, k_homog_hypotheses, cdiv(HG_M * 32, 256), 256, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs,
-           g->scores);
-    LAUNCH(ctx, k_homog_rank, cdiv(HG_M, 256), 256, 0, g->scores, g->top);
-    LAUNCH(ctx, k_homog_refine, HG_TOPK, HG_RT, 0, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->Hs, g->scores, g->top,
-           g->Hc, g->cand_cost);
-    LAUNCH(ctx, k_homog_pick, 1, 32, 0, g->Hc, g->cand_cost, g->top, g->scores, g->H_dev, g->n_pairs + 1);
+    LAUNCH(ctx, k_rho, 1, RHO_NT, RHO_SMEM, (const float2 *)g->pts, (const float2 *)g->pts_last, g->n_pairs, g->H_dev, g->n_pairs, g->inl_mask);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }

@@ -37,21 +37,19 @@ def test_flow_residual_stream(seq_c1, refine):
         print("frame %d refine %d: flow EPE %.4f, IoU low %.4f high %.4f, thr gpu %s cpu %s, stage ms %s" % (
             k, refine, epe, _iou(lo, ref["low"]), _iou(hi, ref["high"]), res["thr"], ref["thr"], np.round(sd.stage_ms()[:5], 3)))
         assert epe <= FLOW_EPE_TOL
-        # The homography estimators differ (device PROSAC/LO estimator vs cv::findHomography RHO).  Where the
-        # consensus is well conditioned they agree to ~1e-2 px and the independently computed masks must match; where many
-        # models have near-equal consensus (e.g. the first frame after the sign-flipped refinement, quirk B#1) RHO returns
-        # its first good-enough PROSAC sample, which no other estimator reproduces -- that case is only reported.
-        dres = float(np.abs(orc.homography_residual(ref["flow"], res["H"]) - orc.homography_residual(ref["flow"], ref["H"])).mean())
-        print("   homography agreement on identical flow: mean |residual difference| %.4f px" % dres)
-        if dres < 0.02:
-            assert _iou(lo, ref["low"]) >= MASK_IOU_MIN and _iou(hi, ref["high"]) >= MASK_IOU_MIN
-            n_checked[0] += 1
+        # k_rho restates cv::findHomography(RHO) (DynaDetect.cc:1235): on the device's own flow and state the device H must be
+        # the library's H bit for bit (the oracle's sample list is bit-exact with the device's, tests/test_homography_gpu.py)
+        p, q = orc.sample_pairs(res["flow"], z, z)      # the flow-only entry point leaves imgDynaLast / imgLabelLast at zero
+        assert np.array_equal(res["H"], orc.estimate_homography(p, q)), k
+        # masks from independently solved flows (GPU Brox vs CPU Brox, EPE ~0.003 px): a stated IoU floor on every frame
+        assert _iou(lo, ref["low"]) >= MASK_IOU_MIN and _iou(hi, ref["high"]) >= MASK_IOU_MIN
+        n_checked[0] += 1
         # identical flow + identical H -> residual / thresholds / masks bit-exact
         mag = orc.homography_residual(res["flow"], res["H"])
         olo, ohi, othr, _ = orc.threshold_masks(mag)
         assert np.array_equal(othr, res["thr"])
         assert np.array_equal(lo, olo) and np.array_equal(hi, ohi)
-    assert n_checked[0] >= 2      # at least two of the three frames are well conditioned
+    assert n_checked[0] == 3
     sd.close()
 
 
