@@ -150,8 +150,10 @@ int sindyn_flow_refine(sindyn_handle h, const uint8_t *I0, const uint8_t *I1, in
 /* Replaces: cv::findHomography(srcPoints, dstPoints, cv::noArray(), cv::RHO) (the call of DynaDetect.cc:1235; OpenCV calib3d
  * rho.cpp, un-vendored) on an arbitrary ORDERED list of n <= 4096 correspondences (x, y floats; the PROSAC sampler of RHO
  * consumes the order).  H_out: 3x3 row-major doubles, bit-identical to the library's result for n >= 5 (all zeros when fewer
- * than 4 inliers were found); inlier_mask_out (optional): n bytes; info_out (optional): [0] n, [1] inliers of the best model,
- * [2] models evaluated, [3] refinement iterations. */
+ * than 4 inliers were found); inlier_mask_out (optional): n bytes; info_out (optional, 12 ints): [0] n, [1] inliers of the best
+ * model, [2] models evaluated, [3] refinement iterations, [4..6] diagnostics: kilo-cycles of the sampling loop, of the
+ * non-randomness optimisation and of the refinement, [7] PROSAC iterations, [8..10] kilo-cycles of the control thread in
+ * sampling + 4-point solve / reprojection tests + SPRT scan / bookkeeping, [11] models that needed the sequential SPRT fallback. */
 int sindyn_find_homography_rho(sindyn_handle h, const float *src_xy, const float *dst_xy, int n, double *H_out, uint8_t *inlier_mask_out,
                                int *info_out);
 /* Sample weighting + sort + in-border filter (DynaDetect.cc:1163-1231) followed by the robust

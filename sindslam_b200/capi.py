@@ -342,7 +342,7 @@ class SinDyn:
         dst = np.ascontiguousarray(dst, np.float32).reshape(-1, 2)
         Hm = np.zeros((3, 3), np.float64)
         mask = np.zeros(len(src), np.uint8)
-        info = np.zeros(4, np.int32)
+        info = np.zeros(12, np.int32)
         self._ck(self.lib.sindyn_find_homography_rho(self.h, _p(src), _p(dst), len(src), _p(Hm), _p(mask), _p(info)), "find_homography_rho")
         return (Hm if info[1] >= 4 else None), mask, info
 

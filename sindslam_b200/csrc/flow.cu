@@ -382,7 +382,7 @@ extern "C" int sindyn_find_homography_rho(sindyn_handle h, const float *src_xy, 
     if (!h) return SINDYN_ERR_INVALID;
     cudaSetDevice(h->device);
     if (!src_xy || !dst_xy || !H_out || n < 0 || n > HG_MAX_SAMPLES) return SINDYN_ERR_INVALID;
-    int info[4] = {n, 0, 0, 0};
+    int info[12] = {n, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     CU_CHECK(h, cudaMemcpyAsync(h->homog.n_pairs, info, sizeof info, cudaMemcpyHostToDevice, h->stream));
     if (n) {
         CU_CHECK(h, cudaMemcpyAsync(h->homog.pts, src_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, h->stream));
@@ -393,7 +393,7 @@ extern "C" int sindyn_find_homography_rho(sindyn_handle h, const float *src_xy, 
     CU_CHECK(h, cudaMemcpyAsync(H_out, h->homog.H_dev, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
     if (inlier_mask_out && n) CU_CHECK(h, cudaMemcpyAsync(inlier_mask_out, h->homog.inl_mask, n, cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
-    if (info_out) for (int k = 0; k < 4; ++k) info_out[k] = info[k];
+    if (info_out) for (int k = 0; k < 12; ++k) info_out[k] = info[k];
     return SINDYN_OK;
 }
 

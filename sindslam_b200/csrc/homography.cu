@@ -13,6 +13,8 @@
 // on the induced flow (tests/test_homography_gpu.py).
 #include "homography.cuh"
 
+#include <math_constants.h>
+
 __device__ const float c_gauss[HG_GAUSS_N] = {
 #include "gauss_table.inc"
 };
@@ -326,14 +328,18 @@ __device__ void rho_h_func(const float2 *k, float *H)
 __device__ bool rho_chol8(const float (*A)[8], float lambda, float (*L)[8])
 {
     const float lambdap1 = lambda + 1.0f;
+#pragma unroll
     for (int i = 0; i < 8; i++) {
-        for (int j = 0; j < i; j++) {
+    #pragma unroll
+    for (int j = 0; j < i; j++) {
             float x = A[i][j];
-            for (int k = 0; k < j; k++) x -= L[i][k] * L[j][k];
+        #pragma unroll
+    for (int k = 0; k < j; k++) x -= L[i][k] * L[j][k];
             L[i][j] = x / L[j][j];
         }
         float x = A[i][i] * lambdap1;
-        for (int k = 0; k < i; k++) x -= L[i][k] * L[i][k];
+    #pragma unroll
+    for (int k = 0; k < i; k++) x -= L[i][k] * L[i][k];
         if (x < 0) return false;
         L[i][i] = sqrtf(x);
     }
@@ -342,11 +348,13 @@ __device__ bool rho_chol8(const float (*A)[8], float lambda, float (*L)[8])
 __device__ void rho_tr_inv8(float (*M)[8])     // in place: M = L on entry
 {
     float s[2][2], t[2][2], u[4][4], v[4][4];
+#pragma unroll
     for (int i = 0; i < 8; i++) M[i][i] = 1.0f / M[i][i];
     M[1][0] = -M[1][1] * M[1][0] * M[0][0];
     M[3][2] = -M[3][3] * M[3][2] * M[2][2];
     M[5][4] = -M[5][5] * M[5][4] * M[4][4];
     M[7][6] = -M[7][7] * M[7][6] * M[6][6];
+#pragma unroll
     for (int blk = 0; blk < 2; blk++) {
         const int o = 4 * blk;
         s[0][0] = -M[o + 2][o + 2] * M[o + 2][o + 0];
@@ -359,32 +367,40 @@ __device__ void rho_tr_inv8(float (*M)[8])     // in place: M = L on entry
         t[1][1] = s[1][1] * M[o + 1][o + 1];
         M[o + 2][o + 0] = t[0][0]; M[o + 2][o + 1] = t[0][1]; M[o + 3][o + 0] = t[1][0]; M[o + 3][o + 1] = t[1][1];
     }
+#pragma unroll
     for (int c = 0; c < 4; c++) {
         u[0][c] = -M[4][4] * M[4][c];
         u[1][c] = -M[5][4] * M[4][c] + -M[5][5] * M[5][c];
         u[2][c] = -M[6][4] * M[4][c] + -M[6][5] * M[5][c] + -M[6][6] * M[6][c];
         u[3][c] = -M[7][4] * M[4][c] + -M[7][5] * M[5][c] + -M[7][6] * M[6][c] + -M[7][7] * M[7][c];
     }
+#pragma unroll
     for (int r = 0; r < 4; r++) {
         v[r][0] = u[r][0] * M[0][0] + u[r][1] * M[1][0] + u[r][2] * M[2][0] + u[r][3] * M[3][0];
         v[r][1] = u[r][1] * M[1][1] + u[r][2] * M[2][1] + u[r][3] * M[3][1];
         v[r][2] = u[r][2] * M[2][2] + u[r][3] * M[3][2];
         v[r][3] = u[r][3] * M[3][3];
     }
+#pragma unroll
     for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) M[4 + r][c] = v[r][c];
+    #pragma unroll
+    for (int c = 0; c < 4; c++) M[4 + r][c] = v[r][c];
 }
 __device__ void rho_tri_solve8(const float (*L)[8], const float *Jte, float *dH)
 {
     float t[8];
+#pragma unroll
     for (int i = 0; i < 8; i++) {
         float v = L[i][0] * Jte[0];
-        for (int k = 1; k <= i; k++) v += L[i][k] * Jte[k];
+    #pragma unroll
+    for (int k = 1; k <= i; k++) v += L[i][k] * Jte[k];
         t[i] = v;
     }
+#pragma unroll
     for (int i = 0; i < 8; i++) {
         float v = L[i][i] * t[i];
-        for (int k = i + 1; k < 8; k++) v += L[k][i] * t[k];
+    #pragma unroll
+    for (int k = i + 1; k < 8; k++) v += L[k][i] * t[k];
         dH[i] = v;
     }
 }
@@ -403,13 +419,15 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
     unsigned *s_new = (unsigned *)(s_idx + HG_MAX_SAMPLES), *s_buf0 = s_new + RHO_WORDS, *s_buf1 = s_buf0 + RHO_WORDS;
     float *s_prod = (float *)(s_buf1 + RHO_WORDS);                           // RHO_ACC x (RHO_TILE + 1)
     __shared__ float s_H[9], s_acc[RHO_ACC];
-    __shared__ int s_go, s_ninl_list, s_warp_cnt[RHO_WORDS];
+    __shared__ int s_go, s_ninl_list, s_warp_cnt[RHO_WORDS], s_tot_inl, s_nstar, s_ns_which, s_ns_stop, s_cert, s_unc;
+    __shared__ double s_logAcc, s_logRej, s_logA, s_scan_s[RHO_NT / 32], s_scan_m[RHO_NT / 32];
+    __shared__ unsigned s_ns_n[RHO_NT], s_ns_i[RHO_NT], s_ns_wn[RHO_NT / 32], s_ns_wi[RHO_NT / 32], s_ns_out[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int N = min(n_ptr[0], HG_MAX_SAMPLES);
     const int nwords = (N + 31) >> 5;
     if (N < 5) {   // fewer than 4 points: failure; exactly 4: cv::findHomography bypasses RHO -- neither occurs on the 2961-sample grid
         if (tid < 9) H_out[tid] = 0.0;
-        if (tid == 0) { info_out[1] = 0; info_out[2] = 0; info_out[3] = 0; }
+        if (tid == 0) for (int q = 1; q < 12; q++) info_out[q] = 0;
         return;
     }
     for (int i = tid; i < N; i += RHO_NT) { s_src[i] = g_src[i]; s_dst[i] = g_dst[i]; }
@@ -426,7 +444,9 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
     // ---- control state (thread 0)
     RhoPrng prng;
     unsigned it = 0, phNum = 4, phEndI = 1, phMax = N, phNumInl = 0, maxI = 2000, numInl_b = 0, n_models = 0;
-    double phEndFpI = 0, epsilon = 0.1, delta = 0.01, A = 0, lamAcc = 0, lamRej = 0;
+    double phEndFpI = 0, epsilon = 0.1, delta = 0.01, A = 0, lamAcc = 0, lamRej = 0, logAcc = 0, logRej = 0, logA_d = 0;
+    int dbg_replay = 0;
+    long long clk_loop = 0, clk_nstar = 0, clk_lm = 0, clk_t0 = clock64(), clk_a = 0, clk_b = 0, clk_c = 0, clk_d = 0, clk_x = clock64();
     float Hb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     unsigned *cur = s_buf0, *best = s_buf1;
     if (tid == 0) {
@@ -438,11 +458,93 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
         A = rho_design_sprt(delta, epsilon);
         lamRej = (1.0 - delta) / (1.0 - epsilon);
         lamAcc = delta / epsilon;
+        logAcc = log(lamAcc); logRej = log(lamRej); logA_d = log(A);
     }
     const float distSq = 3.0f * 3.0f;
+    if (tid == 0) s_nstar = 0;
     for (;;) {
+        // ---- nStarOptimize of the model that has just become the best one (RHO_HEST_REFC::nStarOptimize), CTA-parallel.
+        // The library walks test_n = N .. 21 with a running best ratio (inliers among the first test_n points) / test_n, strict
+        // improvement only, stops at the first improving test_n whose inlier count is below the non-randomness table, or when the
+        // prefix holds no inlier.  Here: prefix counts from the bit words, per-thread chunk maxima, an exclusive "first maximum"
+        // scan over the threads, and the earliest stop position decides which prefix of improvements counts.
+        __syncthreads();
+        if (s_nstar) {
+            const unsigned *bb = s_ns_which ? s_buf1 : s_buf0;
+            for (int w = tid; w < RHO_WORDS; w += RHO_NT) s_warp_cnt[w] = w < nwords ? __popc(bb[w]) : 0;
+            if (tid == 0) s_ns_stop = 0x7fffffff;
+            __syncthreads();
+            if (tid == 0) { int acc = 0; for (int w = 0; w < nwords; w++) { const int c = s_warp_cnt[w]; s_warp_cnt[w] = acc; acc += c; } }
+            __syncthreads();
+            auto I_of = [&](int n) -> unsigned { return n >= 32 * nwords ? (unsigned)(s_warp_cnt[nwords - 1] + __popc(bb[nwords - 1]))
+                                                                        : (unsigned)(s_warp_cnt[n >> 5] + __popc(bb[n >> 5] & ((1u << (n & 31)) - 1u))); };
+            // position j <-> test_n = N - j, j = 0 .. N - 21 ; chunk of this thread
+            const int total = max(N - 20, 1), C = (total + RHO_NT - 1) / RHO_NT;   // (N <= 20: the walk is empty, position 0 = the initial state)
+            const int j0 = min(tid * C, total), j1 = min(j0 + C, total);
+            auto better = [](unsigned bi, unsigned bn, unsigned ai, unsigned an) { return bi * an > ai * bn; };   // b strictly better than a
+            unsigned ln = 0, li = 0;     // chunk maximum (first occurrence); ln == 0: none
+            for (int j = j0; j < j1; ++j) {
+                const unsigned n = N - j, i = I_of((int)n);
+                if (!ln || better(i, n, li, ln)) { ln = n; li = i; }
+            }
+            s_ns_n[tid] = ln; s_ns_i[tid] = li;
+            __syncthreads();
+            unsigned an = 0, ai = 0;     // first maximum over the earlier chunks of this warp
+            for (int l = 0; l < lane; ++l) {
+                const unsigned bn = s_ns_n[wid * 32 + l], bi = s_ns_i[wid * 32 + l];
+                if (bn && (!an || better(bi, bn, ai, an))) { an = bn; ai = bi; }
+            }
+            if (lane == 31) {
+                unsigned wn = an, wi = ai;
+                if (ln && (!wn || better(li, ln, wi, wn))) { wn = ln; wi = li; }
+                s_ns_wn[wid] = wn; s_ns_wi[wid] = wi;
+            }
+            __syncthreads();
+            unsigned cn = 0, ci = 0;     // incoming running best of this thread's chunk
+            for (int w = 0; w < wid; ++w) {
+                const unsigned bn = s_ns_wn[w], bi = s_ns_wi[w];
+                if (bn && (!cn || better(bi, bn, ci, cn))) { cn = bn; ci = bi; }
+            }
+            if (an && (!cn || better(ai, an, ci, cn))) { cn = an; ci = ai; }
+            // walk the chunk with the true state: first stop position (zero prefix, or an improvement below the table)
+            int stop = 0x7fffffff;
+            {
+                unsigned rn = cn, ri = ci;
+                for (int j = j0; j < j1; ++j) {
+                    const unsigned n = N - j, i = I_of((int)n);
+                    if (i == 0) { stop = j; break; }
+                    if (!rn) { rn = n; ri = i; continue; }            // j == 0: the initial state (N, numInl)
+                    if (better(i, n, ri, rn)) {
+                        if (i < s_tbl[n]) { stop = j; break; }
+                        rn = n; ri = i;
+                    }
+                }
+            }
+            if (stop != 0x7fffffff) atomicMin(&s_ns_stop, stop);
+            __syncthreads();
+            const int E = min(s_ns_stop, total);     // positions j < E count; E >= 1 (position 0 is the initial state)
+            if (j0 < E && E <= j1) {                 // exactly one thread: its chunk holds the last counted position
+                unsigned rn = cn, ri = ci;
+                for (int j = j0; j < E; ++j) {
+                    const unsigned n = N - j, i = I_of((int)n);
+                    if (!rn) { rn = n; ri = i; continue; }
+                    if (better(i, n, ri, rn)) { rn = n; ri = i; }
+                }
+                s_ns_out[0] = rn; s_ns_out[1] = ri;
+            }
+            __syncthreads();
+        }
         // ---- hypothesize (thread 0): PROSAC sample until a non-degenerate model or the end of the loop
         if (tid == 0) {
+            if (s_nstar) {
+                s_nstar = 0;
+                const unsigned best_n = s_ns_out[0], bestNumInl = s_ns_out[1];
+                if (bestNumInl * phMax > phNumInl * best_n) {
+                    phMax = best_n;
+                    phNumInl = bestNumInl;
+                    maxI = rho_iter_bound(0.995, (double)phNumInl / phMax, maxI);
+                }
+            }
             int go = 0;
             while (it < maxI || it < 100) {
                 if (it >= phEndI && phNum < phMax) {
@@ -466,6 +568,9 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                 break;
             }
             s_go = go;
+            s_tot_inl = 0; s_cert = 0x7fffffff; s_unc = 0x7fffffff;
+            s_logAcc = logAcc; s_logRej = logRej; s_logA = logA_d;
+            { const long long t_ = clock64(); clk_a += t_ - clk_x; clk_x = t_; }
         }
         __syncthreads();
         if (!s_go) break;
@@ -486,51 +591,72 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                     inl = (rx + ry) <= distSq;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, inl);
-                if (lane == 0 && (i >> 5) < RHO_WORDS) s_new[i >> 5] = m;
+                if (lane == 0 && (i >> 5) < RHO_WORDS) { s_new[i >> 5] = m; if (m) atomicAdd(&s_tot_inl, __popc(m)); }
             }
         }
         __syncthreads();
-        // ---- SPRT (thread 0): first point at which lambda exceeds A, replayed exactly only where it can matter
+        // ---- SPRT: the first point at which lambda = prod(accept / reject factors) exceeds A (evaluateModelSPRT stops there).
+        // The library multiplies sequentially in FP64; a dependent FP64 chain over up to 3000 points costs ~0.1 ms per model
+        // on this part, so the decision is taken in the log domain, in parallel: S_i = FP64 prefix sum of the log factors
+        // (a block scan), compared with log A.  |S_i - log(lambda_i)| < 1e-11, so outside a band of 1e-9 around log A the
+        // comparison "lambda_i <= A" is decided exactly as the library decides it; the sequential product can also underflow
+        // (to a denormal, or to zero where it stays): C_i = S_i - min(0, min_j<=i S_j + 700) bounds it from above after such a
+        // dip.  Only if a point inside the band (or a recovery from a dip) comes before the first certain exit -- never
+        // observed -- thread 0 falls back to the library's sequential product.
+        {
+            const int CH = (N + RHO_NT - 1) / RHO_NT;                    // consecutive points per thread
+            const int i0 = min(tid * CH, N), i1 = min(i0 + CH, N);
+            double loc = 0.0, locmin = 0.0;                              // chunk sum, minimum prefix inside the chunk (0 = empty prefix)
+            for (int i = i0; i < i1; ++i) {
+                loc += ((s_new[i >> 5] >> (i & 31)) & 1u) ? s_logAcc : s_logRej;
+                locmin = fmin(locmin, loc);
+            }
+            // inclusive scan of (sum, min prefix) over the threads: (s1, m1) . (s2, m2) = (s1 + s2, min(m1, s1 + m2))
+            double ss = loc, mm = locmin;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double ps = __shfl_up_sync(0xffffffffu, ss, off), pm = __shfl_up_sync(0xffffffffu, mm, off);
+                if (lane >= off) { mm = fmin(pm, ps + mm); ss = ps + ss; }
+            }
+            if (lane == 31) { s_scan_s[wid] = ss; s_scan_m[wid] = mm; }
+            __syncthreads();
+            double bs = 0.0, bm = 0.0;                                   // everything before this warp
+            for (int q = 0; q < wid; ++q) { bm = fmin(bm, bs + s_scan_m[q]); bs += s_scan_s[q]; }
+            // exclusive prefix of this thread = (before the warp) . (inclusive of the previous lane)
+            double es = __shfl_up_sync(0xffffffffu, ss, 1), em = __shfl_up_sync(0xffffffffu, mm, 1);
+            if (lane == 0) { es = 0.0; em = 0.0; }
+            double S = bs + es, M = fmin(bm, bs + em);
+            const double lA = s_logA;
+            int cert = 0x7fffffff, unc = 0x7fffffff;
+            if (!(lA == CUDART_INF))             // A = inf (epsilon = 1): "lambda <= A" can never fail
+            for (int i = i0; i < i1; ++i) {
+                S += ((s_new[i >> 5] >> (i & 31)) & 1u) ? s_logAcc : s_logRej;
+                M = fmin(M, S);
+                if (M >= -700.0) {
+                    if (S > lA + 1e-9) { if (cert == 0x7fffffff) cert = i; }
+                    else if (!(S < lA - 1e-9)) { if (unc == 0x7fffffff) unc = i; }       // inside the band (or NaN)
+                } else if (!(S - (M + 700.0) < lA - 1e-9)) { if (unc == 0x7fffffff) unc = i; }
+            }
+            if (cert != 0x7fffffff) atomicMin(&s_cert, cert);
+            if (unc != 0x7fffffff) atomicMin(&s_unc, unc);
+            // merge of the tested prefix into the current inlier buffer happens below, once Ntested is known
+        }
+        __syncthreads();
         if (tid == 0) {
+            { const long long t_ = clock64(); clk_b += t_ - clk_x; clk_x = t_; }
             ++n_models;
-            const double safe = A * (1.0 - 1e-9);
-            double lamRej32 = 1.0;
-            for (int q = 0; q < 32; q++) lamRej32 *= lamRej;
-            lamRej32 *= 1.0 + 1e-12;
             int Ntested = N;
             bool good = true;
-            double ck_lam = 1.0;      // exact lambda at the start of word ck_w
-            int ck_w = 0;
-            bool exact = true;        // processing in exact mode from the checkpoint
-            double U = 1.0;           // upper bound on lambda in bound mode
-            int w = 0;
-            while (w < nwords && good) {
-                const int cnt = min(32, N - 32 * w);
-                const unsigned bits = s_new[w];
-                if (!exact) {
-                    const int k = __popc(bits), m = cnt - k;
-                    double worst = U;
-                    for (int q = 0; q < m; q++) worst *= lamRej;          // all rejections first: the largest prefix product of the word
-                    if (worst * (1.0 + 1e-12) <= safe) {
-                        double nu = worst;
-                        for (int q = 0; q < k; q++) nu *= lamAcc;
-                        U = fmax(nu * (1.0 + 1e-12), 1e-300);
-                        ++w;
-                        continue;
-                    }
-                    exact = true; w = ck_w;                                // not provably safe: replay exactly from the checkpoint
-                    continue;
+            if (s_unc < s_cert) {
+                // fallback: the library's sequential FP64 product
+                ++dbg_replay;
+                double lam = 1.0;
+                for (int i = 0; i < N; ++i) {
+                    lam *= ((s_new[i >> 5] >> (i & 31)) & 1u) ? lamAcc : lamRej;
+                    if (!(lam <= A)) { good = false; Ntested = i + 1; break; }
                 }
-                double lam = ck_lam;
-                for (int q = 0; q < cnt; q++) {
-                    lam *= ((bits >> q) & 1u) ? lamAcc : lamRej;
-                    if (!(lam <= A)) { good = false; Ntested = 32 * w + q + 1; break; }
-                }
-                if (!good) break;
-                ++w;
-                ck_lam = lam; ck_w = w;
-                if (lam * lamRej32 <= safe) { exact = false; U = fmax(lam * (1.0 + 1e-12), 1e-300); }
-            }
+            } else if (s_cert != 0x7fffffff) { good = false; Ntested = s_cert + 1; }
+            { const long long t_ = clock64(); clk_c += t_ - clk_x; clk_x = t_; }
             // the evaluation overwrote the inlier flags of the points it tested only
             unsigned numInl_c = 0;
             {
@@ -549,6 +675,7 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                     A = rho_design_sprt(delta, epsilon);
                     lamRej = (1.0 - delta) / (1.0 - epsilon);
                     lamAcc = delta / epsilon;
+                    logAcc = log(lamAcc); logRej = log(lamRej); logA_d = log(A);
                 }
             } else {
                 const double newDelta = (double)numInl_c / Ntested;
@@ -559,6 +686,7 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                         A = rho_design_sprt(delta, epsilon);
                         lamRej = (1.0 - delta) / (1.0 - epsilon);
                         lamAcc = delta / epsilon;
+                        logAcc = log(lamAcc); logRej = log(lamRej); logA_d = log(A);
                     }
                 }
             }
@@ -567,26 +695,15 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                 unsigned *t = cur; cur = best; best = t;
                 numInl_b = numInl_c;
                 maxI = rho_iter_bound(0.995, (double)numInl_b / N, maxI);
-                unsigned best_n = N, test_n = N, bestNumInl = numInl_b, testNumInl = numInl_b;
-                for (; test_n > 20 && testNumInl; test_n--) {
-                    if (testNumInl * best_n > bestNumInl * test_n) {
-                        if (testNumInl < s_tbl[test_n]) break;
-                        best_n = test_n;
-                        bestNumInl = testNumInl;
-                    }
-                    testNumInl -= (best[(test_n - 1) >> 5] >> ((test_n - 1) & 31)) & 1u;
-                }
-                if (bestNumInl * phMax > phNumInl * best_n) {
-                    phMax = best_n;
-                    phNumInl = bestNumInl;
-                    maxI = rho_iter_bound(0.995, (double)phNumInl / phMax, maxI);
-                }
+                s_nstar = 1; s_ns_which = best == s_buf1 ? 1 : 0;      // nStarOptimize runs CTA-wide at the top of the next iteration
             }
             ++it;
+            { const long long t_ = clock64(); clk_d += t_ - clk_x; clk_x = t_; }
         }
     }
     // ---- final refinement (RHO_HEST_REFC::refine) over the inliers of the best model, canRefine: more than 4 inliers
     __shared__ int s_nb, s_which, s_lm;
+    if (tid == 0) { clk_loop = clock64() - clk_t0; clk_t0 = clock64(); }
     if (tid == 0) { s_nb = (int)numInl_b; s_which = best == s_buf1 ? 1 : 0; for (int q = 0; q < 9; q++) s_H[q] = Hb[q]; }
     __syncthreads();
     const unsigned *bestb = s_which ? s_buf1 : s_buf0;
@@ -713,9 +830,13 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
     if (tid == 0) {
         const bool ok = numInl_b >= 4;
         for (int q = 0; q < 9; q++) H_out[q] = ok ? (double)Hb[q] : 0.0;
+        clk_lm = clock64() - clk_t0;
         info_out[1] = ok ? (int)numInl_b : 0;
         info_out[2] = (int)n_models;
         info_out[3] = lm_iters;
+        info_out[4] = (int)(clk_loop >> 10); info_out[5] = (int)(clk_nstar >> 10); info_out[6] = (int)(clk_lm >> 10); info_out[7] = (int)it;
+        info_out[8] = (int)(clk_a >> 10); info_out[9] = (int)(clk_b >> 10); info_out[10] = (int)(clk_d >> 10); info_out[11] = dbg_replay;
+        (void)clk_c;
     }
 }
 
@@ -727,7 +848,7 @@ int homography_init(sindyn_base *ctx, HomographyStage *g, int W, int H)
     SD_CHECK(ctx->dalloc(&g->counts, 32));
     SD_CHECK(ctx->dalloc(&g->pts, 2 * HG_MAX_SAMPLES));
     SD_CHECK(ctx->dalloc(&g->pts_last, 2 * HG_MAX_SAMPLES));
-    SD_CHECK(ctx->dalloc(&g->n_pairs, 4));
+    SD_CHECK(ctx->dalloc(&g->n_pairs, 12));
     SD_CHECK(ctx->dalloc(&g->H_dev, 9));
     SD_CHECK(ctx->dalloc(&g->inl_mask, HG_MAX_SAMPLES));
     CU_CHECK(ctx, cudaFuncSetAttribute(k_rho, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RHO_SMEM));
