@@ -28,7 +28,11 @@ enum sindyn_status {
     SINDYN_ERR_CUDA = 2,      /* CUDA runtime error (see sindyn_last_error) */
     SINDYN_ERR_NO_DEVICE = 3, /* no CUDA device: there is NO CPU fallback */
     SINDYN_ERR_STATE = 4,     /* call order violated (e.g. detect before set_prev_frames) */
-    SINDYN_ERR_CAPACITY = 5   /* fixed-capacity device list overflowed */
+    SINDYN_ERR_CAPACITY = 5   /* fixed-capacity device list overflowed (> 128 components of one frame, > 64 planes, ...).  Reported by the
+                               * call that synchronises the frame, AFTER the frame has been committed: the outputs and the inter-frame
+                               * state (imgDynaLast, imgLabelLast, ...) hold the truncated result and the frame ring has rolled.  The
+                               * reference has no such caps; a caller that wants to continue treats the frame as degraded, one that
+                               * wants to retry restores the state with sindyn_set_state first. */
 };
 
 /* Constructor arguments of ORB_SLAM2::DynaDetect (include/DynaDetect.h:98-105) plus the

@@ -757,11 +757,22 @@ def deepflow_restated(I0_u8, I1_u8):
     return flow, len(pyr)
 
 
-def flow_residual_cpu(bgr_cur, bgr_last, bgr_lastlast, dyna_last, label_last, engine="brox", refine=True):
+def flow_residual_cpu(bgr_cur, bgr_last, bgr_lastlast, dyna_last, label_last, engine="brox", refine=True, inject_flow=None):
     """DynaDetect::DetectDynaByDenseOpticalFLow (DynaDetect.cc:1023-1374) end to end on the CPU.
     engine: 'brox' (USECUDA build's solver, oracle/brox_cpu.c) or 'deepflow' (default CPU build, restated).
+    inject_flow: (full-resolution flow, large_motion) -- the authors' own identical-flow hook (the .flo injection at
+    DynaDetect.cc:1149-1158): everything AFTER the dense flow runs here (sample weighting, the real cv2.findHomography(RHO),
+    residual, Otsu / Triangle thresholds, masks).
     Returns dict(low, high, thr, flow, H, large_motion)."""
     H, W = bgr_cur.shape[:2]
+    if inject_flow is not None:
+        full, lm = inject_flow
+        full = np.ascontiguousarray(full, np.float32)
+        p, q = sample_pairs(full, dyna_last, label_last)
+        Hm = estimate_homography(p, q)
+        mag = homography_residual(full, Hm)
+        low, high, thr, _ = threshold_masks(mag)
+        return dict(low=low, high=high, thr=thr, flow=full, H=Hm, large_motion=bool(lm))
     g = [gray_small(bgr2gray(x)) for x in (bgr_cur, bgr_last, bgr_lastlast)]
 
     def calc(i_ref):
@@ -798,12 +809,14 @@ class DynaDetectOracle:
         z = np.zeros((H, W), np.uint8)
         self.dyna_last, self.high_last, self.label_last = z.copy(), z.copy(), z.copy()
 
-    def detect(self, bgr, depth, inject_masks=None):
+    def detect(self, bgr, depth, inject_masks=None, inject_flow=None):
         """Returns dict(mask, label, + every intermediate).  inject_masks = (low, high): skip the flow branch and use
-        these masks instead (the authors' own identical-flow hook, DynaDetect.cc:1149-1158)."""
+        these masks instead; inject_flow = (flow, large_motion): skip only the dense-flow engine (the authors' own
+        identical-flow hook, DynaDetect.cc:1149-1158) and run the sampling, the real RHO, the residual and the thresholds here."""
         out = {}
         if inject_masks is None:
-            fr = flow_residual_cpu(bgr, self.rgb_last, self.rgb_lastlast, self.dyna_last, self.label_last, self.engine, self.refine)
+            fr = flow_residual_cpu(bgr, self.rgb_last, self.rgb_lastlast, self.dyna_last, self.label_last, self.engine, self.refine,
+                                   inject_flow=inject_flow)
             low, high = fr["low"], fr["high"]
             out["flow"] = fr
         else:

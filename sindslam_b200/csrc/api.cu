@@ -32,6 +32,16 @@ extern "C" void sindyn_default_config(sindyn_config *c, int width, int height)
 extern "C" int sindyn_create(const sindyn_config *cfg, sindyn_handle *out)
 {
     if (!cfg || !out || cfg->width < 64 || cfg->height < 64) return SINDYN_ERR_INVALID;
+    // The number of k-means clusters is a compile-time constant of the kernels (numCluster = nRowCluster * nColCluster = 12,
+    // DynaDetect.cc:46-47); the remaining parameters must leave a usable flow grid and a finite solver.
+    if (cfg->n_row_cluster * cfg->n_col_cluster != 12 || cfg->n_row_cluster < 1 || cfg->n_col_cluster < 1) return SINDYN_ERR_INVALID;
+    if (!(cfg->flow_scale > 0.0f && cfg->flow_scale <= 1.0f) || (int)(cfg->flow_scale * (float)cfg->width) < 16 ||
+        (int)(cfg->flow_scale * (float)cfg->height) < 16)
+        return SINDYN_ERR_INVALID;
+    if (!(cfg->brox_alpha > 0.0f) || !(cfg->brox_gamma >= 0.0f) || !(cfg->brox_pyr_scale > 0.0f && cfg->brox_pyr_scale < 1.0f) || cfg->brox_inner < 1 ||
+        cfg->brox_outer < 1 || cfg->brox_solver < 1 || !(cfg->brox_omega > 0.0f && cfg->brox_omega < 2.0f))
+        return SINDYN_ERR_INVALID;
+    if (!(cfg->fx > 0.0f) || !(cfg->fy > 0.0f) || !(cfg->depth_scale > 0.0f) || !(cfg->depth_weight > 0.0f)) return SINDYN_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) return SINDYN_ERR_NO_DEVICE;
     sindyn_ctx *c = new (std::nothrow) sindyn_ctx();

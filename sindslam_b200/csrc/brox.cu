@@ -80,8 +80,10 @@ __device__ __forceinline__ float bilinear_clamped(const float *__restrict__ img,
 //   * every thread owns a FIXED set of <= 3 red + 3 black pixels for the whole launch: their current (du,dv) stay in
 //     registers, the 2x2 system of a pixel (j12, b1, b2, 1/d1 | 1/d2) in the thread's private shared-memory slots
 //     (1024 threads, 64 registers each);
-//   * tiles: the tile plus a 21-pixel ring lives in shared memory; the 10 fused sweeps are exact because a pixel at
-//     distance d from a halo edge stays valid for d half-sweeps (temporal blocking) and only the interior is written.
+//   * tiles: the tile plus a (2 x sweeps + 1)-pixel ring lives in shared memory -- shipped: 5 fused sweeps per launch, ring of
+//     11 (two launches per lagged-nonlinearity iteration; 10 sweeps / ring 21 measured slower); the fused sweeps are exact
+//     because a pixel at distance d from a halo edge stays valid for d half-sweeps (temporal blocking) and only the
+//     interior is written.
 // Warp I1 by (u, v): A = (I0 + I1w) / 2, Iz = I1w - I0; 5-tap first derivatives of A and Iz, second derivatives of A; reset the
 // increment -- one launch: a 32 x 8 tile warps its pixels plus a 4-pixel ring into shared
 // memory (the 5-tap second derivatives reach 4 pixels out; 2.5x redundant bilinear fetches, no intermediate planes through
@@ -182,7 +184,7 @@ struct BroxInnerP {
 // launch weighs more than the halo redundancy)
 constexpr int BROX_SMAX = SINDYN_BROX_SMAX, BROX_SMAX_SMALL = SINDYN_BROX_SMAX_SMALL, BROX_NT = 1024;
 // Tile menu: a level uses the smallest tile whose grid still fits into one wave of 148 SMs -- the time of a launch is
-// the time of ONE CTA, which is proportional to the staged region (tile + 2 x 21 halo), so mid-size levels run on
+// the time of ONE CTA, which is proportional to the staged region (tile + 2 x (2 x sweeps + 1) halo), so mid-size levels run on
 // many small tiles instead of a few large ones.
 template <int TW_, int TH_, int SMAX_ = BROX_SMAX> struct BroxTile {
     static constexpr int TW = TW_, TH = TH_, SMAX = SMAX_, R = 2 * SMAX_ + 1;
@@ -418,8 +420,9 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_level(BroxInnerP p)
 
 // ------------------------------------------------------------------ tiled levels: system kernel + SOR kernel
 // For levels larger than one tile the lagged-nonlinearity coefficients are computed ONCE per pixel by k_brox_system
-// (no halo redundancy: computed inside the sweep kernel they ran on the whole tile + 21-px halo region, 6.4x the
-// pixels of the tile, and took 44 % of the launch) and the temporally blocked sweeps (k_brox_sor) only stage them.
+// (no halo redundancy: computed inside the sweep kernel they ran on the whole tile + halo region -- 6.4x the pixels of
+// the tile with the 21-px ring of 10 fused sweeps -- and took 44 % of the launch) and the temporally blocked sweeps
+// (k_brox_sor) only stage them.
 struct BroxSysP {
     const float *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz, *u, *v, *dub, *dvb;
     float2 *W;
@@ -524,7 +527,7 @@ struct BroxSorP {
     int nsweeps;
 };
 
-// nsweeps (<= 10) red-black SOR sweeps on one tile + 21-px halo (temporal blocking): same data layout and sweep loop as
+// nsweeps (<= SMAX_, shipped 5) red-black SOR sweeps on one tile + (2 x nsweeps + 1)-px halo (temporal blocking): same data layout and sweep loop as
 // k_brox_level, the systems come from k_brox_system.
 template <class T>
 __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)

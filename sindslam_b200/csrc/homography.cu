@@ -5,12 +5,7 @@
 //   (:1182-1204), std::sort by weight descending (:1217-1219), the inBorder filter with its int truncation and
 //   inclusive upper bound (:1221-1231, inBorder :103-106), and cv::findHomography(pts, ptsLast, noArray(), RHO)
 //   (:1235).
-// The sample list is bit-exact against the oracle.  cv::findHomography(RHO) is OpenCV's PROSAC+SPRT estimator
-// (un-vendored; order sensitive); it is replaced by a deterministic PROSAC-style parallel
-// hypothesise-and-verify estimator: HG_M minimal 4-point hypotheses drawn progressively from the top of the
-// sorted list (one warp each: DLT in double + inlier count at the RHO default 3 px), best consensus, then
-// Gauss-Newton refinement of the reprojection error on the inliers.  Parity with RHO is a stated tolerance
-// on the induced flow (tests/test_homography_gpu.py).
+// The sample list is bit-exact against the oracle; the homography is bit-identical to the library's (k_rho below).
 #include "homography.cuh"
 
 #include <math_constants.h>

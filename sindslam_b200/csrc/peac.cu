@@ -64,6 +64,7 @@ struct PeacImpl {
     float *dist = nullptr;
     int *head = nullptr;         // per pixel: head of the list of this level's visits
     int *qa = nullptr, *qb = nullptr;                                        // FIFO level n / n + 1: (plane << 20) | pixel
+    struct PgRec *rec = nullptr;                                            // visit records of the large levels (cluster kernel)
     int *v_pix = nullptr, *v_info = nullptr, *v_next = nullptr;              // visit records of one level, slot = 4 * entry + direction
     float *v_dist = nullptr;
     unsigned char *v_push = nullptr;
@@ -95,7 +96,7 @@ __device__ __forceinline__ double eig33_min_val(const Sym3 &K)
     const double c2 = K.a00 + K.a11 + K.a22;
     const double c1 = m0 + m1 + m2;
     const double c0 = K.a00 * m0 - K.a01 * (K.a01 * K.a22 - K.a12 * K.a02) + K.a02 * (K.a01 * K.a12 - K.a11 * K.a02);
-    // three float iterations from 0 (cheap: the FP64 chain below costs ~20 cycles per dependent operation), then FP64 to convergence.
+    // three float iterations from 0 (cheap: the FP64 chain below costs ~50 cycles per dependent operation), then FP64 to convergence.
     // A float iterate may land slightly right of the root; p < 0 and p' < 0 there, so the FP64 steps walk back onto it.
     float lf = 0.0f;
     {
@@ -116,7 +117,7 @@ __device__ __forceinline__ double eig33_min_val(const Sym3 &K)
         if (!(dp < 0.0)) break;                  // flat cubic (rank-deficient block): keep the current iterate
         const double dl = p * peac_rcp(dp);
         l -= dl;
-        if (fabs(dl) <= 4e-16 * fabs(l)) break;
+        if (fabs(dl) <= 1e-8 * fabs(l)) break;   // quadratic convergence: the iterate just written is already exact to ~1e-16
     }
     return l;
 }
@@ -497,12 +498,10 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                 const int e = i * nt + tid;
                 const int ru = root[eu[e]], rv = root[ev[e]];
                 const int o = ru == p ? rv : (rv == p ? ru : -1);
-                // two grown nodes share one edge per pair of adjacent blocks: dozens of threads would hit the same stamp.  Only one
-                // lane per distinct neighbour of the warp tries, and only if the stamp is not set yet.
-                bool fresh = o >= 0 && o != p && (flags[o] & PF_ALIVE) && stamp[o] != pop_id;
+                // two grown nodes share one edge per pair of adjacent blocks: the stamp is read first, so that after the first hit the
+                // other edges of the pair skip the atomic
+                const bool fresh = o >= 0 && o != p && (flags[o] & PF_ALIVE) && stamp[o] != pop_id && atomicExch(&stamp[o], pop_id) != pop_id;
                 const unsigned act = __activemask();
-                const unsigned same = __match_any_sync(act, fresh ? o : -1 - lane);
-                fresh = fresh && lane == __ffs(same) - 1 && atomicExch(&stamp[o], pop_id) != pop_id;
                 const unsigned m = __ballot_sync(act, fresh);     // one shared-memory atomic per warp, not per candidate
                 if (fresh) {
                     const int leader = __ffs(m) - 1;
@@ -737,12 +736,13 @@ __device__ __forceinline__ int pg_block_scan(int v, int *s_warp, int &total)
 // eroded border blocks: ~8 k entries, 30 k visits per level) and throughput bound on one SM, so they run on a cluster of
 // PG_CL CTAs (phases separated by cluster barriers, everything in global memory, loads of data written by other CTAs
 // bypass L1); as soon as a level fits the shared-memory path the frontier is handed to the single-CTA kernel below.
-#define PG_CL 8
+#define PG_CL 16                // CTAs of the cluster (non-portable size: opted in at init)
 #define PG_SCAP 2048
-__global__ void __cluster_dims__(PG_CL, 1, 1) __launch_bounds__(PG_NT)
+struct __align__(16) PgRec { int pix, info, next; float dist; };   // one visit: target pixel (-1: none), plane | ok << 8 | push << 9, list link, distance
+
+__global__ void __launch_bounds__(PG_NT)
 k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy, float inv_scale, int Nw, int Nh,
-                    PeacControl *ctl, int *member, float *dist, int *head, int *qa, int *qb, int *g_pix, int *g_info, float *g_dist, int *g_next,
-                    unsigned char *g_push)
+                    PeacControl *ctl, int *member, float *dist, int *head, int *qa, int *qb, PgRec *rec)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -759,7 +759,7 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
     }
     __syncthreads();
     // ---- seeds in the order of findBlockMembership (AHCPlaneFitter.hpp:660-703): blocks in raster order, per block the run
-    // along its top edge, then the run along its left edge (CTA 0; every CTA computes the count)
+    // along its top edge, then the run along its left edge (CTA 0 writes them; every CTA computes the count)
     int *cur = qa, *nxt = qb;
     int n = 0;
     {
@@ -806,9 +806,15 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
     }
     cluster.sync();
     int levels = 0, entries = 0, buf = 0;
+#ifdef PEAC_CLOCKS
+    long long gc[4] = {0, 0, 0, 0}, gt = clock64();
+#define GCLK(i) do { if (g == 0) { const long long t_ = clock64(); gc[i] += t_ - gt; gt = t_; } } while (0)
+#else
+#define GCLK(i) do { } while (0)
+#endif
     while (n > PG_SCAP && n <= PG_CAP) {
         ++levels; entries += n;
-        // ---- phase A
+        // ---- phase A: one entry per thread (n <= G for every level seen so far; the loop covers the rest)
         for (int e = g; e < n; e += G) {
             const int ent = __ldcg(&cur[e]);
             const int s = ent & 0xfffff, plid = ent >> 20;
@@ -831,65 +837,84 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int key = e * 4 + q, c = cc[q];
-                g_pix[key] = c;
-                if (c < 0) continue;
-                const int ccy = c / W, ccx = c - ccy * W;
-                bool ok = false;
-                float cd = -1.0f;
+                const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
                 const float df = (float)dv[q];
-                if (!(df < 1e-3f)) {
-                    const float z = df * inv_scale;
-                    const double P0 = ((float)ccx - cx) * z / fx, P1 = ((float)ccy - cy) * z / fy, P2 = z;
-                    cd = (float)fabs(s_pn[plid][0] * (P0 - s_pc[plid][0]) + s_pn[plid][1] * (P1 - s_pc[plid][1]) + s_pn[plid][2] * (P2 - s_pc[plid][2]));
-                    ok = (double)cd * (double)cd < s_thr[plid];
+                const float z = df * inv_scale;
+                const double P0 = ((float)ccx - cx) * z / fx, P1 = ((float)ccy - cy) * z / fy, P2 = z;
+                const float cd = (float)fabs(s_pn[plid][0] * (P0 - s_pc[plid][0]) + s_pn[plid][1] * (P1 - s_pc[plid][1]) + s_pn[plid][2] * (P2 - s_pc[plid][2]));
+                const bool has = !(df < 1e-3f);
+                const bool ok = has && (double)cd * (double)cd < s_thr[plid];
+                PgRec r;
+                r.pix = cc[q]; r.info = plid | (ok ? 256 : 0); r.next = link[q]; r.dist = has ? cd : -1.0f;
+                rec[e * 4 + q] = r;
+            }
+        }
+        cluster.sync();
+        GCLK(0);
+        // ---- phase B: one owner per visited pixel replays its visits in queue order; the loads of up to four keys of a thread
+        // are issued together
+        for (int k0 = g; k0 < 4 * n; k0 += 4 * G) {
+            PgRec r[4];
+            int tr[4], hd[4];
+            float dd[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int key = k0 + j * G;
+                r[j].pix = -1; r[j].next = 0;
+                if (key < 4 * n) {
+                    const int4 v = __ldcg(reinterpret_cast<const int4 *>(rec) + key);
+                    r[j].pix = v.x; r[j].info = v.y; r[j].next = v.z; r[j].dist = __int_as_float(v.w);
                 }
-                g_info[key] = plid | (ok ? 256 : 0);
-                g_dist[key] = cd;
-                g_push[key] = 0;
-                g_next[key] = link[q];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool own = r[j].pix >= 0 && r[j].next == -1;
+                const int c = own ? r[j].pix : 0;
+                tr[j] = own ? __ldcg(&member[c]) : 0;
+                dd[j] = own ? __ldcg(&dist[c]) : 0.0f;
+                hd[j] = own ? __ldcg(&head[c]) : -1;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!(r[j].pix >= 0 && r[j].next == -1)) continue;      // the visit linked first (list tail) owns the pixel
+                const int c = r[j].pix;
+                int trail = tr[j];
+                float d = dd[j];
+                const int h0 = hd[j];
+                head[c] = -1;
+                int last = -1;
+                for (;;) {
+                    if (trail <= -6) break;
+                    int k = 0x7fffffff;
+                    for (int w = h0; w >= 0; w = __ldcg(&rec[w].next))
+                        if (w > last && w < k) k = w;
+                    if (k == 0x7fffffff) break;
+                    last = k;
+                    const int info = __ldcg(&rec[k].info), plid = info & 255;
+                    if (trail >= 0 && trail == plid) continue;
+                    if (info & 256) {
+                        if (trail >= 0) {
+                            const double sm = fabs(s_pn[plid][0] * s_pn[trail][0] + s_pn[plid][1] * s_pn[trail][1] + s_pn[plid][2] * s_pn[trail][2]);
+                            if (sm >= PEAC_SIM_REFINE) { atomicOr(&ctl->conn[trail], 1ull << plid); atomicOr(&ctl->conn[plid], 1ull << trail); }
+                        }
+                        const float cd = __ldcg(&rec[k].dist);
+                        if (cd < d) { trail = plid; d = cd; rec[k].info = info | 512; }
+                        else if (trail < 0) trail -= 1;
+                    } else if (trail < 0) trail -= 1;
+                }
+                member[c] = trail;
+                dist[c] = d;
             }
         }
         cluster.sync();
-        // ---- phase B
-        for (int key = g; key < 4 * n; key += G) {
-            const int c = __ldcg(&g_pix[key]);
-            if (c < 0 || __ldcg(&g_next[key]) != -1) continue;
-            int trail = __ldcg(&member[c]);
-            float d = __ldcg(&dist[c]);
-            const int h0 = __ldcg(&head[c]);
-            head[c] = -1;
-            int last = -1;
-            for (;;) {
-                if (trail <= -6) break;
-                int k = 0x7fffffff;
-                for (int w = h0; w >= 0; w = __ldcg(&g_next[w]))
-                    if (w > last && w < k) k = w;
-                if (k == 0x7fffffff) break;
-                last = k;
-                const int info = __ldcg(&g_info[k]), plid = info & 255;
-                if (trail >= 0 && trail == plid) continue;
-                if (info & 256) {
-                    if (trail >= 0) {
-                        const double sm = fabs(s_pn[plid][0] * s_pn[trail][0] + s_pn[plid][1] * s_pn[trail][1] + s_pn[plid][2] * s_pn[trail][2]);
-                        if (sm >= PEAC_SIM_REFINE) { atomicOr(&ctl->conn[trail], 1ull << plid); atomicOr(&ctl->conn[plid], 1ull << trail); }
-                    }
-                    const float cd = __ldcg(&g_dist[k]);
-                    if (cd < d) { trail = plid; d = cd; g_push[k] = 1; }
-                    else if (trail < 0) trail -= 1;
-                } else if (trail < 0) trail -= 1;
-            }
-            member[c] = trail;
-            dist[c] = d;
-        }
-        cluster.sync();
+        GCLK(1);
         // ---- phase C: ordered compaction over the whole cluster
         {
             const int total_keys = 4 * n;
             const int L = (total_keys + G - 1) / G;
             const int k0 = min(g * L, total_keys), k1 = min(k0 + L, total_keys);
             int cnt = 0;
-            for (int k = k0; k < k1; ++k) cnt += (__ldcg(&g_pix[k]) >= 0 && __ldcg(&g_push[k])) ? 1 : 0;
+            for (int k = k0; k < k1; ++k) cnt += (__ldcg(&rec[k].info) & 512) ? 1 : 0;
             int total;
             int o = pg_block_scan(cnt, s_warp, total);
             if (tid == 0) ctl->grow_tot[rank] = total;
@@ -902,14 +927,20 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
             }
             o += base;
             if (all <= PG_CAP)
-                for (int k = k0; k < k1; ++k)
-                    if (__ldcg(&g_pix[k]) >= 0 && __ldcg(&g_push[k])) nxt[o++] = ((__ldcg(&g_info[k]) & 255) << 20) | __ldcg(&g_pix[k]);
+                for (int k = k0; k < k1; ++k) {
+                    const int info = __ldcg(&rec[k].info);
+                    if (info & 512) nxt[o++] = ((info & 255) << 20) | __ldcg(&rec[k].pix);
+                }
             n = all;
         }
         cluster.sync();
+        GCLK(2);
         int *t = cur; cur = nxt; nxt = t;
         buf ^= 1;
     }
+#ifdef PEAC_CLOCKS
+    if (g == 0) { ctl->clk[60][0] = gc[0]; ctl->clk[60][1] = gc[1]; ctl->clk[60][2] = gc[2]; ctl->clk[60][3] = levels; }
+#endif
     if (g == 0) {
         ctl->grow_n = n; ctl->grow_buf = buf; ctl->grow_levels = levels; ctl->grow_entries = entries;
         if (n > PG_CAP) ctl->overflow = 1;
@@ -954,6 +985,13 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
     }
     __syncthreads();
     int levels = ctl->grow_levels, entries = ctl->grow_entries;
+#ifdef PEAC_CLOCKS
+    long long fc[4] = {0, 0, 0, 0}, ft = clock64();
+    const int lv0 = levels;
+#define FCLK(i) do { if (tid == 0) { const long long t_ = clock64(); fc[i] += t_ - ft; ft = t_; } } while (0)
+#else
+#define FCLK(i) do { } while (0)
+#endif
     while (n > 0) {
         if (n > PG_CAP) { if (tid == 0) ctl->overflow = 1; break; }
         ++levels; entries += n;
@@ -982,60 +1020,84 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
                     }
                 }
             }
+            // the four point-plane distances are independent FP64 chains (~50 cycles per dependent operation on this part):
+            // straight-line code, so that they overlap
+            float cdv[4];
+            bool okv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
+                const float df = (float)dv[q];
+                const float z = df * inv_scale;                                   // organised cloud point (DynaDetect.cc:562-587)
+                const double P0 = ((float)ccx - cx) * z / fx, P1 = ((float)ccy - cy) * z / fy, P2 = z;
+                const float cd = (float)fabs(s_pn[plid][0] * (P0 - s_pc[plid][0]) + s_pn[plid][1] * (P1 - s_pc[plid][1]) + s_pn[plid][2] * (P2 - s_pc[plid][2]));
+                const bool has = !(df < 1e-3f);
+                cdv[q] = has ? cd : -1.0f;
+                okv[q] = has && (double)cd * (double)cd < s_thr[plid];            // point-plane distance within 3 sigma
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int key = e * 4 + q, c = cc[q];
                 v_pix[key] = c;
-                if (c < 0) continue;
-                const int ccy = c / W, ccx = c - ccy * W;
-                bool ok = false;
-                float cd = -1.0f;
-                const float df = (float)dv[q];
-                if (!(df < 1e-3f)) {                                              // organised cloud point (DynaDetect.cc:562-587)
-                    const float z = df * inv_scale;
-                    const double P0 = ((float)ccx - cx) * z / fx, P1 = ((float)ccy - cy) * z / fy, P2 = z;
-                    cd = (float)fabs(s_pn[plid][0] * (P0 - s_pc[plid][0]) + s_pn[plid][1] * (P1 - s_pc[plid][1]) + s_pn[plid][2] * (P2 - s_pc[plid][2]));
-                    ok = (double)cd * (double)cd < s_thr[plid];                   // point-plane distance within 3 sigma
+                if (c >= 0) {
+                    v_info[key] = plid | (okv[q] ? 256 : 0);
+                    v_dist[key] = cdv[q];
+                    v_push[key] = 0;
+                    v_next[key] = link[q];
                 }
-                v_info[key] = plid | (ok ? 256 : 0);
-                v_dist[key] = cd;
-                v_push[key] = 0;
-                v_next[key] = link[q];
             }
         }
         __syncthreads();
+        FCLK(0);
         // ---- phase B: one owner per visited pixel replays its visits in queue order
-        for (int key = tid; key < 4 * n; key += PG_NT) {
-            const int c = v_pix[key];
-            if (c < 0 || v_next[key] != -1) continue;      // the visit linked first (list tail) owns the pixel
-            int trail = member[c];
-            float d = dist[c];
-            const int h0 = head[c];
-            head[c] = -1;
-            int last = -1;
-            for (;;) {
-                if (trail <= -6) break;                      // visited from 4 neighbours already (:563); nothing can change any more
-                int k = 0x7fffffff;                          // next visit in key order
-                for (int w = h0; w >= 0; w = v_next[w])
-                    if (w > last && w < k) k = w;
-                if (k == 0x7fffffff) break;
-                last = k;
-                const int info = v_info[k], plid = info & 255;
-                if (trail >= 0 && trail == plid) continue;   // visited by the same plane (:564)
-                if (info & 256) {
-                    if (trail >= 0) {                        // two planes meet: potential merge (:575-580)
-                        const double sm = fabs(s_pn[plid][0] * s_pn[trail][0] + s_pn[plid][1] * s_pn[trail][1] + s_pn[plid][2] * s_pn[trail][2]);
-                        if (sm >= PEAC_SIM_REFINE) { atomicOr(&s_conn[trail], 1ull << plid); atomicOr(&s_conn[plid], 1ull << trail); }
-                    }
-                    const float cd = v_dist[k];
-                    if (cd < d) { trail = plid; d = cd; v_push[k] = 1; }
-                    else if (trail < 0) trail -= 1;
-                } else if (trail < 0) trail -= 1;
+        for (int k0 = tid; k0 < 4 * n; k0 += 4 * PG_NT) {
+            int pc[4], tr[4], hd[4];
+            float dd[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int key = k0 + j * PG_NT;
+                const int c = key < 4 * n ? v_pix[key] : -1;
+                pc[j] = (c >= 0 && v_next[key] == -1) ? c : -1;     // the visit linked first (list tail) owns the pixel
             }
-            member[c] = trail;
-            dist[c] = d;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                           // the loads of the four pixels are in flight together
+                const int c = pc[j] < 0 ? 0 : pc[j];
+                tr[j] = member[c]; dd[j] = dist[c]; hd[j] = head[c];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (pc[j] < 0) continue;
+                const int c = pc[j];
+                int trail = tr[j];
+                float d = dd[j];
+                const int h0 = hd[j];
+                head[c] = -1;
+                int last = -1;
+                for (;;) {
+                    if (trail <= -6) break;                      // visited from 4 neighbours already (:563); nothing can change any more
+                    int k = 0x7fffffff;                          // next visit in key order
+                    for (int w = h0; w >= 0; w = v_next[w])
+                        if (w > last && w < k) k = w;
+                    if (k == 0x7fffffff) break;
+                    last = k;
+                    const int info = v_info[k], plid = info & 255;
+                    if (trail >= 0 && trail == plid) continue;   // visited by the same plane (:564)
+                    if (info & 256) {
+                        if (trail >= 0) {                        // two planes meet: potential merge (:575-580)
+                            const double sm = fabs(s_pn[plid][0] * s_pn[trail][0] + s_pn[plid][1] * s_pn[trail][1] + s_pn[plid][2] * s_pn[trail][2]);
+                            if (sm >= PEAC_SIM_REFINE) { atomicOr(&s_conn[trail], 1ull << plid); atomicOr(&s_conn[plid], 1ull << trail); }
+                        }
+                        const float cd = v_dist[k];
+                        if (cd < d) { trail = plid; d = cd; v_push[k] = 1; }
+                        else if (trail < 0) trail -= 1;
+                    } else if (trail < 0) trail -= 1;
+                }
+                member[c] = trail;
+                dist[c] = d;
+            }
         }
         __syncthreads();
+        FCLK(1);
         // ---- phase C: the appended entries, in key order, are the next level
         int *nxt;
         {
@@ -1055,8 +1117,12 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
             else nxt_g = nxt_g == qa ? qb : qa;
         }
         __syncthreads();
+        FCLK(2);
         cur = nxt;
     }
+#ifdef PEAC_CLOCKS
+    if (tid == 0) { ctl->clk[61][0] = fc[0]; ctl->clk[61][1] = fc[1]; ctl->clk[61][2] = fc[2]; ctl->clk[61][3] = levels - lv0; }
+#endif
     __syncthreads();
     for (int k = tid; k < np; k += PG_NT) ctl->conn[k] |= s_conn[k];
     if (tid == 0) { ctl->grow_levels = levels; ctl->grow_entries = entries; }
@@ -1187,6 +1253,8 @@ int peac_init(sindyn_base *ctx, PeacStage *p, int W, int H)
     SD_CHECK(ctx->dalloc(&im->v_dist, (size_t)4 * PG_CAP));
     SD_CHECK(ctx->dalloc(&im->v_push, (size_t)4 * PG_CAP));
     SD_CHECK(ctx->dalloc(&im->PB, (size_t)W * H));
+    SD_CHECK(ctx->dalloc(&im->rec, (size_t)4 * PG_CAP));
+    CU_CHECK(ctx, cudaFuncSetAttribute(k_peac_grow_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     if ((size_t)W * H >= (1u << 20)) { ctx->err = "peac: image too large for the packed queue entries"; return SINDYN_ERR_INVALID; }
     const size_t smem = PEAC_AHC_SMEM;
     CU_CHECK(ctx, cudaFuncSetAttribute(k_peac_ahc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1208,8 +1276,17 @@ int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t 
     LAUNCH(ctx, k_peac_blockmap, cdiv(NB, 128), 128, 0, im->ctl, Nw, Nh);
     const dim3 blk(32, 8), grd(cdiv(W, 32), cdiv(H, 8));
     LAUNCH(ctx, k_peac_init_labels, grd, blk, 0, im->ctl, W, H, Nw, Nh, im->label, im->dist, im->head);
-    LAUNCH(ctx, k_peac_grow_cluster, PG_CL, PG_NT, 0, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->ctl, im->label, im->dist, im->head, im->qa, im->qb,
-           im->v_pix, im->v_info, im->v_dist, im->v_next, im->v_push);
+    {   // one cluster of PG_CL CTAs
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(PG_CL); cfg.blockDim = dim3(PG_NT); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = PG_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CU_CHECK(ctx, cudaLaunchKernelEx(&cfg, k_peac_grow_cluster, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->ctl, im->label, im->dist, im->head, im->qa,
+                                         im->qb, im->rec));
+        ctx->launches++;
+    }
     LAUNCH(ctx, k_peac_grow_fifo, 1, PG_NT, PG_SMEM, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->ctl, im->label, im->dist, im->head, im->qa, im->qb,
            im->v_pix, im->v_info, im->v_dist, im->v_next, im->v_push);
     LAUNCH(ctx, k_peac_merge, 1, 32, 0, im->ctl);
@@ -1232,7 +1309,9 @@ int peac_get_debug(sindyn_base *ctx, PeacStage *p, int *label_out, int *planes_r
                     host.clk[c][8], (double)host.clk[c][9] / host.clk[c][8], (double)host.clk[c][10] / host.clk[c][8], host.clk[c][0] / 1000, host.clk[c][1] / 1000,
                     host.clk[c][2] / 1000, host.clk[c][3] / 1000, host.clk[c][4] / 1000, host.clk[c][5] / 1000, host.clk[c][6] / 1000, host.clk[c][7] / 1000);
         }
-    fprintf(stderr, "peac grow: levels %d entries %d\n", host.grow_levels, host.grow_entries);
+    fprintf(stderr, "peac grow: levels %d entries %d | cluster kernel: %lld levels, kcycles A %lld B %lld C %lld | single-CTA kernel: %lld levels, kcycles A %lld B %lld C %lld\n",
+            host.grow_levels, host.grow_entries, host.clk[60][3], host.clk[60][0] / 1000, host.clk[60][1] / 1000, host.clk[60][2] / 1000, host.clk[61][3],
+            host.clk[61][0] / 1000, host.clk[61][1] / 1000, host.clk[61][2] / 1000);
 #endif
     if (n_planes) *n_planes = host.n_planes;
     if (n_final) *n_final = host.n_final;

@@ -3,7 +3,7 @@
 // Replaces cv::cvtColor(BGR2GRAY) (ORB_SLAM2/src/DynaDetect.cc:1390-1392), cv::resize(gray, 0.6x,
 // INTER_LINEAR) (DynaDetect.cc:1037-1039), GpuMat::convertTo(CV_32F, 1/255) (DynaDetect.cc:1046-1048)
 // and the resize inside ORBextractor::ComputePyramid (ORB_SLAM2/src/ORBextractor.cc:1179).
-// Arithmetic contracts (oracle/cvprims.py pins them against cv2):
+// Arithmetic contracts (tests/test_flow_gpu.py pins them bit for bit against cv2.cvtColor / cv2.resize):
 //   gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15
 //   resize: 11-bit integer weights, horizontal sum kept as int, vertical
 //           dst = (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2

@@ -51,3 +51,27 @@ def test_config_struct_layout_matches_header(lib_built):
     assert (cfg.brox_inner, cfg.brox_outer, cfg.brox_solver) == (10, 77, 10)   # DynaDetect.cc:1029
     assert (cfg.n_row_cluster, cfg.n_col_cluster) == (3, 4) and cfg.depth_weight == 1.5  # DynaDetect.cc:46-48
     assert abs(cfg.flow_scale - 0.6) < 1e-6                                      # DynaDetect.cc:1033
+
+
+def test_create_rejects_unusable_configs(lib_built):
+    """sindyn_create validates the configuration BEFORE it looks for a device: the cluster grid must give the 12 clusters the
+    kernels are compiled for (DynaDetect.cc:46-47), the flow scale and the solver parameters must be usable."""
+    from sindslam_b200 import capi
+    lib = capi.load_library()
+
+    def status(**over):
+        cfg = capi.Config()
+        lib.sindyn_default_config(ctypes.byref(cfg), 640, 480)
+        for k, v in over.items():
+            setattr(cfg, k, v)
+        h = ctypes.c_void_p()
+        st = lib.sindyn_create(ctypes.byref(cfg), ctypes.byref(h))
+        if h:
+            lib.sindyn_destroy(h)
+        return st
+
+    for bad in (dict(n_row_cluster=4, n_col_cluster=4), dict(n_row_cluster=2, n_col_cluster=4), dict(flow_scale=0.0), dict(flow_scale=1.5),
+                dict(flow_scale=0.01), dict(brox_inner=0), dict(brox_pyr_scale=1.0), dict(brox_omega=2.5), dict(fx=0.0), dict(depth_scale=-1.0),
+                dict(width=32)):
+        assert status(**bad) == 1, bad                      # SINDYN_ERR_INVALID
+    assert status() in (0, 3)                               # OK with a device, NO_DEVICE without: never INVALID
