@@ -450,8 +450,8 @@ def run_ours(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak" if not args.sequences else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cam, extra={"refine": True, "sequences_total": n_seq_total, "sequences_per_gpu": len(handles),
-                                                  "keypoints_per_frame": round(kp_per_frame, 1)}),
+            "config": workload_config(cam),     # identical for both arms (--impl reference prints the same dict)
+            "run": {"refine": True, "sequences_total": n_seq_total, "sequences_per_gpu": len(handles), "keypoints_per_frame": round(kp_per_frame, 1)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * cam.width * cam.height * 5,
                     "d2h_bytes_per_step": FRAMES_PER_STEP * d2h, "ms_per_step": e2e_ms / args.steps,
                     "note": "one sequence per GPU through sindyn_track_frame (host buffers)"},

@@ -42,7 +42,7 @@ struct ImageView {   // what cv::InputArray::getMat() gives the reference: a bor
     ImageView(const void *d, int r, int c, size_t s, int ch, int eb) : data(d), rows(r), cols(c), step(s), channels(ch), elem_bytes(eb) {}
     bool empty() const { return !data || rows <= 0 || cols <= 0; }
 #ifdef SINDYN_WITH_OPENCV
-    ImageView(const cv::Mat &m) : data(m.data), rows(m.rows), cols(m.cols), step(m.step), channels(m.channels()), elem_bytes((int)m.elemSize1()) {}
+    explicit ImageView(const cv::Mat &m) : data(m.data), rows(m.rows), cols(m.cols), step(m.step), channels(m.channels()), elem_bytes((int)m.elemSize1()) {}
 #endif
 };
 

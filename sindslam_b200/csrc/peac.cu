@@ -986,7 +986,11 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
     __syncthreads();
     int levels = ctl->grow_levels, entries = ctl->grow_entries;
 #ifdef PEAC_CLOCKS
-    long long fc[4] = {0, 0, 0, 0}, ft = clock64();
+    long long fc[6] = {0, 0, 0, 0, 0, 0}, ft = clock64();
+    __shared__ int s_tmax[2], s_seg[3];
+    long long sg[3] = {0, 0, 0};
+    if (tid == 0) { s_tmax[0] = 0; s_tmax[1] = 0; s_seg[0] = s_seg[1] = s_seg[2] = 0; }
+    __syncthreads();
     const int lv0 = levels;
 #define FCLK(i) do { if (tid == 0) { const long long t_ = clock64(); fc[i] += t_ - ft; ft = t_; } } while (0)
 #else
@@ -999,6 +1003,9 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
         int *v_pix = small ? s_pix : g_pix, *v_info = small ? s_info : g_info, *v_next = small ? s_next : g_next;
         float *v_dist = small ? s_dist : g_dist;
         unsigned char *v_push = small ? s_push : g_push;
+#ifdef PEAC_CLOCKS
+        long long tw0 = clock64();
+#endif
         // ---- phase A
         for (int e = tid; e < n; e += PG_NT) {
             const int ent = cur[e];
@@ -1020,8 +1027,10 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
                     }
                 }
             }
-            // the four point-plane distances are independent FP64 chains (~50 cycles per dependent operation on this part):
-            // straight-line code, so that they overlap
+#ifdef PEAC_CLOCKS
+            const long long ta_ = clock64();
+#endif
+            // the four point-plane distances are independent FP64 chains: straight-line code, so that they overlap
             float cdv[4];
             bool okv[4];
 #pragma unroll
@@ -1035,6 +1044,9 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
                 cdv[q] = has ? cd : -1.0f;
                 okv[q] = has && (double)cd * (double)cd < s_thr[plid];            // point-plane distance within 3 sigma
             }
+#ifdef PEAC_CLOCKS
+            const long long tb_ = clock64();
+#endif
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int key = e * 4 + q, c = cc[q];
@@ -1046,8 +1058,18 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
                     v_next[key] = link[q];
                 }
             }
+#ifdef PEAC_CLOCKS
+            { const long long tc_ = clock64(); atomicMax(&s_seg[0], (int)(ta_ - tw0)); atomicMax(&s_seg[1], (int)(tb_ - ta_)); atomicMax(&s_seg[2], (int)(tc_ - tb_)); }
+#endif
         }
+#ifdef PEAC_CLOCKS
+        { const long long d_ = clock64() - tw0; atomicMax(&s_tmax[0], (int)d_); }
+#endif
         __syncthreads();
+#ifdef PEAC_CLOCKS
+        if (tid == 0) { fc[3] += s_tmax[0]; s_tmax[0] = 0; for (int q = 0; q < 3; ++q) { sg[q] += s_seg[q]; s_seg[q] = 0; } }
+        tw0 = clock64();
+#endif
         FCLK(0);
         // ---- phase B: one owner per visited pixel replays its visits in queue order
         for (int k0 = tid; k0 < 4 * n; k0 += 4 * PG_NT) {
@@ -1096,7 +1118,13 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
                 dist[c] = d;
             }
         }
+#ifdef PEAC_CLOCKS
+        { const long long d_ = clock64() - tw0; atomicMax(&s_tmax[1], (int)d_); }
+#endif
         __syncthreads();
+#ifdef PEAC_CLOCKS
+        if (tid == 0) { fc[4] += s_tmax[1]; s_tmax[1] = 0; }
+#endif
         FCLK(1);
         // ---- phase C: the appended entries, in key order, are the next level
         int *nxt;
@@ -1121,7 +1149,7 @@ __global__ void __launch_bounds__(PG_NT) k_peac_grow_fifo(const uint16_t *__rest
         cur = nxt;
     }
 #ifdef PEAC_CLOCKS
-    if (tid == 0) { ctl->clk[61][0] = fc[0]; ctl->clk[61][1] = fc[1]; ctl->clk[61][2] = fc[2]; ctl->clk[61][3] = levels - lv0; }
+    if (tid == 0) { ctl->clk[61][0] = fc[0]; ctl->clk[61][1] = fc[1]; ctl->clk[61][2] = fc[2]; ctl->clk[61][3] = levels - lv0; ctl->clk[61][4] = fc[3]; ctl->clk[61][5] = fc[4]; ctl->clk[61][6] = sg[0]; ctl->clk[61][7] = sg[1]; ctl->clk[61][8] = sg[2]; }
 #endif
     __syncthreads();
     for (int k = tid; k < np; k += PG_NT) ctl->conn[k] |= s_conn[k];
@@ -1309,9 +1337,9 @@ int peac_get_debug(sindyn_base *ctx, PeacStage *p, int *label_out, int *planes_r
                     host.clk[c][8], (double)host.clk[c][9] / host.clk[c][8], (double)host.clk[c][10] / host.clk[c][8], host.clk[c][0] / 1000, host.clk[c][1] / 1000,
                     host.clk[c][2] / 1000, host.clk[c][3] / 1000, host.clk[c][4] / 1000, host.clk[c][5] / 1000, host.clk[c][6] / 1000, host.clk[c][7] / 1000);
         }
-    fprintf(stderr, "peac grow: levels %d entries %d | cluster kernel: %lld levels, kcycles A %lld B %lld C %lld | single-CTA kernel: %lld levels, kcycles A %lld B %lld C %lld\n",
+    fprintf(stderr, "peac grow: levels %d entries %d | cluster kernel: %lld levels, kcycles A %lld B %lld C %lld | single-CTA kernel: %lld levels, kcycles A %lld B %lld C %lld (slowest thread A %lld B %lld; A segments issue %lld math %lld store %lld)\n",
             host.grow_levels, host.grow_entries, host.clk[60][3], host.clk[60][0] / 1000, host.clk[60][1] / 1000, host.clk[60][2] / 1000, host.clk[61][3],
-            host.clk[61][0] / 1000, host.clk[61][1] / 1000, host.clk[61][2] / 1000);
+            host.clk[61][0] / 1000, host.clk[61][1] / 1000, host.clk[61][2] / 1000, host.clk[61][4] / 1000, host.clk[61][5] / 1000, host.clk[61][6] / 1000, host.clk[61][7] / 1000, host.clk[61][8] / 1000);
 #endif
     if (n_planes) *n_planes = host.n_planes;
     if (n_final) *n_final = host.n_final;

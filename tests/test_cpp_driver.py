@@ -75,3 +75,37 @@ def test_driver_matches_c_abi(tmp_path, seq_c1):
         assert len(kps) == counts[k]
     sd.close()
     orb.close()
+
+
+def _build_opencv_overload_check(tmp_path, lib_built):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "opencv_overloads")
+    libdir = os.path.dirname(lib_built)
+    cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-O1", "-I" + os.path.join(root, "tests", "stubs"), "-I" + os.path.join(root, "include"),
+           os.path.join(root, "tests", "stubs", "opencv_overloads.cpp"), "-o", exe, "-L" + libdir, "-lsindyn_cuda", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_reference_signature_overloads_type_check(tmp_path, lib_built):
+    """include/sindyn_classes.hpp with -DSINDYN_WITH_OPENCV: the exact reference signatures -- DynaDetect(const cv::InputArray&,
+    const cv::InputArray&, float x5), DetectDynaArea(const cv::InputArray&, const cv::InputArray&, cv::OutputArray&,
+    cv::OutputArray&, int) (DynaDetect.h:98-131), ORBextractor::operator()(cv::InputArray, cv::InputArray,
+    std::vector<cv::KeyPoint>&, cv::OutputArray) (ORBextractor.h:62-64) -- compile, warning-free, against a stand-in
+    <opencv2/core.hpp> (tests/stubs; OpenCV C++ headers are not installed here) in a caller written like the reference driver.
+    Without a device the program must fail loudly (exit 3), never produce outputs."""
+    exe = _build_opencv_overload_check(tmp_path, lib_built)
+    import torch
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "sindyn::Error" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_signature_overloads_run(tmp_path, lib_built):
+    exe = _build_opencv_overload_check(tmp_path, lib_built)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ok: mask 640x480 label 640x480"), r.stdout + r.stderr

@@ -119,3 +119,20 @@ def test_long_stream_invariants():
     assert np.median(ious) > 0.8
     s.close()
     orb.close()
+
+
+def test_fuzz_streams_bit_exact():
+    """A reduced tools/fuzz_parity.py under the gpu marker: 12 random short sequences (both camera models, box / humanoid
+    objects, depth-hole rates 0.03 % - 5 %, every 4th with frame jumps) streamed through sindyn_detect with the PEAC stage ON,
+    free-running state on both sides, the oracle fed with the device's low / high masks: merged labels, dynamic masks and the
+    masked ORB key points + descriptors must be bit-exact on every frame."""
+    n = 0
+    for seq in range(2000, 2012):
+        kind = ("box", "humanoid")[seq % 2]
+        cam = (synth.TUM3, synth.D455_848)[(seq // 2) % 2]
+        hole = (0.015, 0.0003, 0.05, 0.001)[seq % 4]
+        _, frames = synth.make_sequence(5, cam, seq=seq, kind=kind, start=3 + seq % 5, hole_rate=hole)
+        order = list(range(5)) if seq % 4 else [0, 1, 4, 2, 3]
+        _stream(cam, frames, order, orb_every=2)
+        n += 1
+    assert n == 12

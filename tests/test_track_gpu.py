@@ -1,0 +1,41 @@
+"""sindyn_track_frame (one driver iteration: rgbd_tum_noros.cc:132-139 + Tracking::GrabImageRGBD's colour conversion +
+ORBextractor::operator() on the dilated mask) must equal the three reference-shaped calls it fuses -- sindyn_detect,
+sindyn_morph_ellipse(15, dilate), sindyn_orb_extract on cv2's RGB2GRAY / BGR2GRAY image -- bit for bit, for host buffers
+(pageable and pinned) and for device-resident frames."""
+import cv2
+import numpy as np
+import pytest
+
+from sindslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rgb_order", [1, 0])
+def test_track_frame_equals_separate_calls(rgb_order):
+    from sindslam_b200.capi import Orb, SinDyn
+    cam = synth.TUM3
+    _, frames = synth.make_sequence(6, cam, seq=7, kind="box", start=5, hole_rate=0.0005)
+    mk = lambda: (SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=1), Orb(1500, 1.2, 8, 15, 5, cam.width, cam.height))
+    (sa, oa), (sb, ob), (sc, oc) = mk(), mk(), mk()
+    for s in (sa, sb, sc):
+        s.set_prev_frames(frames[0].bgr, frames[0].bgr)
+    for i, f in enumerate(frames):
+        sc.upload_frame(i, f.bgr, f.depth)
+    code = cv2.COLOR_RGB2GRAY if rgb_order else cv2.COLOR_BGR2GRAY
+    for k in range(1, 6):
+        f = frames[k]
+        mask, label = sa.detect(f.bgr, f.depth, k)
+        dil = sa.morph_ellipse(mask, 15, 0)
+        kps, desc = oa.extract(cv2.cvtColor(f.bgr, code), dil)
+        m2, l2, k2, d2 = ob.track_frame(sb, f.bgr, f.depth, k, rgb_order=rgb_order, dilate_k=15)
+        assert np.array_equal(m2, dil) and np.array_equal(l2, label), k
+        assert len(k2) == len(kps) and np.array_equal(d2, desc), k
+        for name in ("x", "y", "angle", "response", "octave"):
+            assert np.array_equal(k2[name], kps[name]), (k, name)
+        oc.track_frame_resident(sc, k, k, rgb_order=rgb_order, dilate_k=15)
+        m3, l3, k3, d3 = oc.track_results(sc)
+        assert np.array_equal(m3, dil) and np.array_equal(l3, label) and np.array_equal(d3, desc), k
+        assert np.array_equal(k3["x"], kps["x"]) and np.array_equal(k3["octave"], kps["octave"]), k
+    for h in (oa, ob, oc, sa, sb, sc):
+        h.close()
