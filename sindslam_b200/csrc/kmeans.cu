@@ -32,21 +32,27 @@ __global__ void k_depth_half(const uint16_t *__restrict__ src, int sw, uint16_t 
 struct KmIntr { float fx, fy, cx, cy, depth_scale, depth_weight; };
 
 // DynaDetect.cc:347-369 in float32, evaluated left to right without contraction (file built with -fmad=false)
-__global__ void k_km_points(const uint16_t *__restrict__ depth, int w, int h, float s, KmIntr K, float *__restrict__ pts)
+__device__ __forceinline__ void km_point(const uint16_t *__restrict__ depth, int i, int w, float s, const KmIntr &K, float &X, float &Y, float &Z)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w * h) return;
-    int row = i / w, col = i - row * w;
-    float dfull = (float)depth[i] * s;
-    uint16_t d = (uint16_t)dfull;  // ushort depth = pyr(row,col) * scales[level]
-    float X = 0.f, Y = 0.f, Z = 0.f;
-    float df = (float)d;
+    const int row = i / w, col = i - row * w;
+    const float dfull = (float)depth[i] * s;
+    const uint16_t d = (uint16_t)dfull;  // ushort depth = pyr(row,col) * scales[level]
+    X = 0.f; Y = 0.f; Z = 0.f;
+    const float df = (float)d;
     if (!(df / K.depth_scale >= 6.0f || d == 0)) {
-        float depth2 = df * (1.0f / K.depth_scale);
+        const float depth2 = df * (1.0f / K.depth_scale);
         Z = depth2 * K.depth_weight;
         X = (((float)col - K.cx * s) * depth2) * (1.0f / (K.fx * s));
         Y = (((float)row - K.cy * s) * depth2) * (1.0f / (K.fy * s));
     }
+}
+
+__global__ void k_km_points(const uint16_t *__restrict__ depth, int w, int h, float s, KmIntr K, float *__restrict__ pts)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    float X, Y, Z;
+    km_point(depth, i, w, s, K, X, Y, Z);
     pts[3 * (size_t)i] = X;
     pts[3 * (size_t)i + 1] = Y;
     pts[3 * (size_t)i + 2] = Z;
@@ -105,29 +111,55 @@ __global__ void k_km_labels_resize(const T *__restrict__ src, int sw, int sh, in
     dst[y * dw + x] = __float2int_rn(top * (1.f - ty) + bot * ty);
 }
 
-__device__ __forceinline__ void km_block_accum(const float *__restrict__ pts, const int *__restrict__ labels, int i,
-                                               unsigned long long *s_sum, int *s_cnt, int lab)
+// Centre sums (2^-36 fixed point, exact and order independent).  A warp walks spans of KM_SPAN consecutive pixels (lane + 32 j):
+// coalesced, and the pixels one lane sees in a row lie 32 px apart on the same image rows, i.e. almost always in the same
+// cluster -- so every lane keeps a RUN (label, three 64-bit sums, count) in registers and touches shared memory only
+// when the label changes (about once per span instead of four atomics per pixel); block totals go to the level's state
+// with one global atomic per (block, cluster, component).  The back-projected point is recomputed from the u16 depth
+// (2 B per pixel instead of the 12 B of the point plane; same float expressions as k_km_points).
+struct KmRun { long long sx, sy, sz; int cnt, lab; };
+__device__ __forceinline__ void km_run_flush(KmRun &r, unsigned long long *s_sum, int *s_cnt)
 {
-    (void)labels;
-    float x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
-    atomicAdd(&s_sum[lab * 3 + 0], (unsigned long long)__double2ll_rn((double)x * KM_FIX_SCALE));
-    atomicAdd(&s_sum[lab * 3 + 1], (unsigned long long)__double2ll_rn((double)y * KM_FIX_SCALE));
-    atomicAdd(&s_sum[lab * 3 + 2], (unsigned long long)__double2ll_rn((double)z * KM_FIX_SCALE));
-    atomicAdd(&s_cnt[lab], 1);
+    if (r.cnt) {
+        atomicAdd(&s_sum[r.lab * 3 + 0], (unsigned long long)r.sx);
+        atomicAdd(&s_sum[r.lab * 3 + 1], (unsigned long long)r.sy);
+        atomicAdd(&s_sum[r.lab * 3 + 2], (unsigned long long)r.sz);
+        atomicAdd(&s_cnt[r.lab], r.cnt);
+    }
+    r.sx = r.sy = r.sz = 0; r.cnt = 0;
 }
+__device__ __forceinline__ void km_run_add(KmRun &r, int lab, float x, float y, float z, unsigned long long *s_sum, int *s_cnt)
+{
+    if (lab != r.lab) { km_run_flush(r, s_sum, s_cnt); r.lab = lab; }
+    r.sx += __double2ll_rn((double)x * KM_FIX_SCALE);
+    r.sy += __double2ll_rn((double)y * KM_FIX_SCALE);
+    r.sz += __double2ll_rn((double)z * KM_FIX_SCALE);
+    r.cnt++;
+}
+#define KM_SPAN 128
 
 // first centre pass of a level: sums of the initial labels
-__global__ void k_km_accum(const float *__restrict__ pts, const int *__restrict__ labels, int n, KmState *st)
+__global__ void k_km_accum(const uint16_t *__restrict__ depth, int w, float s, KmIntr K, const int *__restrict__ labels, int n, KmState *st)
 {
     __shared__ unsigned long long s_sum[KM_K * 3];
     __shared__ int s_cnt[KM_K];
     for (int j = threadIdx.x; j < KM_K * 3; j += blockDim.x) s_sum[j] = 0ull;
     for (int j = threadIdx.x; j < KM_K; j += blockDim.x) s_cnt[j] = 0;
     __syncthreads();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int lab = labels[i];
-        if ((unsigned)lab < (unsigned)KM_K) km_block_accum(pts, labels, i, s_sum, s_cnt, lab);
-    }
+    const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    KmRun r; r.sx = r.sy = r.sz = 0; r.cnt = 0; r.lab = 0;
+    for (int base = gw * KM_SPAN; base < n; base += nw * KM_SPAN)
+#pragma unroll 4
+        for (int j = 0; j < KM_SPAN / 32; ++j) {
+            const int i = base + j * 32 + lane;
+            if (i >= n) break;
+            const int lab = labels[i];
+            if ((unsigned)lab >= (unsigned)KM_K) continue;
+            float x, y, z;
+            km_point(depth, i, w, s, K, x, y, z);
+            km_run_add(r, lab, x, y, z, s_sum, s_cnt);
+        }
+    km_run_flush(r, s_sum, s_cnt);
     __syncthreads();
     for (int j = threadIdx.x; j < KM_K * 3; j += blockDim.x)
         if (s_sum[j]) atomicAdd(&st->sums[0][j], s_sum[j]);
@@ -136,7 +168,7 @@ __global__ void k_km_accum(const float *__restrict__ pts, const int *__restrict_
 }
 
 // assignment (argmin of float32 squared distance, first minimum wins) fused with the next centre pass
-__global__ void k_km_assign_accum(const float *__restrict__ pts, int *__restrict__ labels, int n, KmState *st, int it)
+__global__ void k_km_assign_accum(const uint16_t *__restrict__ depth, int w, float s, KmIntr K, int *__restrict__ labels, int n, KmState *st, int it)
 {
     if (st->done) return;
     __shared__ unsigned long long s_sum[KM_K * 3];
@@ -145,24 +177,29 @@ __global__ void k_km_assign_accum(const float *__restrict__ pts, int *__restrict
     for (int j = threadIdx.x; j < KM_K * 3; j += blockDim.x) { s_sum[j] = 0ull; s_c[j] = st->centers[j]; }
     for (int j = threadIdx.x; j < KM_K; j += blockDim.x) s_cnt[j] = 0;
     __syncthreads();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
-        float best = 0.f;
-        int lab = 0;
+    const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    KmRun r; r.sx = r.sy = r.sz = 0; r.cnt = 0; r.lab = 0;
+    for (int base = gw * KM_SPAN; base < n; base += nw * KM_SPAN)
+#pragma unroll 2
+        for (int j = 0; j < KM_SPAN / 32; ++j) {
+            const int i = base + j * 32 + lane;
+            if (i >= n) break;
+            float x, y, z;
+            km_point(depth, i, w, s, K, x, y, z);
+            float best = 0.f;
+            int lab = 0;
 #pragma unroll
-        for (int k = 0; k < KM_K; ++k) {
-            float d0 = x - s_c[3 * k], d1 = y - s_c[3 * k + 1], d2 = z - s_c[3 * k + 2];
-            float dist = d0 * d0;
-            dist = dist + d1 * d1;
-            dist = dist + d2 * d2;
-            if (k == 0 || dist < best) { best = dist; lab = k; }
+            for (int k = 0; k < KM_K; ++k) {
+                float d0 = x - s_c[3 * k], d1 = y - s_c[3 * k + 1], d2 = z - s_c[3 * k + 2];
+                float dist = d0 * d0;
+                dist = dist + d1 * d1;
+                dist = dist + d2 * d2;
+                if (k == 0 || dist < best) { best = dist; lab = k; }
+            }
+            labels[i] = lab;
+            km_run_add(r, lab, x, y, z, s_sum, s_cnt);
         }
-        labels[i] = lab;
-        atomicAdd(&s_sum[lab * 3 + 0], (unsigned long long)__double2ll_rn((double)x * KM_FIX_SCALE));
-        atomicAdd(&s_sum[lab * 3 + 1], (unsigned long long)__double2ll_rn((double)y * KM_FIX_SCALE));
-        atomicAdd(&s_sum[lab * 3 + 2], (unsigned long long)__double2ll_rn((double)z * KM_FIX_SCALE));
-        atomicAdd(&s_cnt[lab], 1);
-    }
+    km_run_flush(r, s_sum, s_cnt);
     __syncthreads();
     const int b = (it + 1) & 1;
     for (int j = threadIdx.x; j < KM_K * 3; j += blockDim.x)
@@ -227,27 +264,33 @@ __global__ void __launch_bounds__(1024) k_km_finalize(const float *__restrict__ 
         }
         __syncthreads();
     }
+    // centres, centre shift and the stop decision: one thread per cluster (same operations and order per cluster as the serial loop)
+    __shared__ double s_dist[KM_K];
+    if (threadIdx.x < KM_K) {
+        const int k = threadIdx.x;
+        const float scale = 1.f / (float)counts[k];
+        double dist = 0.0;
+        for (int j = 0; j < 3; ++j) {
+            const float c = (float)((double)sums[k * 3 + j] * (1.0 / KM_FIX_SCALE)) * scale;
+            st->centers[k * 3 + j] = c;
+            const double t = (double)c - (double)st->old[k * 3 + j];
+            dist += t * t;
+        }
+        s_dist[k] = dist;
+        st->final_counts[k] = counts[k];
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         double shift = 0.0;
-        for (int k = 0; k < KM_K; ++k) {
-            float scale = 1.f / (float)counts[k];
-            double dist = 0.0;
-            for (int j = 0; j < 3; ++j) {
-                float c = (float)((double)sums[k * 3 + j] * (1.0 / KM_FIX_SCALE)) * scale;
-                st->centers[k * 3 + j] = c;
-                double t = (double)c - (double)st->old[k * 3 + j];
-                dist += t * t;
-            }
-            if (it > 0 && dist > shift) shift = dist;
-        }
-        bool last = (it + 1 == max_iter) || (it > 0 && shift <= eps2);
-        for (int k = 0; k < KM_K; ++k) st->final_counts[k] = counts[k];
+        for (int k = 0; k < KM_K; ++k)
+            if (it > 0 && s_dist[k] > shift) shift = s_dist[k];
+        const bool last = (it + 1 == max_iter) || (it > 0 && shift <= eps2);
         if (last) st->done = 1;
         st->iters = it + 1;
-        // zero the accumulators of the next centre pass
-        for (int j = 0; j < KM_K * 3; ++j) st->sums[b ^ 1][j] = 0ull;
-        for (int j = 0; j < KM_K; ++j) st->counts[b ^ 1][j] = 0;
     }
+    // zero the accumulators of the next centre pass
+    if (threadIdx.x < KM_K * 3) st->sums[b ^ 1][threadIdx.x] = 0ull;
+    if (threadIdx.x < KM_K) st->counts[b ^ 1][threadIdx.x] = 0;
 }
 
 __global__ void k_i32_to_u8(const int *__restrict__ src, uint8_t *__restrict__ dst, int n)
@@ -352,11 +395,11 @@ int kmeans_run(sindyn_base *ctx, KmeansStage *k, const uint16_t *depth, const ui
             float fx = (float)(1.0 / ((double)w / (double)k->lw[l + 1])), fy = (float)(1.0 / ((double)h / (double)k->lh[l + 1]));
             LAUNCH(ctx, k_km_labels_resize<int>, grd, blk, 0, k->labels[l + 1], k->lw[l + 1], k->lh[l + 1], k->labels[l], w, h, fx, fy);
         }
-        int nblk = min(cdiv(n, 256), SINDYN_NUM_SMS_B200 * 4);
-        LAUNCH(ctx, k_km_accum, nblk, 256, 0, pts, k->labels[l], n, st);
+        int nblk = min(cdiv(n, KM_SPAN * 8), SINDYN_NUM_SMS_B200 * 8);     // 8 warps per block, one span per warp and trip
+        LAUNCH(ctx, k_km_accum, nblk, 256, 0, k->depth_pyr[l], w, scales[l], K, k->labels[l], n, st);
         for (int it = 0; it < 4; ++it) {
             LAUNCH(ctx, k_km_finalize, 1, 1024, 0, pts, k->labels[l], n, st, it, 4, 0.07 * 0.07);
-            if (it < 3) LAUNCH(ctx, k_km_assign_accum, nblk, 256, 0, pts, k->labels[l], n, st, it);
+            if (it < 3) LAUNCH(ctx, k_km_assign_accum, nblk, 256, 0, k->depth_pyr[l], w, scales[l], K, k->labels[l], n, st, it);
         }
     }
     const int N = k->W * k->H;
