@@ -475,6 +475,10 @@ def run_ours(args):
 
 
 def main():
+    # torchrun exports OMP_NUM_THREADS=1; the CPU legs (cpu_baseline on rank 0, --impl reference) use all host threads at every N,
+    # so that their figures are comparable across N.  Must happen before torch / cv2 / the OpenMP oracle load their runtimes.
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and int(os.environ.get("RANK", "0")) == 0:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
