@@ -57,8 +57,11 @@ static int check_capacity(sindyn_ctx *c)
     int sc[4];
     CU_CHECK(c, cudaMemcpyAsync(&ctl, c->rc.ctl, sizeof ctl, cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaMemcpyAsync(sc, c->edges.scalars, sizeof sc, cudaMemcpyDeviceToHost, c->stream));
+    int peac_hdr[4] = {0, 0, 0, 0};
+    if (c->cfg.plane_edges && c->peac.built) SD_CHECK(peac_copy_header(c, &c->peac, peac_hdr));
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     flow_collect_flag(c);
+    if (peac_hdr[2]) { c->err = "plane fitter: a fixed-capacity list overflowed (> 64 planes, > 512 neighbours of one node, or a region-growing level > 131072 entries)"; return SINDYN_ERR_CAPACITY; }
     if (ctl.overflow) { c->err = "recluster: more than RC_MAXC components"; return SINDYN_ERR_CAPACITY; }
     if (ctl.pf_overflow) { c->err = "plane-edge filter: more than RC_PF_MAXC contours"; return SINDYN_ERR_CAPACITY; }
     if (sc[3]) { c->err = "depth_edges: more than EDGE_EP_CAP candidate end points"; return SINDYN_ERR_CAPACITY; }

@@ -1435,6 +1435,13 @@ int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t 
     return plane_contours_run(ctx, rc, im->PB, &im->ctl->n_final, plane_edges_out);
 }
 
+int peac_copy_header(sindyn_base *ctx, PeacStage *p, int *host4)
+{
+    PeacImpl *im = (PeacImpl *)p->impl;
+    CU_CHECK(ctx, cudaMemcpyAsync(host4, im->ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return SINDYN_OK;
+}
+
 int peac_get_debug(sindyn_base *ctx, PeacStage *p, int *label_out, int *planes_rid_n, int *n_planes, int *n_final)
 {
     PeacImpl *im = (PeacImpl *)p->impl;

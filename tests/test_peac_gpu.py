@@ -59,3 +59,39 @@ def test_detect_with_plane_edges_mask_iou(seq_c1):
         assert np.array_equal(mask, r["mask"]) and np.array_equal(label, r["label"]), k     # free-running state on both sides
     assert min(ious) >= 0.99
     s.close()
+
+
+def _crafted_depth(kind, W=640, H=480, factor=5000.0, seed=5):
+    rng = np.random.default_rng(seed)
+    u, v = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    if kind == "wall":            # one slanted plane filling the image: a single graph component of 1200 blocks
+        z = 2.0 + 0.4 * u / W + 0.1 * v / H
+    elif kind == "corner":        # two walls meeting at a vertical edge + a floor
+        z = np.where(u < W * 0.45, 1.5 + 1.2 * (W * 0.45 - u) / W, 1.5 + 0.9 * (u - W * 0.45) / W)
+        z = np.where(v > H * 0.7, np.minimum(z, 1.0 + 2.5 * (H - v) / H), z)
+    else:                         # "steps": many small fronto-parallel patches (lots of small components, nothing reaches minSupport in places)
+        z = 1.0 + 0.25 * ((u // 48).astype(int) % 5) + 0.2 * ((v // 40).astype(int) % 3)
+    z = z + rng.normal(0, 0.0015, z.shape)
+    d = np.clip(np.rint(z * factor), 0, 65535).astype(np.uint16)
+    d[rng.random(d.shape) < 0.0002] = 0
+    return d
+
+
+@pytest.mark.parametrize("kind", ["wall", "corner", "steps"])
+def test_plane_edges_crafted_scenes(kind):
+    """Extremes of the block graph: ONE component that covers the whole image (the longest serial chain, the widest
+    candidate lists), two large planes meeting, and a scene of many small patches -- still bit-exact."""
+    from sindslam_b200.capi import SinDyn
+    cam = synth.TUM3
+    depth = _crafted_depth(kind)
+    sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=1)
+    got = sd.plane_edges(depth)
+    dbg = sd.peac_debug()
+    ref_dbg = {}
+    ref = po.plane_edges(depth, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, ref_dbg)
+    print(kind, "planes", ref_dbg["coarse"], "->", ref_dbg["n"], ref_dbg.get("stats"))
+    assert [(int(r), int(n)) for r, n, _ in dbg["planes"]] == ref_dbg["coarse"]
+    assert dbg["n_final"] == ref_dbg["n"]
+    assert np.array_equal(dbg["member"], ref_dbg["member"])
+    assert np.array_equal(got, ref)
+    sd.close()
