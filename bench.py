@@ -297,6 +297,51 @@ def roofline_per_stage(ms, peak):
     return out
 
 
+def multi_sequence_stats(cam, device, n_seq=4, n_frames=76, steps=4):
+    """Batched throughput on ONE GPU ('report both single-frame latency and batched throughput'): n_seq independent
+    sequences, one detector + extractor handle, stream and host thread each, frames resident, the same full per-frame path as
+    the headline.  A single sequence leaves most of the chip idle (serial chains on one or a few SMs), so sequences overlap."""
+    import torch
+    from sindslam_b200 import synth
+    from sindslam_b200.capi import Orb, SinDyn
+    hs = []
+    for s in range(n_seq):
+        _, fr = synth.make_sequence_parallel(n_frames, cam, seq=200 + s, kind="box", start=0, hole_rate=HOLE_RATE)
+        sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=device, refine=1, plane_edges=1)
+        orb = Orb(*ORB_CFG, cam.width, cam.height, device=device)
+        st = torch.cuda.Stream(device=device)
+        sd.set_stream(st.cuda_stream)
+        for i, f in enumerate(fr):
+            sd.upload_frame(i, f.bgr, f.depth)
+        sd.set_prev_frames(fr[0].bgr, fr[0].bgr)
+        hs.append((sd, orb))
+    order = frame_order(n_frames, (steps + 1) * FRAMES_PER_STEP)
+
+    def work(h, a, b):
+        for j in range(a, b):
+            h[1].track_frame_resident(h[0], order[j], j)
+        h[0].synchronize()
+
+    def run(a, b):
+        th = [threading.Thread(target=work, args=(h, a, b)) for h in hs]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+
+    run(0, FRAMES_PER_STEP)                         # warm-up: graph capture, first frames
+    t0 = time.perf_counter()
+    run(FRAMES_PER_STEP, (steps + 1) * FRAMES_PER_STEP)
+    dt = time.perf_counter() - t0
+    for sd, orb in hs:
+        orb.track_results(sd)
+        orb.close()
+        sd.close()
+    return {"sequences_per_gpu": n_seq, "pairs_per_s": n_seq * steps * FRAMES_PER_STEP / dt, "frames_per_sequence": steps * FRAMES_PER_STEP,
+            "note": "same full per-frame path as the headline, n_seq concurrent sequences on one GPU, host wall clock"}
+
+
 def run_ours(args):
     import torch
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
@@ -437,6 +482,7 @@ def run_ours(args):
             ms = stage_profile(cam, frames, local)
             extras["stage_ms_device"] = ms
             extras["roofline_per_stage"] = roofline_per_stage(ms, peak)
+            extras["multi_sequence"] = multi_sequence_stats(cam, local) if world == 1 else None
             cpu_v, cpu_n, cpu_dt = cpu_full_pipeline(frames, cam, "brox", "fx", budget_s=15.0, max_pairs=40)
             extras["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                       "sample": f"{cpu_n} frame pairs in {cpu_dt:.1f} s through the full oracle pipeline (oracle/brox_cpu.c OpenMP Brox + cv2 "
