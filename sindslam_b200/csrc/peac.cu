@@ -262,6 +262,7 @@ struct MergeResult { double st[9], c[3], n[3], mse; };
 #define PEAC_AHC_NT 256   // threads of k_peac_ahc (a power of two: node b is owned by thread b & (PEAC_AHC_NT - 1))
 #define PEAC_BATCH 4      // queue heads processed per round (PEAC_AHC_NT / PEAC_BATCH threads evaluate the candidates of one of them)
 #define PEAC_CANDK 512    // distinct graph neighbours of one node
+#define PEAC_WTOP 3        // queue heads every warp contributes to the selection of a round (8 warps x 3 <= 32 lanes)
 #define PEAC_AHC_CTAS 32  // CTAs of k_peac_ahc: one connected component of the block graph each (more components: round robin)
 
 // Edges exist only between blocks of one connected component of the initial graph and every later edge is inherited from
@@ -430,8 +431,8 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
         if (tid < PEAC_BATCH) { s_ncand[tid] = 0; s_guard[tid] = 0; }
         int round_id = 0;
         // arg-min state of this thread over the nodes it owns (b = tid, tid + nt, ...): recomputed only after one of them changed
-        unsigned long long my_key = ~0ull;   // order-preserving bit pattern of the mse (peac_key)
-        int my_p = -1, my_s = 0x7fffffff;
+        unsigned long long my_key = ~0ull, my_key2 = ~0ull;   // order-preserving bit pattern of the mse (peac_key): best, second best
+        int my_p = -1, my_s = 0x7fffffff, my_p2 = -1, my_s2 = 0x7fffffff;
         bool my_dirty = true;
         // lexicographic (mse bits, seq) minimum of the warp with three hardware reductions; seq is unique
         auto warp_argmin = [&](unsigned long long key, int sq, int node) -> int {
@@ -466,47 +467,57 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                         if (root[b2] == lose) root[b2] = (unsigned short)win;
                 }
             }
-            if (my_dirty) {
+            if (my_dirty) {     // best and second best of the nodes this thread owns, one pass
                 my_key = ~0ull; my_p = -1; my_s = 0x7fffffff;
+                my_key2 = ~0ull; my_p2 = -1; my_s2 = 0x7fffffff;
                 for (int b2 = tid; b2 < NB; b2 += nt)
                     if ((flags[b2] & (PF_ALIVE | PF_QUEUED)) == (PF_ALIVE | PF_QUEUED)) {
                         const unsigned long long kb = peac_key(mse_a[b2]);
                         const int sq = seq_a[b2];
-                        if (kb < my_key || (kb == my_key && sq < my_s)) { my_key = kb; my_p = b2; my_s = sq; }
+                        if (kb < my_key || (kb == my_key && sq < my_s)) {
+                            my_key2 = my_key; my_p2 = my_p; my_s2 = my_s;
+                            my_key = kb; my_p = b2; my_s = sq;
+                        } else if (kb < my_key2 || (kb == my_key2 && sq < my_s2)) { my_key2 = kb; my_p2 = b2; my_s2 = sq; }
                     }
                 my_dirty = false;
             }
-            // ---- the two smallest (mse, seq) of every warp (the lane that gave the first rescans its nodes without it) ...
+            // ---- the PEAC_WTOP smallest (mse, seq) of every warp: a lane that gave its best continues with its second best
+            // (a lane that has to give a third rescans its nodes; rare) ...
             {
-                unsigned long long k1 = my_key;
-                int p1 = my_p, s1 = my_s;
+                unsigned long long k1 = my_key, k2 = my_key2;
+                int p1 = my_p, s1 = my_s, p2 = my_p2, s2 = my_s2, given = 0, g0 = -1, g1 = -1;
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
+                for (int r = 0; r < PEAC_WTOP; ++r) {
                     const int wl = warp_argmin(k1, s1, p1);
                     const int src = wl >= 0 ? wl : 0;
                     const unsigned long long k0 = __shfl_sync(0xffffffffu, k1, src);
                     const int p0 = __shfl_sync(0xffffffffu, p1, src), s0 = __shfl_sync(0xffffffffu, s1, src);
                     if (lane == 0) { w4_key[wid][r] = k0; w4_p[wid][r] = wl >= 0 ? p0 : -1; w4_seq[wid][r] = s0; }
-                    if (r == 0 && wl >= 0 && lane == wl) {
-                        const int taken = p1;
-                        k1 = ~0ull; p1 = -1; s1 = 0x7fffffff;
-                        for (int b2 = tid; b2 < NB; b2 += nt)
-                            if (b2 != taken && (flags[b2] & (PF_ALIVE | PF_QUEUED)) == (PF_ALIVE | PF_QUEUED)) {
-                                const unsigned long long kb = peac_key(mse_a[b2]);
-                                const int sq = seq_a[b2];
-                                if (kb < k1 || (kb == k1 && sq < s1)) { k1 = kb; p1 = b2; s1 = sq; }
-                            }
+                    if (r + 1 < PEAC_WTOP && wl >= 0 && lane == wl) {
+                        if (given == 0) { g0 = p1; k1 = k2; p1 = p2; s1 = s2; given = 1; }
+                        else {
+                            g1 = p1; given = 2;
+                            k1 = ~0ull; p1 = -1; s1 = 0x7fffffff;
+                            for (int b2 = tid; b2 < NB; b2 += nt)
+                                if (b2 != g0 && b2 != g1 && (flags[b2] & (PF_ALIVE | PF_QUEUED)) == (PF_ALIVE | PF_QUEUED)) {
+                                    const unsigned long long kb = peac_key(mse_a[b2]);
+                                    const int sq = seq_a[b2];
+                                    if (kb < k1 || (kb == k1 && sq < s1)) { k1 = kb; p1 = b2; s1 = sq; }
+                                }
+                        }
                     }
                 }
             }
             __syncthreads();
-            // ---- ... and of the CTA: every warp merges the 16 warp entries (lane l < 16 holds entry l).  Beyond a warp's second
-            // entry its third is unknown, so the merged order is provably the queue order only up to and including the first
-            // "second entry" taken: the batch ends there.
+            // ---- ... and of the CTA: every warp merges the 8 x PEAC_WTOP warp entries (lane l holds entry l).  Beyond a warp's
+            // last entry its next one is unknown, so the merged order is provably the queue order only up to and including the
+            // first "last entry" taken: the batch ends there.
             int P[PEAC_BATCH], npk = 0;
             {
-                unsigned long long k1 = lane < 16 ? w4_key[lane >> 1][lane & 1] : ~0ull;
-                int p1 = lane < 16 ? w4_p[lane >> 1][lane & 1] : -1, s1 = lane < 16 ? w4_seq[lane >> 1][lane & 1] : 0x7fffffff;
+                const bool has = lane < (PEAC_AHC_NT / 32) * PEAC_WTOP;
+                const int ew = lane / PEAC_WTOP, er = lane - ew * PEAC_WTOP;
+                unsigned long long k1 = has ? w4_key[ew][er] : ~0ull;
+                int p1 = has ? w4_p[ew][er] : -1, s1 = has ? w4_seq[ew][er] : 0x7fffffff;
                 bool open = true;
 #pragma unroll
                 for (int r = 0; r < PEAC_BATCH; ++r) {
@@ -516,7 +527,7 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                         P[r] = __shfl_sync(0xffffffffu, p1, wl);
                         if (lane == wl) p1 = -1;
                         npk = r + 1;
-                        if (wl & 1) open = false;     // a warp's second entry: nothing after it is certain
+                        if (wl % PEAC_WTOP == PEAC_WTOP - 1) open = false;     // a warp's last entry: nothing after it is certain
                     } else open = false;
                 }
             }
@@ -596,15 +607,9 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                     }
                 }
             }
-            {   // best of the warp (a batch node's threads are two whole warps)
-                double wb = best, wc = bc2;
-                int wo = best_o;
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double om = __shfl_xor_sync(0xffffffffu, wb, off), oc = __shfl_xor_sync(0xffffffffu, wc, off);
-                    const int oo = __shfl_xor_sync(0xffffffffu, wo, off);
-                    if (oo >= 0 && (wo < 0 || om < wb || (om == wb && oo < wo))) { wb = om; wo = oo; wc = oc; }
-                }
-                if (lane == 0) { ws_mse[slot_j][wid & 1] = wb; ws_o[slot_j][wid & 1] = wo; ws_c2[slot_j][wid & 1] = wc; }
+            {   // best of the warp (a batch node's threads are two whole warps): three integer warp reductions on the order-preserving key
+                const int wl = warp_argmin(peac_key(best), best_o, best_o);      // ties in the MSE: the smaller node id
+                if (wl >= 0 ? lane == wl : lane == 0) { ws_mse[slot_j][wid & 1] = best; ws_o[slot_j][wid & 1] = wl >= 0 ? best_o : -1; ws_c2[slot_j][wid & 1] = bc2; }
             }
             __syncthreads();
             PCLK(5);   // candidate evaluation + warp reduction
