@@ -818,7 +818,8 @@ __global__ void k_peac_init_labels(const PeacControl *__restrict__ ctl, int W, i
 //     visits that append to the queue;
 //   * phase C: the flagged visits, compacted in key order, are the next level -- the same sequence the serial queue holds.
 // ~200 levels per frame, one 1024-thread CTA (the levels are a dependent chain; a level is 1-10 k entries).
-#define PG_NT 1024
+#define PG_NT 512             // threads per CTA of the cluster kernel (PG_U visits each: 128 registers)
+#define PG_U 4
 __device__ __forceinline__ int pg_block_scan(int v, int *s_warp, int &total)
 {
     // exclusive scan of v over the CTA (PG_NT threads); all threads must call
@@ -854,18 +855,21 @@ __device__ __forceinline__ int pg_block_scan(int v, int *s_warp, int &total)
 // bypass L1); as soon as a level fits the shared-memory path the frontier is handed to the single-CTA kernel below.
 #define PG_CL 16                // CTAs of the cluster (non-portable size: opted in at init)
 #define PG_SCAP 2048
+#define PG_HAND 1024           // levels of at most PG_HAND entries are handed to the single-CTA kernel
 #define PG_FNT 1024            // threads of the single-CTA kernel (levels of a few hundred entries: more warps only add barrier and scan overhead)
 struct __align__(16) PgRec { int pix, info, next; float dist; };   // one visit: target pixel (-1: none), plane | ok << 8 | push << 9, list link, distance
 
 __global__ void __launch_bounds__(PG_NT)
 k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy, float inv_scale, int Nw, int Nh,
-                    PeacControl *ctl, int *member, float *dist, int *head, int *qa, int *qb, PgRec *rec)
+                    PeacControl *ctl, int *member, float *dist, int *head, int *qa, int *qb, PgRec *rec, float *curd)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ int s_blk[PEAC_MAXB];
     __shared__ double s_pn[PEAC_MAXP][3], s_pc[PEAC_MAXP][3], s_thr[PEAC_MAXP];
     __shared__ int s_warp[33];
+    __shared__ int s_tot, s_base[2];
+    __shared__ unsigned long long s_conn[PEAC_MAXP];    // plane adjacency found by this CTA (every boundary pixel would hit the same two global words)
     const int tid = threadIdx.x, NB = Nw * Nh, rank = (int)cluster.block_rank();
     const int g = rank * PG_NT + tid, G = PG_CL * PG_NT;
     const int np = ctl->n_planes;
@@ -873,6 +877,7 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
     for (int k = tid; k < np; k += PG_NT) {
         for (int d = 0; d < 3; ++d) { s_pn[k][d] = ctl->pl[k].normal[d]; s_pc[k][d] = ctl->pl[k].center[d]; }
         s_thr[k] = ctl->pl[k].thr;
+        s_conn[k] = 0ull;
     }
     __syncthreads();
     // ---- seeds in the order of findBlockMembership (AHCPlaneFitter.hpp:660-703): blocks in raster order, per block the run
@@ -880,9 +885,12 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
     int *cur = qa, *nxt = qb;
     int n = 0;
     {
-        int cnt[2] = {0, 0}, offs[2];
-        for (int r = 0; r < 2; ++r) {
-            const int b = tid * 2 + r;
+        constexpr int SB = (PEAC_MAXB + PG_NT - 1) / PG_NT;      // consecutive blocks per thread
+        int cnt[SB], offs[SB];
+#pragma unroll
+        for (int r = 0; r < SB; ++r) {
+            const int b = tid * SB + r;
+            cnt[r] = 0;
             if (b < NB) {
                 const int i = b / Nw, j = b - i * Nw, m = s_blk[b];
                 const bool top = i > 0 && (m < 0 ? s_blk[b - Nw] >= 0 : s_blk[b - Nw] != m);
@@ -891,12 +899,18 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
             }
         }
         int total;
-        const int base = pg_block_scan(cnt[0] + cnt[1], s_warp, total);
-        offs[0] = base; offs[1] = base + cnt[0];
+        int mine = 0;
+#pragma unroll
+        for (int r = 0; r < SB; ++r) mine += cnt[r];
+        const int base = pg_block_scan(mine, s_warp, total);
+        offs[0] = base;
+#pragma unroll
+        for (int r = 1; r < SB; ++r) offs[r] = offs[r - 1] + cnt[r - 1];
         n = total;
         if (rank == 0 && n <= PG_CAP)
-            for (int r = 0; r < 2; ++r) {
-                const int b = tid * 2 + r;
+#pragma unroll
+            for (int r = 0; r < SB; ++r) {
+                const int b = tid * SB + r;
                 if (b >= NB || !cnt[r]) continue;
                 const int i = b / Nw, j = b - i * Nw, m = s_blk[b];
                 int o = offs[r];
@@ -929,95 +943,155 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
 #else
 #define GCLK(i) do { } while (0)
 #endif
-    while (n > PG_SCAP && n <= PG_CAP) {
+    // Every phase is a chain of L2 round trips (~800 cycles each) and cluster barriers (~600 cycles, ~1500 after global stores), so
+    // a thread works on PG_U visits at a time with the loads of all of them in flight together; a level of up to PG_U * G
+    // visits (practically every level) is ONE batch, and then the thread's own visit records stay in registers between the
+    // phases.
+    while (n > PG_HAND && n <= PG_CAP) {
         ++levels; entries += n;
-        // ---- phase A: one entry per thread (n <= G for every level seen so far; the loop covers the rest)
-        for (int e = g; e < n; e += G) {
-            const int ent = __ldcg(&cur[e]);
-            const int s = ent & 0xfffff, plid = ent >> 20;
-            const int sy = s / W, sx = s - sy * W;
-            int cc[4], link[4];
-            unsigned dv[4];
+        const int nk = 4 * n;
+        const bool single = nk <= PG_U * G;
+        int oc[PG_U], oi[PG_U], ol[PG_U];      // own visit records of the (last) batch: pixel, info, link
+        float od[PG_U], ocur[PG_U];             // point-plane distance, distMap of the target pixel
+        // ---- phase A: one thread per visit (key = 4 * queue rank + direction).  The membership and the distance of the target
+        // pixel only change in phase B, so they are fetched here, together with the depth and the list link: ONE L2 round trip
+        for (int v0 = g; v0 < nk; v0 += PG_U * G) {
+            int ent[PG_U];
+            unsigned dv[PG_U];
+            int tr[PG_U];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const bool ex = q == 0 ? sx > 0 : (q == 1 ? sx < W - 1 : (q == 2 ? sy > 0 : sy < H - 1));
-                cc[q] = -1; link[q] = -1; dv[q] = 0;
-                if (ex) {
+            for (int j = 0; j < PG_U; ++j) {
+                const int v = v0 + j * G;
+                ent[j] = v < nk ? __ldcg(&cur[v >> 2]) : -1;
+            }
+#pragma unroll
+            for (int j = 0; j < PG_U; ++j) {
+                const int v = v0 + j * G, q = v & 3;
+                int c = -1;
+                if (ent[j] >= 0) {
+                    const int s = ent[j] & 0xfffff;
+                    const int sy = s / W, sx = s - sy * W;
                     const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
-                    const int bx = ccx / PEAC_WIN, by = ccy / PEAC_WIN;
-                    if (!(bx < Nw && by < Nh && s_blk[by * Nw + bx] >= 0)) {
-                        cc[q] = ccy * W + ccx;
-                        link[q] = atomicExch(&head[cc[q]], e * 4 + q);
-                        dv[q] = depth[cc[q]];
+                    if (ccx >= 0 && ccx < W && ccy >= 0 && ccy < H) {
+                        const int bx = ccx / PEAC_WIN, by = ccy / PEAC_WIN;
+                        if (!(bx < Nw && by < Nh && s_blk[by * Nw + bx] >= 0)) c = ccy * W + ccx;
                     }
+                }
+                oc[j] = c; ol[j] = -1; dv[j] = 0; tr[j] = 0; ocur[j] = 0.0f;
+                if (c >= 0) {
+                    ol[j] = atomicExch(&head[c], v);
+                    dv[j] = depth[c];
+                    tr[j] = __ldcg(&member[c]);
+                    ocur[j] = __ldcg(&dist[c]);
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
-                const float df = (float)dv[q];
+            for (int j = 0; j < PG_U; ++j) {
+                const int v = v0 + j * G, c = oc[j];
+                if (v >= nk) continue;
+                if (c < 0) { rec[v].pix = -1; continue; }
+                const int plid = ent[j] >> 20;
+                const int ccy = c / W, ccx = c - ccy * W;
+                const float df = (float)dv[j];
                 const float z = df * inv_scale;
                 const double P0 = ((float)ccx - cx) * z / fx, P1 = ((float)ccy - cy) * z / fy, P2 = z;
                 const float cd = (float)fabs(s_pn[plid][0] * (P0 - s_pc[plid][0]) + s_pn[plid][1] * (P1 - s_pc[plid][1]) + s_pn[plid][2] * (P2 - s_pc[plid][2]));
-                const bool has = !(df < 1e-3f);
-                const bool ok = has && (double)cd * (double)cd < s_thr[plid];
-                PgRec r;
-                r.pix = cc[q]; r.info = plid | (ok ? 256 : 0); r.next = link[q]; r.dist = has ? cd : -1.0f;
-                rec[e * 4 + q] = r;
+                const bool ok = !(df < 1e-3f) && (double)cd * (double)cd < s_thr[plid];
+                oi[j] = plid | (ok ? 256 : 0) | ((tr[j] + 6) << 16);
+                od[j] = cd;
+                int4 r;
+                r.x = c; r.y = oi[j]; r.z = ol[j]; r.w = __float_as_int(cd);
+                reinterpret_cast<int4 *>(rec)[v] = r;
+                if (!single) curd[v] = ocur[j];
             }
         }
         cluster.sync();
         GCLK(0);
-        // ---- phase B: one owner per visited pixel replays its visits in queue order; the loads of up to four keys of a thread
-        // are issued together
-        for (int k0 = g; k0 < 4 * n; k0 += 4 * G) {
-            PgRec r[4];
-            int tr[4], hd[4];
-            float dd[4];
+        // ---- phase B: the visit linked first owns the pixel.  It walks the pixel's list ONCE (a dependent chain of L2 loads, one
+        // per further visit; the chains of the thread's PG_U visits advance together), sorts the <= 4 visits by key in
+        // registers and replays them in queue order
+        for (int v0 = g; v0 < nk; v0 += PG_U * G) {
+            if (!single) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int key = k0 + j * G;
-                r[j].pix = -1; r[j].next = 0;
-                if (key < 4 * n) {
-                    const int4 v = __ldcg(reinterpret_cast<const int4 *>(rec) + key);
-                    r[j].pix = v.x; r[j].info = v.y; r[j].next = v.z; r[j].dist = __int_as_float(v.w);
+                for (int j = 0; j < PG_U; ++j) {
+                    const int v = v0 + j * G;
+                    oc[j] = -1;
+                    if (v < nk) {
+                        const int4 t = __ldcg(reinterpret_cast<const int4 *>(rec) + v);
+                        oc[j] = t.x; oi[j] = t.y; ol[j] = t.z; od[j] = __int_as_float(t.w);
+                        ocur[j] = __ldcg(&curd[v]);
+                    }
                 }
             }
+            int w[PG_U], h0[PG_U];
+            // visits of the pixel: key << 10 | (plane | ok << 8), distance; slot 0 is filled from the list head
+            int KI[PG_U][4];
+            float DD[PG_U][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool own = r[j].pix >= 0 && r[j].next == -1;
-                const int c = own ? r[j].pix : 0;
-                tr[j] = own ? __ldcg(&member[c]) : 0;
-                dd[j] = own ? __ldcg(&dist[c]) : 0.0f;
-                hd[j] = own ? __ldcg(&head[c]) : -1;
+            for (int j = 0; j < PG_U; ++j) {
+                const bool owner = oc[j] >= 0 && ol[j] == -1;
+                h0[j] = owner ? __ldcg(&head[oc[j]]) : -1;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { KI[j][r] = 0x7fffffff; DD[j][r] = 0.0f; }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (!(r[j].pix >= 0 && r[j].next == -1)) continue;      // the visit linked first (list tail) owns the pixel
-                const int c = r[j].pix;
-                int trail = tr[j];
-                float d = dd[j];
-                const int h0 = hd[j];
-                head[c] = -1;
-                int last = -1;
-                for (;;) {
-                    if (trail <= -6) break;
-                    int k = 0x7fffffff;
-                    for (int w = h0; w >= 0; w = __ldcg(&rec[w].next))
-                        if (w > last && w < k) k = w;
-                    if (k == 0x7fffffff) break;
-                    last = k;
-                    const int info = __ldcg(&rec[k].info), plid = info & 255;
-                    if (trail >= 0 && trail == plid) continue;
+            for (int j = 0; j < PG_U; ++j) {
+                w[j] = h0[j];
+                if (h0[j] >= 0) head[oc[j]] = -1;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int4 t[PG_U];
+#pragma unroll
+                for (int j = 0; j < PG_U; ++j) {
+                    const int v = v0 + j * G;
+                    t[j].x = 0; t[j].y = 0; t[j].z = -1; t[j].w = 0;
+                    if (w[j] >= 0) {
+                        if (w[j] == v) { t[j].y = oi[j]; t[j].z = -1; t[j].w = __float_as_int(od[j]); }
+                        else t[j] = __ldcg(reinterpret_cast<const int4 *>(rec) + w[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < PG_U; ++j)
+                    if (w[j] >= 0) { KI[j][r] = (w[j] << 10) | (t[j].y & 0x1ff); DD[j][r] = __int_as_float(t[j].w); w[j] = t[j].z; }
+            }
+#pragma unroll
+            for (int j = 0; j < PG_U; ++j) {
+                if (h0[j] < 0) continue;
+                const int c = oc[j];
+                int trail = (oi[j] >> 16) - 6;
+                float d = ocur[j];
+                auto visit = [&](int k, int info, float cd) {       // the reference's per-visit state machine (AHCPlaneFitter.hpp:563-590)
+                    const int plid = info & 255;
+                    if (trail >= 0 && trail == plid) return;
                     if (info & 256) {
                         if (trail >= 0) {
                             const double sm = fabs(s_pn[plid][0] * s_pn[trail][0] + s_pn[plid][1] * s_pn[trail][1] + s_pn[plid][2] * s_pn[trail][2]);
-                            if (sm >= PEAC_SIM_REFINE) { atomicOr(&ctl->conn[trail], 1ull << plid); atomicOr(&ctl->conn[plid], 1ull << trail); }
+                            if (sm >= PEAC_SIM_REFINE && !((s_conn[trail] >> plid) & 1ull)) { atomicOr(&s_conn[trail], 1ull << plid); atomicOr(&s_conn[plid], 1ull << trail); }
                         }
-                        const float cd = __ldcg(&rec[k].dist);
-                        if (cd < d) { trail = plid; d = cd; rec[k].info = info | 512; }
+                        if (cd < d) { trail = plid; d = cd; rec[k].info = info | 512; }   // (phase C reads the plane and the flag only)
                         else if (trail < 0) trail -= 1;
                     } else if (trail < 0) trail -= 1;
+                };
+                if (w[j] < 0) {
+#define PG_CSWAP(A, B)                                                                                          \
+                    if (KI[j][B] < KI[j][A]) { const int tk = KI[j][A]; KI[j][A] = KI[j][B]; KI[j][B] = tk; const float td = DD[j][A]; DD[j][A] = DD[j][B]; DD[j][B] = td; }
+                    PG_CSWAP(0, 1) PG_CSWAP(2, 3) PG_CSWAP(0, 2) PG_CSWAP(1, 3) PG_CSWAP(1, 2)
+#undef PG_CSWAP
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (trail > -6 && KI[j][r] != 0x7fffffff) visit(KI[j][r] >> 10, KI[j][r] & 0x1ff, DD[j][r]);
+                } else {      // more than four visits of one pixel in one level (a pixel queued twice): walk the list per visit
+                    int last = -1;
+                    for (;;) {
+                        if (trail <= -6) break;
+                        int k = 0x7fffffff;
+                        for (int w2 = h0[j]; w2 >= 0; w2 = __ldcg(&rec[w2].next))
+                            if (w2 > last && w2 < k) k = w2;
+                        if (k == 0x7fffffff) break;
+                        last = k;
+                        visit(k, __ldcg(&rec[k].info) & 0x1ff, __ldcg(&rec[k].dist));
+                    }
                 }
                 member[c] = trail;
                 dist[c] = d;
@@ -1025,29 +1099,54 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
         }
         cluster.sync();
         GCLK(1);
-        // ---- phase C: ordered compaction over the whole cluster
+        // ---- phase C: ordered compaction over the whole cluster (every thread a contiguous range of keys; totals through
+        // distributed shared memory)
         {
-            const int total_keys = 4 * n;
-            const int L = (total_keys + G - 1) / G;
-            const int k0 = min(g * L, total_keys), k1 = min(k0 + L, total_keys);
+            const int L = (nk + G - 1) / G;
+            const int k0 = min(g * L, nk), k1 = min(k0 + L, nk);
+            int e[PG_U];                                 // the appended entries of the first PG_U keys stay in registers
             int cnt = 0;
-            for (int k = k0; k < k1; ++k) cnt += (__ldcg(&rec[k].info) & 512) ? 1 : 0;
+            if (L <= PG_U) {
+                int4 t[PG_U];
+#pragma unroll
+                for (int j = 0; j < PG_U; ++j) {
+                    t[j].x = -1; t[j].y = 0;
+                    if (k0 + j < k1) t[j] = __ldcg(reinterpret_cast<const int4 *>(rec) + k0 + j);
+                }
+#pragma unroll
+                for (int j = 0; j < PG_U; ++j) {
+                    const bool f = t[j].x >= 0 && (t[j].y & 512);
+                    e[j] = f ? (((t[j].y & 255) << 20) | t[j].x) : -1;
+                    cnt += f ? 1 : 0;
+                }
+            } else
+                for (int k = k0; k < k1; ++k) {
+                    const int4 t = __ldcg(reinterpret_cast<const int4 *>(rec) + k);
+                    cnt += (t.x >= 0 && (t.y & 512)) ? 1 : 0;
+                }
             int total;
             int o = pg_block_scan(cnt, s_warp, total);
-            if (tid == 0) ctl->grow_tot[rank] = total;
+            if (tid == 0) s_tot = total;
             cluster.sync();
-            int base = 0, all = 0;
-            for (int r = 0; r < PG_CL; ++r) {
-                const int t = __ldcg(&ctl->grow_tot[r]);
-                if (r < rank) base += t;
-                all += t;
+            if (tid < 32) {      // warp 0 reads the PG_CL totals
+                const int t = tid < PG_CL ? *cluster.map_shared_rank(&s_tot, tid) : 0;
+                const int al = __reduce_add_sync(0xffffffffu, t), bs = __reduce_add_sync(0xffffffffu, tid < rank ? t : 0);
+                if (tid == 0) { s_base[0] = bs; s_base[1] = al; }
             }
-            o += base;
-            if (all <= PG_CAP)
-                for (int k = k0; k < k1; ++k) {
-                    const int info = __ldcg(&rec[k].info);
-                    if (info & 512) nxt[o++] = ((info & 255) << 20) | __ldcg(&rec[k].pix);
-                }
+            __syncthreads();
+            const int all = s_base[1];
+            o += s_base[0];
+            if (all <= PG_CAP) {
+                if (L <= PG_U) {
+#pragma unroll
+                    for (int j = 0; j < PG_U; ++j)
+                        if (e[j] >= 0) nxt[o++] = e[j];
+                } else
+                    for (int k = k0; k < k1; ++k) {
+                        const int4 t = __ldcg(reinterpret_cast<const int4 *>(rec) + k);
+                        if (t.x >= 0 && (t.y & 512)) nxt[o++] = ((t.y & 255) << 20) | t.x;
+                    }
+            }
             n = all;
         }
         cluster.sync();
@@ -1058,17 +1157,28 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
 #ifdef PEAC_CLOCKS
     if (g == 0) { ctl->clk[60][0] = gc[0]; ctl->clk[60][1] = gc[1]; ctl->clk[60][2] = gc[2]; ctl->clk[60][3] = levels; }
 #endif
+    __syncthreads();
+    for (int k = tid; k < np; k += PG_NT)
+        if (s_conn[k]) atomicOr(&ctl->conn[k], s_conn[k]);
     if (g == 0) {
         ctl->grow_n = n; ctl->grow_buf = buf; ctl->grow_levels = levels; ctl->grow_entries = entries;
         if (n > PG_CAP) ctl->overflow = 1;
     }
 }
 
-// Levels of at most PG_SCAP entries keep the queue and the visit records in shared memory (the common case: a frame has a
-// few levels of 5-10 k entries right after the seeds and then ~200 levels of a few hundred); larger levels use the global
-// buffers.  Only the per-pixel state (membership, distance, list head) lives in global memory: one L2 round trip in phase
-// A (list link + depth, issued together) and one in phase B.
-#define PG_SMEM ((size_t)(2 * PG_SCAP + 4 * PG_SCAP * 4) * 4 + 4 * PG_SCAP)
+// Levels of at most PG_SCAP entries (the common case: a frame has a few levels of 5-10 k entries right after the seeds and
+// then ~170 levels of a few hundred) run entirely out of shared memory: the queue, the visit records AND the per-pixel
+// visit lists.  A level costs ONE L2 round trip: phase A (one thread per visit) loads the target pixel's depth, membership
+// and distance together -- the state of a pixel only changes in phase B, so the values phase B needs can be fetched here --
+// and links the visit into the pixel's list through a shared-memory hash table keyed by the pixel (word = pixel << 13 |
+// newest visit; compare-and-swap).  Phase B and C touch shared memory only (the new state is written back with plain
+// stores).  Larger levels take the generic path over the global buffers (per-pixel list heads in head[]).
+#define PG_TAB 8192            // hash slots (visits per level <= 4 * PG_SCAP = 8192 = 2^13, distinct pixels fewer)
+#define PG_TAB_EMPTY 0xffffffffu
+#define PG_NONE 0xffffu
+#define PG_SMEM ((size_t)2 * PG_SCAP * 4 + (size_t)4 * PG_SCAP * (4 + 2 + 2 + 4 + 4 + 1) + (size_t)PG_TAB * 4)
+__device__ __forceinline__ unsigned pg_hash(int pix) { return ((unsigned)pix * 2654435761u) >> 19; }   // 13 bits
+
 __global__ void __launch_bounds__(PG_FNT) k_peac_grow_fifo(const uint16_t *__restrict__ depth, int W, int H, float fx, float fy, float cx, float cy,
                                                           float inv_scale, int Nw, int Nh, PeacControl *ctl, int *__restrict__ member,
                                                           float *__restrict__ dist, int *__restrict__ head, int *qa, int *qb,
@@ -1076,9 +1186,13 @@ __global__ void __launch_bounds__(PG_FNT) k_peac_grow_fifo(const uint16_t *__res
 {
     extern __shared__ int pg_dyn[];
     int *s_q0 = pg_dyn, *s_q1 = s_q0 + PG_SCAP;
-    int *s_pix = s_q1 + PG_SCAP, *s_info = s_pix + 4 * PG_SCAP, *s_next = s_info + 4 * PG_SCAP;
-    float *s_dist = (float *)(s_next + 4 * PG_SCAP);
-    unsigned char *s_push = (unsigned char *)(s_dist + 4 * PG_SCAP);
+    int *s_pix = s_q1 + PG_SCAP;                                        // [4 PG_SCAP] target pixel of the visit, -1: none
+    float *s_dist = (float *)(s_pix + 4 * PG_SCAP);                     // point-plane distance of the visit
+    float *s_cur = s_dist + 4 * PG_SCAP;                                // distMap of the target pixel before this level
+    unsigned *s_tab = (unsigned *)(s_cur + 4 * PG_SCAP);                // [PG_TAB] pixel << 13 | newest visit
+    unsigned short *s_next = (unsigned short *)(s_tab + PG_TAB);        // list link (older visit), PG_NONE: first
+    unsigned short *s_info = s_next + 4 * PG_SCAP;                      // plane | ok << 6 | (membership + 6) << 7
+    unsigned char *s_push = (unsigned char *)(s_info + 4 * PG_SCAP);
     __shared__ int s_blk[PEAC_MAXB];
     __shared__ double s_pn[PEAC_MAXP][3], s_pc[PEAC_MAXP][3], s_thr[PEAC_MAXP];
     __shared__ unsigned long long s_conn[PEAC_MAXP];
@@ -1091,6 +1205,7 @@ __global__ void __launch_bounds__(PG_FNT) k_peac_grow_fifo(const uint16_t *__res
         s_thr[k] = ctl->pl[k].thr;
         s_conn[k] = 0ull;
     }
+    for (int i = tid; i < PG_TAB; i += PG_FNT) s_tab[i] = PG_TAB_EMPTY;
     __syncthreads();
     // ---- the frontier left by k_peac_grow_cluster (seeds + the large levels)
     int n = ctl->grow_n;
@@ -1104,169 +1219,230 @@ __global__ void __launch_bounds__(PG_FNT) k_peac_grow_fifo(const uint16_t *__res
     int levels = ctl->grow_levels, entries = ctl->grow_entries;
 #ifdef PEAC_CLOCKS
     long long fc[6] = {0, 0, 0, 0, 0, 0}, ft = clock64();
-    __shared__ int s_tmax[2], s_seg[3];
-    long long sg[3] = {0, 0, 0};
-    if (tid == 0) { s_tmax[0] = 0; s_tmax[1] = 0; s_seg[0] = s_seg[1] = s_seg[2] = 0; }
-    __syncthreads();
     const int lv0 = levels;
+    __shared__ int s_seg[8];
+    long long sg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (tid < 8) s_seg[tid] = 0;
+    __syncthreads();
+#define SEGT(i, t0_) do { const int d_ = (int)(clock64() - (t0_)); if (d_ > s_seg[i]) atomicMax(&s_seg[i], d_); } while (0)
 #define FCLK(i) do { if (tid == 0) { const long long t_ = clock64(); fc[i] += t_ - ft; ft = t_; } } while (0)
 #else
 #define FCLK(i) do { } while (0)
+#define SEGT(i, t0_) do { } while (0)
 #endif
     while (n > 0) {
         if (n > PG_CAP) { if (tid == 0) ctl->overflow = 1; break; }
         ++levels; entries += n;
-        const bool small = n <= PG_SCAP;
-        int *v_pix = small ? s_pix : g_pix, *v_info = small ? s_info : g_info, *v_next = small ? s_next : g_next;
-        float *v_dist = small ? s_dist : g_dist;
-        unsigned char *v_push = small ? s_push : g_push;
+        int *nxt;
 #ifdef PEAC_CLOCKS
-        long long tw0 = clock64();
+        const long long tw0 = clock64();
+        const int ncls = n <= 64 ? 0 : (n <= 256 ? 1 : (n <= 1024 ? 2 : 3));
 #endif
-        // ---- phase A
-        for (int e = tid; e < n; e += PG_FNT) {
-            const int ent = cur[e];
-            const int s = ent & 0xfffff, plid = ent >> 20;
-            const int sy = s / W, sx = s - sy * W;
-            int cc[4], link[4];
-            unsigned dv[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const bool ex = q == 0 ? sx > 0 : (q == 1 ? sx < W - 1 : (q == 2 ? sy > 0 : sy < H - 1));
-                cc[q] = -1; link[q] = -1; dv[q] = 0;
-                if (ex) {
-                    const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
-                    const int bx = ccx / PEAC_WIN, by = ccy / PEAC_WIN;
-                    if (!(bx < Nw && by < Nh && s_blk[by * Nw + bx] >= 0)) {     // only pixels of "black" blocks grow (:567-568)
-                        cc[q] = ccy * W + ccx;
-                        link[q] = atomicExch(&head[cc[q]], e * 4 + q);            // link the visit; the depth load below is in flight with it
-                        dv[q] = depth[cc[q]];
-                    }
-                }
-            }
-#ifdef PEAC_CLOCKS
-            const long long ta_ = clock64();
-#endif
-            // the four point-plane distances are independent FP64 chains: straight-line code, so that they overlap
-            float cdv[4];
-            bool okv[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+        if (n <= PG_SCAP) {
+            // ---- phase A: one thread per visit (key = 4 * queue rank + direction)
+            for (int v = tid; v < 4 * n; v += PG_FNT) {
+                const int ent = cur[v >> 2], q = v & 3;
+                const int s = ent & 0xfffff, plid = ent >> 20;
+                const int sy = s / W, sx = s - sy * W;
                 const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
-                const float df = (float)dv[q];
-                const float z = df * inv_scale;                                   // organised cloud point (DynaDetect.cc:562-587)
+                int c = -1;
+                if (ccx >= 0 && ccx < W && ccy >= 0 && ccy < H) {
+                    const int bx = ccx / PEAC_WIN, by = ccy / PEAC_WIN;
+                    if (!(bx < Nw && by < Nh && s_blk[by * Nw + bx] >= 0)) c = ccy * W + ccx;     // only pixels of "black" blocks grow (:567-568)
+                }
+                s_pix[v] = c;
+                if (c < 0) continue;
+                const unsigned dv = depth[c];                     // the three loads are in flight together
+                const int tr = member[c];
+                const float dcur = dist[c];
+                unsigned link = PG_NONE;                          // link the visit into the list of pixel c
+                for (unsigned h = pg_hash(c);; h = (h + 1) & (PG_TAB - 1)) {
+                    unsigned w = s_tab[h];
+                    bool done = false;
+                    for (;;) {
+                        if (w == PG_TAB_EMPTY) {
+                            const unsigned old = atomicCAS(&s_tab[h], PG_TAB_EMPTY, ((unsigned)c << 13) | (unsigned)v);
+                            if (old == PG_TAB_EMPTY) { done = true; break; }
+                            w = old;
+                        } else if ((int)(w >> 13) == c) {
+                            const unsigned old = atomicCAS(&s_tab[h], w, ((unsigned)c << 13) | (unsigned)v);
+                            if (old == w) { link = w & 8191u; done = true; break; }
+                            w = old;
+                        } else break;                             // another pixel's slot: probe on
+                    }
+                    if (done) break;
+                }
+                const float df = (float)dv;
+                const float z = df * inv_scale;                                       // organised cloud point (DynaDetect.cc:562-587)
                 const double P0 = ((float)ccx - cx) * z / fx, P1 = ((float)ccy - cy) * z / fy, P2 = z;
                 const float cd = (float)fabs(s_pn[plid][0] * (P0 - s_pc[plid][0]) + s_pn[plid][1] * (P1 - s_pc[plid][1]) + s_pn[plid][2] * (P2 - s_pc[plid][2]));
-                const bool has = !(df < 1e-3f);
-                cdv[q] = has ? cd : -1.0f;
-                okv[q] = has && (double)cd * (double)cd < s_thr[plid];            // point-plane distance within 3 sigma
+                const bool ok = !(df < 1e-3f) && (double)cd * (double)cd < s_thr[plid];   // valid point within 3 sigma of the plane
+                s_info[v] = (unsigned short)(plid | (ok ? 64 : 0) | ((tr + 6) << 7));
+                s_dist[v] = cd;
+                s_cur[v] = dcur;
+                s_push[v] = 0;
+                s_next[v] = (unsigned short)link;
             }
-#ifdef PEAC_CLOCKS
-            const long long tb_ = clock64();
-#endif
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int key = e * 4 + q, c = cc[q];
-                v_pix[key] = c;
-                if (c >= 0) {
-                    v_info[key] = plid | (okv[q] ? 256 : 0);
-                    v_dist[key] = cdv[q];
-                    v_push[key] = 0;
-                    v_next[key] = link[q];
-                }
-            }
-#ifdef PEAC_CLOCKS
-            { const long long tc_ = clock64(); atomicMax(&s_seg[0], (int)(ta_ - tw0)); atomicMax(&s_seg[1], (int)(tb_ - ta_)); atomicMax(&s_seg[2], (int)(tc_ - tb_)); }
-#endif
-        }
-#ifdef PEAC_CLOCKS
-        { const long long d_ = clock64() - tw0; atomicMax(&s_tmax[0], (int)d_); }
-#endif
-        __syncthreads();
-#ifdef PEAC_CLOCKS
-        if (tid == 0) { fc[3] += s_tmax[0]; s_tmax[0] = 0; for (int q = 0; q < 3; ++q) { sg[q] += s_seg[q]; s_seg[q] = 0; } }
-        tw0 = clock64();
-#endif
-        FCLK(0);
-        // ---- phase B: one owner per visited pixel replays its visits in queue order
-        for (int k0 = tid; k0 < 4 * n; k0 += 4 * PG_FNT) {
-            int pc[4], tr[4], hd[4];
-            float dd[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int key = k0 + j * PG_FNT;
-                const int c = key < 4 * n ? v_pix[key] : -1;
-                pc[j] = (c >= 0 && v_next[key] == -1) ? c : -1;     // the visit linked first (list tail) owns the pixel
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {                           // the loads of the four pixels are in flight together
-                const int c = pc[j] < 0 ? 0 : pc[j];
-                tr[j] = member[c]; dd[j] = dist[c]; hd[j] = head[c];
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (pc[j] < 0) continue;
-                const int c = pc[j];
-                int trail = tr[j];
-                float d = dd[j];
-                const int h0 = hd[j];
-                head[c] = -1;
+            __syncthreads();
+            FCLK(0);
+            // ---- phase B: the visit linked first owns the pixel and replays its visits in key order
+            for (int v = tid; v < 4 * n; v += PG_FNT) {
+                const int c = s_pix[v];
+                if (c < 0 || s_next[v] != PG_NONE) continue;
+                unsigned h = pg_hash(c);
+                while ((int)(s_tab[h] >> 13) != c) h = (h + 1) & (PG_TAB - 1);
+                const int h0 = (int)(s_tab[h] & 8191u);
+                int trail = (int)(s_info[v] >> 7) - 6;
+                float d = s_cur[v];
                 int last = -1;
                 for (;;) {
                     if (trail <= -6) break;                      // visited from 4 neighbours already (:563); nothing can change any more
                     int k = 0x7fffffff;                          // next visit in key order
-                    for (int w = h0; w >= 0; w = v_next[w])
+                    for (int w = h0; w != (int)PG_NONE; w = s_next[w])
                         if (w > last && w < k) k = w;
                     if (k == 0x7fffffff) break;
                     last = k;
-                    const int info = v_info[k], plid = info & 255;
+                    const int info = s_info[k], plid = info & 63;
                     if (trail >= 0 && trail == plid) continue;   // visited by the same plane (:564)
-                    if (info & 256) {
+                    if (info & 64) {
                         if (trail >= 0) {                        // two planes meet: potential merge (:575-580)
                             const double sm = fabs(s_pn[plid][0] * s_pn[trail][0] + s_pn[plid][1] * s_pn[trail][1] + s_pn[plid][2] * s_pn[trail][2]);
-                            if (sm >= PEAC_SIM_REFINE) { atomicOr(&s_conn[trail], 1ull << plid); atomicOr(&s_conn[plid], 1ull << trail); }
+                            if (sm >= PEAC_SIM_REFINE && !((s_conn[trail] >> plid) & 1ull)) { atomicOr(&s_conn[trail], 1ull << plid); atomicOr(&s_conn[plid], 1ull << trail); }
                         }
-                        const float cd = v_dist[k];
-                        if (cd < d) { trail = plid; d = cd; v_push[k] = 1; }
+                        const float cd = s_dist[k];
+                        if (cd < d) { trail = plid; d = cd; s_push[k] = 1; }
                         else if (trail < 0) trail -= 1;
                     } else if (trail < 0) trail -= 1;
                 }
                 member[c] = trail;
                 dist[c] = d;
             }
+            __syncthreads();
+            FCLK(1);
+            // ---- phase C: the appended entries, in key order, are the next level; the hash table is emptied
+            if (4 * n <= PG_FNT) {      // one key per thread: ballot + one pass over the 32 warp counts (two barriers instead of four)
+                const bool f = tid < 4 * n && s_pix[tid] >= 0 && s_push[tid];
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                const int lane = tid & 31, wid = tid >> 5;
+                if (lane == 0) s_warp[wid] = __popc(m);
+                for (int i = tid; i < PG_TAB; i += PG_FNT) s_tab[i] = PG_TAB_EMPTY;
+                __syncthreads();
+                const int wc = s_warp[lane];
+                const int total = __reduce_add_sync(0xffffffffu, wc), base = __reduce_add_sync(0xffffffffu, lane < wid ? wc : 0);
+                nxt = nxt_s_is_q1 ? s_q1 : s_q0;     // total <= 4 n <= PG_SCAP
+                if (f) nxt[base + __popc(m & ((1u << lane) - 1))] = ((s_info[tid] & 63) << 20) | s_pix[tid];
+                n = total;
+                nxt_s_is_q1 = !nxt_s_is_q1;
+            } else {
+                const int total_keys = 4 * n;
+                const int L = (total_keys + PG_FNT - 1) / PG_FNT;
+                const int k0 = min(tid * L, total_keys), k1 = min(k0 + L, total_keys);
+                int cnt = 0;
+                for (int k = k0; k < k1; ++k) cnt += (s_pix[k] >= 0 && s_push[k]) ? 1 : 0;
+                for (int i = tid; i < PG_TAB; i += PG_FNT) s_tab[i] = PG_TAB_EMPTY;
+                int total;
+                int o = pg_block_scan(cnt, s_warp, total);
+                nxt = total <= PG_SCAP ? (nxt_s_is_q1 ? s_q1 : s_q0) : nxt_g;
+                if (total <= PG_CAP)
+                    for (int k = k0; k < k1; ++k)
+                        if (s_pix[k] >= 0 && s_push[k]) nxt[o++] = ((s_info[k] & 63) << 20) | s_pix[k];
+                n = total;
+                if (total <= PG_SCAP) nxt_s_is_q1 = !nxt_s_is_q1;
+                else nxt_g = nxt_g == qa ? qb : qa;
+            }
+            __syncthreads();
+            FCLK(2);
+#ifdef PEAC_CLOCKS
+            if (tid == 0) { sg[ncls] += clock64() - tw0; sg[4 + ncls] += 1; }
+#endif
+            cur = nxt;
+            continue;
         }
-#ifdef PEAC_CLOCKS
-        { const long long d_ = clock64() - tw0; atomicMax(&s_tmax[1], (int)d_); }
-#endif
+        // ---- generic path (a level of more than PG_SCAP entries after the cluster kernel handed over: rare)
+        // phase A
+        for (int e = tid; e < n; e += PG_FNT) {
+            const int ent = cur[e];
+            const int s = ent & 0xfffff, plid = ent >> 20;
+            const int sy = s / W, sx = s - sy * W;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool ex = q == 0 ? sx > 0 : (q == 1 ? sx < W - 1 : (q == 2 ? sy > 0 : sy < H - 1));
+                const int key = e * 4 + q;
+                int c = -1;
+                const int ccx = sx + (q == 0 ? -1 : (q == 1 ? 1 : 0)), ccy = sy + (q == 2 ? -1 : (q == 3 ? 1 : 0));
+                if (ex) {
+                    const int bx = ccx / PEAC_WIN, by = ccy / PEAC_WIN;
+                    if (!(bx < Nw && by < Nh && s_blk[by * Nw + bx] >= 0)) c = ccy * W + ccx;
+                }
+                g_pix[key] = c;
+                if (c < 0) continue;
+                const int link = atomicExch(&head[c], key);
+                const float df = (float)depth[c];
+                const float z = df * inv_scale;
+                const double P0 = ((float)ccx - cx) * z / fx, P1 = ((float)ccy - cy) * z / fy, P2 = z;
+                const float cd = (float)fabs(s_pn[plid][0] * (P0 - s_pc[plid][0]) + s_pn[plid][1] * (P1 - s_pc[plid][1]) + s_pn[plid][2] * (P2 - s_pc[plid][2]));
+                const bool has = !(df < 1e-3f);
+                g_info[key] = plid | ((has && (double)cd * (double)cd < s_thr[plid]) ? 256 : 0);
+                g_dist[key] = has ? cd : -1.0f;
+                g_push[key] = 0;
+                g_next[key] = link;
+            }
+        }
         __syncthreads();
-#ifdef PEAC_CLOCKS
-        if (tid == 0) { fc[4] += s_tmax[1]; s_tmax[1] = 0; }
-#endif
-        FCLK(1);
-        // ---- phase C: the appended entries, in key order, are the next level
-        int *nxt;
+        // phase B
+        for (int key = tid; key < 4 * n; key += PG_FNT) {
+            const int c = g_pix[key];
+            if (c < 0 || g_next[key] != -1) continue;            // the visit linked first (list tail) owns the pixel
+            int trail = member[c];
+            float d = dist[c];
+            const int h0 = head[c];
+            head[c] = -1;
+            int last = -1;
+            for (;;) {
+                if (trail <= -6) break;
+                int k = 0x7fffffff;
+                for (int w = h0; w >= 0; w = g_next[w])
+                    if (w > last && w < k) k = w;
+                if (k == 0x7fffffff) break;
+                last = k;
+                const int info = g_info[k], plid = info & 255;
+                if (trail >= 0 && trail == plid) continue;
+                if (info & 256) {
+                    if (trail >= 0) {
+                        const double sm = fabs(s_pn[plid][0] * s_pn[trail][0] + s_pn[plid][1] * s_pn[trail][1] + s_pn[plid][2] * s_pn[trail][2]);
+                        if (sm >= PEAC_SIM_REFINE && !((s_conn[trail] >> plid) & 1ull)) { atomicOr(&s_conn[trail], 1ull << plid); atomicOr(&s_conn[plid], 1ull << trail); }
+                    }
+                    const float cd = g_dist[k];
+                    if (cd < d) { trail = plid; d = cd; g_push[k] = 1; }
+                    else if (trail < 0) trail -= 1;
+                } else if (trail < 0) trail -= 1;
+            }
+            member[c] = trail;
+            dist[c] = d;
+        }
+        __syncthreads();
+        // phase C
         {
             const int total_keys = 4 * n;
             const int L = (total_keys + PG_FNT - 1) / PG_FNT;
             const int k0 = min(tid * L, total_keys), k1 = min(k0 + L, total_keys);
             int cnt = 0;
-            for (int k = k0; k < k1; ++k) cnt += (v_pix[k] >= 0 && v_push[k]) ? 1 : 0;
+            for (int k = k0; k < k1; ++k) cnt += (g_pix[k] >= 0 && g_push[k]) ? 1 : 0;
             int total;
             int o = pg_block_scan(cnt, s_warp, total);
             nxt = total <= PG_SCAP ? (nxt_s_is_q1 ? s_q1 : s_q0) : nxt_g;
             if (total <= PG_CAP)
                 for (int k = k0; k < k1; ++k)
-                    if (v_pix[k] >= 0 && v_push[k]) nxt[o++] = ((v_info[k] & 255) << 20) | v_pix[k];
+                    if (g_pix[k] >= 0 && g_push[k]) nxt[o++] = ((g_info[k] & 255) << 20) | g_pix[k];
             n = total;
             if (total <= PG_SCAP) nxt_s_is_q1 = !nxt_s_is_q1;
             else nxt_g = nxt_g == qa ? qb : qa;
         }
         __syncthreads();
-        FCLK(2);
         cur = nxt;
     }
 #ifdef PEAC_CLOCKS
-    if (tid == 0) { ctl->clk[61][0] = fc[0]; ctl->clk[61][1] = fc[1]; ctl->clk[61][2] = fc[2]; ctl->clk[61][3] = levels - lv0; ctl->clk[61][4] = fc[3]; ctl->clk[61][5] = fc[4]; ctl->clk[61][6] = sg[0]; ctl->clk[61][7] = sg[1]; ctl->clk[61][8] = sg[2]; }
+    if (tid == 0) { ctl->clk[61][0] = fc[0]; ctl->clk[61][1] = fc[1]; ctl->clk[61][2] = fc[2]; ctl->clk[61][3] = levels - lv0; for (int q = 0; q < 8; ++q) ctl->clk[61][4 + q] = sg[q]; }
 #endif
     __syncthreads();
     for (int k = tid; k < np; k += PG_FNT) ctl->conn[k] |= s_conn[k];
@@ -1429,7 +1605,7 @@ int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t 
         at[0].val.clusterDim.x = PG_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         CU_CHECK(ctx, cudaLaunchKernelEx(&cfg, k_peac_grow_cluster, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->ctl, im->label, im->dist, im->head, im->qa,
-                                         im->qb, im->rec));
+                                         im->qb, im->rec, im->v_dist));
         ctx->launches++;
     }
     LAUNCH(ctx, k_peac_grow_fifo, 1, PG_FNT, PG_SMEM, depth, W, H, fx, fy, cx, cy, inv_scale, Nw, Nh, im->ctl, im->label, im->dist, im->head, im->qa, im->qb,
@@ -1461,9 +1637,9 @@ int peac_get_debug(sindyn_base *ctx, PeacStage *p, int *label_out, int *planes_r
                     host.clk[c][8], (double)host.clk[c][9] / host.clk[c][8], (double)host.clk[c][10] / host.clk[c][8], host.clk[c][0] / 1000, host.clk[c][1] / 1000,
                     host.clk[c][2] / 1000, host.clk[c][3] / 1000, host.clk[c][4] / 1000, host.clk[c][5] / 1000, host.clk[c][11] / 1000, host.clk[c][6] / 1000, host.clk[c][7] / 1000);
         }
-    fprintf(stderr, "peac grow: levels %d entries %d | cluster kernel: %lld levels, kcycles A %lld B %lld C %lld | single-CTA kernel: %lld levels, kcycles A %lld B %lld C %lld (slowest thread A %lld B %lld; A segments issue %lld math %lld store %lld)\n",
+    fprintf(stderr, "peac grow: levels %d entries %d | cluster kernel: %lld levels, kcycles A %lld B %lld C %lld | single-CTA kernel: %lld levels, kcycles A %lld B %lld C %lld (levels of <= 64 / 256 / 1024 / 2048 entries: %lld / %lld / %lld / %lld levels, %lld / %lld / %lld / %lld kcycles)\n",
             host.grow_levels, host.grow_entries, host.clk[60][3], host.clk[60][0] / 1000, host.clk[60][1] / 1000, host.clk[60][2] / 1000, host.clk[61][3],
-            host.clk[61][0] / 1000, host.clk[61][1] / 1000, host.clk[61][2] / 1000, host.clk[61][4] / 1000, host.clk[61][5] / 1000, host.clk[61][6] / 1000, host.clk[61][7] / 1000, host.clk[61][8] / 1000);
+            host.clk[61][0] / 1000, host.clk[61][1] / 1000, host.clk[61][2] / 1000, host.clk[61][8], host.clk[61][9], host.clk[61][10], host.clk[61][11], host.clk[61][4] / 1000, host.clk[61][5] / 1000, host.clk[61][6] / 1000, host.clk[61][7] / 1000);
 #endif
     if (n_planes) *n_planes = host.n_planes;
     if (n_final) *n_final = host.n_final;
