@@ -401,6 +401,7 @@ def run_ours(args):
                 ev[s - s0][0].record(stream)
             for j in range(FRAMES_PER_STEP):
                 orb.track_frame_resident(sd, order[s * FRAMES_PER_STEP + j], s * FRAMES_PER_STEP + j)
+            orb.track_join(sd)      # the step's frames run on several streams (frame pipeline): the end event covers all of them
             if ev is not None:
                 ev[s - s0][1].record(stream)
 

@@ -266,6 +266,12 @@ int sindyn_track_frame(sindyn_handle h, sindyn_orb_handle o, const uint8_t *bgr,
 /* Same on a frame staged with sindyn_upload_frame: no host traffic, no synchronisation (kernel-only timing; the extractor's
  * stream is joined into the detector handle's stream).  Results via sindyn_track_get_results. */
 int sindyn_track_frame_resident(sindyn_handle h, sindyn_orb_handle o, int slot, int rgb_order, int dilate_k, int frame_idx);
+/* sindyn_track_frame_resident only enqueues (on several streams: with CUDA graphs on, the image-only stages of frame i + 1 --
+ * gray / resize, Brox flow, refinement, PEAC plane fitter, the unmasked half of the extractor -- overlap the decision of frame
+ * i, the software pipeline of pipe.cu; the reference's driver loop, rgbd_tum_noros.cc:113-192, hands over one frame after the
+ * other and nothing in those stages reads the detector's state).  After sindyn_track_join everything enqueued so far precedes
+ * the next operation on the detector handle's stream. */
+int sindyn_track_join(sindyn_handle h, sindyn_orb_handle o);
 int sindyn_track_get_results(sindyn_handle h, sindyn_orb_handle o, uint8_t *mask_dilated, uint8_t *labels, sindyn_keypoint *kps, uint8_t *desc,
                              int capacity, int *n_out);
 

@@ -98,6 +98,7 @@ SIGNATURES = {
     "sindyn_orb_extract": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _i, _ip]),
     "sindyn_track_frame": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _vp, _i, _ip, _i]),
     "sindyn_track_frame_resident": (_i, [_vp, _vp, _i, _i, _i, _i]),
+    "sindyn_track_join": (_i, [_vp, _vp]),
     "sindyn_track_get_results": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
     "sindyn_orb_get_pyramid_level": (_i, [_vp, _i, _vp, _ip, _ip]),
     "sindyn_orb_get_candidates": (_i, [_vp, _i, _vp, _i, _ip]),
@@ -512,6 +513,12 @@ class Orb:
         st = self.lib.sindyn_track_frame_resident(sd.h, self.h, slot, int(rgb_order), int(dilate_k), frame_idx)
         if st != 0:
             raise SindynError(f"track_frame_resident: {STATUS.get(st, st)}: {sd.lib.sindyn_last_error(sd.h).decode()}")
+
+    def track_join(self, sd):
+        """Everything the resident frames have enqueued (several streams) precedes the next operation on sd's stream."""
+        st = self.lib.sindyn_track_join(sd.h, self.h)
+        if st != 0:
+            raise SindynError(f"track_join: {STATUS.get(st, st)}: {sd.lib.sindyn_last_error(sd.h).decode()}")
 
     def track_results(self, sd):
         cap = self.nfeatures * 2 + 64

@@ -97,7 +97,8 @@ extern "C" int sindyn_destroy(sindyn_handle h)
 {
     if (!h) return SINDYN_ERR_INVALID;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    cudaDeviceSynchronize();     // (the frame pipeline and the clustering branch run on further streams)
+    pipe_destroy(h);
     brox_destroy(&h->brox);
     brox_destroy(&h->brox_lm);
     flow_tail_drop_graphs(h);
@@ -122,6 +123,7 @@ extern "C" int sindyn_set_stream(sindyn_handle h, void *s)
         h->brox_lm.graph_ok = false;  // graphs are stream-agnostic, but re-capture keeps capture semantics simple
         flow_tail_drop_graphs(h);
         flow_graph_drop(h);
+        pipe_invalidate(h);
     }
     return SINDYN_OK;
 }

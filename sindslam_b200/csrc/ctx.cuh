@@ -66,8 +66,8 @@ struct sindyn_ctx : sindyn_base {
     struct TailGraph { cudaGraphExec_t exec = nullptr; const uint8_t *k0 = nullptr, *k1 = nullptr; cudaStream_t stream = nullptr; unsigned long long launches = 0; };
     TailGraph tail[8];                // captured post-decision part of the flow branch, per frame-ring position
     int tail_next = 0;
-    struct FlowGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; const uint8_t *k0 = nullptr, *k1 = nullptr, *k2 = nullptr; cudaStream_t stream = nullptr; unsigned long long launches = 0, body_launches = 0; };
-    FlowGraph flow_graph[4];          // the whole flow branch incl. the device-side large-motion decision (flow.cu), per ring position
+    struct FlowGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; const uint8_t *k0 = nullptr, *k1 = nullptr, *k2 = nullptr; cudaStream_t stream = nullptr; unsigned long long launches = 0, body_launches = 0; int variant = 0; };
+    FlowGraph flow_graph[12];         // the whole flow branch incl. the device-side large-motion decision (flow.cu), per ring position (x parity in the frame pipeline)
     FlowGraph *flow_graph_last = nullptr;
     int flow_graph_next = 0;
     bool flow_one_graph = true, flow_graph_broken = false, flow_graph_active = false, flow_flag_pending = false;
@@ -76,6 +76,8 @@ struct sindyn_ctx : sindyn_base {
     unsigned long long cluster_graph_launches = 0;
     cudaStream_t stream3 = nullptr;   // PEAC plane fitter, concurrent with k-means / gradient edges
     cudaEvent_t ev_peac_fork = nullptr, ev_peac_join = nullptr;
+
+    struct FramePipe *pipe = nullptr;     // software pipeline over consecutive frames (pipe.cu), allocated on first use
 
     struct CloudStage *cloud = nullptr;   // dense-map consumer stage (cloud.cu), allocated on first use
 
@@ -95,6 +97,20 @@ int flow_finish_all(sindyn_ctx *c, int *large_motion);     // flow.cu: finish + 
 void flow_tail_drop_graphs(sindyn_ctx *c);                 // flow.cu
 void flow_graph_drop(sindyn_ctx *c);                       // flow.cu
 void flow_collect_flag(sindyn_ctx *c);                     // flow.cu: large-motion flag of the last flow-graph launch (after a sync)
+// flow.cu, frame pipeline: part A = Brox .. up-sampling into c->flow_full (on c->stream, one graph launch; variant 1 + parity keys
+// the graph cache), part B = sample weighting + homography + residual / masks from c->flow_full
+int flow_part_a(sindyn_ctx *c, int parity);
+int flow_part_b(sindyn_ctx *c, int parity);
+int pipe_detect_run(sindyn_ctx *c, const uint8_t *bgr_dev, const uint16_t *depth_dev);   // pipe.cu: one frame through the frame pipeline
+int pipe_join(sindyn_ctx *c);                              // pipe.cu: the handle's stream waits for everything the pipeline has enqueued
+void pipe_invalidate(sindyn_ctx *c);                       // pipe.cu: state was changed outside the pipeline: re-synchronise its streams
+void pipe_destroy(sindyn_ctx *c);                          // pipe.cu
+bool pipe_usable(const sindyn_ctx *c);                     // pipe.cu: graphs on, no stage timing
+int pipe_copy_headers(sindyn_ctx *c);                      // pipe.cu: asynchronous copy of the plane-fitter headers of both pipeline instances
+bool pipe_overflow(const sindyn_ctx *c);                   // pipe.cu: ... and their overflow flags, valid after the stream was synchronised
+cudaEvent_t pipe_input_event(sindyn_ctx *c);               // pipe.cu: the last frame's inputs are in place (bgr ring slot, depth)
+int cluster_part1(sindyn_ctx *c);                          // detect.cu: k-means + gradient edges
+int cluster_part2(sindyn_ctx *c);                          // detect.cu: plane-edge filter + re-clustering
 int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll);  // pipeline.cu
 int sindyn_ctx_init_stages(sindyn_ctx *c);              // stages.cu
 void sindyn_ctx_destroy_stages(sindyn_ctx *c);          // stages.cu

@@ -51,6 +51,18 @@ static int cluster_branch(sindyn_ctx *c)
     return SINDYN_OK;
 }
 
+// the two halves of the clustering branch without the plane fitter (frame pipeline: the fitter runs ahead on its own stream)
+int cluster_part1(sindyn_ctx *c)
+{
+    SD_CHECK(kmeans_run(c, &c->km, c->depth, c->label_last, &c->cfg));
+    return edges_run(c, &c->edges, c->depth, c->cfg.depth_scale);
+}
+int cluster_part2(sindyn_ctx *c)
+{
+    SD_CHECK(plane_edge_filter_run(c, &c->rc, c->plane_edges, c->edges.grad_edges, c->edges.ep_xy, c->edges.scalars + 2));
+    return recluster_run(c, &c->rc, &c->km, c->rc.occl1, c->rc.occl2, c->depth);
+}
+
 static int check_capacity(sindyn_ctx *c)
 {
     ReclusterControl ctl;
@@ -59,8 +71,10 @@ static int check_capacity(sindyn_ctx *c)
     CU_CHECK(c, cudaMemcpyAsync(sc, c->edges.scalars, sizeof sc, cudaMemcpyDeviceToHost, c->stream));
     int peac_hdr[4] = {0, 0, 0, 0};
     if (c->cfg.plane_edges && c->peac.built) SD_CHECK(peac_copy_header(c, &c->peac, peac_hdr));
+    SD_CHECK(pipe_copy_headers(c));      // plane-fitter instances of the frame pipeline (asynchronous, on c->stream)
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     flow_collect_flag(c);
+    if (pipe_overflow(c)) peac_hdr[2] = 1;
     if (peac_hdr[2]) { c->err = "plane fitter: a fixed-capacity list overflowed (> 64 planes, > 512 neighbours of one node, or a region-growing level > 131072 entries)"; return SINDYN_ERR_CAPACITY; }
     if (ctl.overflow) { c->err = "recluster: more than RC_MAXC components"; return SINDYN_ERR_CAPACITY; }
     if (ctl.pf_overflow) { c->err = "plane-edge filter: more than RC_PF_MAXC contours"; return SINDYN_ERR_CAPACITY; }
@@ -75,6 +89,8 @@ static int detect_run(sindyn_ctx *c)
 {
     if (!c->have_prev) { c->err = "detect: call sindyn_set_prev_frames first"; return SINDYN_ERR_STATE; }
     if (c->cfg.stage_timing) SD_CHECK(ensure_events(c));
+    SD_CHECK(pipe_join(c));          // frames still in the pipeline finish first; its streams re-synchronise on their next frame
+    pipe_invalidate(c);
     cudaStream_t main_s = c->stream;
     MARK(c, 0);
     CU_CHECK(c, cudaEventRecord(c->ev_fork, main_s));

@@ -88,7 +88,8 @@ void flow_graph_drop(sindyn_ctx *c)
     c->flow_graph_next = 0;
 }
 
-static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t)
+// variant 0: the whole branch; variant 1 (frame pipeline): up to the up-sampled flow only
+static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t, int variant)
 {
     const int nf = c->fw * c->fh;
     cudaGraph_t g = nullptr;
@@ -126,9 +127,11 @@ static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t)
         if (c->cfg.refine)
             st = varref_run_sel(c, &c->varref, c->gsmall[c->i_cur], c->gsmall[c->i_lastlast], c->gsmall[c->i_last], c->fb_flag, c->flow_small);
         if (st == SINDYN_OK) st = launch_resize_flow(c, c->flow_small, c->fw, c->fh, c->flow_full, c->W, c->H, 1.0f / c->cfg.flow_scale);
-        if (st == SINDYN_OK) st = homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last);
-        if (st == SINDYN_OK) st = homography_estimate(c, &c->homog);
-        if (st == SINDYN_OK) st = residual_homography_run_dev(c, &c->resid, c->flow_full, c->homog.H_dev, c->mask_low, c->mask_high);
+        if (variant == 0) {
+            if (st == SINDYN_OK) st = homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last);
+            if (st == SINDYN_OK) st = homography_estimate(c, &c->homog);
+            if (st == SINDYN_OK) st = residual_homography_run_dev(c, &c->resid, c->flow_full, c->homog.H_dev, c->mask_low, c->mask_high);
+        }
         if (st == SINDYN_OK) e = cudaMemcpyAsync(c->fb_flag_host, c->fb_flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream);
     }
     cudaGraph_t g_out = nullptr;
@@ -155,26 +158,27 @@ static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t)
     CU_CHECK(c, cudaGraphInstantiate(&t->exec, g, 0));
     t->body_launches = body_launches;
     t->k0 = c->gsmall[c->i_cur]; t->k1 = c->gsmall[c->i_last]; t->k2 = c->gsmall[c->i_lastlast]; t->stream = c->stream;
+    t->variant = variant;
     return SINDYN_OK;
 }
 
 // launches the flow graph of the current frame-ring position; returns SINDYN_OK with *launched = false when this device /
 // driver cannot build it (the caller then takes the two-graph path with the host decision)
-static int flow_graph_launch(sindyn_ctx *c, bool *launched)
+static int flow_graph_launch(sindyn_ctx *c, bool *launched, int variant = 0)
 {
     *launched = false;
     if (c->flow_graph_broken) return SINDYN_OK;
     const uint8_t *k0 = c->gsmall[c->i_cur], *k1 = c->gsmall[c->i_last], *k2 = c->gsmall[c->i_lastlast];
     sindyn_ctx::FlowGraph *t = nullptr;
     for (auto &q : c->flow_graph)
-        if (q.exec && q.k0 == k0 && q.k1 == k1 && q.k2 == k2 && q.stream == c->stream) t = &q;
+        if (q.exec && q.k0 == k0 && q.k1 == k1 && q.k2 == k2 && q.stream == c->stream && q.variant == variant) t = &q;
     if (!t) {
         t = &c->flow_graph[c->flow_graph_next];
-        c->flow_graph_next = (c->flow_graph_next + 1) % 4;
+        c->flow_graph_next = (c->flow_graph_next + 1) % 12;
         if (t->exec) cudaGraphExecDestroy(t->exec);
         if (t->graph) cudaGraphDestroy(t->graph);
         *t = sindyn_ctx::FlowGraph();
-        if (flow_graph_build(c, t) != SINDYN_OK) {
+        if (flow_graph_build(c, t, variant) != SINDYN_OK) {
             // leave capture mode if the failure happened inside it, remember not to try again
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
             if (cudaStreamIsCapturing(c->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(c->stream, &junk); }
@@ -202,6 +206,49 @@ void flow_collect_flag(sindyn_ctx *c)
     c->flow_flag_pending = false;
     c->large_motion_last = c->fb_flag_host[0];
     if (c->large_motion_last && c->flow_graph_last) c->launches += c->flow_graph_last->body_launches;
+}
+
+// ---------------------------------------------------------------- frame pipeline (pipe.cu): the branch in two parts
+// Part A depends on the three gray images only, part B also on the previous frame's decision (label_last, dyna_last).  The
+// caller has pointed c->flow_full / c->fb_flag / c->fb_flag_host at the buffers of `parity` and c->stream at the stream of the
+// part; variant = 1 + parity keys the graph cache (the pointers are baked into the graph).
+int flow_part_a(sindyn_ctx *c, int parity)
+{
+    bool launched = false;
+    SD_CHECK(flow_graph_launch(c, &launched, 1 + parity));
+    if (!launched) { c->err = "frame pipeline: the flow graph could not be built"; return SINDYN_ERR_CUDA; }
+    return SINDYN_OK;
+}
+
+int flow_part_b(sindyn_ctx *c, int parity)
+{
+    sindyn_ctx::TailGraph *t = nullptr;
+    const uint8_t *k0 = (const uint8_t *)c->flow_full, *k1 = (const uint8_t *)(uintptr_t)(0x100 + parity);
+    for (auto &q : c->tail)
+        if (q.exec && q.k0 == k0 && q.k1 == k1 && q.stream == c->stream) t = &q;
+    if (!t) {
+        t = &c->tail[c->tail_next];
+        c->tail_next = (c->tail_next + 1) % 8;
+        if (t->exec) cudaGraphExecDestroy(t->exec);
+        *t = sindyn_ctx::TailGraph();
+        const unsigned long long before = c->launches;
+        cudaGraph_t gr = nullptr;
+        CU_CHECK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int st = homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last);
+        if (st == SINDYN_OK) st = homography_estimate(c, &c->homog);
+        if (st == SINDYN_OK) st = residual_homography_run_dev(c, &c->resid, c->flow_full, c->homog.H_dev, c->mask_low, c->mask_high);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &gr);
+        t->launches = c->launches - before;
+        c->launches = before;
+        SD_CHECK(st);
+        CU_CHECK(c, e);
+        CU_CHECK(c, cudaGraphInstantiate(&t->exec, gr, 0));
+        cudaGraphDestroy(gr);
+        t->k0 = k0; t->k1 = k1; t->stream = c->stream;
+    }
+    CU_CHECK(c, cudaGraphLaunch(t->exec, c->stream));
+    c->launches += t->launches;
+    return SINDYN_OK;
 }
 
 // Runs on the handle's resident frames (gsmall_f / gsmall of cur, last, lastlast). Result: c->flow_full.

@@ -919,17 +919,54 @@ extern "C" int sindyn_track_frame(sindyn_handle h, sindyn_orb_handle o, const ui
     return SINDYN_OK;
 }
 
+int pipe_note_gray_read(sindyn_ctx *c, cudaStream_t orb_stream);   // pipe.cu
+
+// the same through the frame pipeline (pipe.cu): the detector's image-only stages of this frame may run while the previous
+// frame is still being decided; the inputs are device buffers the pipeline copies on its own stream
+static int track_enqueue_pipe(sindyn_ctx *c, sindyn_orb *o, const uint8_t *bgr_dev, const uint16_t *depth_dev, int rgb_order, int dilate_k)
+{
+    if (o->device != c->device || o->W != c->W || o->H != c->H) { c->err = "track_frame: the two handles differ in device or image size"; return SINDYN_ERR_INVALID; }
+    if (dilate_k < 0 || dilate_k > MORPH_MAX_K) { c->err = "track_frame: dilate_k out of range"; return SINDYN_ERR_INVALID; }
+    TrackSync *t = track_sync(o);
+    const OrbLevel &L0 = o->lv[0];
+    const uint8_t *bgr = c->bgr[c->i_cur];
+    SD_CHECK(pipe_detect_run(c, bgr_dev, depth_dev));
+    CU_CHECK(o, cudaStreamWaitEvent(o->stream, pipe_input_event(c), 0));
+    LAUNCH(o, k_orb_gray_in, dim3(cdiv(o->W, 32), cdiv(o->H, 8)), dim3(32, 8), 0, bgr, o->W, o->H, rgb_order,
+           o->pyr + (size_t)ORB_EDGE * L0.pitch + ORB_EDGE, L0.pitch);
+    SD_CHECK(pipe_note_gray_read(c, o->stream));
+    SD_CHECK(orb_enqueue_unmasked(o));
+    CU_CHECK(c, cudaStreamWaitEvent(c->stream, t->ev_orb_done, 0));
+    if (dilate_k > 1) SD_CHECK(morph_run(c, c->dd.out, o->mask, nullptr, c->W, c->H, dilate_k, MORPH_DILATE));
+    else CU_CHECK(c, cudaMemcpyAsync(o->mask, c->dd.out, c->N, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH_CHECK(c);
+    CU_CHECK(c, cudaEventRecord(t->ev_mask, c->stream));
+    CU_CHECK(o, cudaStreamWaitEvent(o->stream, t->ev_mask, 0));
+    SD_CHECK(orb_enqueue_masked(o, true));
+    CU_CHECK(o, cudaEventRecord(t->ev_orb_done, o->stream));
+    return SINDYN_OK;
+}
+
 extern "C" int sindyn_track_frame_resident(sindyn_handle h, sindyn_orb_handle o, int slot, int rgb_order, int dilate_k, int frame_idx)
 {
     (void)frame_idx;
     if (!h || !o) return SINDYN_ERR_INVALID;
     cudaSetDevice(h->device);
     if (slot < 0 || slot >= SINDYN_MAX_SLOTS || !h->slot_bgr[slot]) { h->err = "track_frame_resident: empty slot"; return SINDYN_ERR_INVALID; }
+    if (pipe_usable(h)) return track_enqueue_pipe(h, o, h->slot_bgr[slot], h->slot_depth[slot], rgb_order, dilate_k);
     CU_CHECK(h, cudaMemcpyAsync(h->bgr[h->i_cur], h->slot_bgr[slot], (size_t)h->N * 3, cudaMemcpyDeviceToDevice, h->stream));
     CU_CHECK(h, cudaMemcpyAsync(h->depth, h->slot_depth[slot], (size_t)h->N * 2, cudaMemcpyDeviceToDevice, h->stream));
-    SD_CHECK(track_enqueue(h, o, rgb_order, dilate_k));
-    // join: the caller synchronises / times on the detector handle's stream only
-    CU_CHECK(h, cudaStreamWaitEvent(h->stream, ((TrackSync *)o->track)->ev_orb_done, 0));
+    return track_enqueue(h, o, rgb_order, dilate_k);
+}
+
+// The frames enqueued by sindyn_track_frame_resident run on several streams; after this call everything they have enqueued
+// precedes whatever is enqueued next on the detector handle's stream (an event record, a synchronisation)
+extern "C" int sindyn_track_join(sindyn_handle h, sindyn_orb_handle o)
+{
+    if (!h || !o) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    SD_CHECK(pipe_join(h));
+    if (o->track) CU_CHECK(h, cudaStreamWaitEvent(h->stream, ((TrackSync *)o->track)->ev_orb_done, 0));
     return SINDYN_OK;
 }
 

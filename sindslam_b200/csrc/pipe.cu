@@ -1,0 +1,236 @@
+// pipe.cu -- software pipeline over consecutive frames of one sequence.
+//
+// One frame of DetectDynaArea (DynaDetect.cc:1377-1666) is a chain of ~4 ms on an otherwise nearly idle GPU, but only part of it
+// depends on the previous frame's result:
+//   A  gray / resize, Brox, large-motion decision, refinement, up-sampling      <- the three gray images only
+//   P  PEAC plane fitter + plane contours                                        <- the depth image only
+//   B  sample weighting, RHO homography, residual, masks                          <- A + the previous frame's labels / dynamic mask
+//   C  k-means (warm-started by the previous labels), gradient edges, plane-edge filter (needs P), re-clustering
+//   D  decision, state roll                                                       <- B + C
+// The reference's driver hands the detector one frame after the other (rgbd_tum_noros.cc:113-192); nothing in A or P reads the
+// detector's state.  So A and P of frame i + 1 run on their own streams while B, C, D of frame i are still in flight: the host
+// enqueues a frame without waiting (CUDA graphs, events), and the streams only wait for what they really read.  Everything a
+// later frame's A / P overwrites while an earlier frame still reads it exists twice (parity of the frame number): the up-sampled
+// flow, the large-motion flag, the depth image, the plane-edge image, the plane fitter and the scratch of its contour pass.
+// Results are bit-identical to the frame-at-a-time path (same kernels, same inputs, same order per buffer).
+#include "ctx.cuh"
+
+struct FramePipe {
+    cudaStream_t sa = nullptr;                      // part A (+ the input copies)
+    cudaStream_t sp[2] = {nullptr, nullptr};        // plane fitter of even / odd frames (2.6 ms each: two frames' fitters overlap)
+    float *flow_full[2] = {nullptr, nullptr};
+    int *fb_flag[2] = {nullptr, nullptr}, *fb_flag_host[2] = {nullptr, nullptr};
+    uint16_t *depth[2] = {nullptr, nullptr};
+    uint8_t *plane_edges[2] = {nullptr, nullptr};
+    PeacStage peac[2];
+    ReclusterStage rc_peac[2];
+    cudaEvent_t ev_in[2] = {}, ev_a[2] = {}, ev_p[2] = {}, ev_done[2] = {}, ev_join = nullptr, ev_sync = nullptr, ev_gray[3] = {};
+    bool gray_pending[3] = {false, false, false};
+    cudaGraphExec_t g_c1[2] = {nullptr, nullptr}, g_c2[2] = {nullptr, nullptr}, g_p[2] = {nullptr, nullptr};
+    unsigned long long n_c1[2] = {0, 0}, n_c2[2] = {0, 0}, n_p[2] = {0, 0};
+    cudaStream_t built_for = nullptr;               // the handle stream the graphs were captured under
+    unsigned long long frame_no = 0;
+    bool fresh = true;                              // the pipeline's streams have to wait for the handle's stream first
+    int last_slot = 0, last_parity = 0;
+    int hdr_host[2][4] = {};
+    // what the handle's own pointers were before the pipeline redirected them
+    float *own_flow_full = nullptr; int *own_fb_flag = nullptr, *own_fb_flag_host = nullptr; uint16_t *own_depth = nullptr; uint8_t *own_plane_edges = nullptr;
+};
+
+bool pipe_usable(const sindyn_ctx *c) { return c->cfg.use_graphs && !c->cfg.stage_timing && c->flow_one_graph && !c->flow_graph_broken; }
+
+static void pipe_drop_graphs(FramePipe *P)
+{
+    for (int p = 0; p < 2; ++p) {
+        if (P->g_c1[p]) cudaGraphExecDestroy(P->g_c1[p]);
+        if (P->g_c2[p]) cudaGraphExecDestroy(P->g_c2[p]);
+        if (P->g_p[p]) cudaGraphExecDestroy(P->g_p[p]);
+        P->g_c1[p] = P->g_c2[p] = P->g_p[p] = nullptr;
+    }
+}
+
+static int pipe_init(sindyn_ctx *c)
+{
+    if (c->pipe) return SINDYN_OK;
+    FramePipe *P = new FramePipe();
+    c->pipe = P;
+    CU_CHECK(c, cudaStreamCreateWithFlags(&P->sa, cudaStreamNonBlocking));
+    P->sp[0] = c->stream3;
+    CU_CHECK(c, cudaStreamCreateWithFlags(&P->sp[1], cudaStreamNonBlocking));
+    P->own_flow_full = c->flow_full; P->own_fb_flag = c->fb_flag; P->own_fb_flag_host = c->fb_flag_host; P->own_depth = c->depth; P->own_plane_edges = c->plane_edges;
+    P->flow_full[0] = c->flow_full; P->fb_flag[0] = c->fb_flag; P->fb_flag_host[0] = c->fb_flag_host; P->depth[0] = c->depth; P->plane_edges[0] = c->plane_edges;
+    SD_CHECK(c->dalloc(&P->flow_full[1], (size_t)c->N * 2));
+    SD_CHECK(c->dalloc(&P->fb_flag[1], 4));
+    SD_CHECK(c->halloc(&P->fb_flag_host[1], 4));
+    SD_CHECK(c->dalloc(&P->depth[1], (size_t)c->N));
+    SD_CHECK(c->dalloc(&P->plane_edges[1], (size_t)c->N));
+    for (int p = 0; p < 2; ++p) {
+        if (c->cfg.plane_edges) {
+            SD_CHECK(peac_init(c, &P->peac[p], c->W, c->H));
+            SD_CHECK(recluster_init(c, &P->rc_peac[p], c->W, c->H));
+        }
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_in[p], cudaEventDisableTiming));
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_a[p], cudaEventDisableTiming));
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_p[p], cudaEventDisableTiming));
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_done[p], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < 3; ++k) CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_gray[k], cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_sync, cudaEventDisableTiming));
+    return SINDYN_OK;
+}
+
+void pipe_destroy(sindyn_ctx *c)
+{
+    FramePipe *P = c->pipe;
+    if (!P) return;
+    pipe_drop_graphs(P);
+    c->flow_full = P->own_flow_full; c->fb_flag = P->own_fb_flag; c->fb_flag_host = P->own_fb_flag_host; c->depth = P->own_depth; c->plane_edges = P->own_plane_edges;
+    for (int p = 0; p < 2; ++p) {
+        cudaEventDestroy(P->ev_in[p]); cudaEventDestroy(P->ev_a[p]); cudaEventDestroy(P->ev_p[p]); cudaEventDestroy(P->ev_done[p]);
+    }
+    for (int k = 0; k < 3; ++k) cudaEventDestroy(P->ev_gray[k]);
+    cudaEventDestroy(P->ev_join); cudaEventDestroy(P->ev_sync);
+    if (P->sa) cudaStreamDestroy(P->sa);
+    if (P->sp[1]) cudaStreamDestroy(P->sp[1]);
+    delete P;
+    c->pipe = nullptr;
+}
+
+void pipe_invalidate(sindyn_ctx *c)
+{
+    if (c->pipe) c->pipe->fresh = true;
+}
+
+// the handle's stream waits for everything enqueued on the pipeline's streams
+int pipe_join(sindyn_ctx *c)
+{
+    FramePipe *P = c->pipe;
+    if (!P) return SINDYN_OK;
+    cudaStream_t ss[4] = {P->sa, c->stream2, P->sp[0], P->sp[1]};
+    for (cudaStream_t s : ss) {
+        CU_CHECK(c, cudaEventRecord(P->ev_sync, s));
+        CU_CHECK(c, cudaStreamWaitEvent(c->stream, P->ev_sync, 0));
+    }
+    return SINDYN_OK;
+}
+
+cudaEvent_t pipe_input_event(sindyn_ctx *c) { return c->pipe ? c->pipe->ev_in[c->pipe->last_parity] : nullptr; }
+
+// the ORB extractor reads the BGR ring slot of the frame on its own stream: the slot may be overwritten only after that
+int pipe_note_gray_read(sindyn_ctx *c, cudaStream_t orb_stream)
+{
+    FramePipe *P = c->pipe;
+    if (!P) return SINDYN_OK;
+    CU_CHECK(c, cudaEventRecord(P->ev_gray[P->last_slot], orb_stream));
+    P->gray_pending[P->last_slot] = true;
+    return SINDYN_OK;
+}
+
+int pipe_copy_headers(sindyn_ctx *c)
+{
+    FramePipe *P = c->pipe;
+    if (!P || !c->cfg.plane_edges) return SINDYN_OK;
+    for (int p = 0; p < 2; ++p)
+        if (P->peac[p].built) SD_CHECK(peac_copy_header(c, &P->peac[p], P->hdr_host[p]));
+    return SINDYN_OK;
+}
+
+bool pipe_overflow(const sindyn_ctx *c)
+{
+    const FramePipe *P = c->pipe;
+    return P && (P->hdr_host[0][2] || P->hdr_host[1][2]);
+}
+
+// capture fn() on stream s into an executable graph
+template <class F> static int pipe_capture(sindyn_ctx *c, cudaStream_t s, cudaGraphExec_t *exec, unsigned long long *n_launches, F fn)
+{
+    cudaStream_t keep = c->stream;
+    const unsigned long long before = c->launches;
+    cudaGraph_t gr = nullptr;
+    CU_CHECK(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    c->stream = s;
+    const int st = fn();
+    c->stream = keep;
+    const cudaError_t e = cudaStreamEndCapture(s, &gr);
+    *n_launches = c->launches - before;
+    c->launches = before;
+    SD_CHECK(st);
+    CU_CHECK(c, e);
+    CU_CHECK(c, cudaGraphInstantiate(exec, gr, 0));
+    cudaGraphDestroy(gr);
+    return SINDYN_OK;
+}
+
+int pipe_detect_run(sindyn_ctx *c, const uint8_t *bgr_dev, const uint16_t *depth_dev)
+{
+    if (!c->have_prev) { c->err = "detect: call sindyn_set_prev_frames first"; return SINDYN_ERR_STATE; }
+    SD_CHECK(pipe_init(c));
+    FramePipe *P = c->pipe;
+    cudaStream_t main_s = c->stream, s2 = c->stream2, sa = P->sa;
+    if (P->built_for != main_s) { pipe_drop_graphs(P); P->built_for = main_s; }
+    const int p = (int)(P->frame_no & 1), slot = c->i_cur;
+    if (P->fresh) {   // whatever the handle's stream has done so far (state set by the caller, frames of the other path) comes first
+        CU_CHECK(c, cudaEventRecord(P->ev_sync, main_s));
+        CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_sync, 0));
+        CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_sync, 0));
+        CU_CHECK(c, cudaStreamWaitEvent(P->sp[0], P->ev_sync, 0));
+        CU_CHECK(c, cudaStreamWaitEvent(P->sp[1], P->ev_sync, 0));
+        P->fresh = false;
+    }
+    c->flow_full = P->flow_full[p]; c->fb_flag = P->fb_flag[p]; c->fb_flag_host = P->fb_flag_host[p]; c->depth = P->depth[p]; c->plane_edges = P->plane_edges[p];
+    // ---- stream A: inputs, gray / resize, Brox .. up-sampling
+    CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_done[p], 0));                 // frame i - 2 has finished with the buffers of this parity
+    if (P->gray_pending[slot]) CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_gray[slot], 0));   // ... and the extractor with this ring slot
+    CU_CHECK(c, cudaMemcpyAsync(c->bgr[slot], bgr_dev, (size_t)c->N * 3, cudaMemcpyDeviceToDevice, sa));
+    CU_CHECK(c, cudaMemcpyAsync(c->depth, depth_dev, (size_t)c->N * 2, cudaMemcpyDeviceToDevice, sa));
+    if (!c->cfg.plane_edges) CU_CHECK(c, cudaMemsetAsync(c->plane_edges, 0, c->N, sa));
+    CU_CHECK(c, cudaEventRecord(P->ev_in[p], sa));
+    c->stream = sa;
+    int st = sindyn_prep_frame(c, slot);
+    if (st == SINDYN_OK) st = flow_part_a(c, p);
+    c->stream = main_s;
+    SD_CHECK(st);
+    CU_CHECK(c, cudaEventRecord(P->ev_a[p], sa));
+    // ---- stream 3: plane fitter (depth only)
+    if (c->cfg.plane_edges) {
+        cudaStream_t s3 = P->sp[p];
+        CU_CHECK(c, cudaStreamWaitEvent(s3, P->ev_in[p], 0));
+        if (!P->g_p[p])
+            SD_CHECK(pipe_capture(c, s3, &P->g_p[p], &P->n_p[p], [&]() {
+                return peac_run(c, &P->peac[p], &P->rc_peac[p], c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges);
+            }));
+        CU_CHECK(c, cudaGraphLaunch(P->g_p[p], s3));
+        c->launches += P->n_p[p];
+        CU_CHECK(c, cudaEventRecord(P->ev_p[p], s3));
+    }
+    // ---- stream 2: k-means + gradient edges (after the previous frame's decision: warm start, shared scratch), then the
+    // plane-edge filter and the re-clustering
+    CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_in[p], 0));
+    CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_done[p ^ 1], 0));
+    if (!P->g_c1[p]) SD_CHECK(pipe_capture(c, s2, &P->g_c1[p], &P->n_c1[p], [&]() { return cluster_part1(c); }));
+    CU_CHECK(c, cudaGraphLaunch(P->g_c1[p], s2));
+    c->launches += P->n_c1[p];
+    if (c->cfg.plane_edges) CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_p[p], 0));
+    if (!P->g_c2[p]) SD_CHECK(pipe_capture(c, s2, &P->g_c2[p], &P->n_c2[p], [&]() { return cluster_part2(c); }));
+    CU_CHECK(c, cudaGraphLaunch(P->g_c2[p], s2));
+    c->launches += P->n_c2[p];
+    CU_CHECK(c, cudaEventRecord(P->ev_join, s2));
+    // ---- the handle's stream: part B, decision, state roll
+    CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_a[p], 0));
+    SD_CHECK(flow_part_b(c, p));
+    CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_join, 0));
+    SD_CHECK(decide_run(c, &c->dd, c->rc.cls, c->rc.labels, c->rc.stats, c->rc.top, c->mask_low, c->mask_high, c->high_last, c->edges.total_area,
+                        c->rc.label_out));
+    CU_CHECK(c, cudaMemcpyAsync(c->dyna_last, c->dd.out, c->N, cudaMemcpyDeviceToDevice, main_s));
+    CU_CHECK(c, cudaMemcpyAsync(c->high_last, c->mask_high, c->N, cudaMemcpyDeviceToDevice, main_s));
+    CU_CHECK(c, cudaMemcpyAsync(c->label_last, c->rc.label_out, c->N, cudaMemcpyDeviceToDevice, main_s));
+    CU_CHECK(c, cudaEventRecord(P->ev_done[p], main_s));
+    P->last_slot = slot; P->last_parity = p;
+    ++P->frame_no;
+    const int t = c->i_lastlast;
+    c->i_lastlast = c->i_last;
+    c->i_last = c->i_cur;
+    c->i_cur = t;
+    return SINDYN_OK;
+}

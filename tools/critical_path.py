@@ -27,12 +27,14 @@ for pe in (1, 0, 1, 0):
     sd.set_prev_frames(frames[0].bgr, frames[0].bgr)
     for j in range(20):
         orb.track_frame_resident(sd, order[j], j)
+    orb.track_join(sd)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     m = 120
     for j in range(20, 20 + m):
         orb.track_frame_resident(sd, order[j], j)
+    orb.track_join(sd)
     e1.record(stream)
     torch.cuda.synchronize()
     orb.track_results(sd)
