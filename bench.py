@@ -449,12 +449,20 @@ def run_ours(args):
     n_kp = 0
 
     def e2e_steps(s0, s1):
+        # the driver loop reads a recorded sequence (rgbd_tum_noros.cc:113-192), so frame i + 1 is at hand while frame i is being
+        # processed: it is submitted first (upload + image-only stages overlap frame i), then frame i's results are collected on
+        # the host -- every frame's inputs cross the bus inside the timed region and every frame's results come back before
+        # frame i + 2 is accepted
         nonlocal n_kp
-        for s in range(s0, s1):
-            for j in range(FRAMES_PER_STEP):
-                k = order2[s * FRAMES_PER_STEP + j]
-                _, _, kps, _ = orb.track_frame(sd, bgr_np[k], dep_np[k], k, mask_out=pin_mask, label_out=pin_label, kps_out=pin_kps, desc_out=pin_desc)
-                n_kp += len(kps)
+        ks = [order2[s * FRAMES_PER_STEP + j] for s in range(s0, s1) for j in range(FRAMES_PER_STEP)]
+        if not ks:
+            return
+        orb.track_submit(sd, bgr_np[ks[0]], dep_np[ks[0]], ks[0])
+        for i in range(1, len(ks) + 1):
+            if i < len(ks):
+                orb.track_submit(sd, bgr_np[ks[i]], dep_np[ks[i]], ks[i])
+            _, _, kps, _ = orb.track_collect(sd, mask_out=pin_mask, label_out=pin_label, kps_out=pin_kps, desc_out=pin_desc)
+            n_kp += len(kps)
 
     e2e_steps(0, args.warmup)
     barrier()
@@ -465,6 +473,20 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    # the same frames one at a time (sindyn_track_frame: a frame's results are on the host before the next frame is accepted --
+    # the latency-bound figure of a caller that cannot look one frame ahead), a few steps, reported next to the headline
+    n_sync = min(args.steps, 4)
+    order3 = frame_order(N_FRAMES, (2 * total_steps + n_sync + 1) * FRAMES_PER_STEP)[2 * total_steps * FRAMES_PER_STEP:]
+    for j in range(FRAMES_PER_STEP):
+        orb.track_frame(sd, bgr_np[order3[j]], dep_np[order3[j]], j, mask_out=pin_mask, label_out=pin_label, kps_out=pin_kps, desc_out=pin_desc)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for j in range(FRAMES_PER_STEP, (n_sync + 1) * FRAMES_PER_STEP):
+        orb.track_frame(sd, bgr_np[order3[j]], dep_np[order3[j]], j, mask_out=pin_mask, label_out=pin_label, kps_out=pin_kps, desc_out=pin_desc)
+    e3.record(stream)
+    barrier()
+    sync_pairs_s = n_sync * FRAMES_PER_STEP / (e2.elapsed_time(e3) * 1e-3)
     clk = clocks.stop() if rank == 0 else None
     kp_per_frame = n_kp / max(1, args.steps * FRAMES_PER_STEP)
 
@@ -491,7 +513,7 @@ def run_ours(args):
                                                 "oracle ORB); the reference's default CPU engine (DeepFlow) is timed by --impl reference"}
         else:
             extras["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "skipped (--headline-only)"}
-        d2h = 2 * cam.width * cam.height + int(round(kp_per_frame * (24 + 32)))
+        d2h = 2 * cam.width * cam.height + (ORB_CFG[0] * 2 + 64) * (24 + 32) + 80   # mask + labels + the fixed-capacity key-point / descriptor block + counters
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -501,7 +523,10 @@ def run_ours(args):
             "run": {"refine": True, "sequences_total": n_seq_total, "sequences_per_gpu": len(handles), "keypoints_per_frame": round(kp_per_frame, 1)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * cam.width * cam.height * 5,
                     "d2h_bytes_per_step": FRAMES_PER_STEP * d2h, "ms_per_step": e2e_ms / args.steps,
-                    "note": "one sequence per GPU through sindyn_track_frame (host buffers)"},
+                    "frame_at_a_time": sync_pairs_s,
+                    "note": "one sequence per GPU through sindyn_track_submit / sindyn_track_collect (pinned host buffers; frame i + 1 is submitted "
+                            "before frame i is collected, at most two frames in flight); frame_at_a_time = the same through sindyn_track_frame, "
+                            "which returns a frame's results before it accepts the next one"},
             "ms_per_frame": dev_ms / (args.steps * FRAMES_PER_STEP),
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "kernel": "k_brox_sor (temporally blocked red-black SOR, 5 sweeps per launch; the 9 finest pyramid levels)",

@@ -272,6 +272,16 @@ int sindyn_track_frame_resident(sindyn_handle h, sindyn_orb_handle o, int slot, 
  * other and nothing in those stages reads the detector's state).  After sindyn_track_join everything enqueued so far precedes
  * the next operation on the detector handle's stream. */
 int sindyn_track_join(sindyn_handle h, sindyn_orb_handle o);
+/* Asynchronous form of sindyn_track_frame for a caller that has the next image at hand while it still works on the current one
+ * (rgbd_tum_noros.cc:113-192 reads a recorded sequence; Tracking::GrabImageRGBD, Tracking.cc:209-240, needs mask + key points of
+ * frame i only).  sindyn_track_submit uploads frame i + 1 and enqueues all of its work without waiting; sindyn_track_collect
+ * returns the oldest submitted frame (same outputs as sindyn_track_frame; mask_out / label_out / kps / desc may be NULL).  At
+ * most two frames may be in flight (SINDYN_ERR_STATE otherwise); results are bit-identical to sindyn_track_frame.  bgr / depth
+ * must stay valid until the frame is collected if they are pinned (page-locked) memory, pageable memory is copied at once. */
+int sindyn_track_submit(sindyn_handle h, sindyn_orb_handle o, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step,
+                        int rgb_order, int dilate_k, int frame_idx);
+int sindyn_track_collect(sindyn_handle h, sindyn_orb_handle o, uint8_t *mask_out, size_t mask_step, uint8_t *label_out, size_t label_step,
+                         sindyn_keypoint *kps, uint8_t *desc, int capacity, int *n_out);
 int sindyn_track_get_results(sindyn_handle h, sindyn_orb_handle o, uint8_t *mask_dilated, uint8_t *labels, sindyn_keypoint *kps, uint8_t *desc,
                              int capacity, int *n_out);
 

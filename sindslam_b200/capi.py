@@ -99,6 +99,8 @@ SIGNATURES = {
     "sindyn_track_frame": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _vp, _i, _ip, _i]),
     "sindyn_track_frame_resident": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "sindyn_track_join": (_i, [_vp, _vp]),
+    "sindyn_track_submit": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, _i, _i, _i]),
+    "sindyn_track_collect": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _i, _ip]),
     "sindyn_track_get_results": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
     "sindyn_orb_get_pyramid_level": (_i, [_vp, _i, _vp, _ip, _ip]),
     "sindyn_orb_get_candidates": (_i, [_vp, _i, _vp, _i, _ip]),
@@ -513,6 +515,32 @@ class Orb:
         st = self.lib.sindyn_track_frame_resident(sd.h, self.h, slot, int(rgb_order), int(dilate_k), frame_idx)
         if st != 0:
             raise SindynError(f"track_frame_resident: {STATUS.get(st, st)}: {sd.lib.sindyn_last_error(sd.h).decode()}")
+
+    def track_submit(self, sd, bgr, depth, frame_idx, rgb_order=1, dilate_k=15):
+        """Asynchronous sindyn_track_frame: upload + enqueue frame `frame_idx` without waiting (at most two frames in flight).
+        bgr / depth must stay alive (and unchanged, if pinned) until the frame is collected."""
+        bgr, depth = _u8(bgr), np.ascontiguousarray(depth, np.uint16)
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((bgr, depth))
+        st = self.lib.sindyn_track_submit(sd.h, self.h, _p(bgr), bgr.strides[0], _p(depth), depth.strides[0], int(rgb_order), int(dilate_k), frame_idx)
+        if st != 0:
+            self._inflight.pop()
+            raise SindynError(f"track_submit: {STATUS.get(st, st)}: {sd.lib.sindyn_last_error(sd.h).decode()}")
+
+    def track_collect(self, sd, mask_out=None, label_out=None, kps_out=None, desc_out=None):
+        """Results of the oldest submitted frame: (mask, labels, keypoints, descriptors)."""
+        cap = self.nfeatures * 2 + 64
+        mask = mask_out if mask_out is not None else np.empty((self.H, self.W), np.uint8)
+        label = label_out if label_out is not None else np.empty((self.H, self.W), np.uint8)
+        kps = kps_out if kps_out is not None else np.zeros(cap, self.KP_DTYPE)
+        desc = desc_out if desc_out is not None else np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        st = self.lib.sindyn_track_collect(sd.h, self.h, _p(mask), 0, _p(label), 0, _p(kps), _p(desc), min(cap, len(kps)), C.byref(n))
+        if getattr(self, "_inflight", None):
+            self._inflight.pop(0)
+        if st != 0:
+            raise SindynError(f"track_collect: {STATUS.get(st, st)}: {sd.lib.sindyn_last_error(sd.h).decode()}")
+        return mask, label, kps[: n.value], desc[: n.value]
 
     def track_join(self, sd):
         """Everything the resident frames have enqueued (several streams) precedes the next operation on sd's stream."""

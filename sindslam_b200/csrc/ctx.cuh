@@ -102,6 +102,8 @@ void flow_collect_flag(sindyn_ctx *c);                     // flow.cu: large-mot
 int flow_part_a(sindyn_ctx *c, int parity);
 int flow_part_b(sindyn_ctx *c, int parity);
 int pipe_detect_run(sindyn_ctx *c, const uint8_t *bgr_dev, const uint16_t *depth_dev);   // pipe.cu: one frame through the frame pipeline
+struct PipeFlags { ReclusterControl rc; int edge_scalars[4]; int peac_hdr[4]; };   // capacity flags of one pipelined frame (pinned host memory)
+int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step, bool host_src, PipeFlags *flags);
 int pipe_join(sindyn_ctx *c);                              // pipe.cu: the handle's stream waits for everything the pipeline has enqueued
 void pipe_invalidate(sindyn_ctx *c);                       // pipe.cu: state was changed outside the pipeline: re-synchronise its streams
 void pipe_destroy(sindyn_ctx *c);                          // pipe.cu

@@ -833,7 +833,17 @@ __global__ void k_orb_gray_in(const uint8_t *__restrict__ bgr, int W, int H, int
 int detect_run_public(sindyn_ctx *c);        // detect.cu
 int detect_check_capacity(sindyn_ctx *c);    // detect.cu (synchronises the handle's stream)
 
-struct TrackSync { cudaEvent_t ev_in = nullptr, ev_mask = nullptr, ev_orb_done = nullptr; };
+struct TrackSync {
+    cudaEvent_t ev_in = nullptr, ev_mask = nullptr, ev_orb_done = nullptr;
+    // asynchronous entry (sindyn_track_submit / sindyn_track_collect): results of the frames in flight, pinned, by parity
+    uint8_t *r_mask[2] = {nullptr, nullptr}, *r_label[2] = {nullptr, nullptr}, *r_desc[2] = {nullptr, nullptr};
+    sindyn_keypoint *r_kp[2] = {nullptr, nullptr};
+    OrbControl *r_ctl[2] = {nullptr, nullptr};
+    PipeFlags *r_flags[2] = {nullptr, nullptr};
+    cudaEvent_t ev_res_main[2] = {}, ev_res_orb[2] = {};
+    int r_cap = 0;
+    unsigned long long n_submit = 0, n_collect = 0;
+};
 static TrackSync *track_sync(sindyn_orb *o)
 {
     if (!o->track) {
@@ -852,6 +862,10 @@ static void track_free(sindyn_orb *o)
     TrackSync *t = (TrackSync *)o->track;
     if (!t) return;
     cudaEventDestroy(t->ev_in); cudaEventDestroy(t->ev_mask); cudaEventDestroy(t->ev_orb_done);
+    for (int p = 0; p < 2; ++p) {
+        if (t->ev_res_main[p]) cudaEventDestroy(t->ev_res_main[p]);
+        if (t->ev_res_orb[p]) cudaEventDestroy(t->ev_res_orb[p]);
+    }
     delete t;
     o->track = nullptr;
 }
@@ -923,14 +937,15 @@ int pipe_note_gray_read(sindyn_ctx *c, cudaStream_t orb_stream);   // pipe.cu
 
 // the same through the frame pipeline (pipe.cu): the detector's image-only stages of this frame may run while the previous
 // frame is still being decided; the inputs are device buffers the pipeline copies on its own stream
-static int track_enqueue_pipe(sindyn_ctx *c, sindyn_orb *o, const uint8_t *bgr_dev, const uint16_t *depth_dev, int rgb_order, int dilate_k)
+static int track_enqueue_pipe(sindyn_ctx *c, sindyn_orb *o, const uint8_t *bgr_src, size_t bgr_step, const uint16_t *depth_src, size_t depth_step, bool host_src,
+                              PipeFlags *flags, int rgb_order, int dilate_k)
 {
     if (o->device != c->device || o->W != c->W || o->H != c->H) { c->err = "track_frame: the two handles differ in device or image size"; return SINDYN_ERR_INVALID; }
     if (dilate_k < 0 || dilate_k > MORPH_MAX_K) { c->err = "track_frame: dilate_k out of range"; return SINDYN_ERR_INVALID; }
     TrackSync *t = track_sync(o);
     const OrbLevel &L0 = o->lv[0];
     const uint8_t *bgr = c->bgr[c->i_cur];
-    SD_CHECK(pipe_detect_run(c, bgr_dev, depth_dev));
+    SD_CHECK(pipe_detect_run_src(c, bgr_src, bgr_step, depth_src, depth_step, host_src, flags));
     CU_CHECK(o, cudaStreamWaitEvent(o->stream, pipe_input_event(c), 0));
     LAUNCH(o, k_orb_gray_in, dim3(cdiv(o->W, 32), cdiv(o->H, 8)), dim3(32, 8), 0, bgr, o->W, o->H, rgb_order,
            o->pyr + (size_t)ORB_EDGE * L0.pitch + ORB_EDGE, L0.pitch);
@@ -953,7 +968,7 @@ extern "C" int sindyn_track_frame_resident(sindyn_handle h, sindyn_orb_handle o,
     if (!h || !o) return SINDYN_ERR_INVALID;
     cudaSetDevice(h->device);
     if (slot < 0 || slot >= SINDYN_MAX_SLOTS || !h->slot_bgr[slot]) { h->err = "track_frame_resident: empty slot"; return SINDYN_ERR_INVALID; }
-    if (pipe_usable(h)) return track_enqueue_pipe(h, o, h->slot_bgr[slot], h->slot_depth[slot], rgb_order, dilate_k);
+    if (pipe_usable(h)) return track_enqueue_pipe(h, o, h->slot_bgr[slot], 0, h->slot_depth[slot], 0, false, nullptr, rgb_order, dilate_k);
     CU_CHECK(h, cudaMemcpyAsync(h->bgr[h->i_cur], h->slot_bgr[slot], (size_t)h->N * 3, cudaMemcpyDeviceToDevice, h->stream));
     CU_CHECK(h, cudaMemcpyAsync(h->depth, h->slot_depth[slot], (size_t)h->N * 2, cudaMemcpyDeviceToDevice, h->stream));
     return track_enqueue(h, o, rgb_order, dilate_k);
@@ -967,6 +982,81 @@ extern "C" int sindyn_track_join(sindyn_handle h, sindyn_orb_handle o)
     cudaSetDevice(h->device);
     SD_CHECK(pipe_join(h));
     if (o->track) CU_CHECK(h, cudaStreamWaitEvent(h->stream, ((TrackSync *)o->track)->ev_orb_done, 0));
+    return SINDYN_OK;
+}
+
+// ---------------------------------------------------------------- asynchronous per-frame entry: submit frame i + 1, then collect frame i
+// sindyn_track_frame returns a frame's results before it accepts the next frame, so the GPU never sees two frames at once.  A
+// caller that has the next image at hand (a dataset on disk, rgbd_tum_noros.cc:113-192; a camera running ahead of the tracker)
+// submits it first: the upload and the image-only stages of frame i + 1 then overlap the decision, the extractor and the
+// download of frame i (pipe.cu).  At most two frames are in flight; results are collected in submission order.
+static int track_async_init(sindyn_ctx *c, sindyn_orb *o, TrackSync *t)
+{
+    if (t->r_mask[0]) return SINDYN_OK;
+    t->r_cap = o->nfeatures * 2 + 64 < ORB_OUT_MAX ? o->nfeatures * 2 + 64 : ORB_OUT_MAX;
+    for (int p = 0; p < 2; ++p) {
+        SD_CHECK(o->halloc(&t->r_mask[p], (size_t)c->N));
+        SD_CHECK(o->halloc(&t->r_label[p], (size_t)c->N));
+        SD_CHECK(o->halloc(&t->r_kp[p], (size_t)t->r_cap));
+        SD_CHECK(o->halloc(&t->r_desc[p], (size_t)t->r_cap * 32));
+        SD_CHECK(o->halloc(&t->r_ctl[p], 1));
+        SD_CHECK(o->halloc(&t->r_flags[p], 1));
+        CU_CHECK(o, cudaEventCreateWithFlags(&t->ev_res_main[p], cudaEventDisableTiming));
+        CU_CHECK(o, cudaEventCreateWithFlags(&t->ev_res_orb[p], cudaEventDisableTiming));
+    }
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_track_submit(sindyn_handle h, sindyn_orb_handle o, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step,
+                                   int rgb_order, int dilate_k, int frame_idx)
+{
+    (void)frame_idx;
+    if (!h || !o || !bgr || !depth) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    if (!pipe_usable(h)) { h->err = "track_submit: needs the CUDA-graph path (use_graphs = 1, stage_timing = 0)"; return SINDYN_ERR_STATE; }
+    TrackSync *t = track_sync(o);
+    SD_CHECK(track_async_init(h, o, t));
+    if (t->n_submit - t->n_collect >= 2) { h->err = "track_submit: two frames are in flight already, collect one first"; return SINDYN_ERR_STATE; }
+    const int p = (int)(t->n_submit & 1);
+    SD_CHECK(track_enqueue_pipe(h, o, bgr, bgr_step, depth, depth_step, true, t->r_flags[p], rgb_order, dilate_k));
+    // results into this parity's pinned buffers: mask and labels on the detector's stream (the labels from the rolled state: the
+    // next frame's re-clustering may already overwrite rc.label_out), key points on the extractor's
+    CU_CHECK(h, cudaMemcpyAsync(t->r_mask[p], o->mask, h->N, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaMemcpyAsync(t->r_label[p], h->label_last, h->N, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaEventRecord(t->ev_res_main[p], h->stream));
+    CU_CHECK(o, cudaMemcpyAsync(t->r_ctl[p], o->ctl, sizeof(OrbControl), cudaMemcpyDeviceToHost, o->stream));
+    CU_CHECK(o, cudaMemcpyAsync(t->r_kp[p], o->out_host_fmt, sizeof(sindyn_keypoint) * t->r_cap, cudaMemcpyDeviceToHost, o->stream));
+    CU_CHECK(o, cudaMemcpyAsync(t->r_desc[p], o->desc, (size_t)32 * t->r_cap, cudaMemcpyDeviceToHost, o->stream));
+    CU_CHECK(o, cudaEventRecord(t->ev_res_orb[p], o->stream));
+    ++t->n_submit;
+    return SINDYN_OK;
+}
+
+extern "C" int sindyn_track_collect(sindyn_handle h, sindyn_orb_handle o, uint8_t *mask_out, size_t mask_step, uint8_t *label_out, size_t label_step,
+                                    sindyn_keypoint *kps, uint8_t *desc, int capacity, int *n_out)
+{
+    if (!h || !o || !n_out) return SINDYN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    *n_out = 0;
+    TrackSync *t = (TrackSync *)o->track;
+    if (!t || t->n_collect >= t->n_submit) { h->err = "track_collect: no frame in flight"; return SINDYN_ERR_STATE; }
+    const int p = (int)(t->n_collect & 1);
+    ++t->n_collect;
+    CU_CHECK(h, cudaEventSynchronize(t->ev_res_main[p]));
+    CU_CHECK(o, cudaEventSynchronize(t->ev_res_orb[p]));
+    const PipeFlags *f = t->r_flags[p];
+    if (f->peac_hdr[2]) { h->err = "plane fitter: a fixed-capacity list overflowed (> 64 planes, > 512 neighbours of one node, or a region-growing level > 131072 entries)"; return SINDYN_ERR_CAPACITY; }
+    if (f->rc.overflow) { h->err = "recluster: more than RC_MAXC components"; return SINDYN_ERR_CAPACITY; }
+    if (f->rc.pf_overflow) { h->err = "plane-edge filter: more than RC_PF_MAXC contours"; return SINDYN_ERR_CAPACITY; }
+    if (f->edge_scalars[3]) { h->err = "depth_edges: more than EDGE_EP_CAP candidate end points"; return SINDYN_ERR_CAPACITY; }
+    if (t->r_ctl[p]->overflow) { h->err = o->err = "orb: a fixed-capacity list overflowed (candidates / nodes / output)"; return SINDYN_ERR_CAPACITY; }
+    const int n = t->r_ctl[p]->n_out;
+    *n_out = n;
+    if (n > capacity || n > t->r_cap) { h->err = o->err = "orb: output capacity too small"; return SINDYN_ERR_CAPACITY; }
+    if (mask_out) stage_out_finish(mask_out, mask_step, t->r_mask[p], h->W, h->H);
+    if (label_out) stage_out_finish(label_out, label_step, t->r_label[p], h->W, h->H);
+    if (n && kps) memcpy(kps, t->r_kp[p], sizeof(sindyn_keypoint) * n);
+    if (n && desc) memcpy(desc, t->r_desc[p], (size_t)32 * n);
     return SINDYN_OK;
 }
 

@@ -33,6 +33,9 @@ struct FramePipe {
     bool fresh = true;                              // the pipeline's streams have to wait for the handle's stream first
     int last_slot = 0, last_parity = 0;
     int hdr_host[2][4] = {};
+    uint8_t *in_bgr[2] = {nullptr, nullptr};        // pinned bounce buffers for pageable host inputs (asynchronous submit)
+    uint16_t *in_depth[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {};
     // what the handle's own pointers were before the pipeline redirected them
     float *own_flow_full = nullptr; int *own_fb_flag = nullptr, *own_fb_flag_host = nullptr; uint16_t *own_depth = nullptr; uint8_t *own_plane_edges = nullptr;
 };
@@ -73,6 +76,7 @@ static int pipe_init(sindyn_ctx *c)
         CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_a[p], cudaEventDisableTiming));
         CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_p[p], cudaEventDisableTiming));
         CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_done[p], cudaEventDisableTiming));
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_h2d[p], cudaEventDisableTiming));
     }
     for (int k = 0; k < 3; ++k) CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_gray[k], cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
@@ -87,7 +91,7 @@ void pipe_destroy(sindyn_ctx *c)
     pipe_drop_graphs(P);
     c->flow_full = P->own_flow_full; c->fb_flag = P->own_fb_flag; c->fb_flag_host = P->own_fb_flag_host; c->depth = P->own_depth; c->plane_edges = P->own_plane_edges;
     for (int p = 0; p < 2; ++p) {
-        cudaEventDestroy(P->ev_in[p]); cudaEventDestroy(P->ev_a[p]); cudaEventDestroy(P->ev_p[p]); cudaEventDestroy(P->ev_done[p]);
+        cudaEventDestroy(P->ev_in[p]); cudaEventDestroy(P->ev_a[p]); cudaEventDestroy(P->ev_p[p]); cudaEventDestroy(P->ev_done[p]); cudaEventDestroy(P->ev_h2d[p]);
     }
     for (int k = 0; k < 3; ++k) cudaEventDestroy(P->ev_gray[k]);
     cudaEventDestroy(P->ev_join); cudaEventDestroy(P->ev_sync);
@@ -162,7 +166,11 @@ template <class F> static int pipe_capture(sindyn_ctx *c, cudaStream_t s, cudaGr
     return SINDYN_OK;
 }
 
-int pipe_detect_run(sindyn_ctx *c, const uint8_t *bgr_dev, const uint16_t *depth_dev)
+int pipe_detect_run(sindyn_ctx *c, const uint8_t *bgr_dev, const uint16_t *depth_dev) { return pipe_detect_run_src(c, bgr_dev, 0, depth_dev, 0, false, nullptr); }
+
+// host_src: bgr / depth are (pitched) host images; flags (pinned, optional): capacity flags of this frame, copied before a later
+// frame can reset them -- valid once the handle's stream has passed the event the caller records next
+int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step, bool host_src, PipeFlags *flags)
 {
     if (!c->have_prev) { c->err = "detect: call sindyn_set_prev_frames first"; return SINDYN_ERR_STATE; }
     SD_CHECK(pipe_init(c));
@@ -182,8 +190,21 @@ int pipe_detect_run(sindyn_ctx *c, const uint8_t *bgr_dev, const uint16_t *depth
     // ---- stream A: inputs, gray / resize, Brox .. up-sampling
     CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_done[p], 0));                 // frame i - 2 has finished with the buffers of this parity
     if (P->gray_pending[slot]) CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_gray[slot], 0));   // ... and the extractor with this ring slot
-    CU_CHECK(c, cudaMemcpyAsync(c->bgr[slot], bgr_dev, (size_t)c->N * 3, cudaMemcpyDeviceToDevice, sa));
-    CU_CHECK(c, cudaMemcpyAsync(c->depth, depth_dev, (size_t)c->N * 2, cudaMemcpyDeviceToDevice, sa));
+    if (!host_src) {
+        CU_CHECK(c, cudaMemcpyAsync(c->bgr[slot], bgr, (size_t)c->N * 3, cudaMemcpyDeviceToDevice, sa));
+        CU_CHECK(c, cudaMemcpyAsync(c->depth, depth, (size_t)c->N * 2, cudaMemcpyDeviceToDevice, sa));
+    } else {
+        // pinned caller memory is read by the DMA directly; pageable memory goes through this parity's bounce buffers (free
+        // again once the copies of frame i - 2 are done)
+        const bool pin_b = host_ptr_is_pinned(bgr), pin_d = host_ptr_is_pinned(depth);
+        if (!pin_b || !pin_d) {
+            if (!P->in_bgr[p]) { SD_CHECK(c->halloc(&P->in_bgr[p], (size_t)c->N * 3)); SD_CHECK(c->halloc(&P->in_depth[p], (size_t)c->N)); }
+            CU_CHECK(c, cudaEventSynchronize(P->ev_h2d[p]));
+        }
+        CU_CHECK(c, stage_in_2d(c->bgr[slot], bgr, bgr_step, (size_t)c->W * 3, c->H, pin_b ? nullptr : P->in_bgr[p], sa));
+        CU_CHECK(c, stage_in_2d(c->depth, depth, depth_step, (size_t)c->W * 2, c->H, pin_d ? nullptr : P->in_depth[p], sa));
+        CU_CHECK(c, cudaEventRecord(P->ev_h2d[p], sa));
+    }
     if (!c->cfg.plane_edges) CU_CHECK(c, cudaMemsetAsync(c->plane_edges, 0, c->N, sa));
     CU_CHECK(c, cudaEventRecord(P->ev_in[p], sa));
     c->stream = sa;
@@ -225,6 +246,12 @@ int pipe_detect_run(sindyn_ctx *c, const uint8_t *bgr_dev, const uint16_t *depth
     CU_CHECK(c, cudaMemcpyAsync(c->dyna_last, c->dd.out, c->N, cudaMemcpyDeviceToDevice, main_s));
     CU_CHECK(c, cudaMemcpyAsync(c->high_last, c->mask_high, c->N, cudaMemcpyDeviceToDevice, main_s));
     CU_CHECK(c, cudaMemcpyAsync(c->label_last, c->rc.label_out, c->N, cudaMemcpyDeviceToDevice, main_s));
+    if (flags) {
+        CU_CHECK(c, cudaMemcpyAsync(&flags->rc, c->rc.ctl, sizeof(ReclusterControl), cudaMemcpyDeviceToHost, main_s));
+        CU_CHECK(c, cudaMemcpyAsync(flags->edge_scalars, c->edges.scalars, sizeof(int) * 4, cudaMemcpyDeviceToHost, main_s));
+        flags->peac_hdr[0] = flags->peac_hdr[1] = flags->peac_hdr[2] = flags->peac_hdr[3] = 0;
+        if (c->cfg.plane_edges) SD_CHECK(peac_copy_header(c, &P->peac[p], flags->peac_hdr));
+    }
     CU_CHECK(c, cudaEventRecord(P->ev_done[p], main_s));
     P->last_slot = slot; P->last_parity = p;
     ++P->frame_no;

@@ -39,3 +39,50 @@ def test_track_frame_equals_separate_calls(rgb_order):
         assert np.array_equal(k3["x"], kps["x"]) and np.array_equal(k3["octave"], kps["octave"]), k
     for h in (oa, ob, oc, sa, sb, sc):
         h.close()
+
+
+def test_pipelined_frames_equal_frame_at_a_time():
+    """The frame pipeline (pipe.cu): frames enqueued back to back without a synchronisation (device-resident slots), and frames
+    submitted one ahead through sindyn_track_submit / sindyn_track_collect (pinned and pageable host buffers), must return exactly
+    what the frame-at-a-time entry returns -- 24 consecutive frames with free-running state, plane edges on."""
+    import torch
+    from sindslam_b200.capi import Orb, SinDyn
+    cam = synth.TUM3
+    n = 25
+    _, frames = synth.make_sequence(n, cam, seq=11, kind="box", start=3, hole_rate=0.0005)
+    mk = lambda: (SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, plane_edges=1), Orb(1500, 1.2, 8, 15, 5, cam.width, cam.height))
+    (sa, oa), (sb, ob), (sc, oc) = mk(), mk(), mk()
+    for s in (sa, sb, sc):
+        s.set_prev_frames(frames[0].bgr, frames[0].bgr)
+    ref = [oa.track_frame(sa, frames[k].bgr, frames[k].depth, k) for k in range(1, n)]
+    ref = [(m.copy(), l.copy(), kp.copy(), d.copy()) for m, l, kp, d in ref]
+
+    def same(got, want, k):
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), k
+        assert len(got[2]) == len(want[2]) and np.array_equal(got[3], want[3]), k
+        for name in ("x", "y", "angle", "response", "octave"):
+            assert np.array_equal(got[2][name], want[2][name]), (k, name)
+
+    # (a) submit one frame ahead: odd frames from pinned buffers, even frames from pageable ones
+    pinned = [(torch.from_numpy(frames[k].bgr.copy()).pin_memory().numpy(), torch.from_numpy(frames[k].depth.view(np.int16).copy()).pin_memory().numpy().view(np.uint16))
+              if k & 1 else (frames[k].bgr, frames[k].depth) for k in range(n)]
+    ob.track_submit(sb, pinned[1][0], pinned[1][1], 1)
+    for k in range(2, n):
+        ob.track_submit(sb, pinned[k][0], pinned[k][1], k)
+        same(ob.track_collect(sb), ref[k - 2], k - 1)
+    same(ob.track_collect(sb), ref[n - 2], n - 1)
+    with pytest.raises(Exception):
+        ob.track_collect(sb)               # nothing in flight
+    # the frame-at-a-time entry continues the same state afterwards
+    extra = synth.make_sequence(n + 1, cam, seq=11, kind="box", start=3, hole_rate=0.0005)[1][n]
+    want = oa.track_frame(sa, extra.bgr, extra.depth, n)
+    same(ob.track_frame(sb, extra.bgr, extra.depth, n), want, n)
+    # (b) resident slots, all frames enqueued without waiting; only the last frame's results are visible afterwards
+    for i, f in enumerate(frames):
+        sc.upload_frame(i, f.bgr, f.depth)
+    for k in range(1, n):
+        oc.track_frame_resident(sc, k, k)
+    oc.track_join(sc)
+    same(oc.track_results(sc), ref[n - 2], n - 1)
+    for h in (oa, ob, oc, sa, sb, sc):
+        h.close()
