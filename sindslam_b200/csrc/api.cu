@@ -56,7 +56,7 @@ extern "C" int sindyn_create(const sindyn_config *cfg, sindyn_handle *out)
     CU_CHECK(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     const size_t N = (size_t)c->N, NF = (size_t)c->fw * c->fh;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         SD_CHECK(c->dalloc(&c->bgr[i], N * 3));
         SD_CHECK(c->dalloc(&c->gray[i], N));
         SD_CHECK(c->dalloc(&c->gsmall[i], NF));

@@ -21,11 +21,14 @@ struct sindyn_ctx : sindyn_base {
     bool have_prev = false;
 
     // frames: BGR (W*H*3), gray full, gray small (u8 + float/255)
-    uint8_t *bgr[3] = {nullptr, nullptr, nullptr};  // ring: cur / last / lastlast by index rotation
-    uint8_t *gray[3] = {nullptr, nullptr, nullptr};
-    uint8_t *gsmall[3] = {nullptr, nullptr, nullptr};
-    float *gsmall_f[3] = {nullptr, nullptr, nullptr};
-    int i_cur = 0, i_last = 1, i_lastlast = 2;
+    // ring of four: cur / last / lastlast by index rotation + one spare slot, the next frame's cur (with two frames' flow
+    // solves in flight in the frame pipeline, the next frame is written while lastlast is still being read)
+    uint8_t *bgr[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *gray[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *gsmall[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *gsmall_f[4] = {nullptr, nullptr, nullptr, nullptr};
+    int i_cur = 0, i_last = 1, i_lastlast = 2, i_spare = 3;
+    void roll_ring() { const int t = i_spare; i_spare = i_lastlast; i_lastlast = i_last; i_last = i_cur; i_cur = t; }   // DynaDetect.cc:1661-1662
     uint16_t *depth = nullptr;
     // pinned bounce buffers of the per-frame entry points (see stage_in_2d)
     uint8_t *pin_bgr = nullptr, *pin_out0 = nullptr, *pin_out1 = nullptr;
@@ -86,6 +89,17 @@ struct sindyn_ctx : sindyn_base {
     bool ev_ok = false;
     int large_motion_last = 0;
 };
+
+// the resources one flow solve (part A of the branch) works in: the handle's own, or one of the frame pipeline's two sets
+struct FlowRes {
+    BroxSolver *brox, *brox_lm;
+    VarRefStage *varref;
+    float *fb_mag;
+    unsigned int *fb_hist;
+    int *fb_flag, *fb_flag_host;
+    float *flow_small, *flow_full;
+};
+FlowRes pipe_flow_res(sindyn_ctx *c, int parity);          // pipe.cu
 
 // internal cross-module helpers (C++ linkage)
 int sindyn_prep_frame(sindyn_ctx *c, int idx);          // api.cu: BGR -> gray -> 0.6x gray (u8 + float)

@@ -145,10 +145,7 @@ static int detect_run(sindyn_ctx *c)
     CU_CHECK(c, cudaMemcpyAsync(c->high_last, c->mask_high, c->N, cudaMemcpyDeviceToDevice, main_s));
     CU_CHECK(c, cudaMemcpyAsync(c->label_last, c->rc.label_out, c->N, cudaMemcpyDeviceToDevice, main_s));
     MARK(c, 7);
-    int t = c->i_lastlast;
-    c->i_lastlast = c->i_last;
-    c->i_last = c->i_cur;
-    c->i_cur = t;
+    c->roll_ring();
     return SINDYN_OK;
 }
 

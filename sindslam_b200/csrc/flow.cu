@@ -89,7 +89,7 @@ void flow_graph_drop(sindyn_ctx *c)
 }
 
 // variant 0: the whole branch; variant 1 (frame pipeline): up to the up-sampled flow only
-static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t, int variant)
+static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t, int variant, const FlowRes &r)
 {
     const int nf = c->fw * c->fh;
     cudaGraph_t g = nullptr;
@@ -99,16 +99,16 @@ static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t, int variant
     CU_CHECK(c, cudaGraphConditionalHandleCreate(&cond, g, 0, cudaGraphCondAssignDefault));
     const unsigned long long before = c->launches;
     CU_CHECK(c, cudaStreamBeginCaptureToGraph(c->stream, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    int st = brox_run(c, &c->brox, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_lastlast], c->flow_small, -1.0f, false);
-    unsigned int *gmax = c->fb_hist + 256;
+    int st = brox_run(c, r.brox, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_lastlast], r.flow_small, -1.0f, false);
+    unsigned int *gmax = r.fb_hist + 256;
     cudaGraphNode_t cnode = nullptr;
     cudaGraph_t body = nullptr;
     cudaError_t e = cudaSuccess;
     if (st == SINDYN_OK) {
-        e = cudaMemsetAsync(c->fb_hist, 0, sizeof(unsigned int) * 260, c->stream);
-        LAUNCH(c, k_flow_mag, cdiv(nf, 256), 256, 0, (const float2 *)c->flow_small, nf, c->fb_mag, gmax);
-        LAUNCH(c, k_u8_hist, SINDYN_NUM_SMS_B200, 256, 0, c->fb_mag, nf, gmax, c->fb_hist);
-        LAUNCH(c, k_large_motion, 1, 32, 0, c->fb_hist, gmax, c->W, c->H, c->cfg.flow_scale, c->fb_flag, cond, 1);
+        e = cudaMemsetAsync(r.fb_hist, 0, sizeof(unsigned int) * 260, c->stream);
+        LAUNCH(c, k_flow_mag, cdiv(nf, 256), 256, 0, (const float2 *)r.flow_small, nf, r.fb_mag, gmax);
+        LAUNCH(c, k_u8_hist, SINDYN_NUM_SMS_B200, 256, 0, r.fb_mag, nf, gmax, r.fb_hist);
+        LAUNCH(c, k_large_motion, 1, 32, 0, r.fb_hist, gmax, c->W, c->H, c->cfg.flow_scale, r.fb_flag, cond, 1);
         // the IF node hangs off everything captured so far; what is captured next hangs off the IF node
         cudaStreamCaptureStatus cs;
         const cudaGraphNode_t *deps = nullptr;
@@ -125,14 +125,14 @@ static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t, int variant
     }
     if (st == SINDYN_OK && e == cudaSuccess) {
         if (c->cfg.refine)
-            st = varref_run_sel(c, &c->varref, c->gsmall[c->i_cur], c->gsmall[c->i_lastlast], c->gsmall[c->i_last], c->fb_flag, c->flow_small);
-        if (st == SINDYN_OK) st = launch_resize_flow(c, c->flow_small, c->fw, c->fh, c->flow_full, c->W, c->H, 1.0f / c->cfg.flow_scale);
+            st = varref_run_sel(c, r.varref, c->gsmall[c->i_cur], c->gsmall[c->i_lastlast], c->gsmall[c->i_last], r.fb_flag, r.flow_small);
+        if (st == SINDYN_OK) st = launch_resize_flow(c, r.flow_small, c->fw, c->fh, r.flow_full, c->W, c->H, 1.0f / c->cfg.flow_scale);
         if (variant == 0) {
-            if (st == SINDYN_OK) st = homography_sample(c, &c->homog, c->flow_full, c->label_last, c->dyna_last);
+            if (st == SINDYN_OK) st = homography_sample(c, &c->homog, r.flow_full, c->label_last, c->dyna_last);
             if (st == SINDYN_OK) st = homography_estimate(c, &c->homog);
-            if (st == SINDYN_OK) st = residual_homography_run_dev(c, &c->resid, c->flow_full, c->homog.H_dev, c->mask_low, c->mask_high);
+            if (st == SINDYN_OK) st = residual_homography_run_dev(c, &c->resid, r.flow_full, c->homog.H_dev, c->mask_low, c->mask_high);
         }
-        if (st == SINDYN_OK) e = cudaMemcpyAsync(c->fb_flag_host, c->fb_flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (st == SINDYN_OK) e = cudaMemcpyAsync(r.fb_flag_host, r.fb_flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream);
     }
     cudaGraph_t g_out = nullptr;
     const cudaError_t e_end = cudaStreamEndCapture(c->stream, &g_out);
@@ -144,7 +144,7 @@ static int flow_graph_build(sindyn_ctx *c, sindyn_ctx::FlowGraph *t, int variant
         const unsigned long long b0 = c->launches;
         e_body = cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
         if (e_body == cudaSuccess) {
-            st = brox_run(c, &c->brox_lm, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_last], c->flow_small, -1.0f, false);
+            st = brox_run(c, r.brox_lm, c->gsmall_f[c->i_cur], c->gsmall_f[c->i_last], r.flow_small, -1.0f, false);
             cudaGraph_t b_out = nullptr;
             e_body = cudaStreamEndCapture(c->stream, &b_out);
         }
@@ -178,7 +178,8 @@ static int flow_graph_launch(sindyn_ctx *c, bool *launched, int variant = 0)
         if (t->exec) cudaGraphExecDestroy(t->exec);
         if (t->graph) cudaGraphDestroy(t->graph);
         *t = sindyn_ctx::FlowGraph();
-        if (flow_graph_build(c, t, variant) != SINDYN_OK) {
+        const FlowRes own = {&c->brox, &c->brox_lm, &c->varref, c->fb_mag, c->fb_hist, c->fb_flag, c->fb_flag_host, c->flow_small, c->flow_full};
+        if (flow_graph_build(c, t, variant, variant ? pipe_flow_res(c, variant - 1) : own) != SINDYN_OK) {
             // leave capture mode if the failure happened inside it, remember not to try again
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
             if (cudaStreamIsCapturing(c->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(c->stream, &junk); }

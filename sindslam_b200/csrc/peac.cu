@@ -47,6 +47,8 @@ struct PeacControl {
     int done, n_comp, grow_levels, grow_entries;
     int grow_n, grow_buf, hdr_pad[6];           // frontier handed from the cluster kernel to the single-CTA kernel
     int grow_tot[16];                           // per-CTA counts of the cluster kernel's ordered compaction
+    int sticky_overflow;                        // never reset: an overflow of ANY frame this instance has processed (frame pipeline: the
+                                                // header above may already belong to a later frame when the host looks)
     long long clk[PEAC_AHC_CTAS_MAX][12];      // PEAC_CLOCKS builds only
     int parent[PEAC_MAXB], size[PEAC_MAXB];
     int blk_map[PEAC_MAXB];
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
         }
         __syncthreads();
         const int NE = min(s_ne, PEAC_MAXE);
-        if (tid == 0 && s_ne > PEAC_MAXE) ctl->overflow = 1;
+        if (tid == 0 && s_ne > PEAC_MAXE) ctl->overflow = ctl->sticky_overflow = 1;
         PCLK(0);   // load + initial edges
         // ---- connected components of the initial graph: minimum-label propagation over the edges + pointer jumping
         for (;;) {
@@ -693,14 +695,14 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                 } else if (slot_t == 0) {   // extract p (or drop it) and cut it out of the graph
                     if (N_a[p] >= PEAC_MIN_SUPPORT) {
                         if (nex_base + my_ex_slot < PEAC_MAXP) { s_ex[nex_base + my_ex_slot] = p; s_exkey[nex_base + my_ex_slot] = mse_a[p]; }
-                        else ctl->overflow = 1;
+                        else ctl->overflow = ctl->sticky_overflow = 1;
                     }
                     flags[p] &= ~(PF_ALIVE | PF_QUEUED);
                 }
             }
             if (tid == 0) {
                 s_seq = seq_base + n_mrg; s_nex = min(nex_base + n_ext, PEAC_MAXP); s_nmerge = n_mrg;
-                for (int j = 0; j < PEAC_BATCH; ++j) { if (s_ncand[j] > PEAC_CANDK) ctl->overflow = 1; s_ncand[j] = 0; }
+                for (int j = 0; j < PEAC_BATCH; ++j) { if (s_ncand[j] > PEAC_CANDK) ctl->overflow = ctl->sticky_overflow = 1; s_ncand[j] = 0; }
             }
             // nodes this thread owns that changed: the committed p_j and their partners
 #pragma unroll
@@ -721,7 +723,7 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                 for (int d = 0; d < 9; ++d) x.st[d] = sst[r * 9 + d];
                 for (int d = 0; d < 3; ++d) x.normal[d] = nrm[3 * r + d];
                 x.mse = mse_a[r]; x.pop_key = s_exkey[tid]; x.N = N_a[r]; x.rid = r;
-            } else ctl->overflow = 1;
+            } else ctl->overflow = ctl->sticky_overflow = 1;
         }
         for (int b = tid; b < NB; b += nt)
             if ((flags[b] & PF_VALID)) { ctl->parent[b] = root[b]; ctl->size[b] = ssize[root[b]]; }
@@ -1162,7 +1164,7 @@ k_peac_grow_cluster(const uint16_t *__restrict__ depth, int W, int H, float fx, 
         if (s_conn[k]) atomicOr(&ctl->conn[k], s_conn[k]);
     if (g == 0) {
         ctl->grow_n = n; ctl->grow_buf = buf; ctl->grow_levels = levels; ctl->grow_entries = entries;
-        if (n > PG_CAP) ctl->overflow = 1;
+        if (n > PG_CAP) ctl->overflow = ctl->sticky_overflow = 1;
     }
 }
 
@@ -1231,7 +1233,7 @@ __global__ void __launch_bounds__(PG_FNT) k_peac_grow_fifo(const uint16_t *__res
 #define SEGT(i, t0_) do { } while (0)
 #endif
     while (n > 0) {
-        if (n > PG_CAP) { if (tid == 0) ctl->overflow = 1; break; }
+        if (n > PG_CAP) { if (tid == 0) ctl->overflow = ctl->sticky_overflow = 1; break; }
         ++levels; entries += n;
         int *nxt;
 #ifdef PEAC_CLOCKS
@@ -1563,6 +1565,7 @@ int peac_init(sindyn_base *ctx, PeacStage *p, int W, int H)
     if (im->Nw * im->Nh > PEAC_MAXB || im->Nw > 128 || im->Nh > 64) { ctx->err = "peac: image too large for the block tables"; return SINDYN_ERR_INVALID; }
     SD_CHECK(ctx->dalloc(&im->nodes, PEAC_MAXB));
     SD_CHECK(ctx->dalloc(&im->ctl, 1));
+    CU_CHECK(ctx, cudaMemsetAsync(im->ctl, 0, sizeof(PeacControl), ctx->stream));
     SD_CHECK(ctx->dalloc(&im->label, (size_t)W * H));
     SD_CHECK(ctx->dalloc(&im->dist, (size_t)W * H));
     SD_CHECK(ctx->dalloc(&im->head, (size_t)W * H));
@@ -1620,6 +1623,13 @@ int peac_copy_header(sindyn_base *ctx, PeacStage *p, int *host4)
 {
     PeacImpl *im = (PeacImpl *)p->impl;
     CU_CHECK(ctx, cudaMemcpyAsync(host4, im->ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return SINDYN_OK;
+}
+
+int peac_copy_sticky_overflow(sindyn_base *ctx, PeacStage *p, int *host1)
+{
+    PeacImpl *im = (PeacImpl *)p->impl;
+    CU_CHECK(ctx, cudaMemcpyAsync(host1, &im->ctl->sticky_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return SINDYN_OK;
 }
 

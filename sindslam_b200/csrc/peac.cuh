@@ -18,5 +18,7 @@ int peac_run(sindyn_base *ctx, PeacStage *p, ReclusterStage *rc, const uint16_t 
              float depth_scale, uint8_t *plane_edges_out);
 // asynchronous copy of the control header {n_planes, n_final, overflow, n_ex} (valid after the stream has been synchronised)
 int peac_copy_header(sindyn_base *ctx, PeacStage *p, int *host4);
+// asynchronous copy of the instance's sticky overflow flag (an overflow in any frame it has processed so far)
+int peac_copy_sticky_overflow(sindyn_base *ctx, PeacStage *p, int *host1);
 // test hook: final membership image (final plane id or -1), extracted planes (rid, N, final id), counts
 int peac_get_debug(sindyn_base *ctx, PeacStage *p, int *label_out, int *planes_rid_n, int *n_planes, int *n_final);

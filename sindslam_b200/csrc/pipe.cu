@@ -15,23 +15,29 @@
 // Results are bit-identical to the frame-at-a-time path (same kernels, same inputs, same order per buffer).
 #include "ctx.cuh"
 
+#define PIPE_NB 4
 struct FramePipe {
-    cudaStream_t sa = nullptr;                      // part A (+ the input copies)
+    cudaStream_t sa[2] = {nullptr, nullptr};        // part A (+ the input copies) of even / odd frames: two frames' flow solves overlap
+    BroxSolver brox[2], brox_lm[2];                 // ... each in its own solver / refinement / scratch (index 1; index 0 = the handle's)
+    VarRefStage varref1;
+    float *fb_mag1 = nullptr, *flow_small1 = nullptr;
+    unsigned int *fb_hist1 = nullptr;
     cudaStream_t sp[2] = {nullptr, nullptr};        // plane fitter of even / odd frames (2.6 ms each: two frames' fitters overlap)
-    float *flow_full[2] = {nullptr, nullptr};
-    int *fb_flag[2] = {nullptr, nullptr}, *fb_flag_host[2] = {nullptr, nullptr};
-    uint16_t *depth[2] = {nullptr, nullptr};
-    uint8_t *plane_edges[2] = {nullptr, nullptr};
+    // buffers a later frame's image-only stages overwrite while an earlier frame still reads them: ring of PIPE_NB, k = frame % PIPE_NB
+    float *flow_full[PIPE_NB] = {};
+    int *fb_flag[PIPE_NB] = {}, *fb_flag_host[PIPE_NB] = {};
+    uint16_t *depth[PIPE_NB] = {};
+    uint8_t *plane_edges[PIPE_NB] = {};
     PeacStage peac[2];
     ReclusterStage rc_peac[2];
-    cudaEvent_t ev_in[2] = {}, ev_a[2] = {}, ev_p[2] = {}, ev_done[2] = {}, ev_join = nullptr, ev_sync = nullptr, ev_gray[3] = {};
-    bool gray_pending[3] = {false, false, false};
-    cudaGraphExec_t g_c1[2] = {nullptr, nullptr}, g_c2[2] = {nullptr, nullptr}, g_p[2] = {nullptr, nullptr};
-    unsigned long long n_c1[2] = {0, 0}, n_c2[2] = {0, 0}, n_p[2] = {0, 0};
+    cudaEvent_t ev_in[PIPE_NB] = {}, ev_a[PIPE_NB] = {}, ev_p[PIPE_NB] = {}, ev_done[PIPE_NB] = {}, ev_join = nullptr, ev_sync = nullptr, ev_gray[4] = {};
+    bool gray_pending[4] = {false, false, false, false};
+    cudaGraphExec_t g_c1[PIPE_NB] = {}, g_c2[PIPE_NB] = {}, g_p[PIPE_NB] = {};
+    unsigned long long n_c1[PIPE_NB] = {}, n_c2[PIPE_NB] = {}, n_p[PIPE_NB] = {};
     cudaStream_t built_for = nullptr;               // the handle stream the graphs were captured under
     unsigned long long frame_no = 0;
     bool fresh = true;                              // the pipeline's streams have to wait for the handle's stream first
-    int last_slot = 0, last_parity = 0;
+    int last_slot = 0, last_k = 0;
     int hdr_host[2][4] = {};
     uint8_t *in_bgr[2] = {nullptr, nullptr};        // pinned bounce buffers for pageable host inputs (asynchronous submit)
     uint16_t *in_depth[2] = {nullptr, nullptr};
@@ -44,7 +50,7 @@ bool pipe_usable(const sindyn_ctx *c) { return c->cfg.use_graphs && !c->cfg.stag
 
 static void pipe_drop_graphs(FramePipe *P)
 {
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < PIPE_NB; ++p) {
         if (P->g_c1[p]) cudaGraphExecDestroy(P->g_c1[p]);
         if (P->g_c2[p]) cudaGraphExecDestroy(P->g_c2[p]);
         if (P->g_p[p]) cudaGraphExecDestroy(P->g_p[p]);
@@ -57,28 +63,42 @@ static int pipe_init(sindyn_ctx *c)
     if (c->pipe) return SINDYN_OK;
     FramePipe *P = new FramePipe();
     c->pipe = P;
-    CU_CHECK(c, cudaStreamCreateWithFlags(&P->sa, cudaStreamNonBlocking));
+    CU_CHECK(c, cudaStreamCreateWithFlags(&P->sa[0], cudaStreamNonBlocking));
+    CU_CHECK(c, cudaStreamCreateWithFlags(&P->sa[1], cudaStreamNonBlocking));
+    {
+        const sindyn_config &g = c->cfg;
+        SD_CHECK(brox_init(c, &P->brox[1], c->fw, c->fh, g.brox_alpha, g.brox_gamma, g.brox_pyr_scale, g.brox_inner, g.brox_outer, g.brox_solver, g.brox_omega));
+        SD_CHECK(brox_init(c, &P->brox_lm[1], c->fw, c->fh, g.brox_alpha, g.brox_gamma, g.brox_pyr_scale, g.brox_inner, g.brox_outer, g.brox_solver, g.brox_omega));
+        SD_CHECK(varref_init(c, &P->varref1, c->fw, c->fh));
+        SD_CHECK(c->dalloc(&P->fb_mag1, (size_t)c->fw * c->fh));
+        SD_CHECK(c->dalloc(&P->fb_hist1, 260));
+        SD_CHECK(c->dalloc(&P->flow_small1, (size_t)c->fw * c->fh * 2));
+    }
     P->sp[0] = c->stream3;
     CU_CHECK(c, cudaStreamCreateWithFlags(&P->sp[1], cudaStreamNonBlocking));
     P->own_flow_full = c->flow_full; P->own_fb_flag = c->fb_flag; P->own_fb_flag_host = c->fb_flag_host; P->own_depth = c->depth; P->own_plane_edges = c->plane_edges;
     P->flow_full[0] = c->flow_full; P->fb_flag[0] = c->fb_flag; P->fb_flag_host[0] = c->fb_flag_host; P->depth[0] = c->depth; P->plane_edges[0] = c->plane_edges;
-    SD_CHECK(c->dalloc(&P->flow_full[1], (size_t)c->N * 2));
-    SD_CHECK(c->dalloc(&P->fb_flag[1], 4));
-    SD_CHECK(c->halloc(&P->fb_flag_host[1], 4));
-    SD_CHECK(c->dalloc(&P->depth[1], (size_t)c->N));
-    SD_CHECK(c->dalloc(&P->plane_edges[1], (size_t)c->N));
+    for (int k = 1; k < PIPE_NB; ++k) {
+        SD_CHECK(c->dalloc(&P->flow_full[k], (size_t)c->N * 2));
+        SD_CHECK(c->dalloc(&P->fb_flag[k], 4));
+        SD_CHECK(c->halloc(&P->fb_flag_host[k], 4));
+        SD_CHECK(c->dalloc(&P->depth[k], (size_t)c->N));
+        SD_CHECK(c->dalloc(&P->plane_edges[k], (size_t)c->N));
+    }
+    for (int k = 0; k < PIPE_NB; ++k) {
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_in[k], cudaEventDisableTiming));
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_a[k], cudaEventDisableTiming));
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_p[k], cudaEventDisableTiming));
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_done[k], cudaEventDisableTiming));
+    }
     for (int p = 0; p < 2; ++p) {
         if (c->cfg.plane_edges) {
             SD_CHECK(peac_init(c, &P->peac[p], c->W, c->H));
             SD_CHECK(recluster_init(c, &P->rc_peac[p], c->W, c->H));
         }
-        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_in[p], cudaEventDisableTiming));
-        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_a[p], cudaEventDisableTiming));
-        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_p[p], cudaEventDisableTiming));
-        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_done[p], cudaEventDisableTiming));
         CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_h2d[p], cudaEventDisableTiming));
     }
-    for (int k = 0; k < 3; ++k) CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_gray[k], cudaEventDisableTiming));
+    for (int k = 0; k < 4; ++k) CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_gray[k], cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_sync, cudaEventDisableTiming));
     return SINDYN_OK;
@@ -90,12 +110,13 @@ void pipe_destroy(sindyn_ctx *c)
     if (!P) return;
     pipe_drop_graphs(P);
     c->flow_full = P->own_flow_full; c->fb_flag = P->own_fb_flag; c->fb_flag_host = P->own_fb_flag_host; c->depth = P->own_depth; c->plane_edges = P->own_plane_edges;
-    for (int p = 0; p < 2; ++p) {
-        cudaEventDestroy(P->ev_in[p]); cudaEventDestroy(P->ev_a[p]); cudaEventDestroy(P->ev_p[p]); cudaEventDestroy(P->ev_done[p]); cudaEventDestroy(P->ev_h2d[p]);
-    }
-    for (int k = 0; k < 3; ++k) cudaEventDestroy(P->ev_gray[k]);
+    for (int k = 0; k < PIPE_NB; ++k) { cudaEventDestroy(P->ev_in[k]); cudaEventDestroy(P->ev_a[k]); cudaEventDestroy(P->ev_p[k]); cudaEventDestroy(P->ev_done[k]); }
+    for (int p = 0; p < 2; ++p) cudaEventDestroy(P->ev_h2d[p]);
+    for (int k = 0; k < 4; ++k) cudaEventDestroy(P->ev_gray[k]);
+    brox_destroy(&P->brox[1]); brox_destroy(&P->brox_lm[1]);
     cudaEventDestroy(P->ev_join); cudaEventDestroy(P->ev_sync);
-    if (P->sa) cudaStreamDestroy(P->sa);
+    if (P->sa[0]) cudaStreamDestroy(P->sa[0]);
+    if (P->sa[1]) cudaStreamDestroy(P->sa[1]);
     if (P->sp[1]) cudaStreamDestroy(P->sp[1]);
     delete P;
     c->pipe = nullptr;
@@ -111,7 +132,7 @@ int pipe_join(sindyn_ctx *c)
 {
     FramePipe *P = c->pipe;
     if (!P) return SINDYN_OK;
-    cudaStream_t ss[4] = {P->sa, c->stream2, P->sp[0], P->sp[1]};
+    cudaStream_t ss[5] = {P->sa[0], P->sa[1], c->stream2, P->sp[0], P->sp[1]};
     for (cudaStream_t s : ss) {
         CU_CHECK(c, cudaEventRecord(P->ev_sync, s));
         CU_CHECK(c, cudaStreamWaitEvent(c->stream, P->ev_sync, 0));
@@ -119,7 +140,14 @@ int pipe_join(sindyn_ctx *c)
     return SINDYN_OK;
 }
 
-cudaEvent_t pipe_input_event(sindyn_ctx *c) { return c->pipe ? c->pipe->ev_in[c->pipe->last_parity] : nullptr; }
+FlowRes pipe_flow_res(sindyn_ctx *c, int k)     // k = frame % PIPE_NB: output buffers k, solver set k & 1
+{
+    FramePipe *P = c->pipe;
+    if ((k & 1) == 0) return FlowRes{&c->brox, &c->brox_lm, &c->varref, c->fb_mag, c->fb_hist, P->fb_flag[k], P->fb_flag_host[k], c->flow_small, P->flow_full[k]};
+    return FlowRes{&P->brox[1], &P->brox_lm[1], &P->varref1, P->fb_mag1, P->fb_hist1, P->fb_flag[k], P->fb_flag_host[k], P->flow_small1, P->flow_full[k]};
+}
+
+cudaEvent_t pipe_input_event(sindyn_ctx *c) { return c->pipe ? c->pipe->ev_in[c->pipe->last_k] : nullptr; }
 
 // the ORB extractor reads the BGR ring slot of the frame on its own stream: the slot may be overwritten only after that
 int pipe_note_gray_read(sindyn_ctx *c, cudaStream_t orb_stream)
@@ -136,7 +164,7 @@ int pipe_copy_headers(sindyn_ctx *c)
     FramePipe *P = c->pipe;
     if (!P || !c->cfg.plane_edges) return SINDYN_OK;
     for (int p = 0; p < 2; ++p)
-        if (P->peac[p].built) SD_CHECK(peac_copy_header(c, &P->peac[p], P->hdr_host[p]));
+        if (P->peac[p].built) SD_CHECK(peac_copy_sticky_overflow(c, &P->peac[p], &P->hdr_host[p][2]));
     return SINDYN_OK;
 }
 
@@ -175,20 +203,23 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     if (!c->have_prev) { c->err = "detect: call sindyn_set_prev_frames first"; return SINDYN_ERR_STATE; }
     SD_CHECK(pipe_init(c));
     FramePipe *P = c->pipe;
-    cudaStream_t main_s = c->stream, s2 = c->stream2, sa = P->sa;
+    cudaStream_t main_s = c->stream, s2 = c->stream2;
     if (P->built_for != main_s) { pipe_drop_graphs(P); P->built_for = main_s; }
-    const int p = (int)(P->frame_no & 1), slot = c->i_cur;
+    const int k = (int)(P->frame_no % PIPE_NB), p = k & 1, slot = c->i_cur;    // buffers k, solver / fitter instance and streams p
     if (P->fresh) {   // whatever the handle's stream has done so far (state set by the caller, frames of the other path) comes first
         CU_CHECK(c, cudaEventRecord(P->ev_sync, main_s));
-        CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_sync, 0));
+        CU_CHECK(c, cudaStreamWaitEvent(P->sa[0], P->ev_sync, 0));
+        CU_CHECK(c, cudaStreamWaitEvent(P->sa[1], P->ev_sync, 0));
         CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_sync, 0));
         CU_CHECK(c, cudaStreamWaitEvent(P->sp[0], P->ev_sync, 0));
         CU_CHECK(c, cudaStreamWaitEvent(P->sp[1], P->ev_sync, 0));
         P->fresh = false;
     }
-    c->flow_full = P->flow_full[p]; c->fb_flag = P->fb_flag[p]; c->fb_flag_host = P->fb_flag_host[p]; c->depth = P->depth[p]; c->plane_edges = P->plane_edges[p];
-    // ---- stream A: inputs, gray / resize, Brox .. up-sampling
-    CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_done[p], 0));                 // frame i - 2 has finished with the buffers of this parity
+    c->flow_full = P->flow_full[k]; c->fb_flag = P->fb_flag[k]; c->fb_flag_host = P->fb_flag_host[k]; c->depth = P->depth[k]; c->plane_edges = P->plane_edges[k];
+    // ---- stream A of this parity: inputs, gray / resize, Brox .. up-sampling.  The ring slot written here held frame i - 4;
+    // its readers (the flow solves of frames i - 4 .. i - 2) are done once frame i - 2 is decided
+    cudaStream_t sa = P->sa[p];
+    CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_done[k], 0));                 // frame i - PIPE_NB has finished with buffers k
     if (P->gray_pending[slot]) CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_gray[slot], 0));   // ... and the extractor with this ring slot
     if (!host_src) {
         CU_CHECK(c, cudaMemcpyAsync(c->bgr[slot], bgr, (size_t)c->N * 3, cudaMemcpyDeviceToDevice, sa));
@@ -206,40 +237,40 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
         CU_CHECK(c, cudaEventRecord(P->ev_h2d[p], sa));
     }
     if (!c->cfg.plane_edges) CU_CHECK(c, cudaMemsetAsync(c->plane_edges, 0, c->N, sa));
-    CU_CHECK(c, cudaEventRecord(P->ev_in[p], sa));
+    CU_CHECK(c, cudaEventRecord(P->ev_in[k], sa));
     c->stream = sa;
     int st = sindyn_prep_frame(c, slot);
-    if (st == SINDYN_OK) st = flow_part_a(c, p);
+    if (st == SINDYN_OK) st = flow_part_a(c, k);
     c->stream = main_s;
     SD_CHECK(st);
-    CU_CHECK(c, cudaEventRecord(P->ev_a[p], sa));
+    CU_CHECK(c, cudaEventRecord(P->ev_a[k], sa));
     // ---- stream 3: plane fitter (depth only)
     if (c->cfg.plane_edges) {
         cudaStream_t s3 = P->sp[p];
-        CU_CHECK(c, cudaStreamWaitEvent(s3, P->ev_in[p], 0));
-        if (!P->g_p[p])
-            SD_CHECK(pipe_capture(c, s3, &P->g_p[p], &P->n_p[p], [&]() {
+        CU_CHECK(c, cudaStreamWaitEvent(s3, P->ev_in[k], 0));
+        if (!P->g_p[k])
+            SD_CHECK(pipe_capture(c, s3, &P->g_p[k], &P->n_p[k], [&]() {
                 return peac_run(c, &P->peac[p], &P->rc_peac[p], c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges);
             }));
-        CU_CHECK(c, cudaGraphLaunch(P->g_p[p], s3));
-        c->launches += P->n_p[p];
-        CU_CHECK(c, cudaEventRecord(P->ev_p[p], s3));
+        CU_CHECK(c, cudaGraphLaunch(P->g_p[k], s3));
+        c->launches += P->n_p[k];
+        CU_CHECK(c, cudaEventRecord(P->ev_p[k], s3));
     }
     // ---- stream 2: k-means + gradient edges (after the previous frame's decision: warm start, shared scratch), then the
     // plane-edge filter and the re-clustering
-    CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_in[p], 0));
-    CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_done[p ^ 1], 0));
-    if (!P->g_c1[p]) SD_CHECK(pipe_capture(c, s2, &P->g_c1[p], &P->n_c1[p], [&]() { return cluster_part1(c); }));
-    CU_CHECK(c, cudaGraphLaunch(P->g_c1[p], s2));
-    c->launches += P->n_c1[p];
-    if (c->cfg.plane_edges) CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_p[p], 0));
-    if (!P->g_c2[p]) SD_CHECK(pipe_capture(c, s2, &P->g_c2[p], &P->n_c2[p], [&]() { return cluster_part2(c); }));
-    CU_CHECK(c, cudaGraphLaunch(P->g_c2[p], s2));
-    c->launches += P->n_c2[p];
+    CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_in[k], 0));
+    CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_done[(k + PIPE_NB - 1) % PIPE_NB], 0));
+    if (!P->g_c1[k]) SD_CHECK(pipe_capture(c, s2, &P->g_c1[k], &P->n_c1[k], [&]() { return cluster_part1(c); }));
+    CU_CHECK(c, cudaGraphLaunch(P->g_c1[k], s2));
+    c->launches += P->n_c1[k];
+    if (c->cfg.plane_edges) CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_p[k], 0));
+    if (!P->g_c2[k]) SD_CHECK(pipe_capture(c, s2, &P->g_c2[k], &P->n_c2[k], [&]() { return cluster_part2(c); }));
+    CU_CHECK(c, cudaGraphLaunch(P->g_c2[k], s2));
+    c->launches += P->n_c2[k];
     CU_CHECK(c, cudaEventRecord(P->ev_join, s2));
     // ---- the handle's stream: part B, decision, state roll
-    CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_a[p], 0));
-    SD_CHECK(flow_part_b(c, p));
+    CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_a[k], 0));
+    SD_CHECK(flow_part_b(c, k));
     CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_join, 0));
     SD_CHECK(decide_run(c, &c->dd, c->rc.cls, c->rc.labels, c->rc.stats, c->rc.top, c->mask_low, c->mask_high, c->high_last, c->edges.total_area,
                         c->rc.label_out));
@@ -250,14 +281,11 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
         CU_CHECK(c, cudaMemcpyAsync(&flags->rc, c->rc.ctl, sizeof(ReclusterControl), cudaMemcpyDeviceToHost, main_s));
         CU_CHECK(c, cudaMemcpyAsync(flags->edge_scalars, c->edges.scalars, sizeof(int) * 4, cudaMemcpyDeviceToHost, main_s));
         flags->peac_hdr[0] = flags->peac_hdr[1] = flags->peac_hdr[2] = flags->peac_hdr[3] = 0;
-        if (c->cfg.plane_edges) SD_CHECK(peac_copy_header(c, &P->peac[p], flags->peac_hdr));
+        if (c->cfg.plane_edges) SD_CHECK(peac_copy_sticky_overflow(c, &P->peac[p], &flags->peac_hdr[2]));
     }
-    CU_CHECK(c, cudaEventRecord(P->ev_done[p], main_s));
-    P->last_slot = slot; P->last_parity = p;
+    CU_CHECK(c, cudaEventRecord(P->ev_done[k], main_s));
+    P->last_slot = slot; P->last_k = k;
     ++P->frame_no;
-    const int t = c->i_lastlast;
-    c->i_lastlast = c->i_last;
-    c->i_last = c->i_cur;
-    c->i_cur = t;
+    c->roll_ring();
     return SINDYN_OK;
 }

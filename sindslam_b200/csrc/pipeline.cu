@@ -28,6 +28,8 @@ int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll)
 {
     if (!c->have_prev) { c->err = "flow_residual: call sindyn_set_prev_frames first"; return SINDYN_ERR_STATE; }
     if (c->cfg.stage_timing) SD_CHECK(ensure_events(c));
+    SD_CHECK(pipe_join(c));
+    pipe_invalidate(c);
     STAGE_MARK(c, 0);
     if (bgr_dev != c->bgr[c->i_cur])
         CU_CHECK(c, cudaMemcpyAsync(c->bgr[c->i_cur], bgr_dev, (size_t)c->N * 3, cudaMemcpyDeviceToDevice, c->stream));
@@ -38,10 +40,7 @@ int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll)
     SD_CHECK(flow_finish_all(c, &lm));   // marks ev[3], ev[4], ev[5]
     c->large_motion_last = lm;
     if (roll) {  // imgRGBLastLast <- imgRGBLast <- cur (DynaDetect.cc:1661-1662): index rotation, no copies
-        int t = c->i_lastlast;
-        c->i_lastlast = c->i_last;
-        c->i_last = c->i_cur;
-        c->i_cur = t;
+        c->roll_ring();
     }
     return SINDYN_OK;
 }
