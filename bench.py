@@ -457,10 +457,12 @@ def run_ours(args):
         ks = [order2[s * FRAMES_PER_STEP + j] for s in range(s0, s1) for j in range(FRAMES_PER_STEP)]
         if not ks:
             return
-        orb.track_submit(sd, bgr_np[ks[0]], dep_np[ks[0]], ks[0])
-        for i in range(1, len(ks) + 1):
-            if i < len(ks):
-                orb.track_submit(sd, bgr_np[ks[i]], dep_np[ks[i]], ks[i])
+        ahead = 2                     # frames submitted before the oldest one is collected (at most three in flight)
+        for i in range(min(ahead, len(ks))):
+            orb.track_submit(sd, bgr_np[ks[i]], dep_np[ks[i]], ks[i])
+        for i in range(len(ks)):
+            if i + ahead < len(ks):
+                orb.track_submit(sd, bgr_np[ks[i + ahead]], dep_np[ks[i + ahead]], ks[i + ahead])
             _, _, kps, _ = orb.track_collect(sd, mask_out=pin_mask, label_out=pin_label, kps_out=pin_kps, desc_out=pin_desc)
             n_kp += len(kps)
 
@@ -524,8 +526,8 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * cam.width * cam.height * 5,
                     "d2h_bytes_per_step": FRAMES_PER_STEP * d2h, "ms_per_step": e2e_ms / args.steps,
                     "frame_at_a_time": sync_pairs_s,
-                    "note": "one sequence per GPU through sindyn_track_submit / sindyn_track_collect (pinned host buffers; frame i + 1 is submitted "
-                            "before frame i is collected, at most two frames in flight); frame_at_a_time = the same through sindyn_track_frame, "
+                    "note": "one sequence per GPU through sindyn_track_submit / sindyn_track_collect (pinned host buffers; frame i + 2 is submitted "
+                            "before frame i is collected, at most three frames in flight); frame_at_a_time = the same through sindyn_track_frame, "
                             "which returns a frame's results before it accepts the next one"},
             "ms_per_frame": dev_ms / (args.steps * FRAMES_PER_STEP),
             "gpu_launches": int(gpu_launches),

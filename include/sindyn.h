@@ -276,8 +276,9 @@ int sindyn_track_join(sindyn_handle h, sindyn_orb_handle o);
  * (rgbd_tum_noros.cc:113-192 reads a recorded sequence; Tracking::GrabImageRGBD, Tracking.cc:209-240, needs mask + key points of
  * frame i only).  sindyn_track_submit uploads frame i + 1 and enqueues all of its work without waiting; sindyn_track_collect
  * returns the oldest submitted frame (same outputs as sindyn_track_frame; mask_out / label_out / kps / desc may be NULL).  At
- * most two frames may be in flight (SINDYN_ERR_STATE otherwise); results are bit-identical to sindyn_track_frame.  bgr / depth
+ * most SINDYN_TRACK_MAX_IN_FLIGHT (3) frames may be in flight (SINDYN_ERR_STATE otherwise); results are bit-identical to sindyn_track_frame.  bgr / depth
  * must stay valid until the frame is collected if they are pinned (page-locked) memory, pageable memory is copied at once. */
+#define SINDYN_TRACK_MAX_IN_FLIGHT 3
 int sindyn_track_submit(sindyn_handle h, sindyn_orb_handle o, const uint8_t *bgr, size_t bgr_step, const uint16_t *depth, size_t depth_step,
                         int rgb_order, int dilate_k, int frame_idx);
 int sindyn_track_collect(sindyn_handle h, sindyn_orb_handle o, uint8_t *mask_out, size_t mask_step, uint8_t *label_out, size_t label_step,

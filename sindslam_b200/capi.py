@@ -517,7 +517,7 @@ class Orb:
             raise SindynError(f"track_frame_resident: {STATUS.get(st, st)}: {sd.lib.sindyn_last_error(sd.h).decode()}")
 
     def track_submit(self, sd, bgr, depth, frame_idx, rgb_order=1, dilate_k=15):
-        """Asynchronous sindyn_track_frame: upload + enqueue frame `frame_idx` without waiting (at most two frames in flight).
+        """Asynchronous sindyn_track_frame: upload + enqueue frame `frame_idx` without waiting (at most three frames in flight).
         bgr / depth must stay alive (and unchanged, if pinned) until the frame is collected."""
         bgr, depth = _u8(bgr), np.ascontiguousarray(depth, np.uint16)
         self._inflight = getattr(self, "_inflight", [])

@@ -240,14 +240,22 @@ __global__ void __launch_bounds__(1024) k_km_finalize(const float *__restrict__ 
         const int max_k = s_maxk;
         unsigned long long best = 0ull;
         bool any = false;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            if (labels[i] != max_k) continue;
-            float d0 = pts[3 * (size_t)i] - s_base[0], d1 = pts[3 * (size_t)i + 1] - s_base[1], d2 = pts[3 * (size_t)i + 2] - s_base[2];
-            float dist = d0 * d0;
-            dist = dist + d1 * d1;
-            dist = dist + d2 * d2;
-            unsigned long long key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)i;  // ties: last index wins
-            if (!any || key > best) { best = key; any = true; }
+        // one CTA walks all n points: eight label loads of a thread are in flight together (the walk is latency bound)
+        for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+            int lb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; lb[u] = i < n ? labels[i] : -1; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (lb[u] != max_k) continue;
+                const int i = i0 + u * blockDim.x;
+                float d0 = pts[3 * (size_t)i] - s_base[0], d1 = pts[3 * (size_t)i + 1] - s_base[1], d2 = pts[3 * (size_t)i + 2] - s_base[2];
+                float dist = d0 * d0;
+                dist = dist + d1 * d1;
+                dist = dist + d2 * d2;
+                unsigned long long key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)i;  // ties: last index wins
+                if (!any || key > best) { best = key; any = true; }
+            }
         }
         if (any) atomicMax(&s_best, best);
         __syncthreads();

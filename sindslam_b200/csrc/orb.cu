@@ -833,14 +833,15 @@ __global__ void k_orb_gray_in(const uint8_t *__restrict__ bgr, int W, int H, int
 int detect_run_public(sindyn_ctx *c);        // detect.cu
 int detect_check_capacity(sindyn_ctx *c);    // detect.cu (synchronises the handle's stream)
 
+#define TRACK_NB 3      // frames in flight through sindyn_track_submit (SINDYN_TRACK_MAX_IN_FLIGHT)
 struct TrackSync {
     cudaEvent_t ev_in = nullptr, ev_mask = nullptr, ev_orb_done = nullptr;
-    // asynchronous entry (sindyn_track_submit / sindyn_track_collect): results of the frames in flight, pinned, by parity
-    uint8_t *r_mask[2] = {nullptr, nullptr}, *r_label[2] = {nullptr, nullptr}, *r_desc[2] = {nullptr, nullptr};
-    sindyn_keypoint *r_kp[2] = {nullptr, nullptr};
-    OrbControl *r_ctl[2] = {nullptr, nullptr};
-    PipeFlags *r_flags[2] = {nullptr, nullptr};
-    cudaEvent_t ev_res_main[2] = {}, ev_res_orb[2] = {};
+    // asynchronous entry (sindyn_track_submit / sindyn_track_collect): results of the frames in flight, pinned, ring of TRACK_NB
+    uint8_t *r_mask[TRACK_NB] = {}, *r_label[TRACK_NB] = {}, *r_desc[TRACK_NB] = {};
+    sindyn_keypoint *r_kp[TRACK_NB] = {};
+    OrbControl *r_ctl[TRACK_NB] = {};
+    PipeFlags *r_flags[TRACK_NB] = {};
+    cudaEvent_t ev_res_main[TRACK_NB] = {}, ev_res_orb[TRACK_NB] = {};
     int r_cap = 0;
     unsigned long long n_submit = 0, n_collect = 0;
 };
@@ -862,7 +863,7 @@ static void track_free(sindyn_orb *o)
     TrackSync *t = (TrackSync *)o->track;
     if (!t) return;
     cudaEventDestroy(t->ev_in); cudaEventDestroy(t->ev_mask); cudaEventDestroy(t->ev_orb_done);
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < TRACK_NB; ++p) {
         if (t->ev_res_main[p]) cudaEventDestroy(t->ev_res_main[p]);
         if (t->ev_res_orb[p]) cudaEventDestroy(t->ev_res_orb[p]);
     }
@@ -988,13 +989,13 @@ extern "C" int sindyn_track_join(sindyn_handle h, sindyn_orb_handle o)
 // ---------------------------------------------------------------- asynchronous per-frame entry: submit frame i + 1, then collect frame i
 // sindyn_track_frame returns a frame's results before it accepts the next frame, so the GPU never sees two frames at once.  A
 // caller that has the next image at hand (a dataset on disk, rgbd_tum_noros.cc:113-192; a camera running ahead of the tracker)
-// submits it first: the upload and the image-only stages of frame i + 1 then overlap the decision, the extractor and the
-// download of frame i (pipe.cu).  At most two frames are in flight; results are collected in submission order.
+// submits it first: the upload and the image-only stages of frames i + 1, i + 2 then overlap the decision, the extractor and the
+// download of frame i (pipe.cu).  At most three frames are in flight; results are collected in submission order.
 static int track_async_init(sindyn_ctx *c, sindyn_orb *o, TrackSync *t)
 {
     if (t->r_mask[0]) return SINDYN_OK;
     t->r_cap = o->nfeatures * 2 + 64 < ORB_OUT_MAX ? o->nfeatures * 2 + 64 : ORB_OUT_MAX;
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < TRACK_NB; ++p) {
         SD_CHECK(o->halloc(&t->r_mask[p], (size_t)c->N));
         SD_CHECK(o->halloc(&t->r_label[p], (size_t)c->N));
         SD_CHECK(o->halloc(&t->r_kp[p], (size_t)t->r_cap));
@@ -1016,8 +1017,8 @@ extern "C" int sindyn_track_submit(sindyn_handle h, sindyn_orb_handle o, const u
     if (!pipe_usable(h)) { h->err = "track_submit: needs the CUDA-graph path (use_graphs = 1, stage_timing = 0)"; return SINDYN_ERR_STATE; }
     TrackSync *t = track_sync(o);
     SD_CHECK(track_async_init(h, o, t));
-    if (t->n_submit - t->n_collect >= 2) { h->err = "track_submit: two frames are in flight already, collect one first"; return SINDYN_ERR_STATE; }
-    const int p = (int)(t->n_submit & 1);
+    if (t->n_submit - t->n_collect >= TRACK_NB) { h->err = "track_submit: three frames are in flight already, collect one first"; return SINDYN_ERR_STATE; }
+    const int p = (int)(t->n_submit % TRACK_NB);
     SD_CHECK(track_enqueue_pipe(h, o, bgr, bgr_step, depth, depth_step, true, t->r_flags[p], rgb_order, dilate_k));
     // results into this parity's pinned buffers: mask and labels on the detector's stream (the labels from the rolled state: the
     // next frame's re-clustering may already overwrite rc.label_out), key points on the extractor's
@@ -1040,7 +1041,7 @@ extern "C" int sindyn_track_collect(sindyn_handle h, sindyn_orb_handle o, uint8_
     *n_out = 0;
     TrackSync *t = (TrackSync *)o->track;
     if (!t || t->n_collect >= t->n_submit) { h->err = "track_collect: no frame in flight"; return SINDYN_ERR_STATE; }
-    const int p = (int)(t->n_collect & 1);
+    const int p = (int)(t->n_collect % TRACK_NB);
     ++t->n_collect;
     CU_CHECK(h, cudaEventSynchronize(t->ev_res_main[p]));
     CU_CHECK(o, cudaEventSynchronize(t->ev_res_orb[p]));

@@ -43,7 +43,7 @@ def test_track_frame_equals_separate_calls(rgb_order):
 
 def test_pipelined_frames_equal_frame_at_a_time():
     """The frame pipeline (pipe.cu): frames enqueued back to back without a synchronisation (device-resident slots), and frames
-    submitted one ahead through sindyn_track_submit / sindyn_track_collect (pinned and pageable host buffers), must return exactly
+    submitted two ahead through sindyn_track_submit / sindyn_track_collect (pinned and pageable host buffers), must return exactly
     what the frame-at-a-time entry returns -- 24 consecutive frames with free-running state, plane edges on."""
     import torch
     from sindslam_b200.capi import Orb, SinDyn
@@ -67,9 +67,14 @@ def test_pipelined_frames_equal_frame_at_a_time():
     pinned = [(torch.from_numpy(frames[k].bgr.copy()).pin_memory().numpy(), torch.from_numpy(frames[k].depth.view(np.int16).copy()).pin_memory().numpy().view(np.uint16))
               if k & 1 else (frames[k].bgr, frames[k].depth) for k in range(n)]
     ob.track_submit(sb, pinned[1][0], pinned[1][1], 1)
-    for k in range(2, n):
-        ob.track_submit(sb, pinned[k][0], pinned[k][1], k)
-        same(ob.track_collect(sb), ref[k - 2], k - 1)
+    ob.track_submit(sb, pinned[2][0], pinned[2][1], 2)
+    for k in range(3, n):
+        ob.track_submit(sb, pinned[k][0], pinned[k][1], k)      # three frames in flight
+        if k == 3:
+            with pytest.raises(Exception):
+                ob.track_submit(sb, pinned[4][0], pinned[4][1], 4)   # a fourth is refused
+        same(ob.track_collect(sb), ref[k - 3], k - 2)
+    same(ob.track_collect(sb), ref[n - 3], n - 2)
     same(ob.track_collect(sb), ref[n - 2], n - 1)
     with pytest.raises(Exception):
         ob.track_collect(sb)               # nothing in flight
