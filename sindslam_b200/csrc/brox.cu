@@ -197,7 +197,7 @@ template <int TW_, int TH_, int SMAX_ = BROX_SMAX> struct BroxTile {
     static constexpr int NPCP = NPC + 2 * G;
     // (du,dv) + edge weights | per-pixel 2x2 systems (5 floats; the staging planes ta / tb / ps alias their start) | u, v
     static constexpr size_t SMEM = sizeof(float2) * 4 * NPCP + sizeof(float) * 10 * NPC + sizeof(float) * 2 * PP;
-    static constexpr size_t SMEM_SOR = sizeof(float2) * 4 * NPCP + sizeof(float) * 10 * NPC;   // k_brox_sor: no u / v planes
+    static constexpr size_t SMEM_SOR = sizeof(float2) * 2 * NPCP;   // k_brox_sor: the (du, dv) pairs only
     static_assert(3 * PP <= 10 * NPC, "ta / tb / ps must fit into the coefficient area they alias");
     static_assert((PW & 1) == 0, "de-interleaving needs an even region width");
     static_assert(NPC < 4096, "pixel index must fit into 12 bits");
@@ -527,18 +527,20 @@ struct BroxSorP {
     int nsweeps;
 };
 
-// nsweeps (<= SMAX_, shipped 5) red-black SOR sweeps on one tile + (2 x nsweeps + 1)-px halo (temporal blocking): same data layout and sweep loop as
-// k_brox_level, the systems come from k_brox_system.
+// nsweeps (<= SMAX_, shipped 5) red-black SOR sweeps on one tile + (2 x nsweeps + 1)-px halo (temporal blocking).  The sweep is
+// bound by shared-memory bandwidth, so only what the sweeps EXCHANGE lives there: the (du, dv) pairs of the region, de-interleaved
+// by colour with zero guards (see above).  Everything that is constant over the sweeps of a launch -- the four edge weights and
+// the 2x2 system (j12, b1, b2, 1/d1, 1/d2) of every owned pixel -- is loaded from global memory (L2 hits: k_brox_system has just
+// written it) straight into registers: 9 floats x <= 2 x SOR_M owned pixels, BROX_SOR_NT = 512 threads of <= 128 registers.
+// A pixel update then costs four LDS.64 + one STS.64 (40 B of shared-memory traffic instead of 76).
+constexpr int BROX_SOR_NT = 512;
 template <class T>
-__global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
+__global__ void __launch_bounds__(BROX_SOR_NT, 1) k_brox_sor(BroxSorP p)
 {
-    constexpr int PW = T::PW, PH = T::PH, HW = T::HW, NPC = T::NPC, M = T::M, G = T::G, NPCP = T::NPCP;
+    constexpr int PW = T::PW, PH = T::PH, HW = T::HW, NPC = T::NPC, G = T::G, NPCP = T::NPCP;
+    constexpr int M = (NPC + BROX_SOR_NT - 1) / BROX_SOR_NT;
     extern __shared__ float4 sm4[];
     float2 *s_uv = (float2 *)sm4 + G;                               // [2][NPCP] (du, dv) by colour, zero guards
-    float *s_wr = (float *)((float2 *)sm4 + 2 * NPCP) + G;          // [2][NPCP]
-    float *s_wd = s_wr + 2 * NPCP;                                  // [2][NPCP]
-    float4 *s_c4 = (float4 *)((float2 *)sm4 + 4 * NPCP);            // [2][NPC]  private to the owning thread
-    float *s_c1 = (float *)(s_c4 + 2 * NPC);                        // [2][NPC]
     const int w = p.w, h = p.h;
     const int gx0 = blockIdx.x * T::TW, gy0 = blockIdx.y * T::TH;
     const int ox = gx0 - T::R, oy = gy0 - T::R;                     // ox + oy is even: local colour == global colour
@@ -551,22 +553,19 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
     long long t_prev = clock64();
     if (prof_on) atomicAdd(&g_brox_clk[15], 1ull);
 #endif
-
     // guards
-    for (int r = tid; r < 12 * G; r += BROX_NT) {
+    for (int r = tid; r < 4 * G; r += BROX_SOR_NT) {
         const int a = r / (2 * G), o = r - a * 2 * G;
         const int off = o < G ? o - G : NPC + (o - G);
-        if (a < 2) s_uv[a * NPCP + off] = make_float2(0.0f, 0.0f);
-        else s_wr[(a - 2) * NPCP + off] = 0.0f;
+        s_uv[a * NPCP + off] = make_float2(0.0f, 0.0f);
     }
     // ---- owned pixels: table (independent of the previous kernel's output: runs under its tail, see pdl_wait)
     unsigned pk[2][M];
-    float rdu[2][M], rdv[2][M];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            const int q = tid + BROX_NT * m;
+            const int q = tid + BROX_SOR_NT * m;
             unsigned v = 0;
             if (q < NPC) {
                 const int ly = q / HW, i = q - ly * HW;
@@ -587,10 +586,8 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
     pdl_wait();
     pdl_trigger();
     BROX_CLK(0)
-    // ---- stage (du, dv) and the edge weights of the whole region and the systems of the owned pixels with asynchronous
-    // global -> shared copies (no register staging: every copy of the thread is in flight at once)
-    // (rows over warps, columns over lanes: no index divisions, the copies of a warp are contiguous in global memory)
-    for (int ly = tid >> 5; ly < PH; ly += BROX_NT / 32) {
+    // ---- stage (du, dv) of the whole region with asynchronous global -> shared copies (rows over warps, columns over lanes)
+    for (int ly = tid >> 5; ly < PH; ly += BROX_SOR_NT / 32) {
         const int y = oy + ly;
         const bool row_in = y >= 0 && y < h;
         for (int lx = tid & 31; lx < PW; lx += 32) {
@@ -600,26 +597,33 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
                 const int g = y * w + x;
                 cp_async4(&s_uv[ci].x, p.dui + g);
                 cp_async4(&s_uv[ci].y, p.dvi + g);
-                cp_async4(&s_wr[ci], &p.W[g].x);
-                cp_async4(&s_wd[ci], &p.W[g].y);
             } else {
                 s_uv[ci] = make_float2(0.0f, 0.0f);
-                s_wr[ci] = 0.0f;
-                s_wd[ci] = 0.0f;
             }
         }
     }
+    // ---- the systems and the edge weights of the owned pixels: global -> registers (a weight towards a pixel outside the image
+    // is zero: Neumann boundary; the left / upper weight is the right / lower weight of the left / upper neighbour)
+    float rdu[2][M], rdv[2][M], wl[2][M], wr[2][M], wu[2][M], wd[2][M], cj[2][M], cb1[2][M], cb2[2][M], cd1[2][M], cd2[2][M];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             const unsigned k = pk[c][m];
+            wl[c][m] = wr[c][m] = wu[c][m] = wd[c][m] = 0.0f;
+            cj[c][m] = cb1[c][m] = cb2[c][m] = cd1[c][m] = cd2[c][m] = 0.0f;
             if (!((k >> 14) & 1u)) continue;
             const int idx = k & 0xfff, par = (k >> 12) & 1;
             const int ly = idx / HW, lx = 2 * (idx - ly * HW) + par;
-            const int g = (oy + ly) * w + ox + lx;
-            cp_async16(&s_c4[c * NPC + idx], p.C4 + g);
-            cp_async4(&s_c1[c * NPC + idx], p.C1 + g);
+            const int x = ox + lx, y = oy + ly;
+            const int g = y * w + x;
+            const float2 W0 = p.W[g];
+            const float4 c4 = p.C4[g];
+            cd2[c][m] = p.C1[g];
+            wr[c][m] = W0.x; wd[c][m] = W0.y;
+            if (x > 0) wl[c][m] = p.W[g - 1].x;
+            if (y > 0) wu[c][m] = p.W[g - w].y;
+            cj[c][m] = c4.x; cb1[c][m] = c4.y; cb2[c][m] = c4.z; cd1[c][m] = c4.w;
         }
     cp_async_wait_all();
     __syncthreads();
@@ -638,24 +642,16 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_sor(BroxSorP p)
     {                                                                                                             \
         const float2 *__restrict__ uo = s_uv + ((C) ^ 1) * NPCP;                                                   \
         float2 *__restrict__ uc_ = s_uv + (C) * NPCP;                                                              \
-        const float *__restrict__ wro = s_wr + ((C) ^ 1) * NPCP;                                                   \
-        const float *__restrict__ wdo = s_wd + ((C) ^ 1) * NPCP;                                                   \
-        const float *__restrict__ wrc = s_wr + (C) * NPCP;                                                         \
-        const float *__restrict__ wdc = s_wd + (C) * NPCP;                                                         \
         _Pragma("unroll") for (int m = 0; m < M; ++m)                                                             \
         {                                                                                                         \
             const unsigned k_ = pk[C][m];                                                                         \
             if (((k_ >> 14) & 1u) && (k_ >> 16) >= thr0 + (unsigned)(K)) {                                        \
                 const int idx = k_ & 0xfff, par = (k_ >> 12) & 1;                                                 \
                 const float2 l = uo[idx - 1 + par], r = uo[idx + par], u_ = uo[idx - HW], d = uo[idx + HW];       \
-                const float wr_ = wrc[idx], wd_ = wdc[idx];                                                       \
-                const float wl = wro[idx - 1 + par], wu = wdo[idx - HW];                                          \
-                const float su = wl * l.x + wr_ * r.x + wu * u_.x + wd_ * d.x;                                    \
-                const float sv = wl * l.y + wr_ * r.y + wu * u_.y + wd_ * d.y;                                    \
-                const float4 cf = s_c4[(C) * NPC + idx];                                                          \
-                const float cd2_ = s_c1[(C) * NPC + idx];                                                         \
-                const float du_new = om1 * rdu[C][m] + omega * (cf.y - cf.x * rdv[C][m] + su) * cf.w;             \
-                const float dv_new = om1 * rdv[C][m] + omega * (cf.z - cf.x * du_new + sv) * cd2_;                \
+                const float su = wl[C][m] * l.x + wr[C][m] * r.x + wu[C][m] * u_.x + wd[C][m] * d.x;              \
+                const float sv = wl[C][m] * l.y + wr[C][m] * r.y + wu[C][m] * u_.y + wd[C][m] * d.y;              \
+                const float du_new = om1 * rdu[C][m] + omega * (cb1[C][m] - cj[C][m] * rdv[C][m] + su) * cd1[C][m]; \
+                const float dv_new = om1 * rdv[C][m] + omega * (cb2[C][m] - cj[C][m] * du_new + sv) * cd2[C][m];  \
                 rdu[C][m] = du_new;                                                                               \
                 rdv[C][m] = dv_new;                                                                               \
                 uc_[idx] = make_float2(du_new, dv_new);                                                           \
@@ -777,7 +773,7 @@ int brox_init(sindyn_base *ctx, BroxSolver *b, int w, int h, float alpha, float 
 template <class T> static bool brox_tile_fits(int w, int h) { return cdiv(w, T::TW) * cdiv(h, T::TH) <= SINDYN_NUM_SMS_B200; }
 template <class T> static void brox_launch_sor(sindyn_base *ctx, BroxSorP &p)
 {
-    LAUNCH_PDL(ctx, k_brox_sor<T>, dim3(cdiv(p.w, T::TW), cdiv(p.h, T::TH)), BROX_NT, T::SMEM_SOR, p);
+    LAUNCH_PDL(ctx, k_brox_sor<T>, dim3(cdiv(p.w, T::TW), cdiv(p.h, T::TH)), BROX_SOR_NT, T::SMEM_SOR, p);
 }
 
 static int brox_enqueue(sindyn_base *ctx, BroxSolver *b, const float *I0, const float *I1, float *flow_out, float sign)
