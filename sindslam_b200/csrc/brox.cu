@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(BROX_NT, 1) k_brox_level(BroxInnerP p)
 // (k_brox_sor) only stage them.
 struct BroxSysP {
     const float *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz, *u, *v, *dub, *dvb;
-    float2 *W;
+    float4 *W;       // (wl, wr, wu, wd): the four edge weights of the pixel (zero across the image border)
     float4 *C4;
     float *C1;
     int w, h;
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(BSY_W *BSY_H) k_brox_system(BroxSysP p)
     if (y > 0) { su += wu * (s_u[cy - 1][cx] - uc); sv += wu * (s_v[cy - 1][cx] - vc); }
     if (y < h - 1) { su += wd * (s_u[cy + 1][cx] - uc); sv += wd * (s_v[cy + 1][cx] - vc); }
     const float sw_ = wl + wr + wu + wd;
-    p.W[g] = make_float2(wr, wd);
+    p.W[g] = make_float4(wl, wr, wu, wd);
     p.C4[g] = make_float4(j12, su - j13, sv - j23, 1.0f / (j11 + sw_));
     p.C1[g] = 1.0f / (j22 + sw_);
 }
@@ -517,7 +517,7 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct BroxSorP {
-    const float2 *W;
+    const float4 *W;
     const float4 *C4;
     const float *C1;
     const float *dui, *dvi;   // increment at the start of this launch's sweeps
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(BROX_SOR_NT, 1) k_brox_sor(BroxSorP p)
         }
     }
     // ---- the systems and the edge weights of the owned pixels: global -> registers (a weight towards a pixel outside the image
-    // is zero: Neumann boundary; the left / upper weight is the right / lower weight of the left / upper neighbour)
+    // is zero: Neumann boundary; k_brox_system stores all four weights of a pixel)
     float rdu[2][M], rdv[2][M], wl[2][M], wr[2][M], wu[2][M], wd[2][M], cj[2][M], cb1[2][M], cb2[2][M], cd1[2][M], cd2[2][M];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
@@ -617,12 +617,10 @@ __global__ void __launch_bounds__(BROX_SOR_NT, 1) k_brox_sor(BroxSorP p)
             const int ly = idx / HW, lx = 2 * (idx - ly * HW) + par;
             const int x = ox + lx, y = oy + ly;
             const int g = y * w + x;
-            const float2 W0 = p.W[g];
+            const float4 W0 = p.W[g];
             const float4 c4 = p.C4[g];
             cd2[c][m] = p.C1[g];
-            wr[c][m] = W0.x; wd[c][m] = W0.y;
-            if (x > 0) wl[c][m] = p.W[g - 1].x;
-            if (y > 0) wu[c][m] = p.W[g - w].y;
+            wl[c][m] = W0.x; wr[c][m] = W0.y; wu[c][m] = W0.z; wd[c][m] = W0.w;
             cj[c][m] = c4.x; cb1[c][m] = c4.y; cb2[c][m] = c4.z; cd1[c][m] = c4.w;
         }
     cp_async_wait_all();

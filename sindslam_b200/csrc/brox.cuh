@@ -16,7 +16,7 @@ struct BroxSolver {
     float *A, *Iz, *Ix, *Iy, *Ixz, *Iyz, *Ixx, *Ixy, *Iyy;
     float *u[2], *v[2], *du[3], *dv[3];
     // per-pixel linear systems of one lagged-nonlinearity iteration (k_brox_system -> k_brox_sor), image layout
-    float2 *sysW = nullptr;   // (weight to the right neighbour, weight to the lower neighbour)
+    float4 *sysW = nullptr;   // edge weights (left, right, up, down)
     float4 *sysC4 = nullptr;  // (j12, b1, b2, 1/d1)
     float *sysC1 = nullptr;   // 1/d2
     // captured CUDA graphs, keyed by the (I0, I1, out, sign) tuple: the frame ring of the handle rotates
