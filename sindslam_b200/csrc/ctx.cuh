@@ -125,7 +125,7 @@ bool pipe_usable(const sindyn_ctx *c);                     // pipe.cu: graphs on
 int pipe_copy_headers(sindyn_ctx *c);                      // pipe.cu: asynchronous copy of the plane-fitter headers of both pipeline instances
 bool pipe_overflow(const sindyn_ctx *c);                   // pipe.cu: ... and their overflow flags, valid after the stream was synchronised
 cudaEvent_t pipe_input_event(sindyn_ctx *c);               // pipe.cu: the last frame's inputs are in place (bgr ring slot, depth)
-int cluster_part1(sindyn_ctx *c);                          // detect.cu: k-means + gradient edges
+int cluster_part1(sindyn_ctx *c);                          // detect.cu: k-means
 int cluster_part2(sindyn_ctx *c);                          // detect.cu: plane-edge filter + re-clustering
 int flow_residual_run(sindyn_ctx *c, const uint8_t *bgr_dev, bool roll);  // pipeline.cu
 int sindyn_ctx_init_stages(sindyn_ctx *c);              // stages.cu

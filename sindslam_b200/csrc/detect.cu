@@ -51,11 +51,11 @@ static int cluster_branch(sindyn_ctx *c)
     return SINDYN_OK;
 }
 
-// the two halves of the clustering branch without the plane fitter (frame pipeline: the fitter runs ahead on its own stream)
-int cluster_part1(sindyn_ctx *c)
+// the two halves of the clustering branch without the plane fitter and the gradient edges (frame pipeline: both run ahead on
+// their own stream)
+int cluster_part1(sindyn_ctx *c)      // (the gradient edges depend on the depth image only: they run ahead, see pipe.cu)
 {
-    SD_CHECK(kmeans_run(c, &c->km, c->depth, c->label_last, &c->cfg));
-    return edges_run(c, &c->edges, c->depth, c->cfg.depth_scale);
+    return kmeans_run(c, &c->km, c->depth, c->label_last, &c->cfg);
 }
 int cluster_part2(sindyn_ctx *c)
 {

@@ -30,10 +30,11 @@ struct FramePipe {
     uint8_t *plane_edges[PIPE_NB] = {};
     PeacStage peac[2];
     ReclusterStage rc_peac[2];
-    cudaEvent_t ev_in[PIPE_NB] = {}, ev_a[PIPE_NB] = {}, ev_p[PIPE_NB] = {}, ev_done[PIPE_NB] = {}, ev_join = nullptr, ev_sync = nullptr, ev_gray[4] = {};
+    EdgeStage edges[PIPE_NB], own_edges;            // gradient edges / end points / total area of a frame (depth only: run ahead, read until the decision)
+    cudaEvent_t ev_in[PIPE_NB] = {}, ev_a[PIPE_NB] = {}, ev_p[PIPE_NB] = {}, ev_done[PIPE_NB] = {}, ev_e[PIPE_NB] = {}, ev_join = nullptr, ev_sync = nullptr, ev_gray[4] = {};
     bool gray_pending[4] = {false, false, false, false};
-    cudaGraphExec_t g_c1[PIPE_NB] = {}, g_c2[PIPE_NB] = {}, g_p[PIPE_NB] = {};
-    unsigned long long n_c1[PIPE_NB] = {}, n_c2[PIPE_NB] = {}, n_p[PIPE_NB] = {};
+    cudaGraphExec_t g_c1[PIPE_NB] = {}, g_c2[PIPE_NB] = {}, g_p[PIPE_NB] = {}, g_e[PIPE_NB] = {};
+    unsigned long long n_c1[PIPE_NB] = {}, n_c2[PIPE_NB] = {}, n_p[PIPE_NB] = {}, n_e[PIPE_NB] = {};
     cudaStream_t built_for = nullptr;               // the handle stream the graphs were captured under
     unsigned long long frame_no = 0;
     bool fresh = true;                              // the pipeline's streams have to wait for the handle's stream first
@@ -54,7 +55,8 @@ static void pipe_drop_graphs(FramePipe *P)
         if (P->g_c1[p]) cudaGraphExecDestroy(P->g_c1[p]);
         if (P->g_c2[p]) cudaGraphExecDestroy(P->g_c2[p]);
         if (P->g_p[p]) cudaGraphExecDestroy(P->g_p[p]);
-        P->g_c1[p] = P->g_c2[p] = P->g_p[p] = nullptr;
+        if (P->g_e[p]) cudaGraphExecDestroy(P->g_e[p]);
+        P->g_c1[p] = P->g_c2[p] = P->g_p[p] = P->g_e[p] = nullptr;
     }
 }
 
@@ -78,7 +80,10 @@ static int pipe_init(sindyn_ctx *c)
     CU_CHECK(c, cudaStreamCreateWithFlags(&P->sp[1], cudaStreamNonBlocking));
     P->own_flow_full = c->flow_full; P->own_fb_flag = c->fb_flag; P->own_fb_flag_host = c->fb_flag_host; P->own_depth = c->depth; P->own_plane_edges = c->plane_edges;
     P->flow_full[0] = c->flow_full; P->fb_flag[0] = c->fb_flag; P->fb_flag_host[0] = c->fb_flag_host; P->depth[0] = c->depth; P->plane_edges[0] = c->plane_edges;
+    P->own_edges = c->edges;
+    P->edges[0] = c->edges;
     for (int k = 1; k < PIPE_NB; ++k) {
+        SD_CHECK(edges_init(c, &P->edges[k], c->W, c->H));
         SD_CHECK(c->dalloc(&P->flow_full[k], (size_t)c->N * 2));
         SD_CHECK(c->dalloc(&P->fb_flag[k], 4));
         SD_CHECK(c->halloc(&P->fb_flag_host[k], 4));
@@ -90,6 +95,7 @@ static int pipe_init(sindyn_ctx *c)
         CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_a[k], cudaEventDisableTiming));
         CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_p[k], cudaEventDisableTiming));
         CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_done[k], cudaEventDisableTiming));
+        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_e[k], cudaEventDisableTiming));
     }
     for (int p = 0; p < 2; ++p) {
         if (c->cfg.plane_edges) {
@@ -109,8 +115,9 @@ void pipe_destroy(sindyn_ctx *c)
     FramePipe *P = c->pipe;
     if (!P) return;
     pipe_drop_graphs(P);
+    c->edges = P->own_edges;
     c->flow_full = P->own_flow_full; c->fb_flag = P->own_fb_flag; c->fb_flag_host = P->own_fb_flag_host; c->depth = P->own_depth; c->plane_edges = P->own_plane_edges;
-    for (int k = 0; k < PIPE_NB; ++k) { cudaEventDestroy(P->ev_in[k]); cudaEventDestroy(P->ev_a[k]); cudaEventDestroy(P->ev_p[k]); cudaEventDestroy(P->ev_done[k]); }
+    for (int k = 0; k < PIPE_NB; ++k) { cudaEventDestroy(P->ev_in[k]); cudaEventDestroy(P->ev_a[k]); cudaEventDestroy(P->ev_p[k]); cudaEventDestroy(P->ev_done[k]); cudaEventDestroy(P->ev_e[k]); }
     for (int p = 0; p < 2; ++p) cudaEventDestroy(P->ev_h2d[p]);
     for (int k = 0; k < 4; ++k) cudaEventDestroy(P->ev_gray[k]);
     brox_destroy(&P->brox[1]); brox_destroy(&P->brox_lm[1]);
@@ -216,6 +223,7 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
         P->fresh = false;
     }
     c->flow_full = P->flow_full[k]; c->fb_flag = P->fb_flag[k]; c->fb_flag_host = P->fb_flag_host[k]; c->depth = P->depth[k]; c->plane_edges = P->plane_edges[k];
+    c->edges = P->edges[k];
     // ---- stream A of this parity: inputs, gray / resize, Brox .. up-sampling.  The ring slot written here held frame i - 4;
     // its readers (the flow solves of frames i - 4 .. i - 2) are done once frame i - 2 is decided
     cudaStream_t sa = P->sa[p];
@@ -244,10 +252,17 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     c->stream = main_s;
     SD_CHECK(st);
     CU_CHECK(c, cudaEventRecord(P->ev_a[k], sa));
-    // ---- stream 3: plane fitter (depth only)
-    if (c->cfg.plane_edges) {
+    // ---- stream 3 of this parity: gradient edges, then the plane fitter (both depth only)
+    {
         cudaStream_t s3 = P->sp[p];
         CU_CHECK(c, cudaStreamWaitEvent(s3, P->ev_in[k], 0));
+        if (!P->g_e[k]) SD_CHECK(pipe_capture(c, s3, &P->g_e[k], &P->n_e[k], [&]() { return edges_run(c, &c->edges, c->depth, c->cfg.depth_scale); }));
+        CU_CHECK(c, cudaGraphLaunch(P->g_e[k], s3));
+        c->launches += P->n_e[k];
+        CU_CHECK(c, cudaEventRecord(P->ev_e[k], s3));
+    }
+    if (c->cfg.plane_edges) {
+        cudaStream_t s3 = P->sp[p];
         if (!P->g_p[k])
             SD_CHECK(pipe_capture(c, s3, &P->g_p[k], &P->n_p[k], [&]() {
                 return peac_run(c, &P->peac[p], &P->rc_peac[p], c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges);
@@ -263,6 +278,7 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     if (!P->g_c1[k]) SD_CHECK(pipe_capture(c, s2, &P->g_c1[k], &P->n_c1[k], [&]() { return cluster_part1(c); }));
     CU_CHECK(c, cudaGraphLaunch(P->g_c1[k], s2));
     c->launches += P->n_c1[k];
+    CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_e[k], 0));
     if (c->cfg.plane_edges) CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_p[k], 0));
     if (!P->g_c2[k]) SD_CHECK(pipe_capture(c, s2, &P->g_c2[k], &P->n_c2[k], [&]() { return cluster_part2(c); }));
     CU_CHECK(c, cudaGraphLaunch(P->g_c2[k], s2));
