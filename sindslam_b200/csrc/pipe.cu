@@ -30,6 +30,10 @@ struct FramePipe {
     uint8_t *plane_edges[PIPE_NB] = {};
     PeacStage peac[2];
     ReclusterStage rc_peac[2];
+    // the decision's own CCL scratch and two label images: the clustering of frame i + 1 (warm-started by frame i's labels) no
+    // longer has to wait for the decision of frame i, which reads those labels and used to share the re-clustering's scratch
+    uint8_t *dd_cls = nullptr; int *dd_labels = nullptr, *dd_top = nullptr; RegionStats *dd_stats = nullptr;
+    uint8_t *label_out[2] = {nullptr, nullptr}, *own_label_out = nullptr;
     EdgeStage edges[PIPE_NB], own_edges;            // gradient edges / end points / total area of a frame (depth only: run ahead, read until the decision)
     cudaEvent_t ev_in[PIPE_NB] = {}, ev_a[PIPE_NB] = {}, ev_p[PIPE_NB] = {}, ev_done[PIPE_NB] = {}, ev_e[PIPE_NB] = {}, ev_join = nullptr, ev_sync = nullptr, ev_gray[4] = {};
     bool gray_pending[4] = {false, false, false, false};
@@ -80,6 +84,16 @@ static int pipe_init(sindyn_ctx *c)
     CU_CHECK(c, cudaStreamCreateWithFlags(&P->sp[1], cudaStreamNonBlocking));
     P->own_flow_full = c->flow_full; P->own_fb_flag = c->fb_flag; P->own_fb_flag_host = c->fb_flag_host; P->own_depth = c->depth; P->own_plane_edges = c->plane_edges;
     P->flow_full[0] = c->flow_full; P->fb_flag[0] = c->fb_flag; P->fb_flag_host[0] = c->fb_flag_host; P->depth[0] = c->depth; P->plane_edges[0] = c->plane_edges;
+    {
+        const size_t N = (size_t)c->N;
+        SD_CHECK(c->dalloc(&P->dd_cls, N * DD_MAXL));
+        SD_CHECK(c->dalloc(&P->dd_labels, (N + 1) * DD_MAXL));
+        SD_CHECK(c->dalloc(&P->dd_top, N * DD_MAXL));
+        SD_CHECK(c->dalloc(&P->dd_stats, N * DD_MAXL));
+        P->own_label_out = c->rc.label_out;
+        P->label_out[0] = c->rc.label_out;
+        SD_CHECK(c->dalloc(&P->label_out[1], N));
+    }
     P->own_edges = c->edges;
     P->edges[0] = c->edges;
     for (int k = 1; k < PIPE_NB; ++k) {
@@ -116,6 +130,7 @@ void pipe_destroy(sindyn_ctx *c)
     if (!P) return;
     pipe_drop_graphs(P);
     c->edges = P->own_edges;
+    c->rc.label_out = P->own_label_out;
     c->flow_full = P->own_flow_full; c->fb_flag = P->own_fb_flag; c->fb_flag_host = P->own_fb_flag_host; c->depth = P->own_depth; c->plane_edges = P->own_plane_edges;
     for (int k = 0; k < PIPE_NB; ++k) { cudaEventDestroy(P->ev_in[k]); cudaEventDestroy(P->ev_a[k]); cudaEventDestroy(P->ev_p[k]); cudaEventDestroy(P->ev_done[k]); cudaEventDestroy(P->ev_e[k]); }
     for (int p = 0; p < 2; ++p) cudaEventDestroy(P->ev_h2d[p]);
@@ -214,6 +229,7 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     if (P->built_for != main_s) { pipe_drop_graphs(P); P->built_for = main_s; }
     const int k = (int)(P->frame_no % PIPE_NB), p = k & 1, slot = c->i_cur;    // buffers k, solver / fitter instance and streams p
     if (P->fresh) {   // whatever the handle's stream has done so far (state set by the caller, frames of the other path) comes first
+        CU_CHECK(c, cudaMemcpyAsync(P->label_out[p ^ 1], c->label_last, c->N, cudaMemcpyDeviceToDevice, main_s));   // the warm start of this frame's k-means
         CU_CHECK(c, cudaEventRecord(P->ev_sync, main_s));
         CU_CHECK(c, cudaStreamWaitEvent(P->sa[0], P->ev_sync, 0));
         CU_CHECK(c, cudaStreamWaitEvent(P->sa[1], P->ev_sync, 0));
@@ -224,6 +240,7 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     }
     c->flow_full = P->flow_full[k]; c->fb_flag = P->fb_flag[k]; c->fb_flag_host = P->fb_flag_host[k]; c->depth = P->depth[k]; c->plane_edges = P->plane_edges[k];
     c->edges = P->edges[k];
+    c->rc.label_out = P->label_out[p];
     // ---- stream A of this parity: inputs, gray / resize, Brox .. up-sampling.  The ring slot written here held frame i - 4;
     // its readers (the flow solves of frames i - 4 .. i - 2) are done once frame i - 2 is decided
     cudaStream_t sa = P->sa[p];
@@ -271,11 +288,11 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
         c->launches += P->n_p[k];
         CU_CHECK(c, cudaEventRecord(P->ev_p[k], s3));
     }
-    // ---- stream 2: k-means + gradient edges (after the previous frame's decision: warm start, shared scratch), then the
-    // plane-edge filter and the re-clustering
+    // ---- stream 2: k-means (warm-started by the previous frame's labels: it follows that frame's re-clustering in stream order),
+    // then the plane-edge filter and the re-clustering.  This parity's label image is free once frame i - 2 is decided.
     CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_in[k], 0));
-    CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_done[(k + PIPE_NB - 1) % PIPE_NB], 0));
-    if (!P->g_c1[k]) SD_CHECK(pipe_capture(c, s2, &P->g_c1[k], &P->n_c1[k], [&]() { return cluster_part1(c); }));
+    CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_done[(k + 2) % PIPE_NB], 0));
+    if (!P->g_c1[k]) SD_CHECK(pipe_capture(c, s2, &P->g_c1[k], &P->n_c1[k], [&]() { return kmeans_run(c, &c->km, c->depth, P->label_out[p ^ 1], &c->cfg); }));
     CU_CHECK(c, cudaGraphLaunch(P->g_c1[k], s2));
     c->launches += P->n_c1[k];
     CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_e[k], 0));
@@ -283,18 +300,18 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     if (!P->g_c2[k]) SD_CHECK(pipe_capture(c, s2, &P->g_c2[k], &P->n_c2[k], [&]() { return cluster_part2(c); }));
     CU_CHECK(c, cudaGraphLaunch(P->g_c2[k], s2));
     c->launches += P->n_c2[k];
+    if (flags) CU_CHECK(c, cudaMemcpyAsync(&flags->rc, c->rc.ctl, sizeof(ReclusterControl), cudaMemcpyDeviceToHost, s2));   // before the next frame's re-clustering resets it
     CU_CHECK(c, cudaEventRecord(P->ev_join, s2));
     // ---- the handle's stream: part B, decision, state roll
     CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_a[k], 0));
     SD_CHECK(flow_part_b(c, k));
     CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_join, 0));
-    SD_CHECK(decide_run(c, &c->dd, c->rc.cls, c->rc.labels, c->rc.stats, c->rc.top, c->mask_low, c->mask_high, c->high_last, c->edges.total_area,
+    SD_CHECK(decide_run(c, &c->dd, P->dd_cls, P->dd_labels, P->dd_stats, P->dd_top, c->mask_low, c->mask_high, c->high_last, c->edges.total_area,
                         c->rc.label_out));
     CU_CHECK(c, cudaMemcpyAsync(c->dyna_last, c->dd.out, c->N, cudaMemcpyDeviceToDevice, main_s));
     CU_CHECK(c, cudaMemcpyAsync(c->high_last, c->mask_high, c->N, cudaMemcpyDeviceToDevice, main_s));
     CU_CHECK(c, cudaMemcpyAsync(c->label_last, c->rc.label_out, c->N, cudaMemcpyDeviceToDevice, main_s));
     if (flags) {
-        CU_CHECK(c, cudaMemcpyAsync(&flags->rc, c->rc.ctl, sizeof(ReclusterControl), cudaMemcpyDeviceToHost, main_s));
         CU_CHECK(c, cudaMemcpyAsync(flags->edge_scalars, c->edges.scalars, sizeof(int) * 4, cudaMemcpyDeviceToHost, main_s));
         flags->peac_hdr[0] = flags->peac_hdr[1] = flags->peac_hdr[2] = flags->peac_hdr[3] = 0;
         if (c->cfg.plane_edges) SD_CHECK(peac_copy_sticky_overflow(c, &P->peac[p], &flags->peac_hdr[2]));
