@@ -170,11 +170,11 @@ __global__ void __launch_bounds__(1024) k_sample_pairs(const float2 *__restrict_
 //   * refinement: the float accumulations of J^T J, J^T e and the squared error run strictly in inlier order (one thread
 //     per accumulator over per-point products staged in shared memory), because float addition is order dependent.
 #define RHO_NT 512
-#define RHO_TILE 512
+#define RHO_TILE2 256            // inliers per product tile of the refinement (two tiles: double buffered)
 #define RHO_ACC 36               // the 27 entries of JtJ the library updates (lower triangle without the zero block), 8 of Jte, S
 #define RHO_WORDS (HG_MAX_SAMPLES / 32)
 #define RHO_SMEM (sizeof(float2) * 2 * HG_MAX_SAMPLES + sizeof(unsigned short) * (2 * HG_MAX_SAMPLES + 8) + sizeof(unsigned) * 3 * RHO_WORDS + \
-                  sizeof(float) * RHO_ACC * (RHO_TILE + 1))
+                  sizeof(float) * 2 * RHO_ACC * (RHO_TILE2 + 1))
 
 struct RhoPrng { unsigned long long s0, s1; };
 __device__ __forceinline__ double rho_random(RhoPrng &g)
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
     unsigned short *s_tbl = (unsigned short *)(s_dst + HG_MAX_SAMPLES);     // non-randomness table, N + 1 entries
     unsigned short *s_idx = s_tbl + HG_MAX_SAMPLES + 8;                      // inlier indexes of the best model, ascending
     unsigned *s_new = (unsigned *)(s_idx + HG_MAX_SAMPLES), *s_buf0 = s_new + RHO_WORDS, *s_buf1 = s_buf0 + RHO_WORDS;
-    float *s_prod = (float *)(s_buf1 + RHO_WORDS);                           // RHO_ACC x (RHO_TILE + 1)
+    float *s_prod = (float *)(s_buf1 + RHO_WORDS);                           // 2 x RHO_ACC x (RHO_TILE2 + 1)
     __shared__ float s_H[9], s_acc[RHO_ACC];
     __shared__ int s_go, s_ninl_list, s_warp_cnt[RHO_WORDS], s_tot_inl, s_nstar, s_ns_which, s_ns_stop, s_cert, s_unc;
     __shared__ double s_logAcc, s_logRej, s_logA, s_scan_s[RHO_NT / 32], s_scan_m[RHO_NT / 32];
@@ -720,47 +720,57 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
         __syncthreads();
         const int ni = s_ninl_list;
         // sacCalcJacobianErrors at the homography in s_H: per-point products staged per tile, accumulators summed in inlier order
+        // The sequential sums (one dependent FADD per inlier and accumulator, ~6 cycles each) are the critical path of the
+        // refinement; the per-point products hide behind them: while the RHO_ACC accumulator threads (warps 0 and 1, alone on
+        // the SM's schedulers 0 and 1) sum tile t, the producer warps (those of schedulers 2 and 3: warps 2, 3, 6, 7, ...) fill
+        // tile t + 1 of the double buffer.
+        const int wq = tid >> 5;
+        const int pt = (wq & 2) ? (((wq >> 2) * 2 + (wq & 1)) * 32 + (tid & 31)) : -1;     // producer index 0 .. RHO_TILE2 - 1
+        auto produce = [&](int t0, int tn, float *buf) {
+            if (pt < 0 || pt >= tn) return;
+            const int i = s_idx[t0 + pt];
+            const float x = s_src[i].x, y = s_src[i].y, X = s_dst[i].x, Y = s_dst[i].y;
+            const float Wd = s_H[6] * x + s_H[7] * y + 1.0f;
+            const float iW = fabsf(Wd) > 1.1920929e-07f ? 1.0f / Wd : 0;
+            const float rX = (s_H[0] * x + s_H[1] * y + s_H[2]) * iW;
+            const float rY = (s_H[3] * x + s_H[4] * y + s_H[5]) * iW;
+            const float eX = rX - X, eY = rY - Y;
+            const float e = eX * eX + eY * eY;
+            const float dxh11 = x * iW, dxh12 = y * iW, dxh13 = iW, dxh31 = -rX * x * iW, dxh32 = -rX * y * iW;
+            const float dyh21 = x * iW, dyh22 = y * iW, dyh23 = iW, dyh31 = -rY * x * iW, dyh32 = -rY * y * iW;
+            float *col = buf + pt;
+#define RHO_P(a, v) col[(a) * (RHO_TILE2 + 1)] = (v)
+            RHO_P(0, dxh11 * dxh11);
+            RHO_P(1, dxh11 * dxh12); RHO_P(2, dxh12 * dxh12);
+            RHO_P(3, dxh11 * dxh13); RHO_P(4, dxh12 * dxh13); RHO_P(5, dxh13 * dxh13);
+            RHO_P(6, dyh21 * dyh21);
+            RHO_P(7, dyh21 * dyh22); RHO_P(8, dyh22 * dyh22);
+            RHO_P(9, dyh21 * dyh23); RHO_P(10, dyh22 * dyh23); RHO_P(11, dyh23 * dyh23);
+            RHO_P(12, dxh11 * dxh31); RHO_P(13, dxh12 * dxh31); RHO_P(14, dxh13 * dxh31);
+            RHO_P(15, dyh21 * dyh31); RHO_P(16, dyh22 * dyh31); RHO_P(17, dyh23 * dyh31);
+            RHO_P(18, dxh31 * dxh31 + dyh31 * dyh31);
+            RHO_P(19, dxh11 * dxh32); RHO_P(20, dxh12 * dxh32); RHO_P(21, dxh13 * dxh32);
+            RHO_P(22, dyh21 * dyh32); RHO_P(23, dyh22 * dyh32); RHO_P(24, dyh23 * dyh32);
+            RHO_P(25, dxh31 * dxh32 + dyh31 * dyh32);
+            RHO_P(26, dxh32 * dxh32 + dyh32 * dyh32);
+            RHO_P(27, eX * dxh11); RHO_P(28, eX * dxh12); RHO_P(29, eX * dxh13);
+            RHO_P(30, eY * dyh21); RHO_P(31, eY * dyh22); RHO_P(32, eY * dyh23);
+            RHO_P(33, eX * dxh31 + eY * dyh31);
+            RHO_P(34, eX * dxh32 + eY * dyh32);
+            RHO_P(35, e);
+#undef RHO_P
+        };
         auto eval = [&]() {
             float acc = 0.0f;
-            for (int t0 = 0; t0 < ni; t0 += RHO_TILE) {
-                const int tn = min(RHO_TILE, ni - t0);
-                __syncthreads();
-                if (tid < tn) {
-                    const int i = s_idx[t0 + tid];
-                    const float x = s_src[i].x, y = s_src[i].y, X = s_dst[i].x, Y = s_dst[i].y;
-                    const float Wd = s_H[6] * x + s_H[7] * y + 1.0f;
-                    const float iW = fabsf(Wd) > 1.1920929e-07f ? 1.0f / Wd : 0;
-                    const float rX = (s_H[0] * x + s_H[1] * y + s_H[2]) * iW;
-                    const float rY = (s_H[3] * x + s_H[4] * y + s_H[5]) * iW;
-                    const float eX = rX - X, eY = rY - Y;
-                    const float e = eX * eX + eY * eY;
-                    const float dxh11 = x * iW, dxh12 = y * iW, dxh13 = iW, dxh31 = -rX * x * iW, dxh32 = -rX * y * iW;
-                    const float dyh21 = x * iW, dyh22 = y * iW, dyh23 = iW, dyh31 = -rY * x * iW, dyh32 = -rY * y * iW;
-                    float *col = s_prod + tid;
-#define RHO_P(a, v) col[(a) * (RHO_TILE + 1)] = (v)
-                    RHO_P(0, dxh11 * dxh11);
-                    RHO_P(1, dxh11 * dxh12); RHO_P(2, dxh12 * dxh12);
-                    RHO_P(3, dxh11 * dxh13); RHO_P(4, dxh12 * dxh13); RHO_P(5, dxh13 * dxh13);
-                    RHO_P(6, dyh21 * dyh21);
-                    RHO_P(7, dyh21 * dyh22); RHO_P(8, dyh22 * dyh22);
-                    RHO_P(9, dyh21 * dyh23); RHO_P(10, dyh22 * dyh23); RHO_P(11, dyh23 * dyh23);
-                    RHO_P(12, dxh11 * dxh31); RHO_P(13, dxh12 * dxh31); RHO_P(14, dxh13 * dxh31);
-                    RHO_P(15, dyh21 * dyh31); RHO_P(16, dyh22 * dyh31); RHO_P(17, dyh23 * dyh31);
-                    RHO_P(18, dxh31 * dxh31 + dyh31 * dyh31);
-                    RHO_P(19, dxh11 * dxh32); RHO_P(20, dxh12 * dxh32); RHO_P(21, dxh13 * dxh32);
-                    RHO_P(22, dyh21 * dyh32); RHO_P(23, dyh22 * dyh32); RHO_P(24, dyh23 * dyh32);
-                    RHO_P(25, dxh31 * dxh32 + dyh31 * dyh32);
-                    RHO_P(26, dxh32 * dxh32 + dyh32 * dyh32);
-                    RHO_P(27, eX * dxh11); RHO_P(28, eX * dxh12); RHO_P(29, eX * dxh13);
-                    RHO_P(30, eY * dyh21); RHO_P(31, eY * dyh22); RHO_P(32, eY * dyh23);
-                    RHO_P(33, eX * dxh31 + eY * dyh31);
-                    RHO_P(34, eX * dxh32 + eY * dyh32);
-                    RHO_P(35, e);
-#undef RHO_P
-                }
-                __syncthreads();
+            __syncthreads();                                   // s_H of this evaluation is visible; the buffers are free
+            produce(0, min(RHO_TILE2, ni), s_prod);
+            __syncthreads();
+            int par = 0;
+            for (int t0 = 0; t0 < ni; t0 += RHO_TILE2, par ^= 1) {
+                const int tn = min(RHO_TILE2, ni - t0);
+                if (t0 + RHO_TILE2 < ni) produce(t0 + RHO_TILE2, min(RHO_TILE2, ni - t0 - RHO_TILE2), s_prod + (par ^ 1) * RHO_ACC * (RHO_TILE2 + 1));
                 if (tid < RHO_ACC) {
-                    const float *row = s_prod + tid * (RHO_TILE + 1);
+                    const float *row = s_prod + par * RHO_ACC * (RHO_TILE2 + 1) + tid * (RHO_TILE2 + 1);
                     int q = 0;
                     for (; q + 8 <= tn; q += 8) {
                         const float v0 = row[q], v1 = row[q + 1], v2 = row[q + 2], v3 = row[q + 3], v4 = row[q + 4], v5 = row[q + 5], v6 = row[q + 6], v7 = row[q + 7];
@@ -768,6 +778,7 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                     }
                     for (; q < tn; q++) acc += row[q];
                 }
+                __syncthreads();
             }
             if (tid < RHO_ACC) s_acc[tid] = acc;
             __syncthreads();
