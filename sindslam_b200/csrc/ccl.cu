@@ -28,10 +28,12 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b)
 // instead of N/256 of them (the decision stage launches 128 planes for ~10 active ones).
 #define CCL_BPP 96   // blocks per plane
 
-__global__ void k_ccl_init(const uint8_t *__restrict__ cls, int *__restrict__ labels, int W, int H, const int *__restrict__ active)
+// key_from: planes key_from, key_from + 1, ... are CCL_KEY8 planes that are always active (the decision stage labels its
+// cluster planes and its two keyed planes in one launch chain)
+__global__ void k_ccl_init(const uint8_t *__restrict__ cls, int *__restrict__ labels, int W, int H, const int *__restrict__ active, int key_from)
 {
     const int plane = blockIdx.z;
-    if (active && plane >= *active) return;
+    if (plane < key_from && active && plane >= *active) return;
     const int N = W * H;
     const int segs = (W + 31) >> 5;
     const int lane = threadIdx.x & 31;
@@ -50,10 +52,11 @@ __global__ void k_ccl_init(const uint8_t *__restrict__ cls, int *__restrict__ la
     if (blockIdx.x == 0 && threadIdx.x == 0) L[N] = N;
 }
 
-__global__ void k_ccl_merge(const uint8_t *__restrict__ cls, int *__restrict__ labels, int W, int H, int mode, const int *__restrict__ active)
+__global__ void k_ccl_merge(const uint8_t *__restrict__ cls, int *__restrict__ labels, int W, int H, int mode, const int *__restrict__ active, int key_from)
 {
     const int plane = blockIdx.z;
-    if (active && plane >= *active) return;
+    if (plane < key_from && active && plane >= *active) return;
+    if (plane >= key_from) mode = CCL_KEY8;
     const int N = W * H;
     const uint8_t *c = cls + (size_t)plane * N;
     int *L = labels + (size_t)plane * (N + 1);
@@ -79,10 +82,10 @@ __global__ void k_ccl_merge(const uint8_t *__restrict__ cls, int *__restrict__ l
     }
 }
 
-__global__ void k_ccl_flatten(int *__restrict__ labels, int N, const int *__restrict__ active)
+__global__ void k_ccl_flatten(int *__restrict__ labels, int N, const int *__restrict__ active, int key_from)
 {
     const int plane = blockIdx.z;
-    if (active && plane >= *active) return;
+    if (plane < key_from && active && plane >= *active) return;
     int *L = labels + (size_t)plane * (N + 1);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= N; i += gridDim.x * blockDim.x) L[i] = uf_find(L, i);
 }
@@ -91,11 +94,17 @@ static inline int ccl_blocks(int work_items) { int b = cdiv(work_items, 256); re
 
 int ccl_run(sindyn_base *ctx, const uint8_t *cls, int *labels, int W, int H, int planes, int mode, const int *active_planes)
 {
+    return ccl_run_mixed(ctx, cls, labels, W, H, planes, 0, mode, active_planes);
+}
+
+int ccl_run_mixed(sindyn_base *ctx, const uint8_t *cls, int *labels, int W, int H, int planes, int key_planes, int mode, const int *active_planes)
+{
     const int N = W * H;
     const int segs = (W + 31) >> 5;
-    LAUNCH(ctx, k_ccl_init, dim3(ccl_blocks(segs * H * 32), 1, planes), 256, 0, cls, labels, W, H, active_planes);
-    LAUNCH(ctx, k_ccl_merge, dim3(ccl_blocks(N), 1, planes), 256, 0, cls, labels, W, H, mode, active_planes);
-    LAUNCH(ctx, k_ccl_flatten, dim3(ccl_blocks(N + 1), 1, planes), 256, 0, labels, N, active_planes);
+    const int key_from = key_planes ? planes : 0x7fffffff, nz = planes + key_planes;
+    LAUNCH(ctx, k_ccl_init, dim3(ccl_blocks(segs * H * 32), 1, nz), 256, 0, cls, labels, W, H, active_planes, key_from);
+    LAUNCH(ctx, k_ccl_merge, dim3(ccl_blocks(N), 1, nz), 256, 0, cls, labels, W, H, mode, active_planes, key_from);
+    LAUNCH(ctx, k_ccl_flatten, dim3(ccl_blocks(N + 1), 1, nz), 256, 0, labels, N, active_planes, key_from);
     LAUNCH_CHECK(ctx);
     return SINDYN_OK;
 }

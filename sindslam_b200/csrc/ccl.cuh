@@ -30,6 +30,8 @@ struct RegionStats {       // per (plane, root pixel)
 // labels: planes x (N + 1) ints (index N is the exterior node in CCL_REGION mode).
 // active_planes (device, may be null): planes >= *active_planes exit immediately.
 int ccl_run(sindyn_base *ctx, const uint8_t *cls, int *labels, int W, int H, int planes, int mode, const int *active_planes);
+// the same with key_planes further planes (index planes, planes + 1, ...) that are CCL_KEY8 and always active: one launch chain
+int ccl_run_mixed(sindyn_base *ctx, const uint8_t *cls, int *labels, int W, int H, int planes, int key_planes, int mode, const int *active_planes);
 
 // Region helpers usable from other translation units (device inline)
 __device__ __forceinline__ int rc_exterior(const int *L, int N) { return L[N]; }

@@ -158,8 +158,6 @@ int decide_init(sindyn_base *ctx, DecideStage *d, int W, int H)
     d->ctl = c;
     uint8_t **up[] = {&d->low0, &d->low, &d->filled, &d->dyna, &d->tmp, &d->out};
     for (uint8_t **p : up) SD_CHECK(ctx->dalloc(p, N));
-    SD_CHECK(ctx->dalloc(&d->key, 2 * N));
-    SD_CHECK(ctx->dalloc(&d->keyL, 2 * (N + 1)));
     SD_CHECK(ctx->dalloc(&d->seedflag, 2 * N));
     return SINDYN_OK;
 }
@@ -172,14 +170,17 @@ int decide_run(sindyn_base *ctx, DecideStage *d, uint8_t *cls, int *labelsL, Reg
     LAUNCH(ctx, k_dd_reset, 1, 256, 0, ctl);
     LAUNCH(ctx, k_dd_low_counts, SINDYN_NUM_SMS_B200 * 2, 256, 0, low_in, high, high_last, total_area, labels, N, d->low0, ctl);
     SD_CHECK(morph_run(ctx, d->low0, d->low, d->tmp, W, H, 5, MORPH_DILATE));
-    LAUNCH(ctx, k_dd_planes, cdiv(N, 256), 256, 0, labels, high, d->low, N, ctl, cls, d->key);
-    SD_CHECK(ccl_run(ctx, cls, labelsL, W, H, DD_MAXL, CCL_REGION, &ctl->nmax));
+    // the two keyed planes of the flood-fill surrogate are planes DD_MAXL, DD_MAXL + 1 of the caller's scratch: all labelling in
+    // one launch chain (the keyed pass alone costs as much as the 128-plane one: it is latency, not work)
+    uint8_t *key = cls + (size_t)DD_MAXL * N;
+    int *keyL = labelsL + (size_t)DD_MAXL * (N + 1);
+    LAUNCH(ctx, k_dd_planes, cdiv(N, 256), 256, 0, labels, high, d->low, N, ctl, cls, key);
+    SD_CHECK(ccl_run_mixed(ctx, cls, labelsL, W, H, DD_MAXL, 2, CCL_REGION, &ctl->nmax));
     SD_CHECK(ccl_top_image(ctx, labelsL, top, W, H, DD_MAXL, &ctl->nmax, stats));
     SD_CHECK(ccl_quad_stats_ccomp(ctx, cls, labelsL, stats, W, H, DD_MAXL, &ctl->nmax));
-    SD_CHECK(ccl_run(ctx, d->key, d->keyL, W, H, 2, CCL_KEY8, nullptr));
     CU_CHECK(ctx, cudaMemsetAsync(d->seedflag, 0, 2 * (size_t)N, ctx->stream));
-    LAUNCH(ctx, k_dd_seeds, dim3(96, 1, DD_MAXL), 256, 0, cls, labelsL, stats, d->low, labels, d->keyL, W, H, ctl, d->seedflag);
-    LAUNCH(ctx, k_dd_filled, SINDYN_NUM_SMS_B200 * 2, 256, 0, labels, d->low, d->keyL, d->seedflag, N, ctl, d->filled);
+    LAUNCH(ctx, k_dd_seeds, dim3(96, 1, DD_MAXL), 256, 0, cls, labelsL, stats, d->low, labels, keyL, W, H, ctl, d->seedflag);
+    LAUNCH(ctx, k_dd_filled, SINDYN_NUM_SMS_B200 * 2, 256, 0, labels, d->low, keyL, d->seedflag, N, ctl, d->filled);
     LAUNCH(ctx, k_dd_dyna, cdiv(N, 256), 256, 0, labels, d->filled, N, ctl, d->dyna);
     SD_CHECK(morph_run(ctx, d->dyna, d->filled, d->tmp, W, H, 9, MORPH_DILATE));
     LAUNCH(ctx, k_dd_final, cdiv(N, 256), 256, 0, d->filled, total_area, N, d->out);

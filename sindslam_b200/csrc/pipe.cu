@@ -37,8 +37,8 @@ struct FramePipe {
     EdgeStage edges[PIPE_NB], own_edges;            // gradient edges / end points / total area of a frame (depth only: run ahead, read until the decision)
     cudaEvent_t ev_in[PIPE_NB] = {}, ev_a[PIPE_NB] = {}, ev_p[PIPE_NB] = {}, ev_done[PIPE_NB] = {}, ev_e[PIPE_NB] = {}, ev_join = nullptr, ev_sync = nullptr, ev_gray[4] = {};
     bool gray_pending[4] = {false, false, false, false};
-    cudaGraphExec_t g_c1[PIPE_NB] = {}, g_c2[PIPE_NB] = {}, g_p[PIPE_NB] = {}, g_e[PIPE_NB] = {};
-    unsigned long long n_c1[PIPE_NB] = {}, n_c2[PIPE_NB] = {}, n_p[PIPE_NB] = {}, n_e[PIPE_NB] = {};
+    cudaGraphExec_t g_c1[PIPE_NB] = {}, g_c2[PIPE_NB] = {}, g_p[PIPE_NB] = {}, g_e[PIPE_NB] = {}, g_d[PIPE_NB] = {};
+    unsigned long long n_c1[PIPE_NB] = {}, n_c2[PIPE_NB] = {}, n_p[PIPE_NB] = {}, n_e[PIPE_NB] = {}, n_d[PIPE_NB] = {};
     cudaStream_t built_for = nullptr;               // the handle stream the graphs were captured under
     unsigned long long frame_no = 0;
     bool fresh = true;                              // the pipeline's streams have to wait for the handle's stream first
@@ -60,7 +60,8 @@ static void pipe_drop_graphs(FramePipe *P)
         if (P->g_c2[p]) cudaGraphExecDestroy(P->g_c2[p]);
         if (P->g_p[p]) cudaGraphExecDestroy(P->g_p[p]);
         if (P->g_e[p]) cudaGraphExecDestroy(P->g_e[p]);
-        P->g_c1[p] = P->g_c2[p] = P->g_p[p] = P->g_e[p] = nullptr;
+        if (P->g_d[p]) cudaGraphExecDestroy(P->g_d[p]);
+        P->g_c1[p] = P->g_c2[p] = P->g_p[p] = P->g_e[p] = P->g_d[p] = nullptr;
     }
 }
 
@@ -86,8 +87,8 @@ static int pipe_init(sindyn_ctx *c)
     P->flow_full[0] = c->flow_full; P->fb_flag[0] = c->fb_flag; P->fb_flag_host[0] = c->fb_flag_host; P->depth[0] = c->depth; P->plane_edges[0] = c->plane_edges;
     {
         const size_t N = (size_t)c->N;
-        SD_CHECK(c->dalloc(&P->dd_cls, N * DD_MAXL));
-        SD_CHECK(c->dalloc(&P->dd_labels, (N + 1) * DD_MAXL));
+        SD_CHECK(c->dalloc(&P->dd_cls, N * (DD_MAXL + 2)));
+        SD_CHECK(c->dalloc(&P->dd_labels, (N + 1) * (DD_MAXL + 2)));
         SD_CHECK(c->dalloc(&P->dd_top, N * DD_MAXL));
         SD_CHECK(c->dalloc(&P->dd_stats, N * DD_MAXL));
         P->own_label_out = c->rc.label_out;
@@ -306,11 +307,17 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_a[k], 0));
     SD_CHECK(flow_part_b(c, k));
     CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_join, 0));
-    SD_CHECK(decide_run(c, &c->dd, P->dd_cls, P->dd_labels, P->dd_stats, P->dd_top, c->mask_low, c->mask_high, c->high_last, c->edges.total_area,
-                        c->rc.label_out));
-    CU_CHECK(c, cudaMemcpyAsync(c->dyna_last, c->dd.out, c->N, cudaMemcpyDeviceToDevice, main_s));
-    CU_CHECK(c, cudaMemcpyAsync(c->high_last, c->mask_high, c->N, cudaMemcpyDeviceToDevice, main_s));
-    CU_CHECK(c, cudaMemcpyAsync(c->label_last, c->rc.label_out, c->N, cudaMemcpyDeviceToDevice, main_s));
+    if (!P->g_d[k])     // decision + state roll (DynaDetect.cc:1543-1636,1660-1664): ~25 launches and three copies as one graph
+        SD_CHECK(pipe_capture(c, main_s, &P->g_d[k], &P->n_d[k], [&]() -> int {
+            SD_CHECK(decide_run(c, &c->dd, P->dd_cls, P->dd_labels, P->dd_stats, P->dd_top, c->mask_low, c->mask_high, c->high_last, c->edges.total_area,
+                                c->rc.label_out));
+            CU_CHECK(c, cudaMemcpyAsync(c->dyna_last, c->dd.out, c->N, cudaMemcpyDeviceToDevice, c->stream));
+            CU_CHECK(c, cudaMemcpyAsync(c->high_last, c->mask_high, c->N, cudaMemcpyDeviceToDevice, c->stream));
+            CU_CHECK(c, cudaMemcpyAsync(c->label_last, c->rc.label_out, c->N, cudaMemcpyDeviceToDevice, c->stream));
+            return (int)SINDYN_OK;
+        }));
+    CU_CHECK(c, cudaGraphLaunch(P->g_d[k], main_s));
+    c->launches += P->n_d[k];
     if (flags) {
         CU_CHECK(c, cudaMemcpyAsync(flags->edge_scalars, c->edges.scalars, sizeof(int) * 4, cudaMemcpyDeviceToHost, main_s));
         flags->peac_hdr[0] = flags->peac_hdr[1] = flags->peac_hdr[2] = flags->peac_hdr[3] = 0;

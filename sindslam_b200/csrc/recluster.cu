@@ -471,8 +471,8 @@ int recluster_init(sindyn_base *ctx, ReclusterStage *r, int W, int H)
     SD_CHECK(ctx->dalloc(&r->plane_of, N));
     SD_CHECK(ctx->dalloc(&r->mcl, N));
     SD_CHECK(ctx->dalloc(&r->mcl_tmp, N));
-    SD_CHECK(ctx->dalloc(&r->cls, N * RC_MAXC));
-    SD_CHECK(ctx->dalloc(&r->labels, (N + 1) * RC_MAXC));
+    SD_CHECK(ctx->dalloc(&r->cls, N * (RC_MAXC + 2)));            // (+ 2: the decision stage's keyed planes, decide.cu)
+    SD_CHECK(ctx->dalloc(&r->labels, (N + 1) * (RC_MAXC + 2)));
     SD_CHECK(ctx->dalloc(&r->top, N * RC_MAXC));
     SD_CHECK(ctx->dalloc(&r->stats, N * RC_MAXC));
     B128 **bp[] = {&r->F, &r->CI, &r->CD, &r->T1, &r->LJ, &r->tmpb, &r->tmpb2};
