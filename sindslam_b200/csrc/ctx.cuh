@@ -124,6 +124,8 @@ void pipe_destroy(sindyn_ctx *c);                          // pipe.cu
 bool pipe_usable(const sindyn_ctx *c);                     // pipe.cu: graphs on, no stage timing
 int pipe_copy_headers(sindyn_ctx *c);                      // pipe.cu: asynchronous copy of the plane-fitter headers of both pipeline instances
 bool pipe_overflow(const sindyn_ctx *c);                   // pipe.cu: ... and their overflow flags, valid after the stream was synchronised
+cudaEvent_t pipe_done_event(sindyn_ctx *c);                // pipe.cu: the last frame is decided (final mask, labels, rolled state)
+int pipe_note_mask_read(sindyn_ctx *c, cudaStream_t s);    // pipe.cu: stream s has read the last frame's final mask
 cudaEvent_t pipe_input_event(sindyn_ctx *c);               // pipe.cu: the last frame's inputs are in place (bgr ring slot, depth)
 int cluster_part1(sindyn_ctx *c);                          // detect.cu: k-means
 int cluster_part2(sindyn_ctx *c);                          // detect.cu: plane-edge filter + re-clustering

@@ -952,12 +952,20 @@ static int track_enqueue_pipe(sindyn_ctx *c, sindyn_orb *o, const uint8_t *bgr_s
            o->pyr + (size_t)ORB_EDGE * L0.pitch + ORB_EDGE, L0.pitch);
     SD_CHECK(pipe_note_gray_read(c, o->stream));
     SD_CHECK(orb_enqueue_unmasked(o));
-    CU_CHECK(c, cudaStreamWaitEvent(c->stream, t->ev_orb_done, 0));
-    if (dilate_k > 1) SD_CHECK(morph_run(c, c->dd.out, o->mask, nullptr, c->W, c->H, dilate_k, MORPH_DILATE));
-    else CU_CHECK(c, cudaMemcpyAsync(o->mask, c->dd.out, c->N, cudaMemcpyDeviceToDevice, c->stream));
+    // the 15x15 dilation runs on the extractor's stream (after the previous frame's erasure half in stream order, so o->mask is
+    // free): the detector's stream goes straight on to the next frame's homography -- that chain bounds the frame rate
+    CU_CHECK(o, cudaStreamWaitEvent(o->stream, pipe_done_event(c), 0));
+    {
+        cudaStream_t keep = c->stream;
+        c->stream = o->stream;
+        int st = SINDYN_OK;
+        if (dilate_k > 1) st = morph_run(c, c->dd.out, o->mask, nullptr, c->W, c->H, dilate_k, MORPH_DILATE);
+        else if (cudaMemcpyAsync(o->mask, c->dd.out, c->N, cudaMemcpyDeviceToDevice, o->stream) != cudaSuccess) st = SINDYN_ERR_CUDA;
+        c->stream = keep;
+        SD_CHECK(st);
+    }
     LAUNCH_CHECK(c);
-    CU_CHECK(c, cudaEventRecord(t->ev_mask, c->stream));
-    CU_CHECK(o, cudaStreamWaitEvent(o->stream, t->ev_mask, 0));
+    SD_CHECK(pipe_note_mask_read(c, o->stream));
     SD_CHECK(orb_enqueue_masked(o, true));
     CU_CHECK(o, cudaEventRecord(t->ev_orb_done, o->stream));
     return SINDYN_OK;
@@ -1020,11 +1028,11 @@ extern "C" int sindyn_track_submit(sindyn_handle h, sindyn_orb_handle o, const u
     if (t->n_submit - t->n_collect >= TRACK_NB) { h->err = "track_submit: three frames are in flight already, collect one first"; return SINDYN_ERR_STATE; }
     const int p = (int)(t->n_submit % TRACK_NB);
     SD_CHECK(track_enqueue_pipe(h, o, bgr, bgr_step, depth, depth_step, true, t->r_flags[p], rgb_order, dilate_k));
-    // results into this parity's pinned buffers: mask and labels on the detector's stream (the labels from the rolled state: the
-    // next frame's re-clustering may already overwrite rc.label_out), key points on the extractor's
-    CU_CHECK(h, cudaMemcpyAsync(t->r_mask[p], o->mask, h->N, cudaMemcpyDeviceToHost, h->stream));
+    // results into this slot's pinned buffers: the labels on the detector's stream (from the rolled state: a later frame's
+    // re-clustering may already overwrite rc.label_out), the dilated mask and the key points on the extractor's
     CU_CHECK(h, cudaMemcpyAsync(t->r_label[p], h->label_last, h->N, cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaEventRecord(t->ev_res_main[p], h->stream));
+    CU_CHECK(o, cudaMemcpyAsync(t->r_mask[p], o->mask, h->N, cudaMemcpyDeviceToHost, o->stream));
     CU_CHECK(o, cudaMemcpyAsync(t->r_ctl[p], o->ctl, sizeof(OrbControl), cudaMemcpyDeviceToHost, o->stream));
     CU_CHECK(o, cudaMemcpyAsync(t->r_kp[p], o->out_host_fmt, sizeof(sindyn_keypoint) * t->r_cap, cudaMemcpyDeviceToHost, o->stream));
     CU_CHECK(o, cudaMemcpyAsync(t->r_desc[p], o->desc, (size_t)32 * t->r_cap, cudaMemcpyDeviceToHost, o->stream));

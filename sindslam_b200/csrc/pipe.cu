@@ -37,6 +37,8 @@ struct FramePipe {
     EdgeStage edges[PIPE_NB], own_edges;            // gradient edges / end points / total area of a frame (depth only: run ahead, read until the decision)
     cudaEvent_t ev_in[PIPE_NB] = {}, ev_a[PIPE_NB] = {}, ev_p[PIPE_NB] = {}, ev_done[PIPE_NB] = {}, ev_e[PIPE_NB] = {}, ev_join = nullptr, ev_sync = nullptr, ev_gray[4] = {};
     bool gray_pending[4] = {false, false, false, false};
+    cudaEvent_t ev_ddout = nullptr;                 // the extractor's stream has read the final mask (dd.out) of the last frame
+    bool ddout_pending = false;
     cudaGraphExec_t g_c1[PIPE_NB] = {}, g_c2[PIPE_NB] = {}, g_p[PIPE_NB] = {}, g_e[PIPE_NB] = {}, g_d[PIPE_NB] = {};
     unsigned long long n_c1[PIPE_NB] = {}, n_c2[PIPE_NB] = {}, n_p[PIPE_NB] = {}, n_e[PIPE_NB] = {}, n_d[PIPE_NB] = {};
     cudaStream_t built_for = nullptr;               // the handle stream the graphs were captured under
@@ -121,6 +123,7 @@ static int pipe_init(sindyn_ctx *c)
     }
     for (int k = 0; k < 4; ++k) CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_gray[k], cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_ddout, cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_sync, cudaEventDisableTiming));
     return SINDYN_OK;
 }
@@ -137,7 +140,7 @@ void pipe_destroy(sindyn_ctx *c)
     for (int p = 0; p < 2; ++p) cudaEventDestroy(P->ev_h2d[p]);
     for (int k = 0; k < 4; ++k) cudaEventDestroy(P->ev_gray[k]);
     brox_destroy(&P->brox[1]); brox_destroy(&P->brox_lm[1]);
-    cudaEventDestroy(P->ev_join); cudaEventDestroy(P->ev_sync);
+    cudaEventDestroy(P->ev_join); cudaEventDestroy(P->ev_sync); cudaEventDestroy(P->ev_ddout);
     if (P->sa[0]) cudaStreamDestroy(P->sa[0]);
     if (P->sa[1]) cudaStreamDestroy(P->sa[1]);
     if (P->sp[1]) cudaStreamDestroy(P->sp[1]);
@@ -171,6 +174,17 @@ FlowRes pipe_flow_res(sindyn_ctx *c, int k)     // k = frame % PIPE_NB: output b
 }
 
 cudaEvent_t pipe_input_event(sindyn_ctx *c) { return c->pipe ? c->pipe->ev_in[c->pipe->last_k] : nullptr; }
+cudaEvent_t pipe_done_event(sindyn_ctx *c) { return c->pipe ? c->pipe->ev_done[c->pipe->last_k] : nullptr; }
+
+// the caller dilates / copies the last frame's final mask (dd.out) on another stream: the next decision overwrites it only after that
+int pipe_note_mask_read(sindyn_ctx *c, cudaStream_t s)
+{
+    FramePipe *P = c->pipe;
+    if (!P) return SINDYN_OK;
+    CU_CHECK(c, cudaEventRecord(P->ev_ddout, s));
+    P->ddout_pending = true;
+    return SINDYN_OK;
+}
 
 // the ORB extractor reads the BGR ring slot of the frame on its own stream: the slot may be overwritten only after that
 int pipe_note_gray_read(sindyn_ctx *c, cudaStream_t orb_stream)
@@ -307,6 +321,7 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_a[k], 0));
     SD_CHECK(flow_part_b(c, k));
     CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_join, 0));
+    if (P->ddout_pending) { CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_ddout, 0)); P->ddout_pending = false; }
     if (!P->g_d[k])     // decision + state roll (DynaDetect.cc:1543-1636,1660-1664): ~25 launches and three copies as one graph
         SD_CHECK(pipe_capture(c, main_s, &P->g_d[k], &P->n_d[k], [&]() -> int {
             SD_CHECK(decide_run(c, &c->dd, P->dd_cls, P->dd_labels, P->dd_stats, P->dd_top, c->mask_low, c->mask_high, c->high_last, c->edges.total_area,
