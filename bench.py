@@ -342,6 +342,67 @@ def multi_sequence_stats(cam, device, n_seq=4, n_frames=76, steps=4):
             "note": "same full per-frame path as the headline, n_seq concurrent sequences on one GPU, host wall clock"}
 
 
+def other_configs(device):
+    """The other single-GPU BASELINE configurations, outside the headline: configs[1] -- the flow + ego-motion-residual branch alone
+    on 640x480 pairs (sindyn_flow_residual_resident: Brox, refinement, RHO, residual, thresholds, masks; frame at a time) -- and
+    configs[3] -- the full per-frame path on an 848x480 D455-shaped sequence with a humanoid-sized dynamic region (frame pipeline,
+    like the headline)."""
+    import torch
+    from sindslam_b200 import synth
+    from sindslam_b200.capi import Orb, SinDyn
+    out = {}
+    # ---- configs[1]
+    cam = synth.TUM3
+    n = 46
+    _, fr = synth.make_sequence_parallel(n, cam, seq=300, kind="box", start=0, hole_rate=HOLE_RATE)
+    sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=device, refine=1, plane_edges=1)
+    st = torch.cuda.Stream(device=device)
+    sd.set_stream(st.cuda_stream)
+    for i, f in enumerate(fr):
+        sd.upload_frame(i, f.bgr, f.depth)
+    sd.set_prev_frames(fr[0].bgr, fr[0].bgr)
+    for k in range(1, 16):
+        sd.flow_residual_resident(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for k in range(16, n):
+        sd.flow_residual_resident(k)
+    e1.record(st)
+    torch.cuda.synchronize()
+    out["configs1_flow_residual_branch"] = {"pairs_per_s": 1e3 * (n - 16) / e0.elapsed_time(e1), "ms_per_pair": e0.elapsed_time(e1) / (n - 16),
+                                            "note": "640x480, frames resident, one pair at a time (no look-ahead), device time"}
+    sd.close()
+    # ---- configs[3]
+    cam = synth.D455_848
+    n = 61
+    _, fr = synth.make_sequence_parallel(n, cam, seq=301, kind="humanoid", start=0, hole_rate=HOLE_RATE)
+    sd = SinDyn(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_factor, device=device, refine=1, plane_edges=1)
+    orb = Orb(*ORB_CFG, cam.width, cam.height, device=device)
+    st = torch.cuda.Stream(device=device)
+    sd.set_stream(st.cuda_stream)
+    for i, f in enumerate(fr):
+        sd.upload_frame(i, f.bgr, f.depth)
+    sd.set_prev_frames(fr[0].bgr, fr[0].bgr)
+    for k in range(1, 16):
+        orb.track_frame_resident(sd, k, k)
+    orb.track_join(sd)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for k in range(16, n):
+        orb.track_frame_resident(sd, k, k)
+    orb.track_join(sd)
+    e1.record(st)
+    torch.cuda.synchronize()
+    orb.track_results(sd)        # surfaces capacity errors
+    out["configs3_848x480_humanoid"] = {"pairs_per_s": 1e3 * (n - 16) / e0.elapsed_time(e1), "ms_per_pair": e0.elapsed_time(e1) / (n - 16),
+                                        "note": "848x480 D455-shaped, humanoid-sized dynamic region, full per-frame path incl. 15x15 dilation and masked ORB, "
+                                                "frames resident, frame pipeline, device time"}
+    orb.close()
+    sd.close()
+    return out
+
+
 def run_ours(args):
     import torch
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
@@ -508,6 +569,7 @@ def run_ours(args):
             extras["stage_ms_device"] = ms
             extras["roofline_per_stage"] = roofline_per_stage(ms, peak)
             extras["multi_sequence"] = multi_sequence_stats(cam, local) if world == 1 else None
+            extras["other_configs"] = other_configs(local) if world == 1 else None
             cpu_v, cpu_n, cpu_dt = cpu_full_pipeline(frames, cam, "brox", "fx", budget_s=15.0, max_pairs=40)
             extras["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                       "sample": f"{cpu_n} frame pairs in {cpu_dt:.1f} s through the full oracle pipeline (oracle/brox_cpu.c OpenMP Brox + cv2 "
