@@ -153,6 +153,8 @@ extern "C" int sindyn_set_prev_frames(sindyn_handle h, const uint8_t *bgr_last, 
 {
     H_CHECK(h);
     if (!bgr_last || !bgr_lastlast) return SINDYN_ERR_INVALID;
+    SD_CHECK(pipe_join(h));
+    pipe_invalidate(h);
     const size_t rb = (size_t)h->W * 3;
     CU_CHECK(h, copy_in_2d(h->bgr[h->i_last], bgr_last, step_last, rb, h->H, h->stream));
     CU_CHECK(h, copy_in_2d(h->bgr[h->i_lastlast], bgr_lastlast, step_lastlast, rb, h->H, h->stream));
@@ -263,6 +265,8 @@ extern "C" int sindyn_set_state(sindyn_handle h, int which, const uint8_t *in)
     case 4: dst = h->bgr[h->i_lastlast]; nb *= 3; prep = h->i_lastlast; break;
     default: return SINDYN_ERR_INVALID;
     }
+    SD_CHECK(pipe_join(h));      // frames still in the frame pipeline finish first; it re-reads the state on its next frame
+    pipe_invalidate(h);
     CU_CHECK(h, cudaMemcpyAsync(dst, in, nb, cudaMemcpyHostToDevice, h->stream));
     if (prep >= 0) { SD_CHECK(prep_frame(h, prep)); h->have_prev = true; }
     CU_CHECK(h, cudaStreamSynchronize(h->stream));

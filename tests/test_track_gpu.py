@@ -89,5 +89,22 @@ def test_pipelined_frames_equal_frame_at_a_time():
         oc.track_frame_resident(sc, k, k)
     oc.track_join(sc)
     same(oc.track_results(sc), ref[n - 2], n - 1)
+    # (c) state injected from outside (sindyn_set_state) between pipelined frames is picked up: labels (k-means warm start,
+    # sample weights) and dynamic mask (sample weights).  sa has seen frame n in (a): sc catches up first.
+    more = synth.make_sequence(n + 4, cam, seq=11, kind="box", start=3, hole_rate=0.0005)[1]
+    sc.upload_frame(0, more[n].bgr, more[n].depth)
+    oc.track_frame_resident(sc, 0, n)
+    same(oc.track_results(sc), want, n)
+    rng = np.random.default_rng(4)
+    lab = rng.integers(0, 6, (cam.height // 40, cam.width // 40)).repeat(40, 0).repeat(40, 1).astype(np.uint8)
+    dyn = np.full((cam.height, cam.width), 125, np.uint8)
+    dyn[100:220, 300:420] = 255
+    for s in (sa, sc):
+        s.set_state(2, lab)
+        s.set_state(0, dyn)
+    for k in range(n + 1, n + 4):
+        sc.upload_frame(k % 8, more[k].bgr, more[k].depth)
+        oc.track_frame_resident(sc, k % 8, k)
+        same(oc.track_results(sc), oa.track_frame(sa, more[k].bgr, more[k].depth, k), k)
     for h in (oa, ob, oc, sa, sb, sc):
         h.close()
