@@ -414,8 +414,8 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
     unsigned *s_new = (unsigned *)(s_idx + HG_MAX_SAMPLES), *s_buf0 = s_new + RHO_WORDS, *s_buf1 = s_buf0 + RHO_WORDS;
     float *s_prod = (float *)(s_buf1 + RHO_WORDS);                           // 2 x RHO_ACC x (RHO_TILE2 + 1)
     __shared__ float s_H[9], s_acc[RHO_ACC];
-    __shared__ int s_go, s_ninl_list, s_warp_cnt[RHO_WORDS], s_tot_inl, s_nstar, s_ns_which, s_ns_stop, s_cert, s_unc;
-    __shared__ double s_logAcc, s_logRej, s_logA, s_scan_s[RHO_NT / 32], s_scan_m[RHO_NT / 32];
+    __shared__ int s_go, s_ninl_list, s_warp_cnt[RHO_WORDS], s_tot_inl, s_nstar, s_ns_which, s_ns_stop, s_cert, s_unc, s_curw, s_cnt;
+    __shared__ double s_logAcc, s_logRej, s_logA, s_scan_s[RHO_NT / 32], s_scan_m[RHO_NT / 32], s_pre_s[RHO_NT / 32], s_pre_m[RHO_NT / 32];
     __shared__ unsigned s_ns_n[RHO_NT], s_ns_i[RHO_NT], s_ns_wn[RHO_NT / 32], s_ns_wi[RHO_NT / 32], s_ns_out[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int N = min(n_ptr[0], HG_MAX_SAMPLES);
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
         logAcc = log(lamAcc); logRej = log(lamRej); logA_d = log(A);
     }
     const float distSq = 3.0f * 3.0f;
-    if (tid == 0) s_nstar = 0;
+    if (tid == 0) { s_nstar = 0; s_curw = 0; }
     for (;;) {
         // ---- nStarOptimize of the model that has just become the best one (RHO_HEST_REFC::nStarOptimize), CTA-parallel.
         // The library walks test_n = N .. 21 with a running best ratio (inliers among the first test_n points) / test_n, strict
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                 break;
             }
             s_go = go;
-            s_tot_inl = 0; s_cert = 0x7fffffff; s_unc = 0x7fffffff;
+            s_tot_inl = 0; s_cert = 0x7fffffff; s_unc = 0x7fffffff; s_cnt = 0;
             s_logAcc = logAcc; s_logRej = logRej; s_logA = logA_d;
             { const long long t_ = clock64(); clk_a += t_ - clk_x; clk_x = t_; }
         }
@@ -615,8 +615,19 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
             }
             if (lane == 31) { s_scan_s[wid] = ss; s_scan_m[wid] = mm; }
             __syncthreads();
-            double bs = 0.0, bm = 0.0;                                   // everything before this warp
-            for (int q = 0; q < wid; ++q) { bm = fmin(bm, bs + s_scan_m[q]); bs += s_scan_s[q]; }
+            if (wid == 0) {     // exclusive scan of the RHO_NT / 32 warp totals with the same operator (one warp, four shuffle steps)
+                double ws = lane < RHO_NT / 32 ? s_scan_s[lane] : 0.0, wm = lane < RHO_NT / 32 ? s_scan_m[lane] : 0.0;
+#pragma unroll
+                for (int off = 1; off < RHO_NT / 32; off <<= 1) {
+                    const double ps = __shfl_up_sync(0xffffffffu, ws, off), pm = __shfl_up_sync(0xffffffffu, wm, off);
+                    if (lane >= off) { wm = fmin(pm, ps + wm); ws = ps + ws; }
+                }
+                double xs = __shfl_up_sync(0xffffffffu, ws, 1), xm = __shfl_up_sync(0xffffffffu, wm, 1);
+                if (lane == 0) { xs = 0.0; xm = 0.0; }
+                if (lane < RHO_NT / 32) { s_pre_s[lane] = xs; s_pre_m[lane] = xm; }
+            }
+            __syncthreads();
+            const double bs = s_pre_s[wid], bm = s_pre_m[wid];           // everything before this warp
             // exclusive prefix of this thread = (before the warp) . (inclusive of the previous lane)
             double es = __shfl_up_sync(0xffffffffu, ss, 1), em = __shfl_up_sync(0xffffffffu, mm, 1);
             if (lane == 0) { es = 0.0; em = 0.0; }
@@ -637,12 +648,29 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
             // merge of the tested prefix into the current inlier buffer happens below, once Ntested is known
         }
         __syncthreads();
+        // ---- the evaluation overwrote the inlier flags of the points it tested only: merge the tested prefix into the current
+        // buffer and count its inliers, one word per thread (unless the sequential fallback has to find the exit first)
+        const bool fallback = s_unc < s_cert;
+        if (!fallback) {
+            const int Nt = s_cert != 0x7fffffff ? s_cert + 1 : N;
+            const int full = Nt >> 5, rem = Nt & 31;
+            unsigned *cw = s_curw ? s_buf1 : s_buf0;
+            int c = 0;
+            if (tid < full) { const unsigned b = s_new[tid]; cw[tid] = b; c = __popc(b); }
+            else if (tid == full && rem) { const unsigned msk = (1u << rem) - 1u, b = s_new[full] & msk; cw[full] = (cw[full] & ~msk) | b; c = __popc(b); }
+            if (tid < ((nwords + 31) & ~31)) {       // whole warps
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0 && c) atomicAdd(&s_cnt, c);
+            }
+            __syncthreads();
+        }
         if (tid == 0) {
             { const long long t_ = clock64(); clk_b += t_ - clk_x; clk_x = t_; }
             ++n_models;
             int Ntested = N;
             bool good = true;
-            if (s_unc < s_cert) {
+            unsigned numInl_c = 0;
+            if (fallback) {
                 // fallback: the library's sequential FP64 product
                 ++dbg_replay;
                 double lam = 1.0;
@@ -650,11 +678,6 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                     lam *= ((s_new[i >> 5] >> (i & 31)) & 1u) ? lamAcc : lamRej;
                     if (!(lam <= A)) { good = false; Ntested = i + 1; break; }
                 }
-            } else if (s_cert != 0x7fffffff) { good = false; Ntested = s_cert + 1; }
-            { const long long t_ = clock64(); clk_c += t_ - clk_x; clk_x = t_; }
-            // the evaluation overwrote the inlier flags of the points it tested only
-            unsigned numInl_c = 0;
-            {
                 const int full = Ntested >> 5, rem = Ntested & 31;
                 for (int q = 0; q < full; q++) { const unsigned b = s_new[q]; cur[q] = b; numInl_c += __popc(b); }
                 if (rem) {
@@ -662,7 +685,11 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                     cur[full] = (cur[full] & ~msk) | b;
                     numInl_c += __popc(b);
                 }
+            } else {
+                if (s_cert != 0x7fffffff) { good = false; Ntested = s_cert + 1; }
+                numInl_c = (unsigned)s_cnt;
             }
+            { const long long t_ = clock64(); clk_c += t_ - clk_x; clk_x = t_; }
             // updateSPRT
             if (good) {
                 if (numInl_c > numInl_b) {
@@ -688,6 +715,7 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
             if (numInl_c > numInl_b) {      // saveBestModel, updateBounds, nStarOptimize
                 for (int q = 0; q < 9; q++) Hb[q] = s_H[q];
                 unsigned *t = cur; cur = best; best = t;
+                s_curw = cur == s_buf1 ? 1 : 0;
                 numInl_b = numInl_c;
                 maxI = rho_iter_bound(0.995, (double)numInl_b / N, maxI);
                 s_nstar = 1; s_ns_which = best == s_buf1 ? 1 : 0;      // nStarOptimize runs CTA-wide at the top of the next iteration
