@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(1024) k_sample_pairs(const float2 *__restrict_
 //     per accumulator over per-point products staged in shared memory), because float addition is order dependent.
 #define RHO_NT 512
 #define RHO_TILE2 256            // inliers per product tile of the refinement (two tiles: double buffered)
+#define RHO_NE (RHO_NT - 32)     // threads that evaluate a model (warps 1 .. 15); warp 0 holds the control thread
 #define RHO_ACC 36               // the 27 entries of JtJ the library updates (lower triangle without the zero block), 8 of Jte, S
 #define RHO_WORDS (HG_MAX_SAMPLES / 32)
 #define RHO_SMEM (sizeof(float2) * 2 * HG_MAX_SAMPLES + sizeof(unsigned short) * (2 * HG_MAX_SAMPLES + 8) + sizeof(unsigned) * 3 * RHO_WORDS + \
@@ -404,6 +405,8 @@ __device__ void rho_tri_solve8(const float (*L)[8], const float *Jte, float *dH)
 __constant__ signed char c_rho_acc_r[27] = {0, 1, 1, 2, 2, 2, 3, 4, 4, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7};
 __constant__ signed char c_rho_acc_c[27] = {0, 0, 1, 0, 1, 2, 3, 3, 4, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 7};
 
+__device__ __forceinline__ void rho_ebar() { asm volatile("bar.sync 1, %0;" ::"n"(RHO_NE) : "memory"); }    // barrier of the evaluating warps
+
 __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src, const float2 *__restrict__ g_dst, const int *__restrict__ n_ptr,
                                                double *__restrict__ H_out, int *__restrict__ info_out, unsigned char *__restrict__ mask_out)
 {
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
     unsigned short *s_idx = s_tbl + HG_MAX_SAMPLES + 8;                      // inlier indexes of the best model, ascending
     unsigned *s_new = (unsigned *)(s_idx + HG_MAX_SAMPLES), *s_buf0 = s_new + RHO_WORDS, *s_buf1 = s_buf0 + RHO_WORDS;
     float *s_prod = (float *)(s_buf1 + RHO_WORDS);                           // 2 x RHO_ACC x (RHO_TILE2 + 1)
-    __shared__ float s_H[9], s_acc[RHO_ACC];
+    __shared__ float s_H[9], s_Hn[9], s_acc[RHO_ACC];
     __shared__ int s_go, s_ninl_list, s_warp_cnt[RHO_WORDS], s_tot_inl, s_nstar, s_ns_which, s_ns_stop, s_cert, s_unc, s_curw, s_cnt;
     __shared__ double s_logAcc, s_logRej, s_logA, s_scan_s[RHO_NT / 32], s_scan_m[RHO_NT / 32], s_pre_s[RHO_NT / 32], s_pre_m[RHO_NT / 32];
     __shared__ unsigned s_ns_n[RHO_NT], s_ns_i[RHO_NT], s_ns_wn[RHO_NT / 32], s_ns_wi[RHO_NT / 32], s_ns_out[2];
@@ -444,6 +447,11 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
     long long clk_loop = 0, clk_nstar = 0, clk_lm = 0, clk_t0 = clock64(), clk_a = 0, clk_b = 0, clk_c = 0, clk_d = 0, clk_x = clock64();
     float Hb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     unsigned *cur = s_buf0, *best = s_buf1;
+    RhoPrng sp_prng = prng;
+    unsigned sp_it = 0, sp_phNum = 4, sp_phEndI = 1;
+    double sp_phEndFpI = 0;
+    bool have_spec = false;
+    int spec_go = 0;
     if (tid == 0) {
         prng.s0 = ~0ull; prng.s1 = 0ull;
         for (int i = 0; i < 20; i++) rho_random(prng);
@@ -529,7 +537,33 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
             }
             __syncthreads();
         }
-        // ---- hypothesize (thread 0): PROSAC sample until a non-degenerate model or the end of the loop
+        // ---- hypothesize (thread 0): PROSAC sample until a non-degenerate model or the end of the loop.  While warps 1 .. 15
+        // evaluate model i, thread 0 already generates hypothesis i + 1 (2.5 k cycles of serial work: sampling, degeneracy
+        // tests, the 8 x 9 elimination) on a COPY of the generator state.  Nothing the generator reads changes unless model i
+        // becomes the best one (maxI, phMax); in that case the speculation is dropped and redone after the update.
+        auto generate = [&](RhoPrng &g_prng, unsigned &g_it, unsigned &g_phNum, unsigned &g_phEndI, double &g_phEndFpI, float *Hdst) -> int {
+            while (g_it < maxI || g_it < 100) {
+                if (g_it >= g_phEndI && g_phNum < phMax) {
+                    g_phNum++;
+                    const double next = (g_phEndFpI * g_phNum) / (g_phNum - 4);
+                    g_phEndI += (unsigned)ceil(next - g_phEndFpI);
+                    g_phEndFpI = next;
+                }
+                unsigned smpl[4];
+                if (g_it > g_phEndI) rho_rnd_smpl(g_prng, 4, smpl, g_phNum);
+                else { rho_rnd_smpl(g_prng, 3, smpl, g_phNum - 1); smpl[3] = g_phNum - 1; }
+                float2 k[8];
+                for (int q = 0; q < 4; q++) { k[q] = s_src[smpl[q]]; k[4 + q] = s_dst[smpl[q]]; }
+                if (rho_sample_degenerate(k)) { ++g_it; continue; }
+                float Hc[9];
+                rho_h_func(k, Hc);
+                const float f = Hc[0] + Hc[1] + Hc[2] + Hc[3] + Hc[4] + Hc[5] + Hc[6] + Hc[7];
+                if (f != f) { ++g_it; continue; }
+                for (int q = 0; q < 9; q++) Hdst[q] = Hc[q];
+                return 1;
+            }
+            return 0;
+        };
         if (tid == 0) {
             if (s_nstar) {
                 s_nstar = 0;
@@ -540,28 +574,9 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                     maxI = rho_iter_bound(0.995, (double)phNumInl / phMax, maxI);
                 }
             }
-            int go = 0;
-            while (it < maxI || it < 100) {
-                if (it >= phEndI && phNum < phMax) {
-                    phNum++;
-                    const double next = (phEndFpI * phNum) / (phNum - 4);
-                    phEndI += (unsigned)ceil(next - phEndFpI);
-                    phEndFpI = next;
-                }
-                unsigned smpl[4];
-                if (it > phEndI) rho_rnd_smpl(prng, 4, smpl, phNum);
-                else { rho_rnd_smpl(prng, 3, smpl, phNum - 1); smpl[3] = phNum - 1; }
-                float2 k[8];
-                for (int q = 0; q < 4; q++) { k[q] = s_src[smpl[q]]; k[4 + q] = s_dst[smpl[q]]; }
-                if (rho_sample_degenerate(k)) { ++it; continue; }
-                float Hc[9];
-                rho_h_func(k, Hc);
-                const float f = Hc[0] + Hc[1] + Hc[2] + Hc[3] + Hc[4] + Hc[5] + Hc[6] + Hc[7];
-                if (f != f) { ++it; continue; }
-                for (int q = 0; q < 9; q++) s_H[q] = Hc[q];
-                go = 1;
-                break;
-            }
+            int go;
+            if (have_spec) { for (int q = 0; q < 9; q++) s_H[q] = s_Hn[q]; go = spec_go; }     // accepted speculation of the last round
+            else go = generate(prng, it, phNum, phEndI, phEndFpI, s_H);
             s_go = go;
             s_tot_inl = 0; s_cert = 0x7fffffff; s_unc = 0x7fffffff; s_cnt = 0;
             s_logAcc = logAcc; s_logRej = logRej; s_logA = logA_d;
@@ -569,11 +584,18 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
         }
         __syncthreads();
         if (!s_go) break;
-        // ---- all reprojection tests of the model (evaluateModelSPRT's per-point arithmetic)
+        if (wid == 0) {
+            if (tid == 0) {      // hypothesis i + 1, speculatively (the iteration counter advances by one at the end of this round)
+                sp_prng = prng; sp_it = it + 1; sp_phNum = phNum; sp_phEndI = phEndI; sp_phEndFpI = phEndFpI;
+                spec_go = generate(sp_prng, sp_it, sp_phNum, sp_phEndI, sp_phEndFpI, s_Hn);
+            }
+        } else {
+        // ---- warps 1 .. 15 (RHO_NE threads, barrier 1): all reprojection tests of the model (evaluateModelSPRT's per-point arithmetic)
+        const int et = tid - 32, ew = wid - 1;
         {
             const float h0 = s_H[0], h1 = s_H[1], h2 = s_H[2], h3 = s_H[3], h4 = s_H[4], h5 = s_H[5], h6 = s_H[6], h7 = s_H[7];
-            for (int base = 0; base < nwords * 32; base += RHO_NT) {
-                const int i = base + tid;
+            for (int base = 0; base < nwords * 32; base += RHO_NE) {
+                const int i = base + et;
                 bool inl = false;
                 if (i < N) {
                     const float x = s_src[i].x, y = s_src[i].y, X = s_dst[i].x, Y = s_dst[i].y;
@@ -589,7 +611,7 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                 if (lane == 0 && (i >> 5) < RHO_WORDS) { s_new[i >> 5] = m; if (m) atomicAdd(&s_tot_inl, __popc(m)); }
             }
         }
-        __syncthreads();
+        rho_ebar();
         // ---- SPRT: the first point at which lambda = prod(accept / reject factors) exceeds A (evaluateModelSPRT stops there).
         // The library multiplies sequentially in FP64; a dependent FP64 chain over up to 3000 points costs ~0.1 ms per model
         // on this part, so the decision is taken in the log domain, in parallel: S_i = FP64 prefix sum of the log factors
@@ -599,8 +621,8 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
         // dip.  Only if a point inside the band (or a recovery from a dip) comes before the first certain exit -- never
         // observed -- thread 0 falls back to the library's sequential product.
         {
-            const int CH = (N + RHO_NT - 1) / RHO_NT;                    // consecutive points per thread
-            const int i0 = min(tid * CH, N), i1 = min(i0 + CH, N);
+            const int CH = (N + RHO_NE - 1) / RHO_NE;                    // consecutive points per thread
+            const int i0 = min(et * CH, N), i1 = min(i0 + CH, N);
             double loc = 0.0, locmin = 0.0;                              // chunk sum, minimum prefix inside the chunk (0 = empty prefix)
             for (int i = i0; i < i1; ++i) {
                 loc += ((s_new[i >> 5] >> (i & 31)) & 1u) ? s_logAcc : s_logRej;
@@ -613,21 +635,21 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                 const double ps = __shfl_up_sync(0xffffffffu, ss, off), pm = __shfl_up_sync(0xffffffffu, mm, off);
                 if (lane >= off) { mm = fmin(pm, ps + mm); ss = ps + ss; }
             }
-            if (lane == 31) { s_scan_s[wid] = ss; s_scan_m[wid] = mm; }
-            __syncthreads();
-            if (wid == 0) {     // exclusive scan of the RHO_NT / 32 warp totals with the same operator (one warp, four shuffle steps)
-                double ws = lane < RHO_NT / 32 ? s_scan_s[lane] : 0.0, wm = lane < RHO_NT / 32 ? s_scan_m[lane] : 0.0;
+            if (lane == 31) { s_scan_s[ew] = ss; s_scan_m[ew] = mm; }
+            rho_ebar();
+            if (ew == 0) {     // exclusive scan of the RHO_NE / 32 warp totals with the same operator (one warp, four shuffle steps)
+                double ws = lane < RHO_NE / 32 ? s_scan_s[lane] : 0.0, wm = lane < RHO_NE / 32 ? s_scan_m[lane] : 0.0;
 #pragma unroll
-                for (int off = 1; off < RHO_NT / 32; off <<= 1) {
+                for (int off = 1; off < 16; off <<= 1) {
                     const double ps = __shfl_up_sync(0xffffffffu, ws, off), pm = __shfl_up_sync(0xffffffffu, wm, off);
                     if (lane >= off) { wm = fmin(pm, ps + wm); ws = ps + ws; }
                 }
                 double xs = __shfl_up_sync(0xffffffffu, ws, 1), xm = __shfl_up_sync(0xffffffffu, wm, 1);
                 if (lane == 0) { xs = 0.0; xm = 0.0; }
-                if (lane < RHO_NT / 32) { s_pre_s[lane] = xs; s_pre_m[lane] = xm; }
+                if (lane < RHO_NE / 32) { s_pre_s[lane] = xs; s_pre_m[lane] = xm; }
             }
-            __syncthreads();
-            const double bs = s_pre_s[wid], bm = s_pre_m[wid];           // everything before this warp
+            rho_ebar();
+            const double bs = s_pre_s[ew], bm = s_pre_m[ew];             // everything before this warp
             // exclusive prefix of this thread = (before the warp) . (inclusive of the previous lane)
             double es = __shfl_up_sync(0xffffffffu, ss, 1), em = __shfl_up_sync(0xffffffffu, mm, 1);
             if (lane == 0) { es = 0.0; em = 0.0; }
@@ -645,25 +667,25 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
             }
             if (cert != 0x7fffffff) atomicMin(&s_cert, cert);
             if (unc != 0x7fffffff) atomicMin(&s_unc, unc);
-            // merge of the tested prefix into the current inlier buffer happens below, once Ntested is known
         }
-        __syncthreads();
+        rho_ebar();
         // ---- the evaluation overwrote the inlier flags of the points it tested only: merge the tested prefix into the current
         // buffer and count its inliers, one word per thread (unless the sequential fallback has to find the exit first)
-        const bool fallback = s_unc < s_cert;
-        if (!fallback) {
+        if (!(s_unc < s_cert)) {
             const int Nt = s_cert != 0x7fffffff ? s_cert + 1 : N;
             const int full = Nt >> 5, rem = Nt & 31;
             unsigned *cw = s_curw ? s_buf1 : s_buf0;
             int c = 0;
-            if (tid < full) { const unsigned b = s_new[tid]; cw[tid] = b; c = __popc(b); }
-            else if (tid == full && rem) { const unsigned msk = (1u << rem) - 1u, b = s_new[full] & msk; cw[full] = (cw[full] & ~msk) | b; c = __popc(b); }
-            if (tid < ((nwords + 31) & ~31)) {       // whole warps
+            if (et < full) { const unsigned b = s_new[et]; cw[et] = b; c = __popc(b); }
+            else if (et == full && rem) { const unsigned msk = (1u << rem) - 1u, b = s_new[full] & msk; cw[full] = (cw[full] & ~msk) | b; c = __popc(b); }
+            if (et < ((nwords + 31) & ~31)) {       // whole warps
                 c = __reduce_add_sync(0xffffffffu, c);
                 if (lane == 0 && c) atomicAdd(&s_cnt, c);
             }
-            __syncthreads();
         }
+        }
+        __syncthreads();
+        const bool fallback = s_unc < s_cert;
         if (tid == 0) {
             { const long long t_ = clock64(); clk_b += t_ - clk_x; clk_x = t_; }
             ++n_models;
@@ -721,6 +743,9 @@ __global__ void __launch_bounds__(RHO_NT) k_rho(const float2 *__restrict__ g_src
                 s_nstar = 1; s_ns_which = best == s_buf1 ? 1 : 0;      // nStarOptimize runs CTA-wide at the top of the next iteration
             }
             ++it;
+            // the speculated hypothesis i + 1 stands unless this model changed what the generator reads (maxI here, phMax after nStarOptimize)
+            have_spec = !s_nstar;
+            if (have_spec) { prng = sp_prng; it = sp_it; phNum = sp_phNum; phEndI = sp_phEndI; phEndFpI = sp_phEndFpI; }
             { const long long t_ = clock64(); clk_d += t_ - clk_x; clk_x = t_; }
         }
     }
