@@ -22,14 +22,14 @@ struct FramePipe {
     VarRefStage varref1;
     float *fb_mag1 = nullptr, *flow_small1 = nullptr;
     unsigned int *fb_hist1 = nullptr;
-    cudaStream_t sp[2] = {nullptr, nullptr};        // plane fitter of even / odd frames (2.6 ms each: two frames' fitters overlap)
+    cudaStream_t sp[PIPE_NB] = {};                  // gradient edges + plane fitter of frame k (2.9 ms each, more under load: up to four frames' fitters overlap)
     // buffers a later frame's image-only stages overwrite while an earlier frame still reads them: ring of PIPE_NB, k = frame % PIPE_NB
     float *flow_full[PIPE_NB] = {};
     int *fb_flag[PIPE_NB] = {}, *fb_flag_host[PIPE_NB] = {};
     uint16_t *depth[PIPE_NB] = {};
     uint8_t *plane_edges[PIPE_NB] = {};
-    PeacStage peac[2];
-    ReclusterStage rc_peac[2];
+    PeacStage peac[PIPE_NB];
+    ReclusterStage rc_peac[PIPE_NB];
     // the decision's own CCL scratch and two label images: the clustering of frame i + 1 (warm-started by frame i's labels) no
     // longer has to wait for the decision of frame i, which reads those labels and used to share the re-clustering's scratch
     uint8_t *dd_cls = nullptr; int *dd_labels = nullptr, *dd_top = nullptr; RegionStats *dd_stats = nullptr;
@@ -45,7 +45,7 @@ struct FramePipe {
     unsigned long long frame_no = 0;
     bool fresh = true;                              // the pipeline's streams have to wait for the handle's stream first
     int last_slot = 0, last_k = 0;
-    int hdr_host[2][4] = {};
+    int hdr_host[PIPE_NB][4] = {};
     uint8_t *in_bgr[2] = {nullptr, nullptr};        // pinned bounce buffers for pageable host inputs (asynchronous submit)
     uint16_t *in_depth[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[2] = {};
@@ -84,7 +84,7 @@ static int pipe_init(sindyn_ctx *c)
         SD_CHECK(c->dalloc(&P->flow_small1, (size_t)c->fw * c->fh * 2));
     }
     P->sp[0] = c->stream3;
-    CU_CHECK(c, cudaStreamCreateWithFlags(&P->sp[1], cudaStreamNonBlocking));
+    for (int k = 1; k < PIPE_NB; ++k) CU_CHECK(c, cudaStreamCreateWithFlags(&P->sp[k], cudaStreamNonBlocking));
     P->own_flow_full = c->flow_full; P->own_fb_flag = c->fb_flag; P->own_fb_flag_host = c->fb_flag_host; P->own_depth = c->depth; P->own_plane_edges = c->plane_edges;
     P->flow_full[0] = c->flow_full; P->fb_flag[0] = c->fb_flag; P->fb_flag_host[0] = c->fb_flag_host; P->depth[0] = c->depth; P->plane_edges[0] = c->plane_edges;
     {
@@ -114,13 +114,12 @@ static int pipe_init(sindyn_ctx *c)
         CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_done[k], cudaEventDisableTiming));
         CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_e[k], cudaEventDisableTiming));
     }
-    for (int p = 0; p < 2; ++p) {
+    for (int k = 0; k < PIPE_NB; ++k)
         if (c->cfg.plane_edges) {
-            SD_CHECK(peac_init(c, &P->peac[p], c->W, c->H));
-            SD_CHECK(recluster_init(c, &P->rc_peac[p], c->W, c->H));
+            SD_CHECK(peac_init(c, &P->peac[k], c->W, c->H));
+            SD_CHECK(recluster_init(c, &P->rc_peac[k], c->W, c->H));
         }
-        CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_h2d[p], cudaEventDisableTiming));
-    }
+    for (int p = 0; p < 2; ++p) CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_h2d[p], cudaEventDisableTiming));
     for (int k = 0; k < 4; ++k) CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_gray[k], cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&P->ev_ddout, cudaEventDisableTiming));
@@ -143,7 +142,7 @@ void pipe_destroy(sindyn_ctx *c)
     cudaEventDestroy(P->ev_join); cudaEventDestroy(P->ev_sync); cudaEventDestroy(P->ev_ddout);
     if (P->sa[0]) cudaStreamDestroy(P->sa[0]);
     if (P->sa[1]) cudaStreamDestroy(P->sa[1]);
-    if (P->sp[1]) cudaStreamDestroy(P->sp[1]);
+    for (int k = 1; k < PIPE_NB; ++k) if (P->sp[k]) cudaStreamDestroy(P->sp[k]);
     delete P;
     c->pipe = nullptr;
 }
@@ -158,7 +157,8 @@ int pipe_join(sindyn_ctx *c)
 {
     FramePipe *P = c->pipe;
     if (!P) return SINDYN_OK;
-    cudaStream_t ss[5] = {P->sa[0], P->sa[1], c->stream2, P->sp[0], P->sp[1]};
+    cudaStream_t ss[3 + PIPE_NB] = {P->sa[0], P->sa[1], c->stream2};
+    for (int k = 0; k < PIPE_NB; ++k) ss[3 + k] = P->sp[k];
     for (cudaStream_t s : ss) {
         CU_CHECK(c, cudaEventRecord(P->ev_sync, s));
         CU_CHECK(c, cudaStreamWaitEvent(c->stream, P->ev_sync, 0));
@@ -200,7 +200,7 @@ int pipe_copy_headers(sindyn_ctx *c)
 {
     FramePipe *P = c->pipe;
     if (!P || !c->cfg.plane_edges) return SINDYN_OK;
-    for (int p = 0; p < 2; ++p)
+    for (int p = 0; p < PIPE_NB; ++p)
         if (P->peac[p].built) SD_CHECK(peac_copy_sticky_overflow(c, &P->peac[p], &P->hdr_host[p][2]));
     return SINDYN_OK;
 }
@@ -208,7 +208,10 @@ int pipe_copy_headers(sindyn_ctx *c)
 bool pipe_overflow(const sindyn_ctx *c)
 {
     const FramePipe *P = c->pipe;
-    return P && (P->hdr_host[0][2] || P->hdr_host[1][2]);
+    if (!P) return false;
+    for (int p = 0; p < PIPE_NB; ++p)
+        if (P->hdr_host[p][2]) return true;
+    return false;
 }
 
 // capture fn() on stream s into an executable graph
@@ -249,8 +252,7 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
         CU_CHECK(c, cudaStreamWaitEvent(P->sa[0], P->ev_sync, 0));
         CU_CHECK(c, cudaStreamWaitEvent(P->sa[1], P->ev_sync, 0));
         CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_sync, 0));
-        CU_CHECK(c, cudaStreamWaitEvent(P->sp[0], P->ev_sync, 0));
-        CU_CHECK(c, cudaStreamWaitEvent(P->sp[1], P->ev_sync, 0));
+        for (int q = 0; q < PIPE_NB; ++q) CU_CHECK(c, cudaStreamWaitEvent(P->sp[q], P->ev_sync, 0));
         P->fresh = false;
     }
     c->flow_full = P->flow_full[k]; c->fb_flag = P->fb_flag[k]; c->fb_flag_host = P->fb_flag_host[k]; c->depth = P->depth[k]; c->plane_edges = P->plane_edges[k];
@@ -284,9 +286,9 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     c->stream = main_s;
     SD_CHECK(st);
     CU_CHECK(c, cudaEventRecord(P->ev_a[k], sa));
-    // ---- stream 3 of this parity: gradient edges, then the plane fitter (both depth only)
+    // ---- this ring position's depth stream: gradient edges, then the plane fitter (both depth only)
     {
-        cudaStream_t s3 = P->sp[p];
+        cudaStream_t s3 = P->sp[k];
         CU_CHECK(c, cudaStreamWaitEvent(s3, P->ev_in[k], 0));
         if (!P->g_e[k]) SD_CHECK(pipe_capture(c, s3, &P->g_e[k], &P->n_e[k], [&]() { return edges_run(c, &c->edges, c->depth, c->cfg.depth_scale); }));
         CU_CHECK(c, cudaGraphLaunch(P->g_e[k], s3));
@@ -294,10 +296,10 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
         CU_CHECK(c, cudaEventRecord(P->ev_e[k], s3));
     }
     if (c->cfg.plane_edges) {
-        cudaStream_t s3 = P->sp[p];
+        cudaStream_t s3 = P->sp[k];
         if (!P->g_p[k])
             SD_CHECK(pipe_capture(c, s3, &P->g_p[k], &P->n_p[k], [&]() {
-                return peac_run(c, &P->peac[p], &P->rc_peac[p], c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges);
+                return peac_run(c, &P->peac[k], &P->rc_peac[k], c->depth, c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy, c->cfg.depth_scale, c->plane_edges);
             }));
         CU_CHECK(c, cudaGraphLaunch(P->g_p[k], s3));
         c->launches += P->n_p[k];
@@ -336,7 +338,7 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     if (flags) {
         CU_CHECK(c, cudaMemcpyAsync(flags->edge_scalars, c->edges.scalars, sizeof(int) * 4, cudaMemcpyDeviceToHost, main_s));
         flags->peac_hdr[0] = flags->peac_hdr[1] = flags->peac_hdr[2] = flags->peac_hdr[3] = 0;
-        if (c->cfg.plane_edges) SD_CHECK(peac_copy_sticky_overflow(c, &P->peac[p], &flags->peac_hdr[2]));
+        if (c->cfg.plane_edges) SD_CHECK(peac_copy_sticky_overflow(c, &P->peac[k], &flags->peac_hdr[2]));
     }
     CU_CHECK(c, cudaEventRecord(P->ev_done[k], main_s));
     P->last_slot = slot; P->last_k = k;
