@@ -19,10 +19,14 @@ frame jump is introduced.  value = pairs/s = frames / time.
 
 value    : frames resident in HBM (device slots, 300 x 1.5 MB = 460 MB per sequence, larger than the 126 MB L2 and each
            read once per pass; a 256 MiB flush is written between steps as well), one call sindyn_track_frame_resident per
-           frame, CUDA events on the handle's stream around every step, summed; max over ranks.
-e2e      : the same frames through the host C-ABI call sindyn_track_frame (what the C++ classes of
-           include/sindyn_classes.hpp call) with pinned HOST buffers: H2D of the BGR + depth frame and D2H of the dilated
-           mask, the label image, the key points and the descriptors inside the timed region.
+           frame (frame pipeline: the image-only stages of the next frames overlap the decision of the current one, so a
+           step boundary is not a synchronisation point), one pair of CUDA events on the handle's stream around the K
+           steps, the end event after a join of all the pipeline's streams; max over ranks.
+e2e      : the same frames through the host C-ABI pair sindyn_track_submit / sindyn_track_collect with pinned HOST buffers
+           (frame i + 2 is submitted before frame i is collected): H2D of the BGR + depth frame and D2H of the dilated
+           mask, the label image, the key points and the descriptors inside the timed region.  e2e.frame_at_a_time: the
+           same through sindyn_track_frame (what the C++ classes of include/sindyn_classes.hpp call), which returns a
+           frame's results before it accepts the next frame.
 roofline : the dominant kernel, k_brox_sor (temporally blocked red-black SOR), timed per launch with CUDA events on the
            handle's stream (sindyn_brox_profile); algorithmic bytes = 52 B per pixel and sweep.
 roofline_per_stage: SURVEY.md 8(d) algorithmic bytes of every stage / its device ms / the measured HBM peak.
@@ -455,16 +459,20 @@ def run_ours(args):
 
     # ---------------- device-resident throughput (value)
     def run_steps_resident(sd, orb, stream, s0, s1, ev):
+        # ev: one (start, end) event pair around ALL the steps.  The frame pipeline keeps several frames in flight on its own
+        # streams, so a step boundary is not a synchronisation point: the L2 flush of a step is enqueued on the handle's stream
+        # next to the frames (it evicts the lines as intended and its 40 us are inside the timed region), the end event follows
+        # a join of all the pipeline's streams.
+        if ev is not None:
+            ev[0].record(stream)
         for s in range(s0, s1):
             with torch.cuda.stream(stream):
                 flush.fill_(s & 255)
-            if ev is not None:
-                ev[s - s0][0].record(stream)
             for j in range(FRAMES_PER_STEP):
                 orb.track_frame_resident(sd, order[s * FRAMES_PER_STEP + j], s * FRAMES_PER_STEP + j)
-            orb.track_join(sd)      # the step's frames run on several streams (frame pipeline): the end event covers all of them
-            if ev is not None:
-                ev[s - s0][1].record(stream)
+        orb.track_join(sd)
+        if ev is not None:
+            ev[1].record(stream)
 
     def over_handles(fn):
         if len(handles) == 1:
@@ -479,16 +487,16 @@ def run_ours(args):
     over_handles(lambda h: run_steps_resident(h[0], h[1], h[2], 0, args.warmup, None))
     barrier()
     l0 = sum(h[0].launches + h[1].launches for h in handles)
-    evs = {id(h[0]): [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)] for h in handles}
+    evs = {id(h[0]): (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for h in handles}
     t_host0 = time.perf_counter()
     over_handles(lambda h: run_steps_resident(h[0], h[1], h[2], args.warmup, total_steps, evs[id(h[0])]))
     barrier()
     t_host1 = time.perf_counter()
     gpu_launches = sum(h[0].launches + h[1].launches for h in handles) - l0
-    # one sequence: summed per-step event times (flush excluded); several concurrent sequences on one GPU: the wall time of
-    # the region (events of different streams overlap)
+    # one sequence: device time of the K steps between two events on the handle's stream; several concurrent sequences on one
+    # GPU: the wall time of the region (events of different streams overlap)
     if len(handles) == 1:
-        dev_ms = sum(a.elapsed_time(b) for a, b in evs[id(handles[0][0])])
+        dev_ms = evs[id(handles[0][0])][0].elapsed_time(evs[id(handles[0][0])][1])
     else:
         dev_ms = (t_host1 - t_host0) * 1e3
     for h in handles:   # surface capacity errors of the resident path

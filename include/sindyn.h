@@ -270,7 +270,7 @@ int sindyn_track_frame_resident(sindyn_handle h, sindyn_orb_handle o, int slot, 
  * gray / resize, Brox flow, refinement, PEAC plane fitter, the unmasked half of the extractor -- overlap the decision of frame
  * i, the software pipeline of pipe.cu; the reference's driver loop, rgbd_tum_noros.cc:113-192, hands over one frame after the
  * other and nothing in those stages reads the detector's state).  After sindyn_track_join everything enqueued so far precedes
- * the next operation on the detector handle's stream. */
+ * the next operation on the detector handle's stream, and the next frame follows whatever that stream holds by then. */
 int sindyn_track_join(sindyn_handle h, sindyn_orb_handle o);
 /* Asynchronous form of sindyn_track_frame for a caller that has the next image at hand while it still works on the current one
  * (rgbd_tum_noros.cc:113-192 reads a recorded sequence; Tracking::GrabImageRGBD, Tracking.cc:209-240, needs mask + key points of

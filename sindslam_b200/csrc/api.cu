@@ -131,6 +131,7 @@ extern "C" int sindyn_set_stream(sindyn_handle h, void *s)
 extern "C" int sindyn_synchronize(sindyn_handle h)
 {
     H_CHECK(h);
+    SD_CHECK(pipe_join(h));      // frames in the frame pipeline run on further streams
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     return SINDYN_OK;
 }
@@ -245,6 +246,7 @@ extern "C" int sindyn_get_state(sindyn_handle h, int which, uint8_t *out)
     case 4: src = h->bgr[h->i_lastlast]; nb *= 3; break;
     default: return SINDYN_ERR_INVALID;
     }
+    SD_CHECK(pipe_join(h));
     CU_CHECK(h, cudaMemcpyAsync(out, src, nb, cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     return SINDYN_OK;

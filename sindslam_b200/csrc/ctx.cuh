@@ -124,6 +124,7 @@ void pipe_destroy(sindyn_ctx *c);                          // pipe.cu
 bool pipe_usable(const sindyn_ctx *c);                     // pipe.cu: graphs on, no stage timing
 int pipe_copy_headers(sindyn_ctx *c);                      // pipe.cu: asynchronous copy of the plane-fitter headers of both pipeline instances
 bool pipe_overflow(const sindyn_ctx *c);                   // pipe.cu: ... and their overflow flags, valid after the stream was synchronised
+cudaStream_t pipe_chain_stream(sindyn_ctx *c);             // pipe.cu: the stream the state chain (part B, decision, state roll) runs on
 cudaEvent_t pipe_done_event(sindyn_ctx *c);                // pipe.cu: the last frame is decided (final mask, labels, rolled state)
 int pipe_note_mask_read(sindyn_ctx *c, cudaStream_t s);    // pipe.cu: stream s has read the last frame's final mask
 cudaEvent_t pipe_input_event(sindyn_ctx *c);               // pipe.cu: the last frame's inputs are in place (bgr ring slot, depth)

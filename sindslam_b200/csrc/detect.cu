@@ -67,6 +67,7 @@ static int check_capacity(sindyn_ctx *c)
 {
     ReclusterControl ctl;
     int sc[4];
+    SD_CHECK(pipe_join(c));      // frames of the frame pipeline finish first (their decision runs on the pipeline's own stream)
     CU_CHECK(c, cudaMemcpyAsync(&ctl, c->rc.ctl, sizeof ctl, cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaMemcpyAsync(sc, c->edges.scalars, sizeof sc, cudaMemcpyDeviceToHost, c->stream));
     int peac_hdr[4] = {0, 0, 0, 0};

@@ -1030,8 +1030,8 @@ extern "C" int sindyn_track_submit(sindyn_handle h, sindyn_orb_handle o, const u
     SD_CHECK(track_enqueue_pipe(h, o, bgr, bgr_step, depth, depth_step, true, t->r_flags[p], rgb_order, dilate_k));
     // results into this slot's pinned buffers: the labels on the detector's stream (from the rolled state: a later frame's
     // re-clustering may already overwrite rc.label_out), the dilated mask and the key points on the extractor's
-    CU_CHECK(h, cudaMemcpyAsync(t->r_label[p], h->label_last, h->N, cudaMemcpyDeviceToHost, h->stream));
-    CU_CHECK(h, cudaEventRecord(t->ev_res_main[p], h->stream));
+    CU_CHECK(h, cudaMemcpyAsync(t->r_label[p], h->label_last, h->N, cudaMemcpyDeviceToHost, pipe_chain_stream(h)));   // (before the next frame's state roll)
+    CU_CHECK(h, cudaEventRecord(t->ev_res_main[p], pipe_chain_stream(h)));
     CU_CHECK(o, cudaMemcpyAsync(t->r_mask[p], o->mask, h->N, cudaMemcpyDeviceToHost, o->stream));
     CU_CHECK(o, cudaMemcpyAsync(t->r_ctl[p], o->ctl, sizeof(OrbControl), cudaMemcpyDeviceToHost, o->stream));
     CU_CHECK(o, cudaMemcpyAsync(t->r_kp[p], o->out_host_fmt, sizeof(sindyn_keypoint) * t->r_cap, cudaMemcpyDeviceToHost, o->stream));

@@ -22,6 +22,8 @@ struct FramePipe {
     VarRefStage varref1;
     float *fb_mag1 = nullptr, *flow_small1 = nullptr;
     unsigned int *fb_hist1 = nullptr;
+    cudaStream_t sc = nullptr;                      // the state chain (part B, decision, state roll): highest priority, its ~30 kernels are
+                                                    // what bounds the frame rate and must not queue behind a wave of flow-solve CTAs
     cudaStream_t sp[PIPE_NB] = {};                  // gradient edges + plane fitter of frame k (2.9 ms each, more under load: up to four frames' fitters overlap)
     // buffers a later frame's image-only stages overwrite while an earlier frame still reads them: ring of PIPE_NB, k = frame % PIPE_NB
     float *flow_full[PIPE_NB] = {};
@@ -83,6 +85,11 @@ static int pipe_init(sindyn_ctx *c)
         SD_CHECK(c->dalloc(&P->fb_hist1, 260));
         SD_CHECK(c->dalloc(&P->flow_small1, (size_t)c->fw * c->fh * 2));
     }
+    {
+        int lo = 0, hi = 0;
+        CU_CHECK(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU_CHECK(c, cudaStreamCreateWithPriority(&P->sc, cudaStreamNonBlocking, hi));
+    }
     P->sp[0] = c->stream3;
     for (int k = 1; k < PIPE_NB; ++k) CU_CHECK(c, cudaStreamCreateWithFlags(&P->sp[k], cudaStreamNonBlocking));
     P->own_flow_full = c->flow_full; P->own_fb_flag = c->fb_flag; P->own_fb_flag_host = c->fb_flag_host; P->own_depth = c->depth; P->own_plane_edges = c->plane_edges;
@@ -143,6 +150,7 @@ void pipe_destroy(sindyn_ctx *c)
     if (P->sa[0]) cudaStreamDestroy(P->sa[0]);
     if (P->sa[1]) cudaStreamDestroy(P->sa[1]);
     for (int k = 1; k < PIPE_NB; ++k) if (P->sp[k]) cudaStreamDestroy(P->sp[k]);
+    if (P->sc) cudaStreamDestroy(P->sc);
     delete P;
     c->pipe = nullptr;
 }
@@ -157,12 +165,13 @@ int pipe_join(sindyn_ctx *c)
 {
     FramePipe *P = c->pipe;
     if (!P) return SINDYN_OK;
-    cudaStream_t ss[3 + PIPE_NB] = {P->sa[0], P->sa[1], c->stream2};
-    for (int k = 0; k < PIPE_NB; ++k) ss[3 + k] = P->sp[k];
+    cudaStream_t ss[4 + PIPE_NB] = {P->sa[0], P->sa[1], c->stream2, P->sc};
+    for (int k = 0; k < PIPE_NB; ++k) ss[4 + k] = P->sp[k];
     for (cudaStream_t s : ss) {
         CU_CHECK(c, cudaEventRecord(P->ev_sync, s));
         CU_CHECK(c, cudaStreamWaitEvent(c->stream, P->ev_sync, 0));
     }
+    P->fresh = true;     // ... and the pipeline's next frame follows whatever the handle's stream holds by then (a join is two-way)
     return SINDYN_OK;
 }
 
@@ -174,6 +183,7 @@ FlowRes pipe_flow_res(sindyn_ctx *c, int k)     // k = frame % PIPE_NB: output b
 }
 
 cudaEvent_t pipe_input_event(sindyn_ctx *c) { return c->pipe ? c->pipe->ev_in[c->pipe->last_k] : nullptr; }
+cudaStream_t pipe_chain_stream(sindyn_ctx *c) { return c->pipe ? c->pipe->sc : c->stream; }
 cudaEvent_t pipe_done_event(sindyn_ctx *c) { return c->pipe ? c->pipe->ev_done[c->pipe->last_k] : nullptr; }
 
 // the caller dilates / copies the last frame's final mask (dd.out) on another stream: the next decision overwrites it only after that
@@ -243,12 +253,13 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     if (!c->have_prev) { c->err = "detect: call sindyn_set_prev_frames first"; return SINDYN_ERR_STATE; }
     SD_CHECK(pipe_init(c));
     FramePipe *P = c->pipe;
-    cudaStream_t main_s = c->stream, s2 = c->stream2;
-    if (P->built_for != main_s) { pipe_drop_graphs(P); P->built_for = main_s; }
+    cudaStream_t user_s = c->stream, main_s = P->sc, s2 = c->stream2;   // main_s: where the state chain runs
+    if (P->built_for != user_s) { pipe_drop_graphs(P); P->built_for = user_s; }
     const int k = (int)(P->frame_no % PIPE_NB), p = k & 1, slot = c->i_cur;    // buffers k, solver / fitter instance and streams p
     if (P->fresh) {   // whatever the handle's stream has done so far (state set by the caller, frames of the other path) comes first
-        CU_CHECK(c, cudaMemcpyAsync(P->label_out[p ^ 1], c->label_last, c->N, cudaMemcpyDeviceToDevice, main_s));   // the warm start of this frame's k-means
-        CU_CHECK(c, cudaEventRecord(P->ev_sync, main_s));
+        CU_CHECK(c, cudaMemcpyAsync(P->label_out[p ^ 1], c->label_last, c->N, cudaMemcpyDeviceToDevice, user_s));   // the warm start of this frame's k-means
+        CU_CHECK(c, cudaEventRecord(P->ev_sync, user_s));
+        CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_sync, 0));
         CU_CHECK(c, cudaStreamWaitEvent(P->sa[0], P->ev_sync, 0));
         CU_CHECK(c, cudaStreamWaitEvent(P->sa[1], P->ev_sync, 0));
         CU_CHECK(c, cudaStreamWaitEvent(s2, P->ev_sync, 0));
@@ -283,7 +294,7 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     c->stream = sa;
     int st = sindyn_prep_frame(c, slot);
     if (st == SINDYN_OK) st = flow_part_a(c, k);
-    c->stream = main_s;
+    c->stream = user_s;
     SD_CHECK(st);
     CU_CHECK(c, cudaEventRecord(P->ev_a[k], sa));
     // ---- this ring position's depth stream: gradient edges, then the plane fitter (both depth only)
@@ -321,7 +332,10 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     CU_CHECK(c, cudaEventRecord(P->ev_join, s2));
     // ---- the handle's stream: part B, decision, state roll
     CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_a[k], 0));
-    SD_CHECK(flow_part_b(c, k));
+    c->stream = main_s;
+    st = flow_part_b(c, k);
+    c->stream = user_s;
+    SD_CHECK(st);
     CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_join, 0));
     if (P->ddout_pending) { CU_CHECK(c, cudaStreamWaitEvent(main_s, P->ev_ddout, 0)); P->ddout_pending = false; }
     if (!P->g_d[k])     // decision + state roll (DynaDetect.cc:1543-1636,1660-1664): ~25 launches and three copies as one graph
@@ -338,7 +352,12 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     if (flags) {
         CU_CHECK(c, cudaMemcpyAsync(flags->edge_scalars, c->edges.scalars, sizeof(int) * 4, cudaMemcpyDeviceToHost, main_s));
         flags->peac_hdr[0] = flags->peac_hdr[1] = flags->peac_hdr[2] = flags->peac_hdr[3] = 0;
-        if (c->cfg.plane_edges) SD_CHECK(peac_copy_sticky_overflow(c, &P->peac[k], &flags->peac_hdr[2]));
+        if (c->cfg.plane_edges) {
+            c->stream = main_s;
+            st = peac_copy_sticky_overflow(c, &P->peac[k], &flags->peac_hdr[2]);
+            c->stream = user_s;
+            SD_CHECK(st);
+        }
     }
     CU_CHECK(c, cudaEventRecord(P->ev_done[k], main_s));
     P->last_slot = slot; P->last_k = k;
