@@ -261,10 +261,12 @@ struct MergeResult { double st[9], c[3], n[3], mse; };
 #else
 #define PCLK(i) do { } while (0)
 #endif
-#define PEAC_AHC_NT 256   // threads of k_peac_ahc (a power of two: node b is owned by thread b & (PEAC_AHC_NT - 1))
-#define PEAC_BATCH 4      // queue heads processed per round (PEAC_AHC_NT / PEAC_BATCH threads evaluate the candidates of one of them)
+#define PEAC_AHC_NT 512   // threads of k_peac_ahc (a power of two: node b is owned by thread b & (PEAC_AHC_NT - 1))
+#define PEAC_BATCH 2      // queue heads processed per round (PEAC_AHC_NT / PEAC_BATCH threads evaluate the candidates of one of them)
 #define PEAC_CANDK 512    // distinct graph neighbours of one node
-#define PEAC_WTOP 3        // queue heads every warp contributes to the selection of a round (8 warps x 3 <= 32 lanes)
+#define PEAC_WTOP 2        // queue heads every warp contributes to the selection of a round (16 warps x 2 = 32 lanes)
+// (measured on the B200, bit-exact in every variant: 256 threads / batch 4 / 3 heads per warp 1.77 ms; 256 / 2 / 2 1.64; 128 / 2 / 2
+//  1.97; 512 / 4 / 2 1.63; 512 / 2 / 2 1.55 -- a round commits ~2 pops whatever the batch size)
 #define PEAC_AHC_CTAS 32  // CTAs of k_peac_ahc: one connected component of the block graph each (more components: round robin)
 
 // Edges exist only between blocks of one connected component of the initial graph and every later edge is inherited from
@@ -296,10 +298,11 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
     __shared__ unsigned short cand[PEAC_BATCH][PEAC_CANDK];
     __shared__ unsigned long long w4_key[PEAC_AHC_NT / 32][PEAC_BATCH];
     __shared__ int w4_p[PEAC_AHC_NT / 32][PEAC_BATCH], w4_seq[PEAC_AHC_NT / 32][PEAC_BATCH];
-    __shared__ double ws_mse[PEAC_BATCH][2], ws_c2[PEAC_BATCH][2], pl_M[PEAC_BATCH], pl_mp[PEAC_BATCH];
+    constexpr int WPS = PEAC_AHC_NT / PEAC_BATCH / 32;      // warps that evaluate the candidates of one batch node
+    __shared__ double ws_mse[PEAC_BATCH][WPS], ws_c2[PEAC_BATCH][WPS], pl_M[PEAC_BATCH], pl_mp[PEAC_BATCH];
     __shared__ int pl_ext[PEAC_BATCH], pl_clash[PEAC_BATCH];
     __shared__ int pl_O[PEAC_BATCH], pl_MG[PEAC_BATCH], pl_seq[PEAC_BATCH], pl_ex[PEAC_BATCH], pl_L, pl_nm, pl_ne, s_P[PEAC_BATCH];
-    __shared__ int ws_o[PEAC_BATCH][2];
+    __shared__ int ws_o[PEAC_BATCH][WPS];
     __shared__ unsigned short s_active[PEAC_MAXB / 8 + 1];
     __shared__ int s_ex[PEAC_MAXP];
     __shared__ double s_exkey[PEAC_MAXP];
@@ -609,9 +612,9 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                     }
                 }
             }
-            {   // best of the warp (a batch node's threads are two whole warps): three integer warp reductions on the order-preserving key
+            {   // best of the warp (a batch node's threads are WPS whole warps): three integer warp reductions on the order-preserving key
                 const int wl = warp_argmin(peac_key(best), best_o, best_o);      // ties in the MSE: the smaller node id
-                if (wl >= 0 ? lane == wl : lane == 0) { ws_mse[slot_j][wid & 1] = best; ws_o[slot_j][wid & 1] = wl >= 0 ? best_o : -1; ws_c2[slot_j][wid & 1] = bc2; }
+                if (wl >= 0 ? lane == wl : lane == 0) { ws_mse[slot_j][wid % WPS] = best; ws_o[slot_j][wid % WPS] = wl >= 0 ? best_o : -1; ws_c2[slot_j][wid % WPS] = bc2; }
             }
             __syncthreads();
             PCLK(5);   // candidate evaluation + warp reduction
@@ -626,9 +629,11 @@ __global__ void __launch_bounds__(PEAC_AHC_NT) k_peac_ahc(const PeacNode *__rest
                         km = ws_mse[lane][0];
                         double kc = ws_c2[lane][0];
                         ko = ws_o[lane][0];
-                        const double om = ws_mse[lane][1];
-                        const int oo = ws_o[lane][1];
-                        if (oo >= 0 && (ko < 0 || om < km || (om == km && oo < ko))) { km = om; ko = oo; kc = ws_c2[lane][1]; }
+                        for (int q = 1; q < WPS; ++q) {      // best of the slot's warps: smallest MSE, ties to the smaller node id
+                            const double om = ws_mse[lane][q];
+                            const int oo = ws_o[lane][q];
+                            if (oo >= 0 && (ko < 0 || om < km || (om == km && oo < ko))) { km = om; ko = oo; kc = ws_c2[lane][q]; }
+                        }
                         mg = ko >= 0 && km < peac_t_mse(false, kc);
                         const int pme = s_P[lane];
                         mp = mse_a[pme];
