@@ -273,6 +273,9 @@ int pipe_detect_run_src(sindyn_ctx *c, const uint8_t *bgr, size_t bgr_step, cons
     // its readers (the flow solves of frames i - 4 .. i - 2) are done once frame i - 2 is decided
     cudaStream_t sa = P->sa[p];
     CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_done[k], 0));                 // frame i - PIPE_NB has finished with buffers k
+    // the ring slot written below is frame i - 3's "last" image: its large-motion solve / refinement ran on the OTHER part-A
+    // stream, nothing else orders it before this frame's input copy
+    CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_a[(k + 1) % PIPE_NB], 0));
     if (P->gray_pending[slot]) CU_CHECK(c, cudaStreamWaitEvent(sa, P->ev_gray[slot], 0));   // ... and the extractor with this ring slot
     if (!host_src) {
         CU_CHECK(c, cudaMemcpyAsync(c->bgr[slot], bgr, (size_t)c->N * 3, cudaMemcpyDeviceToDevice, sa));
